@@ -1,0 +1,200 @@
+/* mmf_b200.h — C ABI of the B200-native attention-MIL / fusion / survival-head hot path.
+ *
+ * The reference (MultimodalFusion/multimodalfusion) is pure PyTorch: it has no FFI of its own,
+ * its boundary is the nn.Module surface.  Each entry point below therefore replaces a *stock
+ * ATen op sequence* of the reference; the citation on every function names that sequence
+ * (paths relative to the reference tree).  INTEGRATION.md shows the ctypes binding and the
+ * torch.autograd.Function a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter name ends in `_host`;
+ *   - the caller owns all buffers (including workspaces); the library never allocates device
+ *     memory, keeps no global state and is re-entrant;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no host synchronisation;
+ *   - return value: MMF_OK (0) or a negative MMF_E_* code; values <= -1000 are -(1000+cudaError_t);
+ *   - bf16 arrays are row-major, 16-byte aligned, leading dimension a multiple of 8 elements;
+ *   - requires an sm_100a device (B200): tcgen05/TMEM/TMA kernels, no fallback path.
+ */
+#ifndef MMF_B200_H_
+#define MMF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMF_ABI_VERSION 1
+
+enum {
+  MMF_OK = 0,
+  MMF_E_INVALID = -1,     /* bad argument (null pointer, size, unsupported L/D) */
+  MMF_E_ALIGN = -2,       /* pointer / leading dimension alignment */
+  MMF_E_DRIVER = -3,      /* cuTensorMapEncodeTiled entry point unavailable */
+  MMF_E_TMAP = -4,        /* tensor-map encode failed */
+  MMF_E_UNSUPPORTED = -5, /* feature size not compiled in */
+  MMF_E_WORKSPACE = -6    /* workspace too small */
+};
+
+/* flags for the attention-MIL kernels */
+enum {
+  MMF_GATED = 1,        /* Attn_Net_Gated (tanh ⊙ sigmoid) vs Attn_Net (tanh only) */
+  MMF_DROPOUT_H = 2,    /* train mode: Dropout(0.25) on h = relu(fc(x)) (always on in the reference) */
+  MMF_DROPOUT_ATTN = 4, /* train mode with dropout=True: Dropout(0.25) on the tanh / sigmoid outputs */
+  MMF_NEED_DX = 8       /* backward also produces dx (radio path: reduce_dim sits upstream) */
+};
+
+#define MMF_IN_FEATURES 1024 /* ResNet50-layer3 feature width, fixed by the reference models */
+#define MMF_TILE_ROWS 128    /* instances per CTA tile; one (m, l, acc[L]) partial per tile */
+
+int mmf_version(void);
+const char* mmf_error_string(int rc);
+
+/* Weights of fc(1024->L) + attention net, prepared once per optimizer step by the caller.
+ * Reference: models/model_attention_mil_path.py:19-29 (fc_WSI, Attn_Net_Gated / Attn_Net),
+ * models/model_modules.py:70-110. */
+typedef struct MmfAmilWeights {
+  const void* W1;        /* bf16 [L,1024]           attention_net_*.0.weight                      */
+  const float* b1;       /* f32  [L]                attention_net_*.0.bias                        */
+  const void* Wab;       /* bf16 [2D,L] (gated: attention_a.0.weight stacked on attention_b.0.weight)
+                                 [D,L]  (un-gated: module.0.weight)                               */
+  const void* Wab_packed;/* bf16, same rows regrouped per 128-wide D chunk c:
+                            gated: rows [c*256, c*256+128) = Wa[c*128..], next 128 = Wb[c*128..];
+                            un-gated: identical to Wab. See mmf_pack_wab().                        */
+  const float* bab;      /* f32  [2D] = ba ++ bb   (un-gated: [D])                                */
+  const float* wc;       /* f32  [D]               attention_c.weight / module.{2|3}.weight       */
+  const float* bc;       /* f32  [1]               attention_c.bias (device scalar)                */
+} MmfAmilWeights;
+
+typedef struct MmfAmilGrads {
+  float* dW1;  /* f32 [L,1024] */
+  float* db1;  /* f32 [L]      */
+  float* dWab; /* f32 [2D,L] (un-gated [D,L]), natural row order */
+  float* dbab; /* f32 [2D] / [D] */
+  float* dwc;  /* f32 [D] */
+  float* dbc;  /* f32 [1] */
+} MmfAmilGrads;
+
+/* fp32 -> bf16 feature / weight conversion (round-to-nearest-even), n elements. */
+int mmf_cast_f32_to_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
+
+/* Regroups Wab[2D,L] into the per-chunk layout the fused kernel streams with one TMA box. */
+int mmf_pack_wab(const void* Wab_bf16, void* Wab_packed_bf16, int L, int D, int gated, void* stream);
+
+/* Number of 128-row tiles (= number of softmax partials) for a bag of N instances. */
+int64_t mmf_amil_num_tiles(int64_t N);
+
+/* Fused attention-MIL forward for one bag (or one rank's shard of a bag).
+ *   h = relu(x W1^T + b1) [dropout];  s = wc·(tanh(Wa h + ba) ⊙ sigmoid(Wb h + bb)) + bc
+ *   per 128-row tile t: (m_t, l_t, acc_t[L]) = (max s, Σ e^{s-m_t}, Σ e^{s-m_t} h)
+ * Replaces: nn.Linear+ReLU+Dropout (models/model_attention_mil_path.py:20-21,29),
+ *           Attn_Net_Gated.forward / Attn_Net.forward (models/model_modules.py:84-85,105-110),
+ *           transpose+softmax+mm (models/model_attention_mil_path.py:53-56) up to the combine.
+ *   x        bf16 [N, ldx>=1024]
+ *   A_raw    f32 [N]            raw (pre-softmax) attention scores
+ *   partials f32 [num_tiles, L+2]  row t = (m_t, l_t, acc_t[0..L))
+ *   H_stash  bf16 [N, L] or NULL: when non-NULL the h tile is also written out (consumed by
+ *            mmf_amil_bwd with h_stash != NULL, which then skips the fc recompute). */
+int mmf_amil_fwd(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, int L, int D,
+                 int flags, uint64_t seed, float* A_raw, float* partials, void* H_stash,
+                 void* stream);
+
+/* Combines n softmax partials (rows of L+2 floats) into one.
+ *   normalize != 0: M[L] = Σ acc_t e^{m_t-m} / l,  ml[2] = (m, l)           (final result)
+ *   normalize == 0: out[L+2] = (m, l, Σ acc_t e^{m_t-m})                   (rank-local partial,
+ *                   all-gathered across ranks and combined again with normalize = 1)
+ * Replaces the tail of F.softmax + torch.mm (models/model_attention_mil_path.py:55-56). */
+int mmf_amil_combine(const float* partials, int64_t n, int L, int normalize, float* out_M_or_partial,
+                     float* ml, void* stream);
+
+size_t mmf_amil_bwd_workspace_bytes(int64_t N, int L, int D, int flags);
+
+/* Backward of mmf_amil_fwd + combine, given dM = dLoss/dM [L] and optionally dA_raw [N].
+ * Recomputes h and the attention activations tile by tile (nothing but A_raw, (m,l), M is kept
+ * from the forward). Accumulates INTO g (caller zeroes or carries gradient accumulation).
+ *   M, ml are the GLOBAL (all-rank) pooled vector and (max, sum) — a rank that owns a shard of the
+ *   bag passes the combined values and obtains its shard's contribution to the weight grads.
+ *   dx bf16 [N,1024] is written only with MMF_NEED_DX.
+ * Replaces autograd through the same reference ops (utils/core_utils.py:242-247 loss.backward()). */
+int mmf_amil_bwd(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, int L, int D,
+                 int flags, uint64_t seed, const float* A_raw, const float* ml, const float* M,
+                 const float* dM, const float* dA_raw, const void* H_stash, const MmfAmilGrads* g,
+                 void* dx, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Dense bf16 tensor-core GEMM used either side of the AMIL core (radio reduce_dim and its
+ * gradients): C[M,N] = A[M,K] B[N,K]^T + bias (A given as up to 4 K-segments = the modality
+ * bags that the reference concatenates, models/model_attention_mil_radio.py:81-82).
+ *   out_bf16 / out_f32: exactly one non-NULL. */
+int mmf_linear_bf16(const void* const* A_segs, int n_segs, int64_t M, int K_per_seg, int64_t lda,
+                    const void* W /*bf16 [N,K]*/, const float* bias /*[N] or NULL*/, int N,
+                    void* out_bf16, float* out_f32, int64_t ldc, void* stream);
+
+/* dW[N,K] += dY[M,N]^T X[M,K] (X as up to 4 K-segments), db[N] += colsum(dY). dY bf16 [M,N]. */
+int mmf_linear_bf16_wgrad(const void* dY, int64_t M, int N, int64_t lddy, const void* const* X_segs,
+                          int n_segs, int K_per_seg, int64_t ldx, float* dW /*[N, n_segs*K_per_seg]*/,
+                          float* db /*[N] or NULL*/, void* workspace, size_t workspace_bytes,
+                          void* stream);
+size_t mmf_linear_bf16_wgrad_workspace_bytes(int64_t M, int N);
+
+/* ---- small fp32 kernels: heads, SNN, Kronecker fusion, survival losses -------------------- */
+
+/* activation codes for mmf_dense_* */
+enum { MMF_ACT_NONE = 0, MMF_ACT_RELU = 1, MMF_ACT_SELU = 2, MMF_ACT_SIGMOID = 3, MMF_ACT_TANH = 4 };
+
+/* y[B,out] = act(x[B,in] W[out,in]^T + b) * mask   (mask f32 [B,out] or NULL; carries the
+ * inverted-dropout / alpha-dropout scaling when training).
+ * Replaces nn.Linear + activation (+Dropout/AlphaDropout) blocks: SNN_Block
+ * (models/model_modules.py:64-68), classifier heads, XlinearFusion.reduce/encoder layers. */
+int mmf_dense_fwd(const float* x, int64_t ldx, const float* W, const float* b, int B, int in_dim,
+                  int out_dim, int act, float* y, int64_t ldy, void* stream);
+/* Given y (post-activation) and dy: dpre = dy * act'(y); dx[B,in] (=|+=) dpre W; dW += dpre^T x;
+ * db += colsum(dpre).  dx may be NULL. accumulate_dx != 0 adds into dx. */
+int mmf_dense_bwd(const float* x, int64_t ldx, const float* W, int B, int in_dim, int out_dim,
+                  int act, const float* y, int64_t ldy, const float* dy, int64_t lddy, float* dx,
+                  int64_t lddx, int accumulate_dx, float* dW, float* db, void* stream);
+
+/* Kronecker ("Xlinear") fusion encoder1: out[B,H] = relu(W1 · (o_1 ⊗ o_2 [⊗ o_3]) + b1) with
+ * o_i[B,E] (E = dim+1, last column = 1) never materialising the E^m-wide outer product.
+ * Replaces torch.bmm outer products + encoder1 Linear+ReLU (models/model_modules.py:167-173). */
+int mmf_kron_enc_fwd(const float* const* o /*HOST array of m device ptrs [B,E]*/, int m, int E, int B,
+                     const float* W /*[H,E^m]*/, const float* b, int H, float* out /*[B,H]*/,
+                     void* stream);
+/* workspace: B * E^m floats (the gradient w.r.t. the outer product, contracted immediately). */
+size_t mmf_kron_enc_workspace_bytes(int m, int E, int B);
+int mmf_kron_enc_bwd(const float* const* o, int m, int E, int B, const float* W, int H,
+                     const float* out, const float* dout, float* const* d_o /*m ptrs [B,E]*/,
+                     float* dW, float* db, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Discrete-hazard head: logits = M Wk^T + bk; hazards = sigmoid(logits); S = cumprod(1-hazards);
+ * Y_hat = argmax logits.  Replaces models/model_attention_mil_path.py:58-61. */
+int mmf_hazard_head_fwd(const float* M, int B, int Lin, const float* Wk, const float* bk, int K,
+                        float* hazards, float* S, int64_t* Y_hat, void* stream);
+int mmf_hazard_head_bwd(const float* M, int B, int Lin, const float* Wk, int K, const float* hazards,
+                        const float* S, const float* d_hazards, const float* d_S, float* dM,
+                        float* dWk, float* dbk, void* stream);
+
+/* nll_loss (utils/loss_utils.py:22-39): loss scalar + d_hazards, d_S [B,K]. Y int64 [B], c f32 [B]. */
+int mmf_nll_surv_fwd_bwd(const float* hazards, const float* S, const int64_t* Y, const float* c,
+                         int B, int K, float alpha, float eps, float* loss, float* d_hazards,
+                         float* d_S, void* stream);
+
+/* CoxSurvLoss (utils/loss_utils.py:124-139): loss = -mean_i (theta_i - log Σ_{t_j>=t_i} e^{theta_j})(1-c_i).
+ * O(B log B) sort + tie-aware suffix sums instead of the reference's O(B^2) host loop.
+ * workspace: mmf_cox_workspace_bytes(B). dtheta may be NULL. */
+size_t mmf_cox_workspace_bytes(int B);
+int mmf_cox_fwd_bwd(const float* theta, const float* times, const float* c, int B, float* loss,
+                    float* dtheta, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ranking_loss (utils/loss_utils.py:58-101): over comparable pairs (t_a < t_b and event_a),
+ * loss = -mean|sum phi(r_a - r_b); phi: 0 = sigmoid, 1 = relu; reduction: 0 = mean, 1 = sum.
+ * n_pairs (device int64) receives the pair count (0 -> loss 0, zero gradient). */
+size_t mmf_ranking_workspace_bytes(int B);
+int mmf_ranking_fwd_bwd(const float* risks, const float* times, const float* c, int B, int phi,
+                        int reduction, float* loss, float* drisks, int64_t* n_pairs, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMF_B200_H_ */

@@ -1,0 +1,148 @@
+"""ctypes binding of the C-ABI library (include/mmf_b200.h).
+
+The shared object is built in-tree (``multimodalfusion_b200/libmmf_b200.so``) by
+:func:`build` (``nvcc -gencode arch=compute_100a,code=sm_100a``).  There is no CPU or PyTorch
+fallback: if the library is missing, or a kernel is asked to run without a CUDA device, the
+call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+import threading
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_PKG_DIR, "csrc")
+LIB_PATH = os.path.join(_PKG_DIR, "libmmf_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_PKG_DIR), "include", "mmf_b200.h")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "-shared", "-Xcompiler", "-fPIC",
+]
+
+# error codes / flags mirrored from the header
+MMF_OK = 0
+MMF_GATED, MMF_DROPOUT_H, MMF_DROPOUT_ATTN, MMF_NEED_DX = 1, 2, 4, 8
+ACT_NONE, ACT_RELU, ACT_SELU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3, 4
+
+
+class MmfError(RuntimeError):
+    pass
+
+
+def _sources():
+    return sorted(
+        os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cu", ".cuh"))
+    ) + [HEADER_PATH]
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(s) > t for s in _sources())
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/capi.cu for sm_100a into the in-tree shared object."""
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise MmfError("nvcc not found: cannot build libmmf_b200.so")
+    tmp = LIB_PATH + ".tmp"
+    cmd = [nvcc, *NVCC_FLAGS, "-o", tmp, os.path.join(_CSRC, "capi.cu")]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise MmfError("nvcc failed:\n" + r.stdout + r.stderr)
+    os.replace(tmp, LIB_PATH)
+    if verbose:
+        print(r.stderr)
+    return LIB_PATH
+
+
+class AmilWeights(C.Structure):
+    _fields_ = [
+        ("W1", C.c_void_p), ("b1", C.c_void_p), ("Wab", C.c_void_p), ("Wab_packed", C.c_void_p),
+        ("bab", C.c_void_p), ("wc", C.c_void_p), ("bc", C.c_void_p),
+    ]
+
+
+class AmilGrads(C.Structure):
+    _fields_ = [
+        ("dW1", C.c_void_p), ("db1", C.c_void_p), ("dWab", C.c_void_p), ("dbab", C.c_void_p),
+        ("dwc", C.c_void_p), ("dbc", C.c_void_p),
+    ]
+
+
+_vp, _i, _i64, _sz, _f, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_float, C.c_uint64
+_PP = C.POINTER(C.c_void_p)
+
+# name -> (restype, argtypes); the single source of truth the symbol test checks against the header
+SIGNATURES = {
+    "mmf_version": (_i, []),
+    "mmf_error_string": (C.c_char_p, [_i]),
+    "mmf_cast_f32_to_bf16": (_i, [_vp, _vp, _i64, _vp]),
+    "mmf_pack_wab": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "mmf_amil_num_tiles": (_i64, [_i64]),
+    "mmf_amil_fwd": (_i, [_vp, _i64, _i64, C.POINTER(AmilWeights), _i, _i, _i, _u64, _vp, _vp, _vp, _vp]),
+    "mmf_amil_combine": (_i, [_vp, _i64, _i, _i, _vp, _vp, _vp]),
+    "mmf_amil_bwd_workspace_bytes": (_sz, [_i64, _i, _i, _i]),
+    "mmf_amil_bwd": (_i, [_vp, _i64, _i64, C.POINTER(AmilWeights), _i, _i, _i, _u64, _vp, _vp, _vp, _vp,
+                          _vp, _vp, C.POINTER(AmilGrads), _vp, _vp, _sz, _vp]),
+    "mmf_linear_bf16": (_i, [_PP, _i, _i64, _i, _i64, _vp, _vp, _i, _vp, _vp, _i64, _vp]),
+    "mmf_linear_bf16_wgrad_workspace_bytes": (_sz, [_i64, _i]),
+    "mmf_linear_bf16_wgrad": (_i, [_vp, _i64, _i, _i64, _PP, _i, _i, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "mmf_dense_fwd": (_i, [_vp, _i64, _vp, _vp, _i, _i, _i, _i, _vp, _i64, _vp]),
+    "mmf_dense_bwd": (_i, [_vp, _i64, _vp, _i, _i, _i, _i, _vp, _i64, _vp, _i64, _vp, _i64, _i, _vp, _vp, _vp]),
+    "mmf_kron_enc_fwd": (_i, [_PP, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
+    "mmf_kron_enc_workspace_bytes": (_sz, [_i, _i, _i]),
+    "mmf_kron_enc_bwd": (_i, [_PP, _i, _i, _i, _vp, _i, _vp, _vp, _PP, _vp, _vp, _vp, _sz, _vp]),
+    "mmf_hazard_head_fwd": (_i, [_vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "mmf_hazard_head_bwd": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mmf_nll_surv_fwd_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _f, _vp, _vp, _vp, _vp]),
+    "mmf_cox_workspace_bytes": (_sz, [_i]),
+    "mmf_cox_fwd_bwd": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
+    "mmf_ranking_workspace_bytes": (_sz, [_i]),
+    "mmf_ranking_fwd_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def lib() -> C.CDLL:
+    """The loaded library. Raises (never falls back) if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise MmfError(
+                    f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                    "(there is no CPU fallback for the CUDA path)")
+            handle = C.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(handle, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != MMF_OK:
+        msg = lib().mmf_error_string(rc).decode()
+        raise MmfError(f"{what or 'mmf call'} failed: {msg} (rc={rc})")
+
+
+def ptr_array(ptrs):
+    arr = (C.c_void_p * len(ptrs))(*ptrs)
+    return arr

@@ -1,0 +1,186 @@
+"""torch.autograd.Functions over the C-ABI kernels (the `wrapped as torch.autograd.Functions over a
+thin C-ABI extension` layer of the north star).  Forward and backward both run in
+``libmmf_b200.so``; autograd only routes gradients between them.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from ._lib import MMF_NEED_DX
+
+
+class AmilPool(torch.autograd.Function):
+    """x[N,1024] -> (A_raw[1,N], M[1,L]): fc+ReLU(+dropout) -> (gated) attention scores -> softmax
+    pooling, fused (reference: models/model_attention_mil_path.py:52-56).
+
+    With ``group`` set, x is this rank's shard of the bag: the per-rank (m, l, acc) partial is
+    all-gathered (L+2 floats per rank) and combined on every rank, so M is replicated; the backward
+    then yields this rank's contribution to the weight gradients (sum over ranks = full gradient).
+    """
+
+    @staticmethod
+    def forward(ctx, x, W1, b1, Wa, ba, Wb, bb, wc, bc, prep, flags: int, seed: int, group=None):
+        ctx.set_materialize_grads(False)
+        xb = ops.to_bf16(x)
+        if x.requires_grad:
+            flags |= MMF_NEED_DX
+        A_raw, partials = ops.amil_partials(xb, prep, flags, seed)
+        if group is None:
+            M, ml = ops.amil_combine(partials, prep.L, True)
+        else:
+            local = ops.amil_combine(partials, prep.L, False)
+            world = dist.get_world_size(group)
+            gathered = torch.empty(world, prep.L + 2, dtype=torch.float32, device=xb.device)
+            dist.all_gather_into_tensor(gathered, local.reshape(1, -1), group=group)
+            M, ml = ops.amil_combine(gathered, prep.L, True)
+        ctx.save_for_backward(xb, A_raw, M, ml)
+        ctx.prep, ctx.flags, ctx.seed = prep, flags, seed
+        ctx.x_dtype = x.dtype
+        ctx.gated = Wb is not None
+        return A_raw.view(1, -1), M.view(1, -1)
+
+    @staticmethod
+    def backward(ctx, dA, dM):
+        xb, A_raw, M, ml = ctx.saved_tensors
+        prep = ctx.prep
+        if dM is None:
+            dM = torch.zeros(prep.L, dtype=torch.float32, device=xb.device)
+        g = ops.amil_backward(xb, prep, ctx.flags, ctx.seed, A_raw, ml, M, dM, dA)
+        D = prep.D
+        dx = g["dx"].to(ctx.x_dtype) if (ctx.flags & MMF_NEED_DX) else None
+        if ctx.gated:
+            dWa, dWb, dba, dbb = g["dWab"][:D], g["dWab"][D:], g["dbab"][:D], g["dbab"][D:]
+        else:
+            dWa, dWb, dba, dbb = g["dWab"], None, g["dbab"], None
+        return (dx, g["dW1"], g["db1"], dWa, dba, dWb, dbb, g["dwc"].view(1, D), g["dbc"],
+                None, None, None, None)
+
+
+class HazardHead(torch.autograd.Function):
+    """M[B,L] -> (hazards, S, Y_hat)  (models/model_attention_mil_path.py:58-61)."""
+
+    @staticmethod
+    def forward(ctx, M, Wk, bk):
+        ctx.set_materialize_grads(False)
+        haz, S, Y = ops.hazard_head_fwd(M, Wk, bk)
+        ctx.save_for_backward(M, Wk, haz, S)
+        ctx.mark_non_differentiable(Y)
+        return haz, S, Y
+
+    @staticmethod
+    def backward(ctx, d_haz, d_S, _dY):
+        M, Wk, haz, S = ctx.saved_tensors
+        if d_haz is None and d_S is None:
+            return None, None, None
+        dM, dWk, dbk = ops.hazard_head_bwd(M, Wk, haz, S, d_haz, d_S)
+        return dM, dWk, dbk
+
+
+class Dense(torch.autograd.Function):
+    """y = act(x W^T + b), fp32 (SNN blocks, classifier heads, Xlinear reduce / encoder layers)."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, act: int):
+        y = ops.dense_fwd(x, W, b, act)
+        ctx.save_for_backward(x, W, y)
+        ctx.act = act
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W, y = ctx.saved_tensors
+        dx, dW, db = ops.dense_bwd(x, W, ctx.act, y, dy, need_dx=ctx.needs_input_grad[0],
+                                   need_dw=ctx.needs_input_grad[1],
+                                   need_db=ctx.has_bias and ctx.needs_input_grad[2])
+        return dx, dW, db, None
+
+
+class KronEncoder(torch.autograd.Function):
+    """relu(W (o_1 ⊗ o_2 [⊗ o_3]) + b) without materialising the outer product in the forward
+    (models/model_modules.py:167-173)."""
+
+    @staticmethod
+    def forward(ctx, W, b, *o_list):
+        out = ops.kron_enc_fwd(o_list, W, b)
+        ctx.save_for_backward(W, out, *o_list)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        W, out, *o_list = ctx.saved_tensors
+        d_o, dW, db = ops.kron_enc_bwd(o_list, W, out, dout)
+        return (dW, db, *d_o)
+
+
+class SegmentedLinearBf16(torch.autograd.Function):
+    """y = cat(segs, 1) @ W^T + b on the bf16 tensor-core GEMM, the modality bags are read in place
+    (radio reduce_dim: models/model_attention_mil_radio.py:81-82). Output bf16 feeds AmilPool."""
+
+    @staticmethod
+    def forward(ctx, W, b, *segs):
+        segs_b = [ops.to_bf16(s) for s in segs]
+        Wb = ops.to_bf16(W)
+        y = ops.linear_bf16(segs_b, Wb, b.detach().float().contiguous(), torch.bfloat16)
+        ctx.save_for_backward(*segs_b)
+        ctx.w_shape = W.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        segs_b = ctx.saved_tensors
+        dW = torch.zeros(ctx.w_shape, dtype=torch.float32, device=dy.device)
+        db = torch.zeros(ctx.w_shape[0], dtype=torch.float32, device=dy.device)
+        ops.linear_bf16_wgrad(ops.to_bf16(dy), segs_b, dW, db)
+        return (dW, db, *([None] * len(segs_b)))
+
+
+class NllSurv(torch.autograd.Function):
+    """utils/loss_utils.py:22-39; loss and both input gradients come from one kernel."""
+
+    @staticmethod
+    def forward(ctx, hazards, S, Y, c, alpha: float, eps: float):
+        loss, dh, dS = ops.nll_surv(hazards, S, Y, c, alpha, eps)
+        ctx.save_for_backward(dh, dS)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dl):
+        dh, dS = ctx.saved_tensors
+        return dh * dl, dS * dl, None, None, None, None
+
+
+class CoxLoss(torch.autograd.Function):
+    """utils/loss_utils.py:124-139 (sort + scan instead of the O(B^2) host loop)."""
+
+    @staticmethod
+    def forward(ctx, theta, times, c):
+        loss, dtheta = ops.cox(theta, times, c)
+        ctx.save_for_backward(dtheta)
+        ctx.shape = theta.shape
+        return loss
+
+    @staticmethod
+    def backward(ctx, dl):
+        (dtheta,) = ctx.saved_tensors
+        return (dtheta * dl).view(ctx.shape), None, None
+
+
+class RankingLoss(torch.autograd.Function):
+    """utils/loss_utils.py:58-101."""
+
+    @staticmethod
+    def forward(ctx, risks, times, c, phi: str, reduction: str):
+        loss, dr, _ = ops.ranking(risks, times, c, phi, reduction)
+        ctx.save_for_backward(dr)
+        ctx.shape = risks.shape
+        return loss
+
+    @staticmethod
+    def backward(ctx, dl):
+        (dr,) = ctx.saved_tensors
+        return (dr * dl).view(ctx.shape), None, None, None, None

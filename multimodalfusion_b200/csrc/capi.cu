@@ -1,0 +1,439 @@
+// capi.cu — the extern "C" surface declared in include/mmf_b200.h. Host-side orchestration only:
+// argument checks, TMA descriptor construction, workspace carving, kernel launches on the
+// caller's stream. No allocation, no synchronisation, no global state.
+#include <cuda_bf16.h>
+
+#include "../../include/mmf_b200.h"
+#include "amil_tile.cuh"
+#include "gemm_tc.cuh"
+#include "mmf_host.cuh"
+#include "small_kernels.cuh"
+
+using namespace mmf;
+
+namespace {
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct BwdWs {
+  size_t off_H, off_dG, off_dU, off_cs, off_dbc, off_db1, total;
+};
+BwdWs bwd_layout(int64_t N, int L, int D, int gated) {
+  const int64_t tiles = (N + 127) / 128;
+  const int KD = gated ? 2 * D : D;
+  const int ncols = gated ? 3 * D : 2 * D;
+  BwdWs w;
+  size_t o = 0;
+  w.off_H = o;   o = align_up(o + (size_t)N * L * 2, 1024);
+  w.off_dG = o;  o = align_up(o + (size_t)N * KD * 2, 1024);
+  w.off_dU = o;  o = align_up(o + (size_t)N * L * 2, 1024);
+  w.off_cs = o;  o = align_up(o + (size_t)tiles * 4 * ncols * 4, 1024);
+  w.off_dbc = o; o = align_up(o + (size_t)tiles * 4 * 4, 1024);
+  w.off_db1 = o; o = align_up(o + (size_t)tiles * 4 * L * 4, 1024);
+  w.total = o;
+  return w;
+}
+
+template <int A_MN, int B_MN, int EPI>
+int launch_gemm(const TMapSet& tmA, const TMapSet& tmB, const GemmArgs& g, int splits, cudaStream_t st) {
+  static bool configured = false;
+  auto kern = gemm_tc_kernel<A_MN, B_MN, EPI>;
+  if (!configured) {
+    MMF_TRY(cuda_rc(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES)));
+    configured = true;
+  }
+  dim3 grid((g.M + GEMM_BM - 1) / GEMM_BM, (g.N + GEMM_BN - 1) / GEMM_BN, splits);
+  kern<<<grid, 256, GEMM_SMEM_BYTES, st>>>(tmA, tmB, g);
+  return launch_status();
+}
+
+// split-K factor so that the grid roughly fills 148 SMs once or twice
+int pick_splits(int out_tiles, int kb_total, int* kb_per_split) {
+  int splits = (148 + out_tiles - 1) / out_tiles;
+  if (splits < 1) splits = 1;
+  if (splits > kb_total) splits = kb_total;
+  int per = (kb_total + splits - 1) / splits;
+  splits = (kb_total + per - 1) / per;  // no empty slices
+  *kb_per_split = per;
+  return splits;
+}
+
+template <int L, int D, bool GATED, int MODE>
+int launch_amil(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, const AmilArgs& a,
+                void* Hbuf, cudaStream_t st) {
+  using C = AmilCfg<L, D, GATED>;
+  static bool configured = false;
+  auto kern = amil_tile_kernel<L, D, GATED, MODE>;
+  if (!configured) {
+    MMF_TRY(cuda_rc(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES)));
+    configured = true;
+  }
+  CUtensorMap tmX, tmW1, tmWab, tmH;
+  MMF_TRY(make_tmap_bf16(&tmX, x, (uint64_t)N, 1024, (uint64_t)ldx, 128));
+  MMF_TRY(make_tmap_bf16(&tmW1, w->W1, L, 1024, 1024, 256));
+  MMF_TRY(make_tmap_bf16(&tmWab, w->Wab_packed, (uint64_t)C::NCH * C::CHN, L, L, C::CHN));
+  if (Hbuf) MMF_TRY(make_tmap_bf16(&tmH, Hbuf, (uint64_t)N, L, L, 128));
+  else tmH = tmX;
+  const int tiles = (int)((N + 127) / 128);
+  kern<<<tiles, 256, C::SMEM_BYTES, st>>>(tmX, tmW1, tmWab, tmH, a);
+  return launch_status();
+}
+
+template <int MODE>
+int dispatch_amil(int L, int D, int gated, const void* x, int64_t N, int64_t ldx,
+                  const MmfAmilWeights* w, const AmilArgs& a, void* Hbuf, cudaStream_t st) {
+#define MMF_CASE(LL, DD)                                                                  \
+  if (L == LL && D == DD)                                                                 \
+    return gated ? launch_amil<LL, DD, true, MODE>(x, N, ldx, w, a, Hbuf, st)             \
+                 : launch_amil<LL, DD, false, MODE>(x, N, ldx, w, a, Hbuf, st);
+  MMF_CASE(256, 256)
+  MMF_CASE(512, 384)
+  MMF_CASE(256, 384)
+#undef MMF_CASE
+  return MMF_E_UNSUPPORTED;
+}
+
+int check_amil_common(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, int L, int D) {
+  if (!x || !w || N <= 0 || ldx < 1024) return MMF_E_INVALID;
+  if (!w->W1 || !w->b1 || !w->Wab || !w->Wab_packed || !w->bab || !w->wc || !w->bc) return MMF_E_INVALID;
+  if (!((L == 256 && D == 256) || (L == 512 && D == 384) || (L == 256 && D == 384))) return MMF_E_UNSUPPORTED;
+  if (N > 0x7fffff00LL) return MMF_E_INVALID;
+  return MMF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mmf_version(void) { return MMF_ABI_VERSION; }
+
+const char* mmf_error_string(int rc) {
+  switch (rc) {
+    case MMF_OK: return "ok";
+    case MMF_E_INVALID: return "invalid argument";
+    case MMF_E_ALIGN: return "pointer or leading dimension not 16-byte aligned";
+    case MMF_E_DRIVER: return "cuTensorMapEncodeTiled driver entry point unavailable";
+    case MMF_E_TMAP: return "tensor map encode failed";
+    case MMF_E_UNSUPPORTED: return "unsupported configuration";
+    case MMF_E_WORKSPACE: return "workspace too small";
+    default:
+      if (rc <= -1000) return cudaGetErrorString((cudaError_t)(-rc - 1000));
+      return "unknown error";
+  }
+}
+
+int mmf_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  if (!src || !dst || n < 0) return MMF_E_INVALID;
+  if (n == 0) return MMF_OK;
+  if ((reinterpret_cast<uintptr_t>(src) & 15u) || (reinterpret_cast<uintptr_t>(dst) & 7u)) return MMF_E_ALIGN;
+  const long long n4 = n / 4;
+  const int tail = (int)(n - n4 * 4);
+  long long blocks = (n4 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  cast_f32_bf16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(src), reinterpret_cast<uint2*>(dst), n4, src + n4 * 4,
+      reinterpret_cast<__nv_bfloat16*>(dst) + n4 * 4, tail);
+  return launch_status();
+}
+
+int mmf_pack_wab(const void* Wab, void* packed, int L, int D, int gated, void* stream) {
+  if (!Wab || !packed || L % 8 || D % 128) return MMF_E_INVALID;
+  pack_wab_kernel<<<148, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(Wab),
+                                                         reinterpret_cast<uint4*>(packed), L, D, gated);
+  return launch_status();
+}
+
+int64_t mmf_amil_num_tiles(int64_t N) { return (N + MMF_TILE_ROWS - 1) / MMF_TILE_ROWS; }
+
+int mmf_amil_fwd(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, int L, int D,
+                 int flags, uint64_t seed, float* A_raw, float* partials, void* H_stash, void* stream) {
+  MMF_TRY(check_amil_common(x, N, ldx, w, L, D));
+  if (!A_raw || !partials) return MMF_E_INVALID;
+  AmilArgs a = {};
+  a.N = N; a.b1 = w->b1; a.bab = w->bab; a.wc = w->wc; a.bc = w->bc;
+  a.A_raw = A_raw; a.partials = partials; a.store_h = H_stash != nullptr;
+  a.flags = flags; a.seed = seed;
+  return dispatch_amil<AMIL_FWD>(L, D, flags & MMF_GATED, x, N, ldx, w, a, H_stash, (cudaStream_t)stream);
+}
+
+int mmf_amil_combine(const float* partials, int64_t n, int L, int normalize, float* out, float* ml,
+                     void* stream) {
+  if (!partials || !out || n <= 0 || L <= 0 || (normalize && !ml)) return MMF_E_INVALID;
+  amil_combine_kernel<<<(L + 31) / 32, dim3(32, 8), 0, (cudaStream_t)stream>>>(partials, n, L, normalize, out, ml);
+  return launch_status();
+}
+
+size_t mmf_amil_bwd_workspace_bytes(int64_t N, int L, int D, int flags) {
+  if (N <= 0) return 0;
+  return bwd_layout(N, L, D, flags & MMF_GATED).total;
+}
+
+int mmf_amil_bwd(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, int L, int D,
+                 int flags, uint64_t seed, const float* A_raw, const float* ml, const float* M,
+                 const float* dM, const float* dA_raw, const void* H_stash, const MmfAmilGrads* g,
+                 void* dx, void* workspace, size_t workspace_bytes, void* stream) {
+  (void)H_stash;  // TODO(round 2): skip the fc recompute when the forward stashed H
+  MMF_TRY(check_amil_common(x, N, ldx, w, L, D));
+  if (!A_raw || !ml || !M || !dM || !g || !workspace) return MMF_E_INVALID;
+  if (!g->dW1 || !g->db1 || !g->dWab || !g->dbab || !g->dwc || !g->dbc) return MMF_E_INVALID;
+  if ((flags & MMF_NEED_DX) && !dx) return MMF_E_INVALID;
+  const int gated = flags & MMF_GATED;
+  const BwdWs lay = bwd_layout(N, L, D, gated);
+  if (workspace_bytes < lay.total) return MMF_E_WORKSPACE;
+  if (reinterpret_cast<uintptr_t>(workspace) & 1023u) return MMF_E_ALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  __nv_bfloat16* Hb = reinterpret_cast<__nv_bfloat16*>(ws + lay.off_H);
+  __nv_bfloat16* dG = reinterpret_cast<__nv_bfloat16*>(ws + lay.off_dG);
+  __nv_bfloat16* dU = reinterpret_cast<__nv_bfloat16*>(ws + lay.off_dU);
+  float* cs = reinterpret_cast<float*>(ws + lay.off_cs);
+  float* dbc_ws = reinterpret_cast<float*>(ws + lay.off_dbc);
+  float* db1_ws = reinterpret_cast<float*>(ws + lay.off_db1);
+  const int KD = gated ? 2 * D : D;
+  const int ncols = gated ? 3 * D : 2 * D;
+  const int64_t tiles = (N + 127) / 128;
+
+  // 1. row-stationary pass: recompute H and the attention branches, emit dG, H, column sums
+  AmilArgs a = {};
+  a.N = N; a.b1 = w->b1; a.bab = w->bab; a.wc = w->wc; a.bc = w->bc;
+  a.A_raw = const_cast<float*>(A_raw); a.flags = flags; a.seed = seed;
+  a.ml = ml; a.M = M; a.dM = dM; a.dA_raw = dA_raw;
+  a.dG = dG; a.lddg = KD; a.colsum_ws = cs; a.dbc_ws = dbc_ws;
+  MMF_TRY(dispatch_amil<AMIL_BWD_GATE>(L, D, gated, x, N, ldx, w, a, Hb, st));
+
+  // 2. dwc, dbab, dbc from the per-warp partial sums
+  reduce_rows_kernel<<<(D + 31) / 32, dim3(32, 8), 0, st>>>(cs, tiles * 4, D, ncols, g->dwc, 1);
+  reduce_rows_kernel<<<(KD + 31) / 32, dim3(32, 8), 0, st>>>(cs + D, tiles * 4, KD, ncols, g->dbab, 1);
+  reduce_rows_kernel<<<1, dim3(32, 8), 0, st>>>(dbc_ws, tiles * 4, 1, 1, g->dbc, 1);
+  MMF_TRY(launch_status());
+
+  // 3. dU = (dG Wab + p dM^T) ⊙ relu'(H) [* 1/(1-p)]
+  {
+    TMapSet tA = {}, tB = {};
+    MMF_TRY(make_tmap_bf16(&tA.m[0], dG, (uint64_t)N, KD, KD, 128));
+    MMF_TRY(make_tmap_bf16(&tB.m[0], w->Wab, KD, L, L, 64));
+    GemmArgs ga = {};
+    ga.M = (int)N; ga.N = L; ga.kb_total = KD / 64; ga.kb_per_split = ga.kb_total;
+    ga.a_seg_kb = ga.kb_total; ga.b_seg_n = L;
+    ga.c_bf16 = dU; ga.ldc = L;
+    ga.s_raw = A_raw; ga.ml = ml; ga.dM = dM; ga.H = Hb; ga.ldh = L; ga.colsum_ws = db1_ws;
+    ga.du_scale = (flags & MMF_DROPOUT_H) ? (1.0f / 0.75f) : 1.0f;
+    MMF_TRY((launch_gemm<0, 1, EPI_DU>(tA, tB, ga, 1, st)));
+    reduce_rows_kernel<<<(L + 31) / 32, dim3(32, 8), 0, st>>>(db1_ws, tiles * 4, L, L, g->db1, 1);
+    MMF_TRY(launch_status());
+  }
+  const int kb_rows = (int)((N + 63) / 64);
+  // 4. dW1 += dU^T X
+  {
+    TMapSet tA = {}, tB = {};
+    MMF_TRY(make_tmap_bf16(&tA.m[0], dU, (uint64_t)N, L, L, 64));
+    MMF_TRY(make_tmap_bf16(&tB.m[0], x, (uint64_t)N, 1024, (uint64_t)ldx, 64));
+    GemmArgs ga = {};
+    ga.M = L; ga.N = 1024; ga.kb_total = kb_rows;
+    const int splits = pick_splits((L / 128) * (1024 / 256), kb_rows, &ga.kb_per_split);
+    ga.a_seg_kb = kb_rows; ga.b_seg_n = 1024;
+    ga.c_f32 = g->dW1; ga.ldc = 1024;
+    MMF_TRY((launch_gemm<1, 1, EPI_ATOMIC>(tA, tB, ga, splits, st)));
+  }
+  // 5. dWab += dG^T H
+  {
+    TMapSet tA = {}, tB = {};
+    MMF_TRY(make_tmap_bf16(&tA.m[0], dG, (uint64_t)N, KD, KD, 64));
+    MMF_TRY(make_tmap_bf16(&tB.m[0], Hb, (uint64_t)N, L, L, 64));
+    GemmArgs ga = {};
+    ga.M = KD; ga.N = L; ga.kb_total = kb_rows;
+    const int splits = pick_splits((KD / 128) * ((L + 255) / 256), kb_rows, &ga.kb_per_split);
+    ga.a_seg_kb = kb_rows; ga.b_seg_n = L;
+    ga.c_f32 = g->dWab; ga.ldc = L;
+    MMF_TRY((launch_gemm<1, 1, EPI_ATOMIC>(tA, tB, ga, splits, st)));
+  }
+  // 6. dx = dU W1 (only when a layer sits upstream of the bag features)
+  if (flags & MMF_NEED_DX) {
+    TMapSet tA = {}, tB = {};
+    MMF_TRY(make_tmap_bf16(&tA.m[0], dU, (uint64_t)N, L, L, 128));
+    MMF_TRY(make_tmap_bf16(&tB.m[0], w->W1, L, 1024, 1024, 64));
+    GemmArgs ga = {};
+    ga.M = (int)N; ga.N = 1024; ga.kb_total = L / 64; ga.kb_per_split = ga.kb_total;
+    ga.a_seg_kb = ga.kb_total; ga.b_seg_n = 1024;
+    ga.c_bf16 = dx; ga.ldc = 1024;
+    MMF_TRY((launch_gemm<0, 1, EPI_STORE>(tA, tB, ga, 1, st)));
+  }
+  return MMF_OK;
+}
+
+int mmf_linear_bf16(const void* const* A_segs, int n_segs, int64_t M, int K_per_seg, int64_t lda,
+                    const void* W, const float* bias, int N, void* out_bf16, float* out_f32,
+                    int64_t ldc, void* stream) {
+  if (!A_segs || n_segs < 1 || n_segs > 4 || M <= 0 || !W || N <= 0) return MMF_E_INVALID;
+  if ((out_bf16 == nullptr) == (out_f32 == nullptr)) return MMF_E_INVALID;
+  if (K_per_seg % 64 || N % 32) return MMF_E_UNSUPPORTED;
+  TMapSet tA = {}, tB = {};
+  for (int i = 0; i < n_segs; ++i)
+    MMF_TRY(make_tmap_bf16(&tA.m[i], A_segs[i], (uint64_t)M, K_per_seg, (uint64_t)lda, 128));
+  const int64_t Ktot = (int64_t)n_segs * K_per_seg;
+  MMF_TRY(make_tmap_bf16(&tB.m[0], W, N, Ktot, Ktot, 256));
+  GemmArgs ga = {};
+  ga.M = (int)M; ga.N = N; ga.kb_total = (int)(Ktot / 64); ga.kb_per_split = ga.kb_total;
+  ga.a_seg_kb = K_per_seg / 64; ga.b_seg_n = N;
+  ga.c_bf16 = out_bf16; ga.c_f32 = out_f32; ga.ldc = ldc; ga.bias = bias;
+  return launch_gemm<0, 0, EPI_STORE>(tA, tB, ga, 1, (cudaStream_t)stream);
+}
+
+size_t mmf_linear_bf16_wgrad_workspace_bytes(int64_t M, int N) { (void)M; (void)N; return 0; }
+
+int mmf_linear_bf16_wgrad(const void* dY, int64_t M, int N, int64_t lddy, const void* const* X_segs,
+                          int n_segs, int K_per_seg, int64_t ldx, float* dW, float* db,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+  (void)workspace; (void)workspace_bytes;
+  if (!dY || !X_segs || n_segs < 1 || n_segs > 4 || M <= 0 || !dW) return MMF_E_INVALID;
+  if (N % 128 || K_per_seg % 256) return MMF_E_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  TMapSet tA = {}, tB = {};
+  MMF_TRY(make_tmap_bf16(&tA.m[0], dY, (uint64_t)M, N, (uint64_t)lddy, 64));
+  for (int i = 0; i < n_segs; ++i)
+    MMF_TRY(make_tmap_bf16(&tB.m[i], X_segs[i], (uint64_t)M, K_per_seg, (uint64_t)ldx, 64));
+  const int Ktot = n_segs * K_per_seg;
+  GemmArgs ga = {};
+  ga.M = N; ga.N = Ktot; ga.kb_total = (int)((M + 63) / 64);
+  const int splits = pick_splits((N / 128) * (Ktot / 256), ga.kb_total, &ga.kb_per_split);
+  ga.a_seg_kb = ga.kb_total; ga.b_seg_n = K_per_seg;
+  ga.c_f32 = dW; ga.ldc = Ktot;
+  MMF_TRY((launch_gemm<1, 1, EPI_ATOMIC>(tA, tB, ga, splits, st)));
+  if (db) {
+    colsum_bf16_kernel<<<(N + 31) / 32, dim3(32, 8), 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(dY), M, N, lddy, db, 1);
+    MMF_TRY(launch_status());
+  }
+  return MMF_OK;
+}
+
+// ------------------------------ small fp32 kernels --------------------------------------------
+
+int mmf_dense_fwd(const float* x, int64_t ldx, const float* W, const float* b, int B, int in_dim,
+                  int out_dim, int act, float* y, int64_t ldy, void* stream) {
+  if (!x || !W || !y || B <= 0 || in_dim <= 0 || out_dim <= 0) return MMF_E_INVALID;
+  launch_sgemm(B, out_dim, in_dim, LoadRowMajor{x, ldx}, LoadRowMajor{W, in_dim},
+               EpiBiasAct{y, ldy, b, act}, (cudaStream_t)stream);
+  return launch_status();
+}
+
+int mmf_dense_bwd(const float* x, int64_t ldx, const float* W, int B, int in_dim, int out_dim,
+                  int act, const float* y, int64_t ldy, const float* dy, int64_t lddy, float* dx,
+                  int64_t lddx, int accumulate_dx, float* dW, float* db, void* stream) {
+  if (!x || !W || !y || !dy || B <= 0) return MMF_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dx)  // dx[b,i] = sum_o dpre[b,o] W[o,i]
+    launch_sgemm(B, in_dim, out_dim, LoadDpre{dy, lddy, y, ldy, act}, LoadColMajor{W, in_dim},
+                 EpiStoreAcc{dx, lddx, accumulate_dx}, st);
+  if (dW)  // dW[o,i] += sum_b dpre[b,o] x[b,i]
+    launch_sgemm(out_dim, in_dim, B, LoadDpreT{dy, lddy, y, ldy, act}, LoadColMajor{x, ldx},
+                 EpiStoreAcc{dW, in_dim, 1}, st);
+  if (db)
+    colsum_functor_kernel<<<(out_dim + 127) / 128, 128, 0, st>>>(B, out_dim, LoadDpre{dy, lddy, y, ldy, act}, db, 1);
+  return launch_status();
+}
+
+int mmf_kron_enc_fwd(const float* const* o, int m, int E, int B, const float* W, const float* b,
+                     int H, float* out, void* stream) {
+  if (!o || (m != 2 && m != 3) || E <= 0 || B <= 0 || !W || !out) return MMF_E_INVALID;
+  KronElem e{o[0], o[1], m == 3 ? o[2] : nullptr, m, E};
+  const int KK = (m == 3) ? E * E * E : E * E;
+  launch_sgemm(B, H, KK, LoadKronA{e}, LoadRowMajor{W, KK}, EpiBiasAct{out, H, b, MMF_ACT_RELU},
+               (cudaStream_t)stream);
+  return launch_status();
+}
+
+size_t mmf_kron_enc_workspace_bytes(int m, int E, int B) {
+  size_t kk = (m == 3) ? (size_t)E * E * E : (size_t)E * E;
+  return kk * (size_t)B * sizeof(float);
+}
+
+int mmf_kron_enc_bwd(const float* const* o, int m, int E, int B, const float* W, int H,
+                     const float* out, const float* dout, float* const* d_o, float* dW, float* db,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+  if (!o || (m != 2 && m != 3) || !W || !out || !dout || !workspace) return MMF_E_INVALID;
+  if (workspace_bytes < mmf_kron_enc_workspace_bytes(m, E, B)) return MMF_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  KronElem e{o[0], o[1], m == 3 ? o[2] : nullptr, m, E};
+  const int KK = (m == 3) ? E * E * E : E * E;
+  float* dkron = reinterpret_cast<float*>(workspace);
+  LoadDpre dpre{dout, H, out, H, MMF_ACT_RELU};
+  LoadDpreT dpreT{dout, H, out, H, MMF_ACT_RELU};
+  if (d_o) {
+    // dkron[b,kk] = sum_h dpre[b,h] W[h,kk]
+    launch_sgemm(B, KK, H, dpre, LoadColMajor{W, KK}, EpiStoreAcc{dkron, KK, 0}, st);
+    kron_contract_kernel<<<B, 256, 6 * E * sizeof(float), st>>>(dkron, e, B, d_o[0], d_o[1],
+                                                                m == 3 ? d_o[2] : nullptr);
+  }
+  if (dW)  // dW[h,kk] += sum_b dpre[b,h] kron[b,kk]
+    launch_sgemm(H, KK, B, dpreT, LoadKronB{e}, EpiStoreAcc{dW, KK, 1}, st);
+  if (db) colsum_functor_kernel<<<(H + 127) / 128, 128, 0, st>>>(B, H, dpre, db, 1);
+  return launch_status();
+}
+
+int mmf_hazard_head_fwd(const float* M, int B, int Lin, const float* Wk, const float* bk, int K,
+                        float* hazards, float* S, int64_t* Y_hat, void* stream) {
+  if (!M || !Wk || !bk || !hazards || !S || B <= 0 || K <= 0 || K > 16) return MMF_E_INVALID;
+  const int warps_per_block = 4;
+  hazard_head_fwd_kernel<<<(B + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0,
+                           (cudaStream_t)stream>>>(M, B, Lin, Wk, bk, K, hazards, S,
+                                                   reinterpret_cast<long long*>(Y_hat));
+  return launch_status();
+}
+
+int mmf_hazard_head_bwd(const float* M, int B, int Lin, const float* Wk, int K, const float* hazards,
+                        const float* S, const float* d_hazards, const float* d_S, float* dM,
+                        float* dWk, float* dbk, void* stream) {
+  (void)S;
+  if (!M || !Wk || !hazards || B <= 0 || K <= 0 || K > 16) return MMF_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  HazardDlogit d{hazards, d_hazards, d_S, K};
+  if (dM)  // dM[b,l] = sum_j dlogit[b,j] Wk[j,l]
+    launch_sgemm(B, Lin, K, LoadHazA{d}, LoadColMajor{Wk, Lin}, EpiStoreAcc{dM, Lin, 0}, st);
+  if (dWk)  // dWk[j,l] += sum_b dlogit[b,j] M[b,l]
+    launch_sgemm(K, Lin, B, LoadHazAT{d}, LoadColMajor{M, Lin}, EpiStoreAcc{dWk, Lin, 1}, st);
+  if (dbk) colsum_functor_kernel<<<1, 32, 0, st>>>(B, K, LoadHazA{d}, dbk, 1);
+  return launch_status();
+}
+
+int mmf_nll_surv_fwd_bwd(const float* hazards, const float* S, const int64_t* Y, const float* c,
+                         int B, int K, float alpha, float eps, float* loss, float* d_hazards,
+                         float* d_S, void* stream) {
+  if (!hazards || !S || !Y || !c || !loss || B <= 0 || K <= 0) return MMF_E_INVALID;
+  nll_surv_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(hazards, S, reinterpret_cast<const long long*>(Y), c, B, K,
+                                                       alpha, eps, loss, d_hazards, d_S);
+  return launch_status();
+}
+
+size_t mmf_cox_workspace_bytes(int B) { (void)B; return 0; }
+
+int mmf_cox_fwd_bwd(const float* theta, const float* times, const float* c, int B, float* loss,
+                    float* dtheta, void* workspace, size_t workspace_bytes, void* stream) {
+  (void)workspace; (void)workspace_bytes;
+  if (!theta || !times || !c || !loss || B <= 0) return MMF_E_INVALID;
+  if (B > MMF_COX_MAXB) return MMF_E_UNSUPPORTED;
+  cox_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(theta, times, c, B, loss, dtheta);
+  return launch_status();
+}
+
+size_t mmf_ranking_workspace_bytes(int B) { return 16 + (size_t)B * sizeof(float); }
+
+int mmf_ranking_fwd_bwd(const float* risks, const float* times, const float* c, int B, int phi,
+                        int reduction, float* loss, float* drisks, int64_t* n_pairs, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  if (!risks || !times || !c || !loss || !workspace || B < 2) return MMF_E_INVALID;
+  if (workspace_bytes < mmf_ranking_workspace_bytes(B)) return MMF_E_WORKSPACE;
+  if (reinterpret_cast<uintptr_t>(workspace) & 7u) return MMF_E_ALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  double* acc = reinterpret_cast<double*>(workspace);
+  float* g = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + 16);
+  MMF_TRY(cuda_rc(cudaMemsetAsync(acc, 0, 16, st)));
+  const int blocks = (B + 127) / 128;
+  ranking_pairs_kernel<<<blocks, 128, 0, st>>>(risks, times, c, B, phi, acc, g);
+  ranking_finalize_kernel<<<blocks, 128, 0, st>>>(acc, B, reduction, loss, drisks, g,
+                                                  reinterpret_cast<long long*>(n_pairs));
+  return launch_status();
+}
+
+}  // extern "C"

@@ -1,0 +1,67 @@
+// mmf_host.cuh — host-side helpers shared by the C-ABI entry points: error codes,
+// TMA descriptor (CUtensorMap) construction through the driver entry point (no link-time
+// dependency on libcuda, so the library also loads on a box without a driver), launch checks.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/mmf_b200.h"
+
+namespace mmf {
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<PFN_encodeTiled>(p);
+  return fn;
+}
+
+// 2-D row-major bf16 array [rows][cols] with leading dimension `ld` (elements); box is
+// [box_rows][64 cols] (128-byte rows) with the 128-byte swizzle. Out-of-bounds elements of a
+// box read as zero and are dropped on store.
+inline int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                          uint64_t ld, uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return MMF_E_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0 || (ld * 2) % 16 != 0) return MMF_E_ALIGN;
+  if (rows == 0 || cols == 0) return MMF_E_INVALID;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {ld * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MMF_OK : MMF_E_TMAP;
+}
+
+inline int launch_status() {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    fprintf(stderr, "mmf: CUDA launch error: %s\n", cudaGetErrorString(e));
+    return -(1000 + (int)e);
+  }
+  return MMF_OK;
+}
+
+#define MMF_TRY(expr)            \
+  do {                           \
+    int _rc = (expr);            \
+    if (_rc != MMF_OK) return _rc; \
+  } while (0)
+
+inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? MMF_OK : -(1000 + (int)e); }
+
+}  // namespace mmf

@@ -1,0 +1,515 @@
+// small_kernels.cuh — fp32 SIMT kernels for the latency-bound parts of the path: dense layers
+// (SNN blocks, classifier heads, Xlinear reduce/encoder layers), the Kronecker-fusion encoder,
+// the discrete-hazard head, and the survival losses (NLL, Cox, pairwise ranking).
+//
+// One functor-driven 64x64x16 SGEMM serves every small matrix product: operand elements are
+// produced by loader functors, so activation derivatives, the hazard/cumprod chain rule and the
+// Kronecker outer product are formed on the fly instead of being materialised.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+namespace mmf {
+
+// -------------------------------------------------------------------------------------------
+// activations (y = act(pre)); derivative expressed through y so no pre-activation is stored
+// -------------------------------------------------------------------------------------------
+#define MMF_SELU_ALPHA 1.6732632423543772848170429916717f
+#define MMF_SELU_SCALE 1.0507009873554804934193349852946f
+
+__device__ __forceinline__ float act_fwd(int act, float x) {
+  switch (act) {
+    case 1: return fmaxf(x, 0.f);
+    case 2: return MMF_SELU_SCALE * (x > 0.f ? x : MMF_SELU_ALPHA * expm1f(x));
+    case 3: return 1.f / (1.f + expf(-x));
+    case 4: return tanhf(x);
+    default: return x;
+  }
+}
+__device__ __forceinline__ float act_grad_from_y(int act, float y) {
+  switch (act) {
+    case 1: return y > 0.f ? 1.f : 0.f;
+    case 2: return y > 0.f ? MMF_SELU_SCALE : (y + MMF_SELU_SCALE * MMF_SELU_ALPHA);
+    case 3: return y * (1.f - y);
+    case 4: return 1.f - y * y;
+    default: return 1.f;
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// loader / epilogue functors
+// -------------------------------------------------------------------------------------------
+struct LoadRowMajor {            // element (i, k) = p[i*ld + k]       (k contiguous)
+  const float* p; long long ld;
+  static constexpr bool kContig = true;
+  __device__ __forceinline__ float operator()(int i, int k) const { return p[i * ld + k]; }
+};
+struct LoadColMajor {            // element (i, k) = p[k*ld + i]       (i contiguous)
+  const float* p; long long ld;
+  static constexpr bool kContig = false;
+  __device__ __forceinline__ float operator()(int i, int k) const { return p[k * ld + i]; }
+};
+// dpre(b, o) = dy[b,o] * act'(y[b,o])
+struct LoadDpre {                // element (b, o), o contiguous -> as A(m=b, k=o): k contiguous
+  const float* dy; long long lddy; const float* y; long long ldy; int act;
+  static constexpr bool kContig = true;
+  __device__ __forceinline__ float operator()(int b, int o) const {
+    return dy[b * lddy + o] * act_grad_from_y(act, y[b * ldy + o]);
+  }
+};
+struct LoadDpreT {               // element (o, b): A(m=o, k=b): m contiguous
+  const float* dy; long long lddy; const float* y; long long ldy; int act;
+  static constexpr bool kContig = false;
+  __device__ __forceinline__ float operator()(int o, int b) const {
+    return dy[b * lddy + o] * act_grad_from_y(act, y[b * ldy + o]);
+  }
+};
+// Kronecker product element kk of o_1 ⊗ o_2 (⊗ o_3) for sample b (first factor slowest).
+struct KronElem {
+  const float* o0; const float* o1; const float* o2; int m; int E;
+  __device__ __forceinline__ float at(int b, int kk) const {
+    if (m == 2) { const int i = kk / E, j = kk - i * E; return o0[b * E + i] * o1[b * E + j]; }
+    const int i = kk / (E * E); const int r = kk - i * E * E; const int j = r / E, k = r - j * E;
+    return o0[b * E + i] * o1[b * E + j] * o2[b * E + k];
+  }
+};
+struct LoadKronA {               // A(m=b, k=kk)
+  KronElem e; static constexpr bool kContig = true;
+  __device__ __forceinline__ float operator()(int b, int kk) const { return e.at(b, kk); }
+};
+struct LoadKronB {               // B(n=kk, k=b)  (n contiguous)
+  KronElem e; static constexpr bool kContig = false;
+  __device__ __forceinline__ float operator()(int kk, int b) const { return e.at(b, kk); }
+};
+// d(logit) of the hazard head given d_hazards and d_S (cumprod chain rule), K <= 16.
+struct HazardDlogit {
+  const float* haz; const float* dhaz; const float* dS; int K;
+  __device__ __forceinline__ float at(int b, int j) const {
+    const float* h = haz + (long long)b * K;
+    float g = dhaz ? dhaz[(long long)b * K + j] : 0.f;
+    if (dS) {
+      // dS_k/dh_j = -prod_{i<=k, i!=j} (1-h_i)  for k >= j
+      float pre = 1.f;
+      for (int i = 0; i < j; ++i) pre *= (1.f - h[i]);
+      float run = pre;  // prod_{i<=k, i != j}
+      for (int k = j; k < K; ++k) {
+        if (k > j) run *= (1.f - h[k]);
+        g -= dS[(long long)b * K + k] * run;
+      }
+    }
+    return g * h[j] * (1.f - h[j]);
+  }
+};
+struct LoadHazA { HazardDlogit d; static constexpr bool kContig = true;
+  __device__ __forceinline__ float operator()(int b, int j) const { return d.at(b, j); } };
+struct LoadHazAT { HazardDlogit d; static constexpr bool kContig = false;
+  __device__ __forceinline__ float operator()(int j, int b) const { return d.at(b, j); } };
+
+struct EpiBiasAct {              // y[m*ld+n] = act(acc + bias[n])
+  float* y; long long ld; const float* bias; int act;
+  __device__ __forceinline__ void operator()(int m, int n, float acc) const {
+    y[m * ld + n] = act_fwd(act, acc + (bias ? bias[n] : 0.f));
+  }
+};
+struct EpiStoreAcc {             // c[m*ld+n] = (accumulate ? c : 0) + acc
+  float* c; long long ld; int accumulate;
+  __device__ __forceinline__ void operator()(int m, int n, float acc) const {
+    float* p = c + m * ld + n;
+    *p = accumulate ? *p + acc : acc;
+  }
+};
+
+// C(m,n) = sum_k A(m,k) * B(n,k).  64x64 tile, 256 threads, 4x4 micro-tile, BK = 16.
+template <class ALoad, class BLoad, class Epi>
+__global__ void __launch_bounds__(256)
+sgemm_functor_kernel(int M, int N, int K, ALoad la, BLoad lb, Epi epi) {
+  __shared__ float As[16][68];
+  __shared__ float Bs[16][68];
+  const int tid = threadIdx.x;
+  const int tm = tid / 16, tn = tid % 16;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += 16) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = tid + e * 256;
+      {
+        const int mm = ALoad::kContig ? idx / 16 : idx % 64;
+        const int kk = ALoad::kContig ? idx % 16 : idx / 64;
+        const int gm = m0 + mm, gk = k0 + kk;
+        As[kk][mm] = (gm < M && gk < K) ? la(gm, gk) : 0.f;
+      }
+      {
+        const int nn = BLoad::kContig ? idx / 16 : idx % 64;
+        const int kk = BLoad::kContig ? idx % 16 : idx / 64;
+        const int gn = n0 + nn, gk = k0 + kk;
+        Bs[kk][nn] = (gn < N && gk < K) ? lb(gn, gk) : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av[i] = As[kk][tm * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bv[j] = Bs[kk][tn * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gm = m0 + tm * 4 + i, gn = n0 + tn * 4 + j;
+      if (gm < M && gn < N) epi(gm, gn, acc[i][j]);
+    }
+}
+
+template <class ALoad, class BLoad, class Epi>
+inline void launch_sgemm(int M, int N, int K, ALoad la, BLoad lb, Epi epi, cudaStream_t st) {
+  dim3 grid((N + 63) / 64, (M + 63) / 64);
+  sgemm_functor_kernel<ALoad, BLoad, Epi><<<grid, 256, 0, st>>>(M, N, K, la, lb, epi);
+}
+
+// out[o] (+)= sum_b elem(b, o)   — one thread per column
+template <class Elem>
+__global__ void colsum_functor_kernel(int B, int O, Elem e, float* out, int accumulate) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= O) return;
+  float s = 0.f;
+  for (int b = 0; b < B; ++b) s += e(b, o);
+  out[o] = accumulate ? out[o] + s : s;
+}
+
+// -------------------------------------------------------------------------------------------
+// Kronecker encoder backward, input side: given dkron[B, E^m] contract against the other factors
+//   d_o0[b,i] = sum_{j,k} dkron[b,(i,j,k)] o1[b,j] o2[b,k]   etc.   One block per sample.
+// -------------------------------------------------------------------------------------------
+__global__ void kron_contract_kernel(const float* __restrict__ dkron, KronElem e, int B,
+                                     float* d0, float* d1, float* d2) {
+  extern __shared__ float sh[];  // 3*E accumulators + 3*E factor values
+  const int E = e.E, m = e.m, b = blockIdx.x;
+  float* acc = sh;
+  float* f = sh + 3 * E;
+  for (int i = threadIdx.x; i < 3 * E; i += blockDim.x) acc[i] = 0.f;
+  for (int i = threadIdx.x; i < E; i += blockDim.x) {
+    f[i] = e.o0[b * E + i];
+    f[E + i] = e.o1[b * E + i];
+    f[2 * E + i] = (m == 3) ? e.o2[b * E + i] : 1.f;
+  }
+  __syncthreads();
+  const int KK = (m == 3) ? E * E * E : E * E;
+  const float* row = dkron + (long long)b * KK;
+  for (int kk = threadIdx.x; kk < KK; kk += blockDim.x) {
+    const float g = row[kk];
+    int i, j, k;
+    if (m == 3) { i = kk / (E * E); const int r = kk - i * E * E; j = r / E; k = r - j * E; }
+    else { i = kk / E; j = kk - i * E; k = 0; }
+    const float v0 = f[i], v1 = f[E + j], v2 = f[2 * E + k];
+    atomicAdd(&acc[i], g * v1 * v2);
+    atomicAdd(&acc[E + j], g * v0 * v2);
+    if (m == 3) atomicAdd(&acc[2 * E + k], g * v0 * v1);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < E; i += blockDim.x) {
+    d0[b * E + i] = acc[i];
+    d1[b * E + i] = acc[E + i];
+    if (m == 3) d2[b * E + i] = acc[2 * E + i];
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// hazard head forward: one warp per sample.
+// -------------------------------------------------------------------------------------------
+__global__ void hazard_head_fwd_kernel(const float* __restrict__ M, int B, int Lin,
+                                       const float* __restrict__ Wk, const float* __restrict__ bk,
+                                       int K, float* hazards, float* S, long long* Y_hat) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= B) return;
+  const float* mrow = M + (long long)warp * Lin;
+  float best = -CUDART_INF_F; int besti = 0; float surv = 1.f;
+  for (int j = 0; j < K; ++j) {
+    float d = 0.f;
+    for (int l = lane; l < Lin; l += 32) d = fmaf(mrow[l], Wk[(long long)j * Lin + l], d);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    const float logit = d + bk[j];
+    if (logit > best) { best = logit; besti = j; }
+    const float h = 1.f / (1.f + expf(-logit));
+    surv *= (1.f - h);
+    if (lane == 0) { hazards[(long long)warp * K + j] = h; S[(long long)warp * K + j] = surv; }
+  }
+  if (lane == 0 && Y_hat) Y_hat[warp] = besti;
+}
+
+// -------------------------------------------------------------------------------------------
+// NLL survival loss (utils/loss_utils.py:22-39), forward + gradient. Single block.
+// -------------------------------------------------------------------------------------------
+__global__ void nll_surv_kernel(const float* __restrict__ haz, const float* __restrict__ S,
+                                const long long* __restrict__ Y, const float* __restrict__ c, int B,
+                                int K, float alpha, float eps, float* loss, float* d_haz, float* d_S) {
+  __shared__ float red[32];
+  float local = 0.f;
+  const float invB = 1.f / (float)B;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const long long y = Y[b];
+    const float cb = c[b];
+    const float* h = haz + (long long)b * K;
+    const float* s = S + (long long)b * K;
+    for (int k = 0; k < K; ++k) {
+      if (d_haz) d_haz[(long long)b * K + k] = 0.f;
+      if (d_S) d_S[(long long)b * K + k] = 0.f;
+    }
+    const float sp_y = (y == 0) ? 1.f : s[y - 1];       // S_padded[Y]
+    const float h_y = h[y];
+    const float sp_y1 = s[y];                             // S_padded[Y+1]
+    const float unc = -(1.f - cb) * (logf(fmaxf(sp_y, eps)) + logf(fmaxf(h_y, eps)));
+    const float cen = -cb * logf(fmaxf(sp_y1, eps));
+    local += (1.f - alpha) * (cen + unc) + alpha * unc;
+    if (d_S) {
+      if (y > 0 && sp_y >= eps) d_S[(long long)b * K + y - 1] += -(1.f - cb) / sp_y * invB;
+      if (sp_y1 >= eps) d_S[(long long)b * K + y] += -(1.f - alpha) * cb / sp_y1 * invB;
+    }
+    if (d_haz && h_y >= eps) d_haz[(long long)b * K + y] += -(1.f - cb) / h_y * invB;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    *loss = t * invB;
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// Cox partial likelihood (utils/loss_utils.py:124-139), B <= 2048, single block of 1024.
+// sort by time descending (bitonic on (time, index)), inclusive prefix sums of e^{theta-max}
+// extended to tie-group ends, suffix sums of (1-c)/E for the gradient.
+// -------------------------------------------------------------------------------------------
+#define MMF_COX_MAXB 2048
+__global__ void __launch_bounds__(1024)
+cox_kernel(const float* __restrict__ theta, const float* __restrict__ times,
+           const float* __restrict__ cens, int B, float* loss, float* dtheta) {
+  __shared__ float s_t[MMF_COX_MAXB];
+  __shared__ int s_i[MMF_COX_MAXB];
+  __shared__ float s_a[MMF_COX_MAXB];   // scan buffer A
+  __shared__ float s_b[MMF_COX_MAXB];   // scan buffer B
+  __shared__ float s_red[33];
+  const int tid = threadIdx.x;
+  int P = 1;
+  while (P < B) P <<= 1;
+  // load; padding sorts to the end (time = -inf in a descending sort)
+  float tmax = -CUDART_INF_F;
+  for (int i = tid; i < P; i += blockDim.x) {
+    s_t[i] = i < B ? times[i] : -CUDART_INF_F;
+    s_i[i] = i < B ? i : -1;
+    if (i < B) tmax = fmaxf(tmax, theta[i]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+  if ((tid & 31) == 0) s_red[tid >> 5] = tmax;
+  __syncthreads();
+  if (tid == 0) {
+    float v = s_red[0];
+    for (int i = 1; i < 32; ++i) v = fmaxf(v, s_red[i]);
+    s_red[32] = v;
+  }
+  __syncthreads();
+  tmax = s_red[32];
+  // bitonic sort, descending by time
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < P; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const bool desc = (i & k) == 0;
+          const float a = s_t[i], b = s_t[ixj];
+          if (desc ? (a < b) : (a > b)) {
+            s_t[i] = b; s_t[ixj] = a;
+            const int ti = s_i[i]; s_i[i] = s_i[ixj]; s_i[ixj] = ti;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // w_k = exp(theta_k - max) in sorted order; inclusive scan (Hillis-Steele, ping-pong)
+  for (int i = tid; i < P; i += blockDim.x) s_a[i] = (s_i[i] >= 0) ? expf(theta[s_i[i]] - tmax) : 0.f;
+  __syncthreads();
+  float* src = s_a; float* dst = s_b;
+  for (int off = 1; off < P; off <<= 1) {
+    for (int i = tid; i < P; i += blockDim.x) dst[i] = src[i] + (i >= off ? src[i - off] : 0.f);
+    __syncthreads();
+    float* t = src; src = dst; dst = t;
+  }
+  // src = inclusive prefix. E_k = prefix[end of tie group]; q_k = (1-c)/E_k ; loss terms
+  float local = 0.f;
+  for (int i = tid; i < P; i += blockDim.x) {
+    float q = 0.f;
+    if (i < B) {
+      int e = i;
+      while (e + 1 < B && s_t[e + 1] == s_t[i]) ++e;
+      const float E = src[e];
+      const int orig = s_i[i];
+      const float ev = 1.f - cens[orig];
+      local += ev * (theta[orig] - tmax - logf(E));
+      q = ev / E;
+    }
+    dst[i] = q;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if ((tid & 31) == 0) s_red[tid >> 5] = local;
+  __syncthreads();
+  if (tid == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 32; ++i) t += s_red[i];
+    *loss = -t / (float)B;
+  }
+  if (dtheta == nullptr) return;
+  // suffix sums of q (reverse inclusive scan) : ping-pong between dst (holds q) and src
+  float* a = dst; float* b = src;
+  for (int off = 1; off < P; off <<= 1) {
+    for (int i = tid; i < P; i += blockDim.x) b[i] = a[i] + (i + off < P ? a[i + off] : 0.f);
+    __syncthreads();
+    float* t = a; a = b; b = t;
+  }
+  // a = suffix sums. grad_k = -(1/B) [ (1-c_k) - w_k * Q[start of tie group] ]
+  for (int i = tid; i < B; i += blockDim.x) {
+    int s0 = i;
+    while (s0 > 0 && s_t[s0 - 1] == s_t[i]) --s0;
+    const int orig = s_i[i];
+    const float w = expf(theta[orig] - tmax);
+    dtheta[orig] = -((1.f - cens[orig]) - w * a[s0]) / (float)B;
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// pairwise ranking loss (utils/loss_utils.py:58-101)
+// -------------------------------------------------------------------------------------------
+__device__ __forceinline__ float rank_phi(int phi, float r) {
+  return phi == 0 ? 1.f / (1.f + expf(-r)) : fmaxf(r, 0.f);
+}
+__device__ __forceinline__ float rank_dphi(int phi, float r) {
+  if (phi == 0) { const float s = 1.f / (1.f + expf(-r)); return s * (1.f - s); }
+  return r > 0.f ? 1.f : 0.f;
+}
+// acc[0] = sum phi, acc[1] = pair count (as double to stay exact); g[i] = unnormalised d(sum phi)/dr_i
+__global__ void ranking_pairs_kernel(const float* __restrict__ risks, const float* __restrict__ times,
+                                     const float* __restrict__ cens, int B, int phi, double* acc,
+                                     float* g) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float sum = 0.f, gi = 0.f;
+  unsigned int cnt = 0;
+  if (i < B) {
+    const float ri = risks[i], ti = times[i];
+    const bool ei = (1.f - cens[i]) != 0.f;
+    for (int j = 0; j < B; ++j) {
+      if (j == i) continue;
+      const float rj = risks[j], tj = times[j];
+      if (ei && ti < tj) {             // (i risky, j safe)
+        sum += rank_phi(phi, ri - rj);
+        gi += rank_dphi(phi, ri - rj);
+        ++cnt;
+      }
+      if (((1.f - cens[j]) != 0.f) && tj < ti) {  // (j risky, i safe)
+        gi -= rank_dphi(phi, rj - ri);
+      }
+    }
+    g[i] = gi;
+  }
+  // block reduce
+  __shared__ float s_sum[32];
+  __shared__ unsigned int s_cnt[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  if ((threadIdx.x & 31) == 0) { s_sum[threadIdx.x >> 5] = sum; s_cnt[threadIdx.x >> 5] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0, n = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { t += s_sum[w]; n += s_cnt[w]; }
+    atomicAdd(&acc[0], t);
+    atomicAdd(&acc[1], n);
+  }
+}
+__global__ void ranking_finalize_kernel(const double* acc, int B, int reduction, float* loss,
+                                        float* drisks, const float* g, long long* n_pairs) {
+  const double n = acc[1];
+  const float scale = (n > 0.0) ? (reduction == 0 ? (float)(1.0 / n) : 1.f) : 0.f;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B && drisks) drisks[i] = -g[i] * scale;
+  if (i == 0) {
+    *loss = (n > 0.0) ? (float)(-(acc[0]) * (reduction == 0 ? 1.0 / n : 1.0)) : 0.f;
+    if (n_pairs) *n_pairs = (long long)n;
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// format helpers
+// -------------------------------------------------------------------------------------------
+__global__ void cast_f32_bf16_kernel(const float4* __restrict__ src, uint2* __restrict__ dst,
+                                     long long n4, const float* src_tail, __nv_bfloat16* dst_tail,
+                                     int tail) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = src[i];
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&lo);
+    o.y = *reinterpret_cast<uint32_t*>(&hi);
+    dst[i] = o;
+  }
+  if (blockIdx.x == 0 && (int)threadIdx.x < tail) dst_tail[threadIdx.x] = __float2bfloat16_rn(src_tail[threadIdx.x]);
+}
+
+// packed[c*CHN + r][l] = (r < 128 ? Wa[c*128 + r] : Wb[c*128 + r - 128])[l]   (gated)
+__global__ void pack_wab_kernel(const uint4* __restrict__ Wab, uint4* __restrict__ packed, int L,
+                                int D, int gated) {
+  const int chn = gated ? 256 : 128;
+  const int rows = gated ? 2 * D : D;
+  const int vec_per_row = L / 8;
+  const long long total = (long long)rows * vec_per_row;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int prow = (int)(i / vec_per_row), v = (int)(i % vec_per_row);
+    const int c = prow / chn, r = prow % chn;
+    const int srow = gated ? (r < 128 ? c * 128 + r : D + c * 128 + (r - 128)) : prow;
+    packed[i] = Wab[(long long)srow * vec_per_row + v];
+  }
+}
+
+// out[c] (+)= sum_r Y[r][c], bf16 input
+__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ Y, long long rows, int cols,
+                                   long long ld, float* out, int accumulate) {
+  __shared__ float part[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float acc = 0.f;
+  if (c < cols)
+    for (long long r = threadIdx.y; r < rows; r += blockDim.y) acc += __bfloat162float(Y[r * ld + c]);
+  part[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    float t = 0.f;
+    for (int j = 0; j < (int)blockDim.y; ++j) t += part[j][threadIdx.x];
+    out[c] = accumulate ? out[c] + t : t;
+  }
+}
+
+}  // namespace mmf

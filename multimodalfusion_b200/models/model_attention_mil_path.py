@@ -1,0 +1,50 @@
+"""Pathology attention-MIL survival model — drop-in for
+models/model_attention_mil_path.py (constructors :13-34,:46; forward :50-72).
+
+forward(path_features=[N,1024]) runs two kernels for the bag (fused tile kernel + combine) and one
+for the discrete-hazard head; the [N,L] activations never reach HBM in the forward.
+"""
+import torch
+import torch.nn as nn
+
+from ..autograd import HazardHead
+from ..utils.utils import initialize_weights
+from .model_modules import AmilBranch, Attn_Net, Attn_Net_Gated
+
+
+class MIL_Attention_fc_path(nn.Module):
+    def __init__(self, gate_path=True, dropout=True, model_size_wsi: str = 'small', n_classes=4):
+        super().__init__()
+        self.size_dict_WSI = {"small": [1024, 256, 256], "big": [1024, 512, 384]}
+        in_dim, L, D = self.size_dict_WSI[model_size_wsi]
+        attn_cls = Attn_Net_Gated if gate_path else Attn_Net
+        self.attention_net_WSI = nn.Sequential(
+            nn.Linear(in_dim, L), nn.ReLU(), nn.Dropout(0.25),
+            attn_cls(L=L, D=D, dropout=dropout, n_classes=1))
+        self.classifier = nn.Linear(L, n_classes)
+        initialize_weights(self)
+        self.bag_group = None  # set to a torch.distributed group to shard one bag across ranks
+
+    def relocate(self):
+        device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+        self.attention_net_WSI = self.attention_net_WSI.to(device)
+        self.classifier = self.classifier.to(device)
+
+    def forward(self, h, return_features=False, attention_only=False):
+        pass
+
+
+class MIL_Attention_fc_surv_path(MIL_Attention_fc_path):
+    def __init__(self, gate_path=True, model_size_wsi: str = 'small', dropout=False, n_classes=4):
+        super().__init__(gate_path=gate_path, model_size_wsi=model_size_wsi, dropout=dropout,
+                         n_classes=n_classes)
+
+    def forward(self, **kwargs):
+        x = kwargs['path_features']
+        A_raw, M = AmilBranch.pooled(self.attention_net_WSI, x, self.training, self.bag_group)
+        if kwargs.get('return_features'):
+            return M
+        if kwargs.get('attention_only'):
+            return A_raw
+        hazards, S, Y_hat = HazardHead.apply(M, self.classifier.weight, self.classifier.bias)
+        return hazards, S, Y_hat, A_raw

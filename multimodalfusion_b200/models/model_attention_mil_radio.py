@@ -1,0 +1,77 @@
+"""Radiology attention-MIL survival model — drop-in for models/model_attention_mil_radio.py
+(constructors :14-51,:67-71; forward :73-115).
+
+The four modality bags are never concatenated: the reduce_dim GEMM reads them as four K-segments
+through separate TMA descriptors and writes the bf16 [N,1024] bag the fused AMIL kernel consumes.
+"""
+import torch
+import torch.nn as nn
+
+from ..autograd import HazardHead, SegmentedLinearBf16
+from ..utils.utils import initialize_weights
+from .model_modules import AmilBranch, Attn_Net, Attn_Net_Gated, XlinearFusion
+
+
+class MIL_Attention_fc_radio(nn.Module):
+    def __init__(self, radio_fusion='concat', gate_radio=True, dropout=True,
+                 model_size_radio: str = 'small', n_classes=4, modalities=['T1', 'T2', 'T1Gd', 'FLAIR']):
+        super().__init__()
+        self.radio_fusion = radio_fusion
+        self.n_classes = n_classes
+        self.size_dict_radio = {"small": [1024, 256, 256], "big": [1024, 512, 384]}
+        self.modalities = modalities
+        in_dim, L, D = self.size_dict_radio[model_size_radio]
+        if len(modalities) > 1:
+            if radio_fusion == 'tensor':
+                self.radio_xfusion = XlinearFusion(dim=1024, scale_dim=64, mmhid1=1024, mmhid2=1024, skip=0)
+            elif radio_fusion == 'concat':
+                self.reduce_dim = nn.Linear(in_dim * len(modalities), in_dim)
+        attn_cls = Attn_Net_Gated if gate_radio else Attn_Net
+        self.attention_net_radio = nn.Sequential(
+            nn.Linear(in_dim, L), nn.ReLU(), nn.Dropout(0.25),
+            attn_cls(L=L, D=D, dropout=dropout, n_classes=1))
+        self.classifier = nn.Linear(L, n_classes)
+        initialize_weights(self)
+        self.bag_group = None
+
+    def relocate(self):
+        device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+        if len(self.modalities) > 1:
+            if self.radio_fusion == 'tensor':
+                self.radio_xfusion = self.radio_xfusion.to(device)
+            elif self.radio_fusion == 'concat':
+                self.reduce_dim = self.reduce_dim.to(device)
+        self.attention_net_radio = self.attention_net_radio.to(device)
+        self.classifier = self.classifier.to(device)
+
+    def forward(self, h, return_features=False, attention_only=False):
+        pass
+
+
+class MIL_Attention_fc_surv_radio(MIL_Attention_fc_radio):
+    def __init__(self, radio_fusion='concat', gate_radio=True, dropout=True,
+                 model_size_radio: str = 'small', n_classes=4, modalities=['T1', 'T2', 'T1Gd', 'FLAIR']):
+        # the reference pins model_size_radio to 'small' regardless of the argument (:70)
+        super().__init__(radio_fusion=radio_fusion, gate_radio=gate_radio, model_size_radio='small',
+                         dropout=dropout, n_classes=n_classes, modalities=modalities)
+
+    def forward(self, **kwargs):
+        bags = [kwargs[m] for m in self.modalities]
+        if len(bags) > 1:
+            if self.radio_fusion == 'concat':
+                x = SegmentedLinearBf16.apply(self.reduce_dim.weight, self.reduce_dim.bias, *bags)
+            else:
+                # radio_fusion='tensor' is dead code in the reference (calls a missing attribute,
+                # SURVEY.md App. B-3)
+                raise NotImplementedError("radio_fusion='tensor' cannot run in the reference either")
+        else:
+            x = bags[0]
+        A_raw, M = AmilBranch.pooled(self.attention_net_radio, x, self.training, self.bag_group)
+        if kwargs.get('attention_only'):
+            return A_raw
+        if kwargs.get('return_features'):
+            return M
+        if kwargs.get('return_attention'):
+            return A_raw
+        hazards, S, Y_hat = HazardHead.apply(M, self.classifier.weight, self.classifier.bias)
+        return hazards, S, Y_hat, A_raw

@@ -1,0 +1,136 @@
+"""End-to-end three-modality model (radiology AMIL + pathology AMIL + genomic SNN -> Kronecker or
+concat fusion -> discrete-hazard head) — drop-in for models/model_mm_attention_mil.py
+(constructor :19-98,:118-126; forward :128-200).
+
+The reference class cannot be instantiated or run as shipped (SURVEY.md App. B-1,2,3,6). This
+mirror keeps the constructor signature, attribute names and state_dict keys the reference
+*defines*, and implements the evidently intended semantics:
+  * ``gate_omic`` is accepted and ignored (the base class has no such parameter, :19-23 vs :124);
+  * ``size_path`` (:83) is read as ``size_WSI``;
+  * ``self.xfusion`` (:141) is read as ``self.radio_xfusion`` — and since that branch only ever
+    used slice 0 of each modality it stays unsupported (``radio_fusion='tensor'`` raises);
+  * ``return_features`` returns the fused embedding ``MM`` (the reference references undefined
+    names there, :196-198).
+"""
+import torch
+import torch.nn as nn
+
+from .._lib import ACT_NONE, ACT_RELU
+from ..autograd import Dense, HazardHead, SegmentedLinearBf16
+from ..utils.utils import initialize_weights
+from .model_modules import (AmilBranch, Attn_Net, Attn_Net_Gated, SNN_Block, XlinearFusion,
+                            snn_block_forward)
+
+
+class MM_MIL_Attention_fc(nn.Module):
+    def __init__(self, input_dim: int = 80, radio_fusion='concat', fusion='tensor',
+                 gate=True, gate_path=True, gate_radio=True, dropout=True,
+                 model_size_radio: str = 'small', model_size_wsi: str = 'small',
+                 model_size_omic: str = 'small', n_classes=4,
+                 modalities=['T1', 'T2', 'T1Gd', 'FLAIR'], mode='radio_path_omic'):
+        super().__init__()
+        self.radio_fusion, self.fusion, self.n_classes = radio_fusion, fusion, n_classes
+        self.size_dict_radio = {"small": [1024, 256, 256], "big": [1024, 256, 384]}
+        self.size_dict_WSI = {"small": [1024, 256, 256], "big": [1024, 256, 384]}
+        self.size_dict_omic = {'small': [256, 256], 'big': [1024, 256]}
+        self.modalities, self.mode = modalities, mode
+
+        size_omic = self.size_dict_omic[model_size_omic]
+        blocks = [SNN_Block(dim1=input_dim, dim2=size_omic[0])]
+        for i in range(len(size_omic) - 1):
+            blocks.append(SNN_Block(dim1=size_omic[i], dim2=size_omic[i + 1], dropout=0.25))
+        self.fc_omic = nn.Sequential(*blocks)
+
+        size_radio = self.size_dict_radio[model_size_radio]
+        attn_r = Attn_Net_Gated if gate_radio else Attn_Net
+        self.attention_net_radio = nn.Sequential(
+            nn.Linear(size_radio[0], size_radio[1]), nn.ReLU(), nn.Dropout(0.25),
+            attn_r(L=size_radio[1], D=size_radio[2], dropout=dropout, n_classes=1))
+        if radio_fusion == 'tensor':
+            self.radio_xfusion = XlinearFusion(dim=1024, scale_dim=64, mmhid1=1024, mmhid2=1024, skip=0)
+        elif radio_fusion == 'concat':
+            self.reduce_dim = nn.Linear(size_radio[0] * len(modalities), size_radio[0])
+
+        size_WSI = self.size_dict_WSI[model_size_wsi]
+        attn_p = Attn_Net_Gated if gate_path else Attn_Net
+        self.attention_net_WSI = nn.Sequential(
+            nn.Linear(size_WSI[0], size_WSI[1]), nn.ReLU(), nn.Dropout(0.25),
+            attn_p(L=size_WSI[1], D=size_WSI[2], dropout=dropout, n_classes=1))
+
+        widths = {'radio': size_radio[1], 'path': size_WSI[1], 'omic': size_omic[1]}
+        present = [k for k in ('radio', 'path', 'omic') if k in mode]
+        classifier_size = sum(widths[k] for k in present)
+        if fusion == 'tensor':
+            self.mm = XlinearFusion(dim=256, scale_dim=16, mmhid1=512, mmhid2=512,
+                                    num_modalities=len(present), gate=gate, skip=1)
+            self.classifier = nn.Sequential(nn.Linear(512, 256), nn.ReLU(), nn.Dropout(0.25),
+                                            nn.Linear(256, n_classes))
+        elif fusion == 'concat':
+            self.classifier = nn.Linear(classifier_size, n_classes)
+        initialize_weights(self)
+
+    def relocate(self):
+        device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+        self.to(device)
+
+    def forward(self, h, return_features=False, attention_only=False):
+        pass
+
+
+class MM_MIL_Attention_fc_surv(MM_MIL_Attention_fc):
+    def __init__(self, input_dim: int = 80, radio_fusion: str = 'concat', fusion: str = 'tensor',
+                 gate=True, gate_path=True, gate_omic=True, gate_radio=True,
+                 model_size_radio="small", model_size_wsi: str = 'small', model_size_omic='small',
+                 dropout=False, n_classes=4, mode='radio_path_omic'):
+        super().__init__(input_dim=input_dim, radio_fusion=radio_fusion, fusion=fusion, gate=gate,
+                         gate_path=gate_path, gate_radio=gate_radio, model_size_radio='small',
+                         model_size_wsi=model_size_wsi, model_size_omic=model_size_omic,
+                         dropout=dropout, n_classes=n_classes, mode=mode)
+
+    def forward(self, **kwargs):
+        A_raw = {}
+        emb = {}
+        if 'radio' in self.mode:
+            bags = [kwargs[m] for m in self.modalities]
+            if len(bags) > 1:
+                if self.radio_fusion != 'concat':
+                    raise NotImplementedError("radio_fusion='tensor' cannot run in the reference either")
+                x = SegmentedLinearBf16.apply(self.reduce_dim.weight, self.reduce_dim.bias, *bags)
+            else:
+                x = bags[0]
+            A_raw['radiology'], emb['radio'] = AmilBranch.pooled(self.attention_net_radio, x, self.training)
+        if 'path' in self.mode:
+            A_raw['pathology'], emb['path'] = AmilBranch.pooled(self.attention_net_WSI,
+                                                                kwargs['path_features'], self.training)
+        if 'omic' in self.mode:
+            o = kwargs['genomic_features']
+            o = o.unsqueeze(0) if o.dim() == 1 else o
+            for block in self.fc_omic:
+                o = snn_block_forward(block, o)
+            emb['omic'] = o
+        # fusion order of the reference (:167-186): (radio, path), (radio, omic), (omic, path),
+        # (radio, path, omic)
+        has = lambda k: k in emb
+        if has('radio') and has('path') and has('omic'):
+            order = ['radio', 'path', 'omic']
+        elif has('radio') and has('path'):
+            order = ['radio', 'path']
+        elif has('radio') and has('omic'):
+            order = ['radio', 'omic']
+        elif has('omic') and has('path'):
+            order = ['omic', 'path']
+        else:
+            raise NotImplementedError(f"mode {self.mode!r} needs at least two modalities")
+        vs = [emb[k] for k in order]
+        if self.fusion == 'tensor':
+            MM = self.mm(v_list=vs)
+            hid = Dense.apply(MM, self.classifier[0].weight, self.classifier[0].bias, ACT_RELU)
+            hid = self.classifier[2](hid)
+            Wk, bk = self.classifier[3].weight, self.classifier[3].bias
+        else:
+            MM = torch.cat(vs, dim=1)
+            hid, Wk, bk = MM, self.classifier.weight, self.classifier.bias
+        if kwargs.get('return_features'):
+            return MM
+        hazards, S, Y_hat = HazardHead.apply(hid, Wk, bk)
+        return hazards, S, Y_hat, A_raw

@@ -1,0 +1,176 @@
+"""Building blocks with the reference's names, constructor signatures and state_dict keys
+(reference: models/model_modules.py:64-178), executing on the libmmf_b200 kernels.
+
+The parameter containers are ordinary ``nn.Linear`` modules created in the same order as the
+reference creates them, so a seeded construction consumes the RNG identically and checkpoints load
+either way.  ``forward`` never calls ``nn.Linear.forward``: it hands the parameters to the fused
+kernels through :mod:`multimodalfusion_b200.autograd`.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from ..autograd import Dense, KronEncoder
+from .._lib import ACT_NONE, ACT_RELU, ACT_SELU, ACT_SIGMOID, ACT_TANH
+
+
+def _seed_from_torch() -> int:
+    """Per-call dropout seed drawn from torch's CPU generator (reproducible under manual_seed)."""
+    return int(torch.randint(0, 2 ** 62, (1,)).item())
+
+
+def SNN_Block(dim1, dim2, dropout=0.25):
+    """Linear -> SELU -> AlphaDropout container (models/model_modules.py:64-68); executed by
+    :func:`snn_block_forward`."""
+    return nn.Sequential(nn.Linear(dim1, dim2), nn.SELU(), nn.AlphaDropout(p=dropout, inplace=False))
+
+
+def snn_block_forward(block: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
+    y = Dense.apply(x, block[0].weight, block[0].bias, ACT_SELU)
+    if block.training and block[2].p > 0:
+        y = F.alpha_dropout(y, block[2].p, True)  # elementwise mask only; the GEMM+SELU is ours
+    return y
+
+
+class _AttnBase(nn.Module):
+    def amil_weights(self):
+        """(Wa, ba, Wb, bb, wc, bc) with Wb = bb = None for the un-gated net."""
+        raise NotImplementedError
+
+    def forward(self, x):
+        """Stand-alone use (scores for an already computed h): returns (A [N, n_classes], x)."""
+        Wa, ba, Wb, bb, wc, bc = self.amil_weights()
+        a = Dense.apply(x, Wa, ba, ACT_TANH)
+        if self.training and self.use_dropout:
+            a = F.dropout(a, 0.25, True)
+        if Wb is not None:
+            b = Dense.apply(x, Wb, bb, ACT_SIGMOID)
+            if self.training and self.use_dropout:
+                b = F.dropout(b, 0.25, True)
+            a = a * b
+        return Dense.apply(a, wc, bc, ACT_NONE), x
+
+
+class Attn_Net(_AttnBase):
+    """Un-gated attention net: Linear(L,D) -> Tanh [-> Dropout] -> Linear(D,n_classes)
+    (models/model_modules.py:70-85; keys ``module.0.*`` and ``module.2.*`` / ``module.3.*``)."""
+
+    def __init__(self, L=1024, D=256, dropout=False, n_classes=1):
+        super().__init__()
+        layers = [nn.Linear(L, D), nn.Tanh()]
+        if dropout:
+            layers.append(nn.Dropout(0.25))
+        layers.append(nn.Linear(D, n_classes))
+        self.module = nn.Sequential(*layers)
+        self.use_dropout = bool(dropout)
+
+    def amil_weights(self):
+        first, last = self.module[0], self.module[-1]
+        return first.weight, first.bias, None, None, last.weight, last.bias
+
+
+class Attn_Net_Gated(_AttnBase):
+    """Gated attention net: tanh(Wa h) ⊙ sigmoid(Wb h) -> Linear(D,n_classes)
+    (models/model_modules.py:87-110; keys ``attention_{a,b}.0.*``, ``attention_c.*``)."""
+
+    def __init__(self, L=1024, D=256, dropout=False, n_classes=1):
+        super().__init__()
+        branch_a = [nn.Linear(L, D), nn.Tanh()]
+        branch_b = [nn.Linear(L, D), nn.Sigmoid()]
+        if dropout:
+            branch_a.append(nn.Dropout(0.25))
+            branch_b.append(nn.Dropout(0.25))
+        self.attention_a = nn.Sequential(*branch_a)
+        self.attention_b = nn.Sequential(*branch_b)
+        self.attention_c = nn.Linear(D, n_classes)
+        self.use_dropout = bool(dropout)
+
+    def amil_weights(self):
+        return (self.attention_a[0].weight, self.attention_a[0].bias, self.attention_b[0].weight,
+                self.attention_b[0].bias, self.attention_c.weight, self.attention_c.bias)
+
+
+class AmilBranch:
+    """Mixin-style helper: runs ``nn.Sequential(Linear(1024,L), ReLU, Dropout, Attn_Net*)`` as ONE
+    fused kernel and caches the bf16 / packed weight copies until a parameter changes."""
+
+    @staticmethod
+    def pooled(seq: nn.Sequential, x: torch.Tensor, training: bool, group=None):
+        from ..autograd import AmilPool
+        fc, attn = seq[0], seq[3]
+        Wa, ba, Wb, bb, wc, bc = attn.amil_weights()
+        if wc.shape[0] != 1:
+            raise NotImplementedError("fused attention-MIL pooling supports n_classes=1 attention heads")
+        params = (fc.weight, fc.bias, Wa, ba, Wb, bb, wc, bc)
+        key = tuple((p.data_ptr(), p._version) for p in params if p is not None)
+        cache = getattr(seq, "_mmf_prep", None)
+        if cache is None or cache[0] != key:
+            cache = (key, ops.prepare_amil_weights(*params))
+            seq._mmf_prep = cache
+        prep = cache[1]
+        flags = ops.amil_flags(prep.gated, dropout_h=training, dropout_attn=training and attn.use_dropout)
+        seed = _seed_from_torch() if training else 0
+        return AmilPool.apply(x, *params, prep, flags, seed, group)
+
+
+class XlinearFusion(nn.Module):
+    """Kronecker ("Xlinear") late fusion (models/model_modules.py:113-178): per-modality gated
+    reduction to ``dim//scale_dim`` (+1 constant), outer product across modalities, two encoders
+    with an optional skip of the raw embeddings. The outer product is formed inside the
+    ``encoder1`` kernel and never materialised in the forward."""
+
+    def __init__(self, skip=1, use_bilinear=0, gate=1, dim=256, scale_dim=16, num_modalities=4,
+                 mmhid1=256, mmhid2=256, dropout_rate=0.25):
+        super().__init__()
+        self.skip, self.use_bilinear, self.gate, self.num_modalities = skip, use_bilinear, gate, num_modalities
+        full, small = dim, dim // scale_dim
+        skip_dim = full * num_modalities if skip else 0
+        blocks = []
+        for _ in range(num_modalities):
+            lin_h = nn.Sequential(nn.Linear(full, small), nn.ReLU())
+            lin_z = (nn.Bilinear(full, full, small) if use_bilinear
+                     else nn.Sequential(nn.Linear(full * num_modalities, small)))
+            lin_o = nn.Sequential(nn.Linear(small, small), nn.ReLU(), nn.Dropout(p=dropout_rate))
+            blocks.append(nn.ModuleList([lin_h, lin_z, lin_o] if gate else [lin_h, lin_o]))
+        self.reduce = nn.ModuleList(blocks)
+        self.post_fusion_dropout = nn.Dropout(p=dropout_rate)
+        self.encoder1 = nn.Sequential(nn.Linear((small + 1) ** num_modalities, mmhid1), nn.ReLU(),
+                                      nn.Dropout(p=dropout_rate))
+        self.encoder2 = nn.Sequential(nn.Linear(mmhid1 + skip_dim, mmhid2), nn.ReLU(),
+                                      nn.Dropout(p=dropout_rate))
+
+    def forward(self, v_list: list):
+        if self.use_bilinear:
+            raise NotImplementedError("use_bilinear=1 (nn.Bilinear gate) is not on the accelerated path")
+        if not self.gate:
+            # the reference indexes reduce[i][2] unconditionally (models/model_modules.py:163), so
+            # gate=0 cannot run there either
+            raise NotImplementedError("gate=0 is not runnable in the reference (IndexError on reduce[i][2])")
+        if len(v_list) not in (2, 3):
+            raise NotImplementedError("Kronecker fusion kernel supports 2 or 3 modalities")
+        v_list = [v.float() for v in v_list]
+        v_cat = torch.cat(v_list, dim=1)
+        o_list = []
+        for v, blk in zip(v_list, self.reduce):
+            h = Dense.apply(v, blk[0][0].weight, blk[0][0].bias, ACT_RELU)
+            z = Dense.apply(v_cat, blk[1][0].weight, blk[1][0].bias, ACT_SIGMOID)
+            o = Dense.apply(z * h, blk[2][0].weight, blk[2][0].bias, ACT_RELU)
+            o = blk[2][2](o)
+            o_list.append(torch.cat([o, torch.ones(o.shape[0], 1, dtype=o.dtype, device=o.device)], dim=1))
+        if self.training and self.post_fusion_dropout.p > 0:
+            # dropout on the fused tensor needs it materialised: train-mode only (eval never does)
+            fused = o_list[0]
+            for o in o_list[1:]:
+                fused = (fused.unsqueeze(2) * o.unsqueeze(1)).flatten(1)
+            fused = self.post_fusion_dropout(fused)
+            out = Dense.apply(fused, self.encoder1[0].weight, self.encoder1[0].bias, ACT_RELU)
+        else:
+            out = KronEncoder.apply(self.encoder1[0].weight, self.encoder1[0].bias, *o_list)
+        out = self.encoder1[2](out)
+        if self.skip:
+            out = torch.cat([out] + v_list, dim=1)
+        out = Dense.apply(out, self.encoder2[0].weight, self.encoder2[0].bias, ACT_RELU)
+        return self.encoder2[2](out)

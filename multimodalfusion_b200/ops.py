@@ -1,0 +1,335 @@
+"""Torch-facing wrappers over the C ABI: tensors in, tensors out, all on the current stream.
+
+PyTorch is used here for device memory, streams and autograd bookkeeping only; every FLOP of
+the path runs in the kernels of ``libmmf_b200.so``.  All functions raise on CPU tensors — there
+is no fallback implementation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_NONE, ACT_RELU, ACT_SELU, ACT_SIGMOID, ACT_TANH, MMF_DROPOUT_ATTN,
+                   MMF_DROPOUT_H, MMF_GATED, MMF_NEED_DX, AmilGrads, AmilWeights, check, lib)
+
+IN_FEATURES = 1024
+TILE_ROWS = 128
+
+
+def _require_cuda(*tensors: Optional[torch.Tensor]) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "multimodalfusion_b200 kernels need CUDA tensors (sm_100a); there is no CPU fallback. "
+                "Move the model with .relocate()/.cuda() and the inputs with .cuda().")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# formats
+# ------------------------------------------------------------------------------------------------
+def to_bf16(x: torch.Tensor) -> torch.Tensor:
+    """fp32 -> bf16 (RNE) with the library's cast kernel; bf16 input is returned as is."""
+    _require_cuda(x)
+    if x.dtype == torch.bfloat16:
+        return x.contiguous()
+    x = _f32c(x)
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    check(lib().mmf_cast_f32_to_bf16(_p(x), _p(out), x.numel(), _stream()), "mmf_cast_f32_to_bf16")
+    return out
+
+
+@dataclass
+class AmilPrepared:
+    """bf16 / packed copies of the fc + attention-net weights, rebuilt when parameters change."""
+    L: int
+    D: int
+    gated: bool
+    W1: torch.Tensor          # bf16 [L,1024]
+    b1: torch.Tensor          # f32 [L]
+    Wab: torch.Tensor         # bf16 [2D,L] / [D,L]
+    Wab_packed: torch.Tensor  # bf16 same shape, chunk-interleaved rows
+    bab: torch.Tensor         # f32 [2D] / [D]
+    wc: torch.Tensor          # f32 [D]
+    bc: torch.Tensor          # f32 [1]
+
+    def struct(self) -> AmilWeights:
+        return AmilWeights(_p(self.W1), _p(self.b1), _p(self.Wab), _p(self.Wab_packed), _p(self.bab),
+                           _p(self.wc), _p(self.bc))
+
+
+def prepare_amil_weights(W1, b1, Wa, ba, Wb, bb, wc, bc) -> AmilPrepared:
+    """Wa/ba are the tanh branch (or the only branch when Wb is None = un-gated Attn_Net)."""
+    _require_cuda(W1, Wa, wc)
+    gated = Wb is not None
+    L, D = W1.shape[0], Wa.shape[0]
+    if W1.shape[1] != IN_FEATURES:
+        raise ValueError(f"fc input width must be {IN_FEATURES}, got {W1.shape[1]}")
+    W1b = to_bf16(W1)
+    if gated:
+        Wab32 = torch.cat([_f32c(Wa), _f32c(Wb)], dim=0)
+        bab = torch.cat([_f32c(ba), _f32c(bb)], dim=0)
+    else:
+        Wab32, bab = _f32c(Wa), _f32c(ba)
+    Wab = to_bf16(Wab32)
+    packed = torch.empty_like(Wab)
+    check(lib().mmf_pack_wab(_p(Wab), _p(packed), L, D, int(gated), _stream()), "mmf_pack_wab")
+    return AmilPrepared(L, D, gated, W1b, _f32c(b1), Wab, packed, bab, _f32c(wc).reshape(-1),
+                        _f32c(bc).reshape(-1))
+
+
+# ------------------------------------------------------------------------------------------------
+# fused attention-MIL forward / backward
+# ------------------------------------------------------------------------------------------------
+def amil_flags(gated: bool, dropout_h: bool = False, dropout_attn: bool = False, need_dx: bool = False) -> int:
+    return ((MMF_GATED if gated else 0) | (MMF_DROPOUT_H if dropout_h else 0)
+            | (MMF_DROPOUT_ATTN if dropout_attn else 0) | (MMF_NEED_DX if need_dx else 0))
+
+
+def amil_partials(x: torch.Tensor, w: AmilPrepared, flags: int, seed: int = 0,
+                  h_stash: Optional[torch.Tensor] = None):
+    """Runs the fused tile kernel: returns (A_raw [N] f32, partials [tiles, L+2] f32)."""
+    _require_cuda(x)
+    if x.dtype != torch.bfloat16 or x.dim() != 2 or x.shape[1] != IN_FEATURES or x.stride(1) != 1:
+        raise ValueError("x must be a bf16 [N,1024] tensor with unit inner stride")
+    N = x.shape[0]
+    if N == 0:
+        raise ValueError("empty bag")
+    tiles = (N + TILE_ROWS - 1) // TILE_ROWS
+    A_raw = torch.empty(N, dtype=torch.float32, device=x.device)
+    partials = torch.empty(tiles, w.L + 2, dtype=torch.float32, device=x.device)
+    ws = w.struct()
+    check(lib().mmf_amil_fwd(_p(x), N, x.stride(0), C.byref(ws), w.L, w.D, flags, seed, _p(A_raw),
+                             _p(partials), _p(h_stash), _stream()), "mmf_amil_fwd")
+    return A_raw, partials
+
+
+def amil_combine(partials: torch.Tensor, L: int, normalize: bool = True):
+    """normalize: (M [L], ml [2]);  else one (L+2) partial row (m, l, acc)."""
+    _require_cuda(partials)
+    partials = partials.contiguous()
+    n = partials.shape[0]
+    if normalize:
+        M = torch.empty(L, dtype=torch.float32, device=partials.device)
+        ml = torch.empty(2, dtype=torch.float32, device=partials.device)
+        check(lib().mmf_amil_combine(_p(partials), n, L, 1, _p(M), _p(ml), _stream()), "mmf_amil_combine")
+        return M, ml
+    out = torch.empty(L + 2, dtype=torch.float32, device=partials.device)
+    check(lib().mmf_amil_combine(_p(partials), n, L, 0, _p(out), None, _stream()), "mmf_amil_combine")
+    return out
+
+
+def amil_forward(x: torch.Tensor, w: AmilPrepared, flags: int, seed: int = 0):
+    A_raw, partials = amil_partials(x, w, flags, seed)
+    M, ml = amil_combine(partials, w.L, True)
+    return A_raw, M, ml
+
+
+def amil_backward(x: torch.Tensor, w: AmilPrepared, flags: int, seed: int, A_raw, ml, M, dM,
+                  dA_raw=None, grads: Optional[dict] = None):
+    """Returns dict(dW1, db1, dWab, dbab, dwc, dbc[, dx]); accumulates into `grads` if given."""
+    _require_cuda(x, dM)
+    N = x.shape[0]
+    dev = x.device
+    KD = (2 if w.gated else 1) * w.D
+    if grads is None:
+        grads = dict(
+            dW1=torch.zeros(w.L, IN_FEATURES, dtype=torch.float32, device=dev),
+            db1=torch.zeros(w.L, dtype=torch.float32, device=dev),
+            dWab=torch.zeros(KD, w.L, dtype=torch.float32, device=dev),
+            dbab=torch.zeros(KD, dtype=torch.float32, device=dev),
+            dwc=torch.zeros(w.D, dtype=torch.float32, device=dev),
+            dbc=torch.zeros(1, dtype=torch.float32, device=dev),
+        )
+    need_dx = bool(flags & MMF_NEED_DX)
+    dx = torch.empty(N, IN_FEATURES, dtype=torch.bfloat16, device=dev) if need_dx else None
+    nbytes = lib().mmf_amil_bwd_workspace_bytes(N, w.L, w.D, flags)
+    ws_buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+    off = (-ws_buf.data_ptr()) % 1024
+    g = AmilGrads(_p(grads["dW1"]), _p(grads["db1"]), _p(grads["dWab"]), _p(grads["dbab"]),
+                  _p(grads["dwc"]), _p(grads["dbc"]))
+    wst = w.struct()
+    dM = _f32c(dM).reshape(-1)
+    dA = None if dA_raw is None else _f32c(dA_raw).reshape(-1)
+    check(lib().mmf_amil_bwd(_p(x), N, x.stride(0), C.byref(wst), w.L, w.D, flags, seed, _p(A_raw), _p(ml),
+                             _p(M), _p(dM), _p(dA), None, C.byref(g), _p(dx), ws_buf.data_ptr() + off,
+                             nbytes, _stream()), "mmf_amil_bwd")
+    if need_dx:
+        grads["dx"] = dx
+    return grads
+
+
+# ------------------------------------------------------------------------------------------------
+# bf16 tensor-core linear (radio reduce_dim) and its weight gradient
+# ------------------------------------------------------------------------------------------------
+def linear_bf16(segs: Sequence[torch.Tensor], W_bf16: torch.Tensor, bias: Optional[torch.Tensor],
+                out_dtype=torch.bfloat16) -> torch.Tensor:
+    """y[M,N] = cat(segs, dim=1) @ W^T + bias, segments are bf16 [M,Kseg] (never concatenated)."""
+    _require_cuda(*segs)
+    M, Kseg = segs[0].shape
+    N = W_bf16.shape[0]
+    for s in segs:
+        if s.dtype != torch.bfloat16 or s.shape != (M, Kseg) or s.stride(1) != 1 or s.stride(0) != segs[0].stride(0):
+            raise ValueError("segments must be bf16 [M,Kseg] with identical strides")
+    out = torch.empty(M, N, dtype=out_dtype, device=segs[0].device)
+    arr = _lib.ptr_array([s.data_ptr() for s in segs])
+    ob, of = (_p(out), None) if out_dtype == torch.bfloat16 else (None, _p(out))
+    check(lib().mmf_linear_bf16(arr, len(segs), M, Kseg, segs[0].stride(0), _p(W_bf16), _p(bias), N, ob, of,
+                                N, _stream()), "mmf_linear_bf16")
+    return out
+
+
+def linear_bf16_wgrad(dY: torch.Tensor, segs: Sequence[torch.Tensor], dW: torch.Tensor,
+                      db: Optional[torch.Tensor]) -> None:
+    """dW[N, sum Kseg] += dY^T cat(segs); db[N] += colsum(dY).  dY bf16 [M,N]."""
+    _require_cuda(dY, dW)
+    M, N = dY.shape
+    Kseg = segs[0].shape[1]
+    arr = _lib.ptr_array([s.data_ptr() for s in segs])
+    check(lib().mmf_linear_bf16_wgrad(_p(dY), M, N, dY.stride(0), arr, len(segs), Kseg, segs[0].stride(0),
+                                      _p(dW), _p(db), None, 0, _stream()), "mmf_linear_bf16_wgrad")
+
+
+# ------------------------------------------------------------------------------------------------
+# small fp32 kernels
+# ------------------------------------------------------------------------------------------------
+def dense_fwd(x, W, b, act: int) -> torch.Tensor:
+    _require_cuda(x, W)
+    x, W = _f32c(x), _f32c(W)
+    B, in_dim = x.shape
+    out = torch.empty(B, W.shape[0], dtype=torch.float32, device=x.device)
+    check(lib().mmf_dense_fwd(_p(x), in_dim, _p(W), _p(None if b is None else _f32c(b)), B, in_dim, W.shape[0],
+                              act, _p(out), W.shape[0], _stream()), "mmf_dense_fwd")
+    return out
+
+
+def dense_bwd(x, W, act: int, y, dy, need_dx=True, need_dw=True, need_db=True):
+    x, W, y, dy = _f32c(x), _f32c(W), _f32c(y), _f32c(dy)
+    B, in_dim = x.shape
+    out_dim = W.shape[0]
+    dx = torch.empty_like(x) if need_dx else None
+    dW = torch.zeros_like(W) if need_dw else None
+    db = torch.zeros(out_dim, dtype=torch.float32, device=x.device) if need_db else None
+    check(lib().mmf_dense_bwd(_p(x), in_dim, _p(W), B, in_dim, out_dim, act, _p(y), out_dim, _p(dy), out_dim,
+                              _p(dx), in_dim, 0, _p(dW), _p(db), _stream()), "mmf_dense_bwd")
+    return dx, dW, db
+
+
+def kron_enc_fwd(o_list, W, b) -> torch.Tensor:
+    o_list = [_f32c(o) for o in o_list]
+    _require_cuda(*o_list)
+    B, E = o_list[0].shape
+    H = W.shape[0]
+    out = torch.empty(B, H, dtype=torch.float32, device=W.device)
+    arr = _lib.ptr_array([o.data_ptr() for o in o_list])
+    check(lib().mmf_kron_enc_fwd(arr, len(o_list), E, B, _p(_f32c(W)), _p(_f32c(b)), H, _p(out), _stream()),
+          "mmf_kron_enc_fwd")
+    return out
+
+
+def kron_enc_bwd(o_list, W, out, dout):
+    o_list = [_f32c(o) for o in o_list]
+    W, out, dout = _f32c(W), _f32c(out), _f32c(dout)
+    B, E = o_list[0].shape
+    H = W.shape[0]
+    m = len(o_list)
+    d_o = [torch.empty_like(o) for o in o_list]
+    dW = torch.zeros_like(W)
+    db = torch.zeros(H, dtype=torch.float32, device=W.device)
+    nbytes = lib().mmf_kron_enc_workspace_bytes(m, E, B)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=W.device)
+    arr = _lib.ptr_array([o.data_ptr() for o in o_list])
+    darr = _lib.ptr_array([o.data_ptr() for o in d_o])
+    check(lib().mmf_kron_enc_bwd(arr, m, E, B, _p(W), H, _p(out), _p(dout), darr, _p(dW), _p(db), _p(ws),
+                                 nbytes, _stream()), "mmf_kron_enc_bwd")
+    return d_o, dW, db
+
+
+def hazard_head_fwd(M, Wk, bk):
+    _require_cuda(M, Wk)
+    M, Wk, bk = _f32c(M), _f32c(Wk), _f32c(bk)
+    B, Lin = M.shape
+    K = Wk.shape[0]
+    haz = torch.empty(B, K, dtype=torch.float32, device=M.device)
+    S = torch.empty_like(haz)
+    Y = torch.empty(B, 1, dtype=torch.int64, device=M.device)
+    check(lib().mmf_hazard_head_fwd(_p(M), B, Lin, _p(Wk), _p(bk), K, _p(haz), _p(S), _p(Y), _stream()),
+          "mmf_hazard_head_fwd")
+    return haz, S, Y
+
+
+def hazard_head_bwd(M, Wk, haz, S, d_haz, d_S):
+    M, Wk = _f32c(M), _f32c(Wk)
+    B, Lin = M.shape
+    K = Wk.shape[0]
+    dM = torch.empty_like(M)
+    dWk = torch.zeros_like(Wk)
+    dbk = torch.zeros(K, dtype=torch.float32, device=M.device)
+    check(lib().mmf_hazard_head_bwd(_p(M), B, Lin, _p(Wk), K, _p(haz), _p(S),
+                                    _p(None if d_haz is None else _f32c(d_haz)),
+                                    _p(None if d_S is None else _f32c(d_S)), _p(dM), _p(dWk), _p(dbk),
+                                    _stream()), "mmf_hazard_head_bwd")
+    return dM, dWk, dbk
+
+
+def nll_surv(hazards, S, Y, c, alpha: float, eps: float = 1e-7):
+    """Returns (loss [scalar tensor], d_hazards, d_S)."""
+    _require_cuda(hazards, S)
+    hazards, S = _f32c(hazards), _f32c(S)
+    B, K = hazards.shape
+    Y = Y.detach().reshape(-1).to(device=hazards.device, dtype=torch.int64).contiguous()
+    c = c.detach().reshape(-1).to(device=hazards.device, dtype=torch.float32).contiguous()
+    loss = torch.empty((), dtype=torch.float32, device=hazards.device)
+    dh, dS = torch.empty_like(hazards), torch.empty_like(S)
+    check(lib().mmf_nll_surv_fwd_bwd(_p(hazards), _p(S), _p(Y), _p(c), B, K, float(alpha), float(eps), _p(loss),
+                                     _p(dh), _p(dS), _stream()), "mmf_nll_surv_fwd_bwd")
+    return loss, dh, dS
+
+
+def cox(theta, times, c):
+    _require_cuda(theta)
+    theta = _f32c(theta).reshape(-1)
+    B = theta.numel()
+    times = torch.as_tensor(times).detach().reshape(-1).to(device=theta.device, dtype=torch.float32).contiguous()
+    c = torch.as_tensor(c).detach().reshape(-1).to(device=theta.device, dtype=torch.float32).contiguous()
+    loss = torch.empty((), dtype=torch.float32, device=theta.device)
+    dtheta = torch.empty_like(theta)
+    check(lib().mmf_cox_fwd_bwd(_p(theta), _p(times), _p(c), B, _p(loss), _p(dtheta), None, 0, _stream()),
+          "mmf_cox_fwd_bwd")
+    return loss, dtheta
+
+
+def ranking(risks, times, c, phi: str = "sigmoid", reduction: str = "mean"):
+    _require_cuda(risks)
+    risks = _f32c(risks).reshape(-1)
+    B = risks.numel()
+    times = torch.as_tensor(times).detach().reshape(-1).to(device=risks.device, dtype=torch.float32).contiguous()
+    c = torch.as_tensor(c).detach().reshape(-1).to(device=risks.device, dtype=torch.float32).contiguous()
+    loss = torch.empty((), dtype=torch.float32, device=risks.device)
+    dr = torch.empty_like(risks)
+    npairs = torch.empty((), dtype=torch.int64, device=risks.device)
+    nbytes = lib().mmf_ranking_workspace_bytes(B)
+    ws = torch.empty(nbytes + 8, dtype=torch.uint8, device=risks.device)
+    off = (-ws.data_ptr()) % 8
+    check(lib().mmf_ranking_fwd_bwd(_p(risks), _p(times), _p(c), B, {"sigmoid": 0, "relu": 1}[phi],
+                                    {"mean": 0, "sum": 1}[reduction], _p(loss), _p(dr), _p(npairs),
+                                    ws.data_ptr() + off, nbytes, _stream()), "mmf_ranking_fwd_bwd")
+    return loss, dr, npairs

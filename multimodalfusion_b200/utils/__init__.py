@@ -1,0 +1,3 @@
+from .loss_utils import (CoxSurvLoss, NLLSurvLoss, RankingNLLSurvLoss, RankingSurvLoss,  # noqa: F401
+                         nll_loss, ranking_loss)
+from .utils import init_max_weights, initialize_weights  # noqa: F401
