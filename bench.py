@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""Headline benchmark: patches/s of gated attention-MIL forward+backward on 16384 x 1024 bags
+(BASELINE.json metric), big preset (fc 1024->512, D=384), nll_surv head, train mode.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one bag: fused AMIL forward (+combine) -> discrete-hazard
+head -> nll_surv loss+grad -> head backward -> AMIL backward (gate / hidden / wgrad stages).
+  value : device-resident throughput — the step is captured once per bag in a CUDA graph and
+          replayed; inputs rotate over 8 distinct bags (256 MiB > L2) so x always comes from HBM.
+  e2e   : the public drop-in API (MIL_Attention_fc_surv_path + NLLSurvLoss + autograd) with pinned HOST
+          bags: H2D copy of every step's bag and D2H read of loss/risk inside the timed region.
+  N > 1 : cohort data-parallel (one bag per rank per step, weak scaling) with an NCCL all-reduce of the
+          flat fp32 gradient buffer every step; time = max over ranks.
+`--impl reference` times the CPU port of the reference step (oracle/cpu_reference.py) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.dont_write_bytecode = True
+
+N_BAG, L, D, K_CLASSES = 16384, 512, 384, 4
+N_BAGS = 8
+METRIC = "patches/sec (fwd+bwd) gated-AMIL @16k x 1024 bag"
+WORKLOAD = "path_attention_mil gated AMIL big (fc 1024->512, D=384), one 16384x1024 bf16 bag per step, nll_surv fwd+bwd, train mode"
+
+
+def flops_per_patch_algorithmic():
+    return 2 * (2 * 1024 * L + 6 * L * D)          # recompute excluded, no dX
+
+
+def flops_tile_kernel(n):
+    return 2 * n * (1024 * L + 2 * L * D)          # GEMM1 + GEMM2 executed by one tile-kernel launch
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc = index, None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+        return self
+
+    def __exit__(self, *exc):
+        self.result = None
+        if self.proc is None:
+            return
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [t.strip() for t in line.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if sm:
+            self.result = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                           "samples": len(sm)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured"
+    return 1590.0, 1400.0, 6650.0, "fallback"
+
+
+def run_reference(args):
+    """CPU arm: the port of the reference step on the host cores (rank 0 only)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from oracle.cpu_reference import time_cpu_steps
+    pps, dt, threads = time_cpu_steps(N_BAG, L, D, K_CLASSES, steps=args.steps, warmup=min(args.warmup, 3))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": pps, "unit": "patches/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": min(args.warmup, 3), "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "bag": [N_BAG, 1024], "preset": "big"},
+        "cpu_baseline": {"value": pps, "unit": "patches/s", "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} full steps (fwd+bwd) on one {N_BAG}x1024 bag, torch fp32 autograd"},
+        "e2e": {"value": pps, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import multimodalfusion_b200 as mmf
+    from multimodalfusion_b200 import ops
+    from multimodalfusion_b200.models import MIL_Attention_fc_surv_path
+    from multimodalfusion_b200.utils import NLLSurvLoss
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (sm_100a); there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    mmf.lib()  # fail loudly if the extension is missing
+
+    torch.manual_seed(0)
+    model = MIL_Attention_fc_surv_path(gate_path=True, model_size_wsi="big", dropout=False,
+                                       n_classes=K_CLASSES).to(dev).train()
+    fc, attn = model.attention_net_WSI[0], model.attention_net_WSI[3]
+    prep = ops.prepare_amil_weights(fc.weight, fc.bias, *attn.amil_weights())
+    Wk, bk = model.classifier.weight.detach(), model.classifier.bias.detach()
+    flags = ops.amil_flags(True, dropout_h=True)
+    seed = 0x5EED + rank
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    bags = [(0.5 * torch.randn(N_BAG, 1024, device=dev, generator=g).abs()).to(torch.bfloat16) for _ in range(N_BAGS)]
+    Y = torch.tensor([2], device=dev)
+    c = torch.tensor([0.0], device=dev)
+    KD = 2 * D
+    sizes = [L * 1024, L, KD * L, KD, D, 1, K_CLASSES * L, K_CLASSES]
+    flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+    views, o = [], 0
+    for s in sizes:
+        views.append(flat[o:o + s]); o += s
+    grads = dict(dW1=views[0].view(L, 1024), db1=views[1], dWab=views[2].view(KD, L), dbab=views[3], dwc=views[4],
+                 dbc=views[5])
+    loss_buf = torch.zeros((), device=dev)
+    LAUNCHES_PER_STEP = 15  # tile, combine, head, nll, 3 head-bwd, tile-bwd, 3 reduces, dU gemm, reduce, 2 wgrad
+
+    def step(x):
+        flat.zero_()
+        A_raw, parts = ops.amil_partials(x, prep, flags, seed)
+        M, ml = ops.amil_combine(parts, L, True)
+        haz, S, _ = ops.hazard_head_fwd(M.view(1, -1), Wk, bk)
+        loss, dh, dS = ops.nll_surv(haz, S, Y, c, 0.0)
+        dM, dWk, dbk = ops.hazard_head_bwd(M.view(1, -1), Wk, haz, S, dh, dS)
+        ops.amil_backward(x, prep, flags, seed, A_raw, ml, M, dM.view(-1), grads=grads)
+        views[6].copy_(dWk.view(-1)); views[7].copy_(dbk)
+        loss_buf.copy_(loss)
+
+    # warm up eagerly (configures kernels), then capture one graph per bag
+    for i in range(2):
+        step(bags[i % N_BAGS])
+    torch.cuda.synchronize()
+    graphs = []
+    for i in range(N_BAGS):
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            step(bags[i])
+        graphs.append(gr)
+
+    def run_steps(n, first=0):
+        for i in range(n):
+            graphs[(first + i) % N_BAGS].replay()
+            if world > 1:
+                dist.all_reduce(flat)
+
+    run_steps(max(args.warmup, 3))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        torch.cuda.synchronize()
+        ev0.record()
+        run_steps(args.steps, first=args.warmup)
+        ev1.record()
+        torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    ms_per_step = ms / args.steps
+    value = world * N_BAG / (ms_per_step * 1e-3)
+    assert torch.isfinite(loss_buf).item()
+
+    # ---- e2e through the public drop-in API with pinned host bags ---------------------------------
+    loss_fn = NLLSurvLoss(alpha=0.0)
+    host_bags = [b.cpu().pin_memory() for b in bags[:4]]
+    stage = [torch.empty_like(bags[0]) for _ in range(2)]
+    copy_stream = torch.cuda.Stream()
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def prefetch(i):
+        buf = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[buf])
+            stage[buf].copy_(host_bags[i % len(host_bags)], non_blocking=True)
+            ready[buf].record(copy_stream)
+
+    def e2e_steps(n):
+        last = None
+        for b in range(2):
+            consumed[b].record()
+        prefetch(0)
+        for i in range(n):
+            buf = i % 2
+            if i + 1 < n:
+                prefetch(i + 1)
+            torch.cuda.current_stream().wait_event(ready[buf])
+            hazards, S, Y_hat, A_raw = model(path_features=stage[buf])
+            loss = loss_fn(hazards=hazards, S=S, Y=Y, c=c)
+            model.zero_grad(set_to_none=True)
+            loss.backward()
+            consumed[buf].record()
+            risk = -torch.sum(S, dim=1)
+            last = (loss.item(), risk.detach().cpu().numpy())   # the reference reads both every step
+        return last
+
+    e2e_steps(3)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    n_e2e = max(args.steps // 2, 5)
+    ev0.record()
+    e2e_steps(n_e2e)
+    ev1.record()
+    torch.cuda.synchronize()
+    e2e_ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = t.item()
+    e2e_value = world * N_BAG * n_e2e / (e2e_ms * 1e-3)
+
+    # ---- per-kernel timing for the roofline (rank 0) -----------------------------------------------
+    roof = cpu_base = None
+    kernels = {}
+    if rank == 0:
+        peak_burst, peak_sust, hbm, src = load_peaks()
+        A_raw, parts = ops.amil_partials(bags[0], prep, flags, seed)
+        M, ml = ops.amil_combine(parts, L, True)
+        dM = torch.randn(L, device=dev) * 0.1
+        nbytes = mmf.lib().mmf_amil_bwd_workspace_bytes(N_BAG, L, D, flags)
+        wsbuf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+        wsp = wsbuf.data_ptr() + ((-wsbuf.data_ptr()) % 1024)
+        import ctypes as C
+        from multimodalfusion_b200._lib import AmilGrads, check
+        gstruct = AmilGrads(*[grads[k].data_ptr() for k in ("dW1", "db1", "dWab", "dbab", "dwc", "dbc")])
+        wst = prep.struct()
+        st = torch.cuda.current_stream().cuda_stream
+        lib = mmf.lib()
+
+        def t_fwd(x):
+            ops.amil_partials(x, prep, flags, seed)
+
+        def t_gate(x):
+            check(lib.mmf_amil_bwd_gate(x.data_ptr(), N_BAG, 1024, C.byref(wst), L, D, flags, seed, A_raw.data_ptr(),
+                                        ml.data_ptr(), M.data_ptr(), dM.data_ptr(), None, C.byref(gstruct), wsp,
+                                        nbytes, st))
+
+        def t_hidden(x):
+            check(lib.mmf_amil_bwd_hidden(x.data_ptr(), N_BAG, 1024, C.byref(wst), L, D, flags, A_raw.data_ptr(),
+                                          ml.data_ptr(), dM.data_ptr(), C.byref(gstruct), wsp, nbytes, st))
+
+        def t_wgrad(x):
+            check(lib.mmf_amil_bwd_wgrad(x.data_ptr(), N_BAG, 1024, C.byref(wst), L, D, flags, C.byref(gstruct), None,
+                                         wsp, nbytes, st))
+
+        for name, fn in (("amil_tile_fwd", t_fwd), ("bwd_gate", t_gate), ("bwd_hidden", t_hidden), ("bwd_wgrad", t_wgrad)):
+            for i in range(3):
+                fn(bags[i % N_BAGS])
+            reps = 16
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+            torch.cuda.synchronize()
+            for i in range(reps):
+                evs[i][0].record(); fn(bags[i % N_BAGS]); evs[i][1].record()
+            torch.cuda.synchronize()
+            kernels[name] = statistics.median(a.elapsed_time(b) for a, b in evs) * 1e3  # us
+        t_tile = kernels["amil_tile_fwd"]
+        achieved = flops_tile_kernel(N_BAG) / (t_tile * 1e-6) / 1e12
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f).get("amil_tile_fwd_dram_bytes")
+        step_tf = flops_per_patch_algorithmic() * N_BAG / (ms_per_step * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "amil_tile_kernel<512,384,gated,FWD> (fused fc+gated-attention+softmax-partial)",
+                "achieved": achieved, "peak": peak_burst, "unit": "TFLOP/s", "frac": achieved / peak_burst,
+                "traffic": traffic, "peak_source": f"MEASURED_PEAKS.json bf16_tflops (burst), {src}",
+                "flops_per_launch": flops_tile_kernel(N_BAG),
+                "step_algorithmic_tflops": step_tf, "step_frac_of_sustained_peak": step_tf / peak_sust,
+                "stage_us": kernels}
+        if world == 1:
+            from oracle.cpu_reference import time_cpu_steps
+            pps, dt, threads = time_cpu_steps(N_BAG, L, D, K_CLASSES, steps=5, warmup=1)
+            cpu_base = {"value": pps, "unit": "patches/s", "cores": threads, "kind": "port",
+                        "sample": f"5 full steps (fwd+bwd) on one {N_BAG}x1024 bag, torch fp32 autograd, {dt * 1e3:.0f} ms/step"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "bag": [N_BAG, 1024], "preset": "big", "n_classes": K_CLASSES,
+                       "l2": f"inputs rotate over {N_BAGS} distinct bags ({N_BAGS * N_BAG * 2048 >> 20} MiB) > 126 MB L2",
+                       "parallelism": f"dp{world} (cohort data-parallel, one bag per rank per step, NCCL all-reduce of "
+                                      f"{flat.numel() * 4} B of fp32 grads per step)" if world > 1 else "single GPU",
+                       "timed_with": "CUDA graph replay per step, CUDA events, max over ranks"},
+            "clocks": clk.result,
+            "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": N_BAG * 1024 * 2,
+                    "d2h_bytes_per_step": 4 + 4, "steps": n_e2e,
+                    "note": "drop-in nn.Module + autograd, pinned bf16 host bags, double-buffered H2D on a copy stream"},
+            "gpu_launches": LAUNCHES_PER_STEP * args.steps,
+            "roofline": roof, "cpu_baseline": cpu_base,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps > 20:
+            args.steps = 20   # bounded sample: ~1 s of CPU work per step
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -122,6 +122,22 @@ int mmf_amil_bwd(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w,
                  const float* dM, const float* dA_raw, const void* H_stash, const MmfAmilGrads* g,
                  void* dx, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The three stages of mmf_amil_bwd, individually callable (same workspace; stage k consumes what
+ * stages < k left in it). Exposed so that each tensor-core kernel can be timed and tested alone.
+ *   gate   : recompute tile kernel -> dG, H in workspace; dwc, dbab, dbc accumulated
+ *   hidden : dU = (dG Wab + p dM^T) ⊙ relu'(H) in workspace; db1 accumulated
+ *   wgrad  : dW1 += dU^T x, dWab += dG^T H, optional dx = dU W1 */
+int mmf_amil_bwd_gate(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, int L, int D,
+                      int flags, uint64_t seed, const float* A_raw, const float* ml, const float* M,
+                      const float* dM, const float* dA_raw, const MmfAmilGrads* g, void* workspace,
+                      size_t workspace_bytes, void* stream);
+int mmf_amil_bwd_hidden(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, int L, int D,
+                        int flags, const float* A_raw, const float* ml, const float* dM,
+                        const MmfAmilGrads* g, void* workspace, size_t workspace_bytes, void* stream);
+int mmf_amil_bwd_wgrad(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, int L, int D,
+                       int flags, const MmfAmilGrads* g, void* dx, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
 /* Dense bf16 tensor-core GEMM used either side of the AMIL core (radio reduce_dim and its
  * gradients): C[M,N] = A[M,K] B[N,K]^T + bias (A given as up to 4 K-segments = the modality
  * bags that the reference concatenates, models/model_attention_mil_radio.py:81-82).

@@ -169,65 +169,90 @@ size_t mmf_amil_bwd_workspace_bytes(int64_t N, int L, int D, int flags) {
   return bwd_layout(N, L, D, flags & MMF_GATED).total;
 }
 
-int mmf_amil_bwd(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, int L, int D,
-                 int flags, uint64_t seed, const float* A_raw, const float* ml, const float* M,
-                 const float* dM, const float* dA_raw, const void* H_stash, const MmfAmilGrads* g,
-                 void* dx, void* workspace, size_t workspace_bytes, void* stream) {
-  (void)H_stash;  // TODO(round 2): skip the fc recompute when the forward stashed H
+namespace {
+struct BwdCtx {
+  BwdWs lay; int KD, ncols, gated; int64_t tiles;
+  __nv_bfloat16 *Hb, *dG, *dU; float *cs, *dbc_ws, *db1_ws;
+};
+int bwd_ctx(BwdCtx* c, const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, int L, int D,
+            int flags, void* workspace, size_t workspace_bytes) {
   MMF_TRY(check_amil_common(x, N, ldx, w, L, D));
-  if (!A_raw || !ml || !M || !dM || !g || !workspace) return MMF_E_INVALID;
-  if (!g->dW1 || !g->db1 || !g->dWab || !g->dbab || !g->dwc || !g->dbc) return MMF_E_INVALID;
-  if ((flags & MMF_NEED_DX) && !dx) return MMF_E_INVALID;
-  const int gated = flags & MMF_GATED;
-  const BwdWs lay = bwd_layout(N, L, D, gated);
-  if (workspace_bytes < lay.total) return MMF_E_WORKSPACE;
+  if (!workspace) return MMF_E_INVALID;
+  c->gated = flags & MMF_GATED;
+  c->lay = bwd_layout(N, L, D, c->gated);
+  if (workspace_bytes < c->lay.total) return MMF_E_WORKSPACE;
   if (reinterpret_cast<uintptr_t>(workspace) & 1023u) return MMF_E_ALIGN;
-  cudaStream_t st = (cudaStream_t)stream;
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
-  __nv_bfloat16* Hb = reinterpret_cast<__nv_bfloat16*>(ws + lay.off_H);
-  __nv_bfloat16* dG = reinterpret_cast<__nv_bfloat16*>(ws + lay.off_dG);
-  __nv_bfloat16* dU = reinterpret_cast<__nv_bfloat16*>(ws + lay.off_dU);
-  float* cs = reinterpret_cast<float*>(ws + lay.off_cs);
-  float* dbc_ws = reinterpret_cast<float*>(ws + lay.off_dbc);
-  float* db1_ws = reinterpret_cast<float*>(ws + lay.off_db1);
-  const int KD = gated ? 2 * D : D;
-  const int ncols = gated ? 3 * D : 2 * D;
-  const int64_t tiles = (N + 127) / 128;
+  c->Hb = reinterpret_cast<__nv_bfloat16*>(ws + c->lay.off_H);
+  c->dG = reinterpret_cast<__nv_bfloat16*>(ws + c->lay.off_dG);
+  c->dU = reinterpret_cast<__nv_bfloat16*>(ws + c->lay.off_dU);
+  c->cs = reinterpret_cast<float*>(ws + c->lay.off_cs);
+  c->dbc_ws = reinterpret_cast<float*>(ws + c->lay.off_dbc);
+  c->db1_ws = reinterpret_cast<float*>(ws + c->lay.off_db1);
+  c->KD = c->gated ? 2 * D : D;
+  c->ncols = c->gated ? 3 * D : 2 * D;
+  c->tiles = (N + 127) / 128;
+  return MMF_OK;
+}
+}  // namespace
 
-  // 1. row-stationary pass: recompute H and the attention branches, emit dG, H, column sums
+// Stage 1: row-stationary pass — recompute H and the attention branches tile by tile, emit
+// dG (bf16 [N,2D]) and H (bf16 [N,L]) into the workspace, reduce dwc / dbab / dbc.
+int mmf_amil_bwd_gate(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, int L, int D,
+                      int flags, uint64_t seed, const float* A_raw, const float* ml, const float* M,
+                      const float* dM, const float* dA_raw, const MmfAmilGrads* g, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  BwdCtx c;
+  MMF_TRY(bwd_ctx(&c, x, N, ldx, w, L, D, flags, workspace, workspace_bytes));
+  if (!A_raw || !ml || !M || !dM || !g || !g->dbab || !g->dwc || !g->dbc) return MMF_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
   AmilArgs a = {};
   a.N = N; a.b1 = w->b1; a.bab = w->bab; a.wc = w->wc; a.bc = w->bc;
   a.A_raw = const_cast<float*>(A_raw); a.flags = flags; a.seed = seed;
   a.ml = ml; a.M = M; a.dM = dM; a.dA_raw = dA_raw;
-  a.dG = dG; a.lddg = KD; a.colsum_ws = cs; a.dbc_ws = dbc_ws;
-  MMF_TRY(dispatch_amil<AMIL_BWD_GATE>(L, D, gated, x, N, ldx, w, a, Hb, st));
+  a.dG = c.dG; a.lddg = c.KD; a.colsum_ws = c.cs; a.dbc_ws = c.dbc_ws;
+  MMF_TRY(dispatch_amil<AMIL_BWD_GATE>(L, D, c.gated, x, N, ldx, w, a, c.Hb, st));
+  reduce_rows_kernel<<<(D + 31) / 32, dim3(32, 8), 0, st>>>(c.cs, c.tiles * 4, D, c.ncols, g->dwc, 1);
+  reduce_rows_kernel<<<(c.KD + 31) / 32, dim3(32, 8), 0, st>>>(c.cs + D, c.tiles * 4, c.KD, c.ncols, g->dbab, 1);
+  reduce_rows_kernel<<<1, dim3(32, 8), 0, st>>>(c.dbc_ws, c.tiles * 4, 1, 1, g->dbc, 1);
+  return launch_status();
+}
 
-  // 2. dwc, dbab, dbc from the per-warp partial sums
-  reduce_rows_kernel<<<(D + 31) / 32, dim3(32, 8), 0, st>>>(cs, tiles * 4, D, ncols, g->dwc, 1);
-  reduce_rows_kernel<<<(KD + 31) / 32, dim3(32, 8), 0, st>>>(cs + D, tiles * 4, KD, ncols, g->dbab, 1);
-  reduce_rows_kernel<<<1, dim3(32, 8), 0, st>>>(dbc_ws, tiles * 4, 1, 1, g->dbc, 1);
-  MMF_TRY(launch_status());
+// Stage 2: dU = (dG Wab + p dM^T) ⊙ relu'(H) [* 1/(1-p)] -> workspace (bf16 [N,L]); db1 += colsum.
+int mmf_amil_bwd_hidden(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, int L, int D,
+                        int flags, const float* A_raw, const float* ml, const float* dM,
+                        const MmfAmilGrads* g, void* workspace, size_t workspace_bytes, void* stream) {
+  BwdCtx c;
+  MMF_TRY(bwd_ctx(&c, x, N, ldx, w, L, D, flags, workspace, workspace_bytes));
+  if (!A_raw || !ml || !dM || !g || !g->db1) return MMF_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  TMapSet tA = {}, tB = {};
+  MMF_TRY(make_tmap_bf16(&tA.m[0], c.dG, (uint64_t)N, c.KD, c.KD, 128));
+  MMF_TRY(make_tmap_bf16(&tB.m[0], w->Wab, c.KD, L, L, 64));
+  GemmArgs ga = {};
+  ga.M = (int)N; ga.N = L; ga.kb_total = c.KD / 64; ga.kb_per_split = ga.kb_total;
+  ga.a_seg_kb = ga.kb_total; ga.b_seg_n = L;
+  ga.c_bf16 = c.dU; ga.ldc = L;
+  ga.s_raw = A_raw; ga.ml = ml; ga.dM = dM; ga.H = c.Hb; ga.ldh = L; ga.colsum_ws = c.db1_ws;
+  ga.du_scale = (flags & MMF_DROPOUT_H) ? (1.0f / 0.75f) : 1.0f;
+  MMF_TRY((launch_gemm<0, 1, EPI_DU>(tA, tB, ga, 1, st)));
+  reduce_rows_kernel<<<(L + 31) / 32, dim3(32, 8), 0, st>>>(c.db1_ws, c.tiles * 4, L, L, g->db1, 1);
+  return launch_status();
+}
 
-  // 3. dU = (dG Wab + p dM^T) ⊙ relu'(H) [* 1/(1-p)]
-  {
-    TMapSet tA = {}, tB = {};
-    MMF_TRY(make_tmap_bf16(&tA.m[0], dG, (uint64_t)N, KD, KD, 128));
-    MMF_TRY(make_tmap_bf16(&tB.m[0], w->Wab, KD, L, L, 64));
-    GemmArgs ga = {};
-    ga.M = (int)N; ga.N = L; ga.kb_total = KD / 64; ga.kb_per_split = ga.kb_total;
-    ga.a_seg_kb = ga.kb_total; ga.b_seg_n = L;
-    ga.c_bf16 = dU; ga.ldc = L;
-    ga.s_raw = A_raw; ga.ml = ml; ga.dM = dM; ga.H = Hb; ga.ldh = L; ga.colsum_ws = db1_ws;
-    ga.du_scale = (flags & MMF_DROPOUT_H) ? (1.0f / 0.75f) : 1.0f;
-    MMF_TRY((launch_gemm<0, 1, EPI_DU>(tA, tB, ga, 1, st)));
-    reduce_rows_kernel<<<(L + 31) / 32, dim3(32, 8), 0, st>>>(db1_ws, tiles * 4, L, L, g->db1, 1);
-    MMF_TRY(launch_status());
-  }
+// Stage 3: dW1 += dU^T X, dWab += dG^T H (split-K over the instance axis), optional dx = dU W1.
+int mmf_amil_bwd_wgrad(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, int L, int D,
+                       int flags, const MmfAmilGrads* g, void* dx, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  BwdCtx c;
+  MMF_TRY(bwd_ctx(&c, x, N, ldx, w, L, D, flags, workspace, workspace_bytes));
+  if (!g || !g->dW1 || !g->dWab) return MMF_E_INVALID;
+  if ((flags & MMF_NEED_DX) && !dx) return MMF_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
   const int kb_rows = (int)((N + 63) / 64);
-  // 4. dW1 += dU^T X
   {
     TMapSet tA = {}, tB = {};
-    MMF_TRY(make_tmap_bf16(&tA.m[0], dU, (uint64_t)N, L, L, 64));
+    MMF_TRY(make_tmap_bf16(&tA.m[0], c.dU, (uint64_t)N, L, L, 64));
     MMF_TRY(make_tmap_bf16(&tB.m[0], x, (uint64_t)N, 1024, (uint64_t)ldx, 64));
     GemmArgs ga = {};
     ga.M = L; ga.N = 1024; ga.kb_total = kb_rows;
@@ -236,22 +261,20 @@ int mmf_amil_bwd(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w,
     ga.c_f32 = g->dW1; ga.ldc = 1024;
     MMF_TRY((launch_gemm<1, 1, EPI_ATOMIC>(tA, tB, ga, splits, st)));
   }
-  // 5. dWab += dG^T H
   {
     TMapSet tA = {}, tB = {};
-    MMF_TRY(make_tmap_bf16(&tA.m[0], dG, (uint64_t)N, KD, KD, 64));
-    MMF_TRY(make_tmap_bf16(&tB.m[0], Hb, (uint64_t)N, L, L, 64));
+    MMF_TRY(make_tmap_bf16(&tA.m[0], c.dG, (uint64_t)N, c.KD, c.KD, 64));
+    MMF_TRY(make_tmap_bf16(&tB.m[0], c.Hb, (uint64_t)N, L, L, 64));
     GemmArgs ga = {};
-    ga.M = KD; ga.N = L; ga.kb_total = kb_rows;
-    const int splits = pick_splits((KD / 128) * ((L + 255) / 256), kb_rows, &ga.kb_per_split);
+    ga.M = c.KD; ga.N = L; ga.kb_total = kb_rows;
+    const int splits = pick_splits((c.KD / 128) * ((L + 255) / 256), kb_rows, &ga.kb_per_split);
     ga.a_seg_kb = kb_rows; ga.b_seg_n = L;
     ga.c_f32 = g->dWab; ga.ldc = L;
     MMF_TRY((launch_gemm<1, 1, EPI_ATOMIC>(tA, tB, ga, splits, st)));
   }
-  // 6. dx = dU W1 (only when a layer sits upstream of the bag features)
   if (flags & MMF_NEED_DX) {
     TMapSet tA = {}, tB = {};
-    MMF_TRY(make_tmap_bf16(&tA.m[0], dU, (uint64_t)N, L, L, 128));
+    MMF_TRY(make_tmap_bf16(&tA.m[0], c.dU, (uint64_t)N, L, L, 128));
     MMF_TRY(make_tmap_bf16(&tB.m[0], w->W1, L, 1024, 1024, 64));
     GemmArgs ga = {};
     ga.M = (int)N; ga.N = 1024; ga.kb_total = L / 64; ga.kb_per_split = ga.kb_total;
@@ -260,6 +283,18 @@ int mmf_amil_bwd(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w,
     MMF_TRY((launch_gemm<0, 1, EPI_STORE>(tA, tB, ga, 1, st)));
   }
   return MMF_OK;
+}
+
+int mmf_amil_bwd(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, int L, int D,
+                 int flags, uint64_t seed, const float* A_raw, const float* ml, const float* M,
+                 const float* dM, const float* dA_raw, const void* H_stash, const MmfAmilGrads* g,
+                 void* dx, void* workspace, size_t workspace_bytes, void* stream) {
+  (void)H_stash;  // reserved: skip the fc recompute when the forward stashed H
+  if (!g || !g->dW1 || !g->db1 || !g->dWab || !g->dbab || !g->dwc || !g->dbc) return MMF_E_INVALID;
+  MMF_TRY(mmf_amil_bwd_gate(x, N, ldx, w, L, D, flags, seed, A_raw, ml, M, dM, dA_raw, g, workspace,
+                            workspace_bytes, stream));
+  MMF_TRY(mmf_amil_bwd_hidden(x, N, ldx, w, L, D, flags, A_raw, ml, dM, g, workspace, workspace_bytes, stream));
+  return mmf_amil_bwd_wgrad(x, N, ldx, w, L, D, flags, g, dx, workspace, workspace_bytes, stream);
 }
 
 int mmf_linear_bf16(const void* const* A_segs, int n_segs, int64_t M, int K_per_seg, int64_t lda,
