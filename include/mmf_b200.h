@@ -190,6 +190,17 @@ int mmf_hazard_head_bwd(const float* M, int B, int Lin, const float* Wk, int K, 
                         const float* S, const float* d_hazards, const float* d_S, float* dM,
                         float* dWk, float* dbk, void* stream);
 
+/* Batch-1 training-step tail in ONE launch: combine the n tile partials -> M[L], ml[2]; hazard head;
+ * nll_surv loss (alpha, eps); gradient dM[L] back to the pooled vector; dWk[K,L], dbk[K] accumulated
+ * (may be NULL). Y int64[1], c f32[1] on the device. n <= 4096, L <= 1024, K <= 16.
+ * Replaces, per bag of the reference's hot loop (utils/core_utils.py:200-247): softmax+mm tail,
+ * classifier/sigmoid/cumprod/topk (models/model_attention_mil_path.py:55-61), nll_loss
+ * (utils/loss_utils.py:22-39) and their autograd — about forty ATen launches. */
+int mmf_amil_head_nll_step(const float* partials, int64_t n, int L, const float* Wk, const float* bk, int K,
+                           const int64_t* Y, const float* c, float alpha, float eps, float* M, float* ml,
+                           float* hazards, float* S, int64_t* Y_hat, float* loss, float* dM, float* dWk,
+                           float* dbk, void* stream);
+
 /* nll_loss (utils/loss_utils.py:22-39): loss scalar + d_hazards, d_S [B,K]. Y int64 [B], c f32 [B]. */
 int mmf_nll_surv_fwd_bwd(const float* hazards, const float* S, const int64_t* Y, const float* c,
                          int B, int K, float alpha, float eps, float* loss, float* d_hazards,

@@ -1,0 +1,404 @@
+// amil_tile2.cuh — CTA-pair version of the fused gated attention-MIL tile kernel (sm_100a).
+//
+// Same math and data flow as amil_tile.cuh (GEMM1 -> H in swizzled smem -> chunked GEMM2 -> gate
+// epilogue -> softmax partial / gate backward), re-laid for the hardware limits ncu showed on the
+// single-CTA version (tensor pipe 24 % active, the rest load latency and a serial epilogue):
+//
+//   * a cluster of 2 CTAs (one TPC) owns 256 rows and issues `tcgen05.mma.cta_group::2` (M = 256):
+//     each CTA keeps its own 128 rows of X / H / accumulators but stages only HALF of every weight
+//     tile, so the bytes a CTA pulls through L2 per k-block drop from 80 KB to 48 KB and the GEMM1
+//     ring deepens from 2 to 4 stages (192 KB in flight per SM pair member);
+//   * the producer prefetches its whole X tile into L2 up front (cp.async.bulk.prefetch.tensor), so
+//     the HBM latency of the only operand that is not L2-resident is paid once, not per k-block;
+//   * 8 epilogue warps (two per TMEM lane quadrant, splitting the columns) with TMEM loads issued
+//     one piece ahead, and b1 / [ba|bb] / wc / dM staged once in shared memory instead of being
+//     re-fetched through L1 for every 32-column piece.
+//
+// Barrier protocol (every barrier exists at the same offset in both CTAs):
+//   full*[s]      leader's copy is used; armed by the leader's producer with 2 x stage bytes; the TMA
+//                 loads of BOTH CTAs complete on it (.cta_group::2, peer bit cleared)
+//   empty*[s]     each CTA's own copy; the leader's MMA thread commits to both (multicast 0b11)
+//   acc1, acc2_full[b]   own copy per CTA; multicast commits
+//   h_ready, acc2_empty[b]   leader's copy; one arrive per epilogue warp of either CTA (count 16),
+//                 remote arrives go through mapa + mbarrier.arrive.release.cluster
+#pragma once
+#include "amil_tile.cuh"
+
+namespace mmf {
+
+template <int L, int D, bool GATED>
+struct Amil2Cfg {
+  static constexpr int KB1 = 1024 / 64;
+  static constexpr int NH1 = L / 256;
+  static constexpr int KB2 = L / 64;
+  static constexpr int NCH = D / 128;
+  static constexpr int CHN = GATED ? 256 : 128;       // MMA N of GEMM2 (per pair)
+  static constexpr int KD = GATED ? 2 * D : D;
+  static constexpr uint32_t H_BYTES = 128u * L * 2u;
+  static constexpr uint32_t STAGE1 = 16384u + NH1 * 16384u;  // x tile + this CTA's half of W1
+  static constexpr uint32_t STAGE2 = (CHN / 2) * 128u;       // this CTA's half of the Wab chunk
+  static constexpr uint32_t POOL = 208u * 1024u;
+  static constexpr uint32_t VEC_BYTES = 16u * 1024u;
+  static constexpr int NS1 = (POOL / STAGE1) < 6 ? (POOL / STAGE1) : 6;
+  static constexpr int NS2 = ((POOL - H_BYTES) / STAGE2) < 8 ? ((POOL - H_BYTES) / STAGE2) : 8;
+  static constexpr uint32_t SMEM_BYTES = POOL + VEC_BYTES + 1024u;
+  static constexpr int NCOLS = GATED ? 3 * D : 2 * D;
+  // float offsets inside the vector region
+  static constexpr int V_B1 = 0, V_BAB = L, V_WC = L + KD, V_DM = L + KD + D, V_S = V_DM + L,
+                       V_P = V_S + 256, V_RED = V_P + 128, V_END = V_RED + 16;
+  static_assert(V_END * 4 <= (int)VEC_BYTES, "vector region overflow");
+  static_assert(NS1 >= 2 && NS2 >= 2, "ring too shallow");
+};
+
+constexpr int AMIL2_THREADS = 384;
+constexpr uint32_t AMIL2_EPI_THREADS = 256;
+
+template <int L, int D, bool GATED, int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AMIL2_THREADS, 1)
+amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
+                  const __grid_constant__ CUtensorMap tmWab, const __grid_constant__ CUtensorMap tmH,
+                  const AmilArgs a) {
+  using C = Amil2Cfg<L, D, GATED>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full1[C::NS1], bar_empty1[C::NS1];
+  __shared__ __align__(8) uint64_t bar_full2[C::NS2], bar_empty2[C::NS2];
+  __shared__ __align__(8) uint64_t bar_acc1, bar_h, bar_acc2_full[2], bar_acc2_empty[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const uint32_t pool = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t h_base = pool;
+  const uint32_t ring2 = pool + C::H_BYTES;
+  float* vec = reinterpret_cast<float*>(smem_raw + (pool - smem_u32(smem_raw)) + C::POOL);
+  const int tile = blockIdx.x;
+  const long long row0 = (long long)tile * 128;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::NS1; ++s) { mbar_init(smem_u32(&bar_full1[s]), 1); mbar_init(smem_u32(&bar_empty1[s]), 1); }
+    for (int s = 0; s < C::NS2; ++s) { mbar_init(smem_u32(&bar_full2[s]), 1); mbar_init(smem_u32(&bar_empty2[s]), 1); }
+    mbar_init(smem_u32(&bar_acc1), 1);
+    mbar_init(smem_u32(&bar_h), 16);
+    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&bar_acc2_full[b]), 1); mbar_init(smem_u32(&bar_acc2_empty[b]), 16); }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmWab);
+  }
+  // stage the per-column vectors once
+  for (int i = threadIdx.x; i < L; i += AMIL2_THREADS) {
+    vec[C::V_B1 + i] = __ldg(a.b1 + i);
+    if (MODE == AMIL_BWD_GATE) vec[C::V_DM + i] = __ldg(a.dM + i);
+  }
+  for (int i = threadIdx.x; i < C::KD; i += AMIL2_THREADS) vec[C::V_BAB + i] = __ldg(a.bab + i);
+  for (int i = threadIdx.x; i < D; i += AMIL2_THREADS) vec[C::V_WC + i] = __ldg(a.wc + i);
+  if (warp == 2) {
+    tmem_alloc_pair(smem_u32(&tmem_base_slot), 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // both CTAs' barriers are initialised before any cross-CTA signal
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+
+  if (warp == 0 && lane == 0) {
+    // =============================== TMA producer (both CTAs) ==========================
+    for (int kb = 0; kb < C::KB1; ++kb) tma_prefetch_l2_2d(&tmX, kb * 64, (int)row0);
+    for (int kb = 0; kb < C::KB1; ++kb) {
+      const int s = kb % C::NS1;
+      const uint32_t ph = (kb / C::NS1) & 1;
+      mbar_wait(smem_u32(&bar_empty1[s]), ph ^ 1);
+      const uint32_t full = smem_u32(&bar_full1[s]);
+      const uint32_t dst = pool + s * C::STAGE1;
+      if (leader) mbar_arrive_expect_tx(full, 2 * C::STAGE1);
+      tma_load_2d_pair(dst, &tmX, full, kb * 64, (int)row0);
+#pragma unroll
+      for (int j = 0; j < C::NH1; ++j)
+        tma_load_2d_pair(dst + 16384 + j * 16384, &tmW1, full, kb * 64, j * 256 + 128 * (int)rank);
+    }
+    mbar_wait(smem_u32(&bar_acc1), 0);   // GEMM1 retired: its ring (overlaying H / ring2) is free
+    for (int c = 0; c < C::NCH; ++c) {
+      for (int kb = 0; kb < C::KB2; ++kb) {
+        const int it = c * C::KB2 + kb;
+        const int s = it % C::NS2;
+        const uint32_t ph = (it / C::NS2) & 1;
+        mbar_wait(smem_u32(&bar_empty2[s]), ph ^ 1);
+        const uint32_t full = smem_u32(&bar_full2[s]);
+        if (leader) mbar_arrive_expect_tx(full, 2 * C::STAGE2);
+        tma_load_2d_pair(ring2 + s * C::STAGE2, &tmWab, full, kb * 64, c * C::CHN + (C::CHN / 2) * (int)rank);
+      }
+    }
+  } else if (warp == 1 && lane == 0 && leader) {
+    // =============================== MMA issuer (leader CTA) ===========================
+    constexpr uint32_t idesc1 = umma_idesc_bf16(256, 256, 0, 0);
+    constexpr uint32_t idesc2 = umma_idesc_bf16(256, C::CHN, 0, 0);
+    for (int kb = 0; kb < C::KB1; ++kb) {
+      const int s = kb % C::NS1;
+      const uint32_t ph = (kb / C::NS1) & 1;
+      mbar_wait(smem_u32(&bar_full1[s]), ph);
+      tc_fence_after();
+      const uint32_t xs = pool + s * C::STAGE1;
+      const uint32_t ws = xs + 16384;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint64_t ad = umma_desc_sw128(xs + k * 32, 16, 1024);
+#pragma unroll
+        for (int j = 0; j < C::NH1; ++j)
+          umma_bf16_ss_pair(tmem + j * 256, ad, umma_desc_sw128(ws + j * 16384 + k * 32, 16, 1024), idesc1,
+                            (kb | k) != 0);
+      }
+      umma_commit_pair_mc(smem_u32(&bar_empty1[s]), 3);
+    }
+    umma_commit_pair_mc(smem_u32(&bar_acc1), 3);
+
+    mbar_wait_cluster(smem_u32(&bar_h), 0);   // both CTAs' H tiles written, GEMM1 TMEM columns drained
+    tc_fence_after();
+    for (int c = 0; c < C::NCH; ++c) {
+      const int buf = c & 1;
+      mbar_wait_cluster(smem_u32(&bar_acc2_empty[buf]), ((c >> 1) & 1) ^ 1);
+      tc_fence_after();
+      for (int kb = 0; kb < C::KB2; ++kb) {
+        const int it = c * C::KB2 + kb;
+        const int s = it % C::NS2;
+        const uint32_t ph = (it / C::NS2) & 1;
+        mbar_wait(smem_u32(&bar_full2[s]), ph);
+        tc_fence_after();
+        const uint32_t hs = h_base + kb * 16384;
+        const uint32_t bs = ring2 + s * C::STAGE2;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_ss_pair(tmem + buf * C::CHN, umma_desc_sw128(hs + k * 32, 16, 1024),
+                            umma_desc_sw128(bs + k * 32, 16, 1024), idesc2, (kb | k) != 0);
+        umma_commit_pair_mc(smem_u32(&bar_empty2[s]), 3);
+      }
+      umma_commit_pair_mc(smem_u32(&bar_acc2_full[buf]), 3);
+    }
+  } else if (warp >= 4) {
+    // =============================== epilogue warps (both CTAs) ========================
+    const uint32_t q = warp & 3;
+    const uint32_t half = (warp - 4) >> 2;      // column half handled by this warp
+    const uint32_t r = q * 32 + lane;           // row within the tile == TMEM lane
+    const uint32_t e = threadIdx.x - 128;       // 0..255 epilogue thread index
+    const long long row = row0 + r;
+    const bool row_ok = row < a.N;
+    const uint32_t tq = tmem + ((q * 32u) << 16);
+    const bool drop_h = (a.flags & MMF_DROPOUT_H) != 0;
+    const bool drop_attn = (a.flags & MMF_DROPOUT_ATTN) != 0;
+    const uint32_t rs_h = drop_row_state(a.seed, 0, (uint32_t)row);
+    const uint32_t h_ready_leader = mapa_cluster(smem_u32(&bar_h), 0);
+    float* sS = vec + C::V_S;     // [2][128] per-half partial row sums (t_i in bwd, score in fwd)
+    float* sP = vec + C::V_P;
+    float* sRed = vec + C::V_RED;
+
+    // ---------------- EPI1: H = dropout(relu(U + b1)) -> swizzled smem -----------------
+    mbar_wait(smem_u32(&bar_acc1), 0);
+    tc_fence_after();
+    float t_i = 0.f;
+    constexpr int PIECES1 = L / 64;  // 32-column pieces per half
+    const int cb0 = half * PIECES1;
+    float v[2][32];
+    tmem_ld32(tq + cb0 * 32, v[0]);
+#pragma unroll
+    for (int ii = 0; ii < PIECES1; ++ii) {
+      const int cb = cb0 + ii;
+      tmem_ld_wait();
+      if (ii + 1 < PIECES1) tmem_ld32(tq + (cb + 1) * 32, v[(ii + 1) & 1]);
+      float (&u)[32] = v[ii & 1];
+      const float4* b4p = reinterpret_cast<const float4*>(vec + C::V_B1 + cb * 32);
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 b4 = b4p[i >> 2];
+        u[i] = fmaxf(u[i] + b4.x, 0.f); u[i + 1] = fmaxf(u[i + 1] + b4.y, 0.f);
+        u[i + 2] = fmaxf(u[i + 2] + b4.z, 0.f); u[i + 3] = fmaxf(u[i + 3] + b4.w, 0.f);
+        if (drop_h) {
+          const uint32_t bits = drop_bits4(rs_h, (uint32_t)(cb * 8 + (i >> 2)));
+          u[i] *= drop_scale(bits, 0); u[i + 1] *= drop_scale(bits, 1);
+          u[i + 2] *= drop_scale(bits, 2); u[i + 3] *= drop_scale(bits, 3);
+        }
+      }
+      const uint32_t kb_base = h_base + (cb >> 1) * 16384;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t p0 = pack_bf16x2(u[8 * j], u[8 * j + 1]), p1 = pack_bf16x2(u[8 * j + 2], u[8 * j + 3]);
+        const uint32_t p2 = pack_bf16x2(u[8 * j + 4], u[8 * j + 5]), p3 = pack_bf16x2(u[8 * j + 6], u[8 * j + 7]);
+        st_shared_v4(kb_base + sw128_offset(r, (cb & 1) * 4 + j), p0, p1, p2, p3);
+        if (MODE == AMIL_BWD_GATE) {
+          const uint32_t pk[4] = {p0, p1, p2, p3};
+          const float4* dm4 = reinterpret_cast<const float4*>(vec + C::V_DM + cb * 32 + 8 * j);
+          const float4 d0 = dm4[0], d1 = dm4[1];
+          const float dmv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+          for (int x2 = 0; x2 < 4; ++x2) {
+            const float2 hf = unpack_bf16x2(pk[x2]);
+            t_i = fmaf(hf.x, dmv[2 * x2], t_i);
+            t_i = fmaf(hf.y, dmv[2 * x2 + 1], t_i);
+          }
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive_cluster(h_ready_leader);
+
+    if (MODE == AMIL_BWD_GATE) sS[half * 128 + r] = t_i;
+    if (MODE == AMIL_BWD_GATE || a.store_h) {
+      named_bar_sync(1, AMIL2_EPI_THREADS);   // all H writes of this CTA fenced (+ t_i halves visible)
+      if (e == 0) {
+        for (int kb = 0; kb < C::KB2; ++kb) tma_store_2d(&tmH, h_base + kb * 16384, kb * 64, (int)row0);
+        tma_store_commit();
+      }
+    }
+    float ds = 0.f;
+    if (MODE == AMIL_BWD_GATE) {
+      t_i = sS[r] + sS[128 + r];
+      float dot = 0.f;
+      for (int c = lane; c < L; c += 32) dot = fmaf(vec[C::V_DM + c], __ldg(a.M + c), dot);
+      dot = warp_sum(dot);
+      if (row_ok) {
+        const float p = __expf(__ldg(a.A_raw + row) - __ldg(a.ml)) / __ldg(a.ml + 1);
+        ds = p * (t_i - dot);
+        if (a.dA_raw) ds += __ldg(a.dA_raw + row);
+      }
+    }
+
+    // ---------------- EPI2: gate + score (fwd) / gate backward (bwd) -------------------
+    float s_acc = 0.f;
+    const uint32_t rs_a = drop_row_state(a.seed, 1, (uint32_t)row);
+    const uint32_t rs_g = drop_row_state(a.seed, 2, (uint32_t)row);
+#pragma unroll 1
+    for (int c = 0; c < C::NCH; ++c) {
+      const int buf = c & 1;
+      mbar_wait(smem_u32(&bar_acc2_full[buf]), (c >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int pp = 0; pp < 2; ++pp) {
+        const int pc = half * 2 + pp;
+        const int d0 = c * 128 + pc * 32;
+        float va[32], vg[32];
+        tmem_ld32(tq + buf * C::CHN + pc * 32, va);
+        if (GATED) tmem_ld32(tq + buf * C::CHN + 128 + pc * 32, vg);
+        tmem_ld_wait();
+        float dwc_v[32];
+        const float4* ba4p = reinterpret_cast<const float4*>(vec + C::V_BAB + d0);
+        const float4* bb4p = reinterpret_cast<const float4*>(vec + C::V_BAB + D + d0);
+        const float4* wc4p = reinterpret_cast<const float4*>(vec + C::V_WC + d0);
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 ba4 = ba4p[i >> 2], wc4 = wc4p[i >> 2];
+          float4 bb4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (GATED) bb4 = bb4p[i >> 2];
+          const float bav[4] = {ba4.x, ba4.y, ba4.z, ba4.w};
+          const float bbv[4] = {bb4.x, bb4.y, bb4.z, bb4.w};
+          const float wcv[4] = {wc4.x, wc4.y, wc4.z, wc4.w};
+          uint32_t bits_a = 0, bits_g = 0;
+          if (drop_attn) {
+            bits_a = drop_bits4(rs_a, (uint32_t)((d0 + i) >> 2));
+            bits_g = drop_bits4(rs_g, (uint32_t)((d0 + i) >> 2));
+          }
+#pragma unroll
+          for (int x2 = 0; x2 < 4; ++x2) {
+            const float av = tanh_fast(va[i + x2] + bav[x2]);
+            const float gv = GATED ? sigmoid_fast(vg[i + x2] + bbv[x2]) : 1.f;
+            const float ka = drop_attn ? drop_scale(bits_a, x2) : 1.f;
+            const float kg = (GATED && drop_attn) ? drop_scale(bits_g, x2) : 1.f;
+            const float ad = av * ka, gd = gv * kg;
+            if (MODE == AMIL_FWD) {
+              s_acc = fmaf(wcv[x2], ad * gd, s_acc);
+            } else {
+              const float dq = ds * wcv[x2];
+              dwc_v[i + x2] = ds * ad * gd;
+              va[i + x2] = dq * gd * ka * (1.f - av * av);
+              if (GATED) vg[i + x2] = dq * ad * kg * gv * (1.f - gv);
+            }
+          }
+        }
+        if (MODE == AMIL_BWD_GATE) {
+          if (row_ok) {
+            uint4* dst_a = reinterpret_cast<uint4*>(a.dG + row * a.lddg + d0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              dst_a[j] = make_uint4(pack_bf16x2(va[8 * j], va[8 * j + 1]), pack_bf16x2(va[8 * j + 2], va[8 * j + 3]),
+                                    pack_bf16x2(va[8 * j + 4], va[8 * j + 5]), pack_bf16x2(va[8 * j + 6], va[8 * j + 7]));
+            if (GATED) {
+              uint4* dst_g = reinterpret_cast<uint4*>(a.dG + row * a.lddg + D + d0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                dst_g[j] = make_uint4(pack_bf16x2(vg[8 * j], vg[8 * j + 1]), pack_bf16x2(vg[8 * j + 2], vg[8 * j + 3]),
+                                      pack_bf16x2(vg[8 * j + 4], vg[8 * j + 5]), pack_bf16x2(vg[8 * j + 6], vg[8 * j + 7]));
+            }
+          }
+          float* wsrow = a.colsum_ws + ((long long)tile * 4 + q) * C::NCOLS;
+          const float s0 = warp_colsum32(dwc_v);
+          wsrow[d0 + lane] = s0;
+          const float s1 = warp_colsum32(va);
+          wsrow[D + d0 + lane] = s1;
+          if (GATED) {
+            const float s2 = warp_colsum32(vg);
+            wsrow[2 * D + d0 + lane] = s2;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&bar_acc2_empty[buf]), 0));
+    }
+
+    if (MODE == AMIL_BWD_GATE) {
+      if (half == 0) {
+        const float dsum = warp_sum(ds);
+        if (lane == 0) a.dbc_ws[(long long)tile * 4 + q] = dsum;
+      }
+      if (e == 0) tma_store_wait_all();
+    } else {
+      // ---------------- FWD: scores out + tile softmax partial ------------------------
+      sS[half * 128 + r] = s_acc;
+      named_bar_sync(2, AMIL2_EPI_THREADS);
+      const bool tile_ok = row0 < a.N;
+      if (half == 0) {
+        const float s = row_ok ? sS[r] + sS[128 + r] + __ldg(a.bc) : -INFINITY;
+        if (row_ok) a.A_raw[row] = s;
+        const float wm = warp_max(s);
+        if (lane == 0) sRed[q] = wm;
+        named_bar_sync(3, 128);
+        const float m_t = fmaxf(fmaxf(sRed[0], sRed[1]), fmaxf(sRed[2], sRed[3]));
+        const float p = row_ok ? __expf(s - m_t) : 0.f;
+        sP[r] = p;
+        const float wsum = warp_sum(p);
+        if (lane == 0) sRed[4 + q] = wsum;
+        named_bar_sync(3, 128);
+        if (r == 0 && tile_ok) {
+          float* prow = a.partials + (long long)tile * (L + 2);
+          prow[0] = m_t;
+          prow[1] = sRed[4] + sRed[5] + sRed[6] + sRed[7];
+        }
+      }
+      named_bar_sync(2, AMIL2_EPI_THREADS);   // sP complete
+      if (tile_ok) {
+        float* prow = a.partials + (long long)tile * (L + 2);
+        for (uint32_t cp = e; cp < (uint32_t)L / 2; cp += AMIL2_EPI_THREADS) {
+          const uint32_t col = 2u * cp;
+          const uint32_t kb = col >> 6, chunk = (col & 63u) >> 3, inb = (col & 7u) * 2u;
+          const uint32_t blk = h_base + kb * 16384u;
+          float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 8
+          for (uint32_t rr = 0; rr < 128; ++rr) {
+            const float2 hf = unpack_bf16x2(ld_shared_b32(blk + sw128_offset(rr, chunk) + inb));
+            const float pr = sP[rr];
+            acc0 = fmaf(pr, hf.x, acc0);
+            acc1 = fmaf(pr, hf.y, acc1);
+          }
+          prow[2 + col] = acc0;
+          prow[2 + col + 1] = acc1;
+        }
+      }
+      if (a.store_h && e == 0) tma_store_wait_all();
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  cluster_sync_all();   // the peer may still be reading this CTA's smem / TMEM through the pair MMA
+  if (warp == 2) tmem_dealloc_pair(tmem, 512);
+}
+
+}  // namespace mmf

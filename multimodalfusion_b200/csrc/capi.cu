@@ -5,6 +5,8 @@
 
 #include "../../include/mmf_b200.h"
 #include "amil_tile.cuh"
+#include "amil_tile2.cuh"
+#include <stdlib.h>
 #include "gemm_tc.cuh"
 #include "mmf_host.cuh"
 #include "small_kernels.cuh"
@@ -19,7 +21,7 @@ struct BwdWs {
   size_t off_H, off_dG, off_dU, off_cs, off_dbc, off_db1, total;
 };
 BwdWs bwd_layout(int64_t N, int L, int D, int gated) {
-  const int64_t tiles = (N + 127) / 128;
+  const int64_t tiles = ((N + 255) / 256) * 2;  // padded to whole CTA pairs
   const int KD = gated ? 2 * D : D;
   const int ncols = gated ? 3 * D : 2 * D;
   BwdWs w;
@@ -79,13 +81,49 @@ int launch_amil(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, 
   return launch_status();
 }
 
+// CTA-pair kernel (amil_tile2.cuh): grid = 2 * ceil(N / 256), cluster (2,1,1)
+template <int L, int D, bool GATED, int MODE>
+int launch_amil2(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, const AmilArgs& a,
+                 void* Hbuf, cudaStream_t st) {
+  using C = Amil2Cfg<L, D, GATED>;
+  static bool configured = false;
+  auto kern = amil_tile2_kernel<L, D, GATED, MODE>;
+  if (!configured) {
+    MMF_TRY(cuda_rc(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES)));
+    configured = true;
+  }
+  CUtensorMap tmX, tmW1, tmWab, tmH;
+  MMF_TRY(make_tmap_bf16(&tmX, x, (uint64_t)N, 1024, (uint64_t)ldx, 128));
+  MMF_TRY(make_tmap_bf16(&tmW1, w->W1, L, 1024, 1024, 128));
+  MMF_TRY(make_tmap_bf16(&tmWab, w->Wab_packed, (uint64_t)C::NCH * C::CHN, L, L, C::CHN / 2));
+  if (Hbuf) MMF_TRY(make_tmap_bf16(&tmH, Hbuf, (uint64_t)N, L, L, 128));
+  else tmH = tmX;
+  const int pairs = (int)((N + 255) / 256);
+  kern<<<2 * pairs, AMIL2_THREADS, C::SMEM_BYTES, st>>>(tmX, tmW1, tmWab, tmH, a);
+  return launch_status();
+}
+
+// MMF_TILE_V1=1 selects the single-CTA kernel (kept as the reference implementation of the pair kernel)
+inline bool use_tile_v1() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MMF_TILE_V1");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 template <int MODE>
 int dispatch_amil(int L, int D, int gated, const void* x, int64_t N, int64_t ldx,
                   const MmfAmilWeights* w, const AmilArgs& a, void* Hbuf, cudaStream_t st) {
 #define MMF_CASE(LL, DD)                                                                  \
-  if (L == LL && D == DD)                                                                 \
+  if (L == LL && D == DD) {                                                               \
+    if (!use_tile_v1())                                                                   \
+      return gated ? launch_amil2<LL, DD, true, MODE>(x, N, ldx, w, a, Hbuf, st)          \
+                   : launch_amil2<LL, DD, false, MODE>(x, N, ldx, w, a, Hbuf, st);        \
     return gated ? launch_amil<LL, DD, true, MODE>(x, N, ldx, w, a, Hbuf, st)             \
-                 : launch_amil<LL, DD, false, MODE>(x, N, ldx, w, a, Hbuf, st);
+                 : launch_amil<LL, DD, false, MODE>(x, N, ldx, w, a, Hbuf, st);           \
+  }
   MMF_CASE(256, 256)
   MMF_CASE(512, 384)
   MMF_CASE(256, 384)
@@ -212,9 +250,12 @@ int mmf_amil_bwd_gate(const void* x, int64_t N, int64_t ldx, const MmfAmilWeight
   a.ml = ml; a.M = M; a.dM = dM; a.dA_raw = dA_raw;
   a.dG = c.dG; a.lddg = c.KD; a.colsum_ws = c.cs; a.dbc_ws = c.dbc_ws;
   MMF_TRY(dispatch_amil<AMIL_BWD_GATE>(L, D, c.gated, x, N, ldx, w, a, c.Hb, st));
-  reduce_rows_kernel<<<(D + 31) / 32, dim3(32, 8), 0, st>>>(c.cs, c.tiles * 4, D, c.ncols, g->dwc, 1);
-  reduce_rows_kernel<<<(c.KD + 31) / 32, dim3(32, 8), 0, st>>>(c.cs + D, c.tiles * 4, c.KD, c.ncols, g->dbab, 1);
-  reduce_rows_kernel<<<1, dim3(32, 8), 0, st>>>(c.dbc_ws, c.tiles * 4, 1, 1, g->dbc, 1);
+  ReduceSegs segs = {};
+  segs.n = 3;
+  segs.s[0] = ReduceSeg{c.cs, c.ncols, D, g->dwc};
+  segs.s[1] = ReduceSeg{c.cs + D, c.ncols, c.KD, g->dbab};
+  segs.s[2] = ReduceSeg{c.dbc_ws, 1, 1, g->dbc};
+  launch_reduce_rows(segs, c.tiles * 4, st);
   return launch_status();
 }
 
@@ -236,7 +277,10 @@ int mmf_amil_bwd_hidden(const void* x, int64_t N, int64_t ldx, const MmfAmilWeig
   ga.s_raw = A_raw; ga.ml = ml; ga.dM = dM; ga.H = c.Hb; ga.ldh = L; ga.colsum_ws = c.db1_ws;
   ga.du_scale = (flags & MMF_DROPOUT_H) ? (1.0f / 0.75f) : 1.0f;
   MMF_TRY((launch_gemm<0, 1, EPI_DU>(tA, tB, ga, 1, st)));
-  reduce_rows_kernel<<<(L + 31) / 32, dim3(32, 8), 0, st>>>(c.db1_ws, c.tiles * 4, L, L, g->db1, 1);
+  ReduceSegs segs = {};
+  segs.n = 1;
+  segs.s[0] = ReduceSeg{c.db1_ws, L, L, g->db1};
+  launch_reduce_rows(segs, c.tiles * 4, st);
   return launch_status();
 }
 
@@ -429,6 +473,18 @@ int mmf_hazard_head_bwd(const float* M, int B, int Lin, const float* Wk, int K, 
   if (dWk)  // dWk[j,l] += sum_b dlogit[b,j] M[b,l]
     launch_sgemm(K, Lin, B, LoadHazAT{d}, LoadColMajor{M, Lin}, EpiStoreAcc{dWk, Lin, 1}, st);
   if (dbk) colsum_functor_kernel<<<1, 32, 0, st>>>(B, K, LoadHazA{d}, dbk, 1);
+  return launch_status();
+}
+
+int mmf_amil_head_nll_step(const float* partials, int64_t n, int L, const float* Wk, const float* bk, int K,
+                           const int64_t* Y, const float* c, float alpha, float eps, float* M, float* ml,
+                           float* hazards, float* S, int64_t* Y_hat, float* loss, float* dM, float* dWk,
+                           float* dbk, void* stream) {
+  if (!partials || !Wk || !bk || !Y || !c || !M || !ml || !hazards || !S || !loss || !dM) return MMF_E_INVALID;
+  if (n <= 0 || n > 4096 || L <= 0 || L > 1024 || K <= 0 || K > 16) return MMF_E_UNSUPPORTED;
+  amil_head_step_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(
+      partials, (int)n, L, Wk, bk, K, reinterpret_cast<const long long*>(Y), c, alpha, eps, M, ml, hazards, S,
+      reinterpret_cast<long long*>(Y_hat), loss, dM, dWk, dbk);
   return launch_status();
 }
 

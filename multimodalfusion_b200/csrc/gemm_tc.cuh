@@ -221,21 +221,55 @@ gemm_tc_kernel(const __grid_constant__ TMapSet tmA, const __grid_constant__ TMap
   if (warp == 2) tmem_dealloc(tmem, 256);
 }
 
-// out[c] (+)= sum_r ws[r][c];  one thread per column, rows strided across blockDim.y
-__global__ void reduce_rows_kernel(const float* __restrict__ ws, long long rows, int cols,
-                                   long long ld, float* __restrict__ out, int accumulate) {
+// Column sums of up to three row-major partial-sum workspaces in ONE launch:
+//   seg k: out_k[c] += sum_r ws_k[r * ld_k + c],  c < ncols_k,  r < rows
+// grid = (ceil(total_cols / 32), row_splits); block (32, 8); one atomicAdd per (block, column).
+struct ReduceSeg {
+  const float* ws;
+  long long ld;
+  int ncols;
+  float* out;
+};
+struct ReduceSegs {
+  ReduceSeg s[3];
+  int n;
+};
+__global__ void reduce_rows_multi_kernel(const ReduceSegs segs, long long rows) {
   __shared__ float part[8][33];
-  const int c = blockIdx.x * 32 + threadIdx.x;
+  int c = blockIdx.x * 32 + threadIdx.x;
+  const float* ws = nullptr;
+  long long ld = 0;
+  float* out = nullptr;
+  for (int k = 0; k < segs.n; ++k) {
+    const int padded = (segs.s[k].ncols + 31) & ~31;
+    if (c < padded) {
+      if (c < segs.s[k].ncols) { ws = segs.s[k].ws + c; ld = segs.s[k].ld; out = segs.s[k].out + c; }
+      break;
+    }
+    c -= padded;
+  }
+  const long long per = (rows + gridDim.y - 1) / gridDim.y;
+  const long long r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
   float acc = 0.f;
-  if (c < cols)
-    for (long long r = threadIdx.y; r < rows; r += blockDim.y) acc += ws[r * ld + c];
+  if (ws)
+    for (long long r = r0 + threadIdx.y; r < r1; r += 8) acc += ws[r * ld];
   part[threadIdx.y][threadIdx.x] = acc;
   __syncthreads();
-  if (threadIdx.y == 0 && c < cols) {
+  if (threadIdx.y == 0 && out) {
     float t = 0.f;
-    for (int j = 0; j < (int)blockDim.y; ++j) t += part[j][threadIdx.x];
-    out[c] = accumulate ? out[c] + t : t;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += part[j][threadIdx.x];
+    atomicAdd(out, t);
   }
+}
+
+inline void launch_reduce_rows(const ReduceSegs& segs, long long rows, cudaStream_t st) {
+  int blocks_x = 0;
+  for (int k = 0; k < segs.n; ++k) blocks_x += (segs.s[k].ncols + 31) / 32;
+  int splits = (int)((rows + 63) / 64);
+  if (splits < 1) splits = 1;
+  if (splits > 16) splits = 16;
+  reduce_rows_multi_kernel<<<dim3(blocks_x, splits), dim3(32, 8), 0, st>>>(segs, rows);
 }
 
 }  // namespace mmf

@@ -234,23 +234,167 @@ __global__ void kron_contract_kernel(const float* __restrict__ dkron, KronElem e
 // -------------------------------------------------------------------------------------------
 __global__ void hazard_head_fwd_kernel(const float* __restrict__ M, int B, int Lin,
                                        const float* __restrict__ Wk, const float* __restrict__ bk,
-                                       int K, float* hazards, float* S, long long* Y_hat) {
+                                       int K, float* __restrict__ hazards, float* __restrict__ S,
+                                       long long* __restrict__ Y_hat) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= B) return;
   const float* mrow = M + (long long)warp * Lin;
-  float best = -CUDART_INF_F; int besti = 0; float surv = 1.f;
-  for (int j = 0; j < K; ++j) {
+  float d[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) d[j] = 0.f;
+  for (int l = lane; l < Lin; l += 32) {
+    const float mv = mrow[l];
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (j < K) d[j] = fmaf(mv, Wk[(long long)j * Lin + l], d[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d[j] += __shfl_xor_sync(0xffffffffu, d[j], o);
+  if (lane == 0) {
+    float best = -CUDART_INF_F, surv = 1.f;
+    int besti = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (j < K) {
+        const float logit = d[j] + bk[j];
+        if (logit > best) { best = logit; besti = j; }
+        const float h = 1.f / (1.f + expf(-logit));
+        surv *= (1.f - h);
+        hazards[(long long)warp * K + j] = h;
+        S[(long long)warp * K + j] = surv;
+      }
+    }
+    if (Y_hat) Y_hat[warp] = besti;
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// Single-bag training step tail, ONE launch: combine the tile partials -> M, (m,l); hazard head;
+// nll_surv loss; gradient back to M and to the classifier (dWk, dbk accumulated).
+// Replaces 7 launches (combine, head fwd, nll, 3x head bwd) on the batch-1 hot loop
+// (utils/core_utils.py:200-247).  One block of 512 threads, n <= 4096 partials, L <= 1024, K <= 16.
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512)
+amil_head_step_kernel(const float* __restrict__ parts, int n, int L, const float* __restrict__ Wk,
+                      const float* __restrict__ bk, int K, const long long* __restrict__ Yp,
+                      const float* __restrict__ cp, float alpha, float eps, float* __restrict__ M,
+                      float* __restrict__ ml, float* __restrict__ hazards, float* __restrict__ S,
+                      long long* __restrict__ Y_hat, float* __restrict__ loss, float* __restrict__ dM,
+                      float* __restrict__ dWk, float* __restrict__ dbk) {
+  __shared__ float s_w[4096];
+  __shared__ float s_M[1024];
+  __shared__ float s_red[16];
+  __shared__ float s_logit[16], s_dlogit[16];
+  __shared__ float s_glob[2];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const long long stride = L + 2;
+  // global max
+  float m = -CUDART_INF_F;
+  for (int t = tid; t < n; t += 512) m = fmaxf(m, parts[t * stride]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) s_red[wid] = m;
+  __syncthreads();
+  if (tid == 0) {
+    float v = s_red[0];
+    for (int i = 1; i < 16; ++i) v = fmaxf(v, s_red[i]);
+    s_glob[0] = v;
+  }
+  __syncthreads();
+  m = s_glob[0];
+  float l = 0.f;
+  for (int t = tid; t < n; t += 512) {
+    const float mt = parts[t * stride];
+    const float w = (mt > -CUDART_INF_F) ? __expf(mt - m) : 0.f;
+    s_w[t] = w;
+    l += parts[t * stride + 1] * w;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+  __syncthreads();
+  if (lane == 0) s_red[wid] = l;
+  __syncthreads();
+  if (tid == 0) {
+    float v = 0.f;
+    for (int i = 0; i < 16; ++i) v += s_red[i];
+    s_glob[1] = v;
+    ml[0] = m; ml[1] = v;
+  }
+  __syncthreads();
+  l = s_glob[1];
+  for (int c0 = tid; c0 < L; c0 += 512) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int t = 0;
+    for (; t + 4 <= n; t += 4) {
+      a0 = fmaf(parts[(t + 0) * stride + 2 + c0], s_w[t + 0], a0);
+      a1 = fmaf(parts[(t + 1) * stride + 2 + c0], s_w[t + 1], a1);
+      a2 = fmaf(parts[(t + 2) * stride + 2 + c0], s_w[t + 2], a2);
+      a3 = fmaf(parts[(t + 3) * stride + 2 + c0], s_w[t + 3], a3);
+    }
+    for (; t < n; ++t) a0 = fmaf(parts[t * stride + 2 + c0], s_w[t], a0);
+    const float mv = ((a0 + a1) + (a2 + a3)) / l;
+    s_M[c0] = mv;
+    M[c0] = mv;
+  }
+  __syncthreads();
+  // logits: warp j computes class j
+  if (wid < K) {
     float d = 0.f;
-    for (int l = lane; l < Lin; l += 32) d = fmaf(mrow[l], Wk[(long long)j * Lin + l], d);
+    for (int c0 = lane; c0 < L; c0 += 32) d = fmaf(s_M[c0], Wk[(long long)wid * L + c0], d);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-    const float logit = d + bk[j];
-    if (logit > best) { best = logit; besti = j; }
-    const float h = 1.f / (1.f + expf(-logit));
-    surv *= (1.f - h);
-    if (lane == 0) { hazards[(long long)warp * K + j] = h; S[(long long)warp * K + j] = surv; }
+    if (lane == 0) s_logit[wid] = d + bk[wid];
   }
-  if (lane == 0 && Y_hat) Y_hat[warp] = besti;
+  __syncthreads();
+  if (tid == 0) {
+    float h[16], sv[16], dh[16], dS[16];
+    float surv = 1.f, best = -CUDART_INF_F;
+    int besti = 0;
+    for (int j = 0; j < K; ++j) {
+      const float lg = s_logit[j];
+      if (lg > best) { best = lg; besti = j; }
+      h[j] = 1.f / (1.f + expf(-lg));
+      surv *= (1.f - h[j]);
+      sv[j] = surv;
+      hazards[j] = h[j]; S[j] = surv;
+      dh[j] = 0.f; dS[j] = 0.f;
+    }
+    if (Y_hat) *Y_hat = besti;
+    const long long y = Yp[0];
+    const float cb = cp[0];
+    const float sp_y = (y == 0) ? 1.f : sv[y - 1], h_y = h[y], sp_y1 = sv[y];
+    const float unc = -(1.f - cb) * (logf(fmaxf(sp_y, eps)) + logf(fmaxf(h_y, eps)));
+    const float cen = -cb * logf(fmaxf(sp_y1, eps));
+    *loss = (1.f - alpha) * (cen + unc) + alpha * unc;
+    if (y > 0 && sp_y >= eps) dS[y - 1] += -(1.f - cb) / sp_y;
+    if (sp_y1 >= eps) dS[y] += -(1.f - alpha) * cb / sp_y1;
+    if (h_y >= eps) dh[y] += -(1.f - cb) / h_y;
+    for (int j = 0; j < K; ++j) {
+      float g = dh[j];
+      float pre = 1.f;
+      for (int i = 0; i < j; ++i) pre *= (1.f - h[i]);
+      float run = pre;
+      for (int k = j; k < K; ++k) {
+        if (k > j) run *= (1.f - h[k]);
+        g -= dS[k] * run;
+      }
+      s_dlogit[j] = g * h[j] * (1.f - h[j]);
+    }
+  }
+  __syncthreads();
+  for (int c0 = tid; c0 < L; c0 += 512) {
+    float acc = 0.f;
+    const float mv = s_M[c0];
+    for (int j = 0; j < K; ++j) {
+      const float dl = s_dlogit[j];
+      acc = fmaf(dl, Wk[(long long)j * L + c0], acc);
+      if (dWk) dWk[(long long)j * L + c0] += dl * mv;
+    }
+    dM[c0] = acc;
+  }
+  if (dbk && tid < K) dbk[tid] += s_dlogit[tid];
 }
 
 // -------------------------------------------------------------------------------------------

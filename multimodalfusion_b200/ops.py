@@ -290,6 +290,25 @@ def hazard_head_bwd(M, Wk, haz, S, d_haz, d_S):
     return dM, dWk, dbk
 
 
+def amil_head_nll_step(partials, Wk, bk, Y, c, alpha: float, eps: float = 1e-7, dWk=None, dbk=None):
+    """Fused batch-1 step tail: returns dict(M, ml, hazards, S, Y_hat, loss, dM); dWk/dbk accumulate."""
+    _require_cuda(partials, Wk)
+    n, Lp2 = partials.shape
+    L, K = Lp2 - 2, Wk.shape[0]
+    dev = partials.device
+    out = dict(M=torch.empty(L, dtype=torch.float32, device=dev), ml=torch.empty(2, dtype=torch.float32, device=dev),
+               hazards=torch.empty(1, K, dtype=torch.float32, device=dev),
+               S=torch.empty(1, K, dtype=torch.float32, device=dev),
+               Y_hat=torch.empty(1, 1, dtype=torch.int64, device=dev),
+               loss=torch.empty((), dtype=torch.float32, device=dev),
+               dM=torch.empty(L, dtype=torch.float32, device=dev))
+    check(lib().mmf_amil_head_nll_step(_p(partials), n, L, _p(Wk), _p(bk), K, _p(Y), _p(c), float(alpha), float(eps),
+                                       _p(out["M"]), _p(out["ml"]), _p(out["hazards"]), _p(out["S"]),
+                                       _p(out["Y_hat"]), _p(out["loss"]), _p(out["dM"]), _p(dWk), _p(dbk),
+                                       _stream()), "mmf_amil_head_nll_step")
+    return out
+
+
 def nll_surv(hazards, S, Y, c, alpha: float, eps: float = 1e-7):
     """Returns (loss [scalar tensor], d_hazards, d_S)."""
     _require_cuda(hazards, S)

@@ -204,6 +204,64 @@ def test_amil_pooling_properties_at_full_size(dev):
     assert abs(torch.exp(A_raw - ml[0]).sum().item() / ml[1].item() - 1) < 1e-4
 
 
+@pytest.mark.parametrize("N,L,K,c_val,y", [(1, 256, 4, 0.0, 0), (300, 256, 4, 1.0, 3), (16384, 512, 8, 0.0, 5)])
+def test_fused_head_step_matches_modular_kernels(dev, N, L, K, c_val, y):
+    """mmf_amil_head_nll_step (combine + head + nll + head backward in one launch) == the modular
+    kernels == the oracle."""
+    from multimodalfusion_b200 import ops
+    g = torch.Generator().manual_seed(N + K)
+    tiles = (N + 127) // 128
+    parts = torch.randn(tiles, L + 2, generator=g)
+    parts[:, 1] = parts[:, 1].abs() + 0.5
+    parts[:, 2:] = parts[:, 2:].abs()
+    Wk, bk = torch.randn(K, L, generator=g) * 0.1, torch.randn(K, generator=g) * 0.1
+    Y, c = torch.tensor([y]), torch.tensor([c_val])
+    dWk, dbk = torch.zeros(K, L, device=dev), torch.zeros(K, device=dev)
+    t = ops.amil_head_nll_step(parts.to(dev), Wk.to(dev), bk.to(dev), Y.to(dev), c.to(dev), 0.15, dWk=dWk, dbk=dbk)
+    Mo, m, l = O.combine_partials(parts)
+    Mr = Mo.reshape(1, -1).clone().requires_grad_(True)
+    Wr, br = Wk.clone().requires_grad_(True), bk.clone().requires_grad_(True)
+    hz, S, Yh = O.hazard_head(Mr, Wr, br)
+    loss = O.nll_surv_loss(hz, S, Y, c, alpha=0.15)
+    loss.backward()
+    assert rel_err(t["M"], Mo) < 1e-5 and abs(t["ml"][0].item() - m.item()) < 1e-6
+    assert rel_err(t["hazards"], hz) < 1e-5 and rel_err(t["S"], S) < 1e-5 and torch.equal(t["Y_hat"].cpu(), Yh)
+    assert abs(t["loss"].item() - loss.item()) < 1e-5
+    assert rel_err(t["dM"], Mr.grad) < 1e-5 and rel_err(dWk, Wr.grad) < 1e-5 and rel_err(dbk, br.grad) < 1e-5
+    M2, ml2 = ops.amil_combine(parts.to(dev), L, True)
+    assert rel_err(t["M"], M2) < 1e-6
+
+
+def test_pair_kernel_matches_single_cta_kernel(dev):
+    """The CTA-pair tile kernel (default) and the single-CTA kernel (MMF_TILE_V1=1) are two
+    implementations of the same tile math: run the latter in a subprocess and compare."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, torch; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from test_gpu_parity import _rand_amil\nfrom oracle import cases\nfrom multimodalfusion_b200 import ops\n"
+        "dev = torch.device('cuda'); out = {}\n"
+        "for (N, L, D, g) in [(300, 256, 256, True), (700, 512, 384, True), (129, 256, 256, False)]:\n"
+        "    W = _rand_amil(L, D, g, N); prep = ops.prepare_amil_weights(*[None if t is None else t.to(dev) for t in W])\n"
+        "    x = cases.features(N, 77).to(dev).to(torch.bfloat16); fl = ops.amil_flags(g, True, True)\n"
+        "    A, M, ml = ops.amil_forward(x, prep, fl, 9)\n"
+        "    gr = ops.amil_backward(x, prep, fl, 9, A, ml, M, torch.ones(L, device=dev) * 0.1)\n"
+        "    out[(N, L, D, g)] = {k: v.cpu() for k, v in dict(A=A, M=M, **gr).items()}\n"
+        "torch.save(out, sys.argv[1])\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                             os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for v1 in ("0", "1"):
+        path = f"/tmp/mmf_tile_v{v1}.pt"
+        env = dict(os.environ, MMF_TILE_V1=v1)
+        subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=300)
+        res[v1] = torch.load(path, weights_only=False)
+    for key in res["0"]:
+        for k in res["0"][key]:
+            a, b = res["0"][key][k].float(), res["1"][key][k].float()
+            assert (a - b).abs().max().item() <= 2e-3 * b.abs().max().item() + 1e-5, (key, k)
+
+
 def _grad_check(model, gold_grads, tol, skip_tiny=1e-6):
     worst = {}
     for k, p in model.named_parameters():
