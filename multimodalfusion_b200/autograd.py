@@ -32,11 +32,9 @@ class AmilPool(torch.autograd.Function):
         if group is None:
             M, ml = ops.amil_combine(partials, prep.L, True)
         else:
+            from .parallel import all_gather_combine
             local = ops.amil_combine(partials, prep.L, False)
-            world = dist.get_world_size(group)
-            gathered = torch.empty(world, prep.L + 2, dtype=torch.float32, device=xb.device)
-            dist.all_gather_into_tensor(gathered, local.reshape(1, -1), group=group)
-            M, ml = ops.amil_combine(gathered, prep.L, True)
+            M, ml = all_gather_combine(local, lambda g: ops.amil_combine(g, prep.L, True), group)
         ctx.save_for_backward(xb, A_raw, M, ml)
         ctx.prep, ctx.flags, ctx.seed = prep, flags, seed
         ctx.x_dtype = x.dtype

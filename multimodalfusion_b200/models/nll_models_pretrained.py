@@ -10,7 +10,7 @@ from .model_modules import XlinearFusion
 
 
 class multimodal_pretrained(nn.Module):
-    def __init__(self, dropout=True, n_classes=4, mode='radio_path_omic', train_type=None,
+    def __init__(self, input_dim: int = 37, dropout=True, n_classes=4, mode='radio_path_omic', train_type=None,
                  bag_loss=None, n_layers=1):
         super().__init__()
         self.n_classes, self.mode, self.train_type = n_classes, mode, train_type
