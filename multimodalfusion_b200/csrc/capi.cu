@@ -8,6 +8,7 @@
 #include "amil_tile2.cuh"
 #include <stdlib.h>
 #include "gemm_tc.cuh"
+#include "gemm2_tc.cuh"
 #include "mmf_host.cuh"
 #include "small_kernels.cuh"
 
@@ -49,9 +50,34 @@ int launch_gemm(const TMapSet& tmA, const TMapSet& tmB, const GemmArgs& g, int s
   return launch_status();
 }
 
+template <int A_MN, int B_MN, int EPI, int BN>
+int launch_gemm2(const TMapSet& tmA, const TMapSet& tmB, const GemmArgs& g, int splits, cudaStream_t st) {
+  using C = Gemm2Cfg<BN>;
+  static bool configured = false;
+  auto kern = gemm2_tc_kernel<A_MN, B_MN, EPI, BN>;
+  if (!configured) {
+    MMF_TRY(cuda_rc(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES)));
+    configured = true;
+  }
+  dim3 grid(2 * ((g.M + 255) / 256), (g.N + BN - 1) / BN, splits);
+  kern<<<grid, GEMM2_THREADS, C::SMEM_BYTES, st>>>(tmA, tmB, g);
+  return launch_status();
+}
+
+// split-K factor for the pair kernel: fill the 74 CTA-pair slots once
+int pick_splits_pair(int out_tiles, int kb_total, int* kb_per_split) {
+  int splits = 74 / out_tiles;   // floor: one wave of CTA pairs (148 SMs = 74 pairs)
+  if (splits < 1) splits = 1;
+  if (splits > kb_total) splits = kb_total;
+  int per = (kb_total + splits - 1) / splits;
+  splits = (kb_total + per - 1) / per;
+  *kb_per_split = per;
+  return splits;
+}
+
 // split-K factor so that the grid roughly fills 148 SMs once or twice
 int pick_splits(int out_tiles, int kb_total, int* kb_per_split) {
-  int splits = (148 + out_tiles - 1) / out_tiles;
+  int splits = 148 / out_tiles;  // floor: a single wave
   if (splits < 1) splits = 1;
   if (splits > kb_total) splits = kb_total;
   int per = (kb_total + splits - 1) / splits;
@@ -276,7 +302,9 @@ int mmf_amil_bwd_hidden(const void* x, int64_t N, int64_t ldx, const MmfAmilWeig
   ga.c_bf16 = c.dU; ga.ldc = L;
   ga.s_raw = A_raw; ga.ml = ml; ga.dM = dM; ga.H = c.Hb; ga.ldh = L; ga.colsum_ws = c.db1_ws;
   ga.du_scale = (flags & MMF_DROPOUT_H) ? (1.0f / 0.75f) : 1.0f;
-  MMF_TRY((launch_gemm<0, 1, EPI_DU>(tA, tB, ga, 1, st)));
+  if (use_tile_v1()) MMF_TRY((launch_gemm<0, 1, EPI_DU>(tA, tB, ga, 1, st)));
+  else if (L == 512) MMF_TRY((launch_gemm2<0, 1, EPI_DU, 512>(tA, tB, ga, 1, st)));
+  else MMF_TRY((launch_gemm2<0, 1, EPI_DU, 256>(tA, tB, ga, 1, st)));
   ReduceSegs segs = {};
   segs.n = 1;
   segs.s[0] = ReduceSeg{c.db1_ws, L, L, g->db1};
@@ -300,10 +328,15 @@ int mmf_amil_bwd_wgrad(const void* x, int64_t N, int64_t ldx, const MmfAmilWeigh
     MMF_TRY(make_tmap_bf16(&tB.m[0], x, (uint64_t)N, 1024, (uint64_t)ldx, 64));
     GemmArgs ga = {};
     ga.M = L; ga.N = 1024; ga.kb_total = kb_rows;
-    const int splits = pick_splits((L / 128) * (1024 / 256), kb_rows, &ga.kb_per_split);
     ga.a_seg_kb = kb_rows; ga.b_seg_n = 1024;
     ga.c_f32 = g->dW1; ga.ldc = 1024;
-    MMF_TRY((launch_gemm<1, 1, EPI_ATOMIC>(tA, tB, ga, splits, st)));
+    if (use_tile_v1()) {
+      const int splits = pick_splits((L / 128) * (1024 / 256), kb_rows, &ga.kb_per_split);
+      MMF_TRY((launch_gemm<1, 1, EPI_ATOMIC>(tA, tB, ga, splits, st)));
+    } else {
+      const int splits = pick_splits_pair(((L + 255) / 256) * (1024 / 256), kb_rows, &ga.kb_per_split);
+      MMF_TRY((launch_gemm2<1, 1, EPI_ATOMIC, 256>(tA, tB, ga, splits, st)));
+    }
   }
   {
     TMapSet tA = {}, tB = {};
@@ -311,10 +344,15 @@ int mmf_amil_bwd_wgrad(const void* x, int64_t N, int64_t ldx, const MmfAmilWeigh
     MMF_TRY(make_tmap_bf16(&tB.m[0], c.Hb, (uint64_t)N, L, L, 64));
     GemmArgs ga = {};
     ga.M = c.KD; ga.N = L; ga.kb_total = kb_rows;
-    const int splits = pick_splits((c.KD / 128) * ((L + 255) / 256), kb_rows, &ga.kb_per_split);
     ga.a_seg_kb = kb_rows; ga.b_seg_n = L;
     ga.c_f32 = g->dWab; ga.ldc = L;
-    MMF_TRY((launch_gemm<1, 1, EPI_ATOMIC>(tA, tB, ga, splits, st)));
+    if (use_tile_v1()) {
+      const int splits = pick_splits((c.KD / 128) * ((L + 255) / 256), kb_rows, &ga.kb_per_split);
+      MMF_TRY((launch_gemm<1, 1, EPI_ATOMIC>(tA, tB, ga, splits, st)));
+    } else {
+      const int splits = pick_splits_pair(((c.KD + 255) / 256) * ((L + 255) / 256), kb_rows, &ga.kb_per_split);
+      MMF_TRY((launch_gemm2<1, 1, EPI_ATOMIC, 256>(tA, tB, ga, splits, st)));
+    }
   }
   if (flags & MMF_NEED_DX) {
     TMapSet tA = {}, tB = {};
@@ -324,7 +362,8 @@ int mmf_amil_bwd_wgrad(const void* x, int64_t N, int64_t ldx, const MmfAmilWeigh
     ga.M = (int)N; ga.N = 1024; ga.kb_total = L / 64; ga.kb_per_split = ga.kb_total;
     ga.a_seg_kb = ga.kb_total; ga.b_seg_n = 1024;
     ga.c_bf16 = dx; ga.ldc = 1024;
-    MMF_TRY((launch_gemm<0, 1, EPI_STORE>(tA, tB, ga, 1, st)));
+    if (use_tile_v1()) MMF_TRY((launch_gemm<0, 1, EPI_STORE>(tA, tB, ga, 1, st)));
+    else MMF_TRY((launch_gemm2<0, 1, EPI_STORE, 512>(tA, tB, ga, 1, st)));
   }
   return MMF_OK;
 }
@@ -375,10 +414,15 @@ int mmf_linear_bf16_wgrad(const void* dY, int64_t M, int N, int64_t lddy, const 
   const int Ktot = n_segs * K_per_seg;
   GemmArgs ga = {};
   ga.M = N; ga.N = Ktot; ga.kb_total = (int)((M + 63) / 64);
-  const int splits = pick_splits((N / 128) * (Ktot / 256), ga.kb_total, &ga.kb_per_split);
   ga.a_seg_kb = ga.kb_total; ga.b_seg_n = K_per_seg;
   ga.c_f32 = dW; ga.ldc = Ktot;
-  MMF_TRY((launch_gemm<1, 1, EPI_ATOMIC>(tA, tB, ga, splits, st)));
+  if (use_tile_v1()) {
+    const int splits = pick_splits((N / 128) * (Ktot / 256), ga.kb_total, &ga.kb_per_split);
+    MMF_TRY((launch_gemm<1, 1, EPI_ATOMIC>(tA, tB, ga, splits, st)));
+  } else {
+    const int splits = pick_splits_pair(((N + 255) / 256) * (Ktot / 256), ga.kb_total, &ga.kb_per_split);
+    MMF_TRY((launch_gemm2<1, 1, EPI_ATOMIC, 256>(tA, tB, ga, splits, st)));
+  }
   if (db) {
     colsum_bf16_kernel<<<(N + 31) / 32, dim3(32, 8), 0, st>>>(
         reinterpret_cast<const __nv_bfloat16*>(dY), M, N, lddy, db, 1);
