@@ -80,12 +80,20 @@ __host__ __device__ __forceinline__ uint32_t drop_row_state(unsigned long long s
   uint32_t x = mix32((uint32_t)seed ^ (stream * 0x9E3779B9U));
   return mix32(x + row * 0x85EBCA6BU + (uint32_t)(seed >> 32));
 }
-// 4 bytes for columns 4*cg .. 4*cg+3 ; element kept iff byte >= 64 (p_drop = 0.25)
-__host__ __device__ __forceinline__ uint32_t drop_bits4(uint32_t row_state, uint32_t cg) {
-  return mix32(row_state ^ (cg * 0xC2B2AE35U));
+// One 32-bit hash covers 16 consecutive columns, 2 bits each: an element is DROPPED iff its 2-bit
+// field is 0 (p_drop = 1/4 exactly).
+__host__ __device__ __forceinline__ uint32_t drop_bits16(uint32_t row_state, uint32_t cg16) {
+  return mix32(row_state ^ (cg16 * 0xC2B2AE35U));
+}
+__host__ __device__ __forceinline__ bool drop_keep(uint32_t bits16, uint32_t idx) {
+  return ((bits16 >> (2u * idx)) & 3u) != 0u;
+}
+// 4-column view used by the single-CTA kernel: the 8 bits of columns 4*cg4 .. 4*cg4+3
+__host__ __device__ __forceinline__ uint32_t drop_bits4(uint32_t row_state, uint32_t cg4) {
+  return (drop_bits16(row_state, cg4 >> 2) >> (8u * (cg4 & 3u))) & 0xFFu;
 }
 __host__ __device__ __forceinline__ float drop_scale(uint32_t bits4, uint32_t j) {
-  return ((bits4 >> (8 * j)) & 0xFFu) >= 64u ? (1.0f / 0.75f) : 0.0f;
+  return ((bits4 >> (2u * j)) & 3u) != 0u ? (1.0f / 0.75f) : 0.0f;
 }
 
 template <int L, int D, bool GATED, int MODE>

@@ -84,13 +84,6 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     fence_barrier_init();
     tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmWab);
   }
-  // stage the per-column vectors once
-  for (int i = threadIdx.x; i < L; i += AMIL2_THREADS) {
-    vec[C::V_B1 + i] = __ldg(a.b1 + i);
-    if (MODE == AMIL_BWD_GATE) vec[C::V_DM + i] = __ldg(a.dM + i);
-  }
-  for (int i = threadIdx.x; i < C::KD; i += AMIL2_THREADS) vec[C::V_BAB + i] = __ldg(a.bab + i);
-  for (int i = threadIdx.x; i < D; i += AMIL2_THREADS) vec[C::V_WC + i] = __ldg(a.wc + i);
   if (warp == 2) {
     tmem_alloc_pair(smem_u32(&tmem_base_slot), 512);
     tmem_relinquish_pair();
@@ -189,6 +182,16 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     float* sS = vec + C::V_S;     // [2][128] per-half partial row sums (t_i in bwd, score in fwd)
     float* sP = vec + C::V_P;
     float* sRed = vec + C::V_RED;
+    // stage the per-column vectors once (epilogue warps only: the producer / MMA threads start at once).
+    // The inverted-dropout scale of h is folded into the bias: relu(u + b) * s == relu(s*u + s*b).
+    const float h_scale = drop_h ? (1.0f / 0.75f) : 1.0f;
+    for (int i = e; i < L; i += AMIL2_EPI_THREADS) {
+      vec[C::V_B1 + i] = __ldg(a.b1 + i) * h_scale;
+      if (MODE == AMIL_BWD_GATE) vec[C::V_DM + i] = __ldg(a.dM + i);
+    }
+    for (int i = e; i < C::KD; i += AMIL2_EPI_THREADS) vec[C::V_BAB + i] = __ldg(a.bab + i);
+    for (int i = e; i < D; i += AMIL2_EPI_THREADS) vec[C::V_WC + i] = __ldg(a.wc + i);
+    named_bar_sync(4, AMIL2_EPI_THREADS);
 
     // ---------------- EPI1: H = dropout(relu(U + b1)) -> swizzled smem -----------------
     mbar_wait(smem_u32(&bar_acc1), 0);
@@ -205,16 +208,18 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       if (ii + 1 < PIECES1) tmem_ld32(tq + (cb + 1) * 32, v[(ii + 1) & 1]);
       float (&u)[32] = v[ii & 1];
       const float4* b4p = reinterpret_cast<const float4*>(vec + C::V_B1 + cb * 32);
+      uint32_t hb0 = 0xFFFFFFFFu, hb1 = 0xFFFFFFFFu;   // all kept when dropout is off
+      if (drop_h) { hb0 = drop_bits16(rs_h, (uint32_t)(cb * 2)); hb1 = drop_bits16(rs_h, (uint32_t)(cb * 2 + 1)); }
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
         const float4 b4 = b4p[i >> 2];
-        u[i] = fmaxf(u[i] + b4.x, 0.f); u[i + 1] = fmaxf(u[i + 1] + b4.y, 0.f);
-        u[i + 2] = fmaxf(u[i + 2] + b4.z, 0.f); u[i + 3] = fmaxf(u[i + 3] + b4.w, 0.f);
-        if (drop_h) {
-          const uint32_t bits = drop_bits4(rs_h, (uint32_t)(cb * 8 + (i >> 2)));
-          u[i] *= drop_scale(bits, 0); u[i + 1] *= drop_scale(bits, 1);
-          u[i + 2] *= drop_scale(bits, 2); u[i + 3] *= drop_scale(bits, 3);
-        }
+        const uint32_t hb = (i < 16) ? hb0 : hb1;
+        const float r0 = fmaxf(fmaf(u[i], h_scale, b4.x), 0.f), r1 = fmaxf(fmaf(u[i + 1], h_scale, b4.y), 0.f);
+        const float r2 = fmaxf(fmaf(u[i + 2], h_scale, b4.z), 0.f), r3 = fmaxf(fmaf(u[i + 3], h_scale, b4.w), 0.f);
+        u[i] = drop_keep(hb, (i & 15)) ? r0 : 0.f;
+        u[i + 1] = drop_keep(hb, (i & 15) + 1) ? r1 : 0.f;
+        u[i + 2] = drop_keep(hb, (i & 15) + 2) ? r2 : 0.f;
+        u[i + 3] = drop_keep(hb, (i & 15) + 3) ? r3 : 0.f;
       }
       const uint32_t kb_base = h_base + (cb >> 1) * 16384;
 #pragma unroll
@@ -264,6 +269,7 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 
     // ---------------- EPI2: gate + score (fwd) / gate backward (bwd) -------------------
     float s_acc = 0.f;
+    const float attn_scale = drop_attn ? (1.0f / 0.75f) : 1.0f;
     const uint32_t rs_a = drop_row_state(a.seed, 1, (uint32_t)row);
     const uint32_t rs_g = drop_row_state(a.seed, 2, (uint32_t)row);
 #pragma unroll 1
@@ -280,6 +286,11 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         if (GATED) tmem_ld32(tq + buf * C::CHN + 128 + pc * 32, vg);
         tmem_ld_wait();
         float dwc_v[32];
+        uint32_t ab0 = 0xFFFFFFFFu, ab1 = 0xFFFFFFFFu, gb0 = 0xFFFFFFFFu, gb1 = 0xFFFFFFFFu;
+        if (drop_attn) {
+          ab0 = drop_bits16(rs_a, (uint32_t)(d0 >> 4)); ab1 = drop_bits16(rs_a, (uint32_t)(d0 >> 4) + 1);
+          gb0 = drop_bits16(rs_g, (uint32_t)(d0 >> 4)); gb1 = drop_bits16(rs_g, (uint32_t)(d0 >> 4) + 1);
+        }
         const float4* ba4p = reinterpret_cast<const float4*>(vec + C::V_BAB + d0);
         const float4* bb4p = reinterpret_cast<const float4*>(vec + C::V_BAB + D + d0);
         const float4* wc4p = reinterpret_cast<const float4*>(vec + C::V_WC + d0);
@@ -291,17 +302,13 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           const float bav[4] = {ba4.x, ba4.y, ba4.z, ba4.w};
           const float bbv[4] = {bb4.x, bb4.y, bb4.z, bb4.w};
           const float wcv[4] = {wc4.x, wc4.y, wc4.z, wc4.w};
-          uint32_t bits_a = 0, bits_g = 0;
-          if (drop_attn) {
-            bits_a = drop_bits4(rs_a, (uint32_t)((d0 + i) >> 2));
-            bits_g = drop_bits4(rs_g, (uint32_t)((d0 + i) >> 2));
-          }
 #pragma unroll
           for (int x2 = 0; x2 < 4; ++x2) {
             const float av = tanh_fast(va[i + x2] + bav[x2]);
             const float gv = GATED ? sigmoid_fast(vg[i + x2] + bbv[x2]) : 1.f;
-            const float ka = drop_attn ? drop_scale(bits_a, x2) : 1.f;
-            const float kg = (GATED && drop_attn) ? drop_scale(bits_g, x2) : 1.f;
+            const uint32_t ab = (i < 16) ? ab0 : ab1, gb = (i < 16) ? gb0 : gb1;
+            const float ka = drop_keep(ab, (i & 15) + x2) ? attn_scale : 0.f;
+            const float kg = (!GATED || drop_keep(gb, (i & 15) + x2)) ? (GATED ? attn_scale : 1.f) : 0.f;
             const float ad = av * ka, gd = gv * kg;
             if (MODE == AMIL_FWD) {
               s_acc = fmaf(wcv[x2], ad * gd, s_acc);

@@ -45,16 +45,17 @@ def _mix32(x: np.ndarray) -> np.ndarray:
 
 def dropout_scale_mask(seed: int, stream: int, rows: int, cols: int) -> torch.Tensor:
     """[rows, cols] tensor of {0, 1/0.75}: the inverted-dropout (p = 0.25) factor the kernels apply.
-    stream 0 = h, 1 = tanh branch, 2 = sigmoid branch."""
+    stream 0 = h, 1 = tanh branch, 2 = sigmoid branch. One 32-bit hash per (row, 16-column group),
+    2 bits per column, dropped iff the field is 0 (drop_row_state / drop_bits16 / drop_keep)."""
     m32 = np.uint64(0xFFFFFFFF)
     s0 = _mix32(np.array([(seed & 0xFFFFFFFF) ^ ((stream * 0x9E3779B9) & 0xFFFFFFFF)], dtype=np.uint64))
     r = np.arange(rows, dtype=np.uint64)
     row_state = _mix32((s0 + r * np.uint64(0x85EBCA6B) + np.uint64((seed >> 32) & 0xFFFFFFFF)) & m32)
-    cg = np.arange((cols + 3) // 4, dtype=np.uint64)
+    cg = np.arange((cols + 15) // 16, dtype=np.uint64)
     bits = _mix32(row_state[:, None] ^ ((cg[None, :] * np.uint64(0xC2B2AE35)) & m32))
-    j = np.arange(4, dtype=np.uint64)
-    bytes_ = (bits[:, :, None] >> (np.uint64(8) * j[None, None, :])) & np.uint64(0xFF)
-    keep = (bytes_ >= 64).reshape(rows, -1)[:, :cols]
+    j = np.arange(16, dtype=np.uint64)
+    fields = (bits[:, :, None] >> (np.uint64(2) * j[None, None, :])) & np.uint64(3)
+    keep = (fields != 0).reshape(rows, -1)[:, :cols]
     return torch.from_numpy(keep.astype(np.float32) / 0.75)
 
 
