@@ -49,6 +49,9 @@ enum {
 #define MMF_TILE_ROWS 128    /* instances per CTA tile; one (m, l, acc[L]) partial per tile */
 
 int mmf_version(void);
+/* DEBUG ONLY (process-global): device buffer of gridDim.x*16 uint64 that the fused tile kernels fill
+ * with clock64() phase stamps; NULL (default) disables it. Not for production use. */
+void mmf_debug_set_timing_buffer(void* device_u64_buffer);
 const char* mmf_error_string(int rc);
 
 /* Weights of fc(1024->L) + attention net, prepared once per optimizer step by the caller.

@@ -87,6 +87,7 @@ _PP = C.POINTER(C.c_void_p)
 # name -> (restype, argtypes); the single source of truth the symbol test checks against the header
 SIGNATURES = {
     "mmf_version": (_i, []),
+    "mmf_debug_set_timing_buffer": (None, [_vp]),
     "mmf_error_string": (C.c_char_p, [_i]),
     "mmf_cast_f32_to_bf16": (_i, [_vp, _vp, _i64, _vp]),
     "mmf_pack_wab": (_i, [_vp, _vp, _i, _i, _i, _vp]),

@@ -67,7 +67,10 @@ struct AmilArgs {
   long long lddg;
   float* colsum_ws;   // [tiles*4, NCOLS]
   float* dbc_ws;      // [tiles*4]
+  unsigned long long* dbg;  // optional [gridDim.x, 16] clock64 phase stamps (mmf_debug_set_timing_buffer)
 };
+
+#define MMF_STAMP(a, i) do { if ((a).dbg) (a).dbg[(long long)blockIdx.x * 16 + (i)] = clock64(); } while (0)
 
 // ---- counter-based dropout bits (shared with the oracle: oracle/dropout_mask.py) -------------
 __host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {

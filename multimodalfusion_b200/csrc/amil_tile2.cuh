@@ -76,6 +76,7 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const long long row0 = (long long)tile * 128;
 
   if (threadIdx.x == 0) {
+    MMF_STAMP(a, 0);
     for (int s = 0; s < C::NS1; ++s) { mbar_init(smem_u32(&bar_full1[s]), 1); mbar_init(smem_u32(&bar_empty1[s]), 1); }
     for (int s = 0; s < C::NS2; ++s) { mbar_init(smem_u32(&bar_full2[s]), 1); mbar_init(smem_u32(&bar_empty2[s]), 1); }
     mbar_init(smem_u32(&bar_acc1), 1);
@@ -93,11 +94,16 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   cluster_sync_all();   // both CTAs' barriers are initialised before any cross-CTA signal
   tc_fence_after();
   const uint32_t tmem = tmem_base_slot;
+  if (threadIdx.x == 0) MMF_STAMP(a, 1);
 
   if (warp == 0 && lane == 0) {
     // =============================== TMA producer (both CTAs) ==========================
-    for (int kb = 0; kb < C::KB1; ++kb) tma_prefetch_l2_2d(&tmX, kb * 64, (int)row0);
     for (int kb = 0; kb < C::KB1; ++kb) {
+      // the ring's first NS1 loads go out first; only then is the rest of this CTA's x tile prefetched
+      // into L2 (issuing all 16 prefetches up front queued the first real load behind them:
+      // first stage landed 8k cycles after the cluster sync)
+      if (kb == C::NS1)
+        for (int kp = C::NS1; kp < C::KB1; ++kp) tma_prefetch_l2_2d(&tmX, kp * 64, (int)row0);
       const int s = kb % C::NS1;
       const uint32_t ph = (kb / C::NS1) & 1;
       mbar_wait(smem_u32(&bar_empty1[s]), ph ^ 1);
@@ -109,7 +115,9 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       for (int j = 0; j < C::NH1; ++j)
         tma_load_2d_pair(dst + 16384 + j * 16384, &tmW1, full, kb * 64, j * 256 + 128 * (int)rank);
     }
+    MMF_STAMP(a, 2);
     mbar_wait(smem_u32(&bar_acc1), 0);   // GEMM1 retired: its ring (overlaying H / ring2) is free
+    MMF_STAMP(a, 3);
     for (int c = 0; c < C::NCH; ++c) {
       for (int kb = 0; kb < C::KB2; ++kb) {
         const int it = c * C::KB2 + kb;
@@ -130,6 +138,7 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const uint32_t ph = (kb / C::NS1) & 1;
       mbar_wait(smem_u32(&bar_full1[s]), ph);
       tc_fence_after();
+      if (kb == 0) MMF_STAMP(a, 5);
       const uint32_t xs = pool + s * C::STAGE1;
       const uint32_t ws = xs + 16384;
 #pragma unroll
@@ -143,9 +152,11 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       umma_commit_pair_mc(smem_u32(&bar_empty1[s]), 3);
     }
     umma_commit_pair_mc(smem_u32(&bar_acc1), 3);
+    MMF_STAMP(a, 6);
 
     mbar_wait_cluster(smem_u32(&bar_h), 0);   // both CTAs' H tiles written, GEMM1 TMEM columns drained
     tc_fence_after();
+    MMF_STAMP(a, 7);
     for (int c = 0; c < C::NCH; ++c) {
       const int buf = c & 1;
       mbar_wait_cluster(smem_u32(&bar_acc2_empty[buf]), ((c >> 1) & 1) ^ 1);
@@ -166,6 +177,7 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       }
       umma_commit_pair_mc(smem_u32(&bar_acc2_full[buf]), 3);
     }
+    MMF_STAMP(a, 8);
   } else if (warp >= 4) {
     // =============================== epilogue warps (both CTAs) ========================
     const uint32_t q = warp & 3;
@@ -192,51 +204,60 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     for (int i = e; i < C::KD; i += AMIL2_EPI_THREADS) vec[C::V_BAB + i] = __ldg(a.bab + i);
     for (int i = e; i < D; i += AMIL2_EPI_THREADS) vec[C::V_WC + i] = __ldg(a.wc + i);
     named_bar_sync(4, AMIL2_EPI_THREADS);
+    if (e == 0) MMF_STAMP(a, 9);
 
     // ---------------- EPI1: H = dropout(relu(U + b1)) -> swizzled smem -----------------
     mbar_wait(smem_u32(&bar_acc1), 0);
     tc_fence_after();
+    if (e == 0) MMF_STAMP(a, 10);
     float t_i = 0.f;
     constexpr int PIECES1 = L / 64;  // 32-column pieces per half
     const int cb0 = half * PIECES1;
     float v[2][32];
     tmem_ld32(tq + cb0 * 32, v[0]);
+    // two pieces per iteration so the TMEM double-buffer indices stay static; NOT fully unrolled: the
+    // fully unrolled body (8 x ~500 SASS instructions) thrashed the instruction cache
+    // (ncu: stall_no_inst 18 % of samples in the backward kernel)
+#pragma unroll 1
+    for (int i2 = 0; i2 < PIECES1; i2 += 2) {
 #pragma unroll
-    for (int ii = 0; ii < PIECES1; ++ii) {
-      const int cb = cb0 + ii;
-      tmem_ld_wait();
-      if (ii + 1 < PIECES1) tmem_ld32(tq + (cb + 1) * 32, v[(ii + 1) & 1]);
-      float (&u)[32] = v[ii & 1];
-      const float4* b4p = reinterpret_cast<const float4*>(vec + C::V_B1 + cb * 32);
-      uint32_t hb0 = 0xFFFFFFFFu, hb1 = 0xFFFFFFFFu;   // all kept when dropout is off
-      if (drop_h) { hb0 = drop_bits16(rs_h, (uint32_t)(cb * 2)); hb1 = drop_bits16(rs_h, (uint32_t)(cb * 2 + 1)); }
+      for (int par = 0; par < 2; ++par) {
+        const int ii = i2 + par;
+        const int cb = cb0 + ii;
+        tmem_ld_wait();
+        if (ii + 1 < PIECES1) tmem_ld32(tq + (cb + 1) * 32, v[par ^ 1]);
+        float (&u)[32] = v[par];
+        const float4* b4p = reinterpret_cast<const float4*>(vec + C::V_B1 + cb * 32);
+        uint32_t hb0 = 0xFFFFFFFFu, hb1 = 0xFFFFFFFFu;   // all kept when dropout is off
+        if (drop_h) { hb0 = drop_bits16(rs_h, (uint32_t)(cb * 2)); hb1 = drop_bits16(rs_h, (uint32_t)(cb * 2 + 1)); }
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        const float4 b4 = b4p[i >> 2];
-        const uint32_t hb = (i < 16) ? hb0 : hb1;
-        const float r0 = fmaxf(fmaf(u[i], h_scale, b4.x), 0.f), r1 = fmaxf(fmaf(u[i + 1], h_scale, b4.y), 0.f);
-        const float r2 = fmaxf(fmaf(u[i + 2], h_scale, b4.z), 0.f), r3 = fmaxf(fmaf(u[i + 3], h_scale, b4.w), 0.f);
-        u[i] = drop_keep(hb, (i & 15)) ? r0 : 0.f;
-        u[i + 1] = drop_keep(hb, (i & 15) + 1) ? r1 : 0.f;
-        u[i + 2] = drop_keep(hb, (i & 15) + 2) ? r2 : 0.f;
-        u[i + 3] = drop_keep(hb, (i & 15) + 3) ? r3 : 0.f;
-      }
-      const uint32_t kb_base = h_base + (cb >> 1) * 16384;
+        for (int i = 0; i < 32; i += 4) {
+          const float4 b4 = b4p[i >> 2];
+          const uint32_t hb = (i < 16) ? hb0 : hb1;
+          const float r0 = fmaxf(fmaf(u[i], h_scale, b4.x), 0.f), r1 = fmaxf(fmaf(u[i + 1], h_scale, b4.y), 0.f);
+          const float r2 = fmaxf(fmaf(u[i + 2], h_scale, b4.z), 0.f), r3 = fmaxf(fmaf(u[i + 3], h_scale, b4.w), 0.f);
+          u[i] = drop_keep(hb, (i & 15)) ? r0 : 0.f;
+          u[i + 1] = drop_keep(hb, (i & 15) + 1) ? r1 : 0.f;
+          u[i + 2] = drop_keep(hb, (i & 15) + 2) ? r2 : 0.f;
+          u[i + 3] = drop_keep(hb, (i & 15) + 3) ? r3 : 0.f;
+        }
+        const uint32_t kb_base = h_base + (cb >> 1) * 16384;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t p0 = pack_bf16x2(u[8 * j], u[8 * j + 1]), p1 = pack_bf16x2(u[8 * j + 2], u[8 * j + 3]);
-        const uint32_t p2 = pack_bf16x2(u[8 * j + 4], u[8 * j + 5]), p3 = pack_bf16x2(u[8 * j + 6], u[8 * j + 7]);
-        st_shared_v4(kb_base + sw128_offset(r, (cb & 1) * 4 + j), p0, p1, p2, p3);
-        if (MODE == AMIL_BWD_GATE) {
-          const uint32_t pk[4] = {p0, p1, p2, p3};
-          const float4* dm4 = reinterpret_cast<const float4*>(vec + C::V_DM + cb * 32 + 8 * j);
-          const float4 d0 = dm4[0], d1 = dm4[1];
-          const float dmv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t p0 = pack_bf16x2(u[8 * j], u[8 * j + 1]), p1 = pack_bf16x2(u[8 * j + 2], u[8 * j + 3]);
+          const uint32_t p2 = pack_bf16x2(u[8 * j + 4], u[8 * j + 5]), p3 = pack_bf16x2(u[8 * j + 6], u[8 * j + 7]);
+          st_shared_v4(kb_base + sw128_offset(r, (cb & 1) * 4 + j), p0, p1, p2, p3);
+          if (MODE == AMIL_BWD_GATE) {
+            const uint32_t pk[4] = {p0, p1, p2, p3};
+            const float4* dm4 = reinterpret_cast<const float4*>(vec + C::V_DM + cb * 32 + 8 * j);
+            const float4 d0 = dm4[0], d1 = dm4[1];
+            const float dmv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
-          for (int x2 = 0; x2 < 4; ++x2) {
-            const float2 hf = unpack_bf16x2(pk[x2]);
-            t_i = fmaf(hf.x, dmv[2 * x2], t_i);
-            t_i = fmaf(hf.y, dmv[2 * x2 + 1], t_i);
+            for (int x2 = 0; x2 < 4; ++x2) {
+              const float2 hf = unpack_bf16x2(pk[x2]);
+              t_i = fmaf(hf.x, dmv[2 * x2], t_i);
+              t_i = fmaf(hf.y, dmv[2 * x2 + 1], t_i);
+            }
           }
         }
       }
@@ -245,6 +266,7 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive_cluster(h_ready_leader);
+    if (e == 0) MMF_STAMP(a, 11);
 
     if (MODE == AMIL_BWD_GATE) sS[half * 128 + r] = t_i;
     if (MODE == AMIL_BWD_GATE || a.store_h) {
@@ -351,6 +373,7 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       if (lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&bar_acc2_empty[buf]), 0));
     }
 
+    if (e == 0) MMF_STAMP(a, 12);
     if (MODE == AMIL_BWD_GATE) {
       if (half == 0) {
         const float dsum = warp_sum(ds);
@@ -401,10 +424,12 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       }
       if (a.store_h && e == 0) tma_store_wait_all();
     }
+    if (e == 0) MMF_STAMP(a, 13);
     tc_fence_before();
   }
   __syncthreads();
   cluster_sync_all();   // the peer may still be reading this CTA's smem / TMEM through the pair MMA
+  if (threadIdx.x == 0) MMF_STAMP(a, 14);
   if (warp == 2) tmem_dealloc_pair(tmem, 512);
 }
 

@@ -157,6 +157,10 @@ int dispatch_amil(int L, int D, int gated, const void* x, int64_t N, int64_t ldx
   return MMF_E_UNSUPPORTED;
 }
 
+// debug-only global (the one exception to "no global state"): when set, the tile kernels write
+// clock64 phase stamps [gridDim.x][16]; see tools/phase_timing.py
+unsigned long long* g_timing_buffer = nullptr;
+
 int check_amil_common(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, int L, int D) {
   if (!x || !w || N <= 0 || ldx < 1024) return MMF_E_INVALID;
   if (!w->W1 || !w->b1 || !w->Wab || !w->Wab_packed || !w->bab || !w->wc || !w->bc) return MMF_E_INVALID;
@@ -170,6 +174,10 @@ int check_amil_common(const void* x, int64_t N, int64_t ldx, const MmfAmilWeight
 extern "C" {
 
 int mmf_version(void) { return MMF_ABI_VERSION; }
+
+void mmf_debug_set_timing_buffer(void* device_u64_buffer) {
+  g_timing_buffer = reinterpret_cast<unsigned long long*>(device_u64_buffer);
+}
 
 const char* mmf_error_string(int rc) {
   switch (rc) {
@@ -217,7 +225,7 @@ int mmf_amil_fwd(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w,
   AmilArgs a = {};
   a.N = N; a.b1 = w->b1; a.bab = w->bab; a.wc = w->wc; a.bc = w->bc;
   a.A_raw = A_raw; a.partials = partials; a.store_h = H_stash != nullptr;
-  a.flags = flags; a.seed = seed;
+  a.flags = flags; a.seed = seed; a.dbg = g_timing_buffer;
   return dispatch_amil<AMIL_FWD>(L, D, flags & MMF_GATED, x, N, ldx, w, a, H_stash, (cudaStream_t)stream);
 }
 
@@ -274,7 +282,7 @@ int mmf_amil_bwd_gate(const void* x, int64_t N, int64_t ldx, const MmfAmilWeight
   a.N = N; a.b1 = w->b1; a.bab = w->bab; a.wc = w->wc; a.bc = w->bc;
   a.A_raw = const_cast<float*>(A_raw); a.flags = flags; a.seed = seed;
   a.ml = ml; a.M = M; a.dM = dM; a.dA_raw = dA_raw;
-  a.dG = c.dG; a.lddg = c.KD; a.colsum_ws = c.cs; a.dbc_ws = c.dbc_ws;
+  a.dG = c.dG; a.lddg = c.KD; a.colsum_ws = c.cs; a.dbc_ws = c.dbc_ws; a.dbg = g_timing_buffer;
   MMF_TRY(dispatch_amil<AMIL_BWD_GATE>(L, D, c.gated, x, N, ldx, w, a, c.Hb, st));
   ReduceSegs segs = {};
   segs.n = 3;
