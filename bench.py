@@ -57,10 +57,54 @@ class ClockSampler:
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
+        self._nvml_start()
         return self
 
+    # NVML sampler thread: used when the nvidia-smi binary is missing or printed nothing
+    def _nvml_start(self):
+        self._stop, self._samples, self._thread = None, [], None
+        try:
+            import threading
+
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            return
+        self._stop = threading.Event()
+
+        def loop():
+            while not self._stop.is_set():
+                try:
+                    sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                    rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    self._samples.append((sm, mx, rs))
+                except Exception:
+                    pass
+                self._stop.wait(0.002)
+
+        self._thread = threading.Thread(target=loop, daemon=True)
+        self._thread.start()
+
+    def _nvml_result(self):
+        if self._thread is None:
+            return None
+        self._stop.set()
+        self._thread.join(timeout=2)
+        if not self._samples:
+            return None
+        import pynvml
+        bits = {"hw_slowdown": pynvml.nvmlClocksEventReasonHwSlowdown,
+                "hw_thermal_slowdown": pynvml.nvmlClocksEventReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": pynvml.nvmlClocksEventReasonSwThermalSlowdown,
+                "sw_power_cap": pynvml.nvmlClocksEventReasonSwPowerCap}
+        reasons = sorted(k for k, b in bits.items() if any(r & b for _, _, r in self._samples))
+        return {"sm_mhz": statistics.median(s for s, _, _ in self._samples), "sm_max_mhz": self._samples[0][1],
+                "reasons": reasons, "samples": len(self._samples), "source": "nvml"}
+
     def __exit__(self, *exc):
-        self.result = None
+        self.result = self._nvml_result()
         if self.proc is None:
             return
         self.proc.terminate()
@@ -82,9 +126,9 @@ class ClockSampler:
             for nm, v in zip(names, f[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
-        if sm:
+        if sm and (self.result is None or len(sm) >= 3):
             self.result = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                           "samples": len(sm)}
+                           "samples": len(sm), "source": "nvidia-smi"}
 
 
 def load_peaks():
@@ -157,11 +201,19 @@ def run_ours(args):
     loss_buf = torch.zeros((), device=dev)
     LAUNCHES_PER_STEP = 8  # tile fwd, fused combine+head+nll step, tile bwd, reduce, dU gemm, reduce, 2 wgrad GEMMs
 
+    # backward mode: "stash" (default: the training forward leaves h / branch activations in the backward
+    # workspace, no recompute GEMMs) or "recompute" (MMF_BENCH_BWD=recompute: the tile kernel runs again)
+    bwd_mode = os.environ.get("MMF_BENCH_BWD", "stash")
+    step_ws = ops.amil_bwd_workspace(N_BAG, prep, flags, dev)
+
     def step(x):
         flat.zero_()
-        A_raw, parts = ops.amil_partials(x, prep, flags, seed)
+        if bwd_mode == "stash":
+            A_raw, parts, ws = ops.amil_partials_train(x, prep, flags, seed, workspace=step_ws)
+        else:
+            (A_raw, parts), ws = ops.amil_partials(x, prep, flags, seed), None
         t = ops.amil_head_nll_step(parts, Wk, bk, Y, c, 0.0, dWk=views[6], dbk=views[7])
-        ops.amil_backward(x, prep, flags, seed, A_raw, t["ml"], t["M"], t["dM"], grads=grads)
+        ops.amil_backward(x, prep, flags, seed, A_raw, t["ml"], t["M"], t["dM"], grads=grads, stash=ws)
         loss_buf.copy_(t["loss"])
 
     # warm up eagerly (configures kernels), then capture one graph per bag
@@ -186,12 +238,14 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clk:
-        torch.cuda.synchronize()
-        ev0.record()
-        run_steps(args.steps, first=args.warmup)
-        ev1.record()
-        torch.cuda.synchronize()
+    clk = ClockSampler(local_rank)   # samples through the device-resident AND the e2e timed regions
+    clk.__enter__()
+    time.sleep(0.05)
+    torch.cuda.synchronize()
+    ev0.record()
+    run_steps(args.steps, first=args.warmup)
+    ev1.record()
+    torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     ms = ev0.elapsed_time(ev1)
@@ -247,6 +301,7 @@ def run_ours(args):
     ev1.record()
     torch.cuda.synchronize()
     e2e_ms = ev0.elapsed_time(ev1)
+    clk.__exit__(None, None, None)
     if world > 1:
         t = torch.tensor([e2e_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -274,6 +329,14 @@ def run_ours(args):
         def t_fwd(x):
             ops.amil_partials(x, prep, flags, seed)
 
+        def t_fwd_train(x):
+            ops.amil_partials_train(x, prep, flags, seed, workspace=step_ws)
+
+        def t_gate_stashed(x):
+            check(lib.mmf_amil_bwd_gate_stashed(N_BAG, C.byref(wst), L, D, flags, seed, A_raw.data_ptr(), ml.data_ptr(),
+                                                M.data_ptr(), dM.data_ptr(), None, C.byref(gstruct),
+                                                step_ws.data_ptr(), step_ws.numel(), st))
+
         def t_gate(x):
             check(lib.mmf_amil_bwd_gate(x.data_ptr(), N_BAG, 1024, C.byref(wst), L, D, flags, seed, A_raw.data_ptr(),
                                         ml.data_ptr(), M.data_ptr(), dM.data_ptr(), None, C.byref(gstruct), wsp,
@@ -287,7 +350,11 @@ def run_ours(args):
             check(lib.mmf_amil_bwd_wgrad(x.data_ptr(), N_BAG, 1024, C.byref(wst), L, D, flags, C.byref(gstruct), None,
                                          wsp, nbytes, st))
 
-        for name, fn in (("amil_tile_fwd", t_fwd), ("bwd_gate", t_gate), ("bwd_hidden", t_hidden), ("bwd_wgrad", t_wgrad)):
+        # (bwd_gate_stashed re-reads whatever the previous call left in the workspace: the arithmetic is
+        # meaningless after the first call, the memory traffic is identical)
+        for name, fn in (("amil_tile_fwd", t_fwd), ("amil_tile_fwd_train", t_fwd_train),
+                         ("bwd_gate_stashed", t_gate_stashed), ("bwd_gate_recompute", t_gate), ("bwd_hidden", t_hidden),
+                         ("bwd_wgrad", t_wgrad)):
             for i in range(3):
                 fn(bags[i % N_BAGS])
             reps = 16
@@ -322,7 +389,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "bag": [N_BAG, 1024], "preset": "big", "n_classes": K_CLASSES,
+            "config": {"workload": WORKLOAD, "bag": [N_BAG, 1024], "preset": "big", "n_classes": K_CLASSES, "backward": bwd_mode,
                        "l2": f"inputs rotate over {N_BAGS} distinct bags ({N_BAGS * N_BAG * 2048 >> 20} MiB) > 126 MB L2",
                        "parallelism": f"dp{world} (cohort data-parallel, one bag per rank per step, NCCL all-reduce of "
                                       f"{flat.numel() * 4} B of fp32 grads per step)" if world > 1 else "single GPU",

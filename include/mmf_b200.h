@@ -42,7 +42,9 @@ enum {
   MMF_GATED = 1,        /* Attn_Net_Gated (tanh ⊙ sigmoid) vs Attn_Net (tanh only) */
   MMF_DROPOUT_H = 2,    /* train mode: Dropout(0.25) on h = relu(fc(x)) (always on in the reference) */
   MMF_DROPOUT_ATTN = 4, /* train mode with dropout=True: Dropout(0.25) on the tanh / sigmoid outputs */
-  MMF_NEED_DX = 8       /* backward also produces dx (radio path: reduce_dim sits upstream) */
+  MMF_NEED_DX = 8,      /* backward also produces dx (radio path: reduce_dim sits upstream) */
+  MMF_STASHED = 16      /* mmf_amil_bwd*: the forward was mmf_amil_fwd_train on the same workspace — h and the
+                           branch activations are read from it instead of being recomputed */
 };
 
 #define MMF_IN_FEATURES 1024 /* ResNet50-layer3 feature width, fixed by the reference models */
@@ -113,6 +115,17 @@ int mmf_amil_combine(const float* partials, int64_t n, int L, int normalize, flo
 
 size_t mmf_amil_bwd_workspace_bytes(int64_t N, int L, int D, int flags);
 
+/* Training forward: same outputs as mmf_amil_fwd, and additionally leaves in `workspace` (sized by
+ * mmf_amil_bwd_workspace_bytes, 1024-byte aligned, kept alive by the caller until the backward)
+ * h as bf16 [N,L] and the pre-dropout branch outputs [tanh | sigmoid] as fp16 [N,2D] — 2L + 4D bytes
+ * per instance (2.5 KB big preset). mmf_amil_bwd with MMF_STASHED then skips both recompute GEMMs:
+ * its gate stage becomes one HBM-bound elementwise pass. Trades 40 MB of stores per 16k bag for
+ * 30 GFLOP of recompute; use mmf_amil_fwd + mmf_amil_bwd (no flag) when memory is the constraint.
+ * Replaces the same reference ops as mmf_amil_fwd, with autograd's saved activations made explicit. */
+int mmf_amil_fwd_train(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, int L, int D,
+                       int flags, uint64_t seed, float* A_raw, float* partials, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
 /* Backward of mmf_amil_fwd + combine, given dM = dLoss/dM [L] and optionally dA_raw [N].
  * Recomputes h and the attention activations tile by tile (nothing but A_raw, (m,l), M is kept
  * from the forward). Accumulates INTO g (caller zeroes or carries gradient accumulation).
@@ -134,6 +147,11 @@ int mmf_amil_bwd_gate(const void* x, int64_t N, int64_t ldx, const MmfAmilWeight
                       int flags, uint64_t seed, const float* A_raw, const float* ml, const float* M,
                       const float* dM, const float* dA_raw, const MmfAmilGrads* g, void* workspace,
                       size_t workspace_bytes, void* stream);
+/* gate stage of the MMF_STASHED backward (no x, no GEMM): dG formed in place from the stash. */
+int mmf_amil_bwd_gate_stashed(int64_t N, const MmfAmilWeights* w, int L, int D, int flags, uint64_t seed,
+                              const float* A_raw, const float* ml, const float* M, const float* dM,
+                              const float* dA_raw, const MmfAmilGrads* g, void* workspace,
+                              size_t workspace_bytes, void* stream);
 int mmf_amil_bwd_hidden(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, int L, int D,
                         int flags, const float* A_raw, const float* ml, const float* dM,
                         const MmfAmilGrads* g, void* workspace, size_t workspace_bytes, void* stream);

@@ -26,7 +26,7 @@ NVCC_FLAGS = [
 
 # error codes / flags mirrored from the header
 MMF_OK = 0
-MMF_GATED, MMF_DROPOUT_H, MMF_DROPOUT_ATTN, MMF_NEED_DX = 1, 2, 4, 8
+MMF_GATED, MMF_DROPOUT_H, MMF_DROPOUT_ATTN, MMF_NEED_DX, MMF_STASHED = 1, 2, 4, 8, 16
 ACT_NONE, ACT_RELU, ACT_SELU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3, 4
 
 
@@ -95,6 +95,9 @@ SIGNATURES = {
     "mmf_amil_fwd": (_i, [_vp, _i64, _i64, C.POINTER(AmilWeights), _i, _i, _i, _u64, _vp, _vp, _vp, _vp]),
     "mmf_amil_combine": (_i, [_vp, _i64, _i, _i, _vp, _vp, _vp]),
     "mmf_amil_bwd_workspace_bytes": (_sz, [_i64, _i, _i, _i]),
+    "mmf_amil_fwd_train": (_i, [_vp, _i64, _i64, C.POINTER(AmilWeights), _i, _i, _i, _u64, _vp, _vp, _vp, _sz, _vp]),
+    "mmf_amil_bwd_gate_stashed": (_i, [_i64, C.POINTER(AmilWeights), _i, _i, _i, _u64, _vp, _vp, _vp, _vp, _vp,
+                                       C.POINTER(AmilGrads), _vp, _sz, _vp]),
     "mmf_amil_bwd": (_i, [_vp, _i64, _i64, C.POINTER(AmilWeights), _i, _i, _i, _u64, _vp, _vp, _vp, _vp,
                           _vp, _vp, C.POINTER(AmilGrads), _vp, _vp, _sz, _vp]),
     "mmf_amil_bwd_gate": (_i, [_vp, _i64, _i64, C.POINTER(AmilWeights), _i, _i, _i, _u64, _vp, _vp, _vp, _vp, _vp,

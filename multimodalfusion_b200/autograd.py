@@ -20,7 +20,11 @@ class AmilPool(torch.autograd.Function):
     With ``group`` set, x is this rank's shard of the bag: the per-rank (m, l, acc) partial is
     all-gathered (L+2 floats per rank) and combined on every rank, so M is replicated; the backward
     then yields this rank's contribution to the weight gradients (sum over ranks = full gradient).
+
+    ``use_stash`` (class switch): True = the training forward stashes h / branch activations (2.5 KB per
+    instance) and the backward runs no recompute GEMM; False = the north star's recompute backward.
     """
+    use_stash = True
 
     @staticmethod
     def forward(ctx, x, W1, b1, Wa, ba, Wb, bb, wc, bc, prep, flags: int, seed: int, group=None):
@@ -28,7 +32,14 @@ class AmilPool(torch.autograd.Function):
         xb = ops.to_bf16(x)
         if x.requires_grad:
             flags |= MMF_NEED_DX
-        A_raw, partials = ops.amil_partials(xb, prep, flags, seed)
+        # training (some parameter or x needs a gradient): stash h and the branch activations for the
+        # backward instead of recomputing both GEMMs; inference keeps the N x L intermediates on chip
+        train = any(ctx.needs_input_grad[:9]) and ops.stash_supported() and AmilPool.use_stash
+        stash = None
+        if train:
+            A_raw, partials, stash = ops.amil_partials_train(xb, prep, flags, seed)
+        else:
+            A_raw, partials = ops.amil_partials(xb, prep, flags, seed)
         if group is None:
             M, ml = ops.amil_combine(partials, prep.L, True)
         else:
@@ -36,6 +47,7 @@ class AmilPool(torch.autograd.Function):
             local = ops.amil_combine(partials, prep.L, False)
             M, ml = all_gather_combine(local, lambda g: ops.amil_combine(g, prep.L, True), group)
         ctx.save_for_backward(xb, A_raw, M, ml)
+        ctx.stash = stash
         ctx.prep, ctx.flags, ctx.seed = prep, flags, seed
         ctx.x_dtype = x.dtype
         ctx.gated = Wb is not None
@@ -47,7 +59,8 @@ class AmilPool(torch.autograd.Function):
         prep = ctx.prep
         if dM is None:
             dM = torch.zeros(prep.L, dtype=torch.float32, device=xb.device)
-        g = ops.amil_backward(xb, prep, ctx.flags, ctx.seed, A_raw, ml, M, dM, dA)
+        g = ops.amil_backward(xb, prep, ctx.flags, ctx.seed, A_raw, ml, M, dM, dA, stash=ctx.stash)
+        ctx.stash = None
         D = prep.D
         dx = g["dx"].to(ctx.x_dtype) if (ctx.flags & MMF_NEED_DX) else None
         if ctx.gated:

@@ -56,6 +56,8 @@ struct AmilArgs {
   float* A_raw;     // fwd: out [N]; bwd: in
   float* partials;  // fwd: [tiles, L+2]
   int store_h;      // fwd: also TMA-store the H tile (stash). bwd: always stored.
+  uint16_t* AG;     // fwd stash: pre-dropout [tanh | sigmoid] branch outputs, fp16 [N, ldag] (or null)
+  long long ldag;
   int flags;
   unsigned long long seed;
   // backward only

@@ -334,12 +334,30 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             const float ad = av * ka, gd = gv * kg;
             if (MODE == AMIL_FWD) {
               s_acc = fmaf(wcv[x2], ad * gd, s_acc);
+              va[i + x2] = av;               // kept for the optional activation stash
+              if (GATED) vg[i + x2] = gv;
             } else {
               const float dq = ds * wcv[x2];
               dwc_v[i + x2] = ds * ad * gd;
               va[i + x2] = dq * gd * ka * (1.f - av * av);
               if (GATED) vg[i + x2] = dq * ad * kg * gv * (1.f - gv);
             }
+          }
+        }
+        if (MODE == AMIL_FWD && a.AG != nullptr && row_ok) {
+          // training forward: stash the pre-dropout branch activations (fp16) so that the backward
+          // needs neither GEMM again (amil_gate_ew.cuh consumes them in place)
+          uint4* dst_a = reinterpret_cast<uint4*>(a.AG + row * a.ldag + d0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            dst_a[j] = make_uint4(pack_f16x2(va[8 * j], va[8 * j + 1]), pack_f16x2(va[8 * j + 2], va[8 * j + 3]),
+                                  pack_f16x2(va[8 * j + 4], va[8 * j + 5]), pack_f16x2(va[8 * j + 6], va[8 * j + 7]));
+          if (GATED) {
+            uint4* dst_g = reinterpret_cast<uint4*>(a.AG + row * a.ldag + D + d0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              dst_g[j] = make_uint4(pack_f16x2(vg[8 * j], vg[8 * j + 1]), pack_f16x2(vg[8 * j + 2], vg[8 * j + 3]),
+                                    pack_f16x2(vg[8 * j + 4], vg[8 * j + 5]), pack_f16x2(vg[8 * j + 6], vg[8 * j + 7]));
           }
         }
         if (MODE == AMIL_BWD_GATE) {

@@ -6,6 +6,7 @@
 #include "../../include/mmf_b200.h"
 #include "amil_tile.cuh"
 #include "amil_tile2.cuh"
+#include "amil_gate_ew.cuh"
 #include <stdlib.h>
 #include "gemm_tc.cuh"
 #include "gemm2_tc.cuh"
@@ -19,7 +20,7 @@ namespace {
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct BwdWs {
-  size_t off_H, off_dG, off_dU, off_cs, off_dbc, off_db1, total;
+  size_t off_H, off_dG, off_dU, off_cs, off_dbc, off_db1, off_mask, total;
 };
 BwdWs bwd_layout(int64_t N, int L, int D, int gated) {
   const int64_t tiles = ((N + 255) / 256) * 2;  // padded to whole CTA pairs
@@ -33,6 +34,7 @@ BwdWs bwd_layout(int64_t N, int L, int D, int gated) {
   w.off_cs = o;  o = align_up(o + (size_t)tiles * 4 * ncols * 4, 1024);
   w.off_dbc = o; o = align_up(o + (size_t)tiles * 4 * 4, 1024);
   w.off_db1 = o; o = align_up(o + (size_t)tiles * 4 * L * 4, 1024);
+  w.off_mask = o; o = align_up(o + (size_t)N * (L / 32) * 4, 1024);   // 1 bit per element of H: [h > 0]
   w.total = o;
   return w;
 }
@@ -169,6 +171,26 @@ int check_amil_common(const void* x, int64_t N, int64_t ldx, const MmfAmilWeight
   return MMF_OK;
 }
 
+template <int L, int D, bool GATED, bool DROP>
+int launch_gate_ew2(const GateEwArgs& a, cudaStream_t st) {
+  using C = GateEwCfg<L, D, GATED>;
+  static bool configured = false;
+  auto kern = amil_gate_ew_kernel<L, D, GATED, DROP>;
+  if (!configured) {
+    MMF_TRY(cuda_rc(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES)));
+    configured = true;
+  }
+  const long long chunks = (a.N + C::ROWS - 1) / C::ROWS;
+  const int blocks = (int)(chunks < 148 ? chunks : 148);   // persistent: one CTA per SM
+  kern<<<blocks, C::THREADS, C::SMEM_BYTES, st>>>(a);
+  return launch_status();
+}
+template <int L, int D, bool GATED>
+int launch_gate_ew(const GateEwArgs& a, cudaStream_t st) {
+  return (a.flags & MMF_DROPOUT_ATTN) ? launch_gate_ew2<L, D, GATED, true>(a, st)
+                                      : launch_gate_ew2<L, D, GATED, false>(a, st);
+}
+
 }  // namespace
 
 extern "C" {
@@ -241,10 +263,31 @@ size_t mmf_amil_bwd_workspace_bytes(int64_t N, int L, int D, int flags) {
   return bwd_layout(N, L, D, flags & MMF_GATED).total;
 }
 
+// Training forward: mmf_amil_fwd that also leaves H (bf16 [N,L]) and the branch activations
+// (fp16 [N,KD], in the dG slot) in the backward workspace, for mmf_amil_bwd(... | MMF_STASHED).
+int mmf_amil_fwd_train(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, int L, int D,
+                       int flags, uint64_t seed, float* A_raw, float* partials, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  MMF_TRY(check_amil_common(x, N, ldx, w, L, D));
+  if (!A_raw || !partials || !workspace) return MMF_E_INVALID;
+  if (use_tile_v1()) return MMF_E_UNSUPPORTED;   // the single-CTA reference kernel has no stash epilogue
+  const int gated = flags & MMF_GATED;
+  const BwdWs lay = bwd_layout(N, L, D, gated);
+  if (workspace_bytes < lay.total) return MMF_E_WORKSPACE;
+  if (reinterpret_cast<uintptr_t>(workspace) & 1023u) return MMF_E_ALIGN;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  AmilArgs a = {};
+  a.N = N; a.b1 = w->b1; a.bab = w->bab; a.wc = w->wc; a.bc = w->bc;
+  a.A_raw = A_raw; a.partials = partials; a.store_h = 1;
+  a.AG = reinterpret_cast<uint16_t*>(ws + lay.off_dG); a.ldag = gated ? 2 * D : D;
+  a.flags = flags; a.seed = seed; a.dbg = g_timing_buffer;
+  return dispatch_amil<AMIL_FWD>(L, D, gated, x, N, ldx, w, a, ws + lay.off_H, (cudaStream_t)stream);
+}
+
 namespace {
 struct BwdCtx {
   BwdWs lay; int KD, ncols, gated; int64_t tiles;
-  __nv_bfloat16 *Hb, *dG, *dU; float *cs, *dbc_ws, *db1_ws;
+  __nv_bfloat16 *Hb, *dG, *dU; float *cs, *dbc_ws, *db1_ws; uint32_t* mask;
 };
 int bwd_ctx(BwdCtx* c, const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, int L, int D,
             int flags, void* workspace, size_t workspace_bytes) {
@@ -261,6 +304,7 @@ int bwd_ctx(BwdCtx* c, const void* x, int64_t N, int64_t ldx, const MmfAmilWeigh
   c->cs = reinterpret_cast<float*>(ws + c->lay.off_cs);
   c->dbc_ws = reinterpret_cast<float*>(ws + c->lay.off_dbc);
   c->db1_ws = reinterpret_cast<float*>(ws + c->lay.off_db1);
+  c->mask = reinterpret_cast<uint32_t*>(ws + c->lay.off_mask);
   c->KD = c->gated ? 2 * D : D;
   c->ncols = c->gated ? 3 * D : 2 * D;
   c->tiles = (N + 127) / 128;
@@ -284,6 +328,10 @@ int mmf_amil_bwd_gate(const void* x, int64_t N, int64_t ldx, const MmfAmilWeight
   a.ml = ml; a.M = M; a.dM = dM; a.dA_raw = dA_raw;
   a.dG = c.dG; a.lddg = c.KD; a.colsum_ws = c.cs; a.dbc_ws = c.dbc_ws; a.dbg = g_timing_buffer;
   MMF_TRY(dispatch_amil<AMIL_BWD_GATE>(L, D, c.gated, x, N, ldx, w, a, c.Hb, st));
+  if (!use_tile_v1()) {   // the pair dU GEMM reads [h > 0] as a bitmask (the stash path's gate kernel emits it itself)
+    relu_mask_kernel<<<(int)((N * (L / 32) + 255) / 256), 256, 0, st>>>(c.Hb, N * (L / 32), c.mask);
+    MMF_TRY(launch_status());
+  }
   ReduceSegs segs = {};
   segs.n = 3;
   segs.s[0] = ReduceSeg{c.cs, c.ncols, D, g->dwc};
@@ -291,6 +339,34 @@ int mmf_amil_bwd_gate(const void* x, int64_t N, int64_t ldx, const MmfAmilWeight
   segs.s[2] = ReduceSeg{c.dbc_ws, 1, 1, g->dbc};
   launch_reduce_rows(segs, c.tiles * 4, st);
   return launch_status();
+}
+
+// Stage 1 (stash variant): the forward was mmf_amil_fwd_train — H and the fp16 branch activations
+// are already in the workspace; dG is formed in place by an HBM-bound elementwise kernel.
+int mmf_amil_bwd_gate_stashed(int64_t N, const MmfAmilWeights* w, int L, int D, int flags, uint64_t seed,
+                              const float* A_raw, const float* ml, const float* M, const float* dM,
+                              const float* dA_raw, const MmfAmilGrads* g, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  if (!w || !w->wc || N <= 0 || !workspace) return MMF_E_INVALID;
+  if (!((L == 256 && D == 256) || (L == 512 && D == 384) || (L == 256 && D == 384))) return MMF_E_UNSUPPORTED;
+  if (!A_raw || !ml || !M || !dM || !g || !g->dbab || !g->dwc || !g->dbc) return MMF_E_INVALID;
+  const int gated = flags & MMF_GATED;
+  const BwdWs lay = bwd_layout(N, L, D, gated);
+  if (workspace_bytes < lay.total) return MMF_E_WORKSPACE;
+  if (reinterpret_cast<uintptr_t>(workspace) & 1023u) return MMF_E_ALIGN;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  cudaStream_t st = (cudaStream_t)stream;
+  GateEwArgs a = {};
+  a.N = N; a.H = reinterpret_cast<const __nv_bfloat16*>(ws + lay.off_H); a.AG = ws + lay.off_dG;
+  a.A_raw = A_raw; a.ml = ml; a.M = M; a.dM = dM; a.dA_raw = dA_raw; a.wc = w->wc;
+  a.dwc = g->dwc; a.dbab = g->dbab; a.dbc = g->dbc;
+  a.mask = reinterpret_cast<uint32_t*>(ws + lay.off_mask);
+  a.flags = flags; a.seed = seed;
+  int rc = MMF_E_UNSUPPORTED;
+  if (L == 256 && D == 256) rc = gated ? launch_gate_ew<256, 256, true>(a, st) : launch_gate_ew<256, 256, false>(a, st);
+  if (L == 512 && D == 384) rc = gated ? launch_gate_ew<512, 384, true>(a, st) : launch_gate_ew<512, 384, false>(a, st);
+  if (L == 256 && D == 384) rc = gated ? launch_gate_ew<256, 384, true>(a, st) : launch_gate_ew<256, 384, false>(a, st);
+  return rc;
 }
 
 // Stage 2: dU = (dG Wab + p dM^T) ⊙ relu'(H) [* 1/(1-p)] -> workspace (bf16 [N,L]); db1 += colsum.
@@ -310,9 +386,13 @@ int mmf_amil_bwd_hidden(const void* x, int64_t N, int64_t ldx, const MmfAmilWeig
   ga.c_bf16 = c.dU; ga.ldc = L;
   ga.s_raw = A_raw; ga.ml = ml; ga.dM = dM; ga.H = c.Hb; ga.ldh = L; ga.colsum_ws = c.db1_ws;
   ga.du_scale = (flags & MMF_DROPOUT_H) ? (1.0f / 0.75f) : 1.0f;
-  if (use_tile_v1()) MMF_TRY((launch_gemm<0, 1, EPI_DU>(tA, tB, ga, 1, st)));
-  else if (L == 512) MMF_TRY((launch_gemm2<0, 1, EPI_DU, 512>(tA, tB, ga, 1, st)));
-  else MMF_TRY((launch_gemm2<0, 1, EPI_DU, 256>(tA, tB, ga, 1, st)));
+  if (!use_tile_v1()) {
+    ga.mask = c.mask; ga.mask_ld = L / 32; ga.db1 = g->db1;
+    MMF_TRY(make_tmap_bf16(&tA.m[3], c.dU, (uint64_t)N, L, L, 128));   // output map (TMA store of the staged tile)
+    if (L == 512) return launch_gemm2<0, 1, EPI_DU, 512>(tA, tB, ga, 1, st);
+    return launch_gemm2<0, 1, EPI_DU, 256>(tA, tB, ga, 1, st);
+  }
+  MMF_TRY((launch_gemm<0, 1, EPI_DU>(tA, tB, ga, 1, st)));
   ReduceSegs segs = {};
   segs.n = 1;
   segs.s[0] = ReduceSeg{c.db1_ws, L, L, g->db1};
@@ -380,10 +460,16 @@ int mmf_amil_bwd(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w,
                  int flags, uint64_t seed, const float* A_raw, const float* ml, const float* M,
                  const float* dM, const float* dA_raw, const void* H_stash, const MmfAmilGrads* g,
                  void* dx, void* workspace, size_t workspace_bytes, void* stream) {
-  (void)H_stash;  // reserved: skip the fc recompute when the forward stashed H
+  (void)H_stash;  // superseded by MMF_STASHED (the stash lives in the workspace)
   if (!g || !g->dW1 || !g->db1 || !g->dWab || !g->dbab || !g->dwc || !g->dbc) return MMF_E_INVALID;
-  MMF_TRY(mmf_amil_bwd_gate(x, N, ldx, w, L, D, flags, seed, A_raw, ml, M, dM, dA_raw, g, workspace,
-                            workspace_bytes, stream));
+  if (flags & MMF_STASHED) {
+    MMF_TRY(check_amil_common(x, N, ldx, w, L, D));
+    MMF_TRY(mmf_amil_bwd_gate_stashed(N, w, L, D, flags, seed, A_raw, ml, M, dM, dA_raw, g, workspace,
+                                      workspace_bytes, stream));
+  } else {
+    MMF_TRY(mmf_amil_bwd_gate(x, N, ldx, w, L, D, flags, seed, A_raw, ml, M, dM, dA_raw, g, workspace,
+                              workspace_bytes, stream));
+  }
   MMF_TRY(mmf_amil_bwd_hidden(x, N, ldx, w, L, D, flags, A_raw, ml, dM, g, workspace, workspace_bytes, stream));
   return mmf_amil_bwd_wgrad(x, N, ldx, w, L, D, flags, g, dx, workspace, workspace_bytes, stream);
 }
@@ -533,7 +619,7 @@ int mmf_amil_head_nll_step(const float* partials, int64_t n, int L, const float*
                            float* hazards, float* S, int64_t* Y_hat, float* loss, float* dM, float* dWk,
                            float* dbk, void* stream) {
   if (!partials || !Wk || !bk || !Y || !c || !M || !ml || !hazards || !S || !loss || !dM) return MMF_E_INVALID;
-  if (n <= 0 || n > 4096 || L <= 0 || L > 1024 || K <= 0 || K > 16) return MMF_E_UNSUPPORTED;
+  if (n <= 0 || n > 4096 || L <= 0 || L > 1024 || (L & 1) || K <= 0 || K > 16) return MMF_E_UNSUPPORTED;
   amil_head_step_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(
       partials, (int)n, L, Wk, bk, K, reinterpret_cast<const long long*>(Y), c, alpha, eps, M, ml, hazards, S,
       reinterpret_cast<long long*>(Y_hat), loss, dM, dWk, dbk);

@@ -27,7 +27,7 @@ struct Gemm2Cfg {
   static constexpr uint32_t B_BYTES = NH * 16384u;
   static constexpr uint32_t STAGE = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 6 : 4;
-  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE + 1024;
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE + 2048 + 1024;   // ring + dM vector (EPI_DU) + slack
 };
 
 template <int A_MN, int B_MN, int EPI, int BN>
@@ -127,25 +127,90 @@ gemm2_tc_kernel(const __grid_constant__ TMapSet tmA, const __grid_constant__ TMa
       umma_commit_pair_mc(smem_u32(&bar_empty[s]), 3);
     }
     umma_commit_pair_mc(smem_u32(&bar_acc), 3);
+  } else if (warp >= 4 && EPI == EPI_DU) {
+    // ------------------------------- dU epilogue (both CTAs, 8 warps) -----------------
+    //   dU = (acc + p_i dM) ⊙ [h > 0] * scale  -> bf16, staged in the (now idle) operand ring in the
+    //   TMA 128B-swizzled layout and written out with one TMA store per 64-column block; db1 column
+    //   sums are taken from the staged tile. The ReLU mask comes as 1 bit per element (32 B per row
+    //   and thread instead of 512 B of H): the first version read H with per-thread 16 B loads and
+    //   stored dU the same way — its epilogue took ~35k of the kernel's 56k cycles.
+    const uint32_t q = warp & 3;
+    const uint32_t half = (warp - 4) >> 2;
+    const uint32_t e = threadIdx.x - 128;
+    const uint32_t r = q * 32 + lane;
+    const int row = m0 + (int)r;
+    const bool row_ok = row < g.M;
+    constexpr int PIECES = BN / 64;   // 32-column pieces per half
+    float* s_dm = reinterpret_cast<float*>(smem_raw + (pool - smem_u32(smem_raw)) + C::STAGES * C::STAGE);
+    for (int i = e; i < BN; i += 256) s_dm[i] = (n0 + i < g.N) ? __ldg(g.dM + n0 + i) : 0.f;
+    float p_row = 0.f;
+    uint32_t mw[PIECES];
+#pragma unroll
+    for (int i = 0; i < PIECES; ++i) mw[i] = 0u;
+    if (row_ok) {
+      p_row = __expf(g.s_raw[row] - g.ml[0]) / g.ml[1];
+      const uint32_t* mp = g.mask + (long long)row * g.mask_ld + (n0 >> 5) + half * PIECES;
+#pragma unroll
+      for (int i = 0; i < PIECES; ++i) mw[i] = __ldg(mp + i);
+    }
+    named_bar_sync(1, 256);           // s_dm visible
+    mbar_wait(smem_u32(&bar_acc), 0);  // every MMA retired: accumulator complete, operand ring idle
+    tc_fence_after();
+    float v[2][32];
+    tmem_ld32(tmem + ((q * 32u) << 16) + half * PIECES * 32, v[0]);
+#pragma unroll
+    for (int ii = 0; ii < PIECES; ++ii) {
+      const int cb = half * PIECES + ii;
+      tmem_ld_wait();
+      if (ii + 1 < PIECES) tmem_ld32(tmem + ((q * 32u) << 16) + (cb + 1) * 32, v[(ii + 1) & 1]);
+      float (&u)[32] = v[ii & 1];
+      const uint32_t bits = mw[ii];
+      const float4* dm4 = reinterpret_cast<const float4*>(s_dm + cb * 32);
+      uint32_t packed[16];
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 d = dm4[i >> 2];
+        const float o0 = (bits >> i) & 1u ? g.du_scale * fmaf(p_row, d.x, u[i]) : 0.f;
+        const float o1 = (bits >> (i + 1)) & 1u ? g.du_scale * fmaf(p_row, d.y, u[i + 1]) : 0.f;
+        const float o2 = (bits >> (i + 2)) & 1u ? g.du_scale * fmaf(p_row, d.z, u[i + 2]) : 0.f;
+        const float o3 = (bits >> (i + 3)) & 1u ? g.du_scale * fmaf(p_row, d.w, u[i + 3]) : 0.f;
+        packed[i >> 1] = pack_bf16x2(o0, o1);
+        packed[(i >> 1) + 1] = pack_bf16x2(o2, o3);
+      }
+      const uint32_t blk = pool + (cb >> 1) * 16384;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        st_shared_v4(blk + sw128_offset(r, (cb & 1) * 4 + j), packed[4 * j], packed[4 * j + 1], packed[4 * j + 2],
+                     packed[4 * j + 3]);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    named_bar_sync(1, 256);           // the staged tile is complete
+    if (e == 0) {
+      for (int kb = 0; kb < BN / 64; ++kb)
+        if (n0 + kb * 64 < g.N) tma_store_2d(&tmA.m[3], pool + kb * 16384, n0 + kb * 64, m0);
+      tma_store_commit();
+    }
+    // db1: column sums of the staged bf16 tile (rows past M were staged as zeros: their mask words are 0)
+    for (uint32_t cp = e; cp < (uint32_t)BN / 2; cp += 256) {
+      const uint32_t col = 2u * cp;
+      const uint32_t blk = pool + (col >> 6) * 16384u, chunk = (col & 63u) >> 3, inb = (col & 7u) * 2u;
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll 8
+      for (uint32_t rr = 0; rr < 128; ++rr) {
+        const float2 f = unpack_bf16x2(ld_shared_b32(blk + sw128_offset(rr, chunk) + inb));
+        a0 += f.x; a1 += f.y;
+      }
+      if (n0 + (int)col < g.N) { atomicAdd(g.db1 + n0 + col, a0); atomicAdd(g.db1 + n0 + col + 1, a1); }
+    }
+    if (e == 0) tma_store_wait_all();
   } else if (warp >= 4) {
     // ------------------------------- epilogue (both CTAs, 8 warps) --------------------
     const uint32_t q = warp & 3;
     const uint32_t half = (warp - 4) >> 2;
     const int row = m0 + q * 32 + lane;
     const bool row_ok = row < g.M;
-    const int tile128 = pair_m * 2 + (int)rank;
-    float p_row = 0.f;
-    if (EPI == EPI_DU && row_ok) p_row = __expf(g.s_raw[row] - g.ml[0]) / g.ml[1];
     constexpr int PIECES = BN / 64;   // 32-column pieces per half
-    // EPI_DU: the ReLU-mask source H is prefetched one piece ahead, the first piece while the
-    // mainloop still runs (the loads were the epilogue's dominant stall in ncu: 20 % of all samples
-    // sat on the first use of an H register)
-    uint4 hpre[4];
-    if (EPI == EPI_DU && row_ok) {
-      const uint4* hsrc = reinterpret_cast<const uint4*>(g.H + (long long)row * g.ldh + n0 + half * PIECES * 32);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) hpre[i] = __ldg(hsrc + i);
-    }
     mbar_wait(smem_u32(&bar_acc), 0);
     tc_fence_after();
 #pragma unroll 1
@@ -155,16 +220,6 @@ gemm2_tc_kernel(const __grid_constant__ TMapSet tmA, const __grid_constant__ TMa
       if (col0 >= g.N) break;
       float v[32];
       tmem_ld32(tmem + ((q * 32u) << 16) + cb * 32, v);
-      uint4 hcur[4];
-      if (EPI == EPI_DU) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) hcur[i] = hpre[i];
-        if (row_ok && ii + 1 < PIECES && col0 + 32 < g.N) {
-          const uint4* hsrc = reinterpret_cast<const uint4*>(g.H + (long long)row * g.ldh + col0 + 32);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) hpre[i] = __ldg(hsrc + i);
-        }
-      }
       tmem_ld_wait();
       if (EPI == EPI_STORE) {
         if (g.bias) {
@@ -188,7 +243,7 @@ gemm2_tc_kernel(const __grid_constant__ TMapSet tmA, const __grid_constant__ TMa
             for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
           }
         }
-      } else if (EPI == EPI_ATOMIC) {
+      } else {  // EPI_ATOMIC
         if (row_ok) {
           float* dst = g.c_f32 + (long long)row * g.ldc + col0;
 #pragma unroll
@@ -197,35 +252,6 @@ gemm2_tc_kernel(const __grid_constant__ TMapSet tmA, const __grid_constant__ TMa
                          "f"(v[i + 1]), "f"(v[i + 2]), "f"(v[i + 3])
                          : "memory");
         }
-      } else {  // EPI_DU
-        if (row_ok) {
-          uint32_t packed[16];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint32_t hw[4] = {hcur[i].x, hcur[i].y, hcur[i].z, hcur[i].w};
-            const float4 dm0 = __ldg(reinterpret_cast<const float4*>(g.dM + col0 + 8 * i));
-            const float4 dm1 = __ldg(reinterpret_cast<const float4*>(g.dM + col0 + 8 * i + 4));
-            const float dmv[8] = {dm0.x, dm0.y, dm0.z, dm0.w, dm1.x, dm1.y, dm1.z, dm1.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 hf = unpack_bf16x2(hw[j]);
-              const int c = 8 * i + 2 * j;
-              v[c] = hf.x > 0.f ? g.du_scale * fmaf(p_row, dmv[2 * j], v[c]) : 0.f;
-              v[c + 1] = hf.y > 0.f ? g.du_scale * fmaf(p_row, dmv[2 * j + 1], v[c + 1]) : 0.f;
-              packed[4 * i + j] = pack_bf16x2(v[c], v[c + 1]);
-            }
-          }
-          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(g.c_bf16) +
-                                                (long long)row * g.ldc + col0);
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = 0.f;
-        }
-        const float cs = warp_colsum32(v);
-        g.colsum_ws[((long long)tile128 * 4 + q) * g.N + col0 + lane] = cs;
       }
     }
     tc_fence_before();

@@ -38,6 +38,11 @@ struct GemmArgs {
   long long ldh;
   float* colsum_ws;          // [gridDim.x * 4, N] per-warp column sums of the stored tile
   float du_scale;            // 1, or 1/(1-p) when train-mode dropout was applied to h
+  // pair-kernel EPI_DU (gemm2_tc.cuh): 1-bit ReLU mask instead of H, direct db1 accumulation; the
+  // output tensor map travels in tmA.m[3]
+  const uint32_t* mask;      // [M, mask_ld] words, bit j of word w = (h[row, 32w + j] > 0)
+  long long mask_ld;
+  float* db1;                // [N] accumulated with atomicAdd
 };
 
 constexpr int GEMM_BM = 128, GEMM_BN = 256, GEMM_BK = 64, GEMM_STAGES = 4;

@@ -14,7 +14,7 @@ import torch
 
 from . import _lib
 from ._lib import (ACT_NONE, ACT_RELU, ACT_SELU, ACT_SIGMOID, ACT_TANH, MMF_DROPOUT_ATTN,
-                   MMF_DROPOUT_H, MMF_GATED, MMF_NEED_DX, AmilGrads, AmilWeights, check, lib)
+                   MMF_DROPOUT_H, MMF_GATED, MMF_NEED_DX, MMF_STASHED, AmilGrads, AmilWeights, check, lib)
 
 IN_FEATURES = 1024
 TILE_ROWS = 128
@@ -122,6 +122,43 @@ def amil_partials(x: torch.Tensor, w: AmilPrepared, flags: int, seed: int = 0,
     return A_raw, partials
 
 
+def stash_supported() -> bool:
+    """The activation stash lives in the CTA-pair kernel's epilogue; MMF_TILE_V1=1 (single-CTA reference
+    kernel) has none and always recomputes."""
+    import os
+    return os.environ.get("MMF_TILE_V1", "0")[:1] != "1"
+
+
+def amil_bwd_workspace(N: int, w: AmilPrepared, flags: int, device) -> torch.Tensor:
+    """1024-byte aligned uint8 view sized by mmf_amil_bwd_workspace_bytes."""
+    nbytes = lib().mmf_amil_bwd_workspace_bytes(N, w.L, w.D, flags)
+    buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+    off = (-buf.data_ptr()) % 1024
+    return buf[off:off + nbytes]
+
+
+def amil_partials_train(x: torch.Tensor, w: AmilPrepared, flags: int, seed: int = 0,
+                        workspace: Optional[torch.Tensor] = None):
+    """Training forward: (A_raw, partials, workspace) — the workspace now holds h (bf16) and the branch
+    activations (fp16) and must be handed to amil_backward(..., stash=workspace)."""
+    _require_cuda(x)
+    if x.dtype != torch.bfloat16 or x.dim() != 2 or x.shape[1] != IN_FEATURES or x.stride(1) != 1:
+        raise ValueError("x must be a bf16 [N,1024] tensor with unit inner stride")
+    N = x.shape[0]
+    if N == 0:
+        raise ValueError("empty bag")
+    if workspace is None:
+        workspace = amil_bwd_workspace(N, w, flags, x.device)
+    tiles = (N + TILE_ROWS - 1) // TILE_ROWS
+    A_raw = torch.empty(N, dtype=torch.float32, device=x.device)
+    partials = torch.empty(tiles, w.L + 2, dtype=torch.float32, device=x.device)
+    ws = w.struct()
+    check(lib().mmf_amil_fwd_train(_p(x), N, x.stride(0), C.byref(ws), w.L, w.D, flags, seed, _p(A_raw),
+                                   _p(partials), workspace.data_ptr(), workspace.numel(), _stream()),
+          "mmf_amil_fwd_train")
+    return A_raw, partials, workspace
+
+
 def amil_combine(partials: torch.Tensor, L: int, normalize: bool = True):
     """normalize: (M [L], ml [2]);  else one (L+2) partial row (m, l, acc)."""
     _require_cuda(partials)
@@ -144,8 +181,9 @@ def amil_forward(x: torch.Tensor, w: AmilPrepared, flags: int, seed: int = 0):
 
 
 def amil_backward(x: torch.Tensor, w: AmilPrepared, flags: int, seed: int, A_raw, ml, M, dM,
-                  dA_raw=None, grads: Optional[dict] = None):
-    """Returns dict(dW1, db1, dWab, dbab, dwc, dbc[, dx]); accumulates into `grads` if given."""
+                  dA_raw=None, grads: Optional[dict] = None, stash: Optional[torch.Tensor] = None):
+    """Returns dict(dW1, db1, dWab, dbab, dwc, dbc[, dx]); accumulates into `grads` if given.
+    stash = the workspace amil_partials_train filled: skips the recompute GEMMs (MMF_STASHED)."""
     _require_cuda(x, dM)
     N = x.shape[0]
     dev = x.device
@@ -161,17 +199,18 @@ def amil_backward(x: torch.Tensor, w: AmilPrepared, flags: int, seed: int, A_raw
         )
     need_dx = bool(flags & MMF_NEED_DX)
     dx = torch.empty(N, IN_FEATURES, dtype=torch.bfloat16, device=dev) if need_dx else None
-    nbytes = lib().mmf_amil_bwd_workspace_bytes(N, w.L, w.D, flags)
-    ws_buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
-    off = (-ws_buf.data_ptr()) % 1024
+    if stash is not None:
+        ws_view, flags = stash, flags | MMF_STASHED
+    else:
+        ws_view = amil_bwd_workspace(N, w, flags, dev)
     g = AmilGrads(_p(grads["dW1"]), _p(grads["db1"]), _p(grads["dWab"]), _p(grads["dbab"]),
                   _p(grads["dwc"]), _p(grads["dbc"]))
     wst = w.struct()
     dM = _f32c(dM).reshape(-1)
     dA = None if dA_raw is None else _f32c(dA_raw).reshape(-1)
     check(lib().mmf_amil_bwd(_p(x), N, x.stride(0), C.byref(wst), w.L, w.D, flags, seed, _p(A_raw), _p(ml),
-                             _p(M), _p(dM), _p(dA), None, C.byref(g), _p(dx), ws_buf.data_ptr() + off,
-                             nbytes, _stream()), "mmf_amil_bwd")
+                             _p(M), _p(dM), _p(dA), None, C.byref(g), _p(dx), ws_view.data_ptr(),
+                             ws_view.numel(), _stream()), "mmf_amil_bwd")
     if need_dx:
         grads["dx"] = dx
     return grads

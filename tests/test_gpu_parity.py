@@ -111,10 +111,13 @@ AMIL_SHAPES = [
 ]
 
 
+@pytest.mark.parametrize("stash", [False, True], ids=["recompute", "stash"])
 @pytest.mark.parametrize("N,L,D,gated,drop", AMIL_SHAPES)
-def test_amil_kernels_vs_bf16_oracle(dev, N, L, D, gated, drop):
+def test_amil_kernels_vs_bf16_oracle(dev, N, L, D, gated, drop, stash):
     """Forward (A_raw, M, m, l) and every gradient against the oracle fed with bf16 operands.
-    drop: MMF_DROPOUT_H (2) | MMF_DROPOUT_ATTN (4) — masks regenerated bit-exactly by the oracle."""
+    drop: MMF_DROPOUT_H (2) | MMF_DROPOUT_ATTN (4) — masks regenerated bit-exactly by the oracle.
+    stash: backward from the training forward's activation stash (mmf_amil_fwd_train + MMF_STASHED)
+    instead of the recompute tile kernel — same gradients, same tolerances."""
     from multimodalfusion_b200 import ops
     seed = 0x5EED0000 + N
     W = _rand_amil(L, D, gated, N + L)
@@ -123,7 +126,14 @@ def test_amil_kernels_vs_bf16_oracle(dev, N, L, D, gated, drop):
     prep = ops.prepare_amil_weights(*[None if t is None else t.to(dev) for t in W])
     flags = ops.amil_flags(gated) | drop
     xb = x.to(dev).to(torch.bfloat16)
-    A_raw, M, ml = ops.amil_forward(xb, prep, flags, seed)
+    ws = None
+    if stash:
+        A_raw, parts, ws = ops.amil_partials_train(xb, prep, flags, seed)
+        M, ml = ops.amil_combine(parts, L, True)
+        A2, M2, _ = ops.amil_forward(xb, prep, flags, seed)
+        assert torch.equal(A2, A_raw) and torch.equal(M2, M), "stashing must not change the forward"
+    else:
+        A_raw, M, ml = ops.amil_forward(xb, prep, flags, seed)
     hs = O.dropout_scale_mask(seed, 0, N, L) if drop & 2 else None
     as_ = O.dropout_scale_mask(seed, 1, N, D) if drop & 4 else None
     gs = O.dropout_scale_mask(seed, 2, N, D) if drop & 4 else None
@@ -136,19 +146,22 @@ def test_amil_kernels_vs_bf16_oracle(dev, N, L, D, gated, drop):
     assert abs(ml[1].item() - l.item()) < 5e-3 * l.item()
     dM = torch.randn(L, generator=torch.Generator().manual_seed(N)) * 0.1
     dA = torch.randn(N, generator=torch.Generator().manual_seed(N + 1)) * 0.01
-    gr = ops.amil_backward(xb, prep, flags | 8, seed, A_raw, ml, M, dM.to(dev), dA.to(dev))
+    gr = ops.amil_backward(xb, prep, flags | 8, seed, A_raw, ml, M, dM.to(dev), dA.to(dev), stash=ws)
     go = O.amil_backward(x, bfr(W1), bfr(Wa), bfr(Wb), wc, s, h, a, g, Mo, m, l, dM, dA, drop_h=bool(drop & 2),
                          a_scale=as_, g_scale=gs, need_dx=True)
     for k in ("dW1", "db1", "dWab", "dbab", "dwc", "dbc", "dx"):
         assert rel_err(gr[k], go[k]) < TOL_GRAD_TIGHT, k
-    # gradient accumulation contract: a second call adds
+    # gradient accumulation contract: a second call adds (the stash is consumed by the backward: refill it)
+    if stash:
+        ws = ops.amil_partials_train(xb, prep, flags, seed, workspace=ws)[2]
     gr2 = ops.amil_backward(xb, prep, flags, seed, A_raw, ml, M, dM.to(dev), dA.to(dev),
-                            grads={k: v for k, v in gr.items() if k != "dx"})
+                            grads={k: v for k, v in gr.items() if k != "dx"}, stash=ws)
     assert rel_err(gr2["dW1"], 2 * go["dW1"]) < TOL_GRAD_TIGHT
 
 
+@pytest.mark.parametrize("stash", [False, True], ids=["recompute", "stash"])
 @pytest.mark.parametrize("N", [10000, 16384])
-def test_amil_full_size_vs_oracle(dev, N):
+def test_amil_full_size_vs_oracle(dev, N, stash):
     """BASELINE configs 1 and the metric shape (16k x 1024, big preset), forward + backward."""
     from multimodalfusion_b200 import ops
     L, D = (256, 256) if N == 10000 else (512, 384)
@@ -158,12 +171,17 @@ def test_amil_full_size_vs_oracle(dev, N):
     prep = ops.prepare_amil_weights(*[t.to(dev) for t in W])
     flags = ops.amil_flags(True)
     xb = x.to(dev).to(torch.bfloat16)
-    A_raw, M, ml = ops.amil_forward(xb, prep, flags, 0)
+    ws = None
+    if stash:
+        A_raw, parts, ws = ops.amil_partials_train(xb, prep, flags, 0)
+        M, ml = ops.amil_combine(parts, L, True)
+    else:
+        A_raw, M, ml = ops.amil_forward(xb, prep, flags, 0)
     s32, h32, a32, g32 = O.fc_attention(x, W1, b1, Wa, ba, Wb, bb, wc, bc)
     M32, m32, l32 = O.softmax_pool(s32, h32)
     assert rel_err(A_raw, s32) < TOL_FWD_REF and rel_err(M, M32) < TOL_FWD_REF
     dM = torch.randn(L, generator=torch.Generator().manual_seed(1)) * 0.1
-    gr = ops.amil_backward(xb, prep, flags, 0, A_raw, ml, M, dM.to(dev))
+    gr = ops.amil_backward(xb, prep, flags, 0, A_raw, ml, M, dM.to(dev), stash=ws)
     go = O.amil_backward(x, W1, Wa, Wb, wc, s32, h32, a32, g32, M32, m32, l32, dM)
     for k in ("dW1", "db1", "dWab", "dbab", "dwc"):
         assert rel_err(gr[k], go[k]) < TOL_GRAD_REF, k
