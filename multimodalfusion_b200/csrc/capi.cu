@@ -19,6 +19,10 @@ namespace {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// debug-only global (the one exception to "no global state"): when set, the tensor-core kernels write
+// clock64 phase stamps [gridDim.x][16]; see tools/phase_timing.py
+unsigned long long* g_timing_buffer = nullptr;
+
 struct BwdWs {
   size_t off_H, off_dG, off_dU, off_cs, off_dbc, off_db1, off_mask, total;
 };
@@ -63,6 +67,41 @@ int launch_gemm2(const TMapSet& tmA, const TMapSet& tmB, const GemmArgs& g, int 
   }
   dim3 grid(2 * ((g.M + 255) / 256), (g.N + BN - 1) / BN, splits);
   kern<<<grid, GEMM2_THREADS, C::SMEM_BYTES, st>>>(tmA, tmB, g);
+  return launch_status();
+}
+
+// Grouped split-K launch of the pair kernel (both operands MN-major, EPI_ATOMIC, 256 x 512 tiles): up to two
+// problems over the same reduction axis share ONE wave of <= 74 CTA pairs (148 SMs). 256 x 512 tiles keep the
+// per-CTA operand stream at 48 KB per 1024 MMA cycles (47 B/clk, at the ~43 B/clk/SM L2 cap) where the
+// 256 x 256 tiles of two back-to-back launches needed 64 B/clk and ran the tensor pipe at 35-40 %.
+int launch_gemm2_grouped(const TMapSet& tmA, const TMapSet& tmB, GemmArgs ga, cudaStream_t st) {
+  constexpr int BN = 512;
+  using C = Gemm2Cfg<BN>;
+  static bool configured = false;
+  auto kern = gemm2_tc_kernel<1, 1, EPI_ATOMIC, BN>;
+  if (!configured) {
+    MMF_TRY(cuda_rc(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES)));
+    configured = true;
+  }
+  int tiles_total = 0;
+  for (int p = 0; p < ga.n_groups; ++p) {
+    GemmArgs::Group& P = ga.grp[p];
+    P.tiles_n = (P.N + BN - 1) / BN;
+    tiles_total += ((P.M + 255) / 256) * P.tiles_n;
+  }
+  int splits = 74 / tiles_total;
+  if (splits < 1) splits = 1;
+  if (splits > ga.kb_total) splits = ga.kb_total;
+  const int per = (ga.kb_total + splits - 1) / splits;
+  splits = (ga.kb_total + per - 1) / per;
+  int pairs = 0;
+  for (int p = 0; p < ga.n_groups; ++p) {
+    GemmArgs::Group& P = ga.grp[p];
+    P.splits = splits; P.kb_per_split = per; P.first_pair = pairs;
+    pairs += ((P.M + 255) / 256) * P.tiles_n * splits;
+  }
+  ga.dbg = g_timing_buffer;
+  kern<<<2 * pairs, GEMM2_THREADS, C::SMEM_BYTES, st>>>(tmA, tmB, ga);
   return launch_status();
 }
 
@@ -158,10 +197,6 @@ int dispatch_amil(int L, int D, int gated, const void* x, int64_t N, int64_t ldx
 #undef MMF_CASE
   return MMF_E_UNSUPPORTED;
 }
-
-// debug-only global (the one exception to "no global state"): when set, the tile kernels write
-// clock64 phase stamps [gridDim.x][16]; see tools/phase_timing.py
-unsigned long long* g_timing_buffer = nullptr;
 
 int check_amil_common(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, int L, int D) {
   if (!x || !w || N <= 0 || ldx < 1024) return MMF_E_INVALID;
@@ -387,7 +422,7 @@ int mmf_amil_bwd_hidden(const void* x, int64_t N, int64_t ldx, const MmfAmilWeig
   ga.s_raw = A_raw; ga.ml = ml; ga.dM = dM; ga.H = c.Hb; ga.ldh = L; ga.colsum_ws = c.db1_ws;
   ga.du_scale = (flags & MMF_DROPOUT_H) ? (1.0f / 0.75f) : 1.0f;
   if (!use_tile_v1()) {
-    ga.mask = c.mask; ga.mask_ld = L / 32; ga.db1 = g->db1;
+    ga.mask = c.mask; ga.mask_ld = L / 32; ga.db1 = g->db1; ga.dbg = g_timing_buffer;
     MMF_TRY(make_tmap_bf16(&tA.m[3], c.dU, (uint64_t)N, L, L, 128));   // output map (TMA store of the staged tile)
     if (L == 512) return launch_gemm2<0, 1, EPI_DU, 512>(tA, tB, ga, 1, st);
     return launch_gemm2<0, 1, EPI_DU, 256>(tA, tB, ga, 1, st);
@@ -410,36 +445,55 @@ int mmf_amil_bwd_wgrad(const void* x, int64_t N, int64_t ldx, const MmfAmilWeigh
   if ((flags & MMF_NEED_DX) && !dx) return MMF_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   const int kb_rows = (int)((N + 63) / 64);
-  {
+  if (!use_tile_v1()) {
+    // dW1 += dU^T X and dWab += dG^T H in one single-wave grouped launch
     TMapSet tA = {}, tB = {};
     MMF_TRY(make_tmap_bf16(&tA.m[0], c.dU, (uint64_t)N, L, L, 64));
+    MMF_TRY(make_tmap_bf16(&tA.m[1], c.dG, (uint64_t)N, c.KD, c.KD, 64));
     MMF_TRY(make_tmap_bf16(&tB.m[0], x, (uint64_t)N, 1024, (uint64_t)ldx, 64));
+    MMF_TRY(make_tmap_bf16(&tB.m[1], c.Hb, (uint64_t)N, L, L, 64));
     GemmArgs ga = {};
-    ga.M = L; ga.N = 1024; ga.kb_total = kb_rows;
-    ga.a_seg_kb = kb_rows; ga.b_seg_n = 1024;
-    ga.c_f32 = g->dW1; ga.ldc = 1024;
-    if (use_tile_v1()) {
+    ga.kb_total = kb_rows;
+    ga.n_groups = 2;
+    ga.grp[0].M = L; ga.grp[0].N = 1024; ga.grp[0].a_map = 0; ga.grp[0].b_map = 0;
+    ga.grp[0].c = g->dW1; ga.grp[0].ldc = 1024;
+    ga.grp[0].tma_reduce = 1;
+    MMF_TRY(make_tmap_f32(&tA.m[3], g->dW1, (uint64_t)L, 1024, 1024, 32));
+    if (L >= 512) {
+      ga.grp[1].M = c.KD; ga.grp[1].N = L; ga.grp[1].a_map = 1; ga.grp[1].b_map = 1;
+      ga.grp[1].c = g->dWab; ga.grp[1].ldc = L;
+      ga.grp[1].tma_reduce = 1;
+      MMF_TRY(make_tmap_f32(&tB.m[3], g->dWab, (uint64_t)c.KD, L, L, 32));
+    } else {
+      // L = 256 would fill only half of a 512-wide tile: compute dWab^T = H^T dG (M = L, N = KD) and store transposed
+      ga.grp[1].M = L; ga.grp[1].N = c.KD; ga.grp[1].a_map = 2; ga.grp[1].b_map = 2; ga.grp[1].trans = 1;
+      MMF_TRY(make_tmap_bf16(&tA.m[2], c.Hb, (uint64_t)N, L, L, 64));
+      MMF_TRY(make_tmap_bf16(&tB.m[2], c.dG, (uint64_t)N, c.KD, c.KD, 64));
+      ga.grp[1].c = g->dWab; ga.grp[1].ldc = L;
+    }
+    MMF_TRY(launch_gemm2_grouped(tA, tB, ga, st));
+  } else {
+    {
+      TMapSet tA = {}, tB = {};
+      MMF_TRY(make_tmap_bf16(&tA.m[0], c.dU, (uint64_t)N, L, L, 64));
+      MMF_TRY(make_tmap_bf16(&tB.m[0], x, (uint64_t)N, 1024, (uint64_t)ldx, 64));
+      GemmArgs ga = {};
+      ga.M = L; ga.N = 1024; ga.kb_total = kb_rows;
+      ga.a_seg_kb = kb_rows; ga.b_seg_n = 1024;
+      ga.c_f32 = g->dW1; ga.ldc = 1024;
       const int splits = pick_splits((L / 128) * (1024 / 256), kb_rows, &ga.kb_per_split);
       MMF_TRY((launch_gemm<1, 1, EPI_ATOMIC>(tA, tB, ga, splits, st)));
-    } else {
-      const int splits = pick_splits_pair(((L + 255) / 256) * (1024 / 256), kb_rows, &ga.kb_per_split);
-      MMF_TRY((launch_gemm2<1, 1, EPI_ATOMIC, 256>(tA, tB, ga, splits, st)));
     }
-  }
-  {
-    TMapSet tA = {}, tB = {};
-    MMF_TRY(make_tmap_bf16(&tA.m[0], c.dG, (uint64_t)N, c.KD, c.KD, 64));
-    MMF_TRY(make_tmap_bf16(&tB.m[0], c.Hb, (uint64_t)N, L, L, 64));
-    GemmArgs ga = {};
-    ga.M = c.KD; ga.N = L; ga.kb_total = kb_rows;
-    ga.a_seg_kb = kb_rows; ga.b_seg_n = L;
-    ga.c_f32 = g->dWab; ga.ldc = L;
-    if (use_tile_v1()) {
+    {
+      TMapSet tA = {}, tB = {};
+      MMF_TRY(make_tmap_bf16(&tA.m[0], c.dG, (uint64_t)N, c.KD, c.KD, 64));
+      MMF_TRY(make_tmap_bf16(&tB.m[0], c.Hb, (uint64_t)N, L, L, 64));
+      GemmArgs ga = {};
+      ga.M = c.KD; ga.N = L; ga.kb_total = kb_rows;
+      ga.a_seg_kb = kb_rows; ga.b_seg_n = L;
+      ga.c_f32 = g->dWab; ga.ldc = L;
       const int splits = pick_splits((c.KD / 128) * ((L + 255) / 256), kb_rows, &ga.kb_per_split);
       MMF_TRY((launch_gemm<1, 1, EPI_ATOMIC>(tA, tB, ga, splits, st)));
-    } else {
-      const int splits = pick_splits_pair(((c.KD + 255) / 256) * ((L + 255) / 256), kb_rows, &ga.kb_per_split);
-      MMF_TRY((launch_gemm2<1, 1, EPI_ATOMIC, 256>(tA, tB, ga, splits, st)));
     }
   }
   if (flags & MMF_NEED_DX) {
@@ -620,9 +674,16 @@ int mmf_amil_head_nll_step(const float* partials, int64_t n, int L, const float*
                            float* dbk, void* stream) {
   if (!partials || !Wk || !bk || !Y || !c || !M || !ml || !hazards || !S || !loss || !dM) return MMF_E_INVALID;
   if (n <= 0 || n > 4096 || L <= 0 || L > 1024 || (L & 1) || K <= 0 || K > 16) return MMF_E_UNSUPPORTED;
-  amil_head_step_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(
-      partials, (int)n, L, Wk, bk, K, reinterpret_cast<const long long*>(Y), c, alpha, eps, M, ml, hazards, S,
-      reinterpret_cast<long long*>(Y_hat), loss, dM, dWk, dbk);
+  // cluster kernel: L splits into 8 CTAs x (column pairs that divide 512 threads), i.e. L in {256, 512, 1024}
+  const int cp = L / (2 * HEAD_CLUSTER);
+  if (L % (2 * HEAD_CLUSTER) == 0 && cp >= 16 && cp <= 64 && 512 % cp == 0)
+    amil_head_step_cluster_kernel<<<HEAD_CLUSTER, 512, 0, (cudaStream_t)stream>>>(
+        partials, (int)n, L, Wk, bk, K, reinterpret_cast<const long long*>(Y), c, alpha, eps, M, ml, hazards, S,
+        reinterpret_cast<long long*>(Y_hat), loss, dM, dWk, dbk);
+  else
+    amil_head_step_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(
+        partials, (int)n, L, Wk, bk, K, reinterpret_cast<const long long*>(Y), c, alpha, eps, M, ml, hazards, S,
+        reinterpret_cast<long long*>(Y_hat), loss, dM, dWk, dbk);
   return launch_status();
 }
 

@@ -18,6 +18,7 @@
 namespace mmf {
 
 constexpr int GEMM2_THREADS = 384;
+#define MMF_GSTAMP(g, i) do { if ((g).dbg) (g).dbg[(long long)blockIdx.x * 16 + (i)] = clock64(); } while (0)
 
 template <int BN>
 struct Gemm2Cfg {
@@ -46,14 +47,33 @@ gemm2_tc_kernel(const __grid_constant__ TMapSet tmA, const __grid_constant__ TMa
   const bool leader = rank == 0;
   const uint32_t pool = (smem_u32(smem_raw) + 1023u) & ~1023u;
 
-  const int pair_m = blockIdx.x >> 1, n_tile = blockIdx.y;
+  // problem decode: plain grid (pair_m, n_tile, split) or the grouped single-wave list
+  int pair_m = blockIdx.x >> 1, n_tile = blockIdx.y, split = blockIdx.z;
+  int gM = g.M, gN = g.N, kb_per_split = g.kb_per_split, a_map = 0, b_map = -1, trans = 0, tma_red = 0;
+  const CUtensorMap* cmap = &tmA.m[3];
+  float* c_f32 = g.c_f32;
+  long long ldc = g.ldc;
+  if (g.n_groups > 0) {
+    const int pair = blockIdx.x >> 1;
+    const GemmArgs::Group& P = g.grp[(g.n_groups > 1 && pair >= g.grp[1].first_pair) ? 1 : 0];
+    const int local = pair - P.first_pair;
+    split = local % P.splits;
+    const int t = local / P.splits;
+    n_tile = t % P.tiles_n;
+    pair_m = t / P.tiles_n;
+    gM = P.M; gN = P.N; kb_per_split = P.kb_per_split; a_map = P.a_map; b_map = P.b_map; trans = P.trans;
+    tma_red = P.tma_reduce;
+    if (&P != &g.grp[0]) cmap = &tmB.m[3];
+    c_f32 = P.c; ldc = P.ldc;
+  }
   const int m0 = pair_m * 256 + 128 * (int)rank;   // first output row of this CTA
   const int n0 = n_tile * BN;
-  const int kb0 = blockIdx.z * g.kb_per_split;
-  const int kb1 = min(g.kb_total, kb0 + g.kb_per_split);
+  const int kb0 = split * kb_per_split;
+  const int kb1 = min(g.kb_total, kb0 + kb_per_split);
   const int nkb = kb1 - kb0;
 
   if (threadIdx.x == 0) {
+    MMF_GSTAMP(g, 0);
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(smem_u32(&bar_full[s]), 1);
       mbar_init(smem_u32(&bar_empty[s]), 1);
@@ -70,6 +90,7 @@ gemm2_tc_kernel(const __grid_constant__ TMapSet tmA, const __grid_constant__ TMa
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem = tmem_base_slot;
+  if (threadIdx.x == 0) MMF_GSTAMP(g, 1);
 
   if (warp == 0 && lane == 0) {
     // ------------------------------- TMA producer (both CTAs) -------------------------
@@ -87,7 +108,7 @@ gemm2_tc_kernel(const __grid_constant__ TMapSet tmA, const __grid_constant__ TMa
         tma_load_2d_pair(a_dst, &tmA.m[seg], full, (kb - seg * g.a_seg_kb) * 64, m0);
       } else {
 #pragma unroll
-        for (int j = 0; j < 2; ++j) tma_load_2d_pair(a_dst + j * 8192, &tmA.m[0], full, m0 + j * 64, kb * 64);
+        for (int j = 0; j < 2; ++j) tma_load_2d_pair(a_dst + j * 8192, &tmA.m[a_map], full, m0 + j * 64, kb * 64);
       }
 #pragma unroll
       for (int h = 0; h < C::NH; ++h) {
@@ -95,8 +116,8 @@ gemm2_tc_kernel(const __grid_constant__ TMapSet tmA, const __grid_constant__ TMa
         if (B_MN == 0) {
           tma_load_2d_pair(b_dst + h * 16384, &tmB.m[0], full, kb * 64, nb);
         } else {
-          const int seg = nb / g.b_seg_n;
-          const int c0 = nb - seg * g.b_seg_n;
+          const int seg = b_map >= 0 ? b_map : nb / g.b_seg_n;
+          const int c0 = b_map >= 0 ? nb : nb - seg * g.b_seg_n;
 #pragma unroll
           for (int j = 0; j < 2; ++j)
             tma_load_2d_pair(b_dst + h * 16384 + j * 8192, &tmB.m[seg], full, c0 + j * 64, kb * 64);
@@ -111,6 +132,7 @@ gemm2_tc_kernel(const __grid_constant__ TMapSet tmA, const __grid_constant__ TMa
       const uint32_t ph = (i / C::STAGES) & 1;
       mbar_wait(smem_u32(&bar_full[s]), ph);
       tc_fence_after();
+      if (i == 0) MMF_GSTAMP(g, 2);
       const uint32_t a_src = pool + s * C::STAGE;
       const uint32_t b_src = a_src + C::A_BYTES;
 #pragma unroll
@@ -127,6 +149,7 @@ gemm2_tc_kernel(const __grid_constant__ TMapSet tmA, const __grid_constant__ TMa
       umma_commit_pair_mc(smem_u32(&bar_empty[s]), 3);
     }
     umma_commit_pair_mc(smem_u32(&bar_acc), 3);
+    MMF_GSTAMP(g, 3);
   } else if (warp >= 4 && EPI == EPI_DU) {
     // ------------------------------- dU epilogue (both CTAs, 8 warps) -----------------
     //   dU = (acc + p_i dM) ⊙ [h > 0] * scale  -> bf16, staged in the (now idle) operand ring in the
@@ -156,6 +179,7 @@ gemm2_tc_kernel(const __grid_constant__ TMapSet tmA, const __grid_constant__ TMa
     named_bar_sync(1, 256);           // s_dm visible
     mbar_wait(smem_u32(&bar_acc), 0);  // every MMA retired: accumulator complete, operand ring idle
     tc_fence_after();
+    if (e == 0) MMF_GSTAMP(g, 4);
     float v[2][32];
     tmem_ld32(tmem + ((q * 32u) << 16) + half * PIECES * 32, v[0]);
 #pragma unroll
@@ -203,21 +227,55 @@ gemm2_tc_kernel(const __grid_constant__ TMapSet tmA, const __grid_constant__ TMa
       }
       if (n0 + (int)col < g.N) { atomicAdd(g.db1 + n0 + col, a0); atomicAdd(g.db1 + n0 + col + 1, a1); }
     }
-    if (e == 0) tma_store_wait_all();
+    if (e == 0) { tma_store_wait_all(); MMF_GSTAMP(g, 5); }
   } else if (warp >= 4) {
     // ------------------------------- epilogue (both CTAs, 8 warps) --------------------
     const uint32_t q = warp & 3;
     const uint32_t half = (warp - 4) >> 2;
     const int row = m0 + q * 32 + lane;
-    const bool row_ok = row < g.M;
+    const bool row_ok = row < gM;
     constexpr int PIECES = BN / 64;   // 32-column pieces per half
     mbar_wait(smem_u32(&bar_acc), 0);
     tc_fence_after();
+    if (threadIdx.x == 128) MMF_GSTAMP(g, 4);
+    if (EPI == EPI_ATOMIC && tma_red) {
+      // split-K reduction through the TMA: each warp stages its 32 x 32 fp32 block in the idle operand ring
+      // (128-byte rows, 128B swizzle, two 4 KB buffers per warp) and issues one cp.reduce.async.bulk.tensor
+      // .add per block: full 128-byte lines reach the L2 instead of 32 scattered 16-byte red.global per
+      // warp instruction (the red epilogue took 18k of the wgrad kernel's 51k cycles).
+      const uint32_t wbuf = pool + (warp - 4) * 8192u;
+      const int row_w = m0 + (int)q * 32;
+#pragma unroll 1
+      for (int ii = 0; ii < PIECES; ++ii) {
+        const int cb = half * PIECES + ii;
+        const int col0 = n0 + cb * 32;
+        if (col0 >= gN || row_w >= gM) break;
+        float v[32];
+        tmem_ld32(tmem + ((q * 32u) << 16) + cb * 32, v);
+        const uint32_t buf = wbuf + (ii & 1) * 4096u;
+        if (ii >= 2) {
+          if (lane == 0) bulk_store_wait_read<1>();
+          __syncwarp();
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          st_shared_v4(buf + sw128_offset(lane, j), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                       __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_reduce_add_2d(cmap, buf, col0, row_w);
+          tma_store_commit();
+        }
+      }
+      if (lane == 0) tma_store_wait_all();
+    } else
 #pragma unroll 1
     for (int ii = 0; ii < PIECES; ++ii) {
       const int cb = half * PIECES + ii;
       const int col0 = n0 + cb * 32;
-      if (col0 >= g.N) break;
+      if (col0 >= gN) break;
       float v[32];
       tmem_ld32(tmem + ((q * 32u) << 16) + cb * 32, v);
       tmem_ld_wait();
@@ -232,32 +290,40 @@ gemm2_tc_kernel(const __grid_constant__ TMapSet tmA, const __grid_constant__ TMa
         if (row_ok) {
           if (g.c_bf16) {
             uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(g.c_bf16) +
-                                                  (long long)row * g.ldc + col0);
+                                                  (long long)row * ldc + col0);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
               dst[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
                                   pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
           } else {
-            float4* dst = reinterpret_cast<float4*>(g.c_f32 + (long long)row * g.ldc + col0);
+            float4* dst = reinterpret_cast<float4*>(c_f32 + (long long)row * ldc + col0);
 #pragma unroll
             for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
           }
         }
       } else {  // EPI_ATOMIC
-        if (row_ok) {
-          float* dst = g.c_f32 + (long long)row * g.ldc + col0;
+        if (row_ok && !trans) {
+          float* dst = c_f32 + (long long)row * ldc + col0;
 #pragma unroll
           for (int i = 0; i < 32; i += 4)
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(v[i]),
                          "f"(v[i + 1]), "f"(v[i + 2]), "f"(v[i + 3])
                          : "memory");
+        } else if (row_ok) {
+          // transposed store: the 32 lanes of a warp (consecutive rows) hit 32 consecutive floats
+          float* dst = c_f32 + (long long)col0 * ldc + row;
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (col0 + i < gN) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + (long long)i * ldc), "f"(v[i]) : "memory");
         }
       }
     }
+    if (threadIdx.x == 128) MMF_GSTAMP(g, 5);
     tc_fence_before();
   }
   __syncthreads();
   cluster_sync_all();
+  if (threadIdx.x == 0) MMF_GSTAMP(g, 6);
   if (warp == 2) tmem_dealloc_pair(tmem, BN);
 }
 

@@ -43,6 +43,23 @@ struct GemmArgs {
   const uint32_t* mask;      // [M, mask_ld] words, bit j of word w = (h[row, 32w + j] > 0)
   long long mask_ld;
   float* db1;                // [N] accumulated with atomicAdd
+  // pair-kernel grouped split-K mode (EPI_ATOMIC, both operands MN-major): n_groups > 0 packs up to two
+  // independent problems C_p += A_p^T B_p over the same reduction axis into ONE single-wave launch;
+  // grid.x = 2 * sum_p (tiles_m * tiles_n * splits), grid.y = grid.z = 1
+  unsigned long long* dbg;   // optional [gridDim.x, 16] clock64 phase stamps (mmf_debug_set_timing_buffer)
+  int n_groups;
+  struct Group {
+    int M, N;                // C_p is [M, N] (or [N, M] when trans)
+    int tiles_n, splits;     // tiles along N; split-K slices per tile
+    int kb_per_split;
+    int a_map, b_map;        // indices into tmA.m[] / tmB.m[]
+    int first_pair;          // first CTA-pair index of this group
+    int trans;               // store C^T: element (row, col) goes to c[col * ldc + row]
+    int tma_reduce;          // reduce through the TMA (cp.reduce.async.bulk.tensor .add) — output map in
+                             // tmA.m[3] (group 0) / tmB.m[3] (group 1), fp32 box [32 rows][32 cols]
+    float* c;
+    long long ldc;
+  } grp[2];
 };
 
 constexpr int GEMM_BM = 128, GEMM_BN = 256, GEMM_BK = 64, GEMM_STAGES = 4;

@@ -47,6 +47,24 @@ inline int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uin
   return r == CUDA_SUCCESS ? MMF_OK : MMF_E_TMAP;
 }
 
+// 2-D row-major fp32 array, box [box_rows][32 cols] (128-byte rows, 128-byte swizzle): the target of the
+// split-K epilogue's TMA reduce-add (cp.reduce.async.bulk.tensor ... .add); out-of-bounds elements are dropped.
+inline int make_tmap_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                         uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return MMF_E_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0 || (ld * 4) % 16 != 0) return MMF_E_ALIGN;
+  if (rows == 0 || cols == 0) return MMF_E_INVALID;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {ld * 4};
+  cuuint32_t box[2] = {32, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MMF_OK : MMF_E_TMAP;
+}
+
 inline int launch_status() {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {

@@ -459,6 +459,181 @@ amil_head_step_kernel(const float* __restrict__ parts, int n, int L, const float
 }
 
 // -------------------------------------------------------------------------------------------
+// Cluster version of amil_head_step_kernel: 8 CTAs (one thread-block cluster) split the L pooled
+// columns, so the combine is ONE batch of independent loads per thread (n/RG rows each) instead of
+// four dependent batches on a single SM, and the K partial logits of every CTA are exchanged through
+// distributed shared memory (st.shared::cluster) + one cluster barrier. Everything after the logits
+// (hazards, survival, nll_surv, dlogit) is a few hundred scalar cycles and is recomputed by every
+// CTA; CTA 0 writes the scalars. Same math, same outputs as the single-CTA kernel (kept for L that
+// does not split into 8 x 2 x power-of-two and as the reference implementation).
+// -------------------------------------------------------------------------------------------
+constexpr int HEAD_CLUSTER = 8;
+
+__device__ __forceinline__ void st_cluster_f32(uint32_t cluster_addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
+}
+
+__global__ void __cluster_dims__(HEAD_CLUSTER, 1, 1) __launch_bounds__(512)
+amil_head_step_cluster_kernel(const float* __restrict__ parts, int n, int L, const float* __restrict__ Wk,
+                              const float* __restrict__ bk, int K, const long long* __restrict__ Yp,
+                              const float* __restrict__ cp, float alpha, float eps, float* __restrict__ M,
+                              float* __restrict__ ml, float* __restrict__ hazards, float* __restrict__ S,
+                              long long* __restrict__ Y_hat, float* __restrict__ loss, float* __restrict__ dM,
+                              float* __restrict__ dWk, float* __restrict__ dbk) {
+  __shared__ float s_w[4096];
+  __shared__ float s_acc[1024];            // [RG][LC] partial column sums of this CTA's slice
+  __shared__ float s_M[128];               // this CTA's slice of M
+  __shared__ float s_Wk[16 * 128];         // this CTA's slice of the classifier [K][LC]
+  __shared__ float s_red[16];
+  __shared__ float s_plog[HEAD_CLUSTER][16];   // partial logits of every CTA (filled through DSMEM)
+  __shared__ float s_dlogit[16];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const uint32_t rank = cluster_ctarank();
+  const long long stride = L + 2;
+  const int LC = L / HEAD_CLUSTER;         // columns per CTA (32 .. 128)
+  const int c_lo = rank * LC;
+  const int CP = LC >> 1;                  // column pairs per CTA
+  const int RG = 512 / CP;                 // row groups
+  // early scalar loads (independent of everything else)
+  long long y = 0; float cb = 0.f;
+  if (tid == 0) { y = Yp[0]; cb = cp[0]; }
+  float2 mlv[8];
+  float m = -CUDART_INF_F;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int t = tid + 512 * j;
+    mlv[j] = (t < n) ? *reinterpret_cast<const float2*>(parts + t * stride) : make_float2(-CUDART_INF_F, 0.f);
+    m = fmaxf(m, mlv[j].x);
+  }
+  for (int i = tid; i < K * LC; i += 512) s_Wk[i] = Wk[(long long)(i / LC) * L + c_lo + (i % LC)];
+  // the combine's loads do not depend on the softmax weights: issue them now (16 rows per batch)
+  const int cpair = tid % CP, rg = tid / CP;
+  const float* col = parts + 2 + c_lo + 2 * cpair;
+  float2 v[16];
+#pragma unroll
+  for (int u = 0; u < 16; ++u) {
+    const int t = rg + u * RG;
+    v[u] = (t < n) ? *reinterpret_cast<const float2*>(col + t * stride) : make_float2(0.f, 0.f);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) s_red[wid] = m;
+  __syncthreads();
+  m = s_red[0];
+#pragma unroll
+  for (int i = 1; i < 16; ++i) m = fmaxf(m, s_red[i]);
+  float l = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int t = tid + 512 * j;
+    if (t < n) {
+      const float w = (mlv[j].x > -CUDART_INF_F) ? __expf(mlv[j].x - m) : 0.f;
+      s_w[t] = w;
+      l = fmaf(mlv[j].y, w, l);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+  __syncthreads();
+  if (lane == 0) s_red[wid] = l;
+  __syncthreads();
+  l = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) l += s_red[i];
+  if (rank == 0 && tid == 0) { ml[0] = m; ml[1] = l; }
+  float ax = 0.f, ay = 0.f;
+#pragma unroll
+  for (int u = 0; u < 16; ++u) {
+    const int t = rg + u * RG;
+    const float w = (t < n) ? s_w[t] : 0.f;
+    ax = fmaf(v[u].x, w, ax);
+    ay = fmaf(v[u].y, w, ay);
+  }
+  for (int t0 = rg + 16 * RG; t0 < n; t0 += 16 * RG) {   // n > 16 RG: further batches
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int t = t0 + u * RG;
+      v[u] = (t < n) ? *reinterpret_cast<const float2*>(col + t * stride) : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int t = t0 + u * RG;
+      const float w = (t < n) ? s_w[t] : 0.f;
+      ax = fmaf(v[u].x, w, ax);
+      ay = fmaf(v[u].y, w, ay);
+    }
+  }
+  s_acc[rg * LC + 2 * cpair] = ax;
+  s_acc[rg * LC + 2 * cpair + 1] = ay;
+  __syncthreads();
+  if (tid < LC) {
+    float a = 0.f;
+    for (int r = 0; r < RG; ++r) a += s_acc[r * LC + tid];
+    a /= l;
+    s_M[tid] = a;
+    M[c_lo + tid] = a;
+  }
+  __syncthreads();
+  // partial logits of this CTA's slice -> every CTA's s_plog[rank][j]
+  if (wid < K) {
+    float d = 0.f;
+    for (int c0 = lane; c0 < LC; c0 += 32) d = fmaf(s_M[c0], s_Wk[wid * LC + c0], d);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    if (lane < HEAD_CLUSTER) st_cluster_f32(mapa_cluster(smem_u32(&s_plog[rank][wid]), lane), d);
+  }
+  cluster_sync_all();
+  if (tid == 0) {
+    float h[16], sv[16], dh[16], dS[16];
+    float surv = 1.f, best = -CUDART_INF_F;
+    int besti = 0;
+    for (int j = 0; j < K; ++j) {
+      float lg = bk[j];
+      for (int r = 0; r < HEAD_CLUSTER; ++r) lg += s_plog[r][j];
+      if (lg > best) { best = lg; besti = j; }
+      h[j] = 1.f / (1.f + expf(-lg));
+      surv *= (1.f - h[j]);
+      sv[j] = surv;
+      dh[j] = 0.f; dS[j] = 0.f;
+    }
+    const float sp_y = (y == 0) ? 1.f : sv[y - 1], h_y = h[y], sp_y1 = sv[y];
+    if (rank == 0) {
+      for (int j = 0; j < K; ++j) { hazards[j] = h[j]; S[j] = sv[j]; }
+      if (Y_hat) *Y_hat = besti;
+      const float unc = -(1.f - cb) * (logf(fmaxf(sp_y, eps)) + logf(fmaxf(h_y, eps)));
+      const float cen = -cb * logf(fmaxf(sp_y1, eps));
+      *loss = (1.f - alpha) * (cen + unc) + alpha * unc;
+    }
+    if (y > 0 && sp_y >= eps) dS[y - 1] += -(1.f - cb) / sp_y;
+    if (sp_y1 >= eps) dS[y] += -(1.f - alpha) * cb / sp_y1;
+    if (h_y >= eps) dh[y] += -(1.f - cb) / h_y;
+    for (int j = 0; j < K; ++j) {
+      float g = dh[j];
+      float pre = 1.f;
+      for (int i = 0; i < j; ++i) pre *= (1.f - h[i]);
+      float run = pre;
+      for (int k = j; k < K; ++k) {
+        if (k > j) run *= (1.f - h[k]);
+        g -= dS[k] * run;
+      }
+      s_dlogit[j] = g * h[j] * (1.f - h[j]);
+    }
+  }
+  __syncthreads();
+  if (tid < LC) {
+    float acc = 0.f;
+    const float mv = s_M[tid];
+    for (int j = 0; j < K; ++j) {
+      const float dl = s_dlogit[j];
+      acc = fmaf(dl, s_Wk[j * LC + tid], acc);
+      if (dWk) dWk[(long long)j * L + c_lo + tid] += dl * mv;
+    }
+    dM[c_lo + tid] = acc;
+  }
+  if (rank == 0 && dbk && tid < K) dbk[tid] += s_dlogit[tid];
+}
+
+// -------------------------------------------------------------------------------------------
 // NLL survival loss (utils/loss_utils.py:22-39), forward + gradient. Single block.
 // -------------------------------------------------------------------------------------------
 __global__ void nll_surv_kernel(const float* __restrict__ haz, const float* __restrict__ S,
