@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(GateEwCfg<L, D, GATED>::THREADS, 1) amil_gate_
     bulk_load_1d(dst + C::H_BYTES, reinterpret_cast<const uint16_t*>(a.AG) + r0 * KD, nr * 2u * KD, bar);
   };
 
+  griddep_launch_dependents();
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) mbar_init(smem_u32(&bar_full[s]), 1);
     fence_barrier_init();
@@ -103,6 +104,7 @@ __global__ void __launch_bounds__(GateEwCfg<L, D, GATED>::THREADS, 1) amil_gate_
   }
   for (int i = threadIdx.x; i < 3 * D; i += C::THREADS) s_cols[i] = 0.f;
   __syncthreads();
+  griddep_wait();
   if (threadIdx.x == 0)
     for (long long k = 0; k < my_chunks && k < C::STAGES - 1; ++k) issue_load(k);
 

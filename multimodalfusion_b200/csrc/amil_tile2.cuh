@@ -39,8 +39,9 @@ struct Amil2Cfg {
   static constexpr uint32_t STAGE2 = (CHN / 2) * 128u;       // this CTA's half of the Wab chunk
   static constexpr uint32_t POOL = 208u * 1024u;
   static constexpr uint32_t VEC_BYTES = 16u * 1024u;
+  static constexpr uint32_t XPOSE_BYTES = 8u * 2048u;   // per-epilogue-warp 32 x 32 fp16 transpose scratch (stash stores)
   static constexpr int NS1 = (POOL / STAGE1) < 6 ? (POOL / STAGE1) : 6;
-  static constexpr int NS2 = ((POOL - H_BYTES) / STAGE2) < 8 ? ((POOL - H_BYTES) / STAGE2) : 8;
+  static constexpr int NS2 = ((POOL - H_BYTES - XPOSE_BYTES) / STAGE2) < 8 ? ((POOL - H_BYTES - XPOSE_BYTES) / STAGE2) : 8;
   static constexpr uint32_t SMEM_BYTES = POOL + VEC_BYTES + 1024u;
   static constexpr int NCOLS = GATED ? 3 * D : 2 * D;
   // float offsets inside the vector region
@@ -75,6 +76,7 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const int tile = blockIdx.x;
   const long long row0 = (long long)tile * 128;
 
+  griddep_launch_dependents();   // PDL: the next kernel's prologue may overlap this kernel's tail
   if (threadIdx.x == 0) {
     MMF_STAMP(a, 0);
     for (int s = 0; s < C::NS1; ++s) { mbar_init(smem_u32(&bar_full1[s]), 1); mbar_init(smem_u32(&bar_empty1[s]), 1); }
@@ -94,6 +96,7 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   cluster_sync_all();   // both CTAs' barriers are initialised before any cross-CTA signal
   tc_fence_after();
   const uint32_t tmem = tmem_base_slot;
+  griddep_wait();                // PDL: everything above overlapped the previous kernel; its outputs are visible now
   if (threadIdx.x == 0) MMF_STAMP(a, 1);
 
   if (warp == 0 && lane == 0) {
@@ -344,20 +347,32 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             }
           }
         }
-        if (MODE == AMIL_FWD && a.AG != nullptr && row_ok) {
-          // training forward: stash the pre-dropout branch activations (fp16) so that the backward
-          // needs neither GEMM again (amil_gate_ew.cuh consumes them in place)
-          uint4* dst_a = reinterpret_cast<uint4*>(a.AG + row * a.ldag + d0);
+        if (MODE == AMIL_FWD && a.AG != nullptr) {
+          // training forward: stash the pre-dropout branch activations (fp16) so that the backward needs
+          // neither GEMM again (amil_gate_ew.cuh consumes them in place). Each thread owns one ROW of the
+          // warp's 32 x 32 block; storing that directly is 32 scattered 16-byte writes per instruction
+          // (+10 us per 16k bag). The block is transposed through a 2 KB per-warp scratch so that every
+          // st.global.v4 covers 8 rows x 64 contiguous bytes (full 32-byte sectors).
+          const uint32_t scratch = pool + C::POOL - C::XPOSE_BYTES + (warp - 4) * 2048u;
+          const uint32_t orow = lane >> 2, ochunk = lane & 3u;
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            dst_a[j] = make_uint4(pack_f16x2(va[8 * j], va[8 * j + 1]), pack_f16x2(va[8 * j + 2], va[8 * j + 3]),
-                                  pack_f16x2(va[8 * j + 4], va[8 * j + 5]), pack_f16x2(va[8 * j + 6], va[8 * j + 7]));
-          if (GATED) {
-            uint4* dst_g = reinterpret_cast<uint4*>(a.AG + row * a.ldag + D + d0);
+          for (int br = 0; br < (GATED ? 2 : 1); ++br) {
+            const float (&src)[32] = br == 0 ? va : vg;
+            __syncwarp();   // the previous block's reads of the scratch are done
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              dst_g[j] = make_uint4(pack_f16x2(vg[8 * j], vg[8 * j + 1]), pack_f16x2(vg[8 * j + 2], vg[8 * j + 3]),
-                                    pack_f16x2(vg[8 * j + 4], vg[8 * j + 5]), pack_f16x2(vg[8 * j + 6], vg[8 * j + 7]));
+              st_shared_v4(scratch + lane * 64u + ((j ^ ((lane >> 1) & 3u)) << 4),
+                           pack_f16x2(src[8 * j], src[8 * j + 1]), pack_f16x2(src[8 * j + 2], src[8 * j + 3]),
+                           pack_f16x2(src[8 * j + 4], src[8 * j + 5]), pack_f16x2(src[8 * j + 6], src[8 * j + 7]));
+            __syncwarp();
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const uint32_t rr = 8u * t + orow;
+              const uint4 v4 = ld_shared_v4(scratch + rr * 64u + ((ochunk ^ ((rr >> 1) & 3u)) << 4));
+              const long long grow = row0 + q * 32 + rr;
+              if (grow < a.N)
+                *reinterpret_cast<uint4*>(a.AG + grow * a.ldag + br * D + d0 + ochunk * 8) = v4;
+            }
           }
         }
         if (MODE == AMIL_BWD_GATE) {

@@ -66,8 +66,7 @@ int launch_gemm2(const TMapSet& tmA, const TMapSet& tmB, const GemmArgs& g, int 
     configured = true;
   }
   dim3 grid(2 * ((g.M + 255) / 256), (g.N + BN - 1) / BN, splits);
-  kern<<<grid, GEMM2_THREADS, C::SMEM_BYTES, st>>>(tmA, tmB, g);
-  return launch_status();
+  return launch_pdl(kern, grid, dim3(GEMM2_THREADS), C::SMEM_BYTES, st, tmA, tmB, g);
 }
 
 // Grouped split-K launch of the pair kernel (both operands MN-major, EPI_ATOMIC, 256 x 512 tiles): up to two
@@ -101,8 +100,7 @@ int launch_gemm2_grouped(const TMapSet& tmA, const TMapSet& tmB, GemmArgs ga, cu
     pairs += ((P.M + 255) / 256) * P.tiles_n * splits;
   }
   ga.dbg = g_timing_buffer;
-  kern<<<2 * pairs, GEMM2_THREADS, C::SMEM_BYTES, st>>>(tmA, tmB, ga);
-  return launch_status();
+  return launch_pdl(kern, dim3(2 * pairs), dim3(GEMM2_THREADS), C::SMEM_BYTES, st, tmA, tmB, ga);
 }
 
 // split-K factor for the pair kernel: fill the 74 CTA-pair slots once
@@ -166,8 +164,7 @@ int launch_amil2(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w,
   if (Hbuf) MMF_TRY(make_tmap_bf16(&tmH, Hbuf, (uint64_t)N, L, L, 128));
   else tmH = tmX;
   const int pairs = (int)((N + 255) / 256);
-  kern<<<2 * pairs, AMIL2_THREADS, C::SMEM_BYTES, st>>>(tmX, tmW1, tmWab, tmH, a);
-  return launch_status();
+  return launch_pdl(kern, dim3(2 * pairs), dim3(AMIL2_THREADS), C::SMEM_BYTES, st, tmX, tmW1, tmWab, tmH, a);
 }
 
 // MMF_TILE_V1=1 selects the single-CTA kernel (kept as the reference implementation of the pair kernel)
@@ -217,8 +214,7 @@ int launch_gate_ew2(const GateEwArgs& a, cudaStream_t st) {
   }
   const long long chunks = (a.N + C::ROWS - 1) / C::ROWS;
   const int blocks = (int)(chunks < 148 ? chunks : 148);   // persistent: one CTA per SM
-  kern<<<blocks, C::THREADS, C::SMEM_BYTES, st>>>(a);
-  return launch_status();
+  return launch_pdl(kern, dim3(blocks), dim3(C::THREADS), C::SMEM_BYTES, st, a);
 }
 template <int L, int D, bool GATED>
 int launch_gate_ew(const GateEwArgs& a, cudaStream_t st) {
@@ -677,14 +673,12 @@ int mmf_amil_head_nll_step(const float* partials, int64_t n, int L, const float*
   // cluster kernel: L splits into 8 CTAs x (column pairs that divide 512 threads), i.e. L in {256, 512, 1024}
   const int cp = L / (2 * HEAD_CLUSTER);
   if (L % (2 * HEAD_CLUSTER) == 0 && cp >= 16 && cp <= 64 && 512 % cp == 0)
-    amil_head_step_cluster_kernel<<<HEAD_CLUSTER, 512, 0, (cudaStream_t)stream>>>(
-        partials, (int)n, L, Wk, bk, K, reinterpret_cast<const long long*>(Y), c, alpha, eps, M, ml, hazards, S,
-        reinterpret_cast<long long*>(Y_hat), loss, dM, dWk, dbk);
-  else
-    amil_head_step_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(
-        partials, (int)n, L, Wk, bk, K, reinterpret_cast<const long long*>(Y), c, alpha, eps, M, ml, hazards, S,
-        reinterpret_cast<long long*>(Y_hat), loss, dM, dWk, dbk);
-  return launch_status();
+    return launch_pdl(amil_head_step_cluster_kernel, dim3(HEAD_CLUSTER), dim3(512), 0, (cudaStream_t)stream,
+                      partials, (int)n, L, Wk, bk, K, reinterpret_cast<const long long*>(Y), c, alpha, eps, M, ml,
+                      hazards, S, reinterpret_cast<long long*>(Y_hat), loss, dM, dWk, dbk);
+  return launch_pdl(amil_head_step_kernel, dim3(1), dim3(512), 0, (cudaStream_t)stream, partials, (int)n, L, Wk, bk, K,
+                    reinterpret_cast<const long long*>(Y), c, alpha, eps, M, ml, hazards, S,
+                    reinterpret_cast<long long*>(Y_hat), loss, dM, dWk, dbk);
 }
 
 int mmf_nll_surv_fwd_bwd(const float* hazards, const float* S, const int64_t* Y, const float* c,

@@ -72,6 +72,7 @@ gemm2_tc_kernel(const __grid_constant__ TMapSet tmA, const __grid_constant__ TMa
   const int kb1 = min(g.kb_total, kb0 + kb_per_split);
   const int nkb = kb1 - kb0;
 
+  griddep_launch_dependents();
   if (threadIdx.x == 0) {
     MMF_GSTAMP(g, 0);
     for (int s = 0; s < C::STAGES; ++s) {
@@ -90,6 +91,7 @@ gemm2_tc_kernel(const __grid_constant__ TMapSet tmA, const __grid_constant__ TMa
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem = tmem_base_slot;
+  griddep_wait();
   if (threadIdx.x == 0) MMF_GSTAMP(g, 1);
 
   if (warp == 0 && lane == 0) {

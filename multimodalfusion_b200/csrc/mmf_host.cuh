@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/mmf_b200.h"
 
@@ -72,6 +73,34 @@ inline int launch_status() {
     return -(1000 + (int)e);
   }
   return MMF_OK;
+}
+
+// Launch with the programmatic-stream-serialization attribute (PDL): the kernel may be scheduled while the
+// previous kernel in the stream drains; every kernel launched this way calls griddep_wait() before it
+// touches global memory. MMF_NO_PDL=1 falls back to plain stream order (A/B timing, debugging).
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MMF_NO_PDL");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+template <typename... KArgs, typename... Args>
+inline int launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+  if (e != cudaSuccess) {
+    fprintf(stderr, "mmf: CUDA launch error: %s\n", cudaGetErrorString(e));
+    return -(1000 + (int)e);
+  }
+  return launch_status();
 }
 
 #define MMF_TRY(expr)            \

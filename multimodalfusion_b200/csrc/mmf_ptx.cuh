@@ -92,6 +92,20 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
 }
 
 // ----------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL). A kernel launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the stream
+// is still draining: its CTAs run their prologue (barrier init, TMEM allocation, descriptor prefetch)
+// on SMs the predecessor has already left and block in griddep_wait() until the predecessor has
+// completed and its writes are visible. Both are no-ops for a normally launched kernel.
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ void griddep_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void griddep_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+// ----------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor), 2-D tiles
 // ----------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {

@@ -320,6 +320,8 @@ amil_head_step_kernel(const float* __restrict__ parts, int n, int L, const float
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const long long stride = L + 2;
   const bool wk_smem = K * L <= 4096;
+  griddep_launch_dependents();
+  griddep_wait();
   // (m_t, l_t) of up to 8 partials per thread, kept in registers for both reductions
   float2 mlv[8];
   float m = -CUDART_INF_F;
@@ -494,6 +496,8 @@ amil_head_step_cluster_kernel(const float* __restrict__ parts, int n, int L, con
   const int c_lo = rank * LC;
   const int CP = LC >> 1;                  // column pairs per CTA
   const int RG = 512 / CP;                 // row groups
+  griddep_launch_dependents();
+  griddep_wait();   // PDL: the partials come from the tile kernel launched just before
   // early scalar loads (independent of everything else)
   long long y = 0; float cb = 0.f;
   if (tid == 0) { y = Yp[0]; cb = cp[0]; }
