@@ -242,6 +242,21 @@ int mmf_ranking_fwd_bwd(const float* risks, const float* times, const float* c, 
                         int reduction, float* loss, float* drisks, int64_t* n_pairs, void* workspace,
                         size_t workspace_bytes, void* stream);
 
+/* ---- multi-GPU: SUM all-reduce of a small fp32 buffer over NVLink peer memory ----------------
+ * The gradient all-reduce that closes a cohort-data-parallel step (the reference is
+ * single-GPU and has no counterpart) as one kernel on the caller's stream: ready handshake, reduce of
+ * this rank's slice from all peers + push of the sum to all peers, done handshake. Graph-capturable.
+ *   bufs_host[p]  : rank p's buffer (n floats, same n everywhere) as mapped into THIS process (peer memory /
+ *                   symmetric memory), p < world <= 8; every rank calls with its own mapping of all buffers
+ *   flags_host[p] : rank p's flag block, mmf_p2p_flag_bytes() bytes, zero-initialised once, also peer-mapped
+ *   multicast_ptr : NVLS multicast mapping of the same buffer (all ranks) or NULL; when given, the NVSwitch does
+ *                   the reduction (multimem.ld_reduce / multimem.st) and each rank moves only its 1/world slice
+ *   n             : multiple of 4;  n_ctas <= 64 (0 = default 32); same n_ctas on every rank.
+ * All ranks must call it the same number of times (it is a collective). */
+size_t mmf_p2p_flag_bytes(void);
+int mmf_p2p_allreduce_sum_f32(void* const* bufs_host, void* const* flags_host, void* multicast_ptr, int world,
+                              int rank, int64_t n, int n_ctas, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -36,6 +36,13 @@ class AmilPool(torch.autograd.Function):
         # backward instead of recomputing both GEMMs; inference keeps the N x L intermediates on chip
         train = any(ctx.needs_input_grad[:9]) and ops.stash_supported() and AmilPool.use_stash
         stash = None
+        ctx.empty_shard = group is not None and xb.shape[0] == 0
+        if ctx.empty_shard:
+            # a rank that owns no rows of a sharded bag contributes the neutral partial (m = -inf, l = 0)
+            from .parallel import all_gather_combine, empty_partial
+            M, ml = all_gather_combine(empty_partial(prep.L, xb.device), lambda g: ops.amil_combine(g, prep.L, True), group)
+            ctx.prep, ctx.flags, ctx.gated = prep, flags, Wb is not None
+            return torch.empty(1, 0, device=xb.device), M.view(1, -1)
         if train:
             A_raw, partials, stash = ops.amil_partials_train(xb, prep, flags, seed)
         else:
@@ -55,8 +62,10 @@ class AmilPool(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dA, dM):
-        xb, A_raw, M, ml = ctx.saved_tensors
         prep = ctx.prep
+        if ctx.empty_shard:
+            return (None,) * 13   # no rows here: this rank adds nothing to the SUM all-reduce of the weight grads
+        xb, A_raw, M, ml = ctx.saved_tensors
         if dM is None:
             dM = torch.zeros(prep.L, dtype=torch.float32, device=xb.device)
         g = ops.amil_backward(xb, prep, ctx.flags, ctx.seed, A_raw, ml, M, dM, dA, stash=ctx.stash)

@@ -12,6 +12,7 @@
 #include "gemm2_tc.cuh"
 #include "mmf_host.cuh"
 #include "small_kernels.cuh"
+#include "p2p_allreduce.cuh"
 
 using namespace mmf;
 
@@ -717,6 +718,29 @@ int mmf_ranking_fwd_bwd(const float* risks, const float* times, const float* c, 
   ranking_pairs_kernel<<<blocks, 128, 0, st>>>(risks, times, c, B, phi, acc, g);
   ranking_finalize_kernel<<<blocks, 128, 0, st>>>(acc, B, reduction, loss, drisks, g,
                                                   reinterpret_cast<long long*>(n_pairs));
+  return launch_status();
+}
+
+size_t mmf_p2p_flag_bytes(void) { return (size_t)P2P_FLAG_WORDS * sizeof(uint32_t); }
+
+int mmf_p2p_allreduce_sum_f32(void* const* bufs_host, void* const* flags_host, void* multicast_ptr, int world,
+                              int rank, int64_t n, int n_ctas, void* stream) {
+  if (!bufs_host || !flags_host || world < 1 || world > P2P_MAX_WORLD || rank < 0 || rank >= world) return MMF_E_INVALID;
+  if (n <= 0 || (n & 3)) return MMF_E_INVALID;
+  if (n_ctas <= 0) n_ctas = 32;
+  if (n_ctas > P2P_MAX_CTAS) n_ctas = P2P_MAX_CTAS;
+  P2pArgs a = {};
+  for (int p = 0; p < world; ++p) {
+    if (!bufs_host[p] || !flags_host[p] || (reinterpret_cast<uintptr_t>(bufs_host[p]) & 15u)) return MMF_E_ALIGN;
+    a.buf[p] = reinterpret_cast<float*>(bufs_host[p]);
+    a.flags[p] = reinterpret_cast<uint32_t*>(flags_host[p]);
+  }
+  a.n = n; a.world = world; a.rank = rank;
+  a.mc = reinterpret_cast<float*>(multicast_ptr);
+  if (multicast_ptr && (reinterpret_cast<uintptr_t>(multicast_ptr) & 15u)) return MMF_E_ALIGN;
+  // plain stream-ordered launch: as a programmatic dependent of the wgrad kernel the exchange took 100 us instead
+  // of 35 us (measured at 2 GPUs; its early-resident CTAs sit between the step's 1-CTA-per-SM kernels)
+  p2p_allreduce_sum_kernel<<<n_ctas, P2P_THREADS, 0, (cudaStream_t)stream>>>(a);
   return launch_status();
 }
 

@@ -97,3 +97,63 @@ def gather_risks(local: torch.Tensor, counts: Sequence[int], group=None) -> torc
     out = torch.empty(world, mx, dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out, pad.reshape(1, -1), group=group)
     return torch.cat([out[r, :counts[r]] for r in range(world)])
+
+
+class PeerAllReduce:
+    """SUM all-reduce of flat fp32 buffers over NVLink peer memory with the library's own kernel
+    (``mmf_p2p_allreduce_sum_f32``: ready handshake, reduce-scatter + all-gather by peer loads / stores, done
+    handshake — one launch on the caller's stream, CUDA-graph capturable). torch's symmetric memory is
+    used only to allocate the buffers and to map them into every rank (plumbing).
+
+        ar = PeerAllReduce(numel, n_buffers=2)      # collective: every rank of the group
+        ar.buffer(0)                                 # flat fp32 tensor the backward accumulates into
+        ar.all_reduce(0)                             # in place, on the current stream
+
+    Raises if symmetric memory cannot be set up (no P2P); callers then use ``dist.all_reduce``.
+    """
+
+    def __init__(self, numel: int, n_buffers: int = 1, group=None, n_ctas: int = 0, use_multicast: bool = True):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from . import _lib
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if self.world > 8:
+            raise ValueError("PeerAllReduce supports up to 8 ranks (one NVSwitch domain)")
+        self.numel = (numel + 3) // 4 * 4
+        self.n_ctas = n_ctas
+        dev = torch.device("cuda", torch.cuda.current_device())
+        flag_words = _lib.lib().mmf_p2p_flag_bytes() // 4
+        self._bufs, self._flags, self._ptrs, self._flag_ptrs, self._mc = [], [], [], [], []
+        for _ in range(n_buffers):
+            buf = symm_mem.empty(self.numel, dtype=torch.float32, device=dev)
+            flg = symm_mem.empty(flag_words, dtype=torch.int32, device=dev)
+            buf.zero_(); flg.zero_()
+            hb = symm_mem.rendezvous(buf, self.group)
+            hf = symm_mem.rendezvous(flg, self.group)
+            self._bufs.append(buf); self._flags.append(flg)
+            self._ptrs.append(_lib.ptr_array([int(p) for p in hb.buffer_ptrs]))
+            self._flag_ptrs.append(_lib.ptr_array([int(p) for p in hf.buffer_ptrs]))
+            mc = int(getattr(hb, "multicast_ptr", 0) or 0) if use_multicast else 0
+            self._mc.append(mc if mc else None)   # NVLS multicast mapping when the fabric supports it
+            self._keep = getattr(self, "_keep", []) + [hb, hf]
+        if self.n_ctas <= 0:
+            # the exchange is latency-bound (~27 us at 3.7 MB whatever the CTA count): with NVLS 8 CTAs suffice and
+            # leave the SMs to the step's own kernels when the all-reduce overlaps them; peer loads want more
+            self.n_ctas = 8 if self.multicast else 32
+        torch.cuda.synchronize()
+        dist.barrier(self.group)   # every rank's flags are zeroed before the first handshake
+
+    @property
+    def multicast(self) -> bool:
+        return all(m is not None for m in self._mc)
+
+    def buffer(self, i: int = 0) -> torch.Tensor:
+        return self._bufs[i]
+
+    def all_reduce(self, i: int = 0) -> None:
+        from . import _lib
+        _lib.check(_lib.lib().mmf_p2p_allreduce_sum_f32(self._ptrs[i], self._flag_ptrs[i], self._mc[i], self.world, self.rank,
+                                                        self.numel, self.n_ctas,
+                                                        torch.cuda.current_stream().cuda_stream),
+                   "mmf_p2p_allreduce_sum_f32")
