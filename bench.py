@@ -423,19 +423,27 @@ def run_ours(args):
                 torch.cuda.synchronize()
                 ts.append(e0.elapsed_time(e1) * 1e3 / N_BAGS)
             kernels[name] = statistics.median(ts)  # us
-        t_tile = kernels["amil_tile_fwd"]
+        # the roofline kernel is the dominant kernel of the TIMED step: the fused forward tile kernel in its training
+        # form (with the activation stash); the plain (inference) forward is reported next to it
+        train_key = "amil_tile_fwd_train" if bwd_mode == "stash" else "amil_tile_fwd"
+        t_tile = kernels[train_key]
         achieved = flops_tile_kernel(N_BAG) / (t_tile * 1e-6) / 1e12
         traffic = None
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tp):
             with open(tp) as f:
-                traffic = json.load(f).get("amil_tile_fwd_dram_bytes")
+                traffic = json.load(f).get(train_key + "_dram_bytes")
         step_tf = flops_per_patch_algorithmic() * N_BAG / (ms_per_step * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "amil_tile_kernel<512,384,gated,FWD> (fused fc+gated-attention+softmax-partial)",
+        roof = {"bound": "tensor",
+                "kernel": "amil_tile2_kernel<512,384,gated,FWD> (fused fc + gated attention + softmax partial"
+                          + (" + activation stash)" if bwd_mode == "stash" else ")"),
                 "achieved": achieved, "peak": peak_burst, "unit": "TFLOP/s", "frac": achieved / peak_burst,
                 "traffic": traffic, "peak_source": f"MEASURED_PEAKS.json bf16_tflops (burst), {src}",
                 "flops_per_launch": flops_tile_kernel(N_BAG),
-                "step_algorithmic_tflops": step_tf, "step_frac_of_sustained_peak": step_tf / peak_sust,
+                "timed_with": "8 launches (one per rotating bag) in a CUDA graph, CUDA events, median of 9 replays / 8",
+                "inference_forward_frac": flops_tile_kernel(N_BAG) / (kernels["amil_tile_fwd"] * 1e-6) / 1e12 / peak_burst,
+                "step_algorithmic_tflops": step_tf, "step_frac_of_burst_peak": step_tf / peak_burst,
+                "step_frac_of_sustained_peak": step_tf / peak_sust,
                 "stage_us": kernels}
         if world == 1:
             from oracle.cpu_reference import time_cpu_steps
