@@ -205,16 +205,19 @@ def run_ours(args):
                 print(f"# peer all-reduce unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
             peer_ar = None
     for bi in range(2):
-        fl = peer_ar.buffer(bi) if peer_ar is not None else torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        # (padded to a multiple of 4 floats: cleared / reduced 16 bytes at a time)
+        fl = (peer_ar.buffer(bi) if peer_ar is not None
+              else torch.zeros((sum(sizes) + 3) // 4 * 4, dtype=torch.float32, device=dev))
         vs, o = [], 0
         for sz in sizes:
             vs.append(fl[o:o + sz]); o += sz
         flats.append(fl); views_l.append(vs)
         grads_l.append(dict(dW1=vs[0].view(L, 1024), db1=vs[1], dWab=vs[2].view(KD, L), dbab=vs[3], dwc=vs[4], dbc=vs[5]))
     flat, grads = flats[0], grads_l[0]
-    # our launches per step: tile fwd(+stash), cluster head step, gate backward, dU GEMM, grouped wgrad GEMM
-    # (recompute mode: + ReLU-mask kernel + column-sum reduce); plus one ATen fill that zeroes the flat grad buffer
-    LAUNCHES_PER_STEP = 5 if os.environ.get("MMF_BENCH_BWD", "stash") == "stash" else 7
+    # our launches per step: tile fwd(+stash), cluster head step, fused gate-backward + dU GEMM, grouped wgrad GEMM
+    # (recompute mode: + ReLU-mask kernel + column-sum reduce + one ATen fill that zeroes the flat grad buffer;
+    # stash mode: the forward kernel clears it)
+    LAUNCHES_PER_STEP = 4 if os.environ.get("MMF_BENCH_BWD", "stash") == "stash" else 7
 
     # backward mode: "stash" (default: the training forward leaves h / branch activations in the backward
     # workspace, no recompute GEMMs) or "recompute" (MMF_BENCH_BWD=recompute: the tile kernel runs again)
@@ -222,10 +225,10 @@ def run_ours(args):
     step_ws = ops.amil_bwd_workspace(N_BAG, prep, flags, dev)
 
     def step(x, b=0):
-        flats[b].zero_()
-        if bwd_mode == "stash":
-            A_raw, parts, ws = ops.amil_partials_train(x, prep, flags, seed, workspace=step_ws)
+        if bwd_mode == "stash":   # the training forward clears the step's gradient buffer itself (fused zero_grad)
+            A_raw, parts, ws = ops.amil_partials_train(x, prep, flags, seed, workspace=step_ws, zero=flats[b])
         else:
+            flats[b].zero_()
             (A_raw, parts), ws = ops.amil_partials(x, prep, flags, seed), None
         t = ops.amil_head_nll_step(parts, Wk, bk, Y, c, 0.0, dWk=views_l[b][6], dbk=views_l[b][7])
         ops.amil_backward(x, prep, flags, seed, A_raw, t["ml"], t["M"], t["dM"], grads=grads_l[b], stash=ws)
@@ -386,6 +389,11 @@ def run_ours(args):
                                                 M.data_ptr(), dM.data_ptr(), None, C.byref(gstruct),
                                                 step_ws.data_ptr(), step_ws.numel(), cur_stream()))
 
+        def t_gate_hidden_fused(x):
+            check(lib.mmf_amil_bwd_gate_hidden_stashed(N_BAG, C.byref(wst), L, D, flags, seed, A_raw.data_ptr(),
+                                                       ml.data_ptr(), M.data_ptr(), dM.data_ptr(), None, C.byref(gstruct),
+                                                       step_ws.data_ptr(), step_ws.numel(), cur_stream()))
+
         def t_gate(x):
             check(lib.mmf_amil_bwd_gate(x.data_ptr(), N_BAG, 1024, C.byref(wst), L, D, flags, seed, A_raw.data_ptr(),
                                         ml.data_ptr(), M.data_ptr(), dM.data_ptr(), None, C.byref(gstruct), wsp,
@@ -405,8 +413,9 @@ def run_ours(args):
         # replayed; stage time = median replay time / 8. Eager per-launch events would time the Python/ctypes
         # launch path, not the kernel, once a kernel is shorter than ~40 us.
         for name, fn in (("amil_tile_fwd", t_fwd), ("amil_tile_fwd_train", t_fwd_train),
-                         ("bwd_gate_stashed", t_gate_stashed), ("bwd_gate_recompute", t_gate), ("bwd_hidden", t_hidden),
-                         ("bwd_wgrad", t_wgrad)):
+                         ("bwd_gate_hidden_fused", t_gate_hidden_fused), ("bwd_wgrad", t_wgrad),
+                         ("unfused_bwd_gate_stashed", t_gate_stashed), ("unfused_bwd_hidden", t_hidden),
+                         ("recompute_bwd_gate", t_gate)):
             for i in range(2):
                 fn(bags[i % N_BAGS])
             torch.cuda.synchronize()

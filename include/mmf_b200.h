@@ -54,6 +54,11 @@ int mmf_version(void);
 /* DEBUG ONLY (process-global): device buffer of gridDim.x*16 uint64 that the fused tile kernels fill
  * with clock64() phase stamps; NULL (default) disables it. Not for production use. */
 void mmf_debug_set_timing_buffer(void* device_u64_buffer);
+/* DEBUG ONLY (process-global): device buffer of 16 + 2 * 8192 uint64, zero-filled; CTA 0 of every hot-path kernel
+ * appends (kernel id, %globaltimer ns) at its start to the log at [16 ...] (count in [0]) and at its end to the log at
+ * [16 + 8192 ...] (count in [1]). ids: 0 fused forward, 1 head step, 2 fused gate+hidden backward, 3 wgrad GEMM,
+ * 4 recompute gate, 5 other pair GEMMs. NULL disables. */
+void mmf_debug_set_timeline_buffer(void* device_u64_buffer);
 const char* mmf_error_string(int rc);
 
 /* Weights of fc(1024->L) + attention net, prepared once per optimizer step by the caller.
@@ -121,10 +126,14 @@ size_t mmf_amil_bwd_workspace_bytes(int64_t N, int L, int D, int flags);
  * per instance (2.5 KB big preset). mmf_amil_bwd with MMF_STASHED then skips both recompute GEMMs:
  * its gate stage becomes one HBM-bound elementwise pass. Trades 40 MB of stores per 16k bag for
  * 30 GFLOP of recompute; use mmf_amil_fwd + mmf_amil_bwd (no flag) when memory is the constraint.
- * Replaces the same reference ops as mmf_amil_fwd, with autograd's saved activations made explicit. */
+ * Replaces the same reference ops as mmf_amil_fwd, with autograd's saved activations made explicit.
+ * zero_buf / zero_count (optional, NULL / 0): an fp32 buffer (16-byte aligned, count a multiple of 4) that the
+ * kernel clears while its first GEMM runs — the step's gradient accumulators, i.e. optimizer.zero_grad() fused
+ * into the forward (a separate fill costs two kernel boundaries per step). It must not alias anything the
+ * forward reads. */
 int mmf_amil_fwd_train(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, int L, int D,
                        int flags, uint64_t seed, float* A_raw, float* partials, void* workspace,
-                       size_t workspace_bytes, void* stream);
+                       size_t workspace_bytes, float* zero_buf, int64_t zero_count, void* stream);
 
 /* Backward of mmf_amil_fwd + combine, given dM = dLoss/dM [L] and optionally dA_raw [N].
  * Recomputes h and the attention activations tile by tile (nothing but A_raw, (m,l), M is kept
@@ -152,6 +161,12 @@ int mmf_amil_bwd_gate_stashed(int64_t N, const MmfAmilWeights* w, int L, int D, 
                               const float* A_raw, const float* ml, const float* M, const float* dM,
                               const float* dA_raw, const MmfAmilGrads* g, void* workspace,
                               size_t workspace_bytes, void* stream);
+/* gate + hidden stages of the MMF_STASHED backward in one kernel (the gate backward is the A-operand producer of
+ * the dU GEMM); what mmf_amil_bwd(MMF_STASHED) runs. Same workspace contract as the two calls it replaces. */
+int mmf_amil_bwd_gate_hidden_stashed(int64_t N, const MmfAmilWeights* w, int L, int D, int flags, uint64_t seed,
+                                     const float* A_raw, const float* ml, const float* M, const float* dM,
+                                     const float* dA_raw, const MmfAmilGrads* g, void* workspace,
+                                     size_t workspace_bytes, void* stream);
 int mmf_amil_bwd_hidden(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, int L, int D,
                         int flags, const float* A_raw, const float* ml, const float* dM,
                         const MmfAmilGrads* g, void* workspace, size_t workspace_bytes, void* stream);

@@ -88,6 +88,7 @@ _PP = C.POINTER(C.c_void_p)
 SIGNATURES = {
     "mmf_version": (_i, []),
     "mmf_debug_set_timing_buffer": (None, [_vp]),
+    "mmf_debug_set_timeline_buffer": (None, [_vp]),
     "mmf_error_string": (C.c_char_p, [_i]),
     "mmf_cast_f32_to_bf16": (_i, [_vp, _vp, _i64, _vp]),
     "mmf_pack_wab": (_i, [_vp, _vp, _i, _i, _i, _vp]),
@@ -95,9 +96,12 @@ SIGNATURES = {
     "mmf_amil_fwd": (_i, [_vp, _i64, _i64, C.POINTER(AmilWeights), _i, _i, _i, _u64, _vp, _vp, _vp, _vp]),
     "mmf_amil_combine": (_i, [_vp, _i64, _i, _i, _vp, _vp, _vp]),
     "mmf_amil_bwd_workspace_bytes": (_sz, [_i64, _i, _i, _i]),
-    "mmf_amil_fwd_train": (_i, [_vp, _i64, _i64, C.POINTER(AmilWeights), _i, _i, _i, _u64, _vp, _vp, _vp, _sz, _vp]),
+    "mmf_amil_fwd_train": (_i, [_vp, _i64, _i64, C.POINTER(AmilWeights), _i, _i, _i, _u64, _vp, _vp, _vp, _sz, _vp, _i64,
+                                _vp]),
     "mmf_amil_bwd_gate_stashed": (_i, [_i64, C.POINTER(AmilWeights), _i, _i, _i, _u64, _vp, _vp, _vp, _vp, _vp,
                                        C.POINTER(AmilGrads), _vp, _sz, _vp]),
+    "mmf_amil_bwd_gate_hidden_stashed": (_i, [_i64, C.POINTER(AmilWeights), _i, _i, _i, _u64, _vp, _vp, _vp, _vp, _vp,
+                                              C.POINTER(AmilGrads), _vp, _sz, _vp]),
     "mmf_amil_bwd": (_i, [_vp, _i64, _i64, C.POINTER(AmilWeights), _i, _i, _i, _u64, _vp, _vp, _vp, _vp,
                           _vp, _vp, C.POINTER(AmilGrads), _vp, _vp, _sz, _vp]),
     "mmf_amil_bwd_gate": (_i, [_vp, _i64, _i64, C.POINTER(AmilWeights), _i, _i, _i, _u64, _vp, _vp, _vp, _vp, _vp,

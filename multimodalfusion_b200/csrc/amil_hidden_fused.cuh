@@ -1,0 +1,466 @@
+// amil_hidden_fused.cuh — stash-mode backward, stages 1 + 2 in ONE kernel (sm_100a, CTA pair).
+//
+// Fuses the gate backward (amil_gate_ew.cuh) into the hidden-gradient GEMM as the PRODUCER of its A
+// operand, so dG makes no round trip through L2 between the two and the step loses one launch:
+//
+//   phase A  (epilogue warps, while the producer prefetches Wab): per row i of the 128-row tile
+//            t_i = dM·h_i, p_i = e^{s_i-m}/l, ds_i = p_i (t_i - dM·M) + dA_i, and [h_i > 0] as 16 mask
+//            words, from coalesced warp-per-row loads of the stashed H tile;
+//   mainloop per 64-wide slice c of D ("k-pair"): TMA brings the stashed fp16 tiles a[:, c], g[:, c] into
+//            an A stage; the epilogue warps rewrite them IN PLACE as the bf16 tiles
+//            dG_a = ds wc g (1-a²), dG_g = ds wc a g (1-g)  (column-stationary: thread = 4 columns x 8
+//            rows, so dwc / dba / dbb sums stay in registers), publish them to the MMA warp, and one
+//            thread TMA-stores them to the dG buffer (the wgrad GEMM needs dG);
+//            tcgen05.mma.cta_group::2 (M = 256, N = 256 x L/256):  acc += dG_a Wa[c] + dG_g Wb[c];
+//   epilogue dU = (acc + p_i dM) ⊙ [h > 0] · 1/(1-p) -> bf16 -> swizzled staging -> TMA store; db1 column
+//            sums from the staged tile (as gemm2_tc.cuh EPI_DU, mask words now from shared memory).
+//
+// Math: SURVEY.md App. A.2 = backward of models/model_modules.py:105-110 (gated attention) and
+// models/model_attention_mil_path.py:20-21,29,53-56 (fc + ReLU + dropout, softmax pooling).
+//
+// Shared memory (dynamic, 1024-aligned pool):
+//   B ring  NSB stages x [64 k-rows][L/2 cols] (this CTA's half of a Wab k-block, MN-major boxes)
+//   A ring  NSA stages x (a tile 16 KB + g tile 16 KB)   [128 rows][64 cols], K-major, 128B swizzle
+//   after the mainloop both rings are dead and hold the staged dU tile (128 x L bf16)
+//   vectors: dM[L], wc[D], ds[128], p[128], mask[128][L/32], colsum scratch [3D]
+// Barriers: b_full[s] leader copy (pair TMA), b_empty[s] / a_empty[s] / acc per CTA (multicast commits;
+// a_empty also counts the dG store's read-completion), a_full[s] per CTA (local TMA), a_ready[s] leader
+// copy, one arrive per epilogue warp of either CTA (16).
+#pragma once
+#include <cuda_fp16.h>
+
+#include "amil_tile.cuh"
+#include "gemm_tc.cuh"
+
+namespace mmf {
+
+struct HiddenFusedArgs {
+  long long N;
+  const __nv_bfloat16* H;   // stash [N, L]
+  const float* A_raw;       // [N]
+  const float* ml;          // (m, l)
+  const float* M;           // [L]
+  const float* dM;          // [L]
+  const float* dA_raw;      // [N] or null
+  const float* wc;          // [D]
+  float* dwc;               // [D]  accumulated
+  float* dbab;              // [KD] accumulated
+  float* dbc;               // [1]  accumulated
+  float* db1;               // [L]  accumulated
+  float du_scale;           // 1 or 1/(1-p)
+  unsigned long long seed;
+  unsigned long long* dbg;
+};
+
+template <int L, int D, bool GATED>
+struct HiddenFusedCfg {
+  static constexpr int KD = GATED ? 2 * D : D;
+  static constexpr int NKP = D / 64;                       // k-pairs (64-wide slices of D)
+  static constexpr int NH = L / 256;                       // N = 256 MMAs per k-step
+  static constexpr uint32_t B_STAGE = NH * 16384u;         // this CTA's half of one Wab k-block
+  static constexpr uint32_t A_STAGE = GATED ? 32768u : 16384u;
+  static constexpr int NSB = 4;
+  static constexpr int NSA = 2;
+  static constexpr uint32_t RING_BYTES = NSB * B_STAGE + NSA * A_STAGE;
+  static constexpr uint32_t STAGING = 128u * L * 2u;       // dU tile
+  static constexpr uint32_t POOL = RING_BYTES > STAGING ? RING_BYTES : STAGING;
+  // vector region (floats): dM | wc | ds | p | mask words [128][L/32] (uint32)
+  static constexpr int V_DM = 0, V_WC = L, V_DS = L + D, V_P = V_DS + 128,
+                       V_MASK = V_P + 128, V_END = V_MASK + 128 * (L / 32);
+  static constexpr uint32_t VEC_BYTES = ((V_END * 4u + 1023u) / 1024u) * 1024u;
+  static constexpr uint32_t SMEM_BYTES = POOL + VEC_BYTES + 1024u;
+};
+
+constexpr int HIDDEN_EW = 16;                         // worker (phase A / transform / epilogue) warps: the CUDA-core
+                                                     // phases are latency-bound, 16 warps hide ~2x what 8 did
+constexpr int HIDDEN_ET = HIDDEN_EW * 32;             // worker threads
+constexpr int HIDDEN_THREADS = 128 + HIDDEN_ET;
+
+template <int L, int D, bool GATED, bool DROP>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HIDDEN_THREADS, 1)
+amil_hidden_fused_kernel(const __grid_constant__ CUtensorMap tmAG,   // stash fp16 [N, KD], box [128][64]
+                         const __grid_constant__ CUtensorMap tmDG,   // same memory viewed as bf16 dG (store)
+                         const __grid_constant__ CUtensorMap tmWab,  // bf16 [KD, L], box [64][64]
+                         const __grid_constant__ CUtensorMap tmDU,   // bf16 [N, L], box [128][64] (store)
+                         const HiddenFusedArgs a) {
+  using C = HiddenFusedCfg<L, D, GATED>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_bfull[C::NSB], bar_bempty[C::NSB];
+  __shared__ __align__(8) uint64_t bar_afull[C::NSA], bar_aready[C::NSA], bar_aempty[C::NSA];
+  __shared__ __align__(8) uint64_t bar_acc;
+  __shared__ __align__(8) uint64_t bar_astore[C::NSA];   // local: one arrive per epilogue warp once a stage holds dG
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float s_dbc;
+  // per-warp private column-sum slots (no atomics: shared-memory fp32 atomicAdd is a CAS loop): warp (column group
+  // ctg = w & 3, row quarter rq = w >> 2) owns, per slice, 3 sums (dwc | dba | dbb) x 16 columns
+  __shared__ float s_part[HIDDEN_EW][C::NKP * 48];
+
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const uint32_t pool = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* pool_ptr = smem_raw + (pool - smem_u32(smem_raw));
+  const uint32_t b_ring = pool, a_ring = pool + C::NSB * C::B_STAGE;
+  float* vec = reinterpret_cast<float*>(pool_ptr + C::POOL);
+  uint32_t* s_mask = reinterpret_cast<uint32_t*>(vec + C::V_MASK);
+  const int pair_m = blockIdx.x >> 1;
+  const long long row0 = (long long)pair_m * 256 + 128 * (int)rank;   // first row of this CTA
+
+  timeline_start(2);
+  griddep_launch_dependents();
+  if (threadIdx.x == 0) {
+    MMF_STAMP(a, 0);
+    for (int s = 0; s < C::NSB; ++s) { mbar_init(smem_u32(&bar_bfull[s]), 1); mbar_init(smem_u32(&bar_bempty[s]), 1); }
+    for (int s = 0; s < C::NSA; ++s) {
+      mbar_init(smem_u32(&bar_afull[s]), 1);
+      mbar_init(smem_u32(&bar_aready[s]), 2 * HIDDEN_EW);
+      mbar_init(smem_u32(&bar_aempty[s]), 2);   // MMA commit + the dG store's read-completion
+      mbar_init(smem_u32(&bar_astore[s]), HIDDEN_EW);
+    }
+    mbar_init(smem_u32(&bar_acc), 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmAG); tma_prefetch_desc(&tmWab); tma_prefetch_desc(&tmDG); tma_prefetch_desc(&tmDU);
+    s_dbc = 0.f;
+  }
+  if (warp == 2) {
+    tmem_alloc_pair(smem_u32(&tmem_base_slot), L);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+  griddep_wait();
+  if (threadIdx.x == 0) MMF_STAMP(a, 1);
+
+  if (warp == 0 && lane == 0) {
+    // =============================== TMA producer, B stream (both CTAs) =================
+    // Wab k-block order = [a rows of slice 0, g rows of slice 0, a rows of slice 1, ...]. The A stream has its
+    // own thread (warp 3): a wait for a free B slot must never delay the next slice's activation tiles.
+    constexpr int NKB = C::NKP * (GATED ? 2 : 1);
+    for (int i = 0; i < NKB; ++i) {
+      const int s = i % C::NSB;
+      mbar_wait(smem_u32(&bar_bempty[s]), ((i / C::NSB) & 1) ^ 1);
+      const uint32_t full = smem_u32(&bar_bfull[s]);
+      if (leader) mbar_arrive_expect_tx(full, 2 * C::B_STAGE);
+      const int kp = GATED ? (i >> 1) : i;
+      const int krow = (GATED && (i & 1)) ? D + kp * 64 : kp * 64;   // row of Wab [KD, L]
+#pragma unroll
+      for (int h = 0; h < C::NH; ++h)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          tma_load_2d_pair(b_ring + s * C::B_STAGE + h * 16384 + j * 8192, &tmWab, full,
+                           256 * h + 128 * (int)rank + j * 64, krow);
+    }
+  } else if (warp == 3 && lane == 0) {
+    // =============================== TMA producer, A stream (each CTA its own rows) =====
+    for (int kp = 0; kp < C::NKP; ++kp) {
+      const int s = kp % C::NSA;
+      mbar_wait(smem_u32(&bar_aempty[s]), ((kp / C::NSA) & 1) ^ 1);
+      const uint32_t full = smem_u32(&bar_afull[s]);
+      mbar_arrive_expect_tx(full, C::A_STAGE);
+      tma_load_2d(a_ring + s * C::A_STAGE, &tmAG, full, kp * 64, (int)row0);
+      if (GATED) tma_load_2d(a_ring + s * C::A_STAGE + 16384, &tmAG, full, D + kp * 64, (int)row0);
+    }
+  } else if (warp == 2 && lane == 0) {
+    // =============================== dG store thread (each CTA) =========================
+    // dG -> global for the wgrad GEMM, straight from the transformed A stage (same swizzled tile layout)
+    for (int kp = 0; kp < C::NKP; ++kp) {
+      const int s = kp % C::NSA;
+      mbar_wait(smem_u32(&bar_astore[s]), (kp / C::NSA) & 1);
+      tma_store_2d(&tmDG, a_ring + s * C::A_STAGE, kp * 64, (int)row0);
+      if (GATED) tma_store_2d(&tmDG, a_ring + s * C::A_STAGE + 16384, D + kp * 64, (int)row0);
+      tma_store_commit();
+      tma_store_wait_read();                       // the stage may be overwritten once the store has read it
+      mbar_arrive(smem_u32(&bar_aempty[s]));
+    }
+    tma_store_wait_all();
+  } else if (warp == 1 && lane == 0 && leader) {
+    // =============================== MMA issuer (leader CTA) ===========================
+    constexpr uint32_t idesc = umma_idesc_bf16(256, 256, 0, 1);
+    int bi = 0;
+    for (int kp = 0; kp < C::NKP; ++kp) {
+      const int sa = kp % C::NSA;
+      mbar_wait_cluster(smem_u32(&bar_aready[sa]), (kp / C::NSA) & 1);
+      tc_fence_after();
+      if (kp == 0) MMF_STAMP(a, 2);
+#pragma unroll
+      for (int br = 0; br < (GATED ? 2 : 1); ++br, ++bi) {
+        const int sb = bi % C::NSB;
+        mbar_wait(smem_u32(&bar_bfull[sb]), (bi / C::NSB) & 1);
+        tc_fence_after();
+        const uint32_t a_src = a_ring + sa * C::A_STAGE + br * 16384;
+        const uint32_t b_src = b_ring + sb * C::B_STAGE;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t ad = umma_desc_sw128(a_src + k * 32, 16, 1024);
+#pragma unroll
+          for (int h = 0; h < C::NH; ++h)
+            umma_bf16_ss_pair(tmem + h * 256, ad, umma_desc_sw128(b_src + h * 16384 + k * 2048, 8192, 1024), idesc,
+                              (kp | br | k) != 0);
+        }
+        umma_commit_pair_mc(smem_u32(&bar_bempty[sb]), 3);
+      }
+      umma_commit_pair_mc(smem_u32(&bar_aempty[sa]), 3);
+    }
+    umma_commit_pair_mc(smem_u32(&bar_acc), 3);
+    MMF_STAMP(a, 3);
+  } else if (warp >= 4) {
+    // =============================== epilogue / transform warps ========================
+    const uint32_t q = warp & 3;
+    const uint32_t part = (warp - 4) >> 2;         // column part handled in the epilogue (L / (EW/4) columns)
+    const uint32_t e = threadIdx.x - 128;          // 0..HIDDEN_ET-1
+    const uint32_t ew = warp - 4;                  // 0..EW-1
+    constexpr int ROWS_PER_WARP = 128 / HIDDEN_EW;
+    for (int i = e; i < L; i += HIDDEN_ET) vec[C::V_DM + i] = __ldg(a.dM + i);
+    for (int i = e; i < D; i += HIDDEN_ET) vec[C::V_WC + i] = __ldg(a.wc + i);
+
+
+    // ---------------- phase A: ds_i, p_i, ReLU mask words — one warp per row, 4 rows in flight -------------
+    {
+      constexpr int HJ = L / 256;
+      float dmv[HJ][8];
+      float dotMM = 0.f;
+#pragma unroll
+      for (int j = 0; j < HJ; ++j)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          dmv[j][k] = __ldg(a.dM + 8 * lane + 256 * j + k);
+          dotMM = fmaf(dmv[j][k], __ldg(a.M + 8 * lane + 256 * j + k), dotMM);
+        }
+      dotMM = warp_sum(dotMM);
+      const float m = __ldg(a.ml), inv_l = 1.0f / __ldg(a.ml + 1);
+      float acc_ds = 0.f;
+      // the warp's raw scores / incoming score gradients, fetched once (lane l <-> l-th row of this warp): a load
+      // inside the row loop would put one L2 round trip per row on lane 0's critical path
+      float s_raw_l = 0.f, dA_l = 0.f;
+      {
+        const long long row = row0 + (long long)ew * ROWS_PER_WARP + lane;
+        if (lane < ROWS_PER_WARP && row < a.N) {
+          s_raw_l = __ldg(a.A_raw + row);
+          dA_l = a.dA_raw ? __ldg(a.dA_raw + row) : 0.f;
+        }
+      }
+#pragma unroll 1
+      for (int r0 = (int)ew * ROWS_PER_WARP; r0 < (int)(ew + 1) * ROWS_PER_WARP; r0 += 4) {
+        uint4 hv[4][HJ];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const long long row = row0 + r0 + u;
+          const uint4* hp = reinterpret_cast<const uint4*>(a.H + (row < a.N ? row : 0) * L);
+#pragma unroll
+          for (int j = 0; j < HJ; ++j) hv[u][j] = __ldg(hp + lane + 32 * j);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = r0 + u;
+          const long long row = row0 + r;
+          const bool ok = row < a.N;
+          float t = 0.f;
+#pragma unroll
+          for (int j = 0; j < HJ; ++j) {
+            const uint32_t w[4] = {hv[u][j].x, hv[u][j].y, hv[u][j].z, hv[u][j].w};
+            uint32_t byte = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 f = unpack_bf16x2(w[k]);
+              t = fmaf(f.x, dmv[j][2 * k], t);
+              t = fmaf(f.y, dmv[j][2 * k + 1], t);
+              byte |= (uint32_t)(f.x > 0.f) << (2 * k) | (uint32_t)(f.y > 0.f) << (2 * k + 1);
+            }
+            uint32_t word = ok ? byte << (8 * (lane & 3)) : 0u;
+            word |= __shfl_xor_sync(0xffffffffu, word, 1);
+            word |= __shfl_xor_sync(0xffffffffu, word, 2);
+            if ((lane & 3) == 0) s_mask[r * (L / 32) + (lane >> 2) + 8 * j] = word;
+          }
+          t = warp_sum(t);
+          const float s_raw = __shfl_sync(0xffffffffu, s_raw_l, r - (int)ew * ROWS_PER_WARP);
+          const float dA = __shfl_sync(0xffffffffu, dA_l, r - (int)ew * ROWS_PER_WARP);
+          if (lane == 0) {
+            float p = 0.f, ds = 0.f;
+            if (ok) {
+              p = __expf(s_raw - m) * inv_l;
+              ds = p * (t - dotMM) + dA;
+            }
+            vec[C::V_DS + r] = ds;
+            vec[C::V_P + r] = p;
+            acc_ds += ds;
+          }
+        }
+      }
+      if (lane == 0) atomicAdd(&s_dbc, acc_ds);
+    }
+    named_bar_sync(1, HIDDEN_ET);   // ds / p / mask / vectors visible to all worker threads
+    if (e == 0) MMF_STAMP(a, 4);
+
+    // ---------------- mainloop: transform the stashed activations into dG, in place -------------------------
+    // thread map of a slice: lane = (column quad low bits, row) -> a warp covers 4 column quads x 8 consecutive rows
+    // per load (conflict-free under the 128B swizzle), warps = 4 column-quad groups x 4 row quarters. The column
+    // sums are then reduced over the warp's 8 rows with shuffles and only lanes 0-3 touch shared memory (4-way
+    // contention between the row quarters). Shared-memory fp32 atomicAdd is a CAS loop: the first version had all
+    // 512 threads add into 192 addresses per slice (32-way contention) and spent half the kernel retrying.
+    static_assert(HIDDEN_EW == 16, "slice thread map assumes 16 worker warps");
+    const uint32_t ct = (ew & 3u) * 4u + (lane & 3u);     // column quad 0..15
+    const uint32_t rbase = (ew >> 2) * 32u + (lane >> 2); // first row; rows rbase + 8 u
+    constexpr int RPT = 4;                                 // rows per thread and slice
+    const uint32_t a_ready_leader = mapa_cluster(smem_u32(&bar_aready[0]), 0);
+    constexpr float attn_scale = DROP ? (1.0f / 0.75f) : 1.0f;
+#pragma unroll 1
+    for (int kp = 0; kp < C::NKP; ++kp) {
+      const int s = kp % C::NSA;
+      const int d0 = kp * 64 + 4 * (int)ct;
+      const float4 wc4 = *reinterpret_cast<const float4*>(vec + C::V_WC + d0);
+      const float wcv[4] = {wc4.x, wc4.y, wc4.z, wc4.w};
+      float acc_wc[4] = {}, acc_a[4] = {}, acc_g[4] = {};
+      mbar_wait(smem_u32(&bar_afull[s]), (kp / C::NSA) & 1);
+      if (e == 0 && kp < 3) MMF_STAMP(a, 8 + 2 * kp);
+      uint8_t* ta = pool_ptr + (a_ring - pool) + s * C::A_STAGE;
+#pragma unroll
+      for (int u = 0; u < RPT; ++u) {
+        const uint32_t r = rbase + 8u * u;
+        const uint32_t off = sw128_offset(r, ct >> 1) + (ct & 1u) * 8u;
+        uint2* pa = reinterpret_cast<uint2*>(ta + off);
+        uint2* pg = reinterpret_cast<uint2*>(ta + 16384 + off);
+        const uint2 av = *pa;
+        uint2 gv = make_uint2(0u, 0u);
+        if (GATED) gv = *pg;
+        const float ds = vec[C::V_DS + r];
+        uint32_t ab = 0xFFFFFFFFu, gb = 0xFFFFFFFFu;
+        if (DROP) {
+          ab = drop_bits16(drop_row_state(a.seed, 1, (uint32_t)(row0 + r)), (uint32_t)(d0 >> 4));
+          gb = drop_bits16(drop_row_state(a.seed, 2, (uint32_t)(row0 + r)), (uint32_t)(d0 >> 4));
+        }
+        const float2 a01 = __half22float2(*reinterpret_cast<const __half2*>(&av.x));
+        const float2 a23 = __half22float2(*reinterpret_cast<const __half2*>(&av.y));
+        float2 g01 = make_float2(1.f, 1.f), g23 = make_float2(1.f, 1.f);
+        if (GATED) {
+          g01 = __half22float2(*reinterpret_cast<const __half2*>(&gv.x));
+          g23 = __half22float2(*reinterpret_cast<const __half2*>(&gv.y));
+        }
+        const float aa[4] = {a01.x, a01.y, a23.x, a23.y};
+        const float gg[4] = {g01.x, g01.y, g23.x, g23.y};
+        float da[4], dg[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float ka = (!DROP || drop_keep(ab, (d0 & 15) + k)) ? attn_scale : 0.f;
+          const float kg = (GATED && DROP) ? (drop_keep(gb, (d0 & 15) + k) ? attn_scale : 0.f) : 1.f;
+          const float ad = aa[k] * ka, gd = gg[k] * kg;
+          const float dq = ds * wcv[k];
+          acc_wc[k] = fmaf(ds, ad * gd, acc_wc[k]);
+          da[k] = dq * gd * ka * (1.f - aa[k] * aa[k]);
+          dg[k] = GATED ? dq * ad * kg * gg[k] * (1.f - gg[k]) : 0.f;
+          acc_a[k] += da[k];
+          acc_g[k] += dg[k];
+        }
+        *pa = make_uint2(pack_bf16x2(da[0], da[1]), pack_bf16x2(da[2], da[3]));
+        if (GATED) *pg = make_uint2(pack_bf16x2(dg[0], dg[1]), pack_bf16x2(dg[2], dg[3]));
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (e == 0 && kp < 3) MMF_STAMP(a, 9 + 2 * kp);
+      if (lane == 0) {
+        mbar_arrive_cluster(a_ready_leader + s * 8u);   // bar_aready[s] of the leader: the MMA may consume the stage
+        mbar_arrive(smem_u32(&bar_astore[s]));          // and the store thread (warp 2) may write it out as dG
+      }
+      // column sums of this slice: reduce over the warp's 8 row lanes, then 4 row quarters meet in shared memory
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int o = 4; o <= 16; o <<= 1) {
+          acc_wc[k] += __shfl_xor_sync(0xffffffffu, acc_wc[k], o);
+          acc_a[k] += __shfl_xor_sync(0xffffffffu, acc_a[k], o);
+          if (GATED) acc_g[k] += __shfl_xor_sync(0xffffffffu, acc_g[k], o);
+        }
+      }
+      if (lane < 4) {
+        float* slot = &s_part[ew][kp * 48 + lane * 4];
+        *reinterpret_cast<float4*>(slot) = make_float4(acc_wc[0], acc_wc[1], acc_wc[2], acc_wc[3]);
+        *reinterpret_cast<float4*>(slot + 16) = make_float4(acc_a[0], acc_a[1], acc_a[2], acc_a[3]);
+        if (GATED) *reinterpret_cast<float4*>(slot + 32) = make_float4(acc_g[0], acc_g[1], acc_g[2], acc_g[3]);
+      }
+    }
+    if (e == 0) MMF_STAMP(a, 5);
+
+    // ---------------- epilogue: dU tile -------------------------------------------------------------------
+    const uint32_t r = q * 32 + lane;
+    constexpr int PIECES = L / (8 * HIDDEN_EW);   // 32-column pieces per thread (L / 32 pieces over EW / 4 parts)
+    const float p_row = vec[C::V_P + r];
+    mbar_wait(smem_u32(&bar_acc), 0);   // every MMA retired: accumulator complete, both rings idle
+    tc_fence_after();
+    if (e == 0) MMF_STAMP(a, 6);
+    // (the dG stores of warp 2 have finished reading the A ring: bar_aempty completed before the last MMAs could
+    //  be issued ... except the final NSA stages: wait for their store thread explicitly)
+    mbar_wait(smem_u32(&bar_aempty[(C::NKP - 1) % C::NSA]), ((C::NKP - 1) / C::NSA) & 1);
+    if (C::NKP > 1) mbar_wait(smem_u32(&bar_aempty[(C::NKP - 2) % C::NSA]), ((C::NKP - 2) / C::NSA) & 1);
+    named_bar_sync(1, HIDDEN_ET);
+    float v[2][32];
+    tmem_ld32(tmem + ((q * 32u) << 16) + part * PIECES * 32, v[0]);
+#pragma unroll
+    for (int ii = 0; ii < PIECES; ++ii) {
+      const int cb = part * PIECES + ii;
+      tmem_ld_wait();
+      if (ii + 1 < PIECES) tmem_ld32(tmem + ((q * 32u) << 16) + (cb + 1) * 32, v[(ii + 1) & 1]);
+      float (&u)[32] = v[ii & 1];
+      const uint32_t bits = s_mask[r * (L / 32) + cb];
+      const float4* dm4 = reinterpret_cast<const float4*>(vec + C::V_DM + cb * 32);
+      uint32_t packed[16];
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 d = dm4[i >> 2];
+        const float o0 = (bits >> i) & 1u ? a.du_scale * fmaf(p_row, d.x, u[i]) : 0.f;
+        const float o1 = (bits >> (i + 1)) & 1u ? a.du_scale * fmaf(p_row, d.y, u[i + 1]) : 0.f;
+        const float o2 = (bits >> (i + 2)) & 1u ? a.du_scale * fmaf(p_row, d.z, u[i + 2]) : 0.f;
+        const float o3 = (bits >> (i + 3)) & 1u ? a.du_scale * fmaf(p_row, d.w, u[i + 3]) : 0.f;
+        packed[i >> 1] = pack_bf16x2(o0, o1);
+        packed[(i >> 1) + 1] = pack_bf16x2(o2, o3);
+      }
+      const uint32_t blk = pool + (cb >> 1) * 16384;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        st_shared_v4(blk + sw128_offset(r, (cb & 1) * 4 + j), packed[4 * j], packed[4 * j + 1], packed[4 * j + 2],
+                     packed[4 * j + 3]);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    named_bar_sync(1, HIDDEN_ET);     // the staged tile is complete
+    if (e == 0) {
+      for (int kb = 0; kb < L / 64; ++kb) tma_store_2d(&tmDU, pool + kb * 16384, kb * 64, (int)row0);
+      tma_store_commit();
+    }
+    // db1: column sums of the staged bf16 tile (rows past N were staged as zeros: their mask words are 0)
+    for (uint32_t cp = e; cp < (uint32_t)L / 2; cp += HIDDEN_ET) {
+      const uint32_t col = 2u * cp;
+      const uint32_t blk = pool + (col >> 6) * 16384u, chunk = (col & 63u) >> 3, inb = (col & 7u) * 2u;
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll 8
+      for (uint32_t rr = 0; rr < 128; ++rr) {
+        const float2 f = unpack_bf16x2(ld_shared_b32(blk + sw128_offset(rr, chunk) + inb));
+        a0 += f.x; a1 += f.y;
+      }
+      atomicAdd(a.db1 + col, a0);
+      atomicAdd(a.db1 + col + 1, a1);
+    }
+    // dwc / dbab / dbc of this CTA's rows
+    // column d of branch `which` lives in slice d / 64, column group (d % 64) / 16, slot which * 16 + d % 16 of the
+    // four row-quarter warps of that column group
+    for (int i = e; i < D + C::KD; i += HIDDEN_ET) {
+      const int which = i / D, d = i - which * D;
+      const int kp = d >> 6, ctg = (d & 63) >> 4, off = kp * 48 + which * 16 + (d & 15);
+      const float v = s_part[ctg][off] + s_part[ctg + 4][off] + s_part[ctg + 8][off] + s_part[ctg + 12][off];
+      atomicAdd(which == 0 ? a.dwc + d : a.dbab + (which - 1) * D + d, v);
+    }
+    if (e == 0) {
+      atomicAdd(a.dbc, s_dbc);
+      tma_store_wait_all();
+      MMF_STAMP(a, 7);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  timeline_end(2);
+  if (warp == 2) tmem_dealloc_pair(tmem, L);
+}
+
+}  // namespace mmf

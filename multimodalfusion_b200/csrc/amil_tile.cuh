@@ -58,6 +58,8 @@ struct AmilArgs {
   int store_h;      // fwd: also TMA-store the H tile (stash). bwd: always stored.
   uint16_t* AG;     // fwd stash: pre-dropout [tanh | sigmoid] branch outputs, fp16 [N, ldag] (or null)
   long long ldag;
+  float4* zero_ptr;   // fwd (optional): buffer the epilogue warps clear while GEMM1 runs ("zero_grad" of the step)
+  long long zero_n4;  // its length in float4
   int flags;
   unsigned long long seed;
   // backward only

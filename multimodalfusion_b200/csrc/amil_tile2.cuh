@@ -76,6 +76,7 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const int tile = blockIdx.x;
   const long long row0 = (long long)tile * 128;
 
+  timeline_start(MODE == AMIL_FWD ? 0 : 4);
   griddep_launch_dependents();   // PDL: the next kernel's prologue may overlap this kernel's tail
   if (threadIdx.x == 0) {
     MMF_STAMP(a, 0);
@@ -208,6 +209,14 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     for (int i = e; i < D; i += AMIL2_EPI_THREADS) vec[C::V_WC + i] = __ldg(a.wc + i);
     named_bar_sync(4, AMIL2_EPI_THREADS);
     if (e == 0) MMF_STAMP(a, 9);
+    if (MODE == AMIL_FWD && a.zero_ptr != nullptr) {
+      // fused zero_grad: the epilogue warps have nothing to do until GEMM1 retires (~16k cycles); they clear the
+      // step's gradient accumulators (a separate fill kernel costs ~8 us per step with its two kernel boundaries)
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (long long i = (long long)blockIdx.x * AMIL2_EPI_THREADS + e; i < a.zero_n4;
+           i += (long long)gridDim.x * AMIL2_EPI_THREADS)
+        a.zero_ptr[i] = z;
+    }
 
     // ---------------- EPI1: H = dropout(relu(U + b1)) -> swizzled smem -----------------
     mbar_wait(smem_u32(&bar_acc1), 0);
@@ -463,6 +472,7 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   __syncthreads();
   cluster_sync_all();   // the peer may still be reading this CTA's smem / TMEM through the pair MMA
   if (threadIdx.x == 0) MMF_STAMP(a, 14);
+  timeline_end(MODE == AMIL_FWD ? 0 : 4);
   if (warp == 2) tmem_dealloc_pair(tmem, 512);
 }
 

@@ -7,6 +7,7 @@
 #include "amil_tile.cuh"
 #include "amil_tile2.cuh"
 #include "amil_gate_ew.cuh"
+#include "amil_hidden_fused.cuh"
 #include <stdlib.h>
 #include "gemm_tc.cuh"
 #include "gemm2_tc.cuh"
@@ -205,6 +206,26 @@ int check_amil_common(const void* x, int64_t N, int64_t ldx, const MmfAmilWeight
 }
 
 template <int L, int D, bool GATED, bool DROP>
+int launch_hidden_fused2(const HiddenFusedArgs& a, const CUtensorMap& tmAG, const CUtensorMap& tmWab,
+                         const CUtensorMap& tmDU, cudaStream_t st) {
+  using C = HiddenFusedCfg<L, D, GATED>;
+  static bool configured = false;
+  auto kern = amil_hidden_fused_kernel<L, D, GATED, DROP>;
+  if (!configured) {
+    MMF_TRY(cuda_rc(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES)));
+    configured = true;
+  }
+  const int pairs = (int)((a.N + 255) / 256);
+  return launch_pdl(kern, dim3(2 * pairs), dim3(HIDDEN_THREADS), C::SMEM_BYTES, st, tmAG, tmAG, tmWab, tmDU, a);
+}
+template <int L, int D, bool GATED>
+int launch_hidden_fused(const HiddenFusedArgs& a, int flags, const CUtensorMap& tmAG, const CUtensorMap& tmWab,
+                        const CUtensorMap& tmDU, cudaStream_t st) {
+  return (flags & MMF_DROPOUT_ATTN) ? launch_hidden_fused2<L, D, GATED, true>(a, tmAG, tmWab, tmDU, st)
+                                    : launch_hidden_fused2<L, D, GATED, false>(a, tmAG, tmWab, tmDU, st);
+}
+
+template <int L, int D, bool GATED, bool DROP>
 int launch_gate_ew2(const GateEwArgs& a, cudaStream_t st) {
   using C = GateEwCfg<L, D, GATED>;
   static bool configured = false;
@@ -231,6 +252,11 @@ int mmf_version(void) { return MMF_ABI_VERSION; }
 
 void mmf_debug_set_timing_buffer(void* device_u64_buffer) {
   g_timing_buffer = reinterpret_cast<unsigned long long*>(device_u64_buffer);
+}
+
+void mmf_debug_set_timeline_buffer(void* device_u64_buffer) {
+  unsigned long long* p = reinterpret_cast<unsigned long long*>(device_u64_buffer);
+  cudaMemcpyToSymbol(d_timeline, &p, sizeof(p));
 }
 
 const char* mmf_error_string(int rc) {
@@ -299,7 +325,7 @@ size_t mmf_amil_bwd_workspace_bytes(int64_t N, int L, int D, int flags) {
 // (fp16 [N,KD], in the dG slot) in the backward workspace, for mmf_amil_bwd(... | MMF_STASHED).
 int mmf_amil_fwd_train(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, int L, int D,
                        int flags, uint64_t seed, float* A_raw, float* partials, void* workspace,
-                       size_t workspace_bytes, void* stream) {
+                       size_t workspace_bytes, float* zero_buf, int64_t zero_count, void* stream) {
   MMF_TRY(check_amil_common(x, N, ldx, w, L, D));
   if (!A_raw || !partials || !workspace) return MMF_E_INVALID;
   if (use_tile_v1()) return MMF_E_UNSUPPORTED;   // the single-CTA reference kernel has no stash epilogue
@@ -312,6 +338,10 @@ int mmf_amil_fwd_train(const void* x, int64_t N, int64_t ldx, const MmfAmilWeigh
   a.N = N; a.b1 = w->b1; a.bab = w->bab; a.wc = w->wc; a.bc = w->bc;
   a.A_raw = A_raw; a.partials = partials; a.store_h = 1;
   a.AG = reinterpret_cast<uint16_t*>(ws + lay.off_dG); a.ldag = gated ? 2 * D : D;
+  if (zero_buf) {
+    if ((reinterpret_cast<uintptr_t>(zero_buf) & 15u) || zero_count < 0 || (zero_count & 3)) return MMF_E_ALIGN;
+    a.zero_ptr = reinterpret_cast<float4*>(zero_buf); a.zero_n4 = zero_count >> 2;
+  }
   a.flags = flags; a.seed = seed; a.dbg = g_timing_buffer;
   return dispatch_amil<AMIL_FWD>(L, D, gated, x, N, ldx, w, a, ws + lay.off_H, (cudaStream_t)stream);
 }
@@ -399,6 +429,38 @@ int mmf_amil_bwd_gate_stashed(int64_t N, const MmfAmilWeights* w, int L, int D, 
   if (L == 512 && D == 384) rc = gated ? launch_gate_ew<512, 384, true>(a, st) : launch_gate_ew<512, 384, false>(a, st);
   if (L == 256 && D == 384) rc = gated ? launch_gate_ew<256, 384, true>(a, st) : launch_gate_ew<256, 384, false>(a, st);
   return rc;
+}
+
+// Stages 1 + 2 of the MMF_STASHED backward fused: the gate backward is the A-operand producer of the dU GEMM
+// (amil_hidden_fused.cuh). Leaves dG and dU in the workspace for the wgrad stage; accumulates dwc, dbab, dbc, db1.
+int mmf_amil_bwd_gate_hidden_stashed(int64_t N, const MmfAmilWeights* w, int L, int D, int flags, uint64_t seed,
+                                     const float* A_raw, const float* ml, const float* M, const float* dM,
+                                     const float* dA_raw, const MmfAmilGrads* g, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
+  if (!w || !w->wc || !w->Wab || N <= 0 || !workspace) return MMF_E_INVALID;
+  if (!((L == 256 && D == 256) || (L == 512 && D == 384) || (L == 256 && D == 384))) return MMF_E_UNSUPPORTED;
+  if (!A_raw || !ml || !M || !dM || !g || !g->dbab || !g->dwc || !g->dbc || !g->db1) return MMF_E_INVALID;
+  if (N > 0x7fffff00LL) return MMF_E_INVALID;
+  const int gated = flags & MMF_GATED;
+  const BwdWs lay = bwd_layout(N, L, D, gated);
+  if (workspace_bytes < lay.total) return MMF_E_WORKSPACE;
+  if (reinterpret_cast<uintptr_t>(workspace) & 1023u) return MMF_E_ALIGN;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  const int KD = gated ? 2 * D : D;
+  CUtensorMap tmAG, tmWab, tmDU;
+  MMF_TRY(make_tmap_bf16(&tmAG, ws + lay.off_dG, (uint64_t)N, KD, KD, 128));   // fp16 in / bf16 out: 2-byte elements
+  MMF_TRY(make_tmap_bf16(&tmWab, w->Wab, KD, L, L, 64));
+  MMF_TRY(make_tmap_bf16(&tmDU, ws + lay.off_dU, (uint64_t)N, L, L, 128));
+  HiddenFusedArgs a = {};
+  a.N = N; a.H = reinterpret_cast<const __nv_bfloat16*>(ws + lay.off_H);
+  a.A_raw = A_raw; a.ml = ml; a.M = M; a.dM = dM; a.dA_raw = dA_raw; a.wc = w->wc;
+  a.dwc = g->dwc; a.dbab = g->dbab; a.dbc = g->dbc; a.db1 = g->db1;
+  a.du_scale = (flags & MMF_DROPOUT_H) ? (1.0f / 0.75f) : 1.0f;
+  a.seed = seed; a.dbg = g_timing_buffer;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (L == 256 && D == 256) return gated ? launch_hidden_fused<256, 256, true>(a, flags, tmAG, tmWab, tmDU, st) : launch_hidden_fused<256, 256, false>(a, flags, tmAG, tmWab, tmDU, st);
+  if (L == 512 && D == 384) return gated ? launch_hidden_fused<512, 384, true>(a, flags, tmAG, tmWab, tmDU, st) : launch_hidden_fused<512, 384, false>(a, flags, tmAG, tmWab, tmDU, st);
+  return gated ? launch_hidden_fused<256, 384, true>(a, flags, tmAG, tmWab, tmDU, st) : launch_hidden_fused<256, 384, false>(a, flags, tmAG, tmWab, tmDU, st);
 }
 
 // Stage 2: dU = (dG Wab + p dM^T) ⊙ relu'(H) [* 1/(1-p)] -> workspace (bf16 [N,L]); db1 += colsum.
@@ -515,13 +577,20 @@ int mmf_amil_bwd(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w,
   if (!g || !g->dW1 || !g->db1 || !g->dWab || !g->dbab || !g->dwc || !g->dbc) return MMF_E_INVALID;
   if (flags & MMF_STASHED) {
     MMF_TRY(check_amil_common(x, N, ldx, w, L, D));
-    MMF_TRY(mmf_amil_bwd_gate_stashed(N, w, L, D, flags, seed, A_raw, ml, M, dM, dA_raw, g, workspace,
-                                      workspace_bytes, stream));
+    static const bool unfused = getenv("MMF_BWD_UNFUSED") && getenv("MMF_BWD_UNFUSED")[0] == '1';
+    if (!unfused) {
+      MMF_TRY(mmf_amil_bwd_gate_hidden_stashed(N, w, L, D, flags, seed, A_raw, ml, M, dM, dA_raw, g, workspace,
+                                               workspace_bytes, stream));
+    } else {   // the two-kernel form (elementwise gate pass, then the dU GEMM): kept for A/B timing and tests
+      MMF_TRY(mmf_amil_bwd_gate_stashed(N, w, L, D, flags, seed, A_raw, ml, M, dM, dA_raw, g, workspace,
+                                        workspace_bytes, stream));
+      MMF_TRY(mmf_amil_bwd_hidden(x, N, ldx, w, L, D, flags, A_raw, ml, dM, g, workspace, workspace_bytes, stream));
+    }
   } else {
     MMF_TRY(mmf_amil_bwd_gate(x, N, ldx, w, L, D, flags, seed, A_raw, ml, M, dM, dA_raw, g, workspace,
                               workspace_bytes, stream));
+    MMF_TRY(mmf_amil_bwd_hidden(x, N, ldx, w, L, D, flags, A_raw, ml, dM, g, workspace, workspace_bytes, stream));
   }
-  MMF_TRY(mmf_amil_bwd_hidden(x, N, ldx, w, L, D, flags, A_raw, ml, dM, g, workspace, workspace_bytes, stream));
   return mmf_amil_bwd_wgrad(x, N, ldx, w, L, D, flags, g, dx, workspace, workspace_bytes, stream);
 }
 

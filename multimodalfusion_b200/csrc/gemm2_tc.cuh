@@ -72,6 +72,7 @@ gemm2_tc_kernel(const __grid_constant__ TMapSet tmA, const __grid_constant__ TMa
   const int kb1 = min(g.kb_total, kb0 + kb_per_split);
   const int nkb = kb1 - kb0;
 
+  timeline_start(EPI == EPI_ATOMIC ? 3 : 5);
   griddep_launch_dependents();
   if (threadIdx.x == 0) {
     MMF_GSTAMP(g, 0);
@@ -326,6 +327,7 @@ gemm2_tc_kernel(const __grid_constant__ TMapSet tmA, const __grid_constant__ TMa
   __syncthreads();
   cluster_sync_all();
   if (threadIdx.x == 0) MMF_GSTAMP(g, 6);
+  timeline_end(EPI == EPI_ATOMIC ? 3 : 5);
   if (warp == 2) tmem_dealloc_pair(tmem, BN);
 }
 

@@ -92,6 +92,31 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
 }
 
 // ----------------------------------------------------------------------------------------
+// Debug timeline: when d_timeline is set (mmf_debug_set_timeline_buffer) CTA 0 of every hot-path kernel appends
+// its %globaltimer at kernel start and at kernel end to two logs.
+// ----------------------------------------------------------------------------------------
+__device__ unsigned long long* d_timeline = nullptr;
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Buffer layout (uint64): [0] start-log count, [1] end-log count, [16 + 2 i] = (kernel id, ns) of the i-th kernel
+// start seen by CTA 0, [16 + 8192 + 2 j] = (id, ns) of the j-th kernel end seen by CTA 0.
+__device__ __forceinline__ void timeline_start(int id) {
+  if (d_timeline && threadIdx.x == 0 && blockIdx.x == 0) {
+    const unsigned long long i = atomicAdd(d_timeline, 1ull);
+    if (i < 4096) { d_timeline[16 + 2 * i] = (unsigned long long)id; d_timeline[17 + 2 * i] = globaltimer_ns(); }
+  }
+}
+__device__ __forceinline__ void timeline_end(int id) {
+  if (d_timeline && threadIdx.x == 0 && blockIdx.x == 0) {
+    const unsigned long long j = atomicAdd(d_timeline + 1, 1ull);
+    if (j < 4096) { d_timeline[16 + 8192 + 2 * j] = (unsigned long long)id; d_timeline[17 + 8192 + 2 * j] = globaltimer_ns(); }
+  }
+}
+
+// ----------------------------------------------------------------------------------------
 // Programmatic dependent launch (PDL). A kernel launched with
 // cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the stream
 // is still draining: its CTAs run their prologue (barrier init, TMEM allocation, descriptor prefetch)

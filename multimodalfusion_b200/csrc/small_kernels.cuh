@@ -496,6 +496,7 @@ amil_head_step_cluster_kernel(const float* __restrict__ parts, int n, int L, con
   const int c_lo = rank * LC;
   const int CP = LC >> 1;                  // column pairs per CTA
   const int RG = 512 / CP;                 // row groups
+  timeline_start(1);
   griddep_launch_dependents();
   griddep_wait();   // PDL: the partials come from the tile kernel launched just before
   // early scalar loads (independent of everything else)
@@ -635,6 +636,7 @@ amil_head_step_cluster_kernel(const float* __restrict__ parts, int n, int L, con
     dM[c_lo + tid] = acc;
   }
   if (rank == 0 && dbk && tid < K) dbk[tid] += s_dlogit[tid];
+  timeline_end(1);
 }
 
 // -------------------------------------------------------------------------------------------

@@ -138,9 +138,11 @@ def amil_bwd_workspace(N: int, w: AmilPrepared, flags: int, device) -> torch.Ten
 
 
 def amil_partials_train(x: torch.Tensor, w: AmilPrepared, flags: int, seed: int = 0,
-                        workspace: Optional[torch.Tensor] = None):
+                        workspace: Optional[torch.Tensor] = None, zero: Optional[torch.Tensor] = None):
     """Training forward: (A_raw, partials, workspace) — the workspace now holds h (bf16) and the branch
-    activations (fp16) and must be handed to amil_backward(..., stash=workspace)."""
+    activations (fp16) and must be handed to amil_backward(..., stash=workspace).
+    zero: optional contiguous fp32 tensor (numel % 4 == 0) cleared by the kernel while GEMM1 runs — the step's
+    flat gradient buffer (fused zero_grad)."""
     _require_cuda(x)
     if x.dtype != torch.bfloat16 or x.dim() != 2 or x.shape[1] != IN_FEATURES or x.stride(1) != 1:
         raise ValueError("x must be a bf16 [N,1024] tensor with unit inner stride")
@@ -154,7 +156,8 @@ def amil_partials_train(x: torch.Tensor, w: AmilPrepared, flags: int, seed: int 
     partials = torch.empty(tiles, w.L + 2, dtype=torch.float32, device=x.device)
     ws = w.struct()
     check(lib().mmf_amil_fwd_train(_p(x), N, x.stride(0), C.byref(ws), w.L, w.D, flags, seed, _p(A_raw),
-                                   _p(partials), workspace.data_ptr(), workspace.numel(), _stream()),
+                                   _p(partials), workspace.data_ptr(), workspace.numel(), _p(zero),
+                                   0 if zero is None else zero.numel(), _stream()),
           "mmf_amil_fwd_train")
     return A_raw, partials, workspace
 

@@ -128,7 +128,9 @@ def test_amil_kernels_vs_bf16_oracle(dev, N, L, D, gated, drop, stash):
     xb = x.to(dev).to(torch.bfloat16)
     ws = None
     if stash:
-        A_raw, parts, ws = ops.amil_partials_train(xb, prep, flags, seed)
+        junk = torch.randn(1028, device=dev)   # fused zero_grad: the forward clears this buffer
+        A_raw, parts, ws = ops.amil_partials_train(xb, prep, flags, seed, zero=junk)
+        assert torch.count_nonzero(junk).item() == 0
         M, ml = ops.amil_combine(parts, L, True)
         A2, M2, _ = ops.amil_forward(xb, prep, flags, seed)
         assert torch.equal(A2, A_raw) and torch.equal(M2, M), "stashing must not change the forward"

@@ -31,19 +31,32 @@ names = {0: "start", 1: "after cluster sync", 2: "mma: first stage landed", 3: "
          5: "epi: done", 6: "after final cluster sync"}
 
 
+names_fused = {0: "start", 1: "after cluster sync + PDL wait", 2: "mma: first A stage ready", 3: "mma: all issued",
+               4: "epi: phase A done (ds, mask)", 5: "epi: all slices transformed", 6: "epi: acc ready", 7: "epi: done",
+               8: "slice 0: A tile landed", 9: "slice 0: transformed", 10: "slice 1: A tile landed", 11: "slice 1: transformed",
+               12: "slice 2: A tile landed", 13: "slice 2: transformed"}
+
+
 def run(which):
-    if which == "hidden":
+    if which == "fused":
+        ops.amil_partials_train(x, prep, flags, 1, workspace=ws)
+        torch.cuda.synchronize()
+        if buf_holder: buf_holder[0].zero_()
+        check(lib.mmf_amil_bwd_gate_hidden_stashed(N, C.byref(wst), L, D, flags, 1, A_raw.data_ptr(), ml.data_ptr(), M.data_ptr(), dM.data_ptr(), None, C.byref(gs), ws.data_ptr(), ws.numel(), S))
+    elif which == "hidden":
         check(lib.mmf_amil_bwd_hidden(x.data_ptr(), N, 1024, C.byref(wst), L, D, flags, A_raw.data_ptr(), ml.data_ptr(), dM.data_ptr(), C.byref(gs), ws.data_ptr(), ws.numel(), S))
     else:
         check(lib.mmf_amil_bwd_wgrad(x.data_ptr(), N, 1024, C.byref(wst), L, D, flags, C.byref(gs), None, ws.data_ptr(), ws.numel(), S))
 
 
 check(lib.mmf_amil_bwd_gate_stashed(N, C.byref(wst), L, D, flags, 1, A_raw.data_ptr(), ml.data_ptr(), M.data_ptr(), dM.data_ptr(), None, C.byref(gs), ws.data_ptr(), ws.numel(), S))
-for which in ("hidden", "wgrad"):
+buf_holder = []
+for which in ("fused", "hidden", "wgrad"):
     for _ in range(3):
         run(which)
     torch.cuda.synchronize()
     buf = torch.zeros(512, 16, dtype=torch.int64, device=dev)
+    buf_holder[:] = [buf]
     lib.mmf_debug_set_timing_buffer(buf.data_ptr())
     run(which)
     torch.cuda.synchronize()
@@ -53,10 +66,9 @@ for which in ("hidden", "wgrad"):
     t = t[used]
     rel = t - t[:, :1]
     print(f"== {which}: {int(used.sum())} CTAs; cycles since CTA start (median leader / median peer / max) ==")
-    for k in sorted(names):
+    nm = names_fused if which == "fused" else names
+    for k in sorted(nm):
         lead = rel[0::2, k][t[0::2, k] > 0]; peer = rel[1::2, k][t[1::2, k] > 0]
         allv = rel[:, k][t[:, k] > 0]
         f = lambda v: f"{v.median().item():9.0f}" if len(v) else "      nan"
-        print(f"  {k} {names[k]:28s} {f(lead)} {f(peer)} {allv.max().item() if len(allv) else float('nan'):9.0f}")
-    span = (t[:, 6].max() - t[:, 0].min()).item()
-    print(f"  first start -> last end: {span:.0f} cycles (globaltimer-free estimate; SM clocks are not synchronised)")
+        print(f"  {k} {nm[k]:32s} {f(lead)} {f(peer)} {allv.max().item() if len(allv) else float('nan'):9.0f}")
