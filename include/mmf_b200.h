@@ -110,6 +110,20 @@ int mmf_amil_fwd(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w,
                  int flags, uint64_t seed, float* A_raw, float* partials, void* H_stash,
                  void* stream);
 
+/* Cohort inference over ragged bags in two launches (the per-slide forward of create_heatmaps.py /
+ * pre_trained_feature.py:116-162 for a whole batch of slides; the reference loops one slide at a time).
+ *   x                bf16 [R, ldx]: the bags packed back to back, every bag starting on a 128-row boundary, padding
+ *                    rows ZERO; R a multiple of 128
+ *   tile_valid       int32 [R/128]: rows of tile t that belong to its bag (1..128; 0 for a pure padding tile)
+ *   seg_tile_offsets int32 [n_bags+1]: bag b owns tiles seg_tile_offsets[b] .. seg_tile_offsets[b+1]
+ *   outputs          A_raw f32 [R] (padding rows unwritten), partials f32 [R/128, L+2] (scratch), M f32 [n_bags, L],
+ *                    ml f32 [n_bags, 2] or NULL, hazards / S f32 [n_bags, K], risk f32 [n_bags] = -sum_k S (or NULL),
+ *                    Y_hat int64 [n_bags] or NULL.  Eval mode only (no dropout flags). */
+int mmf_amil_infer_varlen(const void* x, int64_t R, int64_t ldx, const MmfAmilWeights* w, int L, int D, int flags,
+                          const int32_t* tile_valid, const int32_t* seg_tile_offsets, int n_bags, const float* Wk,
+                          const float* bk, int K, float* A_raw, float* partials, float* M, float* ml, float* hazards,
+                          float* S, float* risk, int64_t* Y_hat, void* stream);
+
 /* Combines n softmax partials (rows of L+2 floats) into one.
  *   normalize != 0: M[L] = Σ acc_t e^{m_t-m} / l,  ml[2] = (m, l)           (final result)
  *   normalize == 0: out[L+2] = (m, l, Σ acc_t e^{m_t-m})                   (rank-local partial,

@@ -94,6 +94,8 @@ SIGNATURES = {
     "mmf_pack_wab": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "mmf_amil_num_tiles": (_i64, [_i64]),
     "mmf_amil_fwd": (_i, [_vp, _i64, _i64, C.POINTER(AmilWeights), _i, _i, _i, _u64, _vp, _vp, _vp, _vp]),
+    "mmf_amil_infer_varlen": (_i, [_vp, _i64, _i64, C.POINTER(AmilWeights), _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp,
+                                   _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mmf_amil_combine": (_i, [_vp, _i64, _i, _i, _vp, _vp, _vp]),
     "mmf_amil_bwd_workspace_bytes": (_sz, [_i64, _i, _i, _i]),
     "mmf_amil_fwd_train": (_i, [_vp, _i64, _i64, C.POINTER(AmilWeights), _i, _i, _i, _u64, _vp, _vp, _vp, _sz, _vp, _i64,

@@ -58,6 +58,8 @@ struct AmilArgs {
   int store_h;      // fwd: also TMA-store the H tile (stash). bwd: always stored.
   uint16_t* AG;     // fwd stash: pre-dropout [tanh | sigmoid] branch outputs, fp16 [N, ldag] (or null)
   long long ldag;
+  const int* tile_valid;  // fwd, varlen inference (optional): valid rows (0..128) of every 128-row tile of a packed
+                          // multi-bag buffer; null = one bag of N rows
   float4* zero_ptr;   // fwd (optional): buffer the epilogue warps clear while GEMM1 runs ("zero_grad" of the step)
   long long zero_n4;  // its length in float4
   int flags;

@@ -189,7 +189,12 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const uint32_t r = q * 32 + lane;           // row within the tile == TMEM lane
     const uint32_t e = threadIdx.x - 128;       // 0..255 epilogue thread index
     const long long row = row0 + r;
-    const bool row_ok = row < a.N;
+    // rows of this tile that belong to the bag: the tail of a single bag, or the per-tile count of a packed
+    // multi-bag buffer (varlen cohort inference: bags start on 128-row boundaries, padding rows are zero)
+    const int valid = (row0 >= a.N) ? 0
+                      : (MODE == AMIL_FWD && a.tile_valid != nullptr) ? __ldg(a.tile_valid + tile)
+                      : (int)min((long long)128, a.N - row0);
+    const bool row_ok = (int)r < valid;
     const uint32_t tq = tmem + ((q * 32u) << 16);
     const bool drop_h = (a.flags & MMF_DROPOUT_H) != 0;
     const bool drop_attn = (a.flags & MMF_DROPOUT_ATTN) != 0;
@@ -426,7 +431,7 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       // ---------------- FWD: scores out + tile softmax partial ------------------------
       sS[half * 128 + r] = s_acc;
       named_bar_sync(2, AMIL2_EPI_THREADS);
-      const bool tile_ok = row0 < a.N;
+      const bool tile_ok = valid > 0 || (a.tile_valid != nullptr && row0 < a.N);   // (empty varlen tiles still write m = -inf)
       if (half == 0) {
         const float s = row_ok ? sS[r] + sS[128 + r] + __ldg(a.bc) : -INFINITY;
         if (row_ok) a.A_raw[row] = s;

@@ -309,6 +309,27 @@ int mmf_amil_fwd(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w,
   return dispatch_amil<AMIL_FWD>(L, D, flags & MMF_GATED, x, N, ldx, w, a, H_stash, (cudaStream_t)stream);
 }
 
+// Cohort inference: ONE fused-forward launch over a packed multi-bag buffer + one head launch for all bags.
+int mmf_amil_infer_varlen(const void* x, int64_t R, int64_t ldx, const MmfAmilWeights* w, int L, int D, int flags,
+                          const int32_t* tile_valid, const int32_t* seg_tile_offsets, int n_bags, const float* Wk,
+                          const float* bk, int K, float* A_raw, float* partials, float* M, float* ml, float* hazards,
+                          float* S, float* risk, int64_t* Y_hat, void* stream) {
+  MMF_TRY(check_amil_common(x, R, ldx, w, L, D));
+  if (!tile_valid || !seg_tile_offsets || n_bags <= 0 || !Wk || !bk || !A_raw || !partials || !M || !hazards || !S)
+    return MMF_E_INVALID;
+  if (K <= 0 || K > 16 || L > 1024 || (R % 128) != 0) return MMF_E_UNSUPPORTED;
+  if (use_tile_v1()) return MMF_E_UNSUPPORTED;
+  if (flags & (MMF_DROPOUT_H | MMF_DROPOUT_ATTN)) return MMF_E_INVALID;   // inference only
+  AmilArgs a = {};
+  a.N = R; a.b1 = w->b1; a.bab = w->bab; a.wc = w->wc; a.bc = w->bc;
+  a.A_raw = A_raw; a.partials = partials; a.tile_valid = tile_valid;
+  a.flags = flags; a.dbg = g_timing_buffer;
+  MMF_TRY(dispatch_amil<AMIL_FWD>(L, D, flags & MMF_GATED, x, R, ldx, w, a, nullptr, (cudaStream_t)stream));
+  amil_seg_head_kernel<<<n_bags, 256, 0, (cudaStream_t)stream>>>(partials, seg_tile_offsets, L, Wk, bk, K, M, ml, hazards,
+                                                                 S, risk, reinterpret_cast<long long*>(Y_hat));
+  return launch_status();
+}
+
 int mmf_amil_combine(const float* partials, int64_t n, int L, int normalize, float* out, float* ml,
                      void* stream) {
   if (!partials || !out || n <= 0 || L <= 0 || (normalize && !ml)) return MMF_E_INVALID;

@@ -461,6 +461,106 @@ amil_head_step_kernel(const float* __restrict__ parts, int n, int L, const float
 }
 
 // -------------------------------------------------------------------------------------------
+// Cohort inference tail: one CTA per bag of a packed multi-bag forward. Combines the bag's tile partials
+// (tiles seg_off[b] .. seg_off[b+1]) into M[b], then the discrete-hazard head: hazards, S, Y_hat, risk = -sum S.
+// (models/model_attention_mil_path.py:55-61 + utils/core_utils.py:207, for every slide of a cohort in one launch)
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+amil_seg_head_kernel(const float* __restrict__ parts, const int* __restrict__ seg_off, int L,
+                     const float* __restrict__ Wk, const float* __restrict__ bk, int K, float* __restrict__ M,
+                     float* __restrict__ ml, float* __restrict__ hazards, float* __restrict__ S,
+                     float* __restrict__ risk, long long* __restrict__ Y_hat) {
+  __shared__ float s_w[1024];
+  __shared__ float s_M[1024];
+  __shared__ float s_red[8];
+  __shared__ float s_logit[16];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int t0 = seg_off[b], n = seg_off[b + 1] - t0;
+  const long long stride = L + 2;
+  const float* p0 = parts + (long long)t0 * stride;
+  float m = -CUDART_INF_F;
+  for (int t = tid; t < n; t += 256) m = fmaxf(m, p0[t * stride]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) s_red[wid] = m;
+  __syncthreads();
+  m = s_red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) m = fmaxf(m, s_red[i]);
+  __syncthreads();
+  float l = 0.f;
+  // tiles are processed in blocks of 1024 softmax weights (a 64k-instance slide has 512 tiles)
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int tb = 0; tb < n; tb += 1024) {
+    const int nb = min(1024, n - tb);
+    for (int t = tid; t < nb; t += 256) {
+      const float mt = p0[(tb + t) * stride];
+      const float w = (mt > -CUDART_INF_F) ? __expf(mt - m) : 0.f;
+      s_w[t] = w;
+      l = fmaf(p0[(tb + t) * stride + 1], w, l);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c0 = tid + 256 * j;
+      if (c0 < L) {
+        float a0 = 0.f, a1 = 0.f;
+        int t = 0;
+        for (; t + 2 <= nb; t += 2) {
+          a0 = fmaf(p0[(tb + t) * stride + 2 + c0], s_w[t], a0);
+          a1 = fmaf(p0[(tb + t + 1) * stride + 2 + c0], s_w[t + 1], a1);
+        }
+        if (t < nb) a0 = fmaf(p0[(tb + t) * stride + 2 + c0], s_w[t], a0);
+        acc[j] += a0 + a1;
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+  if (lane == 0) s_red[wid] = l;
+  __syncthreads();
+  l = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) l += s_red[i];
+  const float inv = l > 0.f ? 1.f / l : 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c0 = tid + 256 * j;
+    if (c0 < L) {
+      const float v = acc[j] * inv;
+      s_M[c0] = v;
+      M[(long long)b * L + c0] = v;
+    }
+  }
+  if (tid == 0 && ml) { ml[2 * b] = m; ml[2 * b + 1] = l; }
+  __syncthreads();
+  for (int j = wid; j < K; j += 8) {
+    float d = 0.f;
+    for (int c0 = lane; c0 < L; c0 += 32) d = fmaf(s_M[c0], Wk[(long long)j * L + c0], d);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    if (lane == 0) s_logit[j] = d + bk[j];
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float surv = 1.f, best = -CUDART_INF_F, rsum = 0.f;
+    int besti = 0;
+    for (int j = 0; j < K; ++j) {
+      const float lg = s_logit[j];
+      if (lg > best) { best = lg; besti = j; }
+      const float h = 1.f / (1.f + expf(-lg));
+      surv *= (1.f - h);
+      hazards[(long long)b * K + j] = h;
+      S[(long long)b * K + j] = surv;
+      rsum += surv;
+    }
+    if (risk) risk[b] = -rsum;
+    if (Y_hat) Y_hat[b] = besti;
+  }
+}
+
+// -------------------------------------------------------------------------------------------
 // Cluster version of amil_head_step_kernel: 8 CTAs (one thread-block cluster) split the L pooled
 // columns, so the combine is ONE batch of independent loads per thread (n/RG rows each) instead of
 // four dependent batches on a single SM, and the K partial logits of every CTA are exchanged through

@@ -48,3 +48,17 @@ class MIL_Attention_fc_surv_path(MIL_Attention_fc_path):
             return A_raw
         hazards, S, Y_hat = HazardHead.apply(M, self.classifier.weight, self.classifier.bias)
         return hazards, S, Y_hat, A_raw
+
+    @torch.no_grad()
+    def infer_cohort(self, bags):
+        """Eval-mode forward of MANY slides at once (new capability; the reference loops batch-1, e.g.
+        pre_trained_feature.py:116-162 / create_heatmaps.py): the bags are packed into one varlen buffer and run as
+        one fused-forward launch + one head launch. Returns (hazards [n,K], S [n,K], Y_hat [n,1], [A_raw_i [1,N_i]])
+        — row i equals forward(path_features=bags[i]) in eval mode."""
+        from .. import ops
+        fc, attn = self.attention_net_WSI[0], self.attention_net_WSI[3]
+        prep = ops.prepare_amil_weights(fc.weight, fc.bias, *attn.amil_weights())
+        packed = ops.pack_bags(bags)
+        out = ops.amil_infer_varlen(packed, prep, self.classifier.weight, self.classifier.bias)
+        A = [out["A_raw"][o:o + n].view(1, n) for o, n in zip(packed.row_offsets, packed.sizes)]
+        return out["hazards"], out["S"], out["Y_hat"], A

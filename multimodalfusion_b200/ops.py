@@ -162,6 +162,63 @@ def amil_partials_train(x: torch.Tensor, w: AmilPrepared, flags: int, seed: int 
     return A_raw, partials, workspace
 
 
+@dataclass
+class PackedBags:
+    """Ragged bags packed for one varlen launch: x bf16 [R,1024] (every bag on a 128-row boundary, padding rows
+    zero), tile_valid int32 [R/128], seg_tile_offsets int32 [n+1], row_offsets / sizes (host lists)."""
+    x: torch.Tensor
+    tile_valid: torch.Tensor
+    seg_tile_offsets: torch.Tensor
+    row_offsets: list
+    sizes: list
+
+
+def pack_bags(bags: Sequence[torch.Tensor]) -> PackedBags:
+    """Packs CUDA feature bags ([N_i,1024], fp32 or bf16) into the varlen layout of mmf_amil_infer_varlen."""
+    _require_cuda(*bags)
+    sizes = [int(b.shape[0]) for b in bags]
+    if min(sizes) < 1:
+        raise ValueError("empty bag")
+    tiles = [(n + TILE_ROWS - 1) // TILE_ROWS for n in sizes]
+    seg = [0]
+    for t in tiles:
+        seg.append(seg[-1] + t)
+    R = seg[-1] * TILE_ROWS
+    dev = bags[0].device
+    x = torch.zeros(R, IN_FEATURES, dtype=torch.bfloat16, device=dev)
+    row_off = []
+    for b, t0, n in zip(bags, seg, sizes):
+        row_off.append(t0 * TILE_ROWS)
+        x[t0 * TILE_ROWS:t0 * TILE_ROWS + n].copy_(b)       # casts fp32 -> bf16 (RNE) on the fly
+    tv = torch.full((seg[-1],), TILE_ROWS, dtype=torch.int32)
+    for t0, t, n in zip(seg, tiles, sizes):
+        tv[t0 + t - 1] = n - (t - 1) * TILE_ROWS
+    return PackedBags(x, tv.to(dev), torch.tensor(seg, dtype=torch.int32, device=dev), row_off, sizes)
+
+
+def amil_infer_varlen(packed: PackedBags, w: AmilPrepared, Wk: torch.Tensor, bk: torch.Tensor):
+    """Cohort inference in two launches. Returns dict(A_raw [R] (index with packed.row_offsets / sizes), M [n,L],
+    hazards [n,K], S [n,K], risk [n], Y_hat [n,1])."""
+    _require_cuda(packed.x, Wk)
+    R, n = packed.x.shape[0], len(packed.sizes)
+    dev = packed.x.device
+    K = Wk.shape[0]
+    Wk, bk = _f32c(Wk), _f32c(bk)
+    out = dict(A_raw=torch.empty(R, dtype=torch.float32, device=dev),
+               M=torch.empty(n, w.L, dtype=torch.float32, device=dev),
+               hazards=torch.empty(n, K, dtype=torch.float32, device=dev),
+               S=torch.empty(n, K, dtype=torch.float32, device=dev),
+               risk=torch.empty(n, dtype=torch.float32, device=dev),
+               Y_hat=torch.empty(n, 1, dtype=torch.int64, device=dev))
+    partials = torch.empty(R // TILE_ROWS, w.L + 2, dtype=torch.float32, device=dev)
+    ws = w.struct()
+    check(lib().mmf_amil_infer_varlen(_p(packed.x), R, packed.x.stride(0), C.byref(ws), w.L, w.D, amil_flags(w.gated),
+                                      _p(packed.tile_valid), _p(packed.seg_tile_offsets), n, _p(Wk), _p(bk), K,
+                                      _p(out["A_raw"]), _p(partials), _p(out["M"]), None, _p(out["hazards"]), _p(out["S"]),
+                                      _p(out["risk"]), _p(out["Y_hat"]), _stream()), "mmf_amil_infer_varlen")
+    return out
+
+
 def amil_combine(partials: torch.Tensor, L: int, normalize: bool = True):
     """normalize: (M [L], ml [2]);  else one (L+2) partial row (m, l, acc)."""
     _require_cuda(partials)

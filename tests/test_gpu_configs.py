@@ -155,3 +155,21 @@ def test_config5_cohort_inference_ragged_bags(dev):
             assert r[b] > r[a]
     assert abs(O.concordance_index(r, torch.arange(len(sizes)).float(), torch.ones(len(sizes)))
                - O.concordance_index(rr, torch.arange(len(sizes)).float(), torch.ones(len(sizes)))) < 0.02
+
+
+def test_config5_varlen_cohort_launch_equals_per_slide_forward(dev):
+    """mmf_amil_infer_varlen (all slides of a batch in one fused-forward launch + one head launch) == the batch-1
+    forward slide by slide: identical attention scores, identical hazards / risk / Y_hat up to the fp32 combine order."""
+    from multimodalfusion_b200.models import MIL_Attention_fc_surv_path
+    for size in ("small", "big"):
+        torch.manual_seed(6)
+        model = MIL_Attention_fc_surv_path(gate_path=True, model_size_wsi=size, n_classes=4).eval().to(dev)
+        sizes = [1, 127, 128, 129, 500, 3000, 256, 7777, 64, 20000]
+        bags = [cases.features(n, 40 + i).to(dev) for i, n in enumerate(sizes)]
+        hz, S, Y_hat, A = model.infer_cohort(bags)
+        assert hz.shape == (len(sizes), 4) and Y_hat.shape == (len(sizes), 1)
+        for i, b in enumerate(bags):
+            with torch.no_grad():
+                h1, S1, Y1, A1 = model(path_features=b)
+            assert torch.equal(A[i], A1), (size, i)
+            assert rel_err(hz[i], h1) < 1e-5 and rel_err(S[i], S1) < 1e-5 and Y_hat[i].item() == Y1.item()
