@@ -828,9 +828,24 @@ int mmf_p2p_allreduce_sum_f32(void* const* bufs_host, void* const* flags_host, v
   a.n = n; a.world = world; a.rank = rank;
   a.mc = reinterpret_cast<float*>(multicast_ptr);
   if (multicast_ptr && (reinterpret_cast<uintptr_t>(multicast_ptr) & 15u)) return MMF_E_ALIGN;
-  // plain stream-ordered launch: as a programmatic dependent of the wgrad kernel the exchange took 100 us instead
-  // of 35 us (measured at 2 GPUs; its early-resident CTAs sit between the step's 1-CTA-per-SM kernels)
-  p2p_allreduce_sum_kernel<<<n_ctas, P2P_THREADS, 0, (cudaStream_t)stream>>>(a);
+  // Plain stream-ordered launch (as a programmatic dependent of the wgrad kernel the exchange took 100 us instead of
+  // 35 us), as clusters of 2 CTAs: the exchange usually overlaps the next step on a second stream, and its CTAs sit
+  // in handshake spins until the slowest rank arrives. Scattered single CTAs would each take one SM out of a
+  // different TPC and leave the step's CTA-PAIR kernels (70 pairs of 74 TPCs) short of whole TPCs — a second wave
+  // of the wgrad kernel, +80 us per step at 8 GPUs. Pairs of CTAs occupy whole TPCs instead.
+  if (n_ctas & 1) ++n_ctas;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(n_ctas); cfg.blockDim = dim3(P2P_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  // MMF_P2P_PDL=1: also a programmatic dependent of the previous kernel in the stream (in-stream placement right
+  // after the wgrad GEMM: with only 2-8 TPCs taken by the exchange the wgrad's 70 CTA pairs still fit in one wave)
+  static const bool p2p_pdl = getenv("MMF_P2P_PDL") && getenv("MMF_P2P_PDL")[0] == '1';
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = p2p_pdl ? 2 : 1;
+  MMF_TRY(cuda_rc(cudaLaunchKernelEx(&cfg, p2p_allreduce_sum_kernel, a)));
   return launch_status();
 }
 

@@ -138,9 +138,9 @@ class PeerAllReduce:
             self._mc.append(mc if mc else None)   # NVLS multicast mapping when the fabric supports it
             self._keep = getattr(self, "_keep", []) + [hb, hf]
         if self.n_ctas <= 0:
-            # the exchange is latency-bound (~27 us at 3.7 MB whatever the CTA count): with NVLS 8 CTAs suffice and
-            # leave the SMs to the step's own kernels when the all-reduce overlaps them; peer loads want more
-            self.n_ctas = 8 if self.multicast else 32
+            # the exchange is latency-bound (~27 us at 3.7 MB whatever the CTA count): with NVLS 4 CTAs (2 TPCs) suffice
+            # and leave the SMs to the step's own kernels when the all-reduce overlaps them; peer loads want more
+            self.n_ctas = 4 if self.multicast else 16
         torch.cuda.synchronize()
         dist.barrier(self.group)   # every rank's flags are zeroed before the first handshake
 
