@@ -271,6 +271,25 @@ int mmf_ranking_fwd_bwd(const float* risks, const float* times, const float* c, 
                         int reduction, float* loss, float* drisks, int64_t* n_pairs, void* workspace,
                         size_t workspace_bytes, void* stream);
 
+/* ---- training-step glue -------------------------------------------------
+ * Fused multi-tensor Adam: torch.optim.Adam(lr, weight_decay) as the reference builds it (utils/utils.py:144-151), one
+ * launch for all parameter tensors; step >= 1 is the 1-based step count (bias corrections). Per element:
+ *   g = grad * grad_scale + l1_lambda * sign(p) + weight_decay * p;  m, v updated;  p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+ * l1_lambda folds the reference's l1_reg_all penalty (utils/utils.py:249-257; lambda * sum|W| added to the loss at
+ * utils/core_utils.py:218-221,242) into the update; l1_out (nullable, device) += sum |p| over all tensors (pre-update)
+ * for logging. zero_grad != 0 also clears the gradients (optimizer.zero_grad(), utils/core_utils.py:246).
+ * The *_host arrays are HOST arrays of n_tensors device pointers / element counts. */
+int mmf_adam_step_multi(float* const* params_host, const float* const* grads_host, float* const* exp_avg_host,
+                        float* const* exp_avg_sq_host, const int64_t* numel_host, int n_tensors, int step, float lr,
+                        float beta1, float beta2, float eps, float weight_decay, float grad_scale, float l1_lambda,
+                        int zero_grad, float* l1_out, void* stream);
+
+/* Concordance index counts as sksurv.concordance_index_censored(event, time, risk, tied_tol) computes them
+ * (utils/core_utils.py:258): over comparable pairs (event_i != 0 and t_i < t_j): counts[0] concordant
+ * (risk_i > risk_j + tol), counts[1] discordant, counts[2] tied in risk. c-index = (c + 0.5 t) / (c + d + t). */
+int mmf_cindex_counts(const float* risk, const float* times, const float* event, int B, float tied_tol,
+                      uint64_t* counts, void* stream);
+
 /* ---- multi-GPU: SUM all-reduce of a small fp32 buffer over NVLink peer memory ----------------
  * The gradient all-reduce that closes a cohort-data-parallel step (the reference is
  * single-GPU and has no counterpart) as one kernel on the caller's stream: ready handshake, reduce of

@@ -14,6 +14,8 @@
 #include "mmf_host.cuh"
 #include "small_kernels.cuh"
 #include "p2p_allreduce.cuh"
+#include "train_glue.cuh"
+#include <math.h>
 
 using namespace mmf;
 
@@ -808,6 +810,48 @@ int mmf_ranking_fwd_bwd(const float* risks, const float* times, const float* c, 
   ranking_pairs_kernel<<<blocks, 128, 0, st>>>(risks, times, c, B, phi, acc, g);
   ranking_finalize_kernel<<<blocks, 128, 0, st>>>(acc, B, reduction, loss, drisks, g,
                                                   reinterpret_cast<long long*>(n_pairs));
+  return launch_status();
+}
+
+int mmf_adam_step_multi(float* const* params_host, const float* const* grads_host, float* const* exp_avg_host,
+                        float* const* exp_avg_sq_host, const int64_t* numel_host, int n_tensors, int step, float lr,
+                        float beta1, float beta2, float eps, float weight_decay, float grad_scale, float l1_lambda,
+                        int zero_grad, float* l1_out, void* stream) {
+  if (!params_host || !grads_host || !exp_avg_host || !exp_avg_sq_host || !numel_host || n_tensors <= 0 || step < 1)
+    return MMF_E_INVALID;
+  AdamHyper h = {};
+  h.lr = lr; h.beta1 = beta1; h.beta2 = beta2; h.eps = eps; h.weight_decay = weight_decay; h.grad_scale = grad_scale;
+  h.l1_lambda = l1_lambda; h.zero_grad = zero_grad;
+  h.bias1 = (float)(1.0 - pow((double)beta1, (double)step));
+  h.bias2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+  for (int t0 = 0; t0 < n_tensors; t0 += ADAM_MAX_TENSORS) {
+    AdamTensors T = {};
+    T.n = n_tensors - t0 < ADAM_MAX_TENSORS ? n_tensors - t0 : ADAM_MAX_TENSORS;
+    long long acc = 0;
+    for (int k = 0; k < T.n; ++k) {
+      if (!params_host[t0 + k] || !grads_host[t0 + k] || !exp_avg_host[t0 + k] || !exp_avg_sq_host[t0 + k] ||
+          numel_host[t0 + k] < 0)
+        return MMF_E_INVALID;
+      T.p[k] = params_host[t0 + k]; T.g[k] = grads_host[t0 + k]; T.m[k] = exp_avg_host[t0 + k];
+      T.v[k] = exp_avg_sq_host[t0 + k];
+      T.start[k] = acc; acc += numel_host[t0 + k];
+    }
+    T.start[T.n] = acc;
+    if (acc == 0) continue;
+    long long blocks = (acc + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    adam_multi_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(T, h, l1_out);
+    MMF_TRY(launch_status());
+  }
+  return MMF_OK;
+}
+
+int mmf_cindex_counts(const float* risk, const float* times, const float* event, int B, float tied_tol,
+                      uint64_t* counts, void* stream) {
+  if (!risk || !times || !event || !counts || B <= 0) return MMF_E_INVALID;
+  MMF_TRY(cuda_rc(cudaMemsetAsync(counts, 0, 3 * sizeof(uint64_t), (cudaStream_t)stream)));
+  cindex_pairs_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(risk, times, event, B, tied_tol,
+                                                           reinterpret_cast<unsigned long long*>(counts));
   return launch_status();
 }
 

@@ -1,0 +1,93 @@
+// train_glue.cuh — the training-step glue either side of the hot path: fused multi-tensor
+// Adam (+ weight decay, + the l1_reg_all penalty and its sign gradient) and the concordance index on the device.
+//
+//   Adam      torch.optim.Adam as the reference builds it (utils/utils.py:144-151: lr, weight_decay = --reg, default
+//             betas / eps, no amsgrad), one launch for every parameter tensor of the model instead of ~10 ATen
+//             kernels per tensor; the reference's l1 regulariser (utils/utils.py:249-257: sum |W| over all parameters,
+//             added to the loss as lambda * sum, utils/core_utils.py:218-221,242) is folded in: its gradient
+//             lambda * sign(W) joins the gradient and the penalty value is accumulated for logging.
+//   c-index   sksurv.concordance_index_censored(event, time, risk, tied_tol) as called at utils/core_utils.py:258:
+//             comparable pairs (event_i, t_i < t_j); concordant when risk_i > risk_j; |risk_i - risk_j| <= tied_tol
+//             counts half. O(B^2) pair grid, integer counts (exact).
+#pragma once
+#include <stdint.h>
+
+namespace mmf {
+
+constexpr int ADAM_MAX_TENSORS = 48;
+struct AdamTensors {
+  float* p[ADAM_MAX_TENSORS];
+  const float* g[ADAM_MAX_TENSORS];
+  float* m[ADAM_MAX_TENSORS];
+  float* v[ADAM_MAX_TENSORS];
+  long long start[ADAM_MAX_TENSORS + 1];   // prefix sum of element counts: a flat index space over all tensors
+  int n;
+};
+struct AdamHyper {
+  float lr, beta1, beta2, eps, weight_decay, grad_scale, l1_lambda;
+  float bias1, bias2_sqrt;   // 1 - beta1^t, sqrt(1 - beta2^t)
+  int zero_grad;             // also clear g (optimizer.zero_grad() fused)
+};
+
+__global__ void __launch_bounds__(256) adam_multi_kernel(const AdamTensors T, const AdamHyper h, float* __restrict__ l1_out) {
+  __shared__ float s_red[8];
+  const long long total = T.start[T.n];
+  float l1 = 0.f;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    int k = 0;   // tensor of flat index i (linear scan: n <= 48, cached constants)
+    while (i >= T.start[k + 1]) ++k;
+    const long long j = i - T.start[k];
+    const float p = T.p[k][j];
+    float g = T.g[k][j] * h.grad_scale;
+    if (h.l1_lambda != 0.f) g += h.l1_lambda * (p > 0.f ? 1.f : (p < 0.f ? -1.f : 0.f));
+    l1 += fabsf(p);
+    g = fmaf(h.weight_decay, p, g);
+    const float m = fmaf(h.beta1, T.m[k][j], (1.f - h.beta1) * g);
+    const float v = fmaf(h.beta2, T.v[k][j], (1.f - h.beta2) * g * g);
+    T.m[k][j] = m;
+    T.v[k][j] = v;
+    const float denom = sqrtf(v) / h.bias2_sqrt + h.eps;
+    T.p[k][j] = p - (h.lr / h.bias1) * (m / denom);
+    if (h.zero_grad) const_cast<float*>(T.g[k])[j] = 0.f;
+  }
+  if (l1_out) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) l1 += __shfl_xor_sync(0xffffffffu, l1, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = l1;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int i = 0; i < 8; ++i) t += s_red[i];
+      atomicAdd(l1_out, t);
+    }
+  }
+}
+
+// counts[0] concordant, [1] discordant, [2] tied in risk, over comparable pairs (event_i and t_i < t_j)
+__global__ void __launch_bounds__(256) cindex_pairs_kernel(const float* __restrict__ risk, const float* __restrict__ times,
+                                                           const float* __restrict__ event, int B, float tied_tol,
+                                                           unsigned long long* __restrict__ counts) {
+  __shared__ unsigned long long s_c[3];
+  if (threadIdx.x < 3) s_c[threadIdx.x] = 0ull;
+  __syncthreads();
+  unsigned int conc = 0, disc = 0, tied = 0;
+  const int i = blockIdx.x;
+  if (event[i] != 0.f) {
+    const float ti = times[i], ri = risk[i];
+    for (int j = threadIdx.x; j < B; j += 256) {
+      if (times[j] > ti) {
+        const float d = ri - risk[j];
+        if (fabsf(d) <= tied_tol) ++tied;
+        else if (d > 0.f) ++conc;
+        else ++disc;
+      }
+    }
+  }
+  atomicAdd(&s_c[0], (unsigned long long)conc);
+  atomicAdd(&s_c[1], (unsigned long long)disc);
+  atomicAdd(&s_c[2], (unsigned long long)tied);
+  __syncthreads();
+  if (threadIdx.x < 3 && s_c[threadIdx.x]) atomicAdd(counts + threadIdx.x, s_c[threadIdx.x]);
+}
+
+}  // namespace mmf
