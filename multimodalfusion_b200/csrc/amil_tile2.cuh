@@ -54,7 +54,10 @@ struct Amil2Cfg {
 constexpr int AMIL2_THREADS = 384;
 constexpr uint32_t AMIL2_EPI_THREADS = 256;
 
-template <int L, int D, bool GATED, int MODE>
+// DROPH / DROPA: train-mode dropout on h / on the attention branches, compile-time: with run-time flags the mask
+// selection (shift, and, compare, select per element and branch) was executed even with dropout off and made up
+// 10 of the ~22 instructions per element pair of the gate epilogue, which bounds the GEMM2 phase (issue-bound).
+template <int L, int D, bool GATED, int MODE, bool DROPH, bool DROPA>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AMIL2_THREADS, 1)
 amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                   const __grid_constant__ CUtensorMap tmWab, const __grid_constant__ CUtensorMap tmH,
@@ -196,8 +199,8 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                       : (int)min((long long)128, a.N - row0);
     const bool row_ok = (int)r < valid;
     const uint32_t tq = tmem + ((q * 32u) << 16);
-    const bool drop_h = (a.flags & MMF_DROPOUT_H) != 0;
-    const bool drop_attn = (a.flags & MMF_DROPOUT_ATTN) != 0;
+    constexpr bool drop_h = DROPH;
+    constexpr bool drop_attn = DROPA;
     const uint32_t rs_h = drop_row_state(a.seed, 0, (uint32_t)row);
     const uint32_t h_ready_leader = mapa_cluster(smem_u32(&bar_h), 0);
     float* sS = vec + C::V_S;     // [2][128] per-half partial row sums (t_i in bwd, score in fwd)
@@ -205,12 +208,13 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     float* sRed = vec + C::V_RED;
     // stage the per-column vectors once (epilogue warps only: the producer / MMA threads start at once).
     // The inverted-dropout scale of h is folded into the bias: relu(u + b) * s == relu(s*u + s*b).
-    const float h_scale = drop_h ? (1.0f / 0.75f) : 1.0f;
+    constexpr float h_scale = DROPH ? (1.0f / 0.75f) : 1.0f;
     for (int i = e; i < L; i += AMIL2_EPI_THREADS) {
       vec[C::V_B1 + i] = __ldg(a.b1 + i) * h_scale;
       if (MODE == AMIL_BWD_GATE) vec[C::V_DM + i] = __ldg(a.dM + i);
     }
-    for (int i = e; i < C::KD; i += AMIL2_EPI_THREADS) vec[C::V_BAB + i] = __ldg(a.bab + i);
+    // (the sigmoid branch bias is staged pre-halved: sigmoid(z + bb) = 0.5 tanh(0.5 z + 0.5 bb) + 0.5, one FFMA feeds the MUFU)
+    for (int i = e; i < C::KD; i += AMIL2_EPI_THREADS) vec[C::V_BAB + i] = __ldg(a.bab + i) * ((GATED && i >= D) ? 0.5f : 1.0f);
     for (int i = e; i < D; i += AMIL2_EPI_THREADS) vec[C::V_WC + i] = __ldg(a.wc + i);
     named_bar_sync(4, AMIL2_EPI_THREADS);
     if (e == 0) MMF_STAMP(a, 9);
@@ -253,10 +257,10 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           const uint32_t hb = (i < 16) ? hb0 : hb1;
           const float r0 = fmaxf(fmaf(u[i], h_scale, b4.x), 0.f), r1 = fmaxf(fmaf(u[i + 1], h_scale, b4.y), 0.f);
           const float r2 = fmaxf(fmaf(u[i + 2], h_scale, b4.z), 0.f), r3 = fmaxf(fmaf(u[i + 3], h_scale, b4.w), 0.f);
-          u[i] = drop_keep(hb, (i & 15)) ? r0 : 0.f;
-          u[i + 1] = drop_keep(hb, (i & 15) + 1) ? r1 : 0.f;
-          u[i + 2] = drop_keep(hb, (i & 15) + 2) ? r2 : 0.f;
-          u[i + 3] = drop_keep(hb, (i & 15) + 3) ? r3 : 0.f;
+          u[i] = (!DROPH || drop_keep(hb, (i & 15))) ? r0 : 0.f;
+          u[i + 1] = (!DROPH || drop_keep(hb, (i & 15) + 1)) ? r1 : 0.f;
+          u[i + 2] = (!DROPH || drop_keep(hb, (i & 15) + 2)) ? r2 : 0.f;
+          u[i + 3] = (!DROPH || drop_keep(hb, (i & 15) + 3)) ? r3 : 0.f;
         }
         const uint32_t kb_base = h_base + (cb >> 1) * 16384;
 #pragma unroll
@@ -308,7 +312,7 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 
     // ---------------- EPI2: gate + score (fwd) / gate backward (bwd) -------------------
     float s_acc = 0.f;
-    const float attn_scale = drop_attn ? (1.0f / 0.75f) : 1.0f;
+    constexpr float attn_scale = DROPA ? (1.0f / 0.75f) : 1.0f;
     const uint32_t rs_a = drop_row_state(a.seed, 1, (uint32_t)row);
     const uint32_t rs_g = drop_row_state(a.seed, 2, (uint32_t)row);
 #pragma unroll 1
@@ -344,10 +348,10 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 #pragma unroll
           for (int x2 = 0; x2 < 4; ++x2) {
             const float av = tanh_fast(va[i + x2] + bav[x2]);
-            const float gv = GATED ? sigmoid_fast(vg[i + x2] + bbv[x2]) : 1.f;
+            const float gv = GATED ? fmaf(0.5f, tanh_fast(fmaf(0.5f, vg[i + x2], bbv[x2])), 0.5f) : 1.f;
             const uint32_t ab = (i < 16) ? ab0 : ab1, gb = (i < 16) ? gb0 : gb1;
-            const float ka = drop_keep(ab, (i & 15) + x2) ? attn_scale : 0.f;
-            const float kg = (!GATED || drop_keep(gb, (i & 15) + x2)) ? (GATED ? attn_scale : 1.f) : 0.f;
+            const float ka = (!DROPA || drop_keep(ab, (i & 15) + x2)) ? attn_scale : 0.f;
+            const float kg = (!GATED || !DROPA || drop_keep(gb, (i & 15) + x2)) ? (GATED ? attn_scale : 1.f) : 0.f;
             const float ad = av * ka, gd = gv * kg;
             if (MODE == AMIL_FWD) {
               s_acc = fmaf(wcv[x2], ad * gd, s_acc);

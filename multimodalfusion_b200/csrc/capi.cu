@@ -151,12 +151,12 @@ int launch_amil(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, 
 }
 
 // CTA-pair kernel (amil_tile2.cuh): grid = 2 * ceil(N / 256), cluster (2,1,1)
-template <int L, int D, bool GATED, int MODE>
-int launch_amil2(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, const AmilArgs& a,
-                 void* Hbuf, cudaStream_t st) {
+template <int L, int D, bool GATED, int MODE, bool DROPH, bool DROPA>
+int launch_amil2v(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, const AmilArgs& a,
+                  void* Hbuf, cudaStream_t st) {
   using C = Amil2Cfg<L, D, GATED>;
   static bool configured = false;
-  auto kern = amil_tile2_kernel<L, D, GATED, MODE>;
+  auto kern = amil_tile2_kernel<L, D, GATED, MODE, DROPH, DROPA>;
   if (!configured) {
     MMF_TRY(cuda_rc(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES)));
     configured = true;
@@ -169,6 +169,16 @@ int launch_amil2(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w,
   else tmH = tmX;
   const int pairs = (int)((N + 255) / 256);
   return launch_pdl(kern, dim3(2 * pairs), dim3(AMIL2_THREADS), C::SMEM_BYTES, st, tmX, tmW1, tmWab, tmH, a);
+}
+
+template <int L, int D, bool GATED, int MODE>
+int launch_amil2(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, const AmilArgs& a,
+                 void* Hbuf, cudaStream_t st) {
+  const bool dh = (a.flags & MMF_DROPOUT_H) != 0, da = (a.flags & MMF_DROPOUT_ATTN) != 0;
+  if (dh) return da ? launch_amil2v<L, D, GATED, MODE, true, true>(x, N, ldx, w, a, Hbuf, st)
+                    : launch_amil2v<L, D, GATED, MODE, true, false>(x, N, ldx, w, a, Hbuf, st);
+  return da ? launch_amil2v<L, D, GATED, MODE, false, true>(x, N, ldx, w, a, Hbuf, st)
+            : launch_amil2v<L, D, GATED, MODE, false, false>(x, N, ldx, w, a, Hbuf, st);
 }
 
 // MMF_TILE_V1=1 selects the single-CTA kernel (kept as the reference implementation of the pair kernel)
