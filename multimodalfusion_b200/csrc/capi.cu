@@ -23,6 +23,19 @@ namespace {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Opt a kernel in to > 48 KB of dynamic shared memory, once per (kernel instantiation, device): the attribute is
+// per device, a process may drive several (benign race between host threads: the call is idempotent).
+#define MMF_CONFIGURE_SMEM(kern, bytes)                                                                        \
+  do {                                                                                                         \
+    static bool done_[64] = {};                                                                                \
+    int dev_ = 0;                                                                                              \
+    MMF_TRY(cuda_rc(cudaGetDevice(&dev_)));                                                                    \
+    if (dev_ < 0 || dev_ >= 64 || !done_[dev_]) {                                                              \
+      MMF_TRY(cuda_rc(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)))); \
+      if (dev_ >= 0 && dev_ < 64) done_[dev_] = true;                                                          \
+    }                                                                                                          \
+  } while (0)
+
 // debug-only global (the one exception to "no global state"): when set, the tensor-core kernels write
 // clock64 phase stamps [gridDim.x][16]; see tools/phase_timing.py
 unsigned long long* g_timing_buffer = nullptr;
@@ -49,12 +62,8 @@ BwdWs bwd_layout(int64_t N, int L, int D, int gated) {
 
 template <int A_MN, int B_MN, int EPI>
 int launch_gemm(const TMapSet& tmA, const TMapSet& tmB, const GemmArgs& g, int splits, cudaStream_t st) {
-  static bool configured = false;
   auto kern = gemm_tc_kernel<A_MN, B_MN, EPI>;
-  if (!configured) {
-    MMF_TRY(cuda_rc(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES)));
-    configured = true;
-  }
+  MMF_CONFIGURE_SMEM(kern, GEMM_SMEM_BYTES);
   dim3 grid((g.M + GEMM_BM - 1) / GEMM_BM, (g.N + GEMM_BN - 1) / GEMM_BN, splits);
   kern<<<grid, 256, GEMM_SMEM_BYTES, st>>>(tmA, tmB, g);
   return launch_status();
@@ -63,12 +72,8 @@ int launch_gemm(const TMapSet& tmA, const TMapSet& tmB, const GemmArgs& g, int s
 template <int A_MN, int B_MN, int EPI, int BN>
 int launch_gemm2(const TMapSet& tmA, const TMapSet& tmB, const GemmArgs& g, int splits, cudaStream_t st) {
   using C = Gemm2Cfg<BN>;
-  static bool configured = false;
   auto kern = gemm2_tc_kernel<A_MN, B_MN, EPI, BN>;
-  if (!configured) {
-    MMF_TRY(cuda_rc(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES)));
-    configured = true;
-  }
+  MMF_CONFIGURE_SMEM(kern, C::SMEM_BYTES);
   dim3 grid(2 * ((g.M + 255) / 256), (g.N + BN - 1) / BN, splits);
   return launch_pdl(kern, grid, dim3(GEMM2_THREADS), C::SMEM_BYTES, st, tmA, tmB, g);
 }
@@ -80,12 +85,8 @@ int launch_gemm2(const TMapSet& tmA, const TMapSet& tmB, const GemmArgs& g, int 
 int launch_gemm2_grouped(const TMapSet& tmA, const TMapSet& tmB, GemmArgs ga, cudaStream_t st) {
   constexpr int BN = 512;
   using C = Gemm2Cfg<BN>;
-  static bool configured = false;
   auto kern = gemm2_tc_kernel<1, 1, EPI_ATOMIC, BN>;
-  if (!configured) {
-    MMF_TRY(cuda_rc(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES)));
-    configured = true;
-  }
+  MMF_CONFIGURE_SMEM(kern, C::SMEM_BYTES);
   int tiles_total = 0;
   for (int p = 0; p < ga.n_groups; ++p) {
     GemmArgs::Group& P = ga.grp[p];
@@ -133,12 +134,8 @@ template <int L, int D, bool GATED, int MODE>
 int launch_amil(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, const AmilArgs& a,
                 void* Hbuf, cudaStream_t st) {
   using C = AmilCfg<L, D, GATED>;
-  static bool configured = false;
   auto kern = amil_tile_kernel<L, D, GATED, MODE>;
-  if (!configured) {
-    MMF_TRY(cuda_rc(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES)));
-    configured = true;
-  }
+  MMF_CONFIGURE_SMEM(kern, C::SMEM_BYTES);
   CUtensorMap tmX, tmW1, tmWab, tmH;
   MMF_TRY(make_tmap_bf16(&tmX, x, (uint64_t)N, 1024, (uint64_t)ldx, 128));
   MMF_TRY(make_tmap_bf16(&tmW1, w->W1, L, 1024, 1024, 256));
@@ -155,12 +152,8 @@ template <int L, int D, bool GATED, int MODE, bool DROPH, bool DROPA>
 int launch_amil2v(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, const AmilArgs& a,
                   void* Hbuf, cudaStream_t st) {
   using C = Amil2Cfg<L, D, GATED>;
-  static bool configured = false;
   auto kern = amil_tile2_kernel<L, D, GATED, MODE, DROPH, DROPA>;
-  if (!configured) {
-    MMF_TRY(cuda_rc(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES)));
-    configured = true;
-  }
+  MMF_CONFIGURE_SMEM(kern, C::SMEM_BYTES);
   CUtensorMap tmX, tmW1, tmWab, tmH;
   MMF_TRY(make_tmap_bf16(&tmX, x, (uint64_t)N, 1024, (uint64_t)ldx, 128));
   MMF_TRY(make_tmap_bf16(&tmW1, w->W1, L, 1024, 1024, 128));
@@ -221,12 +214,8 @@ template <int L, int D, bool GATED, bool DROP>
 int launch_hidden_fused2(const HiddenFusedArgs& a, const CUtensorMap& tmAG, const CUtensorMap& tmWab,
                          const CUtensorMap& tmDU, cudaStream_t st) {
   using C = HiddenFusedCfg<L, D, GATED>;
-  static bool configured = false;
   auto kern = amil_hidden_fused_kernel<L, D, GATED, DROP>;
-  if (!configured) {
-    MMF_TRY(cuda_rc(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES)));
-    configured = true;
-  }
+  MMF_CONFIGURE_SMEM(kern, C::SMEM_BYTES);
   const int pairs = (int)((a.N + 255) / 256);
   return launch_pdl(kern, dim3(2 * pairs), dim3(HIDDEN_THREADS), C::SMEM_BYTES, st, tmAG, tmAG, tmWab, tmDU, a);
 }
@@ -240,12 +229,8 @@ int launch_hidden_fused(const HiddenFusedArgs& a, int flags, const CUtensorMap& 
 template <int L, int D, bool GATED, bool DROP>
 int launch_gate_ew2(const GateEwArgs& a, cudaStream_t st) {
   using C = GateEwCfg<L, D, GATED>;
-  static bool configured = false;
   auto kern = amil_gate_ew_kernel<L, D, GATED, DROP>;
-  if (!configured) {
-    MMF_TRY(cuda_rc(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES)));
-    configured = true;
-  }
+  MMF_CONFIGURE_SMEM(kern, C::SMEM_BYTES);
   const long long chunks = (a.N + C::ROWS - 1) / C::ROWS;
   const int blocks = (int)(chunks < 148 ? chunks : 148);   // persistent: one CTA per SM
   return launch_pdl(kern, dim3(blocks), dim3(C::THREADS), C::SMEM_BYTES, st, a);

@@ -161,6 +161,39 @@ def test_amil_kernels_vs_bf16_oracle(dev, N, L, D, gated, drop, stash):
     assert rel_err(gr2["dW1"], 2 * go["dW1"]) < TOL_GRAD_TIGHT
 
 
+@pytest.mark.parametrize("N,L,D,gated,drop", [(700, 256, 256, True, 2), (1500, 512, 384, True, 6), (300, 256, 384, False, 0)])
+def test_stashed_backward_fused_equals_two_kernel_form(dev, N, L, D, gated, drop):
+    """mmf_amil_bwd(MMF_STASHED) runs the fused gate-backward + dU GEMM kernel; the two-kernel form
+    (mmf_amil_bwd_gate_stashed: TMA-streamed elementwise pass, then mmf_amil_bwd_hidden: pair GEMM with the bit-mask
+    epilogue) stays exported for A/B timing — same gradients up to fp32 summation order and one bf16 rounding."""
+    import ctypes as C
+    from multimodalfusion_b200 import ops
+    from multimodalfusion_b200._lib import AmilGrads, check, lib
+    W = _rand_amil(L, D, gated, N)
+    prep = ops.prepare_amil_weights(*[None if t is None else t.to(dev) for t in W])
+    flags = ops.amil_flags(gated) | drop
+    x = cases.features(N, 77).to(dev).to(torch.bfloat16)
+    dM = (torch.randn(L, generator=torch.Generator().manual_seed(N)) * 0.1).to(dev)
+    A_raw, parts, ws = ops.amil_partials_train(x, prep, flags, 9)
+    M, ml = ops.amil_combine(parts, L, True)
+    fused = ops.amil_backward(x, prep, flags, 9, A_raw, ml, M, dM, stash=ws)
+    A2, parts2, ws2 = ops.amil_partials_train(x, prep, flags, 9)
+    KD = (2 if gated else 1) * D
+    g = dict(dW1=torch.zeros(L, 1024, device=dev), db1=torch.zeros(L, device=dev), dWab=torch.zeros(KD, L, device=dev),
+             dbab=torch.zeros(KD, device=dev), dwc=torch.zeros(D, device=dev), dbc=torch.zeros(1, device=dev))
+    gs = AmilGrads(*[g[k].data_ptr() for k in ("dW1", "db1", "dWab", "dbab", "dwc", "dbc")])
+    wst = prep.struct()
+    st = torch.cuda.current_stream().cuda_stream
+    check(lib().mmf_amil_bwd_gate_stashed(N, C.byref(wst), L, D, flags, 9, A2.data_ptr(), ml.data_ptr(), M.data_ptr(),
+                                          dM.data_ptr(), None, C.byref(gs), ws2.data_ptr(), ws2.numel(), st))
+    check(lib().mmf_amil_bwd_hidden(x.data_ptr(), N, 1024, C.byref(wst), L, D, flags, A2.data_ptr(), ml.data_ptr(),
+                                    dM.data_ptr(), C.byref(gs), ws2.data_ptr(), ws2.numel(), st))
+    check(lib().mmf_amil_bwd_wgrad(x.data_ptr(), N, 1024, C.byref(wst), L, D, flags, C.byref(gs), None, ws2.data_ptr(),
+                                   ws2.numel(), st))
+    for k in ("dW1", "db1", "dWab", "dbab", "dwc"):
+        assert rel_err(g[k], fused[k]) < 2e-3, k
+
+
 @pytest.mark.parametrize("stash", [False, True], ids=["recompute", "stash"])
 @pytest.mark.parametrize("N", [10000, 16384])
 def test_amil_full_size_vs_oracle(dev, N, stash):
