@@ -199,7 +199,7 @@ def run_ours(args):
     if world > 1 and os.environ.get("MMF_BENCH_ALLREDUCE", "p2p") == "p2p":
         try:   # the library's own peer-memory all-reduce kernel, captured in the step graph
             from multimodalfusion_b200.parallel import PeerAllReduce
-            peer_ar = PeerAllReduce(sum(sizes), n_buffers=2)
+            peer_ar = PeerAllReduce(sum(sizes), n_buffers=2, use_multicast=os.environ.get("MMF_P2P_NO_MULTICAST") != "1")
         except Exception as e:   # no P2P / symmetric memory: NCCL on a communication stream
             if rank == 0:
                 print(f"# peer all-reduce unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
