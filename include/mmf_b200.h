@@ -256,6 +256,27 @@ int mmf_nll_surv_fwd_bwd(const float* hazards, const float* S, const int64_t* Y,
                          int B, int K, float alpha, float eps, float* loss, float* d_hazards,
                          float* d_S, void* stream);
 
+/* ce_loss (utils/loss_utils.py:41-56): cross-entropy survival loss, scalar + d_hazards, d_S [B,K]. */
+int mmf_ce_surv_fwd_bwd(const float* hazards, const float* S, const int64_t* Y, const float* c, int B, int K,
+                        float alpha, float eps, float* loss, float* d_hazards, float* d_S, void* stream);
+
+/* nn.BatchNorm1d over [B,F] (the fcnn / Highway fusion heads: models/coxranking_models_pretrained.py:80-94,
+ * models/nll_models_pretrained.py:82-99, models/model_modules.py:13-14,18,26). train != 0: batch statistics, running
+ * estimates updated in place (momentum, unbiased variance), B >= 2; train == 0: running statistics. save_mean /
+ * save_invstd [F] receive the statistics used (inputs of the backward). gamma / beta may be NULL (affine off). */
+int mmf_batchnorm1d_fwd(const float* x, int B, int F, const float* gamma, const float* beta, float* running_mean,
+                        float* running_var, int train, float momentum, float eps, float* y, float* save_mean,
+                        float* save_invstd, void* stream);
+/* dx (nullable) written; dgamma / dbeta (nullable) accumulated. */
+int mmf_batchnorm1d_bwd(const float* x, const float* dy, int B, int F, const float* gamma, const float* save_mean,
+                        const float* save_invstd, int train, float* dx, float* dgamma, float* dbeta, void* stream);
+
+/* Highway layer mix y = gate * nonlinear + (1 - gate) * linear and its backward (models/model_modules.py:21-25). */
+int mmf_highway_mix_fwd(const float* gate, const float* nonlinear, const float* linear, int64_t count, float* y,
+                        void* stream);
+int mmf_highway_mix_bwd(const float* gate, const float* nonlinear, const float* linear, const float* dy, int64_t count,
+                        float* dgate, float* dnonlinear, float* dlinear, void* stream);
+
 /* CoxSurvLoss (utils/loss_utils.py:124-139): loss = -mean_i (theta_i - log Σ_{t_j>=t_i} e^{theta_j})(1-c_i).
  * O(B log B) sort + tie-aware suffix sums instead of the reference's O(B^2) host loop.
  * workspace: mmf_cox_workspace_bytes(B). dtheta may be NULL. */

@@ -125,6 +125,11 @@ SIGNATURES = {
     "mmf_amil_head_nll_step": (_i, [_vp, _i64, _i, _vp, _vp, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                     _vp, _vp, _vp]),
     "mmf_nll_surv_fwd_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _f, _vp, _vp, _vp, _vp]),
+    "mmf_ce_surv_fwd_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _f, _vp, _vp, _vp, _vp]),
+    "mmf_batchnorm1d_fwd": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _i, _f, _f, _vp, _vp, _vp, _vp]),
+    "mmf_batchnorm1d_bwd": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "mmf_highway_mix_fwd": (_i, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    "mmf_highway_mix_bwd": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "mmf_cox_workspace_bytes": (_sz, [_i]),
     "mmf_cox_fwd_bwd": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "mmf_adam_step_multi": (_i, [_PP, _PP, _PP, _PP, C.POINTER(C.c_int64), _i, _i, _f, _f, _f, _f, _f, _f, _f, _i, _vp, _vp]),

@@ -204,3 +204,53 @@ class RankingLoss(torch.autograd.Function):
     def backward(ctx, dl):
         (dr,) = ctx.saved_tensors
         return (dr * dl).view(ctx.shape), None, None, None, None
+
+
+class BatchNorm1dFn(torch.autograd.Function):
+    """nn.BatchNorm1d on [B,F] (fcnn / Highway fusion heads). running_mean / running_var are updated in place in
+    training mode, exactly as the module does."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, train: bool, momentum: float, eps: float):
+        y, mean, invstd = ops.batchnorm1d_fwd(x, gamma, beta, running_mean, running_var, train, momentum, eps)
+        ctx.save_for_backward(x, gamma, mean, invstd)
+        ctx.train = train
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, mean, invstd = ctx.saved_tensors
+        dx, dgamma, dbeta = ops.batchnorm1d_bwd(x, dy, gamma, mean, invstd, ctx.train,
+                                                need_dx=ctx.needs_input_grad[0],
+                                                need_affine=ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
+        return dx, dgamma, dbeta, None, None, None, None, None
+
+
+class HighwayMix(torch.autograd.Function):
+    """y = gate * nonlinear + (1 - gate) * linear (models/model_modules.py:21-25)."""
+
+    @staticmethod
+    def forward(ctx, g, n, l):
+        y = ops.highway_mix_fwd(g, n, l)
+        ctx.save_for_backward(g, n, l)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        g, n, l = ctx.saved_tensors
+        return ops.highway_mix_bwd(g.contiguous(), n.contiguous(), l.contiguous(), dy)
+
+
+class CeSurv(torch.autograd.Function):
+    """utils/loss_utils.py:41-56."""
+
+    @staticmethod
+    def forward(ctx, hazards, S, Y, c, alpha: float, eps: float):
+        loss, dh, dS = ops.ce_surv(hazards, S, Y, c, alpha, eps)
+        ctx.save_for_backward(dh, dS)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dl):
+        dh, dS = ctx.saved_tensors
+        return dh * dl, dS * dl, None, None, None, None

@@ -15,6 +15,7 @@
 #include "small_kernels.cuh"
 #include "p2p_allreduce.cuh"
 #include "train_glue.cuh"
+#include "head_kernels.cuh"
 #include <math.h>
 
 using namespace mmf;
@@ -775,6 +776,53 @@ int mmf_nll_surv_fwd_bwd(const float* hazards, const float* S, const int64_t* Y,
   if (!hazards || !S || !Y || !c || !loss || B <= 0 || K <= 0) return MMF_E_INVALID;
   nll_surv_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(hazards, S, reinterpret_cast<const long long*>(Y), c, B, K,
                                                        alpha, eps, loss, d_hazards, d_S);
+  return launch_status();
+}
+
+int mmf_ce_surv_fwd_bwd(const float* hazards, const float* S, const int64_t* Y, const float* c, int B, int K,
+                        float alpha, float eps, float* loss, float* d_hazards, float* d_S, void* stream) {
+  if (!hazards || !S || !Y || !c || !loss || B <= 0 || K <= 0) return MMF_E_INVALID;
+  ce_surv_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(hazards, S, reinterpret_cast<const long long*>(Y), c, B, K, alpha,
+                                                      eps, loss, d_hazards, d_S);
+  return launch_status();
+}
+
+int mmf_batchnorm1d_fwd(const float* x, int B, int F, const float* gamma, const float* beta, float* running_mean,
+                        float* running_var, int train, float momentum, float eps, float* y, float* save_mean,
+                        float* save_invstd, void* stream) {
+  if (!x || !y || B <= 0 || F <= 0 || !save_mean || !save_invstd) return MMF_E_INVALID;
+  if (train && B < 2) return MMF_E_INVALID;   // nn.BatchNorm1d: "Expected more than 1 value per channel when training"
+  if (!train && (!running_mean || !running_var)) return MMF_E_INVALID;
+  batchnorm1d_fwd_kernel<<<(F + 31) / 32, dim3(32, 8), 0, (cudaStream_t)stream>>>(x, B, F, gamma, beta, running_mean,
+                                                                                   running_var, train, momentum, eps, y,
+                                                                                   save_mean, save_invstd);
+  return launch_status();
+}
+
+int mmf_batchnorm1d_bwd(const float* x, const float* dy, int B, int F, const float* gamma, const float* save_mean,
+                        const float* save_invstd, int train, float* dx, float* dgamma, float* dbeta, void* stream) {
+  if (!x || !dy || !save_mean || !save_invstd || B <= 0 || F <= 0) return MMF_E_INVALID;
+  batchnorm1d_bwd_kernel<<<(F + 31) / 32, dim3(32, 8), 0, (cudaStream_t)stream>>>(x, dy, B, F, gamma, save_mean,
+                                                                                   save_invstd, train, dx, dgamma, dbeta);
+  return launch_status();
+}
+
+int mmf_highway_mix_fwd(const float* gate, const float* nonlinear, const float* linear, int64_t count, float* y,
+                        void* stream) {
+  if (!gate || !nonlinear || !linear || !y || count <= 0) return MMF_E_INVALID;
+  long long blocks = (count + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  highway_mix_fwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(gate, nonlinear, linear, count, y);
+  return launch_status();
+}
+
+int mmf_highway_mix_bwd(const float* gate, const float* nonlinear, const float* linear, const float* dy, int64_t count,
+                        float* dgate, float* dnonlinear, float* dlinear, void* stream) {
+  if (!gate || !nonlinear || !linear || !dy || !dgate || !dnonlinear || !dlinear || count <= 0) return MMF_E_INVALID;
+  long long blocks = (count + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  highway_mix_bwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(gate, nonlinear, linear, dy, count, dgate,
+                                                                         dnonlinear, dlinear);
   return launch_status();
 }
 

@@ -1,13 +1,14 @@
-"""Fusion heads over pre-extracted 256-d embeddings with a scalar risk output — drop-in for the
-`kronecker` route of models/coxranking_models_pretrained.py (:62-183, kronecker :95-97,171-180).
-The fcnn / highway / residual heads (BatchNorm-based) are "next" rows of SURVEY.md §8(f)."""
+"""Fusion heads over pre-extracted 256-d embeddings with a scalar risk output — drop-in for
+models/coxranking_models_pretrained.py (:62-183): `kronecker` (:95-97,171-180), `early-fcnn` / `late-fcnn`
+(:80-86,137-140,166), `early-highway` / `late-highway` (:87-94,141-144,167-168)."""
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from .._lib import ACT_NONE
 from ..autograd import Dense
 from ..utils.utils import initialize_weights
-from .model_modules import XlinearFusion
+from .model_modules import Highway, XlinearFusion, fcnn_forward
 
 
 def _pick(mode, h_radio, h_path, h_omic):
@@ -24,6 +25,21 @@ def _pick(mode, h_radio, h_path, h_omic):
     raise NotImplementedError(f"mode {mode!r} needs at least two modalities")
 
 
+def _pick_late(mode, outs):
+    """Concatenation order of the late branches (:146-153): (radio, path), (radio, omic), (omic, path),
+    (radio, path, omic)."""
+    r, p, o = 'radio' in mode, 'path' in mode, 'omic' in mode
+    if r and p and o:
+        return [outs['radio'], outs['path'], outs['omic']]
+    if r and p:
+        return [outs['radio'], outs['path']]
+    if r and o:
+        return [outs['radio'], outs['omic']]
+    if o and p:
+        return [outs['omic'], outs['path']]
+    raise NotImplementedError(f"mode {mode!r} needs at least two modalities")
+
+
 class multimodal_pretrained(nn.Module):
     def __init__(self, dropout=True, n_classes=4, mode='radio_path_omic', train_type=None,
                  bag_loss=None, n_layers=1):
@@ -31,12 +47,27 @@ class multimodal_pretrained(nn.Module):
         self.n_classes, self.mode, self.train_type = n_classes, mode, train_type
         self.bag_loss, self.n_layers = bag_loss, n_layers
         num_modalities = sum(k in mode for k in ('radio', 'path', 'omic'))
-        if train_type == 'kronecker':
+        fcnn = lambda d_in: nn.Sequential(nn.Linear(d_in, 128), nn.BatchNorm1d(128), nn.ReLU(), nn.Dropout(0.7),
+                                          nn.Linear(128, 1))
+        if train_type == 'late-fcnn':
+            self.layer_WSI, self.layer_MRI, self.layer_omic = fcnn(256), fcnn(256), fcnn(256)
+            self.classifier = nn.Sequential(nn.Linear(num_modalities, 1))
+        elif train_type == 'early-fcnn':
+            self.classifier = fcnn(num_modalities * 256)
+        elif train_type == 'early-highway':
+            self.highway = Highway(num_modalities * 256, n_layers, F.relu)
+            self.classifier = nn.Linear(num_modalities * 256, 1)
+        elif train_type == 'late-highway':
+            self.highway_radio = Highway(256, n_layers, F.relu)
+            self.highway_path = Highway(256, n_layers, F.relu)
+            self.highway_omic = Highway(256, n_layers, F.relu)
+            self.classifier = nn.Linear(num_modalities * 256, 1)
+        elif train_type == 'kronecker':
             self.xfusion = XlinearFusion(num_modalities=num_modalities, dropout_rate=0.7)
             self.classifier = nn.Linear(256, 1)
         else:
-            raise NotImplementedError(
-                f"train_type={train_type!r}: only 'kronecker' is on the accelerated path this round")
+            # the reference constructs nothing for other values and fails later in forward (AttributeError)
+            raise NotImplementedError(f"train_type={train_type!r}")
         initialize_weights(self)
 
     def relocate(self):
@@ -44,6 +75,23 @@ class multimodal_pretrained(nn.Module):
         self.to(device)
 
     def forward(self, h_radio, h_path, h_omic):
-        MM = self.xfusion(v_list=_pick(self.mode, h_radio, h_path, h_omic))
-        risk = Dense.apply(MM, self.classifier.weight, self.classifier.bias, ACT_NONE)
-        return risk, None, None
+        tt = self.train_type
+        if tt == 'kronecker':
+            MM = self.xfusion(v_list=_pick(self.mode, h_radio, h_path, h_omic))
+            return Dense.apply(MM, self.classifier.weight, self.classifier.bias, ACT_NONE), None, None
+        if tt.startswith('late'):
+            # the reference evaluates all three branches whatever the mode (:137-144); we run the ones the mode uses
+            branch = {'radio': (self.layer_MRI, h_radio), 'path': (self.layer_WSI, h_path), 'omic': (self.layer_omic, h_omic)} \
+                if tt == 'late-fcnn' else \
+                {'radio': (self.highway_radio, h_radio), 'path': (self.highway_path, h_path), 'omic': (self.highway_omic, h_omic)}
+            outs = {k: (fcnn_forward(m, h.float()) if tt == 'late-fcnn' else m(h)) for k, (m, h) in branch.items()
+                    if k in self.mode}
+            MM = torch.cat(_pick_late(self.mode, outs), dim=1)                      # == cat(axis=2) of the unsqueezed layers
+            lin = self.classifier[0] if tt == 'late-fcnn' else self.classifier
+            risk = Dense.apply(MM, lin.weight, lin.bias, ACT_NONE)
+            return risk.unsqueeze(0).squeeze(), None, None                          # reference: [1,B,1].squeeze()
+        MM = torch.cat([h.float() for h in _pick(self.mode, h_radio, h_path, h_omic)], dim=1)
+        if tt == 'early-fcnn':
+            return fcnn_forward(self.classifier, MM), None, None
+        MM = self.highway(MM)
+        return Dense.apply(MM, self.classifier.weight, self.classifier.bias, ACT_NONE), None, None

@@ -13,13 +13,63 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import ops
-from ..autograd import Dense, KronEncoder
+from ..autograd import BatchNorm1dFn, Dense, HighwayMix, KronEncoder
 from .._lib import ACT_NONE, ACT_RELU, ACT_SELU, ACT_SIGMOID, ACT_TANH
 
 
 def _seed_from_torch() -> int:
     """Per-call dropout seed drawn from torch's CPU generator (reproducible under manual_seed)."""
     return int(torch.randint(0, 2 ** 62, (1,)).item())
+
+
+def batchnorm1d_forward(bn: nn.BatchNorm1d, x: torch.Tensor) -> torch.Tensor:
+    """nn.BatchNorm1d semantics on the library's kernel (batch statistics + running-stat update in training mode,
+    running statistics in eval mode); the module only holds the parameters / buffers."""
+    train = bn.training or not bn.track_running_stats
+    if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    momentum = 0.1 if bn.momentum is None else bn.momentum
+    return BatchNorm1dFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, train, momentum, bn.eps)
+
+
+def fcnn_forward(seq: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
+    """Linear -> BatchNorm1d -> ReLU -> Dropout(.7) [-> Linear] containers of the early/late-fcnn heads
+    (models/coxranking_models_pretrained.py:80-86, models/nll_models_pretrained.py:82-91)."""
+    h = Dense.apply(x, seq[0].weight, seq[0].bias, ACT_NONE)
+    h = torch.relu(batchnorm1d_forward(seq[1], h))
+    h = seq[3](h)                                   # Dropout(0.7): elementwise mask only
+    if len(seq) > 4:
+        h = Dense.apply(h, seq[4].weight, seq[4].bias, ACT_NONE)
+    return h
+
+
+class Highway(nn.Module):
+    """BatchNorm -> Dropout(.7) -> num_layers x [gate * f(nonlinear) + (1 - gate) * linear] -> BatchNorm
+    (models/model_modules.py:5-27; same submodule names and creation order). Only f = relu is used by the
+    reference heads and is what the fused Dense kernel provides."""
+
+    def __init__(self, size, num_layers, f):
+        super().__init__()
+        self.num_layers = num_layers
+        self.nonlinear = nn.ModuleList([nn.Linear(size, size) for _ in range(num_layers)])
+        self.linear = nn.ModuleList([nn.Linear(size, size) for _ in range(num_layers)])
+        self.gate = nn.ModuleList([nn.Linear(size, size) for _ in range(num_layers)])
+        if f is not F.relu and f is not torch.relu:
+            raise NotImplementedError("Highway: only f = relu is on the accelerated path (all the reference's heads use it)")
+        self.f = f
+        self.bn1 = nn.BatchNorm1d(size)
+        self.bn2 = nn.BatchNorm1d(size)
+        self.dropout1 = nn.Dropout(0.7)
+
+    def forward(self, x):
+        x = batchnorm1d_forward(self.bn1, x.float())
+        x = self.dropout1(x)
+        for layer in range(self.num_layers):
+            gate = Dense.apply(x, self.gate[layer].weight, self.gate[layer].bias, ACT_SIGMOID)
+            nonlinear = Dense.apply(x, self.nonlinear[layer].weight, self.nonlinear[layer].bias, ACT_RELU)
+            linear = Dense.apply(x, self.linear[layer].weight, self.linear[layer].bias, ACT_NONE)
+            x = HighwayMix.apply(gate, nonlinear, linear)
+        return batchnorm1d_forward(self.bn2, x)
 
 
 def SNN_Block(dim1, dim2, dropout=0.25):

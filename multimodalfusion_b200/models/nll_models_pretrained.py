@@ -1,12 +1,14 @@
 """Fusion heads over pre-extracted 256-d embeddings with a discrete-hazard output — drop-in for
-the `kronecker` route of models/nll_models_pretrained.py (:101-103,179-197)."""
+models/nll_models_pretrained.py (:64-197): `kronecker` (:101-103,179-188), `early-fcnn` / `late-fcnn` (:82-91),
+`early-highway` / `late-highway` (:92-99)."""
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from ..autograd import HazardHead
 from ..utils.utils import initialize_weights
-from .coxranking_models_pretrained import _pick
-from .model_modules import XlinearFusion
+from .coxranking_models_pretrained import _pick, _pick_late
+from .model_modules import Highway, XlinearFusion, fcnn_forward
 
 
 class multimodal_pretrained(nn.Module):
@@ -16,12 +18,26 @@ class multimodal_pretrained(nn.Module):
         self.n_classes, self.mode, self.train_type = n_classes, mode, train_type
         self.bag_loss, self.n_layers = bag_loss, n_layers
         num_modalities = sum(k in mode for k in ('radio', 'path', 'omic'))
-        if train_type == 'kronecker':
+        fcnn = lambda d_in, d_out=None: nn.Sequential(*([nn.Linear(d_in, 128), nn.BatchNorm1d(128), nn.ReLU(), nn.Dropout(0.7)]
+                                                        + ([nn.Linear(128, d_out)] if d_out else [])))
+        if train_type == 'early-fcnn':
+            self.classifier = fcnn(num_modalities * 256, n_classes)
+        elif train_type == 'late-fcnn':
+            self.layer_WSI, self.layer_MRI, self.layer_omic = fcnn(256), fcnn(256), fcnn(256)
+            self.classifier = nn.Sequential(nn.Linear(num_modalities * 128, n_classes))
+        elif train_type == 'early-highway':
+            self.highway = Highway(num_modalities * 256, n_layers, F.relu)
+            self.classifier = nn.Linear(num_modalities * 256, n_classes)
+        elif train_type == 'late-highway':
+            self.highway_radio = Highway(256, n_layers, F.relu)
+            self.highway_path = Highway(256, n_layers, F.relu)
+            self.highway_omic = Highway(256, n_layers, F.relu)
+            self.classifier = nn.Linear(num_modalities * 256, n_classes)
+        elif train_type == 'kronecker':
             self.xfusion = XlinearFusion(num_modalities=num_modalities, dropout_rate=0.7)
             self.classifier = nn.Linear(256, n_classes)
         else:
-            raise NotImplementedError(
-                f"train_type={train_type!r}: only 'kronecker' is on the accelerated path this round")
+            raise NotImplementedError(f"train_type={train_type!r}")
         initialize_weights(self)
 
     def relocate(self):
@@ -29,7 +45,24 @@ class multimodal_pretrained(nn.Module):
         self.to(device)
 
     def forward(self, h_radio, h_path, h_omic):
-        MM = self.xfusion(v_list=_pick(self.mode, h_radio, h_path, h_omic))
-        hazards, S, _ = HazardHead.apply(MM, self.classifier.weight, self.classifier.bias)
+        tt = self.train_type
+        if tt == 'kronecker':
+            MM, lin = self.xfusion(v_list=_pick(self.mode, h_radio, h_path, h_omic)), self.classifier
+        elif tt.startswith('late'):
+            branch = {'radio': (self.layer_MRI, h_radio), 'path': (self.layer_WSI, h_path), 'omic': (self.layer_omic, h_omic)} \
+                if tt == 'late-fcnn' else \
+                {'radio': (self.highway_radio, h_radio), 'path': (self.highway_path, h_path), 'omic': (self.highway_omic, h_omic)}
+            outs = {k: (fcnn_forward(m, h.float()) if tt == 'late-fcnn' else m(h)) for k, (m, h) in branch.items()
+                    if k in self.mode}
+            MM = torch.cat(_pick_late(self.mode, outs), dim=1)
+            lin = self.classifier[0] if tt == 'late-fcnn' else self.classifier
+        else:
+            MM = torch.cat([h.float() for h in _pick(self.mode, h_radio, h_path, h_omic)], dim=1)
+            if tt == 'early-fcnn':
+                MM = fcnn_forward(nn.Sequential(*list(self.classifier)[:4]), MM)    # up to the Dropout; last Linear = the head
+                lin = self.classifier[4]
+            else:
+                MM, lin = self.highway(MM), self.classifier
+        hazards, S, _ = HazardHead.apply(MM, lin.weight, lin.bias)
         risk = -torch.sum(S, dim=1)
         return risk, hazards, S

@@ -451,3 +451,61 @@ def ranking(risks, times, c, phi: str = "sigmoid", reduction: str = "mean"):
                                     {"mean": 0, "sum": 1}[reduction], _p(loss), _p(dr), _p(npairs),
                                     ws.data_ptr() + off, nbytes, _stream()), "mmf_ranking_fwd_bwd")
     return loss, dr, npairs
+
+
+# ------------------------------------------------------------------------------------------------
+# fcnn / Highway fusion heads: BatchNorm1d, Highway mix, ce_loss
+# ------------------------------------------------------------------------------------------------
+def batchnorm1d_fwd(x, gamma, beta, running_mean, running_var, train: bool, momentum: float, eps: float):
+    """Returns (y, save_mean, save_invstd); running stats are updated in place when train."""
+    _require_cuda(x)
+    x = _f32c(x)
+    B, F = x.shape
+    y = torch.empty_like(x)
+    mean = torch.empty(F, dtype=torch.float32, device=x.device)
+    invstd = torch.empty(F, dtype=torch.float32, device=x.device)
+    check(lib().mmf_batchnorm1d_fwd(_p(x), B, F, _p(gamma), _p(beta), _p(running_mean), _p(running_var), int(train),
+                                    float(momentum), float(eps), _p(y), _p(mean), _p(invstd), _stream()),
+          "mmf_batchnorm1d_fwd")
+    return y, mean, invstd
+
+
+def batchnorm1d_bwd(x, dy, gamma, mean, invstd, train: bool, need_dx=True, need_affine=True):
+    x, dy = _f32c(x), _f32c(dy)
+    B, F = x.shape
+    dx = torch.empty_like(x) if need_dx else None
+    dgamma = torch.zeros(F, dtype=torch.float32, device=x.device) if need_affine else None
+    dbeta = torch.zeros(F, dtype=torch.float32, device=x.device) if need_affine else None
+    check(lib().mmf_batchnorm1d_bwd(_p(x), _p(dy), B, F, _p(gamma), _p(mean), _p(invstd), int(train), _p(dx), _p(dgamma),
+                                    _p(dbeta), _stream()), "mmf_batchnorm1d_bwd")
+    return dx, dgamma, dbeta
+
+
+def highway_mix_fwd(g, n, l):
+    _require_cuda(g)
+    g, n, l = _f32c(g), _f32c(n), _f32c(l)
+    y = torch.empty_like(g)
+    check(lib().mmf_highway_mix_fwd(_p(g), _p(n), _p(l), g.numel(), _p(y), _stream()), "mmf_highway_mix_fwd")
+    return y
+
+
+def highway_mix_bwd(g, n, l, dy):
+    dy = _f32c(dy)
+    dg, dn, dl = torch.empty_like(g), torch.empty_like(g), torch.empty_like(g)
+    check(lib().mmf_highway_mix_bwd(_p(g), _p(n), _p(l), _p(dy), g.numel(), _p(dg), _p(dn), _p(dl), _stream()),
+          "mmf_highway_mix_bwd")
+    return dg, dn, dl
+
+
+def ce_surv(hazards, S, Y, c, alpha: float, eps: float = 1e-7):
+    """utils/loss_utils.py:41-56. Returns (loss, d_hazards, d_S)."""
+    _require_cuda(hazards, S)
+    hazards, S = _f32c(hazards), _f32c(S)
+    B, K = hazards.shape
+    Y = Y.detach().reshape(-1).to(device=hazards.device, dtype=torch.int64).contiguous()
+    c = c.detach().reshape(-1).to(device=hazards.device, dtype=torch.float32).contiguous()
+    loss = torch.empty((), dtype=torch.float32, device=hazards.device)
+    dh, dS = torch.empty_like(hazards), torch.empty_like(S)
+    check(lib().mmf_ce_surv_fwd_bwd(_p(hazards), _p(S), _p(Y), _p(c), B, K, float(alpha), float(eps), _p(loss), _p(dh),
+                                    _p(dS), _stream()), "mmf_ce_surv_fwd_bwd")
+    return loss, dh, dS

@@ -3,7 +3,7 @@ evaluated (loss and gradient) by one libmmf_b200 kernel instead of ~12 ATen laun
 host-side O(B^2) Python loop (Cox, ranking)."""
 import torch
 
-from ..autograd import CoxLoss, NllSurv, RankingLoss
+from ..autograd import CeSurv, CoxLoss, NllSurv, RankingLoss
 
 
 def nll_loss(hazards, S, Y, c, alpha=0.4, eps=1e-7):
@@ -11,6 +11,23 @@ def nll_loss(hazards, S, Y, c, alpha=0.4, eps=1e-7):
     if S is None:
         S = torch.cumprod(1 - hazards, dim=1)
     return NllSurv.apply(hazards, S, Y, c, float(alpha), float(eps))
+
+
+def ce_loss(hazards, S, Y, c, alpha=0.4, eps=1e-7):
+    """utils/loss_utils.py:41-56."""
+    if S is None:
+        S = torch.cumprod(1 - hazards, dim=1)
+    return CeSurv.apply(hazards, S, Y, c, float(alpha), float(eps))
+
+
+class CrossEntropySurvLoss(object):
+    """utils/loss_utils.py:104-112."""
+
+    def __init__(self, alpha=0.15):
+        self.alpha = alpha
+
+    def __call__(self, hazards, S, Y, c, alpha=None):
+        return ce_loss(hazards, S, Y, c, alpha=self.alpha if alpha is None else alpha)
 
 
 def ranking_loss(risks, times, c, phi, reduction):

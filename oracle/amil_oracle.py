@@ -246,6 +246,86 @@ def xfusion_forward(v_list, reduce_params, enc1, enc2, skip=True):
     return torch.relu(out @ enc2[0].t() + enc2[1])
 
 
+# ------------------------------------------------------------------------------------------------
+# fcnn / Highway fusion heads, ce_loss — eval-mode restatements
+# ------------------------------------------------------------------------------------------------
+def batchnorm1d_eval(x, weight, bias, running_mean, running_var, eps=1e-5):
+    """nn.BatchNorm1d in eval mode (models/model_modules.py:13-14, fcnn heads)."""
+    return (x - running_mean) / torch.sqrt(running_var + eps) * weight + bias
+
+
+def batchnorm1d_train(x, weight, bias, eps=1e-5):
+    """nn.BatchNorm1d in training mode: batch statistics, biased variance. Returns (y, mean, unbiased var)."""
+    mean = x.mean(0)
+    var = x.var(0, unbiased=False)
+    return (x - mean) / torch.sqrt(var + eps) * weight + bias, mean, x.var(0, unbiased=True)
+
+
+def _bn(sd, prefix, x):
+    return batchnorm1d_eval(x, sd[prefix + ".weight"], sd[prefix + ".bias"], sd[prefix + ".running_mean"],
+                            sd[prefix + ".running_var"])
+
+
+def fcnn_eval(sd, prefix, x, last=True):
+    """Linear -> BatchNorm1d -> ReLU -> Dropout (identity) [-> Linear] (models/coxranking_models_pretrained.py:80-86)."""
+    h = x @ sd[prefix + ".0.weight"].t() + sd[prefix + ".0.bias"]
+    h = torch.relu(_bn(sd, prefix + ".1", h))
+    if last and (prefix + ".4.weight") in sd:
+        h = h @ sd[prefix + ".4.weight"].t() + sd[prefix + ".4.bias"]
+    return h
+
+
+def highway_eval(sd, prefix, x, num_layers):
+    """Highway.forward in eval mode with f = relu (models/model_modules.py:17-27)."""
+    x = _bn(sd, prefix + ".bn1", x)
+    for i in range(num_layers):
+        lin = lambda nm: x @ sd[f"{prefix}.{nm}.{i}.weight"].t() + sd[f"{prefix}.{nm}.{i}.bias"]
+        gate = torch.sigmoid(lin("gate"))
+        x = gate * torch.relu(lin("nonlinear")) + (1 - gate) * lin("linear")
+    return _bn(sd, prefix + ".bn2", x)
+
+
+def fusion_head2_eval(sd, kind, train_type, mode, n_layers, h_radio, h_path, h_omic):
+    """multimodal_pretrained.forward for the fcnn / highway train types in eval mode
+    (models/coxranking_models_pretrained.py:134-169, models/nll_models_pretrained.py:140-176).
+    Returns the risk (cox) or the hazard logits (nll)."""
+    r, p, o = "radio" in mode, "path" in mode, "omic" in mode
+    if train_type.startswith("late"):
+        if train_type == "late-fcnn":
+            outs = {"radio": fcnn_eval(sd, "layer_MRI", h_radio), "path": fcnn_eval(sd, "layer_WSI", h_path),
+                    "omic": fcnn_eval(sd, "layer_omic", h_omic)}
+            cw, cb = sd["classifier.0.weight"], sd["classifier.0.bias"]
+        else:
+            outs = {"radio": highway_eval(sd, "highway_radio", h_radio, n_layers),
+                    "path": highway_eval(sd, "highway_path", h_path, n_layers),
+                    "omic": highway_eval(sd, "highway_omic", h_omic, n_layers)}
+            cw, cb = sd["classifier.weight"], sd["classifier.bias"]
+        order = (["radio", "path", "omic"] if r and p and o else ["radio", "path"] if r and p
+                 else ["radio", "omic"] if r and o else ["omic", "path"])
+        MM = torch.cat([outs[k] for k in order], dim=1)
+        out = MM @ cw.t() + cb
+        return out.squeeze() if kind == "cox" else out
+    order = ([h_radio, h_path, h_omic] if r and p and o else [h_radio, h_path] if r and p
+             else [h_radio, h_omic] if r and o else [h_omic, h_path])
+    MM = torch.cat(order, dim=1)
+    if train_type == "early-fcnn":
+        return fcnn_eval(sd, "classifier", MM)
+    MM = highway_eval(sd, "highway", MM, n_layers)
+    return MM @ sd["classifier.weight"].t() + sd["classifier.bias"]
+
+
+def ce_surv_loss(hazards, S, Y, c, alpha=0.4, eps=1e-7):
+    """utils/loss_utils.py:41-56."""
+    B = len(Y)
+    Y = Y.view(B, 1)
+    c = c.view(B, 1).float()
+    S_padded = torch.cat([torch.ones_like(c), S], 1)
+    reg = -(1 - c) * (torch.log(torch.gather(S_padded, 1, Y) + eps) + torch.log(torch.gather(hazards, 1, Y).clamp(min=eps)))
+    sy = torch.gather(S, 1, Y).clamp(min=eps)
+    ce = -c * torch.log(sy) - (1 - c) * torch.log(1 - sy)
+    return ((1 - alpha) * ce + alpha * reg).mean()
+
+
 def concordance_index(risk, times, event, tied_tol=1e-8):
     """Harrell's C as sksurv.concordance_index_censored computes it (utils/core_utils.py:258):
     comparable pairs = (i event, t_i < t_j); ties in risk within tied_tol count 1/2."""

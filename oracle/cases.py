@@ -40,6 +40,18 @@ HEAD_CASES = {
     "kron3_nll_b8": dict(seed=44, kind="nll", loss="nll", mode="radio_path_omic", B=8),
     "kron2_nll_b70": dict(seed=45, kind="nll", loss="nll", mode="path_omic", B=70),
 }
+# fcnn / Highway fusion heads: eval mode, BatchNorm running statistics and affine parameters
+# perturbed (perturb_bn) so that the normalisation is not the identity
+HEAD2_CASES = {
+    "cox_late_fcnn_b12": dict(seed=71, kind="cox", loss="cox", mode="radio_path_omic", train_type="late-fcnn", B=12, n_layers=1),
+    "cox_early_fcnn_b33": dict(seed=72, kind="cox", loss="ranking", mode="radio_path", train_type="early-fcnn", B=33, n_layers=1),
+    "cox_early_highway_b9": dict(seed=73, kind="cox", loss="cox", mode="path_omic", train_type="early-highway", B=9, n_layers=2),
+    "cox_late_highway_b20": dict(seed=74, kind="cox", loss="cox", mode="radio_path_omic", train_type="late-highway", B=20, n_layers=1),
+    "nll_late_fcnn_b16": dict(seed=75, kind="nll", loss="nll", mode="radio_path_omic", train_type="late-fcnn", B=16, n_layers=1),
+    "nll_early_fcnn_b8": dict(seed=76, kind="nll", loss="ce", mode="radio_omic", train_type="early-fcnn", B=8, n_layers=1),
+    "nll_early_highway_b40": dict(seed=77, kind="nll", loss="nll", mode="radio_path_omic", train_type="early-highway", B=40, n_layers=1),
+    "nll_late_highway_b6": dict(seed=78, kind="nll", loss="ce", mode="path_omic", train_type="late-highway", B=6, n_layers=2),
+}
 LOSS_CASES = {
     "nll_b7_a0": dict(seed=51, loss="nll", B=7, K=4, alpha=0.0),
     "nll_b64_k8": dict(seed=52, loss="nll", B=64, K=8, alpha=0.15),
@@ -136,6 +148,18 @@ def perturb_biases(model: torch.nn.Module, seed: int) -> None:
         for name, p in model.named_parameters():
             if name.endswith("bias"):
                 p.copy_(0.05 * torch.randn(p.shape, generator=g))
+
+
+def perturb_bn(model: torch.nn.Module, seed: int) -> None:
+    """Seeded non-trivial BatchNorm1d state (running mean / var, weight, bias); identical on both sides."""
+    g = _gen(seed + 211)
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.running_mean.copy_(0.2 * torch.randn(m.num_features, generator=g))
+                m.running_var.copy_(0.5 + torch.rand(m.num_features, generator=g))
+                m.weight.copy_(1.0 + 0.2 * torch.randn(m.num_features, generator=g))
+                m.bias.copy_(0.1 * torch.randn(m.num_features, generator=g))
 
 
 def make_peaky(model: torch.nn.Module, factor: float) -> None:

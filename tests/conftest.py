@@ -27,3 +27,9 @@ def pytest_collection_modifyitems(config, items):
 def goldens():
     path = os.path.join(ROOT, "tests", "golden", "reference_goldens.pt")
     return torch.load(path, map_location="cpu", weights_only=False)
+
+
+@pytest.fixture(scope="session")
+def goldens_heads2():
+    path = os.path.join(ROOT, "tests", "golden", "reference_goldens_heads2.pt")
+    return torch.load(path, map_location="cpu", weights_only=False)

@@ -40,6 +40,17 @@ def build_head_model(cfg):
     return model
 
 
+def build_head2_model(cfg):
+    """fcnn / Highway fusion head for a HEAD2 case: seeded like the reference, biases and BatchNorm state perturbed."""
+    torch.manual_seed(cfg["seed"])
+    mod = cox_heads if cfg["kind"] == "cox" else nll_heads
+    model = mod.multimodal_pretrained(mode=cfg["mode"], train_type=cfg["train_type"], n_classes=4,
+                                      n_layers=cfg["n_layers"]).eval()
+    cases.perturb_biases(model, cfg["seed"])
+    cases.perturb_bn(model, cfg["seed"])
+    return model
+
+
 def amil_weights(seq):
     """(W1, b1, Wa, ba, Wb, bb, wc, bc) as detached fp32 tensors from an attention_net_* Sequential."""
     fc, attn = seq[0], seq[3]

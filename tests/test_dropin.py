@@ -44,6 +44,15 @@ CTOR_MATRIX = [
     ("coxranking_models_pretrained", "multimodal_pretrained", dict(train_type="kronecker", mode="radio_path_omic")),
     ("coxranking_models_pretrained", "multimodal_pretrained", dict(train_type="kronecker", mode="path_omic")),
     ("nll_models_pretrained", "multimodal_pretrained", dict(train_type="kronecker", mode="radio_path", n_classes=8)),
+    ("coxranking_models_pretrained", "multimodal_pretrained", dict(train_type="late-fcnn", mode="radio_path_omic")),
+    ("coxranking_models_pretrained", "multimodal_pretrained", dict(train_type="early-fcnn", mode="radio_path")),
+    ("coxranking_models_pretrained", "multimodal_pretrained", dict(train_type="early-highway", mode="path_omic", n_layers=2)),
+    ("coxranking_models_pretrained", "multimodal_pretrained", dict(train_type="late-highway", mode="radio_path_omic")),
+    ("nll_models_pretrained", "multimodal_pretrained", dict(train_type="late-fcnn", mode="radio_path_omic", n_classes=4)),
+    ("nll_models_pretrained", "multimodal_pretrained", dict(train_type="early-fcnn", mode="radio_omic", n_classes=8)),
+    ("nll_models_pretrained", "multimodal_pretrained", dict(train_type="early-highway", mode="radio_path_omic")),
+    ("nll_models_pretrained", "multimodal_pretrained", dict(train_type="late-highway", mode="path_omic", n_layers=2)),
+    ("model_modules", "Highway", dict(size=256, num_layers=2, f=torch.relu)),
     ("model_modules", "XlinearFusion", dict(num_modalities=3, dim=256, scale_dim=16, mmhid1=512, mmhid2=512)),
     ("model_modules", "Attn_Net_Gated", dict(L=512, D=384, dropout=True, n_classes=1)),
     ("model_modules", "Attn_Net", dict(L=256, D=256, dropout=True, n_classes=1)),
@@ -134,7 +143,7 @@ def test_unsupported_modes_raise_like_the_reference():
         ranking_loss(torch.zeros(1), torch.zeros(1), torch.zeros(1), "sigmoid", "mean")
     with pytest.raises(NotImplementedError):
         from multimodalfusion_b200.models.coxranking_models_pretrained import multimodal_pretrained
-        multimodal_pretrained(train_type="late-fcnn")
+        multimodal_pretrained(train_type="early-residual")   # commented out in the reference as well
     assert hasattr(M.MIL_Attention_fc_surv_path(), "relocate")
 
 

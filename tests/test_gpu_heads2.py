@@ -1,0 +1,102 @@
+"""GPU parity of the fcnn / Highway fusion heads, BatchNorm1d and ce_loss: the drop-in modules on
+the library's kernels against the reference's own fp32 outputs (tests/golden/reference_goldens_heads2.pt) — risk /
+hazards, per-cohort risk ORDER, loss, gradients of every parameter and of the input embeddings — and BatchNorm1d in
+training mode (batch statistics, running-stat update, backward) against torch on the CPU."""
+import pytest
+import torch
+
+from helpers import build_head2_model, rel_err
+from oracle import amil_oracle as O
+from oracle import cases
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda")
+
+
+@pytest.mark.parametrize("name", list(cases.HEAD2_CASES))
+def test_fcnn_highway_heads_vs_reference_goldens(dev, goldens_heads2, name):
+    from multimodalfusion_b200.utils import CoxSurvLoss, CrossEntropySurvLoss, NLLSurvLoss, RankingSurvLoss
+    cfg, gold = cases.HEAD2_CASES[name], goldens_heads2["heads2"][name]
+    model = build_head2_model(cfg).to(dev)
+    hr, hp, ho = [t.to(dev).requires_grad_(True) for t in cases.embeddings(cfg)]
+    times, c = cases.cohort_labels(cfg["B"], cfg["seed"])
+    res = model(hr, hp, ho)
+    if cfg["kind"] == "cox":
+        risk = res[0]
+        assert res[1] is None and res[2] is None and risk.shape == gold["risk"].shape
+        loss = (CoxSurvLoss()(risks=risk, times=times.to(dev), c=c.to(dev)) if cfg["loss"] == "cox"
+                else RankingSurvLoss()(risks=risk.reshape(-1), times=times.to(dev), c=c.to(dev)))
+    else:
+        risk, hazards, S = res
+        assert rel_err(hazards, gold["hazards"]) < 1e-5 and rel_err(S, gold["S"]) < 1e-5
+        lf = NLLSurvLoss(alpha=0.15) if cfg["loss"] == "nll" else CrossEntropySurvLoss(alpha=0.15)
+        loss = lf(hazards=hazards, S=S, Y=(torch.arange(cfg["B"]) % 4).to(dev), c=c.to(dev))
+    assert rel_err(risk, gold["risk"]) < 1e-5
+    assert torch.equal(torch.argsort(risk.reshape(-1).cpu()), torch.argsort(gold["risk"].reshape(-1)))
+    assert abs(loss.item() - gold["loss"].item()) < 1e-5
+    model.zero_grad()
+    loss.backward()
+    for t, gd in zip((hr, hp, ho), gold["d_inputs"]):
+        if gd is not None:
+            assert t.grad is not None and rel_err(t.grad, gd) < 1e-4
+    for k, p in model.named_parameters():
+        fp = gold["grads"][k]
+        if fp is None:                      # branch of a modality the mode does not use: no gradient in the reference
+            assert p.grad is None or p.grad.abs().max().item() == 0, k
+            continue
+        ref = fp["vals"]
+        got = p.grad.detach().reshape(-1).float().cpu()[cases._sample_idx(p.numel())]
+        scale = max(ref.abs().max().item(), 1e-30)
+        assert (got - ref).abs().max().item() <= 1e-4 * scale + 1e-7, k
+
+
+@pytest.mark.parametrize("B,F", [(2, 128), (37, 128), (512, 768), (33, 100)])
+def test_batchnorm1d_train_and_eval_vs_torch(dev, B, F):
+    from multimodalfusion_b200.models.model_modules import batchnorm1d_forward
+    g = torch.Generator().manual_seed(B + F)
+    x = torch.randn(B, F, generator=g) * 1.7 + 0.3
+    dy = torch.randn(B, F, generator=g)
+    ref = torch.nn.BatchNorm1d(F)
+    ours = torch.nn.BatchNorm1d(F)
+    for m in (ref, ours):
+        cases.perturb_bn(m, 5)
+    ours = ours.to(dev)
+    for train in (True, False):
+        ref.train(train); ours.train(train)
+        xr = x.clone().requires_grad_(True)
+        xo = x.clone().to(dev).requires_grad_(True)
+        yr = ref(xr)
+        yo = batchnorm1d_forward(ours, xo)
+        assert rel_err(yo, yr) < 1e-5
+        ref.zero_grad(); ours.zero_grad()
+        yr.backward(dy); yo.backward(dy.to(dev))
+        assert rel_err(xo.grad, xr.grad) < 2e-5
+        assert rel_err(ours.weight.grad, ref.weight.grad) < 2e-5 and rel_err(ours.bias.grad, ref.bias.grad) < 2e-5
+        assert rel_err(ours.running_mean, ref.running_mean) < 1e-5 and rel_err(ours.running_var, ref.running_var) < 1e-5
+        assert int(ours.num_batches_tracked) == int(ref.num_batches_tracked)
+
+
+def test_batchnorm1d_single_sample_training_raises_like_torch(dev):
+    from multimodalfusion_b200._lib import MmfError
+    from multimodalfusion_b200.models.model_modules import batchnorm1d_forward
+    bn = torch.nn.BatchNorm1d(16).to(dev).train()
+    with pytest.raises(MmfError):
+        batchnorm1d_forward(bn, torch.randn(1, 16, device=dev))
+
+
+@pytest.mark.parametrize("B,K,alpha", [(7, 4, 0.0), (64, 8, 0.15), (5, 4, 0.4)])
+def test_ce_loss_vs_oracle(dev, B, K, alpha):
+    from multimodalfusion_b200.utils import ce_loss
+    hz, S, Y, c = cases.nll_inputs(dict(seed=90 + B, B=B, K=K))   # (ce_loss is inf on saturated inputs in the reference too)
+    hr, Sr = hz.clone().requires_grad_(True), S.clone().requires_grad_(True)
+    want = O.ce_surv_loss(hr, Sr, Y, c, alpha=alpha)
+    want.backward()
+    ho, So = hz.clone().to(dev).requires_grad_(True), S.clone().to(dev).requires_grad_(True)
+    got = ce_loss(ho, So, Y.to(dev), c.to(dev), alpha=alpha)
+    got.backward()
+    assert abs(got.item() - want.item()) < 1e-5 * max(1.0, abs(want.item()))
+    assert rel_err(ho.grad, hr.grad) < 1e-5 and rel_err(So.grad, Sr.grad) < 1e-4

@@ -171,3 +171,44 @@ def test_concordance_index_simple():
     risk, t, e = [3.0, 2.0, 1.0], [1.0, 2.0, 3.0], [1, 1, 0]
     assert O.concordance_index(risk, t, e) == 1.0
     assert O.concordance_index(risk[::-1], t, e) == 0.0
+
+
+@pytest.mark.parametrize("name", list(cases.HEAD2_CASES))
+def test_fcnn_highway_heads_match_reference(goldens_heads2, name):
+    """Oracle restatement of the fcnn / Highway fusion heads + ce_loss against the reference's own outputs
+    (tests/golden/reference_goldens_heads2.pt, generated by oracle/make_goldens_heads2.py), weights rebuilt from
+    the seed through the drop-in constructors (fingerprint-checked)."""
+    from helpers import build_head2_model
+    cfg, gold = cases.HEAD2_CASES[name], goldens_heads2["heads2"][name]
+    model = build_head2_model(cfg)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    for k, fp in gold["weights_fp"].items():
+        cases.check_fingerprint(sd[k], fp, 0.0, k)
+    hr, hp, ho = cases.embeddings(cfg)
+    times, c = cases.cohort_labels(cfg["B"], cfg["seed"])
+    out = O.fusion_head2_eval(sd, cfg["kind"], cfg["train_type"], cfg["mode"], cfg["n_layers"], hr, hp, ho)
+    if cfg["kind"] == "cox":
+        assert out.shape == gold["risk"].shape
+        assert torch.allclose(out, gold["risk"], rtol=1e-5, atol=1e-6)
+        loss = O.cox_loss(out.reshape(-1), times, c) if cfg["loss"] == "cox" else O.ranking_loss(out.reshape(-1), times, c)
+    else:
+        hz = torch.sigmoid(out)
+        S = torch.cumprod(1 - hz, dim=1)
+        assert torch.allclose(hz, gold["hazards"], rtol=1e-5, atol=1e-6) and torch.allclose(-S.sum(1), gold["risk"], rtol=1e-5, atol=1e-6)
+        Y = torch.arange(cfg["B"]) % 4
+        loss = (O.nll_surv_loss(hz, S, Y, c, alpha=0.15) if cfg["loss"] == "nll" else O.ce_surv_loss(hz, S, Y, c, alpha=0.15))
+    assert abs(float(loss) - gold["loss"].item()) < 1e-5
+
+
+def test_batchnorm_train_restatement_matches_torch():
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(37, 128, generator=g) * 2 + 0.5
+    w, b = torch.randn(128, generator=g), torch.randn(128, generator=g)
+    bn = torch.nn.BatchNorm1d(128).train()
+    with torch.no_grad():
+        bn.weight.copy_(w); bn.bias.copy_(b)
+    y = bn(x)
+    yo, mean, var_u = O.batchnorm1d_train(x, w, b)
+    assert torch.allclose(y, yo, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(bn.running_mean, 0.1 * mean, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(bn.running_var, 0.9 + 0.1 * var_u, rtol=1e-5, atol=1e-6)
