@@ -311,6 +311,12 @@ int mmf_adam_step_multi(float* const* params_host, const float* const* grads_hos
 int mmf_cindex_counts(const float* risk, const float* times, const float* event, int B, float tied_tol,
                       uint64_t* counts, void* stream);
 
+/* Attention scores -> percentiles for heatmaps: out[q] = scipy.stats.percentileofscore(ref_scores, query[q]) (kind='rank')
+ * = (left + right + [left < right]) * 50 / n_ref with left = #{ref < x}, right = #{ref <= x}; replaces the per-patch host loops of utils/wsi_utils.py:171-174
+ * (to_percentiles: query == ref) and utils/heatmap_utils.py:32-34,99,138 (score2percentile against reference scores). */
+int mmf_percentile_of_score(const float* ref_scores, int n_ref, const float* query, int n_query, float* out,
+                            void* stream);
+
 /* ---- multi-GPU: SUM all-reduce of a small fp32 buffer over NVLink peer memory ----------------
  * The gradient all-reduce that closes a cohort-data-parallel step (the reference is
  * single-GPU and has no counterpart) as one kernel on the caller's stream: ready handshake, reduce of

@@ -133,6 +133,7 @@ SIGNATURES = {
     "mmf_cox_workspace_bytes": (_sz, [_i]),
     "mmf_cox_fwd_bwd": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "mmf_adam_step_multi": (_i, [_PP, _PP, _PP, _PP, C.POINTER(C.c_int64), _i, _i, _f, _f, _f, _f, _f, _f, _f, _i, _vp, _vp]),
+    "mmf_percentile_of_score": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
     "mmf_cindex_counts": (_i, [_vp, _vp, _vp, _i, _f, _vp, _vp]),
     "mmf_p2p_flag_bytes": (_sz, []),
     "mmf_p2p_allreduce_sum_f32": (_i, [_PP, _PP, _vp, _i, _i, _i64, _i, _vp]),

@@ -898,6 +898,14 @@ int mmf_cindex_counts(const float* risk, const float* times, const float* event,
   return launch_status();
 }
 
+int mmf_percentile_of_score(const float* ref_scores, int n_ref, const float* query, int n_query, float* out,
+                            void* stream) {
+  if (!ref_scores || !query || !out || n_ref <= 0 || n_query <= 0) return MMF_E_INVALID;
+  if ((long long)n_ref * n_query > (1ll << 36)) return MMF_E_UNSUPPORTED;   // brute-force pair count: keep it under ~1 s
+  percentile_of_score_kernel<<<(n_query + 255) / 256, 256, 0, (cudaStream_t)stream>>>(ref_scores, n_ref, query, n_query, out);
+  return launch_status();
+}
+
 size_t mmf_p2p_flag_bytes(void) { return (size_t)P2P_FLAG_WORDS * sizeof(uint32_t); }
 
 int mmf_p2p_allreduce_sum_f32(void* const* bufs_host, void* const* flags_host, void* multicast_ptr, int world,

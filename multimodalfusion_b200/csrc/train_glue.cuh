@@ -90,4 +90,32 @@ __global__ void __launch_bounds__(256) cindex_pairs_kernel(const float* __restri
   if (threadIdx.x < 3 && s_c[threadIdx.x]) atomicAdd(counts + threadIdx.x, s_c[threadIdx.x]);
 }
 
+// Attention scores -> percentiles, as utils/wsi_utils.py:171-174 (to_percentiles) and utils/heatmap_utils.py:32-34,99,138
+// compute them with scipy.stats.percentileofscore(ref, x) (kind = 'rank'): (left + right + [left < right]) * 50 / n with
+// left = #{ref < x}, right = #{ref <= x}.
+// The reference runs one O(n) scipy call per patch (O(N n) on the host); here one thread per query counts over
+// shared-memory tiles of the reference scores (exact, ties included).
+__global__ void __launch_bounds__(256) percentile_of_score_kernel(const float* __restrict__ ref, int n_ref,
+                                                                  const float* __restrict__ query, int n_query,
+                                                                  float* __restrict__ out) {
+  __shared__ float tile[2048];
+  const int q = blockIdx.x * 256 + threadIdx.x;
+  const float x = q < n_query ? query[q] : 0.f;
+  unsigned int less = 0, leq = 0;
+  for (int t0 = 0; t0 < n_ref; t0 += 2048) {
+    const int nt = min(2048, n_ref - t0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nt; i += 256) tile[i] = ref[t0 + i];
+    __syncthreads();
+#pragma unroll 8
+    for (int i = 0; i < nt; ++i) {
+      const float r = tile[i];
+      less += r < x;
+      leq += r <= x;
+    }
+  }
+  // scipy (kind='rank'): (left + right + [left < right]) * 50 / n
+  if (q < n_query) out[q] = (float)(less + leq + (less < leq ? 1u : 0u)) * (50.f / (float)n_ref);
+}
+
 }  // namespace mmf

@@ -26,7 +26,10 @@ class FusedAdam(torch.optim.Optimizer):
 
     @torch.no_grad()
     def step(self, closure=None, zero_grad: bool = False, grad_scale: float = 1.0):
-        loss = closure() if closure is not None else None
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
         for group in self.param_groups:
             ps = [p for p in group["params"] if p.grad is not None]
             if not ps:
@@ -83,3 +86,16 @@ def concordance_index(risk: torch.Tensor, times: torch.Tensor, event: torch.Tens
     c, d, tie = counts.tolist()
     tot = c + d + tie
     return (c + 0.5 * tie) / tot if tot else float("nan")
+
+
+def to_percentiles(scores: torch.Tensor, ref_scores: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """utils/wsi_utils.py:171-174 (`to_percentiles(scores)`) and utils/heatmap_utils.py:32-34 (`score2percentile`
+    against reference scores): scipy's percentileofscore (kind='rank') of every score, on the device."""
+    if not scores.is_cuda:
+        raise RuntimeError("multimodalfusion_b200 kernels need CUDA tensors (sm_100a); there is no CPU fallback.")
+    q = scores.detach().reshape(-1).float().contiguous()
+    ref = q if ref_scores is None else ref_scores.detach().reshape(-1).to(q.device, torch.float32).contiguous()
+    out = torch.empty_like(q)
+    check(lib().mmf_percentile_of_score(ref.data_ptr(), ref.numel(), q.data_ptr(), q.numel(), out.data_ptr(),
+                                        torch.cuda.current_stream().cuda_stream), "mmf_percentile_of_score")
+    return out.view(scores.shape)

@@ -79,3 +79,16 @@ def test_short_training_loop_with_fused_optimizer(dev):
         losses.append(loss.item())
     assert losses[-1] < losses[0] - 1e-3, losses
     assert (model.attention_net_WSI[0].weight - w0).abs().max().item() > 0
+
+
+@pytest.mark.parametrize("n,nq", [(1, 1), (1000, 1000), (5000, 300)])
+def test_percentiles_match_scipy(dev, n, nq):
+    """utils/wsi_utils.py:171-174 / utils/heatmap_utils.py:32-34: scipy.stats.percentileofscore per score."""
+    from scipy.stats import percentileofscore
+    from multimodalfusion_b200.utils import to_percentiles
+    g = torch.Generator().manual_seed(n)
+    ref = torch.randn(n, generator=g).round(decimals=2)          # rounding -> plenty of ties
+    q = ref if nq == n else torch.randn(nq, generator=g).round(decimals=2)
+    got = to_percentiles(q.to(dev), None if nq == n else ref.to(dev)).cpu()
+    want = torch.tensor([percentileofscore(ref.numpy(), float(v)) for v in q.numpy()], dtype=torch.float32)
+    assert torch.allclose(got, want, rtol=0, atol=1e-4)
