@@ -204,7 +204,11 @@ def run_ours(args):
             if rank == 0:
                 print(f"# peer all-reduce unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
             peer_ar = None
-    for bi in range(2):
+    # MMF_BENCH_INFLIGHT=n (single GPU): n independent bags of a gradient-accumulation window are in flight on n
+    # streams (lane = step % n, each lane with its own activation workspace and gradient buffer), so that one lane's
+    # kernel boundaries and partial waves (128 CTAs on 148 SMs) are filled by the other lane's kernels
+    lanes = max(1, int(os.environ.get("MMF_BENCH_INFLIGHT", "2"))) if world == 1 else 1
+    for bi in range(max(2, lanes)):
         # (padded to a multiple of 4 floats: cleared / reduced 16 bytes at a time)
         fl = (peer_ar.buffer(bi) if peer_ar is not None
               else torch.zeros((sum(sizes) + 3) // 4 * 4, dtype=torch.float32, device=dev))
@@ -222,11 +226,12 @@ def run_ours(args):
     # backward mode: "stash" (default: the training forward leaves h / branch activations in the backward
     # workspace, no recompute GEMMs) or "recompute" (MMF_BENCH_BWD=recompute: the tile kernel runs again)
     bwd_mode = os.environ.get("MMF_BENCH_BWD", "stash")
-    step_ws = ops.amil_bwd_workspace(N_BAG, prep, flags, dev)
+    step_wss = [ops.amil_bwd_workspace(N_BAG, prep, flags, dev) for _ in range(lanes)]
+    step_ws = step_wss[0]
 
-    def step(x, b=0):
+    def step(x, b=0, lane=0):
         if bwd_mode == "stash":   # the training forward clears the step's gradient buffer itself (fused zero_grad)
-            A_raw, parts, ws = ops.amil_partials_train(x, prep, flags, seed, workspace=step_ws, zero=flats[b])
+            A_raw, parts, ws = ops.amil_partials_train(x, prep, flags, seed, workspace=step_wss[lane], zero=flats[b])
         else:
             flats[b].zero_()
             (A_raw, parts), ws = ops.amil_partials(x, prep, flags, seed), None
@@ -248,11 +253,29 @@ def run_ours(args):
     # a host graph launch is paid once per 8 steps; multi-GPU keeps per-step graphs (an all-reduce follows each)
     loop_graph = None
     comm_stream = torch.cuda.Stream() if world > 1 else None
-    if world == 1:
+    if world == 1 and lanes == 1:
         loop_graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(loop_graph):
             for i in range(N_BAGS):
                 losses.append(step(bags[i], i % 2))
+    elif world == 1:
+        # fork-join graph: bag i runs on lane i % lanes; lanes only share the (read-only) weights
+        side = [torch.cuda.Stream() for _ in range(lanes - 1)]
+        loop_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(loop_graph):
+            cap = torch.cuda.current_stream()
+            fork = torch.cuda.Event()
+            fork.record(cap)
+            for s_ in side:
+                s_.wait_event(fork)
+            for i in range(N_BAGS):
+                lane = i % lanes
+                with torch.cuda.stream(cap if lane == 0 else side[lane - 1]):
+                    losses.append(step(bags[i], lane, lane))
+            for s_ in side:
+                ev = torch.cuda.Event()
+                ev.record(s_)
+                cap.wait_event(ev)
     elif peer_ar is not None and os.environ.get("MMF_BENCH_AR_MODE", "overlap") in ("graph", "inline"):
         # Experimental placements of the gradient exchange inside ONE 8-step graph (default for N > 1 stays: per-step
         # graphs + the exchange launched eagerly on a communication stream). "graph": forked branch on a second
@@ -335,6 +358,11 @@ def run_ours(args):
     ms_per_step = ms / args.steps
     value = world * N_BAG / (ms_per_step * 1e-3)
     assert all(torch.isfinite(l).item() for l in losses)
+    if os.environ.get("MMF_BENCH_QUICK") == "1":   # diagnostic: device-resident value only
+        if rank == 0:
+            print(json.dumps({"quick": True, "lanes": lanes, "ms_per_step": ms_per_step, "value": value,
+                              "loss0": losses[-N_BAGS].item(), "loss1": losses[-N_BAGS + 1].item()}), flush=True)
+        return
 
     # ---- e2e through the public drop-in API with pinned host bags ---------------------------------
     loss_fn = NLLSurvLoss(alpha=0.0)
@@ -500,7 +528,9 @@ def run_ours(args):
                                        + ("own NVLink peer-memory kernel" if peer_ar is not None else "NCCL")
                                        + " on a communication stream, overlapping the next bag's step as in a "
                                          "gradient-accumulation window; all reductions complete inside the timed region)")
-                       if world > 1 else "single GPU",
+                       if world > 1 else ("single GPU" if lanes == 1 else
+                                          f"single GPU, {lanes} independent bags of a gradient-accumulation window in "
+                                          f"flight on {lanes} streams (own activation workspace and gradient buffer each)"),
                        "timed_with": ("CUDA graphs (8 consecutive steps per graph launch, remainder as single-step graphs)"
                                       if loop_graph is not None else "CUDA graph replay per step") + ", CUDA events, max over ranks"},
             "clocks": clk.result,
