@@ -207,7 +207,11 @@ def run_ours(args):
     # MMF_BENCH_INFLIGHT=n (single GPU): n independent bags of a gradient-accumulation window are in flight on n
     # streams (lane = step % n, each lane with its own activation workspace and gradient buffer), so that one lane's
     # kernel boundaries and partial waves (128 CTAs on 148 SMs) are filled by the other lane's kernels
-    lanes = max(1, int(os.environ.get("MMF_BENCH_INFLIGHT", "2"))) if world == 1 else 1
+    # (N > 1: the same two lanes, each step graph replayed on its lane's stream, the exchange of the lane's gradient
+    # buffer on the communication stream)
+    lanes = max(1, int(os.environ.get("MMF_BENCH_INFLIGHT", "2")))
+    if world > 1:
+        lanes = min(lanes, 2)    # the peer all-reduce owns two symmetric gradient buffers
     for bi in range(max(2, lanes)):
         # (padded to a multiple of 4 floats: cleared / reduced 16 bytes at a time)
         fl = (peer_ar.buffer(bi) if peer_ar is not None
@@ -247,7 +251,7 @@ def run_ours(args):
     for i in range(N_BAGS):
         gr = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gr):
-            losses.append(step(bags[i], i % 2))   # the loss scalar lives in the graph's private pool
+            losses.append(step(bags[i], i % 2, i % lanes if lanes == 2 else 0))   # the loss scalar lives in the graph's private pool
         graphs.append(gr)
     # single GPU: the batch-1 loop over the 8 bags is also captured as ONE graph (8 consecutive steps), so that
     # a host graph launch is paid once per 8 steps; multi-GPU keeps per-step graphs (an all-reduce follows each)
@@ -305,8 +309,46 @@ def run_ours(args):
                 if ev is not None:
                     cap.wait_event(ev)
     reduced = [None, None]   # per gradient buffer: event of its last all-reduce
+    lane_streams = [torch.cuda.Stream() for _ in range(2)] if (world > 1 and lanes == 2) else None
+
+    def run_steps_lanes(n, first=0):
+        # N > 1, two lanes: bag -> lane = bag % 2 (its own stream, workspace and gradient buffer); the lane's buffer
+        # is exchanged on the communication stream while the other lane (and this lane's next forward, up to the
+        # point where it clears the buffer) keeps computing
+        cur = torch.cuda.current_stream()
+        start = torch.cuda.Event()
+        start.record(cur)
+        for st in lane_streams:
+            st.wait_event(start)
+        for i in range(n):
+            bag = (first + i) % N_BAGS
+            b = bag % 2
+            st = lane_streams[b]
+            with torch.cuda.stream(st):
+                if reduced[b] is not None:
+                    st.wait_event(reduced[b])
+                graphs[bag].replay()
+                ready = torch.cuda.Event()
+                ready.record(st)
+            with torch.cuda.stream(comm_stream):
+                comm_stream.wait_event(ready)
+                if peer_ar is not None:
+                    peer_ar.all_reduce(b)
+                else:
+                    dist.all_reduce(flats[b])
+                reduced[b] = torch.cuda.Event()
+                reduced[b].record(comm_stream)
+        for st in lane_streams:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            cur.wait_event(ev)
+        for ev in reduced:
+            if ev is not None:
+                cur.wait_event(ev)
 
     def run_steps(n, first=0):
+        if lane_streams is not None and loop_graph is None and os.environ.get("MMF_BENCH_SKIP_ALLREDUCE") != "1":
+            return run_steps_lanes(n, first)
         i = 0
         cur = torch.cuda.current_stream()
         while i < n:
@@ -358,6 +400,24 @@ def run_ours(args):
     ms_per_step = ms / args.steps
     value = world * N_BAG / (ms_per_step * 1e-3)
     assert all(torch.isfinite(l).item() for l in losses)
+    # reported next to the headline: the same 8-step loop with ONE bag in flight (strict batch-1 loop, gc = 1)
+    single_lane = None
+    if world == 1 and lanes > 1:
+        g1 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g1):
+            for i in range(N_BAGS):
+                losses.append(step(bags[i], i % 2))
+        for _ in range(2):
+            g1.replay()
+        torch.cuda.synchronize()
+        reps = max(2, min(args.steps // N_BAGS, 8))
+        ev0.record()
+        for _ in range(reps):
+            g1.replay()
+        ev1.record()
+        torch.cuda.synchronize()
+        ms1 = ev0.elapsed_time(ev1) / (reps * N_BAGS)
+        single_lane = {"ms_per_step": ms1, "value": N_BAG / (ms1 * 1e-3), "steps": reps * N_BAGS}
     if os.environ.get("MMF_BENCH_QUICK") == "1":   # diagnostic: device-resident value only
         if rank == 0:
             print(json.dumps({"quick": True, "lanes": lanes, "ms_per_step": ms_per_step, "value": value,
@@ -523,7 +583,9 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "bag": [N_BAG, 1024], "preset": "big", "n_classes": K_CLASSES, "backward": bwd_mode,
                        "l2": f"inputs rotate over {N_BAGS} distinct bags ({N_BAGS * N_BAG * 2048 >> 20} MiB) > 126 MB L2",
-                       "parallelism": (f"dp{world} (cohort data-parallel, one bag per rank per step, all-reduce of "
+                       "parallelism": (f"dp{world} (cohort data-parallel, one bag per rank per step, "
+                                       + (f"{lanes} bags in flight per rank on {lanes} streams, " if lanes > 1 else "")
+                                       + "all-reduce of "
                                        f"{flat.numel() * 4} B of fp32 grads per step: "
                                        + ("own NVLink peer-memory kernel" if peer_ar is not None else "NCCL")
                                        + " on a communication stream, overlapping the next bag's step as in a "
@@ -540,6 +602,8 @@ def run_ours(args):
             "gpu_launches": (LAUNCHES_PER_STEP + (1 if peer_ar is not None else 0)) * args.steps,
             "roofline": roof, "cpu_baseline": cpu_base,
         }
+        if single_lane is not None:
+            line["one_bag_in_flight"] = single_lane
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
