@@ -220,7 +220,7 @@ int mmf_dense_bwd(const float* x, int64_t ldx, const float* W, int B, int in_dim
                   int act, const float* y, int64_t ldy, const float* dy, int64_t lddy, float* dx,
                   int64_t lddx, int accumulate_dx, float* dW, float* db, void* stream);
 
-/* Kronecker ("Xlinear") fusion encoder1: out[B,H] = relu(W1 · (o_1 ⊗ o_2 [⊗ o_3]) + b1) with
+/* Kronecker ("Xlinear") fusion encoder1: out[B,H] = relu(W1 · (o_1 ⊗ o_2 [⊗ o_3 [⊗ o_4]]) + b1), m = 2..4, with
  * o_i[B,E] (E = dim+1, last column = 1) never materialising the E^m-wide outer product.
  * Replaces torch.bmm outer products + encoder1 Linear+ReLU (models/model_modules.py:167-173). */
 int mmf_kron_enc_fwd(const float* const* o /*HOST array of m device ptrs [B,E]*/, int m, int E, int B,

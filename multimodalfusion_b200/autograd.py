@@ -121,7 +121,7 @@ class Dense(torch.autograd.Function):
 
 
 class KronEncoder(torch.autograd.Function):
-    """relu(W (o_1 ⊗ o_2 [⊗ o_3]) + b) without materialising the outer product in the forward
+    """relu(W (o_1 ⊗ o_2 [⊗ o_3 [⊗ o_4]]) + b) without materialising the outer product in the forward
     (models/model_modules.py:167-173)."""
 
     @staticmethod

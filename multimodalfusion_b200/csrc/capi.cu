@@ -692,35 +692,39 @@ int mmf_dense_bwd(const float* x, int64_t ldx, const float* W, int B, int in_dim
 
 int mmf_kron_enc_fwd(const float* const* o, int m, int E, int B, const float* W, const float* b,
                      int H, float* out, void* stream) {
-  if (!o || (m != 2 && m != 3) || E <= 0 || B <= 0 || !W || !out) return MMF_E_INVALID;
-  KronElem e{o[0], o[1], m == 3 ? o[2] : nullptr, m, E};
-  const int KK = (m == 3) ? E * E * E : E * E;
+  if (!o || m < 2 || m > 4 || E <= 0 || B <= 0 || !W || !out) return MMF_E_INVALID;
+  KronElem e{o[0], o[1], m >= 3 ? o[2] : nullptr, m >= 4 ? o[3] : nullptr, m, E};
+  if (e.width() > (1ll << 30)) return MMF_E_INVALID;
+  const int KK = (int)e.width();
   launch_sgemm(B, H, KK, LoadKronA{e}, LoadRowMajor{W, KK}, EpiBiasAct{out, H, b, MMF_ACT_RELU},
                (cudaStream_t)stream);
   return launch_status();
 }
 
 size_t mmf_kron_enc_workspace_bytes(int m, int E, int B) {
-  size_t kk = (m == 3) ? (size_t)E * E * E : (size_t)E * E;
+  size_t kk = 1;
+  for (int t = 0; t < m; ++t) kk *= (size_t)E;
   return kk * (size_t)B * sizeof(float);
 }
 
 int mmf_kron_enc_bwd(const float* const* o, int m, int E, int B, const float* W, int H,
                      const float* out, const float* dout, float* const* d_o, float* dW, float* db,
                      void* workspace, size_t workspace_bytes, void* stream) {
-  if (!o || (m != 2 && m != 3) || !W || !out || !dout || !workspace) return MMF_E_INVALID;
+  if (!o || m < 2 || m > 4 || !W || !out || !dout || !workspace) return MMF_E_INVALID;
   if (workspace_bytes < mmf_kron_enc_workspace_bytes(m, E, B)) return MMF_E_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
-  KronElem e{o[0], o[1], m == 3 ? o[2] : nullptr, m, E};
-  const int KK = (m == 3) ? E * E * E : E * E;
+  KronElem e{o[0], o[1], m >= 3 ? o[2] : nullptr, m >= 4 ? o[3] : nullptr, m, E};
+  if (e.width() > (1ll << 30)) return MMF_E_INVALID;
+  const int KK = (int)e.width();
   float* dkron = reinterpret_cast<float*>(workspace);
   LoadDpre dpre{dout, H, out, H, MMF_ACT_RELU};
   LoadDpreT dpreT{dout, H, out, H, MMF_ACT_RELU};
   if (d_o) {
     // dkron[b,kk] = sum_h dpre[b,h] W[h,kk]
     launch_sgemm(B, KK, H, dpre, LoadColMajor{W, KK}, EpiStoreAcc{dkron, KK, 0}, st);
-    kron_contract_kernel<<<B, 256, 6 * E * sizeof(float), st>>>(dkron, e, B, d_o[0], d_o[1],
-                                                                m == 3 ? d_o[2] : nullptr);
+    kron_contract_kernel<<<B, 256, 8 * E * sizeof(float), st>>>(dkron, e, B, d_o[0], d_o[1],
+                                                                m >= 3 ? d_o[2] : nullptr,
+                                                                m >= 4 ? d_o[3] : nullptr);
   }
   if (dW)  // dW[h,kk] += sum_b dpre[b,h] kron[b,kk]
     launch_sgemm(H, KK, B, dpreT, LoadKronB{e}, EpiStoreAcc{dW, KK, 1}, st);

@@ -88,13 +88,24 @@ struct LoadDpreT {               // element (o, b): A(m=o, k=b): m contiguous
     return dy[b * lddy + o] * act_grad_from_y(act, y[b * ldy + o]);
   }
 };
-// Kronecker product element kk of o_1 ⊗ o_2 (⊗ o_3) for sample b (first factor slowest).
+// Kronecker product element kk of o_1 ⊗ o_2 (⊗ o_3 (⊗ o_4)) for sample b (first factor slowest).
 struct KronElem {
-  const float* o0; const float* o1; const float* o2; int m; int E;
+  const float* o0; const float* o1; const float* o2; const float* o3; int m; int E;
   __device__ __forceinline__ float at(int b, int kk) const {
     if (m == 2) { const int i = kk / E, j = kk - i * E; return o0[b * E + i] * o1[b * E + j]; }
-    const int i = kk / (E * E); const int r = kk - i * E * E; const int j = r / E, k = r - j * E;
-    return o0[b * E + i] * o1[b * E + j] * o2[b * E + k];
+    if (m == 3) {
+      const int i = kk / (E * E); const int r = kk - i * E * E; const int j = r / E, k = r - j * E;
+      return o0[b * E + i] * o1[b * E + j] * o2[b * E + k];
+    }
+    const int E2 = E * E;
+    const int ij = kk / E2, kl = kk - ij * E2;
+    const int i = ij / E, j = ij - i * E, k = kl / E, l = kl - k * E;
+    return o0[b * E + i] * o1[b * E + j] * o2[b * E + k] * o3[b * E + l];
+  }
+  __host__ __device__ long long width() const {
+    long long w = 1;
+    for (int t = 0; t < m; ++t) w *= E;
+    return w;
   }
 };
 struct LoadKronA {               // A(m=b, k=kk)
@@ -217,38 +228,44 @@ __global__ void colsum_functor_kernel(int B, int O, Elem e, float* out, int accu
 
 // -------------------------------------------------------------------------------------------
 // Kronecker encoder backward, input side: given dkron[B, E^m] contract against the other factors
-//   d_o0[b,i] = sum_{j,k} dkron[b,(i,j,k)] o1[b,j] o2[b,k]   etc.   One block per sample.
+//   d_o0[b,i] = sum_{j,k} dkron[b,(i,j,k)] o1[b,j] o2[b,k]   etc. (2, 3 or 4 factors).   One block per sample.
 // -------------------------------------------------------------------------------------------
 __global__ void kron_contract_kernel(const float* __restrict__ dkron, KronElem e, int B,
-                                     float* d0, float* d1, float* d2) {
-  extern __shared__ float sh[];  // 3*E accumulators + 3*E factor values
+                                     float* d0, float* d1, float* d2, float* d3) {
+  extern __shared__ float sh[];  // 4*E accumulators + 4*E factor values (absent factors read as 1)
   const int E = e.E, m = e.m, b = blockIdx.x;
   float* acc = sh;
-  float* f = sh + 3 * E;
-  for (int i = threadIdx.x; i < 3 * E; i += blockDim.x) acc[i] = 0.f;
+  float* f = sh + 4 * E;
+  for (int i = threadIdx.x; i < 4 * E; i += blockDim.x) acc[i] = 0.f;
   for (int i = threadIdx.x; i < E; i += blockDim.x) {
     f[i] = e.o0[b * E + i];
     f[E + i] = e.o1[b * E + i];
-    f[2 * E + i] = (m == 3) ? e.o2[b * E + i] : 1.f;
+    f[2 * E + i] = (m >= 3) ? e.o2[b * E + i] : 1.f;
+    f[3 * E + i] = (m >= 4) ? e.o3[b * E + i] : 1.f;
   }
   __syncthreads();
-  const int KK = (m == 3) ? E * E * E : E * E;
+  const int KK = (int)e.width();
   const float* row = dkron + (long long)b * KK;
   for (int kk = threadIdx.x; kk < KK; kk += blockDim.x) {
     const float g = row[kk];
-    int i, j, k;
-    if (m == 3) { i = kk / (E * E); const int r = kk - i * E * E; j = r / E; k = r - j * E; }
-    else { i = kk / E; j = kk - i * E; k = 0; }
-    const float v0 = f[i], v1 = f[E + j], v2 = f[2 * E + k];
-    atomicAdd(&acc[i], g * v1 * v2);
-    atomicAdd(&acc[E + j], g * v0 * v2);
-    if (m == 3) atomicAdd(&acc[2 * E + k], g * v0 * v1);
+    int i, j, k = 0, l = 0;
+    if (m == 4) {
+      const int E2 = E * E, ij = kk / E2, kl = kk - ij * E2;
+      i = ij / E; j = ij - i * E; k = kl / E; l = kl - k * E;
+    } else if (m == 3) { i = kk / (E * E); const int r = kk - i * E * E; j = r / E; k = r - j * E; }
+    else { i = kk / E; j = kk - i * E; }
+    const float v0 = f[i], v1 = f[E + j], v2 = f[2 * E + k], v3 = f[3 * E + l];
+    atomicAdd(&acc[i], g * v1 * v2 * v3);
+    atomicAdd(&acc[E + j], g * v0 * v2 * v3);
+    if (m >= 3) atomicAdd(&acc[2 * E + k], g * v0 * v1 * v3);
+    if (m >= 4) atomicAdd(&acc[3 * E + l], g * v0 * v1 * v2);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < E; i += blockDim.x) {
     d0[b * E + i] = acc[i];
     d1[b * E + i] = acc[E + i];
-    if (m == 3) d2[b * E + i] = acc[2 * E + i];
+    if (m >= 3) d2[b * E + i] = acc[2 * E + i];
+    if (m >= 4) d3[b * E + i] = acc[3 * E + i];
   }
 }
 

@@ -199,8 +199,8 @@ class XlinearFusion(nn.Module):
             # the reference indexes reduce[i][2] unconditionally (models/model_modules.py:163), so
             # gate=0 cannot run there either
             raise NotImplementedError("gate=0 is not runnable in the reference (IndexError on reduce[i][2])")
-        if len(v_list) not in (2, 3):
-            raise NotImplementedError("Kronecker fusion kernel supports 2 or 3 modalities")
+        if len(v_list) not in (2, 3, 4):
+            raise NotImplementedError("Kronecker fusion kernel supports 2, 3 or 4 modalities")
         v_list = [v.float() for v in v_list]
         v_cat = torch.cat(v_list, dim=1)
         o_list = []

@@ -52,6 +52,11 @@ HEAD2_CASES = {
     "nll_early_highway_b40": dict(seed=77, kind="nll", loss="nll", mode="radio_path_omic", train_type="early-highway", B=40, n_layers=1),
     "nll_late_highway_b6": dict(seed=78, kind="nll", loss="ce", mode="path_omic", train_type="late-highway", B=6, n_layers=2),
 }
+# XlinearFusion with the reference's DEFAULT num_modalities=4 (17^4 = 83 521-wide outer product)
+XFUSION4_CASES = {
+    "xfusion4_b5": dict(seed=81, B=5),
+    "xfusion4_b33": dict(seed=82, B=33),
+}
 LOSS_CASES = {
     "nll_b7_a0": dict(seed=51, loss="nll", B=7, K=4, alpha=0.0),
     "nll_b64_k8": dict(seed=52, loss="nll", B=64, K=8, alpha=0.15),
@@ -118,6 +123,16 @@ def embeddings(cfg):
     hp = torch.randn(B, 256, generator=g).abs() * 0.5
     ho = torch.randn(B, 256, generator=g)
     return hr, hp, ho
+
+
+def embeddings4(cfg):
+    """Four 256-d embeddings (radio, path, omic + a second non-negative pooled one) and the fixed projection that turns
+    the fused features into a scalar objective for the gradient goldens."""
+    hr, hp, ho = embeddings(cfg)
+    g = _gen(cfg["seed"] + 4)
+    h4 = torch.randn(cfg["B"], 256, generator=g).abs() * 0.5
+    proj = torch.randn(256, generator=g) / 16.0
+    return [hr, hp, ho, h4], proj
 
 
 def nll_inputs(cfg):

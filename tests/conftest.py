@@ -33,3 +33,9 @@ def goldens():
 def goldens_heads2():
     path = os.path.join(ROOT, "tests", "golden", "reference_goldens_heads2.pt")
     return torch.load(path, map_location="cpu", weights_only=False)
+
+
+@pytest.fixture(scope="session")
+def goldens_xfusion4():
+    path = os.path.join(ROOT, "tests", "golden", "reference_goldens_xfusion4.pt")
+    return torch.load(path, map_location="cpu", weights_only=False)

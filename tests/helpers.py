@@ -51,6 +51,15 @@ def build_head2_model(cfg):
     return model
 
 
+def build_xfusion4(cfg):
+    """XlinearFusion with the reference's default ctor (4 modalities), seeded and perturbed like the golden generator."""
+    from multimodalfusion_b200.models.model_modules import XlinearFusion
+    torch.manual_seed(cfg["seed"])
+    model = XlinearFusion().eval()
+    cases.perturb_biases(model, cfg["seed"])
+    return model
+
+
 def amil_weights(seq):
     """(W1, b1, Wa, ba, Wb, bb, wc, bc) as detached fp32 tensors from an attention_net_* Sequential."""
     fc, attn = seq[0], seq[3]

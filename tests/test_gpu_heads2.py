@@ -100,3 +100,25 @@ def test_ce_loss_vs_oracle(dev, B, K, alpha):
     got.backward()
     assert abs(got.item() - want.item()) < 1e-5 * max(1.0, abs(want.item()))
     assert rel_err(ho.grad, hr.grad) < 1e-5 and rel_err(So.grad, Sr.grad) < 1e-4
+
+
+@pytest.mark.parametrize("name", list(cases.XFUSION4_CASES))
+def test_xfusion_four_modalities_vs_reference_goldens(dev, goldens_xfusion4, name):
+    """XlinearFusion() with the reference's default num_modalities=4: the 83 521-wide Kronecker product is formed inside
+    the encoder1 kernel (mmf_kron_enc_fwd, m = 4); features, input gradients and every parameter gradient against the
+    reference's fp32 outputs (models/model_modules.py:156-178)."""
+    from helpers import build_xfusion4
+    cfg, gold = cases.XFUSION4_CASES[name], goldens_xfusion4["xfusion4"][name]
+    model = build_xfusion4(cfg).to(dev)
+    vs, proj = cases.embeddings4(cfg)
+    vs = [v.to(dev).requires_grad_(True) for v in vs]
+    feats = model(v_list=vs)
+    assert feats.shape == gold["features"].shape and rel_err(feats, gold["features"]) < 1e-5
+    loss = (feats * proj.to(dev)).sum()
+    assert abs(loss.item() - gold["loss"].item()) < 1e-4
+    model.zero_grad()
+    loss.backward()
+    for v, gd in zip(vs, gold["d_inputs"]):
+        assert rel_err(v.grad, gd) < 1e-4
+    for k, p in model.named_parameters():
+        cases.check_fingerprint(p.grad, gold["grads"][k], 1e-4, f"grad {k}", atol=1e-7)

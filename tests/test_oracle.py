@@ -212,3 +212,20 @@ def test_batchnorm_train_restatement_matches_torch():
     assert torch.allclose(y, yo, rtol=1e-5, atol=1e-5)
     assert torch.allclose(bn.running_mean, 0.1 * mean, rtol=1e-5, atol=1e-6)
     assert torch.allclose(bn.running_var, 0.9 + 0.1 * var_u, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", list(cases.XFUSION4_CASES))
+def test_xfusion_four_modalities_matches_reference(goldens_xfusion4, name):
+    """Drop-in XlinearFusion() (reference default: 4 modalities, 17^4-wide product) draws bit-identical initial weights,
+    and the oracle restatement reproduces the reference's fused features."""
+    from helpers import build_xfusion4
+    cfg, gold = cases.XFUSION4_CASES[name], goldens_xfusion4["xfusion4"][name]
+    model = build_xfusion4(cfg)
+    for k, v in model.state_dict().items():
+        cases.check_fingerprint(v, gold["weights_fp"][k], 0.0, f"weight {k}")
+    assert set(model.state_dict()) == set(gold["weights_fp"])
+    vs, proj = cases.embeddings4(cfg)
+    red, e1, e2 = xfusion_params(model)
+    feats = O.xfusion_forward(vs, red, e1, e2, skip=True)
+    assert rel_err(feats, gold["features"]) < 5e-5
+    assert abs((feats * proj).sum().item() - gold["loss"].item()) < 1e-4
