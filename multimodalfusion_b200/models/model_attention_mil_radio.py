@@ -3,6 +3,7 @@
 
 The four modality bags are never concatenated: the reduce_dim GEMM reads them as four K-segments
 through separate TMA descriptors and writes the bf16 [N,1024] bag the fused AMIL kernel consumes.
+``radio_fusion='tensor'`` runs with the one-name repair of SURVEY.md App. B-3 (`xfusion` -> `radio_xfusion`).
 """
 import torch
 import torch.nn as nn
@@ -60,10 +61,13 @@ class MIL_Attention_fc_surv_radio(MIL_Attention_fc_radio):
         if len(bags) > 1:
             if self.radio_fusion == 'concat':
                 x = SegmentedLinearBf16.apply(self.reduce_dim.weight, self.reduce_dim.bias, *bags)
+            elif self.radio_fusion == 'tensor':
+                # repaired semantics: the reference calls `self.xfusion` (:84) but defines
+                # `radio_xfusion` (:29); read as written otherwise — slice 0 of every modality enters a
+                # 4-way Kronecker fusion (17^4-wide, formed inside the encoder kernel) and the bag has ONE row
+                x = self.radio_xfusion(v_list=[b[0].unsqueeze(0) for b in bags])
             else:
-                # radio_fusion='tensor' is dead code in the reference (calls a missing attribute,
-                # SURVEY.md App. B-3)
-                raise NotImplementedError("radio_fusion='tensor' cannot run in the reference either")
+                raise NotImplementedError(f"radio_fusion={self.radio_fusion!r}")
         else:
             x = bags[0]
         A_raw, M = AmilBranch.pooled(self.attention_net_radio, x, self.training, self.bag_group)

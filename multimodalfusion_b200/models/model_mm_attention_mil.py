@@ -7,8 +7,8 @@ mirror keeps the constructor signature, attribute names and state_dict keys the 
 *defines*, and implements the evidently intended semantics:
   * ``gate_omic`` is accepted and ignored (the base class has no such parameter, :19-23 vs :124);
   * ``size_path`` (:83) is read as ``size_WSI``;
-  * ``self.xfusion`` (:141) is read as ``self.radio_xfusion`` — and since that branch only ever
-    used slice 0 of each modality it stays unsupported (``radio_fusion='tensor'`` raises);
+  * ``self.xfusion`` (:141) is read as ``self.radio_xfusion``; the branch is otherwise run as written
+    (slice 0 of each modality -> 4-way Kronecker fusion -> a one-row radiology bag);
   * ``return_features`` returns the fused embedding ``MM`` (the reference references undefined
     names there, :196-198).
 """
@@ -93,9 +93,12 @@ class MM_MIL_Attention_fc_surv(MM_MIL_Attention_fc):
         if 'radio' in self.mode:
             bags = [kwargs[m] for m in self.modalities]
             if len(bags) > 1:
-                if self.radio_fusion != 'concat':
-                    raise NotImplementedError("radio_fusion='tensor' cannot run in the reference either")
-                x = SegmentedLinearBf16.apply(self.reduce_dim.weight, self.reduce_dim.bias, *bags)
+                if self.radio_fusion == 'concat':
+                    x = SegmentedLinearBf16.apply(self.reduce_dim.weight, self.reduce_dim.bias, *bags)
+                elif self.radio_fusion == 'tensor':     # as written at :141 with the attribute name repaired
+                    x = self.radio_xfusion(v_list=[b[0].unsqueeze(0) for b in bags])
+                else:
+                    raise NotImplementedError(f"radio_fusion={self.radio_fusion!r}")
             else:
                 x = bags[0]
             A_raw['radiology'], emb['radio'] = AmilBranch.pooled(self.attention_net_radio, x, self.training)

@@ -57,6 +57,13 @@ XFUSION4_CASES = {
     "xfusion4_b5": dict(seed=81, B=5),
     "xfusion4_b33": dict(seed=82, B=33),
 }
+# radio_fusion='tensor' with the one-name repair of SURVEY.md App. B-3 (`model.xfusion = model.radio_xfusion`):
+# slice 0 of each modality -> 4-way Kronecker fusion (dim 1024, scale 64 -> 17^4) -> a ONE-row bag -> AMIL -> head.
+# The seed is chosen so that no fc pre-activation of that single row sits within bf16 rounding of zero (the golden
+# generator prints the margin): one flipped ReLU would move a whole row of dW1.
+RADIO_TENSOR_CASES = {
+    "radio_tensor_n12": dict(seed=100, gated=True, dropout=True, K=4, N=12, Y=1, c=0.0, alpha=0.0),
+}
 LOSS_CASES = {
     "nll_b7_a0": dict(seed=51, loss="nll", B=7, K=4, alpha=0.0),
     "nll_b64_k8": dict(seed=52, loss="nll", B=64, K=8, alpha=0.15),

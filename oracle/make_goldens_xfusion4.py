@@ -45,6 +45,35 @@ def main():
             "grads": {k: cases.fingerprint(p.grad) for k, p in model.named_parameters()},
         }
         print("xfusion4", name, float(loss), tuple(feats.shape))
+    # ---- radiology AMIL with radio_fusion='tensor' (attribute-name repair only) ---------------------------
+    from models.model_attention_mil_radio import MIL_Attention_fc_surv_radio
+    from utils.loss_utils import NLLSurvLoss
+    out["radio_tensor"] = {}
+    for name, cfg in cases.RADIO_TENSOR_CASES.items():
+        torch.manual_seed(cfg["seed"])
+        model = MIL_Attention_fc_surv_radio(radio_fusion="tensor", gate_radio=cfg["gated"], dropout=cfg["dropout"],
+                                            n_classes=cfg["K"]).eval()
+        model.xfusion = model.radio_xfusion           # model_attention_mil_radio.py:84 calls the missing name
+        cases.perturb_biases(model, cfg["seed"])
+        bags = cases.radio_bags(cfg)
+        Y, c = cases.labels(cfg)
+        hazards, S, Y_hat, A_raw = model(**bags)
+        M = model(**bags, return_features=True)
+        loss = NLLSurvLoss(alpha=cfg["alpha"])(hazards=hazards, S=S, Y=Y, c=c)
+        model.zero_grad()
+        loss.backward()
+        with torch.no_grad():
+            x1 = model.radio_xfusion(v_list=[bags[m][0].unsqueeze(0) for m in model.modalities])
+            pre = model.attention_net_radio[0](x1)
+        grads = {k: cases.fingerprint(p.grad) for k, p in model.named_parameters() if not k.startswith("xfusion.")}
+        sd = {k: v for k, v in model.state_dict().items() if not k.startswith("xfusion.")}
+        out["radio_tensor"][name] = {
+            "weights_fp": cases.fingerprint_state(sd), "A_raw": A_raw.detach().clone(), "M": M.detach().clone(),
+            "hazards": hazards.detach().clone(), "S": S.detach().clone(), "loss": loss.detach().clone(), "grads": grads,
+            "relu_margin": (pre.abs().min() / pre.abs().max()).item(),
+        }
+        print("radio_tensor", name, float(loss), "fused row max", float(x1.abs().max()),
+              "min|pre|/max|pre|", out["radio_tensor"][name]["relu_margin"])
     dst = os.path.join(os.path.dirname(HERE), "tests", "golden", "reference_goldens_xfusion4.pt")
     torch.save(out, dst)
     print("wrote", dst, os.path.getsize(dst), "bytes")

@@ -25,6 +25,14 @@ def build_radio_model(cfg):
     return model
 
 
+def build_radio_tensor_model(cfg):
+    torch.manual_seed(cfg["seed"])
+    model = MIL_Attention_fc_surv_radio(radio_fusion="tensor", gate_radio=cfg["gated"], dropout=cfg["dropout"],
+                                        n_classes=cfg["K"]).eval()
+    cases.perturb_biases(model, cfg["seed"])
+    return model
+
+
 def build_omic_model(cfg):
     torch.manual_seed(cfg["seed"])
     model = MaxNet(cfg["d_in"], bag_loss=cfg["bag_loss"], n_classes=4).eval()

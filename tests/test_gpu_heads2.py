@@ -122,3 +122,42 @@ def test_xfusion_four_modalities_vs_reference_goldens(dev, goldens_xfusion4, nam
         assert rel_err(v.grad, gd) < 1e-4
     for k, p in model.named_parameters():
         cases.check_fingerprint(p.grad, gold["grads"][k], 1e-4, f"grad {k}", atol=1e-7)
+
+
+@pytest.mark.parametrize("name", list(cases.RADIO_TENSOR_CASES))
+def test_radio_tensor_fusion_vs_repaired_reference(dev, goldens_xfusion4, name):
+    """MIL_Attention_fc_surv_radio(radio_fusion='tensor'): 4-way Kronecker fusion of slice 0 of each modality (fp32
+    kernels) feeding a ONE-row bag through the fused bf16 AMIL kernel, with dX flowing back into the fusion. Against the
+    reference run with its one-name repair (oracle/make_goldens_xfusion4.py): forward 1e-2, gradients 3e-2
+    (bf16 AMIL + bf16 dX in the chain). The attention net gets an exactly-zero gradient from a one-row softmax."""
+    from helpers import build_radio_tensor_model
+    from multimodalfusion_b200.utils import NLLSurvLoss
+    cfg, gold = cases.RADIO_TENSOR_CASES[name], goldens_xfusion4["radio_tensor"][name]
+    model = build_radio_tensor_model(cfg).to(dev)
+    bags = {k: v.to(dev) for k, v in cases.radio_bags(cfg).items()}
+    Y, c = cases.labels(cfg)
+    hazards, S, Y_hat, A_raw = model(**bags)
+    assert A_raw.shape == gold["A_raw"].shape == (1, 1)
+    assert rel_err(A_raw, gold["A_raw"]) < 1e-2
+    assert rel_err(hazards, gold["hazards"]) < 1e-2 and rel_err(S, gold["S"]) < 1e-2
+    M = model(**bags, return_features=True)
+    assert rel_err(M, gold["M"]) < 1e-2
+    assert torch.equal(M.cpu() > 0, gold["M"] > 0), "a ReLU of the single row flipped under bf16 rounding"
+    assert torch.equal(model(**bags, attention_only=True), A_raw)
+    loss = NLLSurvLoss(alpha=cfg["alpha"])(hazards=hazards, S=S, Y=Y.to(dev), c=c.to(dev))
+    assert abs(loss.item() - gold["loss"].item()) < 1e-2 * abs(gold["loss"].item())
+    model.zero_grad()
+    loss.backward()
+    bad = {}
+    for k, p in model.named_parameters():
+        fp = gold["grads"][k]
+        assert p.grad is not None, k
+        ref = fp["vals"]
+        if ref.abs().max().item() <= 1e-6:
+            assert p.grad.abs().max().item() <= 1e-4, k
+            continue
+        got = p.grad.detach().reshape(-1).float().cpu()[cases._sample_idx(p.numel())]
+        err = (got - ref).abs().max().item() / ref.abs().max().item()
+        if err >= 3e-2:
+            bad[k] = err
+    assert not bad, f"gradients beyond 3e-2: {bad}"

@@ -229,3 +229,24 @@ def test_xfusion_four_modalities_matches_reference(goldens_xfusion4, name):
     feats = O.xfusion_forward(vs, red, e1, e2, skip=True)
     assert rel_err(feats, gold["features"]) < 5e-5
     assert abs((feats * proj).sum().item() - gold["loss"].item()) < 1e-4
+
+
+@pytest.mark.parametrize("name", list(cases.RADIO_TENSOR_CASES))
+def test_radio_tensor_fusion_matches_repaired_reference(goldens_xfusion4, name):
+    """radio_fusion='tensor' (one-name repair of the reference): identical initial weights and the
+    oracle composition xfusion(slice 0 of each modality) -> one-row AMIL -> hazard head reproduces the golden."""
+    from helpers import build_radio_tensor_model
+    cfg, gold = cases.RADIO_TENSOR_CASES[name], goldens_xfusion4["radio_tensor"][name]
+    model = build_radio_tensor_model(cfg)
+    assert set(model.state_dict()) == set(gold["weights_fp"])
+    for k, v in model.state_dict().items():
+        cases.check_fingerprint(v, gold["weights_fp"][k], 0.0, f"weight {k}")
+    bags = cases.radio_bags(cfg)
+    red, e1, e2 = xfusion_params(model.radio_xfusion)
+    x1 = O.xfusion_forward([bags[m][0:1] for m in model.modalities], red, e1, e2, skip=False)
+    s, h, _, _ = O.fc_attention(x1, *amil_weights(model.attention_net_radio))
+    M, _, _ = O.softmax_pool(s, h)
+    M = M.reshape(1, -1)
+    hz, S, _ = O.hazard_head(M, model.classifier.weight.detach(), model.classifier.bias.detach())
+    assert rel_err(s.reshape(1, -1), gold["A_raw"]) < 1e-4 and rel_err(M, gold["M"]) < 1e-4
+    assert rel_err(hz, gold["hazards"]) < 1e-4 and rel_err(S, gold["S"]) < 1e-4
