@@ -94,7 +94,10 @@ int launch_gemm2_grouped(const TMapSet& tmA, const TMapSet& tmB, GemmArgs ga, cu
     P.tiles_n = (P.N + BN - 1) / BN;
     tiles_total += ((P.M + 255) / 256) * P.tiles_n;
   }
-  int splits = 74 / tiles_total;
+  // MMF_WGRAD_PAIR_SLOTS (diagnostic): CTA-pair slots to fill. 74 = one full wave (lowest latency of a lone launch);
+  // fewer slots = fewer, longer split-K slices (less reduction traffic and prologue per FLOP) for concurrent lanes
+  static const int slots = [] { const char* e = getenv("MMF_WGRAD_PAIR_SLOTS"); int v = e ? atoi(e) : 74; return v > 0 ? v : 74; }();
+  int splits = slots / tiles_total;
   if (splits < 1) splits = 1;
   if (splits > ga.kb_total) splits = ga.kb_total;
   const int per = (ga.kb_total + splits - 1) / splits;
