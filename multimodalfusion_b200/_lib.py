@@ -15,7 +15,8 @@ import threading
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG_DIR, "csrc")
-LIB_PATH = os.path.join(_PKG_DIR, "libmmf_b200.so")
+# MMF_LIB_PATH: an alternative build of the same library (A/B timing of compile-time kernel variants); must be in-tree
+LIB_PATH = os.environ.get("MMF_LIB_PATH") or os.path.join(_PKG_DIR, "libmmf_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_PKG_DIR), "include", "mmf_b200.h")
 
 NVCC_FLAGS = [

@@ -59,8 +59,19 @@ struct HiddenFusedCfg {
   static constexpr int NH = L / 256;                       // N = 256 MMAs per k-step
   static constexpr uint32_t B_STAGE = NH * 16384u;         // this CTA's half of one Wab k-block
   static constexpr uint32_t A_STAGE = GATED ? 32768u : 16384u;
-  static constexpr int NSB = 4;
-  static constexpr int NSA = 2;
+  // Ring depths (both stages are 32 KB at L = 512, gated). The mainloop is a dependency cycle per A stage — tile
+  // landed -> transform (until the slowest of 32 worker warps has arrived, ~3k cycles) -> MMAs (~2k) -> commit ->
+  // TMA reload (~2k) — of ~7.3k cycles; with 2 A stages a slice took 3.7-4.4k cycles (measured, tools/phase_gemm.py)
+  // against ~2k of MMA. 3 A stages bring the cycle under the transform / MMA time; the L2-hot Wab stream needs
+  // less cover (one stage is consumed every ~1.2k cycles, reload ~1k), so it gives up one stage.
+#ifndef MMF_HIDDEN_NSB
+#define MMF_HIDDEN_NSB 3
+#endif
+#ifndef MMF_HIDDEN_NSA
+#define MMF_HIDDEN_NSA 3
+#endif
+  static constexpr int NSB = MMF_HIDDEN_NSB;
+  static constexpr int NSA = MMF_HIDDEN_NSA;
   static constexpr uint32_t RING_BYTES = NSB * B_STAGE + NSA * A_STAGE;
   static constexpr uint32_t STAGING = 128u * L * 2u;       // dU tile
   static constexpr uint32_t POOL = RING_BYTES > STAGING ? RING_BYTES : STAGING;
@@ -390,9 +401,10 @@ amil_hidden_fused_kernel(const __grid_constant__ CUtensorMap tmAG,   // stash fp
     tc_fence_after();
     if (e == 0) MMF_STAMP(a, 6);
     // (the dG stores of warp 2 have finished reading the A ring: bar_aempty completed before the last MMAs could
-    //  be issued ... except the final NSA stages: wait for their store thread explicitly)
-    mbar_wait(smem_u32(&bar_aempty[(C::NKP - 1) % C::NSA]), ((C::NKP - 1) / C::NSA) & 1);
-    if (C::NKP > 1) mbar_wait(smem_u32(&bar_aempty[(C::NKP - 2) % C::NSA]), ((C::NKP - 2) / C::NSA) & 1);
+    //  be issued ... except the final NSA slices: wait for their store thread explicitly)
+#pragma unroll
+    for (int j = 1; j <= C::NSA; ++j)
+      if (C::NKP >= j) mbar_wait(smem_u32(&bar_aempty[(C::NKP - j) % C::NSA]), ((C::NKP - j) / C::NSA) & 1);
     named_bar_sync(1, HIDDEN_ET);
     float v[2][32];
     tmem_ld32(tmem + ((q * 32u) << 16) + part * PIECES * 32, v[0]);
