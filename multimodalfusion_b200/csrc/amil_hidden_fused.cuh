@@ -25,7 +25,7 @@
 //   vectors: dM[L], wc[D], ds[128], p[128], mask[128][L/32], colsum scratch [3D]
 // Barriers: b_full[s] leader copy (pair TMA), b_empty[s] / a_empty[s] / acc per CTA (multicast commits;
 // a_empty also counts the dG store's read-completion), a_full[s] per CTA (local TMA), a_ready[s] leader
-// copy, one arrive per epilogue warp of either CTA (16).
+// copy, one arrive per CTA relayed by its dG-store thread (MMF_HIDDEN_RELAY) or one per worker warp of either CTA.
 #pragma once
 #include <cuda_fp16.h>
 
@@ -82,6 +82,13 @@ struct HiddenFusedCfg {
   static constexpr uint32_t SMEM_BYTES = POOL + VEC_BYTES + 1024u;
 };
 
+// MMF_HIDDEN_RELAY = 1: the worker warps publish a transformed stage with ONE local arrive (bar_astore); the CTA's
+// dG-store thread, which waits on that barrier anyway, relays a single cluster-scope arrive to the leader's bar_aready.
+// = 0: every worker warp of either CTA arrives on the leader's barrier itself (32 release.cluster arrives per slice,
+// each draining the warp's shared-memory writes at cluster scope on the transform's critical path).
+#ifndef MMF_HIDDEN_RELAY
+#define MMF_HIDDEN_RELAY 1
+#endif
 constexpr int HIDDEN_EW = 16;                         // worker (phase A / transform / epilogue) warps: the CUDA-core
                                                      // phases are latency-bound, 16 warps hide ~2x what 8 did
 constexpr int HIDDEN_ET = HIDDEN_EW * 32;             // worker threads
@@ -124,7 +131,7 @@ amil_hidden_fused_kernel(const __grid_constant__ CUtensorMap tmAG,   // stash fp
     for (int s = 0; s < C::NSB; ++s) { mbar_init(smem_u32(&bar_bfull[s]), 1); mbar_init(smem_u32(&bar_bempty[s]), 1); }
     for (int s = 0; s < C::NSA; ++s) {
       mbar_init(smem_u32(&bar_afull[s]), 1);
-      mbar_init(smem_u32(&bar_aready[s]), 2 * HIDDEN_EW);
+      mbar_init(smem_u32(&bar_aready[s]), MMF_HIDDEN_RELAY ? 2 : 2 * HIDDEN_EW);
       mbar_init(smem_u32(&bar_aempty[s]), 2);   // MMA commit + the dG store's read-completion
       mbar_init(smem_u32(&bar_astore[s]), HIDDEN_EW);
     }
@@ -177,9 +184,11 @@ amil_hidden_fused_kernel(const __grid_constant__ CUtensorMap tmAG,   // stash fp
   } else if (warp == 2 && lane == 0) {
     // =============================== dG store thread (each CTA) =========================
     // dG -> global for the wgrad GEMM, straight from the transformed A stage (same swizzled tile layout)
+    const uint32_t a_ready_leader = mapa_cluster(smem_u32(&bar_aready[0]), 0);
     for (int kp = 0; kp < C::NKP; ++kp) {
       const int s = kp % C::NSA;
       mbar_wait(smem_u32(&bar_astore[s]), (kp / C::NSA) & 1);
+      if (MMF_HIDDEN_RELAY) mbar_arrive_cluster(a_ready_leader + s * 8u);   // this CTA's half of the stage is ready
       tma_store_2d(&tmDG, a_ring + s * C::A_STAGE, kp * 64, (int)row0);
       if (GATED) tma_store_2d(&tmDG, a_ring + s * C::A_STAGE + 16384, D + kp * 64, (int)row0);
       tma_store_commit();
@@ -253,31 +262,41 @@ amil_hidden_fused_kernel(const __grid_constant__ CUtensorMap tmAG,   // stash fp
           dA_l = a.dA_raw ? __ldg(a.dA_raw + row) : 0.f;
         }
       }
-#pragma unroll 1
-      for (int r0 = (int)ew * ROWS_PER_WARP; r0 < (int)(ew + 1) * ROWS_PER_WARP; r0 += 4) {
-        uint4 hv[4][HJ];
+      // software pipeline over the warp's rows, PA_STEP rows per step: the loads of step i + 1 are in flight while
+      // step i is reduced (the first version loaded 4 rows, waited a full L2 round trip, computed, and only then
+      // issued the next 4 loads: two exposed round trips per warp)
+      constexpr int PA_STEP = 2, PA_STEPS = ROWS_PER_WARP / PA_STEP;
+      static_assert(ROWS_PER_WARP % PA_STEP == 0, "phase A step");
+      uint4 hv[2][PA_STEP][HJ];
+      auto pa_load = [&](int step, int buf) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const long long row = row0 + r0 + u;
+        for (int u = 0; u < PA_STEP; ++u) {
+          const long long row = row0 + (long long)ew * ROWS_PER_WARP + step * PA_STEP + u;
           const uint4* hp = reinterpret_cast<const uint4*>(a.H + (row < a.N ? row : 0) * L);
 #pragma unroll
-          for (int j = 0; j < HJ; ++j) hv[u][j] = __ldg(hp + lane + 32 * j);
+          for (int j = 0; j < HJ; ++j) hv[buf][u][j] = __ldg(hp + lane + 32 * j);
         }
+      };
+      pa_load(0, 0);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int r = r0 + u;
+      for (int step = 0; step < PA_STEPS; ++step) {
+        const int buf = step & 1;
+        if (step + 1 < PA_STEPS) pa_load(step + 1, buf ^ 1);
+#pragma unroll
+        for (int u = 0; u < PA_STEP; ++u) {
+          const int r = (int)ew * ROWS_PER_WARP + step * PA_STEP + u;
           const long long row = row0 + r;
           const bool ok = row < a.N;
-          float t = 0.f;
+          float t0 = 0.f, t1 = 0.f;   // two partial sums: halves the dependent FMA chain
 #pragma unroll
           for (int j = 0; j < HJ; ++j) {
-            const uint32_t w[4] = {hv[u][j].x, hv[u][j].y, hv[u][j].z, hv[u][j].w};
+            const uint32_t w[4] = {hv[buf][u][j].x, hv[buf][u][j].y, hv[buf][u][j].z, hv[buf][u][j].w};
             uint32_t byte = 0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const float2 f = unpack_bf16x2(w[k]);
-              t = fmaf(f.x, dmv[j][2 * k], t);
-              t = fmaf(f.y, dmv[j][2 * k + 1], t);
+              t0 = fmaf(f.x, dmv[j][2 * k], t0);
+              t1 = fmaf(f.y, dmv[j][2 * k + 1], t1);
               byte |= (uint32_t)(f.x > 0.f) << (2 * k) | (uint32_t)(f.y > 0.f) << (2 * k + 1);
             }
             uint32_t word = ok ? byte << (8 * (lane & 3)) : 0u;
@@ -285,9 +304,9 @@ amil_hidden_fused_kernel(const __grid_constant__ CUtensorMap tmAG,   // stash fp
             word |= __shfl_xor_sync(0xffffffffu, word, 2);
             if ((lane & 3) == 0) s_mask[r * (L / 32) + (lane >> 2) + 8 * j] = word;
           }
-          t = warp_sum(t);
-          const float s_raw = __shfl_sync(0xffffffffu, s_raw_l, r - (int)ew * ROWS_PER_WARP);
-          const float dA = __shfl_sync(0xffffffffu, dA_l, r - (int)ew * ROWS_PER_WARP);
+          const float t = warp_sum(t0 + t1);
+          const float s_raw = __shfl_sync(0xffffffffu, s_raw_l, step * PA_STEP + u);
+          const float dA = __shfl_sync(0xffffffffu, dA_l, step * PA_STEP + u);
           if (lane == 0) {
             float p = 0.f, ds = 0.f;
             if (ok) {
@@ -357,10 +376,14 @@ amil_hidden_fused_kernel(const __grid_constant__ CUtensorMap tmAG,   // stash fp
           const float ka = (!DROP || drop_keep(ab, (d0 & 15) + k)) ? attn_scale : 0.f;
           const float kg = (GATED && DROP) ? (drop_keep(gb, (d0 & 15) + k) ? attn_scale : 0.f) : 1.f;
           const float ad = aa[k] * ka, gd = gg[k] * kg;
-          const float dq = ds * wcv[k];
           acc_wc[k] = fmaf(ds, ad * gd, acc_wc[k]);
-          da[k] = dq * gd * ka * (1.f - aa[k] * aa[k]);
-          dg[k] = GATED ? dq * ad * kg * gg[k] * (1.f - gg[k]) : 0.f;
+          // dG_a = dq gd ka (1 - a^2) and dG_g = dq ad kg g (1 - g), factored through q = dq gd (gd = g kg):
+          //   dG_a = ka (q - (q a) a),  dG_g = (q ad) - (q ad) g        (9 instead of 12 operations per element pair)
+          const float q = ds * wcv[k] * gd;
+          const float qa = q * aa[k];
+          const float qad = DROP ? q * ad : qa;
+          da[k] = ka * fmaf(-qa, aa[k], q);
+          dg[k] = GATED ? fmaf(-qad, gg[k], qad) : 0.f;
           acc_a[k] += da[k];
           acc_g[k] += dg[k];
         }
@@ -371,8 +394,8 @@ amil_hidden_fused_kernel(const __grid_constant__ CUtensorMap tmAG,   // stash fp
       __syncwarp();
       if (e == 0 && kp < 3) MMF_STAMP(a, 9 + 2 * kp);
       if (lane == 0) {
-        mbar_arrive_cluster(a_ready_leader + s * 8u);   // bar_aready[s] of the leader: the MMA may consume the stage
-        mbar_arrive(smem_u32(&bar_astore[s]));          // and the store thread (warp 2) may write it out as dG
+        if (!MMF_HIDDEN_RELAY) mbar_arrive_cluster(a_ready_leader + s * 8u);   // bar_aready[s] of the leader
+        mbar_arrive(smem_u32(&bar_astore[s]));   // the store thread (warp 2) relays to the MMA and writes the stage out as dG
       }
       // column sums of this slice: reduce over the warp's 8 row lanes, then 4 row quarters meet in shared memory
 #pragma unroll
