@@ -57,6 +57,16 @@ constexpr uint32_t AMIL2_EPI_THREADS = 256;
 // DROPH / DROPA: train-mode dropout on h / on the attention branches, compile-time: with run-time flags the mask
 // selection (shift, and, compare, select per element and branch) was executed even with dropout off and made up
 // 10 of the ~22 instructions per element pair of the gate epilogue, which bounds the GEMM2 phase (issue-bound).
+// MMF_TILE2_RELAY (round-2 candidate, compiled but NOT yet timed or parity-run on a GPU, hence default 0): the epilogue
+// warps signal "H tile written" and "GEMM2 chunk buffer drained" with a CTA-local arrive, and the otherwise idle warp 3
+// relays ONE cluster-scope arrive per CTA to the leader's barrier — the change that took 11 % off
+// amil_hidden_fused_kernel (profiles/r01i_ncu_full_summary.md). Today every epilogue warp executes
+// mbarrier.arrive.release.cluster itself; in the training form that release follows the st.global stash stores of the
+// chunk and has to wait for them to reach L2 (3 chunks per tile).
+#ifndef MMF_TILE2_RELAY
+#define MMF_TILE2_RELAY 0
+#endif
+
 template <int L, int D, bool GATED, int MODE, bool DROPH, bool DROPA>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AMIL2_THREADS, 1)
 amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
@@ -67,6 +77,9 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   __shared__ __align__(8) uint64_t bar_full1[C::NS1], bar_empty1[C::NS1];
   __shared__ __align__(8) uint64_t bar_full2[C::NS2], bar_empty2[C::NS2];
   __shared__ __align__(8) uint64_t bar_acc1, bar_h, bar_acc2_full[2], bar_acc2_empty[2];
+#if MMF_TILE2_RELAY
+  __shared__ __align__(8) uint64_t bar_h_local, bar_acc2_done[2];   // CTA-local stages of the relayed signals
+#endif
   __shared__ uint32_t tmem_base_slot;
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -86,8 +99,15 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     for (int s = 0; s < C::NS1; ++s) { mbar_init(smem_u32(&bar_full1[s]), 1); mbar_init(smem_u32(&bar_empty1[s]), 1); }
     for (int s = 0; s < C::NS2; ++s) { mbar_init(smem_u32(&bar_full2[s]), 1); mbar_init(smem_u32(&bar_empty2[s]), 1); }
     mbar_init(smem_u32(&bar_acc1), 1);
-    mbar_init(smem_u32(&bar_h), 16);
-    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&bar_acc2_full[b]), 1); mbar_init(smem_u32(&bar_acc2_empty[b]), 16); }
+    mbar_init(smem_u32(&bar_h), MMF_TILE2_RELAY ? 2 : 16);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&bar_acc2_full[b]), 1);
+      mbar_init(smem_u32(&bar_acc2_empty[b]), MMF_TILE2_RELAY ? 2 : 16);
+    }
+#if MMF_TILE2_RELAY
+    mbar_init(smem_u32(&bar_h_local), 8);
+    for (int b = 0; b < 2; ++b) mbar_init(smem_u32(&bar_acc2_done[b]), 8);
+#endif
     fence_barrier_init();
     tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmWab);
   }
@@ -185,6 +205,17 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       umma_commit_pair_mc(smem_u32(&bar_acc2_full[buf]), 3);
     }
     MMF_STAMP(a, 8);
+#if MMF_TILE2_RELAY
+  } else if (warp == 3 && lane == 0) {
+    // =============================== relay thread (both CTAs) ==========================
+    mbar_wait(smem_u32(&bar_h_local), 0);
+    mbar_arrive_cluster(mapa_cluster(smem_u32(&bar_h), 0));
+    for (int c = 0; c < C::NCH; ++c) {
+      const int buf = c & 1;
+      mbar_wait(smem_u32(&bar_acc2_done[buf]), (c >> 1) & 1);
+      mbar_arrive_cluster(mapa_cluster(smem_u32(&bar_acc2_empty[buf]), 0));
+    }
+#endif
   } else if (warp >= 4) {
     // =============================== epilogue warps (both CTAs) ========================
     const uint32_t q = warp & 3;
@@ -286,7 +317,11 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     fence_proxy_async_smem();
     tc_fence_before();
     __syncwarp();
+#if MMF_TILE2_RELAY
+    if (lane == 0) mbar_arrive(smem_u32(&bar_h_local));
+#else
     if (lane == 0) mbar_arrive_cluster(h_ready_leader);
+#endif
     if (e == 0) MMF_STAMP(a, 11);
 
     if (MODE == AMIL_BWD_GATE) sS[half * 128 + r] = t_i;
@@ -421,7 +456,11 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
+#if MMF_TILE2_RELAY
+      if (lane == 0) mbar_arrive(smem_u32(&bar_acc2_done[buf]));
+#else
       if (lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&bar_acc2_empty[buf]), 0));
+#endif
     }
 
     if (e == 0) MMF_STAMP(a, 12);
