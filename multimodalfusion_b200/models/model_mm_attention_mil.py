@@ -10,7 +10,11 @@ mirror keeps the constructor signature, attribute names and state_dict keys the 
   * ``self.xfusion`` (:141) is read as ``self.radio_xfusion``; the branch is otherwise run as written
     (slice 0 of each modality -> 4-way Kronecker fusion -> a one-row radiology bag);
   * ``return_features`` returns the fused embedding ``MM`` (the reference references undefined
-    names there, :196-198).
+    names there, :196-198);
+  * the ``captum*`` entry points (:202-396) keep the reference's arithmetic as written, including the
+    soft-max over a singleton dimension that turns their pooling into a plain sum.
+Parity is pinned against the reference itself made runnable WITHOUT editing it (oracle/make_goldens_mm.py:
+the missing module global ``size_path`` is injected and the base-class constructor is called directly).
 """
 import torch
 import torch.nn as nn
@@ -125,15 +129,84 @@ class MM_MIL_Attention_fc_surv(MM_MIL_Attention_fc):
         else:
             raise NotImplementedError(f"mode {self.mode!r} needs at least two modalities")
         vs = [emb[k] for k in order]
-        if self.fusion == 'tensor':
-            MM = self.mm(v_list=vs)
-            hid = Dense.apply(MM, self.classifier[0].weight, self.classifier[0].bias, ACT_RELU)
-            hid = self.classifier[2](hid)
-            Wk, bk = self.classifier[3].weight, self.classifier[3].bias
-        else:
-            MM = torch.cat(vs, dim=1)
-            hid, Wk, bk = MM, self.classifier.weight, self.classifier.bias
+        MM, hid, Wk, bk = self._fuse(vs)
         if kwargs.get('return_features'):
             return MM
         hazards, S, Y_hat = HazardHead.apply(hid, Wk, bk)
         return hazards, S, Y_hat, A_raw
+
+    def _fuse(self, vs):
+        """Fusion + the classifier's hidden layer: returns (MM, input of the hazard layer, its weight, its bias)."""
+        if self.fusion == 'tensor':
+            MM = self.mm(v_list=vs)
+            hid = Dense.apply(MM, self.classifier[0].weight, self.classifier[0].bias, ACT_RELU)
+            hid = self.classifier[2](hid)
+            return MM, hid, self.classifier[3].weight, self.classifier[3].bias
+        MM = torch.cat(vs, dim=1)
+        return MM, MM, self.classifier.weight, self.classifier.bias
+
+    # ---- Captum entry points (models/model_mm_attention_mil.py:202-396) ------------------------------------------
+    # Positional, batched 3-D bag inputs [B, N, 1024] (integrated gradients stacks n_steps interpolated copies of one
+    # patient) and 2-D omics [B, d]; they return risk [B] = -sum_k S_k. Reference semantics kept AS WRITTEN: the
+    # attention scores are transposed to [B, 1, N] and soft-maxed over dim=1 — a singleton — so every weight is 1 and
+    # the "attention pooling" is a plain SUM over the instances (:222-226, :265-269, :280-285, :364-369); the attention
+    # net therefore does not influence the returned risk. Everything runs in fp32 on the functor SGEMM kernels
+    # (Dense / KronEncoder / HazardHead), which provide dX: attributions differentiate w.r.t. the inputs.
+    def _captum_sum_pool(self, seq, x):
+        if x.dim() != 3:
+            raise ValueError("captum entry points take batched bags [B, N, 1024]")
+        B, N, width = x.shape
+        h = Dense.apply(x.reshape(B * N, width).float(), seq[0].weight, seq[0].bias, ACT_RELU)
+        h = seq[2](h)                                   # nn.Dropout(0.25): identity in eval
+        return h.view(B, N, -1).sum(dim=1)
+
+    def _captum_radio(self, bags):
+        if 'radio' not in self.mode:
+            raise NotImplementedError('use another captum function')
+        if self.radio_fusion != 'concat':
+            # the reference's tensor branch (:218-220) feeds 3-D slices into XlinearFusion's 2-D torch.cat / bmm chain
+            raise NotImplementedError("captum with radio_fusion='tensor' cannot run in the reference either")
+        x = torch.cat([b.float() for b in bags], dim=2)
+        B, N, width = x.shape
+        x = Dense.apply(x.reshape(B * N, width), self.reduce_dim.weight, self.reduce_dim.bias, ACT_NONE)
+        return self._captum_sum_pool(self.attention_net_radio, x.view(B, N, -1))
+
+    def _captum_path(self, h_path):
+        if 'path' not in self.mode:
+            raise NotImplementedError('use another captum function')
+        return self._captum_sum_pool(self.attention_net_WSI, h_path)
+
+    def _captum_omic(self, h_omic):
+        if 'omic' not in self.mode:
+            raise NotImplementedError('use another captum function')
+        o = h_omic.float()
+        for block in self.fc_omic:
+            o = snn_block_forward(block, o)
+        return o
+
+    def _captum_risk(self, vs):
+        _, hid, Wk, bk = self._fuse(vs)
+        _, S, _ = HazardHead.apply(hid, Wk, bk)
+        return -torch.sum(S, dim=1)
+
+    def captum_radio_omic(self, T1, T2, T1Gd, FLAIR, h_omic):
+        given = dict(T1=T1, T2=T2, T1Gd=T1Gd, FLAIR=FLAIR)
+        return self._captum_risk([self._captum_radio([given[m] for m in self.modalities]), self._captum_omic(h_omic)])
+
+    def captum(self, T1, T2, T1Gd, FLAIR, h_path, h_omic):
+        given = dict(T1=T1, T2=T2, T1Gd=T1Gd, FLAIR=FLAIR)
+        return self._captum_risk([self._captum_radio([given[m] for m in self.modalities]), self._captum_path(h_path),
+                                  self._captum_omic(h_omic)])
+
+    def captum_radio_path(self, T1, T2, T1Gd, FLAIR, h_path):
+        given = dict(T1=T1, T2=T2, T1Gd=T1Gd, FLAIR=FLAIR)
+        M_radio, M_path = self._captum_radio([given[m] for m in self.modalities]), self._captum_path(h_path)
+        if 'omic' in self.mode:
+            raise NotImplementedError('use another captum function')
+        return self._captum_risk([M_radio, M_path])
+
+    def captum_path_omic(self, h_omic, h_path):
+        M_path, O = self._captum_path(h_path), self._captum_omic(h_omic)
+        if 'radio' in self.mode:
+            raise NotImplementedError('use another captum function')
+        return self._captum_risk([O, M_path])

@@ -64,6 +64,22 @@ XFUSION4_CASES = {
 RADIO_TENSOR_CASES = {
     "radio_tensor_n12": dict(seed=100, gated=True, dropout=True, K=4, N=12, Y=1, c=0.0, alpha=0.0),
 }
+# MM_MIL_Attention_fc_surv end to end against the reference made runnable without editing it
+# (oracle/make_goldens_mm.py). Nr / Np = radiology / pathology bag sizes, d = omics width.
+MM_CASES = {
+    "mm_tensor_rpo": dict(seed=111, mode="radio_path_omic", fusion="tensor", Nr=23, Np=300, d=36, Y=2, c=0.0, alpha=0.0),
+    "mm_concat_rpo": dict(seed=112, mode="radio_path_omic", fusion="concat", Nr=40, Np=157, d=36, Y=0, c=1.0, alpha=0.15),
+    "mm_tensor_po": dict(seed=113, mode="path_omic", fusion="tensor", Nr=0, Np=260, d=80, Y=3, c=0.0, alpha=0.0),
+    "mm_tensor_ro": dict(seed=114, mode="radio_omic", fusion="tensor", Nr=31, Np=0, d=36, Y=1, c=0.0, alpha=0.0),
+    "mm_tensor_rp": dict(seed=115, mode="radio_path", fusion="tensor", Nr=17, Np=129, d=36, Y=1, c=1.0, alpha=0.4),
+}
+# the captum* entry points: batched 3-D bags [B, N, 1024] (sum pooling as written in the reference)
+CAPTUM_CASES = {
+    "captum_rpo": dict(seed=121, fn="captum", mode="radio_path_omic", fusion="tensor", B=3, Nr=9, Np=40, d=36),
+    "captum_ro": dict(seed=122, fn="captum_radio_omic", mode="radio_omic", fusion="tensor", B=4, Nr=12, Np=0, d=36),
+    "captum_rp": dict(seed=123, fn="captum_radio_path", mode="radio_path", fusion="tensor", B=2, Nr=7, Np=33, d=36),
+    "captum_po_concat": dict(seed=124, fn="captum_path_omic", mode="path_omic", fusion="concat", B=5, Nr=0, Np=21, d=80),
+}
 LOSS_CASES = {
     "nll_b7_a0": dict(seed=51, loss="nll", B=7, K=4, alpha=0.0),
     "nll_b64_k8": dict(seed=52, loss="nll", B=64, K=8, alpha=0.15),
@@ -140,6 +156,32 @@ def embeddings4(cfg):
     h4 = torch.randn(cfg["B"], 256, generator=g).abs() * 0.5
     proj = torch.randn(256, generator=g) / 16.0
     return [hr, hp, ho, h4], proj
+
+
+def mm_inputs(cfg):
+    """kwargs of MM_MIL_Attention_fc_surv.forward for one patient."""
+    kw = {}
+    if "radio" in cfg["mode"]:
+        kw.update(radio_bags(dict(N=cfg["Nr"], seed=cfg["seed"])))
+    if "path" in cfg["mode"]:
+        kw["path_features"] = features(cfg["Np"], cfg["seed"] + 7)
+    if "omic" in cfg["mode"]:
+        kw["genomic_features"] = torch.randn(cfg["d"], generator=_gen(cfg["seed"] + 8))
+    return kw
+
+
+def captum_inputs(cfg):
+    """Positional inputs of the captum entry point named cfg['fn'] (batched bags are scaled down: the reference pools
+    by SUMMING the instances) and the weights of the scalar objective sum(risk * w)."""
+    g = _gen(cfg["seed"] + 9)
+    B = cfg["B"]
+    radio = [0.06 * torch.randn(B, cfg["Nr"], 1024, generator=g).abs() for _ in range(4)] if cfg["Nr"] else []
+    path = 0.03 * torch.randn(B, cfg["Np"], 1024, generator=g).abs() if cfg["Np"] else None
+    omic = torch.randn(B, cfg["d"], generator=g)
+    w = torch.arange(1, B + 1, dtype=torch.float32)
+    args = {"captum": radio + [path, omic], "captum_radio_omic": radio + [omic], "captum_radio_path": radio + [path],
+            "captum_path_omic": [omic, path]}[cfg["fn"]]
+    return args, w
 
 
 def nll_inputs(cfg):

@@ -39,3 +39,9 @@ def goldens_heads2():
 def goldens_xfusion4():
     path = os.path.join(ROOT, "tests", "golden", "reference_goldens_xfusion4.pt")
     return torch.load(path, map_location="cpu", weights_only=False)
+
+
+@pytest.fixture(scope="session")
+def goldens_mm():
+    path = os.path.join(ROOT, "tests", "golden", "reference_goldens_mm.pt")
+    return torch.load(path, map_location="cpu", weights_only=False)

@@ -33,6 +33,18 @@ def build_radio_tensor_model(cfg):
     return model
 
 
+def build_mm_model(cfg):
+    """MM_MIL_Attention_fc_surv seeded and perturbed like oracle/make_goldens_mm.py builds the reference's."""
+    from multimodalfusion_b200.models.model_mm_attention_mil import MM_MIL_Attention_fc_surv
+    torch.manual_seed(cfg["seed"])
+    model = MM_MIL_Attention_fc_surv(input_dim=cfg["d"], radio_fusion="concat", fusion=cfg["fusion"], gate=True,
+                                     gate_path=True, gate_omic=True, gate_radio=True, model_size_radio="small",
+                                     model_size_wsi="small", model_size_omic="small", dropout=False, n_classes=4,
+                                     mode=cfg["mode"]).eval()
+    cases.perturb_biases(model, cfg["seed"])
+    return model
+
+
 def build_omic_model(cfg):
     torch.manual_seed(cfg["seed"])
     model = MaxNet(cfg["d_in"], bag_loss=cfg["bag_loss"], n_classes=4).eval()
