@@ -35,6 +35,15 @@ def _segmented_linear(W, b, *segs):
     return torch.cat([s.float() for s in segs], dim=1) @ W.t() + b
 
 
+def _batchnorm(x, gamma, beta, running_mean, running_var, train, momentum, eps):
+    assert not train, "stand-in covers eval mode"
+    return O.batchnorm1d_eval(x, gamma, beta, running_mean, running_var, eps)
+
+
+def _highway_mix(g, n, l):
+    return g * n + (1 - g) * l
+
+
 def _pooled(seq, x, training, group=None):
     assert not training and group is None, "stand-in covers eval mode, single process"
     fc, attn = seq[0], seq[3]
@@ -45,15 +54,19 @@ def _pooled(seq, x, training, group=None):
 
 @contextlib.contextmanager
 def oracle_kernels():
-    """Route Dense / KronEncoder / HazardHead / SegmentedLinearBf16 / the fused AMIL pooling through fp32 torch ops."""
+    """Route Dense / KronEncoder / HazardHead / SegmentedLinearBf16 / BatchNorm1dFn / HighwayMix / the fused AMIL pooling
+    through fp32 torch ops."""
     saved = [(A.Dense, A.Dense.__dict__.get("apply")), (A.KronEncoder, A.KronEncoder.__dict__.get("apply")),
              (A.HazardHead, A.HazardHead.__dict__.get("apply")),
-             (A.SegmentedLinearBf16, A.SegmentedLinearBf16.__dict__.get("apply"))]
+             (A.SegmentedLinearBf16, A.SegmentedLinearBf16.__dict__.get("apply")),
+             (A.BatchNorm1dFn, A.BatchNorm1dFn.__dict__.get("apply")), (A.HighwayMix, A.HighwayMix.__dict__.get("apply"))]
     pooled = MM.AmilBranch.__dict__["pooled"]
     A.Dense.apply = staticmethod(_dense)
     A.KronEncoder.apply = staticmethod(_kron)
     A.HazardHead.apply = staticmethod(_hazard)
     A.SegmentedLinearBf16.apply = staticmethod(_segmented_linear)
+    A.BatchNorm1dFn.apply = staticmethod(_batchnorm)
+    A.HighwayMix.apply = staticmethod(_highway_mix)
     MM.AmilBranch.pooled = staticmethod(_pooled)
     try:
         yield
