@@ -16,7 +16,8 @@ import threading
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG_DIR, "csrc")
 # MMF_LIB_PATH: an alternative build of the same library (A/B timing of compile-time kernel variants); must be in-tree
-LIB_PATH = os.environ.get("MMF_LIB_PATH") or os.path.join(_PKG_DIR, "libmmf_b200.so")
+DEFAULT_LIB_PATH = os.path.join(_PKG_DIR, "libmmf_b200.so")      # what build() writes
+LIB_PATH = os.environ.get("MMF_LIB_PATH") or DEFAULT_LIB_PATH      # what lib() loads
 HEADER_PATH = os.path.join(os.path.dirname(_PKG_DIR), "include", "mmf_b200.h")
 
 NVCC_FLAGS = [
@@ -42,30 +43,30 @@ def _sources():
 
 
 def needs_build() -> bool:
-    if not os.path.exists(LIB_PATH):
+    if not os.path.exists(DEFAULT_LIB_PATH):
         return True
-    t = os.path.getmtime(LIB_PATH)
+    t = os.path.getmtime(DEFAULT_LIB_PATH)
     return any(os.path.getmtime(s) > t for s in _sources())
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/capi.cu for sm_100a into the in-tree shared object."""
     if not force and not needs_build():
-        return LIB_PATH
+        return DEFAULT_LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise MmfError("nvcc not found: cannot build libmmf_b200.so")
-    tmp = LIB_PATH + ".tmp"
+    tmp = DEFAULT_LIB_PATH + ".tmp"
     cmd = [nvcc, *NVCC_FLAGS, "-o", tmp, os.path.join(_CSRC, "capi.cu")]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise MmfError("nvcc failed:\n" + r.stdout + r.stderr)
-    os.replace(tmp, LIB_PATH)
+    os.replace(tmp, DEFAULT_LIB_PATH)
     if verbose:
         print(r.stderr)
-    return LIB_PATH
+    return DEFAULT_LIB_PATH
 
 
 class AmilWeights(C.Structure):
