@@ -1,5 +1,6 @@
-"""Fusion heads over pre-extracted 256-d embeddings with a scalar risk output — drop-in for
-models/coxranking_models_pretrained.py (:62-183): `kronecker` (:95-97,171-180), `early-fcnn` / `late-fcnn`
+"""Heads over pre-extracted 256-d embeddings with a scalar risk output — drop-in for
+models/coxranking_models_pretrained.py: `unimonal_pretrained` (:14-58: fcnn / highway / residual on ONE modality) and
+`multimodal_pretrained` (:62-183): `kronecker` (:95-97,171-180), `early-fcnn` / `late-fcnn`
 (:80-86,137-140,166), `early-highway` / `late-highway` (:87-94,141-144,167-168)."""
 import torch
 import torch.nn as nn
@@ -8,7 +9,7 @@ import torch.nn.functional as F
 from .._lib import ACT_NONE
 from ..autograd import Dense
 from ..utils.utils import initialize_weights
-from .model_modules import Highway, XlinearFusion, fcnn_forward
+from .model_modules import Highway, Residual, XlinearFusion, fcnn_forward
 
 
 def _pick(mode, h_radio, h_path, h_omic):
@@ -38,6 +39,46 @@ def _pick_late(mode, outs):
     if o and p:
         return [outs['omic'], outs['path']]
     raise NotImplementedError(f"mode {mode!r} needs at least two modalities")
+
+
+def _unimodal_input(mode, kwargs):
+    """h_path / h_radio / h_omic by mode, as the reference selects it (:42-47)."""
+    if mode not in ('path', 'radio', 'omic'):
+        raise NotImplementedError(f"mode={mode!r}")       # the reference hits an UnboundLocalError here
+    return kwargs['h_' + mode].float()
+
+
+class unimonal_pretrained(nn.Module):
+    def __init__(self, dropout=True, n_classes=4, mode='radio', train_type=None, bag_loss=None, n_layers=1):
+        super().__init__()
+        self.n_classes, self.train_type, self.bag_loss = n_classes, train_type, bag_loss
+        self.mode, self.n_layers = mode, n_layers
+        if train_type == 'fcnn':
+            self.classifier = nn.Sequential(nn.Linear(256, 128), nn.BatchNorm1d(128), nn.ReLU(), nn.Dropout(0.7),
+                                            nn.Linear(128, 1))
+        elif train_type == 'highway':
+            self.highway = Highway(256, n_layers, F.relu)
+            self.classifier = nn.Linear(256, 1)
+        elif train_type == 'residual':
+            self.residual = Residual(256, n_layers)
+            self.classifier = nn.Linear(256, 1)
+        initialize_weights(self)      # (like the reference, other train_type values construct nothing and fail in forward)
+
+    def relocate(self):
+        device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+        self.to(device)
+
+    def forward(self, **kwargs):
+        h = _unimodal_input(self.mode, kwargs)
+        if self.train_type == 'fcnn':
+            return fcnn_forward(self.classifier, h).squeeze(), None, None
+        if self.train_type == 'highway':
+            h = self.highway(h)
+        elif self.train_type == 'residual':
+            h = self.residual(h)
+        else:
+            raise NotImplementedError(f"train_type={self.train_type!r}")
+        return Dense.apply(h, self.classifier.weight, self.classifier.bias, ACT_NONE).squeeze(), None, None
 
 
 class multimodal_pretrained(nn.Module):

@@ -72,6 +72,39 @@ class Highway(nn.Module):
         return batchnorm1d_forward(self.bn2, x)
 
 
+class ResidualBlock(nn.Module):
+    """fc1 -> bn1 -> ReLU -> fc2 -> bn2 -> (+ x) -> ReLU (models/model_modules.py:28-49; same submodule names)."""
+
+    def __init__(self, size):
+        super().__init__()
+        self.fc1 = nn.Linear(size, size)
+        self.bn1 = nn.BatchNorm1d(size)
+        self.relu = nn.ReLU(inplace=True)
+        self.fc2 = nn.Linear(size, size)
+        self.bn2 = nn.BatchNorm1d(size)
+
+    def forward(self, x):
+        x = x.float()
+        out = Dense.apply(x, self.fc1.weight, self.fc1.bias, ACT_NONE)
+        out = torch.relu(batchnorm1d_forward(self.bn1, out))
+        out = Dense.apply(out, self.fc2.weight, self.fc2.bias, ACT_NONE)
+        return torch.relu(batchnorm1d_forward(self.bn2, out) + x)
+
+
+class Residual(nn.Module):
+    """n_layer ResidualBlocks (models/model_modules.py:51-59)."""
+
+    def __init__(self, size, n_layer):
+        super().__init__()
+        self.n_layer = n_layer
+        self.blocks = nn.ModuleList([ResidualBlock(size) for _ in range(n_layer)])
+
+    def forward(self, x):
+        for block in self.blocks:
+            x = block(x)
+        return x
+
+
 def SNN_Block(dim1, dim2, dropout=0.25):
     """Linear -> SELU -> AlphaDropout container (models/model_modules.py:64-68); executed by
     :func:`snn_block_forward`."""

@@ -1,14 +1,50 @@
-"""Fusion heads over pre-extracted 256-d embeddings with a discrete-hazard output — drop-in for
-models/nll_models_pretrained.py (:64-197): `kronecker` (:101-103,179-188), `early-fcnn` / `late-fcnn` (:82-91),
+"""Heads over pre-extracted 256-d embeddings with a discrete-hazard output — drop-in for
+models/nll_models_pretrained.py: `unimonal_pretrained` (:14-62: fcnn / highway on ONE modality; its residual branch is
+commented out in the reference) and `multimodal_pretrained` (:64-197): `kronecker` (:101-103,179-188), `early-fcnn` / `late-fcnn` (:82-91),
 `early-highway` / `late-highway` (:92-99)."""
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from ..autograd import HazardHead
+from .._lib import ACT_NONE
+from ..autograd import Dense, HazardHead
 from ..utils.utils import initialize_weights
-from .coxranking_models_pretrained import _pick, _pick_late
+from .coxranking_models_pretrained import _pick, _pick_late, _unimodal_input
 from .model_modules import Highway, XlinearFusion, fcnn_forward
+
+
+class unimonal_pretrained(nn.Module):
+    def __init__(self, dropout=True, n_classes=4, mode=None, train_type=None, bag_loss=None, n_layers=1):
+        super().__init__()
+        self.n_classes, self.train_type, self.bag_loss, self.mode = n_classes, train_type, bag_loss, mode
+        if train_type == 'fcnn':
+            self.classifier = nn.Sequential(nn.Linear(256, n_classes), nn.Dropout(0.7))
+        elif train_type == 'highway':
+            self.highway = Highway(256, n_layers, F.relu)
+            self.classifier = nn.Linear(256, n_classes)
+        initialize_weights(self)
+
+    def relocate(self):
+        device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+        self.to(device)
+
+    def forward(self, **kwargs):
+        h = _unimodal_input(self.mode, kwargs)
+        if self.train_type == 'fcnn':
+            lin = self.classifier[0]
+            if self.training:
+                # the reference drops LOGITS (Linear -> Dropout(0.7), :23): the head kernel fuses linear + sigmoid, so the
+                # train-mode mask goes through the un-fused pair
+                logits = self.classifier[1](Dense.apply(h, lin.weight, lin.bias, ACT_NONE))
+                hazards = torch.sigmoid(logits)
+                S = torch.cumprod(1 - hazards, dim=1)
+                return -torch.sum(S, dim=1), hazards, S
+        elif self.train_type == 'highway':
+            h, lin = self.highway(h), self.classifier
+        else:
+            raise NotImplementedError(f"train_type={self.train_type!r}")
+        hazards, S, _ = HazardHead.apply(h, lin.weight, lin.bias)
+        return -torch.sum(S, dim=1), hazards, S
 
 
 class multimodal_pretrained(nn.Module):

@@ -80,6 +80,14 @@ CAPTUM_CASES = {
     "captum_rp": dict(seed=123, fn="captum_radio_path", mode="radio_path", fusion="tensor", B=2, Nr=7, Np=33, d=36),
     "captum_po_concat": dict(seed=124, fn="captum_path_omic", mode="path_omic", fusion="concat", B=5, Nr=0, Np=21, d=80),
 }
+# unimonal_pretrained heads on ONE modality's 256-d embedding (cox: fcnn / highway / residual; nll: fcnn / highway)
+UNI_CASES = {
+    "uni_cox_fcnn_path_b12": dict(seed=131, kind="cox", loss="cox", mode="path", train_type="fcnn", B=12, n_layers=1),
+    "uni_cox_highway_radio_b9": dict(seed=132, kind="cox", loss="ranking", mode="radio", train_type="highway", B=9, n_layers=2),
+    "uni_cox_residual_omic_b10": dict(seed=133, kind="cox", loss="cox", mode="omic", train_type="residual", B=10, n_layers=2),
+    "uni_nll_fcnn_omic_b8": dict(seed=134, kind="nll", loss="nll", mode="omic", train_type="fcnn", B=8, n_layers=1),
+    "uni_nll_highway_path_b16": dict(seed=135, kind="nll", loss="ce", mode="path", train_type="highway", B=16, n_layers=1),
+}
 LOSS_CASES = {
     "nll_b7_a0": dict(seed=51, loss="nll", B=7, K=4, alpha=0.0),
     "nll_b64_k8": dict(seed=52, loss="nll", B=64, K=8, alpha=0.15),

@@ -45,3 +45,9 @@ def goldens_xfusion4():
 def goldens_mm():
     path = os.path.join(ROOT, "tests", "golden", "reference_goldens_mm.pt")
     return torch.load(path, map_location="cpu", weights_only=False)
+
+
+@pytest.fixture(scope="session")
+def goldens_unimodal():
+    path = os.path.join(ROOT, "tests", "golden", "reference_goldens_unimodal.pt")
+    return torch.load(path, map_location="cpu", weights_only=False)

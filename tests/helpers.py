@@ -71,6 +71,22 @@ def build_head2_model(cfg):
     return model
 
 
+def build_unimodal_model(cfg):
+    """unimonal_pretrained head for a UNI case: seeded like the reference, biases and BatchNorm state perturbed."""
+    torch.manual_seed(cfg["seed"])
+    mod = cox_heads if cfg["kind"] == "cox" else nll_heads
+    model = mod.unimonal_pretrained(mode=cfg["mode"], train_type=cfg["train_type"], n_classes=4,
+                                    n_layers=cfg["n_layers"]).eval()
+    cases.perturb_biases(model, cfg["seed"])
+    cases.perturb_bn(model, cfg["seed"])
+    return model
+
+
+def unimodal_input(cfg):
+    hr, hp, ho = cases.embeddings(cfg)
+    return {"radio": hr, "path": hp, "omic": ho}[cfg["mode"]]
+
+
 def build_xfusion4(cfg):
     """XlinearFusion with the reference's default ctor (4 modalities), seeded and perturbed like the golden generator."""
     from multimodalfusion_b200.models.model_modules import XlinearFusion

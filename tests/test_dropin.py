@@ -144,6 +144,9 @@ def test_unsupported_modes_raise_like_the_reference():
     with pytest.raises(NotImplementedError):
         from multimodalfusion_b200.models.coxranking_models_pretrained import multimodal_pretrained
         multimodal_pretrained(train_type="early-residual")   # commented out in the reference as well
+    from multimodalfusion_b200.models import coxranking_models_pretrained as cox_heads
+    keys = list(cox_heads.unimonal_pretrained(train_type="residual", n_layers=1).state_dict())
+    assert "residual.blocks.0.fc1.weight" in keys and "residual.blocks.0.bn2.running_var" in keys
     assert hasattr(M.MIL_Attention_fc_surv_path(), "relocate")
 
 

@@ -8,7 +8,7 @@ import torch
 
 from cpu_standins import oracle_kernels
 from helpers import (build_head2_model, build_head_model, build_omic_model, build_path_model, build_radio_model,
-                     build_radio_tensor_model, build_xfusion4, rel_err)
+                     build_radio_tensor_model, build_unimodal_model, build_xfusion4, rel_err, unimodal_input)
 from oracle import amil_oracle as O
 from oracle import cases
 
@@ -146,4 +146,35 @@ def test_xfusion4_glue(goldens_xfusion4, name):
     assert rel_err(feats, gold["features"]) < TOL
     for v, gd in zip(vs, gold["d_inputs"]):
         assert rel_err(v.grad, gd) < 2e-4
+    _check_grads(model, gold["grads"])
+
+
+@pytest.mark.parametrize("name", list(cases.UNI_CASES))
+def test_unimodal_head_glue(goldens_unimodal, name):
+    """unimonal_pretrained (fcnn / highway / residual) of both head files: identical initial weights, outputs, loss, input
+    gradient and every parameter gradient against the reference."""
+    cfg, gold = cases.UNI_CASES[name], goldens_unimodal["unimodal"][name]
+    model = build_unimodal_model(cfg)
+    assert list(model.state_dict()) == list(gold["weights_fp"])
+    for k, v in model.state_dict().items():
+        cases.check_fingerprint(v, gold["weights_fp"][k], 0.0, f"weight {k}")
+    h = unimodal_input(cfg).requires_grad_(True)
+    times, c = cases.cohort_labels(cfg["B"], cfg["seed"])
+    with oracle_kernels():
+        res = model(**{"h_" + cfg["mode"]: h})
+        if cfg["kind"] == "cox":
+            risk = res[0]
+            assert res[1] is None and res[2] is None
+            loss = O.cox_loss(risk, times, c) if cfg["loss"] == "cox" else O.ranking_loss(risk.reshape(-1), times, c)
+        else:
+            risk, hazards, S = res
+            assert rel_err(hazards, gold["hazards"]) < TOL and rel_err(S, gold["S"]) < TOL
+            Y = torch.arange(cfg["B"]) % 4
+            loss = (O.nll_surv_loss(hazards, S, Y, c, alpha=0.15) if cfg["loss"] == "nll"
+                    else O.ce_surv_loss(hazards, S, Y, c, alpha=0.15))
+        model.zero_grad()
+        loss.backward()
+    assert risk.shape == gold["risk"].shape and rel_err(risk, gold["risk"]) < TOL
+    assert abs(loss.item() - gold["loss"].item()) < 2e-5
+    assert rel_err(h.grad, gold["d_input"]) < 2e-4
     _check_grads(model, gold["grads"])

@@ -10,7 +10,7 @@ test_gpu_parity._grad_tol), risk order n/a (one patient); captum* run in fp32 on
 import pytest
 import torch
 
-from helpers import build_mm_model, rel_err
+from helpers import build_mm_model, build_unimodal_model, rel_err, unimodal_input
 from oracle import cases
 
 pytestmark = pytest.mark.gpu
@@ -74,4 +74,34 @@ def test_captum_entry_points_vs_reference_goldens(dev, goldens_mm, name):
     for a, fp in zip(args, gold["d_inputs"]):
         assert a.grad is not None
         cases.check_fingerprint(a.grad, fp, 1e-4, "input attribution", atol=1e-8)
+    _check_param_grads(model, gold["grads"], 1e-4)
+
+
+@pytest.mark.parametrize("name", list(cases.UNI_CASES))
+def test_unimodal_heads_vs_reference_goldens(dev, goldens_unimodal, name):
+    """unimonal_pretrained (fcnn / highway / residual on one modality's embedding) of both head files on the library's
+    fp32 kernels (Dense, BatchNorm1d, highway mix, hazard head) against the reference: risk / hazards, loss, risk order,
+    input gradient, every parameter gradient."""
+    from multimodalfusion_b200.utils import CoxSurvLoss, CrossEntropySurvLoss, NLLSurvLoss, RankingSurvLoss
+    cfg, gold = cases.UNI_CASES[name], goldens_unimodal["unimodal"][name]
+    model = build_unimodal_model(cfg).to(dev)
+    h = unimodal_input(cfg).to(dev).requires_grad_(True)
+    times, c = cases.cohort_labels(cfg["B"], cfg["seed"])
+    res = model(**{"h_" + cfg["mode"]: h})
+    if cfg["kind"] == "cox":
+        risk = res[0]
+        assert res[1] is None and res[2] is None
+        loss = (CoxSurvLoss()(risks=risk, times=times.to(dev), c=c.to(dev)) if cfg["loss"] == "cox"
+                else RankingSurvLoss()(risks=risk.reshape(-1), times=times.to(dev), c=c.to(dev)))
+    else:
+        risk, hazards, S = res
+        assert rel_err(hazards, gold["hazards"]) < 1e-5 and rel_err(S, gold["S"]) < 1e-5
+        lf = NLLSurvLoss(alpha=0.15) if cfg["loss"] == "nll" else CrossEntropySurvLoss(alpha=0.15)
+        loss = lf(hazards=hazards, S=S, Y=(torch.arange(cfg["B"]) % 4).to(dev), c=c.to(dev))
+    assert risk.shape == gold["risk"].shape and rel_err(risk, gold["risk"]) < 1e-5
+    assert torch.equal(torch.argsort(risk.reshape(-1).cpu()), torch.argsort(gold["risk"].reshape(-1)))
+    assert abs(loss.item() - gold["loss"].item()) < 1e-5
+    model.zero_grad()
+    loss.backward()
+    assert rel_err(h.grad, gold["d_input"]) < 1e-4
     _check_param_grads(model, gold["grads"], 1e-4)
