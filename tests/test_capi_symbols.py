@@ -48,6 +48,15 @@ def test_argument_validation_happens_before_any_device_work():
     assert lib.mmf_amil_combine(None, 1, 256, 1, None, None, None) == -1
     assert lib.mmf_cox_fwd_bwd(None, None, None, 4, None, None, None, 0, None) == -1
     assert lib.mmf_ranking_fwd_bwd(None, None, None, 1, 0, 0, None, None, None, None, 0, None) == -1
+    # Kronecker encoder: 2..4 factors; anything else is refused before a launch (pointers are never dereferenced)
+    fake = ctypes.c_void_p(16)
+    arr = (ctypes.c_void_p * 5)(16, 16, 16, 16, 16)
+    for m in (1, 5):
+        assert lib.mmf_kron_enc_fwd(arr, m, 17, 4, fake, fake, 256, fake, None) == -1
+        assert lib.mmf_kron_enc_bwd(arr, m, 17, 4, fake, 256, fake, fake, arr, fake, fake, fake, 1 << 30, None) == -1
+    assert lib.mmf_kron_enc_bwd(arr, 4, 17, 4, fake, 256, fake, fake, arr, fake, fake, fake, 16, None) == -6   # workspace
+    assert lib.mmf_kron_enc_workspace_bytes(4, 17, 33) == 17 ** 4 * 33 * 4
+    assert lib.mmf_hazard_head_fwd(fake, 2, 256, fake, fake, 17, fake, fake, None, None) == -1               # K <= 16
 
 
 def test_built_for_sm_100a():
