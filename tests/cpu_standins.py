@@ -52,10 +52,34 @@ def _pooled(seq, x, training, group=None):
     return s.reshape(1, -1), M.reshape(1, -1)
 
 
+def _ste_bf16(t):
+    """bf16 rounding with a straight-through gradient: the value the tensor cores see, the gradient of the identity."""
+    return t + (t.to(torch.bfloat16).float() - t).detach()
+
+
+def _segmented_linear_bf16(W, b, *segs):
+    y = torch.cat([_ste_bf16(s.float()) for s in segs], dim=1) @ _ste_bf16(W).t() + b
+    return _ste_bf16(y)                       # the GEMM writes the bf16 bag the fused AMIL kernel consumes
+
+
+def _pooled_bf16(seq, x, training, group=None):
+    """The fused kernel's operand precision: bf16 x / W1 / Wa / Wb, bf16 h tile, fp32 accumulation and biases."""
+    assert not training and group is None
+    fc, attn = seq[0], seq[3]
+    Wa, ba, Wb, bb, wc, bc = attn.amil_weights()
+    h = _ste_bf16(torch.relu(_ste_bf16(x.float()) @ _ste_bf16(fc.weight).t() + fc.bias))
+    a = torch.tanh(h @ _ste_bf16(Wa).t() + ba)
+    g = torch.sigmoid(h @ _ste_bf16(Wb).t() + bb) if Wb is not None else torch.ones_like(a)
+    s = (a * g) @ wc.reshape(-1) + bc.reshape(())
+    M, _, _ = O.softmax_pool(s, h)
+    return s.reshape(1, -1), M.reshape(1, -1)
+
+
 @contextlib.contextmanager
-def oracle_kernels():
+def oracle_kernels(bf16_operands: bool = False):
     """Route Dense / KronEncoder / HazardHead / SegmentedLinearBf16 / BatchNorm1dFn / HighwayMix / the fused AMIL pooling
-    through fp32 torch ops."""
+    through fp32 torch ops. bf16_operands=True gives the tensor-core GEMMs (fused AMIL, segmented reduce_dim) the operand
+    precision of the kernels, so that the GPU tests' tolerances can be dry-run on the CPU."""
     saved = [(A.Dense, A.Dense.__dict__.get("apply")), (A.KronEncoder, A.KronEncoder.__dict__.get("apply")),
              (A.HazardHead, A.HazardHead.__dict__.get("apply")),
              (A.SegmentedLinearBf16, A.SegmentedLinearBf16.__dict__.get("apply")),
@@ -64,10 +88,10 @@ def oracle_kernels():
     A.Dense.apply = staticmethod(_dense)
     A.KronEncoder.apply = staticmethod(_kron)
     A.HazardHead.apply = staticmethod(_hazard)
-    A.SegmentedLinearBf16.apply = staticmethod(_segmented_linear)
+    A.SegmentedLinearBf16.apply = staticmethod(_segmented_linear_bf16 if bf16_operands else _segmented_linear)
     A.BatchNorm1dFn.apply = staticmethod(_batchnorm)
     A.HighwayMix.apply = staticmethod(_highway_mix)
-    MM.AmilBranch.pooled = staticmethod(_pooled)
+    MM.AmilBranch.pooled = staticmethod(_pooled_bf16 if bf16_operands else _pooled)
     try:
         yield
     finally:
