@@ -4,7 +4,7 @@ after a run-time repair, without editing it). The module's Python glue is pinned
 here the same goldens go through the real kernels: segmented bf16 reduce_dim GEMM -> fused AMIL (radio, path) -> SNN ->
 Kronecker / concat fusion -> hazard head -> nll_surv, and the backward of all of it.
 
-Tolerances: hazards / S / attention scores 1e-2, gradients 2e-2 + 3/N (bf16 operands; tiny bags, see
+Tolerances: hazards / S / pathology attention scores 1e-2 (radiology scores 2e-2: two bf16 stages), gradients 2e-2 + 3/N (bf16 operands; tiny bags, see
 test_gpu_parity._grad_tol), risk order n/a (one patient); captum* run in fp32 on the functor SGEMM kernels: 1e-4.
 (This file sorts last on purpose: it was added after the round's GPU budget was spent and has not run on a device yet.)"""
 import pytest
@@ -71,7 +71,11 @@ def test_mm_model_vs_reference_goldens(dev, goldens_mm, name):
     hazards, S, Y_hat, A_raw = model(**kw)
     assert set(A_raw) == set(gold["A_raw"])
     for k in A_raw:
-        assert A_raw[k].shape == gold["A_raw"][k].shape and rel_err(A_raw[k], gold["A_raw"][k]) < TOL_FWD_REF, k
+        # radiology scores pass through TWO bf16 stages (reduce_dim writes a bf16 bag, then the fused AMIL kernel): the
+        # bf16-operand restatement itself reaches 0.9e-2 on these 17-40-slice bags (tests/test_mm_glue_cpu.py), so they
+        # get 2e-2; pathology scores and the hazards keep the north star's 1e-2
+        tol = 2 * TOL_FWD_REF if k == "radiology" else TOL_FWD_REF
+        assert A_raw[k].shape == gold["A_raw"][k].shape and rel_err(A_raw[k], gold["A_raw"][k]) < tol, k
     assert rel_err(hazards, gold["hazards"]) < TOL_FWD_REF and rel_err(S, gold["S"]) < TOL_FWD_REF
     assert Y_hat.shape == (1, 1) and Y_hat.dtype == torch.int64
     loss = NLLSurvLoss(alpha=cfg["alpha"])(hazards=hazards, S=S, Y=Y.to(dev), c=c.to(dev))
