@@ -131,6 +131,14 @@ def amil_backward(x, W1, Wa, Wb, wc, s, h, a, g, M, m, l, dM, dA_raw=None, *, dr
     ds = p * (h @ dM - dM @ M)
     if dA_raw is not None:
         ds = ds + dA_raw
+    return _amil_backward_from_ds(x, W1, Wa, Wb, wc, h, a, g, p, ds, dM, (h > 0).to(h.dtype), drop_h=drop_h,
+                                  a_scale=a_scale, g_scale=g_scale, need_dx=need_dx)
+
+
+def _amil_backward_from_ds(x, W1, Wa, Wb, wc, h, a, g, p, ds, dM, relu_gate, *, drop_h=False, a_scale=None,
+                           g_scale=None, need_dx=False) -> Dict[str, torch.Tensor]:
+    """Everything downstream of the score gradient ds [N]: gate backward, weight gradients of the
+    attention branches, dh -> ReLU / dropout gate -> weight gradients of the fc layer."""
     ka = a_scale if a_scale is not None else torch.ones_like(a)
     kg = g_scale if (g_scale is not None and Wb is not None) else torch.ones_like(g)
     ad, gd = a * ka, g * kg
@@ -146,12 +154,34 @@ def amil_backward(x, W1, Wa, Wb, wc, s, h, a, g, M, m, l, dM, dA_raw=None, *, dr
     out["dWab"] = dG.t() @ h
     out["dbab"] = dG.sum(0)
     dh = p[:, None] * dM[None, :] + dG @ Wab
-    du = dh * (h > 0).to(h.dtype) * ((1.0 / 0.75) if drop_h else 1.0)
+    du = dh * relu_gate * ((1.0 / 0.75) if drop_h else 1.0)
     out["dW1"] = du.t() @ x
     out["db1"] = du.sum(0)
     if need_dx:
         out["dx"] = du @ W1
     return out
+
+
+def head_projection(h, Wk):
+    """z_i = Wk h_i [N, K] and the ReLU mask [N, L] — what a training forward can emit while the H tile is resident
+    (head-projected phase A; K = n_classes = 4-8 floats per instance)."""
+    return h @ Wk.t(), h > 0
+
+
+def amil_backward_head_projected(x, W1, Wa, Wb, wc, s, h, a, g, M, m, l, dlogits, Wk, z, relu_mask, dA_raw=None,
+                                 **kw) -> Dict[str, torch.Tensor]:
+    """amil_backward for the case where the pooled embedding feeds a LINEAR classifier directly
+    (models/model_attention_mil_path.py:56-58: logits = M Wk^T + bk), restated the way the round-2 kernel is meant to
+    compute it: dM = Wk^T dlogits, hence t_i = dM.h_i = dlogits.(Wk h_i) = dlogits.z_i — K FMAs per instance from the
+    forward's z instead of an L-long dot product over a re-read of the H tile — and the ReLU gate is the forward's
+    stored mask. h still enters the weight-gradient GEMM (dWab = dG^T h) as before. Equal to amil_backward up to fp32
+    re-association (tests/test_oracle.py::test_head_projected_backward_equals_the_general_one)."""
+    dM = Wk.t() @ dlogits
+    p = torch.exp(s - m) / l
+    ds = p * (z @ dlogits - dM @ M)
+    if dA_raw is not None:
+        ds = ds + dA_raw
+    return _amil_backward_from_ds(x, W1, Wa, Wb, wc, h, a, g, p, ds, dM, relu_mask.to(h.dtype), **kw)
 
 
 # ------------------------------------------------------------------------------------------------

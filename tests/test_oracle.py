@@ -250,3 +250,37 @@ def test_radio_tensor_fusion_matches_repaired_reference(goldens_xfusion4, name):
     hz, S, _ = O.hazard_head(M, model.classifier.weight.detach(), model.classifier.bias.detach())
     assert rel_err(s.reshape(1, -1), gold["A_raw"]) < 1e-4 and rel_err(M, gold["M"]) < 1e-4
     assert rel_err(hz, gold["hazards"]) < 1e-4 and rel_err(S, gold["S"]) < 1e-4
+
+
+@pytest.mark.parametrize("gated", [True, False])
+def test_head_projected_backward_equals_the_general_one(gated):
+    """Spec of the round-2 'head-projected phase A' (DESIGN.md §8): with a linear classifier on the pooled embedding,
+    t_i = dM.h_i can be formed from z_i = Wk h_i (K floats per instance, emitted by the forward) and dlogits — every
+    gradient equals the general backward's to fp32 re-association, train-mode dropout scalings included."""
+    g = torch.Generator().manual_seed(17)
+    N, L, D, K = 300, 256, 256, 4
+    x = cases.features(N, 91)
+    W1, b1 = torch.randn(L, 1024, generator=g) * 0.03, torch.randn(L, generator=g) * 0.05
+    Wa, ba = torch.randn(D, L, generator=g) * 0.06, torch.randn(D, generator=g) * 0.05
+    Wb, bb = (torch.randn(D, L, generator=g) * 0.06, torch.randn(D, generator=g) * 0.05) if gated else (None, None)
+    wc, bc = torch.randn(1, D, generator=g) * 0.1, torch.zeros(1)
+    Wk, bk = torch.randn(K, L, generator=g) * 0.05, torch.randn(K, generator=g) * 0.05
+    hs, as_, gs = O.dropout_scale_mask(7, 0, N, L), O.dropout_scale_mask(7, 1, N, D), O.dropout_scale_mask(7, 2, N, D)
+    s, h, a, gg = O.fc_attention(x, W1, b1, Wa, ba, Wb, bb, wc, bc, h_scale=hs, a_scale=as_, g_scale=gs)
+    M, m, l = O.softmax_pool(s, h)
+    Mr = M.reshape(1, -1).clone().requires_grad_(True)
+    logits = Mr @ Wk.t() + bk
+    logits.retain_grad()
+    hazards = torch.sigmoid(logits)
+    loss = O.nll_surv_loss(hazards, torch.cumprod(1 - hazards, dim=1), torch.tensor([2]), torch.tensor([0.0]), alpha=0.15)
+    loss.backward()
+    dA = torch.randn(N, generator=g) * 1e-3
+    kw = dict(drop_h=True, a_scale=as_, g_scale=gs, need_dx=True)
+    ref = O.amil_backward(x, W1, Wa, Wb, wc, s, h, a, gg, M, m, l, Mr.grad.reshape(-1), dA, **kw)
+    z, mask = O.head_projection(h, Wk)
+    assert z.shape == (N, K) and mask.dtype == torch.bool
+    got = O.amil_backward_head_projected(x, W1, Wa, Wb, wc, s, h, a, gg, M, m, l, logits.grad.reshape(-1), Wk, z, mask,
+                                         dA, **kw)
+    assert set(got) == set(ref)
+    for k in ref:
+        assert rel_err(got[k], ref[k]) < 2e-5, k
