@@ -66,6 +66,18 @@ constexpr uint32_t AMIL2_EPI_THREADS = 256;
 #ifndef MMF_TILE2_RELAY
 #define MMF_TILE2_RELAY 0
 #endif
+// MMF_TILE2_EARLY_GEMM2 (round-2 candidate, compiled but NOT yet run on a GPU, default 0; not combinable with
+// MMF_TILE2_RELAY yet): EPI1 drains the GEMM1 accumulator in COLUMN order — the two epilogue warps of a TMEM lane
+// quadrant take the even / odd 32-column pieces instead of the low / high half — and signals once columns 0..L/2-1 are
+// drained and the matching H k-blocks are written. The MMA issuer then starts GEMM2 chunk 0 (TMEM buffer 0 = columns
+// 0..255, smem k-blocks 0..KB2/2-1) while EPI1 is still working on the upper half, instead of waiting for all of EPI1:
+// about half of the first chunk's exposed 4.1k MMA cycles (profiles/r01i_ncu_full_summary.md) moves under EPI1.
+#ifndef MMF_TILE2_EARLY_GEMM2
+#define MMF_TILE2_EARLY_GEMM2 0
+#endif
+#if MMF_TILE2_EARLY_GEMM2 && MMF_TILE2_RELAY
+#error "MMF_TILE2_EARLY_GEMM2 and MMF_TILE2_RELAY are separate experiments"
+#endif
 
 template <int L, int D, bool GATED, int MODE, bool DROPH, bool DROPA>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AMIL2_THREADS, 1)
@@ -73,12 +85,19 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                   const __grid_constant__ CUtensorMap tmWab, const __grid_constant__ CUtensorMap tmH,
                   const AmilArgs a) {
   using C = Amil2Cfg<L, D, GATED>;
+#if MMF_TILE2_EARLY_GEMM2
+  // GEMM2's first TMEM buffer (columns 0..CHN-1) must lie inside the half of the GEMM1 accumulator that EPI1 drains first
+  constexpr bool kEarly = C::CHN * 2 <= L;
+#endif
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full1[C::NS1], bar_empty1[C::NS1];
   __shared__ __align__(8) uint64_t bar_full2[C::NS2], bar_empty2[C::NS2];
   __shared__ __align__(8) uint64_t bar_acc1, bar_h, bar_acc2_full[2], bar_acc2_empty[2];
 #if MMF_TILE2_RELAY
   __shared__ __align__(8) uint64_t bar_h_local, bar_acc2_done[2];   // CTA-local stages of the relayed signals
+#endif
+#if MMF_TILE2_EARLY_GEMM2
+  __shared__ __align__(8) uint64_t bar_h_lo;                        // lower half of H written, TMEM columns 0..L/2-1 drained
 #endif
   __shared__ uint32_t tmem_base_slot;
 
@@ -104,6 +123,9 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       mbar_init(smem_u32(&bar_acc2_full[b]), 1);
       mbar_init(smem_u32(&bar_acc2_empty[b]), MMF_TILE2_RELAY ? 2 : 16);
     }
+#if MMF_TILE2_EARLY_GEMM2
+    mbar_init(smem_u32(&bar_h_lo), 16);
+#endif
 #if MMF_TILE2_RELAY
     mbar_init(smem_u32(&bar_h_local), 8);
     for (int b = 0; b < 2; ++b) mbar_init(smem_u32(&bar_acc2_done[b]), 8);
@@ -181,7 +203,12 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     umma_commit_pair_mc(smem_u32(&bar_acc1), 3);
     MMF_STAMP(a, 6);
 
+#if MMF_TILE2_EARLY_GEMM2
+    // k-blocks 0..KB2/2-1 of both H tiles written, TMEM columns 0..L/2-1 drained (or everything, when !kEarly)
+    mbar_wait_cluster(smem_u32(kEarly ? &bar_h_lo : &bar_h), 0);
+#else
     mbar_wait_cluster(smem_u32(&bar_h), 0);   // both CTAs' H tiles written, GEMM1 TMEM columns drained
+#endif
     tc_fence_after();
     MMF_STAMP(a, 7);
     for (int c = 0; c < C::NCH; ++c) {
@@ -189,6 +216,12 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       mbar_wait_cluster(smem_u32(&bar_acc2_empty[buf]), ((c >> 1) & 1) ^ 1);
       tc_fence_after();
       for (int kb = 0; kb < C::KB2; ++kb) {
+#if MMF_TILE2_EARLY_GEMM2
+        if (kEarly && c == 0 && kb == C::KB2 / 2) {   // the upper half of H (and of the TMEM drain) is needed from here on
+          mbar_wait_cluster(smem_u32(&bar_h), 0);
+          tc_fence_after();
+        }
+#endif
         const int it = c * C::KB2 + kb;
         const int s = it % C::NS2;
         const uint32_t ph = (it / C::NS2) & 1;
@@ -265,8 +298,18 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     float t_i = 0.f;
     constexpr int PIECES1 = L / 64;  // 32-column pieces per half
     const int cb0 = half * PIECES1;
+#if MMF_TILE2_EARLY_GEMM2
+    static_assert(PIECES1 % 4 == 0 && C::KB2 == L / 64, "early GEMM2: the column sweep is split in two halves of k-blocks");
+    // piece ii of this warp = global piece 2 ii + half: both warps of a quadrant sweep the columns left to right together
+#define MMF_EPI1_PIECE(ii) (kEarly ? 2 * (ii) + (int)half : cb0 + (ii))
+    const uint32_t h_lo_leader = mapa_cluster(smem_u32(&bar_h_lo), 0);
+#endif
     float v[2][32];
+#if MMF_TILE2_EARLY_GEMM2
+    tmem_ld32(tq + MMF_EPI1_PIECE(0) * 32, v[0]);
+#else
     tmem_ld32(tq + cb0 * 32, v[0]);
+#endif
     // two pieces per iteration so the TMEM double-buffer indices stay static; NOT fully unrolled: the
     // fully unrolled body (8 x ~500 SASS instructions) thrashed the instruction cache
     // (ncu: stall_no_inst 18 % of samples in the backward kernel)
@@ -275,9 +318,15 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 #pragma unroll
       for (int par = 0; par < 2; ++par) {
         const int ii = i2 + par;
+#if MMF_TILE2_EARLY_GEMM2
+        const int cb = MMF_EPI1_PIECE(ii);
+        tmem_ld_wait();
+        if (ii + 1 < PIECES1) tmem_ld32(tq + MMF_EPI1_PIECE(ii + 1) * 32, v[par ^ 1]);
+#else
         const int cb = cb0 + ii;
         tmem_ld_wait();
         if (ii + 1 < PIECES1) tmem_ld32(tq + (cb + 1) * 32, v[par ^ 1]);
+#endif
         float (&u)[32] = v[par];
         const float4* b4p = reinterpret_cast<const float4*>(vec + C::V_B1 + cb * 32);
         uint32_t hb0 = 0xFFFFFFFFu, hb1 = 0xFFFFFFFFu;   // all kept when dropout is off
@@ -313,6 +362,16 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           }
         }
       }
+#if MMF_TILE2_EARLY_GEMM2
+      if (kEarly && i2 + 2 == PIECES1 / 2) {
+        // global pieces 0..PIECES1-1 = columns 0..L/2-1 are drained (the prefetch in flight is for a column >= L/2) and
+        // the H k-blocks 0..KB2/2-1 are in shared memory: GEMM2 chunk 0 may start on them
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(h_lo_leader);
+      }
+#endif
     }
     fence_proxy_async_smem();
     tc_fence_before();
@@ -321,6 +380,9 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     if (lane == 0) mbar_arrive(smem_u32(&bar_h_local));
 #else
     if (lane == 0) mbar_arrive_cluster(h_ready_leader);
+#endif
+#if MMF_TILE2_EARLY_GEMM2
+#undef MMF_EPI1_PIECE
 #endif
     if (e == 0) MMF_STAMP(a, 11);
 
