@@ -4,10 +4,7 @@ thin C-ABI extension` layer of the north star).  Forward and backward both run i
 """
 from __future__ import annotations
 
-from typing import Optional
-
 import torch
-import torch.distributed as dist
 
 from . import ops
 from ._lib import MMF_NEED_DX

@@ -16,8 +16,7 @@ reference modules in the build container, runs them on seeded inputs and commits
 """
 from __future__ import annotations
 
-import math
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, List, Tuple
 
 import numpy as np
 import torch
