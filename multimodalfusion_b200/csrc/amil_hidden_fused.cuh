@@ -89,6 +89,30 @@ struct HiddenFusedCfg {
 #ifndef MMF_HIDDEN_RELAY
 #define MMF_HIDDEN_RELAY 1
 #endif
+// MMF_HIDDEN_FAST_MASK (round-2 candidate, compiled but NOT yet run on a GPU, default 0): phase A builds the ReLU mask
+// bits of 8 stashed bf16 activations with 4 HSET2.BF16 (packed h > 0 compares, 0xFFFF per true half) + 2 PRMT + 5 integer
+// ops instead of 16 FSETP + 16 SEL + shift / or chains on the up-converted floats (~40 instructions): the same bits, about
+// 40 % fewer instructions in a phase that is issue- / dependency-bound at 4 warps per scheduler (13.5k of 47k cycles).
+#ifndef MMF_HIDDEN_FAST_MASK
+#define MMF_HIDDEN_FAST_MASK 0
+#endif
+#if MMF_HIDDEN_FAST_MASK
+// 0xFFFF per 16-bit half of w whose bf16 value is > 0 (false for -0, NaN: the semantics of the float compare it replaces)
+__device__ __forceinline__ uint32_t bf16x2_gt0_mask(uint32_t w) {
+  return __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&w), __float2bfloat162_rn(0.f));
+}
+__device__ __forceinline__ uint32_t prmt_b32(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+  return r;
+}
+// bit i of the result = (element i > 0) for the 8 bf16 values packed in w[0..3] (element 2k = low half of w[k])
+__device__ __forceinline__ uint32_t relu_mask_byte(const uint32_t (&w)[4]) {
+  const uint32_t X = prmt_b32(bf16x2_gt0_mask(w[0]), bf16x2_gt0_mask(w[1]), 0x6420u);   // one 0x00 / 0xFF byte per element 0..3
+  const uint32_t Y = prmt_b32(bf16x2_gt0_mask(w[2]), bf16x2_gt0_mask(w[3]), 0x6420u);   // elements 4..7
+  return (((X & 0x08040201u) + ((Y & 0x08040201u) << 4)) * 0x01010101u) >> 24;          // byte sum: no carries
+}
+#endif
 constexpr int HIDDEN_EW = 16;                         // worker (phase A / transform / epilogue) warps: the CUDA-core
                                                      // phases are latency-bound, 16 warps hide ~2x what 8 did
 constexpr int HIDDEN_ET = HIDDEN_EW * 32;             // worker threads
@@ -291,13 +315,19 @@ amil_hidden_fused_kernel(const __grid_constant__ CUtensorMap tmAG,   // stash fp
 #pragma unroll
           for (int j = 0; j < HJ; ++j) {
             const uint32_t w[4] = {hv[buf][u][j].x, hv[buf][u][j].y, hv[buf][u][j].z, hv[buf][u][j].w};
+#if MMF_HIDDEN_FAST_MASK
+            const uint32_t byte = relu_mask_byte(w);
+#else
             uint32_t byte = 0;
+#endif
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const float2 f = unpack_bf16x2(w[k]);
               t0 = fmaf(f.x, dmv[j][2 * k], t0);
               t1 = fmaf(f.y, dmv[j][2 * k + 1], t1);
+#if !MMF_HIDDEN_FAST_MASK
               byte |= (uint32_t)(f.x > 0.f) << (2 * k) | (uint32_t)(f.y > 0.f) << (2 * k + 1);
+#endif
             }
             uint32_t word = ok ? byte << (8 * (lane & 3)) : 0u;
             word |= __shfl_xor_sync(0xffffffffu, word, 1);
