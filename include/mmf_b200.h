@@ -149,6 +149,53 @@ int mmf_amil_fwd_train(const void* x, int64_t N, int64_t ldx, const MmfAmilWeigh
                        int flags, uint64_t seed, float* A_raw, float* partials, void* workspace,
                        size_t workspace_bytes, float* zero_buf, int64_t zero_count, void* stream);
 
+/* ---- fused batch-1 training step (utils/core_utils.py:200-247 for the path / radio AMIL models) ------------------
+ * Head block: classifier -> sigmoid -> cumprod (models/model_attention_mil_path.py:57-61), nll_surv
+ * (utils/loss_utils.py:22-39) and their backward, run by the LAST tile CTA of the training forward to finish
+ * (no separate head launch). Inputs: Wk, bk, Wk_split (mmf_pack_head_weights), K <= 8, Y, c, alpha, eps,
+ * loss_scale (1/gc of the reference's gradient accumulation: every gradient of the step is scaled by it).
+ * Outputs: M [L], ml [2], hazards / S [K], Y_hat (or NULL), loss [1] (unscaled), dM [L], hs [16] (dlogits and dM.M for
+ * the head-projected backward), dWk [K,L] / dbk [K] ACCUMULATED (or NULL).
+ * ticket: one uint32 in device memory, zero before the first launch (the kernel leaves it zero). */
+typedef struct MmfHeadStep {
+  const float* Wk;
+  const float* bk;
+  const void* Wk_split; /* bf16 [16, L] */
+  int K;
+  const int64_t* Y;
+  const float* c;
+  float alpha, eps, loss_scale;
+  float* M;
+  float* ml;
+  float* hazards;
+  float* S;
+  int64_t* Y_hat;
+  float* loss;
+  float* dM;
+  float* hs;
+  float* dWk;
+  float* dbk;
+  uint32_t* ticket;
+} MmfHeadStep;
+
+/* Wk f32 [K, L] -> bf16 [16, L]: rows 0..K-1 = bf16(Wk), rows 8..8+K-1 = bf16(Wk - bf16(Wk)), other rows zero: the B
+ * operand of the N = 16 tensor-core side product z_i = Wk h_i of the training forward (hi + lo: fp32-grade z). */
+int mmf_pack_head_weights(const float* Wk, int K, int L, void* Wk_split_bf16, void* stream);
+
+/* mmf_amil_fwd_train + the head block: additionally leaves z_i = Wk h_i (fp32 [N, 4|8]) in the workspace. With
+ * mmf_amil_bwd_head the whole step is THREE launches (forward+head, gate+hidden backward, grouped wgrad). */
+int mmf_amil_fwd_train_head(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, int L, int D,
+                            int flags, uint64_t seed, float* A_raw, float* partials, void* workspace,
+                            size_t workspace_bytes, float* zero_buf, int64_t zero_count, const MmfHeadStep* head,
+                            void* stream);
+
+/* Backward of mmf_amil_fwd_train_head (same workspace, same head block): the pooled embedding feeds the linear
+ * classifier directly, so dM = Wk^T dlogits and t_i = dM.h_i = dlogits.z_i — the per-row 512-long dot products of
+ * the general backward become K FMAs. flags as in the forward (MMF_STASHED implied). Accumulates into g. */
+int mmf_amil_bwd_head(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, int L, int D, int flags,
+                      uint64_t seed, const float* A_raw, const MmfHeadStep* head, const float* dA_raw,
+                      const MmfAmilGrads* g, void* dx, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Backward of mmf_amil_fwd + combine, given dM = dLoss/dM [L] and optionally dA_raw [N].
  * Recomputes h and the attention activations tile by tile (nothing but A_raw, (m,l), M is kept
  * from the forward). Accumulates INTO g (caller zeroes or carries gradient accumulation).

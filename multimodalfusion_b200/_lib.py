@@ -83,6 +83,17 @@ class AmilGrads(C.Structure):
     ]
 
 
+class HeadStep(C.Structure):
+    """MmfHeadStep (include/mmf_b200.h): the head block of the fused batch-1 training step."""
+    _fields_ = [
+        ("Wk", C.c_void_p), ("bk", C.c_void_p), ("Wk_split", C.c_void_p), ("K", C.c_int),
+        ("Y", C.c_void_p), ("c", C.c_void_p), ("alpha", C.c_float), ("eps", C.c_float), ("loss_scale", C.c_float),
+        ("M", C.c_void_p), ("ml", C.c_void_p), ("hazards", C.c_void_p), ("S", C.c_void_p), ("Y_hat", C.c_void_p),
+        ("loss", C.c_void_p), ("dM", C.c_void_p), ("hs", C.c_void_p), ("dWk", C.c_void_p), ("dbk", C.c_void_p),
+        ("ticket", C.c_void_p),
+    ]
+
+
 _vp, _i, _i64, _sz, _f, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_float, C.c_uint64
 _PP = C.POINTER(C.c_void_p)
 
@@ -102,6 +113,11 @@ SIGNATURES = {
     "mmf_amil_bwd_workspace_bytes": (_sz, [_i64, _i, _i, _i]),
     "mmf_amil_fwd_train": (_i, [_vp, _i64, _i64, C.POINTER(AmilWeights), _i, _i, _i, _u64, _vp, _vp, _vp, _sz, _vp, _i64,
                                 _vp]),
+    "mmf_pack_head_weights": (_i, [_vp, _i, _i, _vp, _vp]),
+    "mmf_amil_fwd_train_head": (_i, [_vp, _i64, _i64, C.POINTER(AmilWeights), _i, _i, _i, _u64, _vp, _vp, _vp, _sz, _vp,
+                                     _i64, C.POINTER(HeadStep), _vp]),
+    "mmf_amil_bwd_head": (_i, [_vp, _i64, _i64, C.POINTER(AmilWeights), _i, _i, _i, _u64, _vp, C.POINTER(HeadStep), _vp,
+                               C.POINTER(AmilGrads), _vp, _vp, _sz, _vp]),
     "mmf_amil_bwd_gate_stashed": (_i, [_i64, C.POINTER(AmilWeights), _i, _i, _i, _u64, _vp, _vp, _vp, _vp, _vp,
                                        C.POINTER(AmilGrads), _vp, _sz, _vp]),
     "mmf_amil_bwd_gate_hidden_stashed": (_i, [_i64, C.POINTER(AmilWeights), _i, _i, _i, _u64, _vp, _vp, _vp, _vp, _vp,

@@ -3,9 +3,12 @@
 // Fuses the gate backward (amil_gate_ew.cuh) into the hidden-gradient GEMM as the PRODUCER of its A
 // operand, so dG makes no round trip through L2 between the two and the step loses one launch:
 //
-//   phase A  (epilogue warps, while the producer prefetches Wab): per row i of the 128-row tile
-//            t_i = dM·h_i, p_i = e^{s_i-m}/l, ds_i = p_i (t_i - dM·M) + dA_i, and [h_i > 0] as 16 mask
-//            words, from coalesced warp-per-row loads of the stashed H tile;
+//   phase A  (worker warps, while the producer prefetches Wab): per row i of the 128-row tile
+//            p_i = e^{s_i-m}/l, ds_i = p_i (t_i - dM·M) + dA_i with
+//              HEADPROJ: t_i = dlogits·z_i, z_i = Wk h_i emitted by the forward's tensor cores (K FMAs per row;
+//                        a linear classifier sits directly on M: dM = Wk^T dlogits — path / radio models), or
+//              general : t_i = dM·h_i from coalesced warp-per-row loads of the stashed H tile (dM from a fusion head);
+//            the ReLU mask [h_i > 0] comes as 1 bit per element from the training forward (mask words);
 //   mainloop per 64-wide slice c of D ("k-pair"): TMA brings the stashed fp16 tiles a[:, c], g[:, c] into
 //            an A stage; the epilogue warps rewrite them IN PLACE as the bf16 tiles
 //            dG_a = ds wc g (1-a²), dG_g = ds wc a g (1-g)  (column-stationary: thread = 4 columns x 8
@@ -39,8 +42,12 @@ struct HiddenFusedArgs {
   const __nv_bfloat16* H;   // stash [N, L]
   const float* A_raw;       // [N]
   const float* ml;          // (m, l)
-  const float* M;           // [L]
+  const float* M;           // [L]  (general phase A only)
   const float* dM;          // [L]
+  const uint32_t* mask;     // [N, L/32] ReLU mask words written by the training forward
+  const float* z;           // HEADPROJ: [N, zld] = Wk h_i
+  int zld;                  // 4 or 8
+  const float* hs;          // HEADPROJ: head scalars (amil_head_tail.cuh): dlogits[0..8), hs[HS_DOT] = dM·M
   const float* dA_raw;      // [N] or null
   const float* wc;          // [D]
   float* dwc;               // [D]  accumulated
@@ -75,9 +82,8 @@ struct HiddenFusedCfg {
   static constexpr uint32_t RING_BYTES = NSB * B_STAGE + NSA * A_STAGE;
   static constexpr uint32_t STAGING = 128u * L * 2u;       // dU tile
   static constexpr uint32_t POOL = RING_BYTES > STAGING ? RING_BYTES : STAGING;
-  // vector region (floats): dM | wc | ds | p | mask words [128][L/32] (uint32)
-  static constexpr int V_DM = 0, V_WC = L, V_DS = L + D, V_P = V_DS + 128,
-                       V_MASK = V_P + 128, V_END = V_MASK + 128 * (L / 32);
+  // vector region (floats): dM | wc | ds | p
+  static constexpr int V_DM = 0, V_WC = L, V_DS = L + D, V_P = V_DS + 128, V_END = V_P + 128;
   static constexpr uint32_t VEC_BYTES = ((V_END * 4u + 1023u) / 1024u) * 1024u;
   static constexpr uint32_t SMEM_BYTES = POOL + VEC_BYTES + 1024u;
 };
@@ -89,36 +95,12 @@ struct HiddenFusedCfg {
 #ifndef MMF_HIDDEN_RELAY
 #define MMF_HIDDEN_RELAY 1
 #endif
-// MMF_HIDDEN_FAST_MASK (round-2 candidate, compiled but NOT yet run on a GPU, default 0): phase A builds the ReLU mask
-// bits of 8 stashed bf16 activations with 4 HSET2.BF16 (packed h > 0 compares, 0xFFFF per true half) + 2 PRMT + 5 integer
-// ops instead of 16 FSETP + 16 SEL + shift / or chains on the up-converted floats (~40 instructions): the same bits, about
-// 40 % fewer instructions in a phase that is issue- / dependency-bound at 4 warps per scheduler (13.5k of 47k cycles).
-#ifndef MMF_HIDDEN_FAST_MASK
-#define MMF_HIDDEN_FAST_MASK 0
-#endif
-#if MMF_HIDDEN_FAST_MASK
-// 0xFFFF per 16-bit half of w whose bf16 value is > 0 (false for -0, NaN: the semantics of the float compare it replaces)
-__device__ __forceinline__ uint32_t bf16x2_gt0_mask(uint32_t w) {
-  return __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&w), __float2bfloat162_rn(0.f));
-}
-__device__ __forceinline__ uint32_t prmt_b32(uint32_t a, uint32_t b, uint32_t sel) {
-  uint32_t r;
-  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
-  return r;
-}
-// bit i of the result = (element i > 0) for the 8 bf16 values packed in w[0..3] (element 2k = low half of w[k])
-__device__ __forceinline__ uint32_t relu_mask_byte(const uint32_t (&w)[4]) {
-  const uint32_t X = prmt_b32(bf16x2_gt0_mask(w[0]), bf16x2_gt0_mask(w[1]), 0x6420u);   // one 0x00 / 0xFF byte per element 0..3
-  const uint32_t Y = prmt_b32(bf16x2_gt0_mask(w[2]), bf16x2_gt0_mask(w[3]), 0x6420u);   // elements 4..7
-  return (((X & 0x08040201u) + ((Y & 0x08040201u) << 4)) * 0x01010101u) >> 24;          // byte sum: no carries
-}
-#endif
 constexpr int HIDDEN_EW = 16;                         // worker (phase A / transform / epilogue) warps: the CUDA-core
                                                      // phases are latency-bound, 16 warps hide ~2x what 8 did
 constexpr int HIDDEN_ET = HIDDEN_EW * 32;             // worker threads
 constexpr int HIDDEN_THREADS = 128 + HIDDEN_ET;
 
-template <int L, int D, bool GATED, bool DROP>
+template <int L, int D, bool GATED, bool DROP, bool HEADPROJ>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HIDDEN_THREADS, 1)
 amil_hidden_fused_kernel(const __grid_constant__ CUtensorMap tmAG,   // stash fp16 [N, KD], box [128][64]
                          const __grid_constant__ CUtensorMap tmDG,   // same memory viewed as bf16 dG (store)
@@ -144,7 +126,6 @@ amil_hidden_fused_kernel(const __grid_constant__ CUtensorMap tmAG,   // stash fp
   uint8_t* pool_ptr = smem_raw + (pool - smem_u32(smem_raw));
   const uint32_t b_ring = pool, a_ring = pool + C::NSB * C::B_STAGE;
   float* vec = reinterpret_cast<float*>(pool_ptr + C::POOL);
-  uint32_t* s_mask = reinterpret_cast<uint32_t*>(vec + C::V_MASK);
   const int pair_m = blockIdx.x >> 1;
   const long long row0 = (long long)pair_m * 256 + 128 * (int)rank;   // first row of this CTA
 
@@ -261,8 +242,36 @@ amil_hidden_fused_kernel(const __grid_constant__ CUtensorMap tmAG,   // stash fp
     for (int i = e; i < D; i += HIDDEN_ET) vec[C::V_WC + i] = __ldg(a.wc + i);
 
 
-    // ---------------- phase A: ds_i, p_i, ReLU mask words — one warp per row, 4 rows in flight -------------
-    {
+    // ---------------- phase A: ds_i, p_i -----------------------------------------------------------------
+    if (HEADPROJ) {
+      // t_i = dlogits · z_i (z_i = Wk h_i from the forward), dM·M = dlogits · (logits - bk): K FMAs per row
+      if (e < 128) {
+        const long long row = row0 + e;
+        float ds = 0.f, p = 0.f;
+        if (row < a.N) {
+          const float4 z0 = __ldg(reinterpret_cast<const float4*>(a.z + row * a.zld));
+          float t = __ldg(a.hs + 0) * z0.x;
+          t = fmaf(__ldg(a.hs + 1), z0.y, t);
+          t = fmaf(__ldg(a.hs + 2), z0.z, t);
+          t = fmaf(__ldg(a.hs + 3), z0.w, t);
+          if (a.zld == 8) {
+            const float4 z1 = __ldg(reinterpret_cast<const float4*>(a.z + row * a.zld + 4));
+            t = fmaf(__ldg(a.hs + 4), z1.x, t);
+            t = fmaf(__ldg(a.hs + 5), z1.y, t);
+            t = fmaf(__ldg(a.hs + 6), z1.z, t);
+            t = fmaf(__ldg(a.hs + 7), z1.w, t);
+          }
+          p = __expf(__ldg(a.A_raw + row) - __ldg(a.ml)) / __ldg(a.ml + 1);
+          ds = p * (t - __ldg(a.hs + HS_DOT));
+          if (a.dA_raw) ds += __ldg(a.dA_raw + row);
+        }
+        vec[C::V_DS + e] = ds;
+        vec[C::V_P + e] = p;
+        const float sum = warp_sum(ds);
+        if (lane == 0) atomicAdd(&s_dbc, sum);
+      }
+    } else {
+      // one warp per row, rows software-pipelined two at a time: t_i = dM · h_i from the stashed H tile
       constexpr int HJ = L / 256;
       float dmv[HJ][8];
       float dotMM = 0.f;
@@ -286,9 +295,6 @@ amil_hidden_fused_kernel(const __grid_constant__ CUtensorMap tmAG,   // stash fp
           dA_l = a.dA_raw ? __ldg(a.dA_raw + row) : 0.f;
         }
       }
-      // software pipeline over the warp's rows, PA_STEP rows per step: the loads of step i + 1 are in flight while
-      // step i is reduced (the first version loaded 4 rows, waited a full L2 round trip, computed, and only then
-      // issued the next 4 loads: two exposed round trips per warp)
       constexpr int PA_STEP = 2, PA_STEPS = ROWS_PER_WARP / PA_STEP;
       static_assert(ROWS_PER_WARP % PA_STEP == 0, "phase A step");
       uint4 hv[2][PA_STEP][HJ];
@@ -309,30 +315,17 @@ amil_hidden_fused_kernel(const __grid_constant__ CUtensorMap tmAG,   // stash fp
 #pragma unroll
         for (int u = 0; u < PA_STEP; ++u) {
           const int r = (int)ew * ROWS_PER_WARP + step * PA_STEP + u;
-          const long long row = row0 + r;
-          const bool ok = row < a.N;
+          const bool ok = row0 + r < a.N;
           float t0 = 0.f, t1 = 0.f;   // two partial sums: halves the dependent FMA chain
 #pragma unroll
           for (int j = 0; j < HJ; ++j) {
             const uint32_t w[4] = {hv[buf][u][j].x, hv[buf][u][j].y, hv[buf][u][j].z, hv[buf][u][j].w};
-#if MMF_HIDDEN_FAST_MASK
-            const uint32_t byte = relu_mask_byte(w);
-#else
-            uint32_t byte = 0;
-#endif
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const float2 f = unpack_bf16x2(w[k]);
               t0 = fmaf(f.x, dmv[j][2 * k], t0);
               t1 = fmaf(f.y, dmv[j][2 * k + 1], t1);
-#if !MMF_HIDDEN_FAST_MASK
-              byte |= (uint32_t)(f.x > 0.f) << (2 * k) | (uint32_t)(f.y > 0.f) << (2 * k + 1);
-#endif
             }
-            uint32_t word = ok ? byte << (8 * (lane & 3)) : 0u;
-            word |= __shfl_xor_sync(0xffffffffu, word, 1);
-            word |= __shfl_xor_sync(0xffffffffu, word, 2);
-            if ((lane & 3) == 0) s_mask[r * (L / 32) + (lane >> 2) + 8 * j] = word;
           }
           const float t = warp_sum(t0 + t1);
           const float s_raw = __shfl_sync(0xffffffffu, s_raw_l, step * PA_STEP + u);
@@ -351,7 +344,7 @@ amil_hidden_fused_kernel(const __grid_constant__ CUtensorMap tmAG,   // stash fp
       }
       if (lane == 0) atomicAdd(&s_dbc, acc_ds);
     }
-    named_bar_sync(1, HIDDEN_ET);   // ds / p / mask / vectors visible to all worker threads
+    named_bar_sync(1, HIDDEN_ET);   // ds / p / vectors visible to all worker threads
     if (e == 0) MMF_STAMP(a, 4);
 
     // ---------------- mainloop: transform the stashed activations into dG, in place -------------------------
@@ -450,6 +443,11 @@ amil_hidden_fused_kernel(const __grid_constant__ CUtensorMap tmAG,   // stash fp
     const uint32_t r = q * 32 + lane;
     constexpr int PIECES = L / (8 * HIDDEN_EW);   // 32-column pieces per thread (L / 32 pieces over EW / 4 parts)
     const float p_row = vec[C::V_P + r];
+    // ReLU mask words of this thread's row and column part (written by the training forward; rows past N: 0)
+    uint32_t mw[PIECES];
+#pragma unroll
+    for (int ii = 0; ii < PIECES; ++ii)
+      mw[ii] = (row0 + r < a.N) ? __ldg(a.mask + (row0 + r) * (L / 32) + part * PIECES + ii) : 0u;
     mbar_wait(smem_u32(&bar_acc), 0);   // every MMA retired: accumulator complete, both rings idle
     tc_fence_after();
     if (e == 0) MMF_STAMP(a, 6);
@@ -467,7 +465,7 @@ amil_hidden_fused_kernel(const __grid_constant__ CUtensorMap tmAG,   // stash fp
       tmem_ld_wait();
       if (ii + 1 < PIECES) tmem_ld32(tmem + ((q * 32u) << 16) + (cb + 1) * 32, v[(ii + 1) & 1]);
       float (&u)[32] = v[ii & 1];
-      const uint32_t bits = s_mask[r * (L / 32) + cb];
+      const uint32_t bits = mw[ii];
       const float4* dm4 = reinterpret_cast<const float4*>(vec + C::V_DM + cb * 32);
       uint32_t packed[16];
 #pragma unroll

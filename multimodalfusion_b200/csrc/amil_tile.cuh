@@ -22,6 +22,7 @@
 //   GEMM1 ring (NS1 stages of x[128][128B] + W1[L][128B]) overlays the pool from offset 0: H does
 //   not exist before GEMM1 has drained, and Wab loads start only after GEMM1's last MMA retired.
 #pragma once
+#include "amil_head_tail.cuh"
 #include "mmf_ptx.cuh"
 
 namespace mmf {
@@ -62,6 +63,11 @@ struct AmilArgs {
                           // multi-bag buffer; null = one bag of N rows
   float4* zero_ptr;   // fwd (optional): buffer the epilogue warps clear while GEMM1 runs ("zero_grad" of the step)
   long long zero_n4;  // its length in float4
+  uint32_t* mask_out; // fwd train (optional): ReLU mask words [N, L/32], bit j of word w = (h[row][32 w + j] > 0)
+  float* z_out;       // fwd train (optional): z_i = Wk h_i as fp32 [N, zld] from the N = 16 side MMA (needs tmWk)
+  int zld;            // 4 or 8
+  int head_on;        // fwd train (optional): the last CTA to finish runs the folded head (amil_head_tail.cuh)
+  HeadTail head;
   int flags;
   unsigned long long seed;
   // backward only

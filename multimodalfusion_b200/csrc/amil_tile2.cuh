@@ -57,48 +57,20 @@ constexpr uint32_t AMIL2_EPI_THREADS = 256;
 // DROPH / DROPA: train-mode dropout on h / on the attention branches, compile-time: with run-time flags the mask
 // selection (shift, and, compare, select per element and branch) was executed even with dropout off and made up
 // 10 of the ~22 instructions per element pair of the gate epilogue, which bounds the GEMM2 phase (issue-bound).
-// MMF_TILE2_RELAY (round-2 candidate, compiled but NOT yet timed or parity-run on a GPU, hence default 0): the epilogue
-// warps signal "H tile written" and "GEMM2 chunk buffer drained" with a CTA-local arrive, and the otherwise idle warp 3
-// relays ONE cluster-scope arrive per CTA to the leader's barrier — the change that took 11 % off
-// amil_hidden_fused_kernel (profiles/r01i_ncu_full_summary.md). Today every epilogue warp executes
-// mbarrier.arrive.release.cluster itself; in the training form that release follows the st.global stash stores of the
-// chunk and has to wait for them to reach L2 (3 chunks per tile).
-#ifndef MMF_TILE2_RELAY
-#define MMF_TILE2_RELAY 0
-#endif
-// MMF_TILE2_EARLY_GEMM2 (round-2 candidate, compiled but NOT yet run on a GPU, default 0; not combinable with
-// MMF_TILE2_RELAY yet): EPI1 drains the GEMM1 accumulator in COLUMN order — the two epilogue warps of a TMEM lane
-// quadrant take the even / odd 32-column pieces instead of the low / high half — and signals once columns 0..L/2-1 are
-// drained and the matching H k-blocks are written. The MMA issuer then starts GEMM2 chunk 0 (TMEM buffer 0 = columns
-// 0..255, smem k-blocks 0..KB2/2-1) while EPI1 is still working on the upper half, instead of waiting for all of EPI1:
-// about half of the first chunk's exposed 4.1k MMA cycles (profiles/r01i_ncu_full_summary.md) moves under EPI1.
-#ifndef MMF_TILE2_EARLY_GEMM2
-#define MMF_TILE2_EARLY_GEMM2 0
-#endif
-#if MMF_TILE2_EARLY_GEMM2 && MMF_TILE2_RELAY
-#error "MMF_TILE2_EARLY_GEMM2 and MMF_TILE2_RELAY are separate experiments"
-#endif
+// (Round-2 A/B, gpurun_out/ab_r2a.txt: relaying the epilogue's cluster arrives through one thread and starting GEMM2
+// chunk 0 half-way through EPI1 both measured within noise of this version (112.2 vs 111.6 / 112.4 us per step) and
+// were removed.)
 
 template <int L, int D, bool GATED, int MODE, bool DROPH, bool DROPA>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AMIL2_THREADS, 1)
 amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                   const __grid_constant__ CUtensorMap tmWab, const __grid_constant__ CUtensorMap tmH,
-                  const AmilArgs a) {
+                  const __grid_constant__ CUtensorMap tmWk, const AmilArgs a) {
   using C = Amil2Cfg<L, D, GATED>;
-#if MMF_TILE2_EARLY_GEMM2
-  // GEMM2's first TMEM buffer (columns 0..CHN-1) must lie inside the half of the GEMM1 accumulator that EPI1 drains first
-  constexpr bool kEarly = C::CHN * 2 <= L;
-#endif
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full1[C::NS1], bar_empty1[C::NS1];
   __shared__ __align__(8) uint64_t bar_full2[C::NS2], bar_empty2[C::NS2];
   __shared__ __align__(8) uint64_t bar_acc1, bar_h, bar_acc2_full[2], bar_acc2_empty[2];
-#if MMF_TILE2_RELAY
-  __shared__ __align__(8) uint64_t bar_h_local, bar_acc2_done[2];   // CTA-local stages of the relayed signals
-#endif
-#if MMF_TILE2_EARLY_GEMM2
-  __shared__ __align__(8) uint64_t bar_h_lo;                        // lower half of H written, TMEM columns 0..L/2-1 drained
-#endif
   __shared__ uint32_t tmem_base_slot;
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -118,18 +90,11 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     for (int s = 0; s < C::NS1; ++s) { mbar_init(smem_u32(&bar_full1[s]), 1); mbar_init(smem_u32(&bar_empty1[s]), 1); }
     for (int s = 0; s < C::NS2; ++s) { mbar_init(smem_u32(&bar_full2[s]), 1); mbar_init(smem_u32(&bar_empty2[s]), 1); }
     mbar_init(smem_u32(&bar_acc1), 1);
-    mbar_init(smem_u32(&bar_h), MMF_TILE2_RELAY ? 2 : 16);
+    mbar_init(smem_u32(&bar_h), 16);
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&bar_acc2_full[b]), 1);
-      mbar_init(smem_u32(&bar_acc2_empty[b]), MMF_TILE2_RELAY ? 2 : 16);
+      mbar_init(smem_u32(&bar_acc2_empty[b]), 16);
     }
-#if MMF_TILE2_EARLY_GEMM2
-    mbar_init(smem_u32(&bar_h_lo), 16);
-#endif
-#if MMF_TILE2_RELAY
-    mbar_init(smem_u32(&bar_h_local), 8);
-    for (int b = 0; b < 2; ++b) mbar_init(smem_u32(&bar_acc2_done[b]), 8);
-#endif
     fence_barrier_init();
     tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmWab);
   }
@@ -178,6 +143,17 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         tma_load_2d_pair(ring2 + s * C::STAGE2, &tmWab, full, kb * 64, c * C::CHN + (C::CHN / 2) * (int)rank);
       }
     }
+    if (MODE == AMIL_FWD && a.z_out != nullptr) {
+      // side product z = Wk h (head-projected backward): this CTA's 8 rows of the bf16 hi / lo split of the
+      // classifier, all KB2 k-blocks in ONE ring stage (8 rows x 128 B = one swizzle atom per k-block)
+      constexpr int it = C::NCH * C::KB2;
+      constexpr int s = it % C::NS2;
+      mbar_wait(smem_u32(&bar_empty2[s]), ((it / C::NS2) & 1) ^ 1);
+      const uint32_t full = smem_u32(&bar_full2[s]);
+      if (leader) mbar_arrive_expect_tx(full, 2 * C::KB2 * 1024);
+      for (int kb = 0; kb < C::KB2; ++kb)
+        tma_load_2d_pair(ring2 + s * C::STAGE2 + kb * 1024, &tmWk, full, kb * 64, 8 * (int)rank);
+    }
   } else if (warp == 1 && lane == 0 && leader) {
     // =============================== MMA issuer (leader CTA) ===========================
     constexpr uint32_t idesc1 = umma_idesc_bf16(256, 256, 0, 0);
@@ -203,12 +179,7 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     umma_commit_pair_mc(smem_u32(&bar_acc1), 3);
     MMF_STAMP(a, 6);
 
-#if MMF_TILE2_EARLY_GEMM2
-    // k-blocks 0..KB2/2-1 of both H tiles written, TMEM columns 0..L/2-1 drained (or everything, when !kEarly)
-    mbar_wait_cluster(smem_u32(kEarly ? &bar_h_lo : &bar_h), 0);
-#else
     mbar_wait_cluster(smem_u32(&bar_h), 0);   // both CTAs' H tiles written, GEMM1 TMEM columns drained
-#endif
     tc_fence_after();
     MMF_STAMP(a, 7);
     for (int c = 0; c < C::NCH; ++c) {
@@ -216,12 +187,6 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       mbar_wait_cluster(smem_u32(&bar_acc2_empty[buf]), ((c >> 1) & 1) ^ 1);
       tc_fence_after();
       for (int kb = 0; kb < C::KB2; ++kb) {
-#if MMF_TILE2_EARLY_GEMM2
-        if (kEarly && c == 0 && kb == C::KB2 / 2) {   // the upper half of H (and of the TMEM drain) is needed from here on
-          mbar_wait_cluster(smem_u32(&bar_h), 0);
-          tc_fence_after();
-        }
-#endif
         const int it = c * C::KB2 + kb;
         const int s = it % C::NS2;
         const uint32_t ph = (it / C::NS2) & 1;
@@ -237,18 +202,23 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       }
       umma_commit_pair_mc(smem_u32(&bar_acc2_full[buf]), 3);
     }
-    MMF_STAMP(a, 8);
-#if MMF_TILE2_RELAY
-  } else if (warp == 3 && lane == 0) {
-    // =============================== relay thread (both CTAs) ==========================
-    mbar_wait(smem_u32(&bar_h_local), 0);
-    mbar_arrive_cluster(mapa_cluster(smem_u32(&bar_h), 0));
-    for (int c = 0; c < C::NCH; ++c) {
-      const int buf = c & 1;
-      mbar_wait(smem_u32(&bar_acc2_done[buf]), (c >> 1) & 1);
-      mbar_arrive_cluster(mapa_cluster(smem_u32(&bar_acc2_empty[buf]), 0));
+    if (MODE == AMIL_FWD && a.z_out != nullptr) {
+      // z[256, 16] = H_pair · [Wk_hi | Wk_lo]^T into the chunk buffer the last GEMM2 chunk does not use
+      constexpr uint32_t idescz = umma_idesc_bf16(256, 16, 0, 0);
+      constexpr int c = C::NCH, buf = c & 1, it = C::NCH * C::KB2, s = it % C::NS2;
+      mbar_wait_cluster(smem_u32(&bar_acc2_empty[buf]), ((c >> 1) & 1) ^ 1);
+      mbar_wait(smem_u32(&bar_full2[s]), (it / C::NS2) & 1);
+      tc_fence_after();
+      for (int kb = 0; kb < C::KB2; ++kb) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_ss_pair(tmem + buf * C::CHN, umma_desc_sw128(h_base + kb * 16384 + k * 32, 16, 1024),
+                            umma_desc_sw128(ring2 + s * C::STAGE2 + kb * 1024 + k * 32, 16, 1024), idescz, (kb | k) != 0);
+      }
+      umma_commit_pair_mc(smem_u32(&bar_empty2[s]), 3);
+      umma_commit_pair_mc(smem_u32(&bar_acc2_full[buf]), 3);
     }
-#endif
+    MMF_STAMP(a, 8);
   } else if (warp >= 4) {
     // =============================== epilogue warps (both CTAs) ========================
     const uint32_t q = warp & 3;
@@ -298,18 +268,8 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     float t_i = 0.f;
     constexpr int PIECES1 = L / 64;  // 32-column pieces per half
     const int cb0 = half * PIECES1;
-#if MMF_TILE2_EARLY_GEMM2
-    static_assert(PIECES1 % 4 == 0 && C::KB2 == L / 64, "early GEMM2: the column sweep is split in two halves of k-blocks");
-    // piece ii of this warp = global piece 2 ii + half: both warps of a quadrant sweep the columns left to right together
-#define MMF_EPI1_PIECE(ii) (kEarly ? 2 * (ii) + (int)half : cb0 + (ii))
-    const uint32_t h_lo_leader = mapa_cluster(smem_u32(&bar_h_lo), 0);
-#endif
     float v[2][32];
-#if MMF_TILE2_EARLY_GEMM2
-    tmem_ld32(tq + MMF_EPI1_PIECE(0) * 32, v[0]);
-#else
     tmem_ld32(tq + cb0 * 32, v[0]);
-#endif
     // two pieces per iteration so the TMEM double-buffer indices stay static; NOT fully unrolled: the
     // fully unrolled body (8 x ~500 SASS instructions) thrashed the instruction cache
     // (ncu: stall_no_inst 18 % of samples in the backward kernel)
@@ -318,15 +278,9 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 #pragma unroll
       for (int par = 0; par < 2; ++par) {
         const int ii = i2 + par;
-#if MMF_TILE2_EARLY_GEMM2
-        const int cb = MMF_EPI1_PIECE(ii);
-        tmem_ld_wait();
-        if (ii + 1 < PIECES1) tmem_ld32(tq + MMF_EPI1_PIECE(ii + 1) * 32, v[par ^ 1]);
-#else
         const int cb = cb0 + ii;
         tmem_ld_wait();
         if (ii + 1 < PIECES1) tmem_ld32(tq + (cb + 1) * 32, v[par ^ 1]);
-#endif
         float (&u)[32] = v[par];
         const float4* b4p = reinterpret_cast<const float4*>(vec + C::V_B1 + cb * 32);
         uint32_t hb0 = 0xFFFFFFFFu, hb1 = 0xFFFFFFFFu;   // all kept when dropout is off
@@ -343,11 +297,13 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           u[i + 3] = (!DROPH || drop_keep(hb, (i & 15) + 3)) ? r3 : 0.f;
         }
         const uint32_t kb_base = h_base + (cb >> 1) * 16384;
+        uint32_t mword = 0u;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const uint32_t p0 = pack_bf16x2(u[8 * j], u[8 * j + 1]), p1 = pack_bf16x2(u[8 * j + 2], u[8 * j + 3]);
           const uint32_t p2 = pack_bf16x2(u[8 * j + 4], u[8 * j + 5]), p3 = pack_bf16x2(u[8 * j + 6], u[8 * j + 7]);
           st_shared_v4(kb_base + sw128_offset(r, (cb & 1) * 4 + j), p0, p1, p2, p3);
+          if (MODE == AMIL_FWD) mword |= relu_mask_byte(p0, p1, p2, p3) << (8 * j);
           if (MODE == AMIL_BWD_GATE) {
             const uint32_t pk[4] = {p0, p1, p2, p3};
             const float4* dm4 = reinterpret_cast<const float4*>(vec + C::V_DM + cb * 32 + 8 * j);
@@ -361,29 +317,15 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             }
           }
         }
+        // training forward: [h > 0] of the bf16 activations the backward will see, 1 bit per element (the dU epilogue
+        // of the hidden-gradient kernel reads 64 B per row instead of re-deriving the bits from a re-read of H)
+        if (MODE == AMIL_FWD && a.mask_out != nullptr && row_ok) a.mask_out[row * (L / 32) + cb] = mword;
       }
-#if MMF_TILE2_EARLY_GEMM2
-      if (kEarly && i2 + 2 == PIECES1 / 2) {
-        // global pieces 0..PIECES1-1 = columns 0..L/2-1 are drained (the prefetch in flight is for a column >= L/2) and
-        // the H k-blocks 0..KB2/2-1 are in shared memory: GEMM2 chunk 0 may start on them
-        fence_proxy_async_smem();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(h_lo_leader);
-      }
-#endif
     }
     fence_proxy_async_smem();
     tc_fence_before();
     __syncwarp();
-#if MMF_TILE2_RELAY
-    if (lane == 0) mbar_arrive(smem_u32(&bar_h_local));
-#else
     if (lane == 0) mbar_arrive_cluster(h_ready_leader);
-#endif
-#if MMF_TILE2_EARLY_GEMM2
-#undef MMF_EPI1_PIECE
-#endif
     if (e == 0) MMF_STAMP(a, 11);
 
     if (MODE == AMIL_BWD_GATE) sS[half * 128 + r] = t_i;
@@ -518,13 +460,25 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-#if MMF_TILE2_RELAY
-      if (lane == 0) mbar_arrive(smem_u32(&bar_acc2_done[buf]));
-#else
       if (lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&bar_acc2_empty[buf]), 0));
-#endif
     }
 
+    if (MODE == AMIL_FWD && a.z_out != nullptr) {
+      constexpr int c = C::NCH, buf = c & 1;
+      mbar_wait(smem_u32(&bar_acc2_full[buf]), (c >> 1) & 1);
+      tc_fence_after();
+      if (half == 0) {
+        float zv[16];
+        tmem_ld16(tq + buf * C::CHN, zv);
+        tmem_ld_wait();
+        if (row_ok) {   // columns 0..7 = Wk_hi · h, 8..15 = Wk_lo · h
+          float4* zp = reinterpret_cast<float4*>(a.z_out + row * a.zld);
+          zp[0] = make_float4(zv[0] + zv[8], zv[1] + zv[9], zv[2] + zv[10], zv[3] + zv[11]);
+          if (a.zld == 8) zp[1] = make_float4(zv[4] + zv[12], zv[5] + zv[13], zv[6] + zv[14], zv[7] + zv[15]);
+        }
+      }
+      tc_fence_before();
+    }
     if (e == 0) MMF_STAMP(a, 12);
     if (MODE == AMIL_BWD_GATE) {
       if (half == 0) {
@@ -575,6 +529,24 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         }
       }
       if (a.store_h && e == 0) tma_store_wait_all();
+      if (a.head_on) {
+        // folded head: the last CTA of the grid to get here combines all partials and runs head + loss + their backward
+        __threadfence();                            // this thread's partial columns are visible device-wide
+        named_bar_sync(2, AMIL2_EPI_THREADS);       // (also: the H tile's TMA store has finished reading shared memory)
+        if (e == 0) {
+          const unsigned int t = atomicAdd(a.head.ticket, 1u);
+          sRed[8] = (t == gridDim.x - 1) ? 1.f : 0.f;
+        }
+        named_bar_sync(2, AMIL2_EPI_THREADS);
+        if (sRed[8] != 0.f) {
+          if (e == 0) *a.head.ticket = 0u;          // graph replays and the next step start from zero again
+          __threadfence();
+          // scratch: the H tile is dead (softmax weights of up to 4096 tiles + M + reductions)
+          float* s_w = reinterpret_cast<float*>(smem_raw + (pool - smem_u32(smem_raw)));
+          amil_head_tail<L, (int)AMIL2_EPI_THREADS>(a.head, a.partials, (int)((a.N + 127) / 128), s_w,
+                                                    s_w + HEAD_MAX_TILES, e, 2);
+        }
+      }
     }
     if (e == 0) MMF_STAMP(a, 13);
     tc_fence_before();

@@ -42,7 +42,7 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 unsigned long long* g_timing_buffer = nullptr;
 
 struct BwdWs {
-  size_t off_H, off_dG, off_dU, off_cs, off_dbc, off_db1, off_mask, total;
+  size_t off_H, off_dG, off_dU, off_cs, off_dbc, off_db1, off_mask, off_z, total;
 };
 BwdWs bwd_layout(int64_t N, int L, int D, int gated) {
   const int64_t tiles = ((N + 255) / 256) * 2;  // padded to whole CTA pairs
@@ -57,6 +57,7 @@ BwdWs bwd_layout(int64_t N, int L, int D, int gated) {
   w.off_dbc = o; o = align_up(o + (size_t)tiles * 4 * 4, 1024);
   w.off_db1 = o; o = align_up(o + (size_t)tiles * 4 * L * 4, 1024);
   w.off_mask = o; o = align_up(o + (size_t)N * (L / 32) * 4, 1024);   // 1 bit per element of H: [h > 0]
+  w.off_z = o;    o = align_up(o + (size_t)N * 8 * 4, 1024);          // z_i = Wk h_i (head-projected backward), fp32 [N, 4 | 8]
   w.total = o;
   return w;
 }
@@ -154,28 +155,30 @@ int launch_amil(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, 
 // CTA-pair kernel (amil_tile2.cuh): grid = 2 * ceil(N / 256), cluster (2,1,1)
 template <int L, int D, bool GATED, int MODE, bool DROPH, bool DROPA>
 int launch_amil2v(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, const AmilArgs& a,
-                  void* Hbuf, cudaStream_t st) {
+                  void* Hbuf, const void* wk_split, cudaStream_t st) {
   using C = Amil2Cfg<L, D, GATED>;
   auto kern = amil_tile2_kernel<L, D, GATED, MODE, DROPH, DROPA>;
   MMF_CONFIGURE_SMEM(kern, C::SMEM_BYTES);
-  CUtensorMap tmX, tmW1, tmWab, tmH;
+  CUtensorMap tmX, tmW1, tmWab, tmH, tmWk;
   MMF_TRY(make_tmap_bf16(&tmX, x, (uint64_t)N, 1024, (uint64_t)ldx, 128));
   MMF_TRY(make_tmap_bf16(&tmW1, w->W1, L, 1024, 1024, 128));
   MMF_TRY(make_tmap_bf16(&tmWab, w->Wab_packed, (uint64_t)C::NCH * C::CHN, L, L, C::CHN / 2));
   if (Hbuf) MMF_TRY(make_tmap_bf16(&tmH, Hbuf, (uint64_t)N, L, L, 128));
   else tmH = tmX;
+  if (wk_split) MMF_TRY(make_tmap_bf16(&tmWk, wk_split, 16, L, L, 8));   // [Wk_hi ; Wk_lo], 8 rows per CTA of the pair
+  else tmWk = tmX;
   const int pairs = (int)((N + 255) / 256);
-  return launch_pdl(kern, dim3(2 * pairs), dim3(AMIL2_THREADS), C::SMEM_BYTES, st, tmX, tmW1, tmWab, tmH, a);
+  return launch_pdl(kern, dim3(2 * pairs), dim3(AMIL2_THREADS), C::SMEM_BYTES, st, tmX, tmW1, tmWab, tmH, tmWk, a);
 }
 
 template <int L, int D, bool GATED, int MODE>
 int launch_amil2(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, const AmilArgs& a,
-                 void* Hbuf, cudaStream_t st) {
+                 void* Hbuf, const void* wk_split, cudaStream_t st) {
   const bool dh = (a.flags & MMF_DROPOUT_H) != 0, da = (a.flags & MMF_DROPOUT_ATTN) != 0;
-  if (dh) return da ? launch_amil2v<L, D, GATED, MODE, true, true>(x, N, ldx, w, a, Hbuf, st)
-                    : launch_amil2v<L, D, GATED, MODE, true, false>(x, N, ldx, w, a, Hbuf, st);
-  return da ? launch_amil2v<L, D, GATED, MODE, false, true>(x, N, ldx, w, a, Hbuf, st)
-            : launch_amil2v<L, D, GATED, MODE, false, false>(x, N, ldx, w, a, Hbuf, st);
+  if (dh) return da ? launch_amil2v<L, D, GATED, MODE, true, true>(x, N, ldx, w, a, Hbuf, wk_split, st)
+                    : launch_amil2v<L, D, GATED, MODE, true, false>(x, N, ldx, w, a, Hbuf, wk_split, st);
+  return da ? launch_amil2v<L, D, GATED, MODE, false, true>(x, N, ldx, w, a, Hbuf, wk_split, st)
+            : launch_amil2v<L, D, GATED, MODE, false, false>(x, N, ldx, w, a, Hbuf, wk_split, st);
 }
 
 // MMF_TILE_V1=1 selects the single-CTA kernel (kept as the reference implementation of the pair kernel)
@@ -190,12 +193,12 @@ inline bool use_tile_v1() {
 
 template <int MODE>
 int dispatch_amil(int L, int D, int gated, const void* x, int64_t N, int64_t ldx,
-                  const MmfAmilWeights* w, const AmilArgs& a, void* Hbuf, cudaStream_t st) {
+                  const MmfAmilWeights* w, const AmilArgs& a, void* Hbuf, cudaStream_t st, const void* wk_split = nullptr) {
 #define MMF_CASE(LL, DD)                                                                  \
   if (L == LL && D == DD) {                                                               \
     if (!use_tile_v1())                                                                   \
-      return gated ? launch_amil2<LL, DD, true, MODE>(x, N, ldx, w, a, Hbuf, st)          \
-                   : launch_amil2<LL, DD, false, MODE>(x, N, ldx, w, a, Hbuf, st);        \
+      return gated ? launch_amil2<LL, DD, true, MODE>(x, N, ldx, w, a, Hbuf, wk_split, st) \
+                   : launch_amil2<LL, DD, false, MODE>(x, N, ldx, w, a, Hbuf, wk_split, st); \
     return gated ? launch_amil<LL, DD, true, MODE>(x, N, ldx, w, a, Hbuf, st)             \
                  : launch_amil<LL, DD, false, MODE>(x, N, ldx, w, a, Hbuf, st);           \
   }
@@ -214,14 +217,20 @@ int check_amil_common(const void* x, int64_t N, int64_t ldx, const MmfAmilWeight
   return MMF_OK;
 }
 
-template <int L, int D, bool GATED, bool DROP>
-int launch_hidden_fused2(const HiddenFusedArgs& a, const CUtensorMap& tmAG, const CUtensorMap& tmWab,
+template <int L, int D, bool GATED, bool DROP, bool HEADPROJ>
+int launch_hidden_fused3(const HiddenFusedArgs& a, const CUtensorMap& tmAG, const CUtensorMap& tmWab,
                          const CUtensorMap& tmDU, cudaStream_t st) {
   using C = HiddenFusedCfg<L, D, GATED>;
-  auto kern = amil_hidden_fused_kernel<L, D, GATED, DROP>;
+  auto kern = amil_hidden_fused_kernel<L, D, GATED, DROP, HEADPROJ>;
   MMF_CONFIGURE_SMEM(kern, C::SMEM_BYTES);
   const int pairs = (int)((a.N + 255) / 256);
   return launch_pdl(kern, dim3(2 * pairs), dim3(HIDDEN_THREADS), C::SMEM_BYTES, st, tmAG, tmAG, tmWab, tmDU, a);
+}
+template <int L, int D, bool GATED, bool DROP>
+int launch_hidden_fused2(const HiddenFusedArgs& a, const CUtensorMap& tmAG, const CUtensorMap& tmWab,
+                         const CUtensorMap& tmDU, cudaStream_t st) {
+  return a.z ? launch_hidden_fused3<L, D, GATED, DROP, true>(a, tmAG, tmWab, tmDU, st)
+             : launch_hidden_fused3<L, D, GATED, DROP, false>(a, tmAG, tmWab, tmDU, st);
 }
 template <int L, int D, bool GATED>
 int launch_hidden_fused(const HiddenFusedArgs& a, int flags, const CUtensorMap& tmAG, const CUtensorMap& tmWab,
@@ -343,14 +352,27 @@ size_t mmf_amil_bwd_workspace_bytes(int64_t N, int L, int D, int flags) {
   return bwd_layout(N, L, D, flags & MMF_GATED).total;
 }
 
-// Training forward: mmf_amil_fwd that also leaves H (bf16 [N,L]) and the branch activations
-// (fp16 [N,KD], in the dG slot) in the backward workspace, for mmf_amil_bwd(... | MMF_STASHED).
-int mmf_amil_fwd_train(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, int L, int D,
-                       int flags, uint64_t seed, float* A_raw, float* partials, void* workspace,
-                       size_t workspace_bytes, float* zero_buf, int64_t zero_count, void* stream) {
+}  // extern "C"
+
+namespace {
+int check_head(const MmfHeadStep* h, int64_t N) {
+  if (!h->Wk || !h->bk || !h->Wk_split || !h->Y || !h->c || !h->M || !h->ml || !h->hazards || !h->S || !h->loss ||
+      !h->dM || !h->hs || !h->ticket)
+    return MMF_E_INVALID;
+  if (h->K <= 0 || h->K > HEAD_MAX_K) return MMF_E_UNSUPPORTED;
+  if ((N + 127) / 128 > HEAD_MAX_TILES) return MMF_E_UNSUPPORTED;
+  if (reinterpret_cast<uintptr_t>(h->Wk_split) & 15u) return MMF_E_ALIGN;
+  return MMF_OK;
+}
+
+// Training forward: mmf_amil_fwd that also leaves H (bf16 [N,L]), the branch activations (fp16 [N,KD], in the dG
+// slot) and the ReLU mask words in the backward workspace, for mmf_amil_bwd(... | MMF_STASHED); with a head block
+// additionally z = Wk h (fp32 [N, 4|8]) and the folded head step run by the last tile CTA.
+int fwd_train_impl(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, int L, int D, int flags,
+                   uint64_t seed, float* A_raw, float* partials, void* workspace, size_t workspace_bytes,
+                   float* zero_buf, int64_t zero_count, const MmfHeadStep* head, void* stream) {
   MMF_TRY(check_amil_common(x, N, ldx, w, L, D));
   if (!A_raw || !partials || !workspace) return MMF_E_INVALID;
-  if (use_tile_v1()) return MMF_E_UNSUPPORTED;   // the single-CTA reference kernel has no stash epilogue
   const int gated = flags & MMF_GATED;
   const BwdWs lay = bwd_layout(N, L, D, gated);
   if (workspace_bytes < lay.total) return MMF_E_WORKSPACE;
@@ -360,12 +382,53 @@ int mmf_amil_fwd_train(const void* x, int64_t N, int64_t ldx, const MmfAmilWeigh
   a.N = N; a.b1 = w->b1; a.bab = w->bab; a.wc = w->wc; a.bc = w->bc;
   a.A_raw = A_raw; a.partials = partials; a.store_h = 1;
   a.AG = reinterpret_cast<uint16_t*>(ws + lay.off_dG); a.ldag = gated ? 2 * D : D;
+  a.mask_out = reinterpret_cast<uint32_t*>(ws + lay.off_mask);
   if (zero_buf) {
     if ((reinterpret_cast<uintptr_t>(zero_buf) & 15u) || zero_count < 0 || (zero_count & 3)) return MMF_E_ALIGN;
     a.zero_ptr = reinterpret_cast<float4*>(zero_buf); a.zero_n4 = zero_count >> 2;
   }
   a.flags = flags; a.seed = seed; a.dbg = g_timing_buffer;
-  return dispatch_amil<AMIL_FWD>(L, D, gated, x, N, ldx, w, a, ws + lay.off_H, (cudaStream_t)stream);
+  const void* wk_split = nullptr;
+  if (head) {
+    MMF_TRY(check_head(head, N));
+    wk_split = head->Wk_split;
+    a.z_out = reinterpret_cast<float*>(ws + lay.off_z);
+    a.zld = head->K <= 4 ? 4 : 8;
+    a.head_on = 1;
+    HeadTail& t = a.head;
+    t.Wk = head->Wk; t.bk = head->bk; t.Y = reinterpret_cast<const long long*>(head->Y); t.c = head->c;
+    t.alpha = head->alpha; t.eps = head->eps; t.loss_scale = head->loss_scale; t.K = head->K;
+    t.M = head->M; t.ml = head->ml; t.hazards = head->hazards; t.S = head->S;
+    t.Y_hat = reinterpret_cast<long long*>(head->Y_hat); t.loss = head->loss; t.dM = head->dM; t.hs = head->hs;
+    t.dWk = head->dWk; t.dbk = head->dbk; t.ticket = head->ticket;
+  }
+  return dispatch_amil<AMIL_FWD>(L, D, gated, x, N, ldx, w, a, ws + lay.off_H, (cudaStream_t)stream, wk_split);
+}
+}  // namespace
+
+extern "C" {
+
+int mmf_amil_fwd_train(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, int L, int D,
+                       int flags, uint64_t seed, float* A_raw, float* partials, void* workspace,
+                       size_t workspace_bytes, float* zero_buf, int64_t zero_count, void* stream) {
+  return fwd_train_impl(x, N, ldx, w, L, D, flags, seed, A_raw, partials, workspace, workspace_bytes, zero_buf,
+                        zero_count, nullptr, stream);
+}
+
+int mmf_amil_fwd_train_head(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, int L, int D,
+                            int flags, uint64_t seed, float* A_raw, float* partials, void* workspace,
+                            size_t workspace_bytes, float* zero_buf, int64_t zero_count, const MmfHeadStep* head,
+                            void* stream) {
+  if (!head) return MMF_E_INVALID;
+  return fwd_train_impl(x, N, ldx, w, L, D, flags, seed, A_raw, partials, workspace, workspace_bytes, zero_buf,
+                        zero_count, head, stream);
+}
+
+int mmf_pack_head_weights(const float* Wk, int K, int L, void* Wk_split, void* stream) {
+  if (!Wk || !Wk_split || K <= 0 || K > HEAD_MAX_K || L <= 0 || (L & 7)) return MMF_E_INVALID;
+  pack_head_weights_kernel<<<(16 * L + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      Wk, K, L, reinterpret_cast<__nv_bfloat16*>(Wk_split));
+  return launch_status();
 }
 
 namespace {
@@ -455,10 +518,12 @@ int mmf_amil_bwd_gate_stashed(int64_t N, const MmfAmilWeights* w, int L, int D, 
 
 // Stages 1 + 2 of the MMF_STASHED backward fused: the gate backward is the A-operand producer of the dU GEMM
 // (amil_hidden_fused.cuh). Leaves dG and dU in the workspace for the wgrad stage; accumulates dwc, dbab, dbc, db1.
-int mmf_amil_bwd_gate_hidden_stashed(int64_t N, const MmfAmilWeights* w, int L, int D, int flags, uint64_t seed,
-                                     const float* A_raw, const float* ml, const float* M, const float* dM,
-                                     const float* dA_raw, const MmfAmilGrads* g, void* workspace,
-                                     size_t workspace_bytes, void* stream) {
+}  // extern "C"
+namespace {
+int bwd_gate_hidden_stashed_impl(int64_t N, const MmfAmilWeights* w, int L, int D, int flags, uint64_t seed,
+                                 const float* A_raw, const float* ml, const float* M, const float* dM,
+                                 const float* dA_raw, const MmfAmilGrads* g, void* workspace,
+                                 size_t workspace_bytes, const float* hs, int K, void* stream) {
   if (!w || !w->wc || !w->Wab || N <= 0 || !workspace) return MMF_E_INVALID;
   if (!((L == 256 && D == 256) || (L == 512 && D == 384) || (L == 256 && D == 384))) return MMF_E_UNSUPPORTED;
   if (!A_raw || !ml || !M || !dM || !g || !g->dbab || !g->dwc || !g->dbc || !g->db1) return MMF_E_INVALID;
@@ -477,12 +542,39 @@ int mmf_amil_bwd_gate_hidden_stashed(int64_t N, const MmfAmilWeights* w, int L, 
   a.N = N; a.H = reinterpret_cast<const __nv_bfloat16*>(ws + lay.off_H);
   a.A_raw = A_raw; a.ml = ml; a.M = M; a.dM = dM; a.dA_raw = dA_raw; a.wc = w->wc;
   a.dwc = g->dwc; a.dbab = g->dbab; a.dbc = g->dbc; a.db1 = g->db1;
+  a.mask = reinterpret_cast<const uint32_t*>(ws + lay.off_mask);
+  if (hs) {   // head-projected phase A: z was left in the workspace by mmf_amil_fwd_train_head
+    a.z = reinterpret_cast<const float*>(ws + lay.off_z); a.zld = K <= 4 ? 4 : 8; a.hs = hs;
+  }
   a.du_scale = (flags & MMF_DROPOUT_H) ? (1.0f / 0.75f) : 1.0f;
   a.seed = seed; a.dbg = g_timing_buffer;
   cudaStream_t st = (cudaStream_t)stream;
   if (L == 256 && D == 256) return gated ? launch_hidden_fused<256, 256, true>(a, flags, tmAG, tmWab, tmDU, st) : launch_hidden_fused<256, 256, false>(a, flags, tmAG, tmWab, tmDU, st);
   if (L == 512 && D == 384) return gated ? launch_hidden_fused<512, 384, true>(a, flags, tmAG, tmWab, tmDU, st) : launch_hidden_fused<512, 384, false>(a, flags, tmAG, tmWab, tmDU, st);
   return gated ? launch_hidden_fused<256, 384, true>(a, flags, tmAG, tmWab, tmDU, st) : launch_hidden_fused<256, 384, false>(a, flags, tmAG, tmWab, tmDU, st);
+}
+}  // namespace
+extern "C" {
+
+int mmf_amil_bwd_gate_hidden_stashed(int64_t N, const MmfAmilWeights* w, int L, int D, int flags, uint64_t seed,
+                                     const float* A_raw, const float* ml, const float* M, const float* dM,
+                                     const float* dA_raw, const MmfAmilGrads* g, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
+  return bwd_gate_hidden_stashed_impl(N, w, L, D, flags, seed, A_raw, ml, M, dM, dA_raw, g, workspace, workspace_bytes,
+                                      nullptr, 0, stream);
+}
+
+// Backward of the fused training step (mmf_amil_fwd_train_head on the same workspace and head block): the gate + hidden
+// stage reads t_i = dlogits·z_i instead of the 512-long dot products dM·h_i, then the grouped wgrad GEMM.
+int mmf_amil_bwd_head(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, int L, int D, int flags,
+                      uint64_t seed, const float* A_raw, const MmfHeadStep* head, const float* dA_raw,
+                      const MmfAmilGrads* g, void* dx, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!head || !head->ml || !head->M || !head->dM || !head->hs || head->K <= 0 || head->K > HEAD_MAX_K) return MMF_E_INVALID;
+  if (!g || !g->dW1 || !g->db1 || !g->dWab || !g->dbab || !g->dwc || !g->dbc) return MMF_E_INVALID;
+  MMF_TRY(check_amil_common(x, N, ldx, w, L, D));
+  MMF_TRY(bwd_gate_hidden_stashed_impl(N, w, L, D, flags, seed, A_raw, head->ml, head->M, head->dM, dA_raw, g, workspace,
+                                       workspace_bytes, head->hs, head->K, stream));
+  return mmf_amil_bwd_wgrad(x, N, ldx, w, L, D, flags, g, dx, workspace, workspace_bytes, stream);
 }
 
 // Stage 2: dU = (dG Wab + p dM^T) ⊙ relu'(H) [* 1/(1-p)] -> workspace (bf16 [N,L]); db1 += colsum.

@@ -296,6 +296,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+// 16-column variant (the z = Wk h_i side product of the training forward)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -417,6 +429,22 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
+}
+// ReLU mask bits from packed bf16: 0xFFFF per 16-bit half of w whose bf16 value is > 0 (false for -0 and NaN)
+__device__ __forceinline__ uint32_t bf16x2_gt0_mask(uint32_t w) {
+  return __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&w), __float2bfloat162_rn(0.f));
+}
+__device__ __forceinline__ uint32_t prmt_b32(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+  return r;
+}
+// bit i of the result = (element i > 0) for the 8 bf16 values packed in w0..w3 (element 2k = low half of wk):
+// 4 HSET2.BF16 + 2 PRMT + 5 integer ops instead of 16 compares + selects on up-converted floats
+__device__ __forceinline__ uint32_t relu_mask_byte(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+  const uint32_t X = prmt_b32(bf16x2_gt0_mask(w0), bf16x2_gt0_mask(w1), 0x6420u);   // one 0x00 / 0xFF byte per element 0..3
+  const uint32_t Y = prmt_b32(bf16x2_gt0_mask(w2), bf16x2_gt0_mask(w3), 0x6420u);   // elements 4..7
+  return (((X & 0x08040201u) + ((Y & 0x08040201u) << 4)) * 0x01010101u) >> 24;      // byte sum: no carries
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c,
                                              uint32_t d) {

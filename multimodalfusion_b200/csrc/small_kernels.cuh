@@ -310,6 +310,21 @@ __global__ void hazard_head_fwd_kernel(const float* __restrict__ M, int B, int L
   }
 }
 
+// bf16 hi / lo split of the classifier for the forward's z = Wk h side MMA (N = 16: rows 0..7 go to the even CTA of
+// the pair, rows 8..15 to the odd one): row j < K = bf16(Wk[j]), row 8 + j = bf16(Wk[j] - bf16(Wk[j])), others 0.
+__global__ void pack_head_weights_kernel(const float* __restrict__ Wk, int K, int L, __nv_bfloat16* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 16 * L) return;
+  const int r = i / L, c = i - r * L, j = r & 7;
+  float v = 0.f;
+  if (j < K) {
+    const float w = Wk[(long long)j * L + c];
+    const float hi = __bfloat162float(__float2bfloat16_rn(w));
+    v = (r < 8) ? hi : w - hi;
+  }
+  out[i] = __float2bfloat16_rn(v);
+}
+
 // -------------------------------------------------------------------------------------------
 // Single-bag training step tail, ONE launch: combine the tile partials -> M, (m,l); hazard head;
 // nll_surv loss; gradient back to M and to the classifier (dWk, dbk accumulated).

@@ -14,7 +14,7 @@ import torch
 
 from . import _lib
 from ._lib import (ACT_NONE, ACT_RELU, ACT_SELU, ACT_SIGMOID, ACT_TANH, MMF_DROPOUT_ATTN,
-                   MMF_DROPOUT_H, MMF_GATED, MMF_NEED_DX, MMF_STASHED, AmilGrads, AmilWeights, check, lib)
+                   MMF_DROPOUT_H, MMF_GATED, MMF_NEED_DX, MMF_STASHED, AmilGrads, AmilWeights, HeadStep, check, lib)
 
 IN_FEATURES = 1024
 TILE_ROWS = 128
@@ -406,6 +406,73 @@ def amil_head_nll_step(partials, Wk, bk, Y, c, alpha: float, eps: float = 1e-7, 
                                        _p(out["Y_hat"]), _p(out["loss"]), _p(out["dM"]), _p(dWk), _p(dbk),
                                        _stream()), "mmf_amil_head_nll_step")
     return out
+
+
+class FusedStepBuffers:
+    """Caller-owned buffers of the fused batch-1 training step (mmf_amil_fwd_train_head + mmf_amil_bwd_head):
+    the head block's outputs, the z / activation workspace, the score vector and the tile partials. Allocate once
+    per (bag size, model) and reuse every step — the step itself then allocates nothing and is CUDA-graph capturable.
+    Reference loop: utils/core_utils.py:200-247 (model -> nll_surv -> loss / gc -> backward)."""
+
+    def __init__(self, N: int, w: AmilPrepared, flags: int, K: int, device):
+        if not 1 <= K <= 8:
+            raise ValueError("the folded head supports 1..8 classes")
+        f32 = dict(dtype=torch.float32, device=device)
+        self.N, self.K, self.flags = N, K, flags
+        self.workspace = amil_bwd_workspace(N, w, flags, device)
+        self.A_raw = torch.empty(N, **f32)
+        self.partials = torch.empty((N + TILE_ROWS - 1) // TILE_ROWS, w.L + 2, **f32)
+        self.M, self.ml = torch.empty(w.L, **f32), torch.empty(2, **f32)
+        self.hazards, self.S = torch.empty(1, K, **f32), torch.empty(1, K, **f32)
+        self.Y_hat = torch.empty(1, 1, dtype=torch.int64, device=device)
+        self.loss = torch.empty((), **f32)
+        self.dM, self.hs = torch.empty(w.L, **f32), torch.zeros(16, **f32)
+        self.ticket = torch.zeros(1, dtype=torch.int32, device=device)
+        self.Wk_split = torch.empty(16, w.L, dtype=torch.bfloat16, device=device)
+        self._wk_version = None
+
+    def pack_head(self, Wk: torch.Tensor) -> None:
+        """bf16 hi / lo split of the classifier weight for the z = Wk h side MMA; redone when Wk changed."""
+        ver = (Wk.data_ptr(), Wk._version)
+        if ver != self._wk_version:
+            check(lib().mmf_pack_head_weights(_p(Wk), self.K, Wk.shape[1], _p(self.Wk_split), _stream()),
+                  "mmf_pack_head_weights")
+            self._wk_version = ver
+
+    def head_struct(self, Wk, bk, Y, c, alpha, eps, loss_scale, dWk, dbk) -> HeadStep:
+        return HeadStep(_p(Wk), _p(bk), _p(self.Wk_split), self.K, _p(Y), _p(c), float(alpha), float(eps),
+                        float(loss_scale), _p(self.M), _p(self.ml), _p(self.hazards), _p(self.S), _p(self.Y_hat),
+                        _p(self.loss), _p(self.dM), _p(self.hs), _p(dWk), _p(dbk), _p(self.ticket))
+
+
+def amil_fused_step(x: torch.Tensor, w: AmilPrepared, flags: int, seed: int, buf: FusedStepBuffers, Wk, bk, Y, c,
+                    alpha: float, grads: dict, dWk=None, dbk=None, eps: float = 1e-7, loss_scale: float = 1.0,
+                    zero: Optional[torch.Tensor] = None, repack_head: bool = True):
+    """One batch-1 training step of the path / radio AMIL model in THREE launches: fused forward with the head folded
+    into its tail (combine, classifier, hazards, nll_surv, dlogits, dM, dWk, dbk), fused gate + hidden backward with
+    the head-projected phase A, grouped wgrad GEMM. Gradients accumulate into `grads` (dW1, db1, dWab, dbab, dwc,
+    dbc), dWk, dbk; `zero` (the flat gradient buffer that holds them all) is cleared by the forward first.
+    Outputs are left in `buf` (loss, hazards, S, Y_hat, A_raw, M)."""
+    _require_cuda(x, Wk)
+    if x.dtype != torch.bfloat16 or x.dim() != 2 or x.shape[1] != IN_FEATURES or x.stride(1) != 1:
+        raise ValueError("x must be a bf16 [N,1024] tensor with unit inner stride")
+    N = x.shape[0]
+    if N != buf.N:
+        raise ValueError("FusedStepBuffers were sized for another bag")
+    if repack_head:
+        buf.pack_head(Wk)
+    head = buf.head_struct(Wk, bk, Y, c, alpha, eps, loss_scale, dWk, dbk)
+    wst = w.struct()
+    check(lib().mmf_amil_fwd_train_head(_p(x), N, x.stride(0), C.byref(wst), w.L, w.D, flags, seed, _p(buf.A_raw),
+                                        _p(buf.partials), buf.workspace.data_ptr(), buf.workspace.numel(), _p(zero),
+                                        0 if zero is None else zero.numel(), C.byref(head), _stream()),
+          "mmf_amil_fwd_train_head")
+    g = AmilGrads(_p(grads["dW1"]), _p(grads["db1"]), _p(grads["dWab"]), _p(grads["dbab"]),
+                  _p(grads["dwc"]), _p(grads["dbc"]))
+    check(lib().mmf_amil_bwd_head(_p(x), N, x.stride(0), C.byref(wst), w.L, w.D, flags | MMF_STASHED, seed, _p(buf.A_raw),
+                                  C.byref(head), None, C.byref(g), None, buf.workspace.data_ptr(),
+                                  buf.workspace.numel(), _stream()), "mmf_amil_bwd_head")
+    return buf.loss
 
 
 def nll_surv(hazards, S, Y, c, alpha: float, eps: float = 1e-7):
