@@ -225,7 +225,8 @@ def run_ours(args):
     # our launches per step: tile fwd(+stash), cluster head step, fused gate-backward + dU GEMM, grouped wgrad GEMM
     # (recompute mode: + ReLU-mask kernel + column-sum reduce + one ATen fill that zeroes the flat grad buffer;
     # stash mode: the forward kernel clears it)
-    LAUNCHES_PER_STEP = 4 if os.environ.get("MMF_BENCH_BWD", "stash") == "stash" else 7
+    LAUNCHES_PER_STEP = ((3 if os.environ.get("MMF_BENCH_STEP", "fused3") == "fused3" else 4)
+                         if os.environ.get("MMF_BENCH_BWD", "stash") == "stash" else 7)
 
     # backward mode: "stash" (default: the training forward leaves h / branch activations in the backward
     # workspace, no recompute GEMMs) or "recompute" (MMF_BENCH_BWD=recompute: the tile kernel runs again)
@@ -233,7 +234,18 @@ def run_ours(args):
     step_wss = [ops.amil_bwd_workspace(N_BAG, prep, flags, dev) for _ in range(lanes)]
     step_ws = step_wss[0]
 
+    step_mode = os.environ.get("MMF_BENCH_STEP", "fused3")   # fused3 (default) | modular4 (round-1 step, A/B)
+    fbufs = [ops.FusedStepBuffers(N_BAG, prep, flags, K_CLASSES, dev) for _ in range(lanes)]
+    for fb in fbufs:
+        fb.pack_head(Wk)
+
     def step(x, b=0, lane=0):
+        if bwd_mode == "stash" and step_mode == "fused3":
+            # forward (+ fused zero_grad, + folded head: combine, hazards, nll_surv, dlogits, dM, dWk, dbk) ->
+            # gate + hidden backward (head-projected) -> grouped wgrad
+            return ops.amil_fused_step(x, prep, flags, seed, fbufs[lane], Wk, bk, Y, c, 0.0, grads_l[b],
+                                       dWk=views_l[b][6].view(K_CLASSES, L), dbk=views_l[b][7], zero=flats[b],
+                                       repack_head=False)
         if bwd_mode == "stash":   # the training forward clears the step's gradient buffer itself (fused zero_grad)
             A_raw, parts, ws = ops.amil_partials_train(x, prep, flags, seed, workspace=step_wss[lane], zero=flats[b])
         else:

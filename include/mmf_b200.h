@@ -150,13 +150,17 @@ int mmf_amil_fwd_train(const void* x, int64_t N, int64_t ldx, const MmfAmilWeigh
                        size_t workspace_bytes, float* zero_buf, int64_t zero_count, void* stream);
 
 /* ---- fused batch-1 training step (utils/core_utils.py:200-247 for the path / radio AMIL models) ------------------
- * Head block: classifier -> sigmoid -> cumprod (models/model_attention_mil_path.py:57-61), nll_surv
- * (utils/loss_utils.py:22-39) and their backward, run by the LAST tile CTA of the training forward to finish
- * (no separate head launch). Inputs: Wk, bk, Wk_split (mmf_pack_head_weights), K <= 8, Y, c, alpha, eps,
- * loss_scale (1/gc of the reference's gradient accumulation: every gradient of the step is scaled by it).
- * Outputs: M [L], ml [2], hazards / S [K], Y_hat (or NULL), loss [1] (unscaled), dM [L], hs [16] (dlogits and dM.M for
- * the head-projected backward), dWk [K,L] / dbk [K] ACCUMULATED (or NULL).
- * ticket: one uint32 in device memory, zero before the first launch (the kernel leaves it zero). */
+ * THREE launches: mmf_amil_fwd_train_head (fused forward; also leaves z_i = Wk h_i and the ReLU mask words for the
+ * backward), then mmf_amil_bwd_head = [gate + hidden backward whose prologue runs the head] + [grouped wgrad GEMM].
+ * Head block: softmax combine of the tile partials, classifier -> sigmoid -> cumprod
+ * (models/model_attention_mil_path.py:55-61), nll_surv (utils/loss_utils.py:22-39) and their backward — computed
+ * redundantly by every CTA of the gate + hidden kernel while its first tiles are in flight (no head launch).
+ * Inputs: Wk, bk, Wk_split (mmf_pack_head_weights), K <= 8, Y, c, alpha, eps, loss_scale (1/gc of the reference's
+ * gradient accumulation: every gradient of the step is scaled by it).
+ * Outputs (valid after mmf_amil_bwd_head): M [L], ml [2], hazards / S [K], Y_hat (or NULL), loss [1] (unscaled),
+ * dM [L], hs [16] (dlogits, dM.M), dWk [K,L] / dbk [K] ACCUMULATED (or NULL).
+ * Limits: N <= 32768 (256 tile partials merged per CTA); larger bags: mmf_amil_fwd_train + mmf_amil_head_nll_step +
+ * mmf_amil_bwd. */
 typedef struct MmfHeadStep {
   const float* Wk;
   const float* bk;
@@ -175,26 +179,31 @@ typedef struct MmfHeadStep {
   float* hs;
   float* dWk;
   float* dbk;
-  uint32_t* ticket;
 } MmfHeadStep;
 
 /* Wk f32 [K, L] -> bf16 [16, L]: rows 0..K-1 = bf16(Wk), rows 8..8+K-1 = bf16(Wk - bf16(Wk)), other rows zero: the B
  * operand of the N = 16 tensor-core side product z_i = Wk h_i of the training forward (hi + lo: fp32-grade z). */
 int mmf_pack_head_weights(const float* Wk, int K, int L, void* Wk_split_bf16, void* stream);
 
-/* mmf_amil_fwd_train + the head block: additionally leaves z_i = Wk h_i (fp32 [N, 4|8]) in the workspace. With
- * mmf_amil_bwd_head the whole step is THREE launches (forward+head, gate+hidden backward, grouped wgrad). */
+/* mmf_amil_fwd_train that additionally leaves z_i = Wk h_i (fp32 [N, 4|8]) in the workspace (uses head->Wk_split, K). */
 int mmf_amil_fwd_train_head(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, int L, int D,
                             int flags, uint64_t seed, float* A_raw, float* partials, void* workspace,
                             size_t workspace_bytes, float* zero_buf, int64_t zero_count, const MmfHeadStep* head,
                             void* stream);
 
-/* Backward of mmf_amil_fwd_train_head (same workspace, same head block): the pooled embedding feeds the linear
- * classifier directly, so dM = Wk^T dlogits and t_i = dM.h_i = dlogits.z_i — the per-row 512-long dot products of
- * the general backward become K FMAs. flags as in the forward (MMF_STASHED implied). Accumulates into g. */
+/* Head + backward of mmf_amil_fwd_train_head (same workspace, A_raw and partials): the pooled embedding feeds the
+ * linear classifier directly, so dM = Wk^T dlogits and t_i = dM.h_i = dlogits.z_i — the per-row 512-long dot products
+ * of the general backward become K FMAs. flags as in the forward (MMF_STASHED implied). Accumulates into g. */
 int mmf_amil_bwd_head(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, int L, int D, int flags,
-                      uint64_t seed, const float* A_raw, const MmfHeadStep* head, const float* dA_raw,
-                      const MmfAmilGrads* g, void* dx, void* workspace, size_t workspace_bytes, void* stream);
+                      uint64_t seed, const float* A_raw, const float* partials, const MmfHeadStep* head,
+                      const float* dA_raw, const MmfAmilGrads* g, void* dx, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
+/* The head + gate + hidden stage of mmf_amil_bwd_head alone (the wgrad stage is mmf_amil_bwd_wgrad): stage timing, tests. */
+int mmf_amil_bwd_gate_hidden_head(int64_t N, const MmfAmilWeights* w, int L, int D, int flags, uint64_t seed,
+                                  const float* A_raw, const float* partials, const MmfHeadStep* head,
+                                  const float* dA_raw, const MmfAmilGrads* g, void* workspace, size_t workspace_bytes,
+                                  void* stream);
 
 /* Backward of mmf_amil_fwd + combine, given dM = dLoss/dM [L] and optionally dA_raw [N].
  * Recomputes h and the attention activations tile by tile (nothing but A_raw, (m,l), M is kept

@@ -90,7 +90,6 @@ class HeadStep(C.Structure):
         ("Y", C.c_void_p), ("c", C.c_void_p), ("alpha", C.c_float), ("eps", C.c_float), ("loss_scale", C.c_float),
         ("M", C.c_void_p), ("ml", C.c_void_p), ("hazards", C.c_void_p), ("S", C.c_void_p), ("Y_hat", C.c_void_p),
         ("loss", C.c_void_p), ("dM", C.c_void_p), ("hs", C.c_void_p), ("dWk", C.c_void_p), ("dbk", C.c_void_p),
-        ("ticket", C.c_void_p),
     ]
 
 
@@ -116,8 +115,10 @@ SIGNATURES = {
     "mmf_pack_head_weights": (_i, [_vp, _i, _i, _vp, _vp]),
     "mmf_amil_fwd_train_head": (_i, [_vp, _i64, _i64, C.POINTER(AmilWeights), _i, _i, _i, _u64, _vp, _vp, _vp, _sz, _vp,
                                      _i64, C.POINTER(HeadStep), _vp]),
-    "mmf_amil_bwd_head": (_i, [_vp, _i64, _i64, C.POINTER(AmilWeights), _i, _i, _i, _u64, _vp, C.POINTER(HeadStep), _vp,
+    "mmf_amil_bwd_head": (_i, [_vp, _i64, _i64, C.POINTER(AmilWeights), _i, _i, _i, _u64, _vp, _vp, C.POINTER(HeadStep), _vp,
                                C.POINTER(AmilGrads), _vp, _vp, _sz, _vp]),
+    "mmf_amil_bwd_gate_hidden_head": (_i, [_i64, C.POINTER(AmilWeights), _i, _i, _i, _u64, _vp, _vp, C.POINTER(HeadStep),
+                                           _vp, C.POINTER(AmilGrads), _vp, _sz, _vp]),
     "mmf_amil_bwd_gate_stashed": (_i, [_i64, C.POINTER(AmilWeights), _i, _i, _i, _u64, _vp, _vp, _vp, _vp, _vp,
                                        C.POINTER(AmilGrads), _vp, _sz, _vp]),
     "mmf_amil_bwd_gate_hidden_stashed": (_i, [_i64, C.POINTER(AmilWeights), _i, _i, _i, _u64, _vp, _vp, _vp, _vp, _vp,

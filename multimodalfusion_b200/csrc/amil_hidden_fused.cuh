@@ -47,7 +47,11 @@ struct HiddenFusedArgs {
   const uint32_t* mask;     // [N, L/32] ReLU mask words written by the training forward
   const float* z;           // HEADPROJ: [N, zld] = Wk h_i
   int zld;                  // 4 or 8
-  const float* hs;          // HEADPROJ: head scalars (amil_head_tail.cuh): dlogits[0..8), hs[HS_DOT] = dM·M
+  const float* partials;    // HEADPROJ: the forward's tile partials [n_tiles, L + 2]
+  int n_tiles;              //           (<= HEAD_MAX_TILES)
+  float* gparts;            // HEADPROJ: group partials [HEAD_MAX_GROUPS, L + 2] (first-level merge, written here)
+  unsigned int* gflags;     // HEADPROJ: [HEAD_MAX_GROUPS] "group row written" flags, zeroed by the training forward
+  HeadTail head;            // HEADPROJ: the step's head, run in this kernel's prologue (amil_head_tail.cuh)
   const float* dA_raw;      // [N] or null
   const float* wc;          // [D]
   float* dwc;               // [D]  accumulated
@@ -82,8 +86,10 @@ struct HiddenFusedCfg {
   static constexpr uint32_t RING_BYTES = NSB * B_STAGE + NSA * A_STAGE;
   static constexpr uint32_t STAGING = 128u * L * 2u;       // dU tile
   static constexpr uint32_t POOL = RING_BYTES > STAGING ? RING_BYTES : STAGING;
-  // vector region (floats): dM | wc | ds | p
-  static constexpr int V_DM = 0, V_WC = L, V_DS = L + D, V_P = V_DS + 128, V_END = V_P + 128;
+  // vector region (floats): dM | wc | ds | p | head scratch: merged accumulators of the row groups [RG][L],
+  // their (m, l) [RG][2] (8 floats), per-warp partial logits [16][8]
+  static constexpr int V_DM = 0, V_WC = L, V_DS = L + D, V_P = V_DS + 128, V_HACC = V_P + 128,
+                       V_HML = V_HACC + 1024, V_HRED = V_HML + 8, V_END = V_HRED + 128;
   static constexpr uint32_t VEC_BYTES = ((V_END * 4u + 1023u) / 1024u) * 1024u;
   static constexpr uint32_t SMEM_BYTES = POOL + VEC_BYTES + 1024u;
 };
@@ -95,6 +101,10 @@ struct HiddenFusedCfg {
 #ifndef MMF_HIDDEN_RELAY
 #define MMF_HIDDEN_RELAY 1
 #endif
+#ifndef MMF_HEAD_STAMPS
+#define MMF_HEAD_STAMPS 0    // 1: stamps 8-13 time the head prologue instead of the first three slices
+#endif
+#define MMF_HS(i) do { if (MMF_HEAD_STAMPS && e == 0) MMF_STAMP(a, i); } while (0)
 constexpr int HIDDEN_EW = 16;                         // worker (phase A / transform / epilogue) warps: the CUDA-core
                                                      // phases are latency-bound, 16 warps hide ~2x what 8 did
 constexpr int HIDDEN_ET = HIDDEN_EW * 32;             // worker threads
@@ -238,32 +248,205 @@ amil_hidden_fused_kernel(const __grid_constant__ CUtensorMap tmAG,   // stash fp
     const uint32_t e = threadIdx.x - 128;          // 0..HIDDEN_ET-1
     const uint32_t ew = warp - 4;                  // 0..EW-1
     constexpr int ROWS_PER_WARP = 128 / HIDDEN_EW;
-    for (int i = e; i < L; i += HIDDEN_ET) vec[C::V_DM + i] = __ldg(a.dM + i);
-    for (int i = e; i < D; i += HIDDEN_ET) vec[C::V_WC + i] = __ldg(a.wc + i);
+    if (!HEADPROJ) {
+      for (int i = e; i < L; i += HIDDEN_ET) vec[C::V_DM + i] = __ldg(a.dM + i);
+      for (int i = e; i < D; i += HIDDEN_ET) vec[C::V_WC + i] = __ldg(a.wc + i);
+    }
+    // (HEADPROJ: wc is staged after the head's loads have been requested — the head is a chain of L2 round trips on
+    //  the kernel's critical path, nothing may sit in front of its first request)
 
 
     // ---------------- phase A: ds_i, p_i -----------------------------------------------------------------
     if (HEADPROJ) {
-      // t_i = dlogits · z_i (z_i = Wk h_i from the forward), dM·M = dlogits · (logits - bk): K FMAs per row
-      if (e < 128) {
-        const long long row = row0 + e;
-        float ds = 0.f, p = 0.f;
-        if (row < a.N) {
-          const float4 z0 = __ldg(reinterpret_cast<const float4*>(a.z + row * a.zld));
-          float t = __ldg(a.hs + 0) * z0.x;
-          t = fmaf(__ldg(a.hs + 1), z0.y, t);
-          t = fmaf(__ldg(a.hs + 2), z0.z, t);
-          t = fmaf(__ldg(a.hs + 3), z0.w, t);
-          if (a.zld == 8) {
-            const float4 z1 = __ldg(reinterpret_cast<const float4*>(a.z + row * a.zld + 4));
-            t = fmaf(__ldg(a.hs + 4), z1.x, t);
-            t = fmaf(__ldg(a.hs + 5), z1.y, t);
-            t = fmaf(__ldg(a.hs + 6), z1.z, t);
-            t = fmaf(__ldg(a.hs + 7), z1.w, t);
+      // ---- the step's head, redundantly in every CTA (amil_head_tail.cuh); CTA 0 writes its outputs ----------
+      const HeadTail& h = a.head;
+      constexpr int CP = L / 2, RG = HIDDEN_ET / CP;     // column pairs; row groups (2 at L = 512, 4 at L = 256)
+      static_assert(RG * L <= 1024 && RG <= 4, "head scratch");
+      const int cp = (int)e % CP, rg = (int)e / CP;
+      const int K = h.K;
+      // every global input of the prologue is requested before the first use: one L2 round trip for all of them
+      float2 wk[HEAD_MAX_K];
+#pragma unroll
+      for (int j = 0; j < HEAD_MAX_K; ++j)
+        wk[j] = (j < K) ? __ldg(reinterpret_cast<const float2*>(h.Wk + (long long)j * L + 2 * cp)) : make_float2(0.f, 0.f);
+      const float bk_l = ((int)lane < K) ? __ldg(h.bk + lane) : 0.f;   // lane j <-> class j in the scalar section
+      const int y = (int)__ldg(h.Y);
+      const float cb = __ldg(h.c);
+      const long long prow = row0 + e;               // phase-A row of threads e < 128
+      const bool prow_ok = e < 128 && prow < a.N;
+      float4 z0 = make_float4(0.f, 0.f, 0.f, 0.f), z1 = z0;
+      float s_raw = 0.f, dA = 0.f;
+      if (prow_ok) {
+        z0 = __ldg(reinterpret_cast<const float4*>(a.z + prow * a.zld));
+        if (a.zld == 8) z1 = __ldg(reinterpret_cast<const float4*>(a.z + prow * a.zld + 4));
+        s_raw = __ldg(a.A_raw + prow);
+        if (a.dA_raw) dA = __ldg(a.dA_raw + prow);
+      }
+      float wc_stage = 0.f;
+      if ((int)e < D) wc_stage = __ldg(a.wc + e);
+      static_assert(D <= HIDDEN_ET, "wc staged one element per thread");
+      float* s_hacc = vec + C::V_HACC;
+      float* s_hml = vec + C::V_HML;
+      float* s_hred = vec + C::V_HRED;
+      MMF_HS(8);
+      // Two-level merge of the tile partials (ONE copy of the code, run once or twice). Every CTA needs the pooled
+      // embedding, but 128 CTAs each reading all 128 partial rows is 34 MB of L2 reads of the same 263 KB (measured:
+      // 21k cycles, r2_phase5.log). So CTA g < n_groups first merges rows [16 g, 16 g + 16) into gparts[g] and raises
+      // gflags[g]; then every CTA merges the <= 16 group rows. CTAs 0..15 are scheduled first and wait for nobody
+      // before raising their flag: no deadlock at any grid size.
+      const int n_groups = (a.n_tiles + HEAD_GROUP - 1) / HEAD_GROUP;
+      const bool two_level = n_groups > 1;
+      PoolAcc pm = {-CUDART_INF_F, 0.f, 0.f, 0.f};
+#pragma unroll 1
+      for (int pass = (two_level && (int)blockIdx.x < n_groups) ? 0 : 1; pass < 2; ++pass) {
+        const float* rows = a.partials;
+        int count = a.n_tiles;
+        if (two_level) {
+          if (pass == 0) {
+            rows += (long long)blockIdx.x * HEAD_GROUP * (L + 2);
+            count = min(HEAD_GROUP, a.n_tiles - (int)blockIdx.x * HEAD_GROUP);
+          } else {
+            if ((int)e < n_groups) {
+              uint32_t v = 0, spins = 0;
+              do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.gflags + e) : "memory");
+                if (++spins > (1u << 26)) { printf("mmf: head group flag %d never raised (block %d)\n", (int)e, (int)blockIdx.x); __trap(); }
+              } while (v == 0u);
+            }
+            named_bar_sync(1, HIDDEN_ET);
+            MMF_HS(10);
+            rows = a.gparts; count = n_groups;
           }
-          p = __expf(__ldg(a.A_raw + row) - __ldg(a.ml)) / __ldg(a.ml + 1);
-          ds = p * (t - __ldg(a.hs + HS_DOT));
-          if (a.dA_raw) ds += __ldg(a.dA_raw + row);
+        }
+        // per-thread online merge of the thread's rows, then the row groups meet in shared memory
+        const PoolAcc r = combine_rows_online<L>(rows, count, cp, rg, RG);
+        named_bar_sync(1, HIDDEN_ET);    // (the previous pass's readers are done with the scratch)
+        *reinterpret_cast<float2*>(s_hacc + rg * L + 2 * cp) = make_float2(r.ax, r.ay);
+        if (cp == 0) { s_hml[2 * rg] = r.m; s_hml[2 * rg + 1] = r.l; }
+        named_bar_sync(1, HIDDEN_ET);
+        pm = PoolAcc{-CUDART_INF_F, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int g2 = 0; g2 < RG; ++g2) pm.m = fmaxf(pm.m, s_hml[2 * g2]);
+#pragma unroll
+        for (int g2 = 0; g2 < RG; ++g2) {
+          const float sc = (s_hml[2 * g2] > -CUDART_INF_F) ? __expf(s_hml[2 * g2] - pm.m) : 0.f;
+          const float2 ac = *reinterpret_cast<const float2*>(s_hacc + g2 * L + 2 * cp);
+          pm.l = fmaf(s_hml[2 * g2 + 1], sc, pm.l);
+          pm.ax = fmaf(ac.x, sc, pm.ax);
+          pm.ay = fmaf(ac.y, sc, pm.ay);
+        }
+        if (two_level && pass == 0) {
+          float* grow = a.gparts + (long long)blockIdx.x * (L + 2);
+          if (rg == 0) *reinterpret_cast<float2*>(grow + 2 + 2 * cp) = make_float2(pm.ax, pm.ay);
+          if (e == 0) *reinterpret_cast<float2*>(grow) = make_float2(pm.m, pm.l);
+          named_bar_sync(1, HIDDEN_ET);   // the row's stores are ordered before the release below
+          if (e == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.gflags + blockIdx.x), "r"(1u) : "memory");
+          MMF_HS(9);
+        }
+      }
+      MMF_HS(11);
+      const float m = pm.m, l = pm.l;
+      const float inv_l = 1.f / l;
+      const float M0 = pm.ax * inv_l, M1 = pm.ay * inv_l;
+      // logits - bk: the threads of row group 0 hold every column pair once
+#pragma unroll
+      for (int j = 0; j < HEAD_MAX_K; ++j) {
+        if (j < K && rg == 0) {   // (warp-uniform: a warp lies inside one row group)
+          const float d = warp_sum(fmaf(M0, wk[j].x, M1 * wk[j].y));
+          if (lane == 0) s_hred[ew * HEAD_MAX_K + j] = d;
+        }
+      }
+      named_bar_sync(1, HIDDEN_ET);
+      MMF_HS(12);
+      if ((int)e < D) vec[C::V_WC + e] = wc_stage;
+      // hazards, survival function, nll_surv and its gradient (closed form, amil_head_tail.cuh) by ONE warp, lane j =
+      // class j; the K dlogits and dM·M go to the other warps through shared memory
+      float* s_dl = s_hacc;   // [HEAD_MAX_K] dlogits | [8] dM·M  (the merge scratch is dead: every thread read it before the barrier above)
+      if (ew == 0) {
+        constexpr int NW0 = CP / 32;   // the warps of row group 0 are the only ones with partial logits
+        const int j = (int)lane;
+        float lgm = 0.f;
+        if (j < K)
+#pragma unroll
+          for (int w = 0; w < NW0; ++w) lgm += s_hred[w * HEAD_MAX_K + j];
+        const float lg = lgm + bk_l;
+        const float hz = (j < K) ? 1.f / (1.f + expf(-lg)) : 0.f;
+        float sv = 1.f - hz;             // inclusive product scan over the classes: S(j)
+#pragma unroll
+        for (int o = 1; o < HEAD_MAX_K; o <<= 1) {
+          const float t = __shfl_up_sync(0xffffffffu, sv, o);
+          if (j >= o) sv *= t;
+        }
+        const float sp_y = (y > 0) ? __shfl_sync(0xffffffffu, sv, y > 0 ? y - 1 : 0) : 1.f;   // S(y-1)
+        const float h_y = __shfl_sync(0xffffffffu, hz, y), sp_y1 = __shfl_sync(0xffffffffu, sv, y);
+        const float alpha = h.alpha, eps = h.eps;
+        const float c1 = (y > 0 && sp_y >= eps) ? (1.f - cb) : 0.f;          // h_j, j <= y-1
+        const float c2 = (h_y >= eps) ? (1.f - cb) : 0.f;                    // -(1 - h_y), j == y
+        const float c3 = (sp_y1 >= eps) ? (1.f - alpha) * cb : 0.f;          // h_j, j <= y
+        float dl = hz * ((j <= y - 1 ? c1 : 0.f) + (j <= y ? c3 : 0.f)) - (j == y ? c2 * (1.f - hz) : 0.f);
+        dl = (j < K) ? dl * h.loss_scale : 0.f;
+        const float dot = warp_sum(dl * lgm);          // dM·M = sum_j dlogit_j (logit_j - bk_j)
+        float bv = (j < K) ? lg : -CUDART_INF_F;       // argmax, first maximum (torch.topk on the logits)
+        int bi = j;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (j < HEAD_MAX_K) s_dl[j] = dl;
+        if (j == 0) s_dl[HEAD_MAX_K] = dot;
+        if (blockIdx.x == 0) {
+          if (j < K) {
+            h.hazards[j] = hz; h.S[j] = sv;
+            if (h.dbk) h.dbk[j] += dl;
+          }
+          if (j < HEAD_MAX_K) h.hs[j] = dl;
+          if (j == 0) {
+            h.ml[0] = m; h.ml[1] = l;
+            h.hs[HS_DOT] = dot;
+            if (h.Y_hat) *h.Y_hat = bi;
+            const float unc = -(1.f - cb) * (logf(fmaxf(sp_y, eps)) + logf(fmaxf(h_y, eps)));
+            const float cen = -cb * logf(fmaxf(sp_y1, eps));
+            *h.loss = (1.f - alpha) * (cen + unc) + alpha * unc;
+          }
+        }
+      }
+      named_bar_sync(1, HIDDEN_ET);
+      float dlv[HEAD_MAX_K];
+#pragma unroll
+      for (int j = 0; j < HEAD_MAX_K; ++j) dlv[j] = s_dl[j];
+      const float dot = s_dl[HEAD_MAX_K];
+      float d0 = 0.f, d1 = 0.f;      // dM = Wk^T dlogits, this thread's two columns
+#pragma unroll
+      for (int j = 0; j < HEAD_MAX_K; ++j) {
+        d0 = fmaf(dlv[j], wk[j].x, d0);
+        d1 = fmaf(dlv[j], wk[j].y, d1);
+      }
+      if (rg == 0) *reinterpret_cast<float2*>(vec + C::V_DM + 2 * cp) = make_float2(d0, d1);
+      if (blockIdx.x == 0 && rg == 0) {
+        *reinterpret_cast<float2*>(h.M + 2 * cp) = make_float2(M0, M1);
+        *reinterpret_cast<float2*>(h.dM + 2 * cp) = make_float2(d0, d1);
+        if (h.dWk) {
+#pragma unroll
+          for (int j = 0; j < HEAD_MAX_K; ++j)
+            if (j < K) {   // (scalar accesses: dWk may sit at any 4-byte offset of a flat gradient buffer)
+              float* dw = h.dWk + (long long)j * L + 2 * cp;
+              dw[0] = fmaf(dlv[j], M0, dw[0]);
+              dw[1] = fmaf(dlv[j], M1, dw[1]);
+            }
+        }
+      }
+      MMF_HS(13);
+      // ---- phase A: t_i = dlogits · z_i, p_i from the global (m, l) just formed -----------------------------
+      if (e < 128) {
+        float ds = 0.f, p = 0.f;
+        if (prow_ok) {
+          float t = dlv[0] * z0.x;
+          t = fmaf(dlv[1], z0.y, t); t = fmaf(dlv[2], z0.z, t); t = fmaf(dlv[3], z0.w, t);
+          t = fmaf(dlv[4], z1.x, t); t = fmaf(dlv[5], z1.y, t); t = fmaf(dlv[6], z1.z, t); t = fmaf(dlv[7], z1.w, t);
+          p = __expf(s_raw - m) * inv_l;
+          ds = p * (t - dot) + dA;
         }
         vec[C::V_DS + e] = ds;
         vec[C::V_P + e] = p;
@@ -367,7 +550,7 @@ amil_hidden_fused_kernel(const __grid_constant__ CUtensorMap tmAG,   // stash fp
       const float wcv[4] = {wc4.x, wc4.y, wc4.z, wc4.w};
       float acc_wc[4] = {}, acc_a[4] = {}, acc_g[4] = {};
       mbar_wait(smem_u32(&bar_afull[s]), (kp / C::NSA) & 1);
-      if (e == 0 && kp < 3) MMF_STAMP(a, 8 + 2 * kp);
+      if (!MMF_HEAD_STAMPS && e == 0 && kp < 3) MMF_STAMP(a, 8 + 2 * kp);
       uint8_t* ta = pool_ptr + (a_ring - pool) + s * C::A_STAGE;
 #pragma unroll
       for (int u = 0; u < RPT; ++u) {
@@ -415,7 +598,7 @@ amil_hidden_fused_kernel(const __grid_constant__ CUtensorMap tmAG,   // stash fp
       }
       fence_proxy_async_smem();
       __syncwarp();
-      if (e == 0 && kp < 3) MMF_STAMP(a, 9 + 2 * kp);
+      if (!MMF_HEAD_STAMPS && e == 0 && kp < 3) MMF_STAMP(a, 9 + 2 * kp);
       if (lane == 0) {
         if (!MMF_HIDDEN_RELAY) mbar_arrive_cluster(a_ready_leader + s * 8u);   // bar_aready[s] of the leader
         mbar_arrive(smem_u32(&bar_astore[s]));   // the store thread (warp 2) relays to the MMA and writes the stage out as dG

@@ -66,8 +66,7 @@ struct AmilArgs {
   uint32_t* mask_out; // fwd train (optional): ReLU mask words [N, L/32], bit j of word w = (h[row][32 w + j] > 0)
   float* z_out;       // fwd train (optional): z_i = Wk h_i as fp32 [N, zld] from the N = 16 side MMA (needs tmWk)
   int zld;            // 4 or 8
-  int head_on;        // fwd train (optional): the last CTA to finish runs the folded head (amil_head_tail.cuh)
-  HeadTail head;
+  unsigned int* gflags; // fwd train (optional): [HEAD_MAX_GROUPS] flags of the backward's two-level head merge, cleared here
   int flags;
   unsigned long long seed;
   // backward only

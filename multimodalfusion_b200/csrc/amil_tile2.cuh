@@ -252,6 +252,7 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     for (int i = e; i < D; i += AMIL2_EPI_THREADS) vec[C::V_WC + i] = __ldg(a.wc + i);
     named_bar_sync(4, AMIL2_EPI_THREADS);
     if (e == 0) MMF_STAMP(a, 9);
+    if (MODE == AMIL_FWD && a.gflags != nullptr && blockIdx.x == 0 && e < (uint32_t)HEAD_MAX_GROUPS) a.gflags[e] = 0u;
     if (MODE == AMIL_FWD && a.zero_ptr != nullptr) {
       // fused zero_grad: the epilogue warps have nothing to do until GEMM1 retires (~16k cycles); they clear the
       // step's gradient accumulators (a separate fill kernel costs ~8 us per step with its two kernel boundaries)
@@ -529,24 +530,6 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         }
       }
       if (a.store_h && e == 0) tma_store_wait_all();
-      if (a.head_on) {
-        // folded head: the last CTA of the grid to get here combines all partials and runs head + loss + their backward
-        __threadfence();                            // this thread's partial columns are visible device-wide
-        named_bar_sync(2, AMIL2_EPI_THREADS);       // (also: the H tile's TMA store has finished reading shared memory)
-        if (e == 0) {
-          const unsigned int t = atomicAdd(a.head.ticket, 1u);
-          sRed[8] = (t == gridDim.x - 1) ? 1.f : 0.f;
-        }
-        named_bar_sync(2, AMIL2_EPI_THREADS);
-        if (sRed[8] != 0.f) {
-          if (e == 0) *a.head.ticket = 0u;          // graph replays and the next step start from zero again
-          __threadfence();
-          // scratch: the H tile is dead (softmax weights of up to 4096 tiles + M + reductions)
-          float* s_w = reinterpret_cast<float*>(smem_raw + (pool - smem_u32(smem_raw)));
-          amil_head_tail<L, (int)AMIL2_EPI_THREADS>(a.head, a.partials, (int)((a.N + 127) / 128), s_w,
-                                                    s_w + HEAD_MAX_TILES, e, 2);
-        }
-      }
     }
     if (e == 0) MMF_STAMP(a, 13);
     tc_fence_before();

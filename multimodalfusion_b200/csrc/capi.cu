@@ -42,7 +42,7 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 unsigned long long* g_timing_buffer = nullptr;
 
 struct BwdWs {
-  size_t off_H, off_dG, off_dU, off_cs, off_dbc, off_db1, off_mask, off_z, total;
+  size_t off_H, off_dG, off_dU, off_cs, off_dbc, off_db1, off_mask, off_z, off_gparts, off_gflags, total;
 };
 BwdWs bwd_layout(int64_t N, int L, int D, int gated) {
   const int64_t tiles = ((N + 255) / 256) * 2;  // padded to whole CTA pairs
@@ -58,6 +58,8 @@ BwdWs bwd_layout(int64_t N, int L, int D, int gated) {
   w.off_db1 = o; o = align_up(o + (size_t)tiles * 4 * L * 4, 1024);
   w.off_mask = o; o = align_up(o + (size_t)N * (L / 32) * 4, 1024);   // 1 bit per element of H: [h > 0]
   w.off_z = o;    o = align_up(o + (size_t)N * 8 * 4, 1024);          // z_i = Wk h_i (head-projected backward), fp32 [N, 4 | 8]
+  w.off_gparts = o; o = align_up(o + (size_t)HEAD_MAX_GROUPS * (L + 2) * 4, 1024);   // head: first-level group partials
+  w.off_gflags = o; o = align_up(o + (size_t)HEAD_MAX_GROUPS * 4, 1024);             //       and their "written" flags
   w.total = o;
   return w;
 }
@@ -357,7 +359,7 @@ size_t mmf_amil_bwd_workspace_bytes(int64_t N, int L, int D, int flags) {
 namespace {
 int check_head(const MmfHeadStep* h, int64_t N) {
   if (!h->Wk || !h->bk || !h->Wk_split || !h->Y || !h->c || !h->M || !h->ml || !h->hazards || !h->S || !h->loss ||
-      !h->dM || !h->hs || !h->ticket)
+      !h->dM || !h->hs)
     return MMF_E_INVALID;
   if (h->K <= 0 || h->K > HEAD_MAX_K) return MMF_E_UNSUPPORTED;
   if ((N + 127) / 128 > HEAD_MAX_TILES) return MMF_E_UNSUPPORTED;
@@ -394,13 +396,7 @@ int fwd_train_impl(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* 
     wk_split = head->Wk_split;
     a.z_out = reinterpret_cast<float*>(ws + lay.off_z);
     a.zld = head->K <= 4 ? 4 : 8;
-    a.head_on = 1;
-    HeadTail& t = a.head;
-    t.Wk = head->Wk; t.bk = head->bk; t.Y = reinterpret_cast<const long long*>(head->Y); t.c = head->c;
-    t.alpha = head->alpha; t.eps = head->eps; t.loss_scale = head->loss_scale; t.K = head->K;
-    t.M = head->M; t.ml = head->ml; t.hazards = head->hazards; t.S = head->S;
-    t.Y_hat = reinterpret_cast<long long*>(head->Y_hat); t.loss = head->loss; t.dM = head->dM; t.hs = head->hs;
-    t.dWk = head->dWk; t.dbk = head->dbk; t.ticket = head->ticket;
+    a.gflags = reinterpret_cast<unsigned int*>(ws + lay.off_gflags);
   }
   return dispatch_amil<AMIL_FWD>(L, D, gated, x, N, ldx, w, a, ws + lay.off_H, (cudaStream_t)stream, wk_split);
 }
@@ -523,10 +519,11 @@ namespace {
 int bwd_gate_hidden_stashed_impl(int64_t N, const MmfAmilWeights* w, int L, int D, int flags, uint64_t seed,
                                  const float* A_raw, const float* ml, const float* M, const float* dM,
                                  const float* dA_raw, const MmfAmilGrads* g, void* workspace,
-                                 size_t workspace_bytes, const float* hs, int K, void* stream) {
+                                 size_t workspace_bytes, const MmfHeadStep* head, const float* partials, void* stream) {
   if (!w || !w->wc || !w->Wab || N <= 0 || !workspace) return MMF_E_INVALID;
   if (!((L == 256 && D == 256) || (L == 512 && D == 384) || (L == 256 && D == 384))) return MMF_E_UNSUPPORTED;
-  if (!A_raw || !ml || !M || !dM || !g || !g->dbab || !g->dwc || !g->dbc || !g->db1) return MMF_E_INVALID;
+  if (!A_raw || !g || !g->dbab || !g->dwc || !g->dbc || !g->db1) return MMF_E_INVALID;
+  if (!head && (!ml || !M || !dM)) return MMF_E_INVALID;
   if (N > 0x7fffff00LL) return MMF_E_INVALID;
   const int gated = flags & MMF_GATED;
   const BwdWs lay = bwd_layout(N, L, D, gated);
@@ -543,8 +540,19 @@ int bwd_gate_hidden_stashed_impl(int64_t N, const MmfAmilWeights* w, int L, int 
   a.A_raw = A_raw; a.ml = ml; a.M = M; a.dM = dM; a.dA_raw = dA_raw; a.wc = w->wc;
   a.dwc = g->dwc; a.dbab = g->dbab; a.dbc = g->dbc; a.db1 = g->db1;
   a.mask = reinterpret_cast<const uint32_t*>(ws + lay.off_mask);
-  if (hs) {   // head-projected phase A: z was left in the workspace by mmf_amil_fwd_train_head
-    a.z = reinterpret_cast<const float*>(ws + lay.off_z); a.zld = K <= 4 ? 4 : 8; a.hs = hs;
+  if (head) {   // the step's head runs in the kernel's prologue; z was left in the workspace by mmf_amil_fwd_train_head
+    MMF_TRY(check_head(head, N));
+    if (!partials) return MMF_E_INVALID;
+    a.z = reinterpret_cast<const float*>(ws + lay.off_z); a.zld = head->K <= 4 ? 4 : 8;
+    a.partials = partials; a.n_tiles = (int)((N + 127) / 128);
+    a.gparts = reinterpret_cast<float*>(ws + lay.off_gparts);
+    a.gflags = reinterpret_cast<unsigned int*>(ws + lay.off_gflags);
+    HeadTail& t = a.head;
+    t.Wk = head->Wk; t.bk = head->bk; t.Y = reinterpret_cast<const long long*>(head->Y); t.c = head->c;
+    t.alpha = head->alpha; t.eps = head->eps; t.loss_scale = head->loss_scale; t.K = head->K;
+    t.M = head->M; t.ml = head->ml; t.hazards = head->hazards; t.S = head->S;
+    t.Y_hat = reinterpret_cast<long long*>(head->Y_hat); t.loss = head->loss; t.dM = head->dM; t.hs = head->hs;
+    t.dWk = head->dWk; t.dbk = head->dbk;
   }
   a.du_scale = (flags & MMF_DROPOUT_H) ? (1.0f / 0.75f) : 1.0f;
   a.seed = seed; a.dbg = g_timing_buffer;
@@ -561,19 +569,30 @@ int mmf_amil_bwd_gate_hidden_stashed(int64_t N, const MmfAmilWeights* w, int L, 
                                      const float* dA_raw, const MmfAmilGrads* g, void* workspace,
                                      size_t workspace_bytes, void* stream) {
   return bwd_gate_hidden_stashed_impl(N, w, L, D, flags, seed, A_raw, ml, M, dM, dA_raw, g, workspace, workspace_bytes,
-                                      nullptr, 0, stream);
+                                      nullptr, nullptr, stream);
+}
+
+// gate + hidden stage of mmf_amil_bwd_head alone (stage timing / tests)
+int mmf_amil_bwd_gate_hidden_head(int64_t N, const MmfAmilWeights* w, int L, int D, int flags, uint64_t seed,
+                                  const float* A_raw, const float* partials, const MmfHeadStep* head,
+                                  const float* dA_raw, const MmfAmilGrads* g, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
+  if (!head) return MMF_E_INVALID;
+  return bwd_gate_hidden_stashed_impl(N, w, L, D, flags, seed, A_raw, nullptr, nullptr, nullptr, dA_raw, g, workspace,
+                                      workspace_bytes, head, partials, stream);
 }
 
 // Backward of the fused training step (mmf_amil_fwd_train_head on the same workspace and head block): the gate + hidden
 // stage reads t_i = dlogits·z_i instead of the 512-long dot products dM·h_i, then the grouped wgrad GEMM.
 int mmf_amil_bwd_head(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, int L, int D, int flags,
-                      uint64_t seed, const float* A_raw, const MmfHeadStep* head, const float* dA_raw,
-                      const MmfAmilGrads* g, void* dx, void* workspace, size_t workspace_bytes, void* stream) {
-  if (!head || !head->ml || !head->M || !head->dM || !head->hs || head->K <= 0 || head->K > HEAD_MAX_K) return MMF_E_INVALID;
+                      uint64_t seed, const float* A_raw, const float* partials, const MmfHeadStep* head,
+                      const float* dA_raw, const MmfAmilGrads* g, void* dx, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+  if (!head) return MMF_E_INVALID;
   if (!g || !g->dW1 || !g->db1 || !g->dWab || !g->dbab || !g->dwc || !g->dbc) return MMF_E_INVALID;
   MMF_TRY(check_amil_common(x, N, ldx, w, L, D));
-  MMF_TRY(bwd_gate_hidden_stashed_impl(N, w, L, D, flags, seed, A_raw, head->ml, head->M, head->dM, dA_raw, g, workspace,
-                                       workspace_bytes, head->hs, head->K, stream));
+  MMF_TRY(bwd_gate_hidden_stashed_impl(N, w, L, D, flags, seed, A_raw, nullptr, nullptr, nullptr, dA_raw, g, workspace,
+                                       workspace_bytes, head, partials, stream));
   return mmf_amil_bwd_wgrad(x, N, ldx, w, L, D, flags, g, dx, workspace, workspace_bytes, stream);
 }
 

@@ -427,7 +427,6 @@ class FusedStepBuffers:
         self.Y_hat = torch.empty(1, 1, dtype=torch.int64, device=device)
         self.loss = torch.empty((), **f32)
         self.dM, self.hs = torch.empty(w.L, **f32), torch.zeros(16, **f32)
-        self.ticket = torch.zeros(1, dtype=torch.int32, device=device)
         self.Wk_split = torch.empty(16, w.L, dtype=torch.bfloat16, device=device)
         self._wk_version = None
 
@@ -442,15 +441,15 @@ class FusedStepBuffers:
     def head_struct(self, Wk, bk, Y, c, alpha, eps, loss_scale, dWk, dbk) -> HeadStep:
         return HeadStep(_p(Wk), _p(bk), _p(self.Wk_split), self.K, _p(Y), _p(c), float(alpha), float(eps),
                         float(loss_scale), _p(self.M), _p(self.ml), _p(self.hazards), _p(self.S), _p(self.Y_hat),
-                        _p(self.loss), _p(self.dM), _p(self.hs), _p(dWk), _p(dbk), _p(self.ticket))
+                        _p(self.loss), _p(self.dM), _p(self.hs), _p(dWk), _p(dbk))
 
 
 def amil_fused_step(x: torch.Tensor, w: AmilPrepared, flags: int, seed: int, buf: FusedStepBuffers, Wk, bk, Y, c,
                     alpha: float, grads: dict, dWk=None, dbk=None, eps: float = 1e-7, loss_scale: float = 1.0,
                     zero: Optional[torch.Tensor] = None, repack_head: bool = True):
-    """One batch-1 training step of the path / radio AMIL model in THREE launches: fused forward with the head folded
-    into its tail (combine, classifier, hazards, nll_surv, dlogits, dM, dWk, dbk), fused gate + hidden backward with
-    the head-projected phase A, grouped wgrad GEMM. Gradients accumulate into `grads` (dW1, db1, dWab, dbab, dwc,
+    """One batch-1 training step of the path / radio AMIL model in THREE launches: fused forward (+ z = Wk h and the
+    ReLU mask words), fused gate + hidden backward whose prologue runs the head (combine, classifier, hazards,
+    nll_surv, dlogits, dM, dWk, dbk) and whose phase A is head-projected, grouped wgrad GEMM. N <= 32768. Gradients accumulate into `grads` (dW1, db1, dWab, dbab, dwc,
     dbc), dWk, dbk; `zero` (the flat gradient buffer that holds them all) is cleared by the forward first.
     Outputs are left in `buf` (loss, hazards, S, Y_hat, A_raw, M)."""
     _require_cuda(x, Wk)
@@ -470,7 +469,7 @@ def amil_fused_step(x: torch.Tensor, w: AmilPrepared, flags: int, seed: int, buf
     g = AmilGrads(_p(grads["dW1"]), _p(grads["db1"]), _p(grads["dWab"]), _p(grads["dbab"]),
                   _p(grads["dwc"]), _p(grads["dbc"]))
     check(lib().mmf_amil_bwd_head(_p(x), N, x.stride(0), C.byref(wst), w.L, w.D, flags | MMF_STASHED, seed, _p(buf.A_raw),
-                                  C.byref(head), None, C.byref(g), None, buf.workspace.data_ptr(),
+                                  _p(buf.partials), C.byref(head), None, C.byref(g), None, buf.workspace.data_ptr(),
                                   buf.workspace.numel(), _stream()), "mmf_amil_bwd_head")
     return buf.loss
 

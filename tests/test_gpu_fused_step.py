@@ -91,7 +91,6 @@ def test_fused_step_matches_modular_kernels_and_oracle(dev, N, L, D, gated, drop
     ops.amil_fused_step(xb, prep, flags, seed, buf, Wkd, bkd, Y, c, alpha, grads, dWk=dWk, dbk=dbk, loss_scale=scale,
                         zero=flat)
     torch.cuda.synchronize()
-    assert buf.ticket.item() == 0, "the ticket must be left at zero for the next launch"
 
     # ---- modular: forward(train) -> head step kernel -> general stashed backward ---------------------------------
     flat2, grads2, dWk2, dbk2 = _grad_bufs(L, D, gated, K, dev)

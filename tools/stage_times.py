@@ -39,7 +39,37 @@ def S():
     return torch.cuda.current_stream().cuda_stream
 
 
+fbuf = ops.FusedStepBuffers(N, prep, flags, 4, dev)
+fbuf.pack_head(Wk)
+flat = torch.zeros(4096, device=dev)
+head = fbuf.head_struct(Wk, bk, Y, c, 0.0, 1e-7, 1.0, dWk, dbk)
+fbuf.workspace = ws   # share the stash
+ops.amil_fused_step(xs[0], prep, flags, 1, fbuf, Wk, bk, Y, c, 0.0, grads, dWk=dWk, dbk=dbk)
+
+
+def fwd_train_head(x, h=head):
+    check(lib.mmf_amil_fwd_train_head(x.data_ptr(), N, 1024, C.byref(wst), L, D, flags, 1, fbuf.A_raw.data_ptr(),
+                                      fbuf.partials.data_ptr(), ws.data_ptr(), ws.numel(), flat.data_ptr(), flat.numel(),
+                                      C.byref(h), S()))
+
+
+def hidden_headproj(x):
+    from multimodalfusion_b200._lib import MMF_STASHED
+    # (gate+hidden with the head-projected phase A, then wgrad: subtract the wgrad stage)
+    check(lib.mmf_amil_bwd_head(x.data_ptr(), N, 1024, C.byref(wst), L, D, flags | MMF_STASHED, 1, fbuf.A_raw.data_ptr(),
+                                fbuf.partials.data_ptr(), C.byref(head), None, C.byref(gs), None, ws.data_ptr(), ws.numel(), S()))
+
+
+def hidden_only(x):
+    from multimodalfusion_b200._lib import MMF_STASHED
+    check(lib.mmf_amil_bwd_gate_hidden_head(N, C.byref(wst), L, D, flags | MMF_STASHED, 1, fbuf.A_raw.data_ptr(),
+                                            fbuf.partials.data_ptr(), C.byref(head), None, C.byref(gs), ws.data_ptr(), ws.numel(), S()))
+
+
 stages = {
+    "fwd_train_head": fwd_train_head,
+    "gate_hidden_headproj": hidden_only,
+    "bwd_head(hid+wgrad)": hidden_headproj,
     "fwd": lambda x: ops.amil_partials(x, prep, flags, 1),
     "fwd_hstash": lambda x: ops.amil_partials(x, prep, flags, 1, h_stash=hbuf),
     "fwd_train": lambda x: ops.amil_partials_train(x, prep, flags, 1, workspace=ws),
