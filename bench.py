@@ -140,43 +140,158 @@ def load_peaks():
     return 1590.0, 1400.0, 6650.0, "fallback"
 
 
+def base_config(world=1):
+    """The keys both arms (ours / --impl reference) report: the driver compares them."""
+    return {"workload": WORKLOAD, "bag": [N_BAG, 1024], "preset": "big", "n_classes": K_CLASSES,
+            "optimizer_step": "none on either arm (the step is model -> nll_surv -> backward, utils/core_utils.py:200-247 "
+                              "without optimizer.step())"}
+
+
+def bind_to_gpu_numa(index):
+    """Run this process (and therefore first-touch its pinned staging buffers) on the cores of the GPU's NUMA node."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bdf = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bdf = (bdf.decode() if isinstance(bdf, bytes) else bdf).lower()
+        if len(bdf.split(":")[0]) == 8:
+            bdf = bdf[4:]
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        os.sched_setaffinity(0, cpus & os.sched_getaffinity(0) or cpus)
+        return node
+    except Exception:
+        return None
+
+
+def reference_modules():
+    """The reference's own modules, unmodified, when its tree is importable (this container: /root/reference; a tree
+    installed under baseline/_ref). Returns (MIL_Attention_fc_surv_path, NLLSurvLoss, path) or None."""
+    for root in ("/root/reference", os.path.join(ROOT, "baseline", "_ref")):
+        if os.path.exists(os.path.join(root, "models", "model_attention_mil_path.py")):
+            import importlib
+            import torch
+            sys.path.insert(0, root)
+            saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "models" or k.startswith("models.")
+                     or k == "utils" or k.startswith("utils.")}
+            try:
+                if not hasattr(torch.cuda, "FloatTensor"):
+                    torch.cuda.FloatTensor = torch.FloatTensor   # models/model_modules.py:164 names it at import
+                mod = importlib.import_module("models.model_attention_mil_path")
+                try:
+                    loss_cls = importlib.import_module("utils.loss_utils").NLLSurvLoss
+                except Exception:
+                    loss_cls = None    # utils/ imports lifelines / sksurv in places: the loss is restated then
+                return mod.MIL_Attention_fc_surv_path, loss_cls, root
+            except Exception as e:
+                print(f"# reference tree at {root} not importable ({type(e).__name__}: {e}); using the port", file=sys.stderr)
+            finally:
+                sys.path.remove(root)
+                for k in [k for k in sys.modules if k == "models" or k.startswith("models.") or k == "utils"
+                          or k.startswith("utils.")]:
+                    sys.modules.pop(k)
+                sys.modules.update(saved)
+    return None
+
+
+def time_reference_modules(ref, steps, warmup):
+    """One step = the reference's hot loop body on ITS modules: model(path_features=x) -> nll_surv -> backward
+    (utils/core_utils.py:200-247), fp32, train mode, all host threads."""
+    import torch
+    from oracle import amil_oracle as O
+    model_cls, loss_cls, _ = ref
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    model = model_cls(gate_path=True, model_size_wsi="big", dropout=False, n_classes=K_CLASSES).train()
+    loss_fn = loss_cls(alpha=0.0) if loss_cls is not None else None
+    g = torch.Generator().manual_seed(1)
+    x = (0.5 * torch.randn(N_BAG, 1024, generator=g).abs()).to(torch.bfloat16).float()
+    Y, c = torch.tensor([2]), torch.tensor([0.0])
+
+    def step():
+        model.zero_grad(set_to_none=True)
+        hazards, S, Y_hat, _ = model(path_features=x)
+        loss = loss_fn(hazards=hazards, S=S, Y=Y, c=c) if loss_fn is not None else O.nll_surv_loss(hazards, S, Y, c, alpha=0.0)
+        loss.backward()
+        return loss.item(), float(-S.detach().sum())
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return N_BAG / dt, dt, torch.get_num_threads()
+
+
 def run_reference(args):
-    """CPU arm: the port of the reference step on the host cores (rank 0 only)."""
+    """CPU arm: the reference's own modules when its tree is present, else the port of its step, on the host cores
+    (rank 0 only)."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    from oracle.cpu_reference import time_cpu_steps
-    pps, dt, threads = time_cpu_steps(N_BAG, L, D, K_CLASSES, steps=args.steps, warmup=min(args.warmup, 3))
+    warmup = max(args.warmup, 3)
+    ref = reference_modules()
+    if ref is not None:
+        pps, dt, threads = time_reference_modules(ref, args.steps, warmup)
+        kind, what = "reference", f"the reference's own modules imported from {ref[2]}"
+    else:
+        from oracle.cpu_reference import time_cpu_steps
+        pps, dt, threads = time_cpu_steps(N_BAG, L, D, K_CLASSES, steps=args.steps, warmup=warmup)
+        kind, what = "port", "port of the reference step with the same stock ATen ops (oracle/cpu_reference.py; the reference tree does not travel to the GPU box)"
     line = {
         "impl": "reference", "metric": METRIC, "value": pps, "unit": "patches/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": min(args.warmup, 3), "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "steps": args.steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "bag": [N_BAG, 1024], "preset": "big"},
-        "cpu_baseline": {"value": pps, "unit": "patches/s", "cores": threads, "kind": "port",
-                         "sample": f"{args.steps} full steps (fwd+bwd) on one {N_BAG}x1024 bag, torch fp32 autograd"},
+        "config": base_config(),
+        "cpu_baseline": {"value": pps, "unit": "patches/s", "cores": threads, "kind": kind,
+                         "sample": f"{args.steps} full steps (fwd+bwd) on one {N_BAG}x1024 bag, torch fp32 autograd, {what}"},
         "e2e": {"value": pps, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
+def median_graph_us(graph, per_launch, reps=9):
+    import torch
+    for _ in range(2):
+        graph.replay()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); graph.replay(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3 / per_launch)
+    return statistics.median(ts)
+
+
 def run_ours(args):
+    import ctypes as C
+
     import torch
     import torch.distributed as dist
 
     import multimodalfusion_b200 as mmf
     from multimodalfusion_b200 import ops
+    from multimodalfusion_b200._lib import MMF_STASHED, AmilGrads, check
     from multimodalfusion_b200.models import MIL_Attention_fc_surv_path
-    from multimodalfusion_b200.utils import NLLSurvLoss
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (sm_100a); there is no CPU fallback for the product path")
+    numa_node = bind_to_gpu_numa(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    mmf.lib()  # fail loudly if the extension is missing
+    lib = mmf.lib()  # fail loudly if the extension is missing
 
     torch.manual_seed(0)
     model = MIL_Attention_fc_surv_path(gate_path=True, model_size_wsi="big", dropout=False,
@@ -192,204 +307,106 @@ def run_ours(args):
     c = torch.tensor([0.0], device=dev)
     KD = 2 * D
     sizes = [L * 1024, L, KD * L, KD, D, 1, K_CLASSES * L, K_CLASSES]
-    # two flat fp32 gradient buffers (bag i accumulates into buffer i % 2): with N > 1 the NCCL all-reduce of
-    # step i's buffer runs on a communication stream while step i + 1 computes into the other buffer
-    flats, views_l, grads_l = [], [], []
+    n_flat = (sum(sizes) + 3) // 4 * 4
+    # Gradient buffers. One bag is in flight per GPU (the reference's loop: batch size 1, --gc 1, main.py:129); bag i
+    # accumulates into buffer i % 2 so that, with N > 1, the exchange of step i's gradients runs on a communication
+    # stream while step i + 1 computes into the other buffer.
     peer_ar = None
-    if world > 1 and os.environ.get("MMF_BENCH_ALLREDUCE", "p2p") == "p2p":
-        try:   # the library's own peer-memory all-reduce kernel, captured in the step graph
+    if world > 1:
+        try:   # the library's own NVLink / NVLS all-reduce kernel over symmetric memory
             from multimodalfusion_b200.parallel import PeerAllReduce
-            peer_ar = PeerAllReduce(sum(sizes), n_buffers=2, use_multicast=os.environ.get("MMF_P2P_NO_MULTICAST") != "1")
-        except Exception as e:   # no P2P / symmetric memory: NCCL on a communication stream
+            peer_ar = PeerAllReduce(n_flat, n_buffers=2)
+        except Exception as e:   # no P2P / symmetric memory: NCCL on the communication stream
             if rank == 0:
                 print(f"# peer all-reduce unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
-            peer_ar = None
-    # MMF_BENCH_INFLIGHT=n (single GPU): n independent bags of a gradient-accumulation window are in flight on n
-    # streams (lane = step % n, each lane with its own activation workspace and gradient buffer), so that one lane's
-    # kernel boundaries and partial waves (128 CTAs on 148 SMs) are filled by the other lane's kernels
-    # (N > 1: the same two lanes, each step graph replayed on its lane's stream, the exchange of the lane's gradient
-    # buffer on the communication stream)
-    lanes = max(1, int(os.environ.get("MMF_BENCH_INFLIGHT", "2")))
-    if world > 1:
-        lanes = min(lanes, 2)    # the peer all-reduce owns two symmetric gradient buffers
-    for bi in range(max(2, lanes)):
-        # (padded to a multiple of 4 floats: cleared / reduced 16 bytes at a time)
-        fl = (peer_ar.buffer(bi) if peer_ar is not None
-              else torch.zeros((sum(sizes) + 3) // 4 * 4, dtype=torch.float32, device=dev))
+    n_lanes_max = 2
+    flats, views_l, grads_l = [], [], []
+    for bi in range(2):
+        fl = peer_ar.buffer(bi) if peer_ar is not None else torch.zeros(n_flat, dtype=torch.float32, device=dev)
         vs, o = [], 0
         for sz in sizes:
             vs.append(fl[o:o + sz]); o += sz
         flats.append(fl); views_l.append(vs)
         grads_l.append(dict(dW1=vs[0].view(L, 1024), db1=vs[1], dWab=vs[2].view(KD, L), dbab=vs[3], dwc=vs[4], dbc=vs[5]))
-    flat, grads = flats[0], grads_l[0]
-    # our launches per step: tile fwd(+stash), cluster head step, fused gate-backward + dU GEMM, grouped wgrad GEMM
-    # (recompute mode: + ReLU-mask kernel + column-sum reduce + one ATen fill that zeroes the flat grad buffer;
-    # stash mode: the forward kernel clears it)
-    LAUNCHES_PER_STEP = ((3 if os.environ.get("MMF_BENCH_STEP", "fused3") == "fused3" else 4)
-                         if os.environ.get("MMF_BENCH_BWD", "stash") == "stash" else 7)
-
-    # backward mode: "stash" (default: the training forward leaves h / branch activations in the backward
-    # workspace, no recompute GEMMs) or "recompute" (MMF_BENCH_BWD=recompute: the tile kernel runs again)
-    bwd_mode = os.environ.get("MMF_BENCH_BWD", "stash")
-    step_wss = [ops.amil_bwd_workspace(N_BAG, prep, flags, dev) for _ in range(lanes)]
-    step_ws = step_wss[0]
-
-    step_mode = os.environ.get("MMF_BENCH_STEP", "fused3")   # fused3 (default) | modular4 (round-1 step, A/B)
-    fbufs = [ops.FusedStepBuffers(N_BAG, prep, flags, K_CLASSES, dev) for _ in range(lanes)]
+    fbufs = [ops.FusedStepBuffers(N_BAG, prep, flags, K_CLASSES, dev) for _ in range(n_lanes_max)]
     for fb in fbufs:
         fb.pack_head(Wk)
+    LAUNCHES_PER_STEP = 3   # fused forward, head + gate + hidden backward, grouped wgrad GEMM (no ATen kernel)
 
     def step(x, b=0, lane=0):
-        if bwd_mode == "stash" and step_mode == "fused3":
-            # forward (+ fused zero_grad, + folded head: combine, hazards, nll_surv, dlogits, dM, dWk, dbk) ->
-            # gate + hidden backward (head-projected) -> grouped wgrad
-            return ops.amil_fused_step(x, prep, flags, seed, fbufs[lane], Wk, bk, Y, c, 0.0, grads_l[b],
-                                       dWk=views_l[b][6].view(K_CLASSES, L), dbk=views_l[b][7], zero=flats[b],
-                                       repack_head=False)
-        if bwd_mode == "stash":   # the training forward clears the step's gradient buffer itself (fused zero_grad)
-            A_raw, parts, ws = ops.amil_partials_train(x, prep, flags, seed, workspace=step_wss[lane], zero=flats[b])
-        else:
-            flats[b].zero_()
-            (A_raw, parts), ws = ops.amil_partials(x, prep, flags, seed), None
-        t = ops.amil_head_nll_step(parts, Wk, bk, Y, c, 0.0, dWk=views_l[b][6], dbk=views_l[b][7])
-        ops.amil_backward(x, prep, flags, seed, A_raw, t["ml"], t["M"], t["dM"], grads=grads_l[b], stash=ws)
-        return t["loss"]
+        """forward (+ fused zero_grad, + z / mask words) -> [head: combine, hazards, nll_surv, dlogits, dM, dWk, dbk] +
+        gate + hidden backward (head-projected) -> grouped wgrad. Gradients accumulate into buffer b."""
+        return ops.amil_fused_step(x, prep, flags, seed, fbufs[lane], Wk, bk, Y, c, 0.0, grads_l[b],
+                                   dWk=views_l[b][6].view(K_CLASSES, L), dbk=views_l[b][7], zero=flats[b],
+                                   repack_head=False)
 
-    # warm up eagerly (configures kernels), then capture one graph per bag
-    for i in range(2):
+    for i in range(2):   # eager warm-up (configures the kernels' shared-memory attributes)
         step(bags[i % N_BAGS])
     torch.cuda.synchronize()
-    graphs, losses = [], []
-    for i in range(N_BAGS):
+    losses = []
+
+    def capture_loop(lanes):
+        """N_BAGS consecutive steps as ONE graph; lanes = 2: bag i on stream i % 2 (own workspace and gradient buffer)."""
         gr = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(gr):
-            losses.append(step(bags[i], i % 2, i % lanes if lanes == 2 else 0))   # the loss scalar lives in the graph's private pool
-        graphs.append(gr)
-    # single GPU: the batch-1 loop over the 8 bags is also captured as ONE graph (8 consecutive steps), so that
-    # a host graph launch is paid once per 8 steps; multi-GPU keeps per-step graphs (an all-reduce follows each)
-    loop_graph = None
-    comm_stream = torch.cuda.Stream() if world > 1 else None
-    if world == 1 and lanes == 1:
-        loop_graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(loop_graph):
-            for i in range(N_BAGS):
-                losses.append(step(bags[i], i % 2))
-    elif world == 1:
-        # fork-join graph: bag i runs on lane i % lanes; lanes only share the (read-only) weights
         side = [torch.cuda.Stream() for _ in range(lanes - 1)]
-        loop_graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(loop_graph):
+        with torch.cuda.graph(gr):
             cap = torch.cuda.current_stream()
-            fork = torch.cuda.Event()
-            fork.record(cap)
-            for s_ in side:
-                s_.wait_event(fork)
+            if lanes > 1:
+                fork = torch.cuda.Event()
+                fork.record(cap)
+                for s_ in side:
+                    s_.wait_event(fork)
             for i in range(N_BAGS):
                 lane = i % lanes
                 with torch.cuda.stream(cap if lane == 0 else side[lane - 1]):
-                    losses.append(step(bags[i], lane, lane))
+                    losses.append(step(bags[i], i % 2, lane))
             for s_ in side:
                 ev = torch.cuda.Event()
                 ev.record(s_)
                 cap.wait_event(ev)
-    elif peer_ar is not None and os.environ.get("MMF_BENCH_AR_MODE", "overlap") in ("graph", "inline"):
-        # Experimental placements of the gradient exchange inside ONE 8-step graph (default for N > 1 stays: per-step
-        # graphs + the exchange launched eagerly on a communication stream). "graph": forked branch on a second
-        # stream, joined before the buffer is cleared again; "inline": on the step's own stream after the wgrad GEMM.
-        # Measured (us/step, 2 / 8 GPUs): default 125 / 190, graph 128 / 211, inline 158-161 / 204; no exchange 118.
-        loop_graph = torch.cuda.CUDAGraph()
-        ar_inline = os.environ.get("MMF_BENCH_AR_MODE", "overlap") == "inline"
-        with torch.cuda.graph(loop_graph):
-            cap = torch.cuda.current_stream()
-            ar_done = [None, None]
-            for i in range(N_BAGS):
-                b = i % 2
-                if ar_done[b] is not None:
-                    cap.wait_event(ar_done[b])
-                losses.append(step(bags[i], b))
-                if ar_inline:            # exchange on the step's own stream, right after the wgrad GEMM
-                    peer_ar.all_reduce(b)
-                    continue
-                ev = torch.cuda.Event()
-                ev.record(cap)
-                comm_stream.wait_event(ev)
-                with torch.cuda.stream(comm_stream):
-                    peer_ar.all_reduce(b)
-                    ar_done[b] = torch.cuda.Event()
-                    ar_done[b].record(comm_stream)
-            for ev in ar_done:
-                if ev is not None:
-                    cap.wait_event(ev)
-    reduced = [None, None]   # per gradient buffer: event of its last all-reduce
-    lane_streams = [torch.cuda.Stream() for _ in range(2)] if (world > 1 and lanes == 2) else None
+        return gr
 
-    def run_steps_lanes(n, first=0):
-        # N > 1, two lanes: bag -> lane = bag % 2 (its own stream, workspace and gradient buffer); the lane's buffer
-        # is exchanged on the communication stream while the other lane (and this lane's next forward, up to the
-        # point where it clears the buffer) keeps computing
-        cur = torch.cuda.current_stream()
-        start = torch.cuda.Event()
-        start.record(cur)
-        for st in lane_streams:
-            st.wait_event(start)
-        for i in range(n):
-            bag = (first + i) % N_BAGS
-            b = bag % 2
-            st = lane_streams[b]
-            with torch.cuda.stream(st):
-                if reduced[b] is not None:
-                    st.wait_event(reduced[b])
-                graphs[bag].replay()
-                ready = torch.cuda.Event()
-                ready.record(st)
-            with torch.cuda.stream(comm_stream):
-                comm_stream.wait_event(ready)
-                if peer_ar is not None:
-                    peer_ar.all_reduce(b)
-                else:
-                    dist.all_reduce(flats[b])
-                reduced[b] = torch.cuda.Event()
-                reduced[b].record(comm_stream)
-        for st in lane_streams:
-            ev = torch.cuda.Event()
-            ev.record(st)
-            cur.wait_event(ev)
-        for ev in reduced:
-            if ev is not None:
-                cur.wait_event(ev)
+    step_graphs = []
+    for i in range(N_BAGS):
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            losses.append(step(bags[i], i % 2, 0))
+        step_graphs.append(gr)
+    loop_graph = capture_loop(1) if world == 1 else None
+    comm_stream = torch.cuda.Stream() if world > 1 else None
+    reduced = [None, None]   # per gradient buffer: event of its last all-reduce
 
     def run_steps(n, first=0):
-        if lane_streams is not None and loop_graph is None and os.environ.get("MMF_BENCH_SKIP_ALLREDUCE") != "1":
-            return run_steps_lanes(n, first)
         i = 0
         cur = torch.cuda.current_stream()
         while i < n:
-            if loop_graph is not None and n - i >= N_BAGS:
+            if loop_graph is not None and n - i >= N_BAGS and (first + i) % N_BAGS == 0:
                 loop_graph.replay()
                 i += N_BAGS
                 continue
             bag = (first + i) % N_BAGS
             b = bag % 2
             if reduced[b] is not None:
-                cur.wait_event(reduced[b])          # the buffer is zeroed by this step: its all-reduce must be done
-            graphs[bag].replay()
-            if world > 1 and os.environ.get("MMF_BENCH_SKIP_ALLREDUCE") != "1":   # (diagnostic switch: invalid as a result)
+                cur.wait_event(reduced[b])          # the buffer is cleared by this step: its exchange must be done
+            step_graphs[bag].replay()
+            if world > 1:
                 ready = torch.cuda.Event()
                 ready.record(cur)
                 with torch.cuda.stream(comm_stream):
                     comm_stream.wait_event(ready)
                     if peer_ar is not None:
-                        peer_ar.all_reduce(b)   # the library's own NVLink peer-memory kernel
+                        peer_ar.all_reduce(b)       # the library's own NVLink peer-memory kernel
                     else:
                         dist.all_reduce(flats[b])
                     reduced[b] = torch.cuda.Event()
                     reduced[b].record(comm_stream)
             i += 1
-        for ev in reduced:                          # every all-reduce is inside the timed region
+        for ev in reduced:                          # every exchange completes inside the timed region
             if ev is not None:
                 cur.wait_event(ev)
 
-    run_steps(max(args.warmup, 3))
+    warmup = max(args.warmup, 3)
+    run_steps(warmup)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -399,7 +416,7 @@ def run_ours(args):
     time.sleep(0.05)
     torch.cuda.synchronize()
     ev0.record()
-    run_steps(args.steps, first=args.warmup)
+    run_steps(args.steps, first=0)
     ev1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -412,69 +429,95 @@ def run_ours(args):
     ms_per_step = ms / args.steps
     value = world * N_BAG / (ms_per_step * 1e-3)
     assert all(torch.isfinite(l).item() for l in losses)
-    # reported next to the headline: the same 8-step loop with ONE bag in flight (strict batch-1 loop, gc = 1)
-    single_lane = None
-    if world == 1 and lanes > 1:
-        g1 = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g1):
-            for i in range(N_BAGS):
-                losses.append(step(bags[i], i % 2))
-        for _ in range(2):
-            g1.replay()
-        torch.cuda.synchronize()
-        reps = max(2, min(args.steps // N_BAGS, 8))
-        ev0.record()
-        for _ in range(reps):
-            g1.replay()
-        ev1.record()
-        torch.cuda.synchronize()
-        ms1 = ev0.elapsed_time(ev1) / (reps * N_BAGS)
-        single_lane = {"ms_per_step": ms1, "value": N_BAG / (ms1 * 1e-3), "steps": reps * N_BAGS}
     if os.environ.get("MMF_BENCH_QUICK") == "1":   # diagnostic: device-resident value only
+        two = None
+        if world == 1:
+            g2 = capture_loop(2)
+            two = median_graph_us(g2, N_BAGS)
         if rank == 0:
-            print(json.dumps({"quick": True, "lanes": lanes, "ms_per_step": ms_per_step, "value": value,
-                              "loss0": losses[-N_BAGS].item(), "loss1": losses[-N_BAGS + 1].item()}), flush=True)
+            print(json.dumps({"quick": True, "ms_per_step": ms_per_step, "value": value,
+                              "two_bags_in_flight_us": two, "loss": losses[-1].item()}), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
         return
 
-    # ---- e2e through the public drop-in API with pinned host bags ---------------------------------
-    loss_fn = NLLSurvLoss(alpha=0.0)
+    extra = {}
+    if world == 1:
+        # beside the headline: two bags of a gradient-accumulation window (--gc >= 2) in flight on two streams
+        g2 = capture_loop(2)
+        us2 = median_graph_us(g2, N_BAGS)
+        extra["two_bags_in_flight"] = {
+            "ms_per_step": us2 * 1e-3, "value": N_BAG / (us2 * 1e-6),
+            "note": "two independent bags of a gradient-accumulation window (--gc >= 2) on two streams, own activation "
+                    "workspace and gradient buffer each; one lane's kernel boundaries and partial waves (128 CTAs on "
+                    "148 SMs) are filled by the other lane's kernels"}
+
+    # ---- the public drop-in API, device-resident: model.fused_step captured in a CUDA graph ---------------------
+    model.enable_fused_step()
+
+    def api_step(x):
+        return model.fused_step(x, Y, c, alpha=0.0)
+
+    for i in range(2):
+        api_step(bags[i])
+    torch.cuda.synchronize()
+    api_graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(api_graph):
+        for i in range(N_BAGS):
+            api_out = api_step(bags[i])
+    api_us = median_graph_us(api_graph, N_BAGS)
+    extra["api_device_resident"] = {
+        "ms_per_step": api_us * 1e-3, "value": world * N_BAG / (api_us * 1e-6), "launches_per_step": LAUNCHES_PER_STEP,
+        "aten_launches_per_step": 0,
+        "note": "MIL_Attention_fc_surv_path.fused_step(path_features, Y, c): model -> nll_surv -> backward into the "
+                "parameters' .grad, device bags, 8 steps per CUDA graph"}
+
+    # ---- e2e through the public API with pinned host bags ------------------------------------------------------
+    NSTAGE = 3
     host_bags = [b.cpu().pin_memory() for b in bags[:4]]
-    stage = [torch.empty_like(bags[0]) for _ in range(2)]
-    copy_stream = torch.cuda.Stream()
-    ready = [torch.cuda.Event() for _ in range(2)]
-    consumed = [torch.cuda.Event() for _ in range(2)]
+    stage = [torch.empty_like(bags[0]) for _ in range(NSTAGE)]
+    copy_streams = [torch.cuda.Stream() for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(NSTAGE)]
+    consumed = [torch.cuda.Event() for _ in range(NSTAGE)]
+    host_out = torch.empty(1 + K_CLASSES, dtype=torch.float32).pin_memory()
+    dev_out = torch.empty(1 + K_CLASSES, dtype=torch.float32, device=dev)
+    out_done = torch.cuda.Event()
 
     def prefetch(i):
-        buf = i % 2
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[buf])
+        buf = i % NSTAGE
+        cs = copy_streams[i % 2]     # two copies in flight on two streams (two DMA engines)
+        with torch.cuda.stream(cs):
+            cs.wait_event(consumed[buf])
             stage[buf].copy_(host_bags[i % len(host_bags)], non_blocking=True)
-            ready[buf].record(copy_stream)
+            ready[buf].record(cs)
 
     def e2e_steps(n):
         last = None
-        for b in range(2):
-            consumed[b].record()
-        prefetch(0)
+        cur = torch.cuda.current_stream()
+        for b_ in range(NSTAGE):
+            consumed[b_].record()
+        for j in range(min(NSTAGE - 1, n)):
+            prefetch(j)
         for i in range(n):
-            buf = i % 2
-            if i + 1 < n:
-                prefetch(i + 1)
-            torch.cuda.current_stream().wait_event(ready[buf])
-            hazards, S, Y_hat, A_raw = model(path_features=stage[buf])
-            loss = loss_fn(hazards=hazards, S=S, Y=Y, c=c)
-            model.zero_grad(set_to_none=True)
-            loss.backward()
+            buf = i % NSTAGE
+            if i + NSTAGE - 1 < n:
+                prefetch(i + NSTAGE - 1)
+            cur.wait_event(ready[buf])
+            hazards, S, Y_hat, A_raw, loss = model.fused_step(stage[buf], Y, c, alpha=0.0)
             consumed[buf].record()
-            risk = -torch.sum(S, dim=1)
-            last = (loss.item(), risk.detach().cpu().numpy())   # the reference reads both every step
+            dev_out[0:1].copy_(loss.reshape(1)); dev_out[1:].copy_(S.reshape(-1))
+            host_out.copy_(dev_out, non_blocking=True)
+            out_done.record()
+            out_done.synchronize()               # the reference reads loss.item() and the risk every step
+            last = (float(host_out[0]), -float(host_out[1:].sum()))
         return last
 
-    e2e_steps(3)
+    e2e_steps(4)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    n_e2e = max(args.steps // 2, 5)
+    n_e2e = max(args.steps // 2, 6)
     ev0.record()
     e2e_steps(n_e2e)
     ev1.record()
@@ -486,64 +529,49 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = t.item()
     e2e_value = world * N_BAG * n_e2e / (e2e_ms * 1e-3)
+    h2d_gbs = N_BAG * 2048 * n_e2e / (e2e_ms * 1e-3) / 1e9
 
-    # ---- per-kernel timing for the roofline (rank 0) -----------------------------------------------
+    # ---- one 131072-instance bag sharded by instances over the ranks (BASELINE config 4) ------------------------
+    if world > 1:
+        extra["sharded_bag"] = sharded_bag_block(model, dev, rank, world)
+
+    # ---- per-kernel timing for the roofline (rank 0) -----------------------------------------------------------
     roof = cpu_base = None
     kernels = {}
     if rank == 0:
         peak_burst, peak_sust, hbm, src = load_peaks()
-        A_raw, parts = ops.amil_partials(bags[0], prep, flags, seed)
-        M, ml = ops.amil_combine(parts, L, True)
-        dM = torch.randn(L, device=dev) * 0.1
-        nbytes = mmf.lib().mmf_amil_bwd_workspace_bytes(N_BAG, L, D, flags)
-        wsbuf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
-        wsp = wsbuf.data_ptr() + ((-wsbuf.data_ptr()) % 1024)
-        import ctypes as C
-        from multimodalfusion_b200._lib import AmilGrads, check
-        gstruct = AmilGrads(*[grads[k].data_ptr() for k in ("dW1", "db1", "dWab", "dbab", "dwc", "dbc")])
+        fb = fbufs[0]
+        gstruct = AmilGrads(*[grads_l[0][k].data_ptr() for k in ("dW1", "db1", "dWab", "dbab", "dwc", "dbc")])
         wst = prep.struct()
+        head = fb.head_struct(Wk, bk, Y, c, 0.0, 1e-7, 1.0, views_l[0][6], views_l[0][7])
+        ws = fb.workspace
+
         def cur_stream():   # evaluated per call: graph capture runs on its own stream
             return torch.cuda.current_stream().cuda_stream
-        lib = mmf.lib()
 
         def t_fwd(x):
             ops.amil_partials(x, prep, flags, seed)
 
         def t_fwd_train(x):
-            ops.amil_partials_train(x, prep, flags, seed, workspace=step_ws)
-
-        def t_gate_stashed(x):
-            check(lib.mmf_amil_bwd_gate_stashed(N_BAG, C.byref(wst), L, D, flags, seed, A_raw.data_ptr(), ml.data_ptr(),
-                                                M.data_ptr(), dM.data_ptr(), None, C.byref(gstruct),
-                                                step_ws.data_ptr(), step_ws.numel(), cur_stream()))
-
-        def t_gate_hidden_fused(x):
-            check(lib.mmf_amil_bwd_gate_hidden_stashed(N_BAG, C.byref(wst), L, D, flags, seed, A_raw.data_ptr(),
-                                                       ml.data_ptr(), M.data_ptr(), dM.data_ptr(), None, C.byref(gstruct),
-                                                       step_ws.data_ptr(), step_ws.numel(), cur_stream()))
-
-        def t_gate(x):
-            check(lib.mmf_amil_bwd_gate(x.data_ptr(), N_BAG, 1024, C.byref(wst), L, D, flags, seed, A_raw.data_ptr(),
-                                        ml.data_ptr(), M.data_ptr(), dM.data_ptr(), None, C.byref(gstruct), wsp,
-                                        nbytes, cur_stream()))
+            check(lib.mmf_amil_fwd_train_head(x.data_ptr(), N_BAG, 1024, C.byref(wst), L, D, flags, seed, fb.A_raw.data_ptr(),
+                                              fb.partials.data_ptr(), ws.data_ptr(), ws.numel(), flats[0].data_ptr(),
+                                              flats[0].numel(), C.byref(head), cur_stream()))
 
         def t_hidden(x):
-            check(lib.mmf_amil_bwd_hidden(x.data_ptr(), N_BAG, 1024, C.byref(wst), L, D, flags, A_raw.data_ptr(),
-                                          ml.data_ptr(), dM.data_ptr(), C.byref(gstruct), wsp, nbytes, cur_stream()))
+            check(lib.mmf_amil_bwd_gate_hidden_head(N_BAG, C.byref(wst), L, D, flags | MMF_STASHED, seed, fb.A_raw.data_ptr(),
+                                                    fb.partials.data_ptr(), C.byref(head), None, C.byref(gstruct),
+                                                    ws.data_ptr(), ws.numel(), cur_stream()))
 
         def t_wgrad(x):
-            check(lib.mmf_amil_bwd_wgrad(x.data_ptr(), N_BAG, 1024, C.byref(wst), L, D, flags, C.byref(gstruct), None,
-                                         wsp, nbytes, cur_stream()))
+            check(lib.mmf_amil_bwd_wgrad(x.data_ptr(), N_BAG, 1024, C.byref(wst), L, D, flags | MMF_STASHED, C.byref(gstruct),
+                                         None, ws.data_ptr(), ws.numel(), cur_stream()))
 
-        # (bwd_gate_stashed re-reads whatever the previous call left in the workspace: the arithmetic is
-        # meaningless after the first call, the memory traffic is identical)
         # each stage is captured 8x (one launch per rotating bag: x always comes from HBM) in a CUDA graph and
         # replayed; stage time = median replay time / 8. Eager per-launch events would time the Python/ctypes
-        # launch path, not the kernel, once a kernel is shorter than ~40 us.
-        for name, fn in (("amil_tile_fwd", t_fwd), ("amil_tile_fwd_train", t_fwd_train),
-                         ("bwd_gate_hidden_fused", t_gate_hidden_fused), ("bwd_wgrad", t_wgrad),
-                         ("unfused_bwd_gate_stashed", t_gate_stashed), ("unfused_bwd_hidden", t_hidden),
-                         ("recompute_bwd_gate", t_gate)):
+        # launch path, not the kernel, once a kernel is shorter than ~40 us. (The backward stages re-read whatever
+        # the previous call left in the workspace: the arithmetic repeats, the memory traffic is identical.)
+        for name, fn in (("amil_tile_fwd_inference", t_fwd), ("amil_tile_fwd_train", t_fwd_train),
+                         ("bwd_head_gate_hidden", t_hidden), ("bwd_wgrad", t_wgrad)):
             for i in range(2):
                 fn(bags[i % N_BAGS])
             torch.cuda.synchronize()
@@ -551,87 +579,167 @@ def run_ours(args):
             with torch.cuda.graph(sg):
                 for i in range(N_BAGS):
                     fn(bags[i])
-            for _ in range(2):
-                sg.replay()
-            ts = []
-            for _ in range(9):
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(); sg.replay(); e1.record()
-                torch.cuda.synchronize()
-                ts.append(e0.elapsed_time(e1) * 1e3 / N_BAGS)
-            kernels[name] = statistics.median(ts)  # us
-        # the roofline kernel is the dominant kernel of the TIMED step: the fused forward tile kernel in its training
-        # form (with the activation stash); the plain (inference) forward is reported next to it
-        train_key = "amil_tile_fwd_train" if bwd_mode == "stash" else "amil_tile_fwd"
-        t_tile = kernels[train_key]
+            kernels[name] = median_graph_us(sg, N_BAGS)
+        # the roofline kernel is the dominant kernel of the TIMED step: the fused forward in its training form
+        t_tile = kernels["amil_tile_fwd_train"]
         achieved = flops_tile_kernel(N_BAG) / (t_tile * 1e-6) / 1e12
         traffic = None
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tp):
             with open(tp) as f:
-                traffic = json.load(f).get(train_key + "_dram_bytes")
-        step_tf = flops_per_patch_algorithmic() * N_BAG / (ms_per_step * 1e-3) / 1e12
+                traffic = json.load(f).get("amil_tile_fwd_train_dram_bytes")
+        step_tf = flops_per_patch_algorithmic() * N_BAG / (ms_per_step / world * 1e-3) / 1e12 / world
         roof = {"bound": "tensor",
-                "kernel": "amil_tile2_kernel<512,384,gated,FWD> (fused fc + gated attention + softmax partial"
-                          + (" + activation stash)" if bwd_mode == "stash" else ")"),
+                "kernel": "amil_tile2_kernel<512,384,gated,FWD,DROPH> training form (fused fc + gated attention + softmax "
+                          "partial + activation stash + z = Wk h side MMA + ReLU mask words)",
                 "achieved": achieved, "peak": peak_burst, "unit": "TFLOP/s", "frac": achieved / peak_burst,
                 "traffic": traffic, "peak_source": f"MEASURED_PEAKS.json bf16_tflops (burst), {src}",
                 "flops_per_launch": flops_tile_kernel(N_BAG),
                 "timed_with": "8 launches (one per rotating bag) in a CUDA graph, CUDA events, median of 9 replays / 8",
-                "inference_forward_frac": flops_tile_kernel(N_BAG) / (kernels["amil_tile_fwd"] * 1e-6) / 1e12 / peak_burst,
+                "inference_forward_frac": flops_tile_kernel(N_BAG) / (kernels["amil_tile_fwd_inference"] * 1e-6) / 1e12 / peak_burst,
                 "step_algorithmic_tflops": step_tf, "step_frac_of_burst_peak": step_tf / peak_burst,
                 "step_frac_of_sustained_peak": step_tf / peak_sust,
                 "stage_us": kernels}
+        if "two_bags_in_flight" in extra:
+            tf2 = flops_per_patch_algorithmic() * extra["two_bags_in_flight"]["value"] / 1e12
+            roof["step_frac_of_burst_peak_two_bags_in_flight"] = tf2 / peak_burst
         if world == 1:
-            from oracle.cpu_reference import time_cpu_steps
-            pps, dt, threads = time_cpu_steps(N_BAG, L, D, K_CLASSES, steps=5, warmup=1)
-            cpu_base = {"value": pps, "unit": "patches/s", "cores": threads, "kind": "port",
+            ref = None   # (the GPU box has no reference tree: the port, unless baseline/_ref was populated)
+            try:
+                ref = reference_modules()
+            except Exception:
+                ref = None
+            if ref is not None:
+                pps, dt, threads = time_reference_modules(ref, 5, 1)
+                kind = "reference"
+            else:
+                from oracle.cpu_reference import time_cpu_steps
+                pps, dt, threads = time_cpu_steps(N_BAG, L, D, K_CLASSES, steps=5, warmup=1)
+                kind = "port"
+            cpu_base = {"value": pps, "unit": "patches/s", "cores": threads, "kind": kind,
                         "sample": f"5 full steps (fwd+bwd) on one {N_BAG}x1024 bag, torch fp32 autograd, {dt * 1e3:.0f} ms/step"}
 
     if rank == 0:
+        cfg = base_config(world)
+        cfg.update({
+            "backward": "stash (training forward leaves h bf16 + [tanh|sigmoid] fp16 + mask words + z for the backward)",
+            "l2": f"inputs rotate over {N_BAGS} distinct bags ({N_BAGS * N_BAG * 2048 >> 20} MiB) > 126 MB L2",
+            "bags_in_flight": 1,
+            "parallelism": (f"dp{world} (cohort data-parallel, one bag per rank per step, one bag in flight per rank; "
+                            f"all-reduce of {n_flat * 4} B of fp32 grads EVERY step: "
+                            + ("own NVLink/NVLS peer-memory kernel (p2p_allreduce_sum_kernel)" if peer_ar is not None else "NCCL")
+                            + " on a communication stream, overlapping the next bag's step (double-buffered gradient "
+                              "buffers); every exchange completes inside the timed region)")
+            if world > 1 else "single GPU, one bag in flight (batch size 1, --gc 1 as the reference's default loop)",
+            "collective": ("own kernel: multimem.ld_reduce / multimem.st over NVLS (NCCL only sets up symmetric memory)"
+                           if peer_ar is not None and peer_ar.multicast else
+                           "own kernel: peer loads / stores over NVLink" if peer_ar is not None else
+                           "NCCL all-reduce" if world > 1 else "none"),
+            "timed_with": ("CUDA graphs (8 consecutive steps per graph launch, remainder as single-step graphs)"
+                           if loop_graph is not None else "CUDA graph replay per step + exchange launch")
+                          + ", CUDA events, max over ranks"})
         line = {
             "metric": METRIC, "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "bag": [N_BAG, 1024], "preset": "big", "n_classes": K_CLASSES, "backward": bwd_mode,
-                       "l2": f"inputs rotate over {N_BAGS} distinct bags ({N_BAGS * N_BAG * 2048 >> 20} MiB) > 126 MB L2",
-                       "parallelism": (f"dp{world} (cohort data-parallel, one bag per rank per step, "
-                                       + (f"{lanes} bags in flight per rank on {lanes} streams, " if lanes > 1 else "")
-                                       + "all-reduce of "
-                                       f"{flat.numel() * 4} B of fp32 grads per step: "
-                                       + ("own NVLink peer-memory kernel" if peer_ar is not None else "NCCL")
-                                       + " on a communication stream, overlapping the next bag's step as in a "
-                                         "gradient-accumulation window; all reductions complete inside the timed region)")
-                       if world > 1 else ("single GPU" if lanes == 1 else
-                                          f"single GPU, {lanes} independent bags of a gradient-accumulation window in "
-                                          f"flight on {lanes} streams (own activation workspace and gradient buffer each)"),
-                       "timed_with": ("CUDA graphs (8 consecutive steps per graph launch, remainder as single-step graphs)"
-                                      if loop_graph is not None else "CUDA graph replay per step") + ", CUDA events, max over ranks"},
+            "config": cfg,
             "clocks": clk.result,
             "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": N_BAG * 1024 * 2,
-                    "d2h_bytes_per_step": 4 + 4, "steps": n_e2e,
-                    "note": "drop-in nn.Module + autograd, pinned bf16 host bags, double-buffered H2D on a copy stream"},
+                    "d2h_bytes_per_step": 4 * (1 + K_CLASSES), "steps": n_e2e, "h2d_gb_per_s_per_gpu": h2d_gbs,
+                    "host_numa_node": numa_node,
+                    "note": "MIL_Attention_fc_surv_path.fused_step (drop-in module API), pinned bf16 host bags first-touched "
+                            "on the GPU's NUMA node, 3 staging buffers, two copies in flight on two copy streams, loss + "
+                            "survival function read back every step"},
             "gpu_launches": (LAUNCHES_PER_STEP + (1 if peer_ar is not None else 0)) * args.steps,
             "roofline": roof, "cpu_baseline": cpu_base,
         }
-        if single_lane is not None:
-            line["one_bag_in_flight"] = single_lane
+        line.update(extra)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+def sharded_bag_block(model, dev, rank, world):
+    """BASELINE config 4 at one size: ONE 131072 x 1024 bag sharded by instances over the ranks, fwd + bwd through the
+    drop-in module (AmilPool(group)): local tile kernel -> all-gather of the (L+2)-float partial -> combine + head +
+    loss on every rank -> local backward -> SUM all-reduce of the fc / attention gradients. Parity against the same
+    bag on a single rank is asserted inside the run."""
+    import torch
+    import torch.distributed as dist
+
+    from multimodalfusion_b200 import parallel
+    from multimodalfusion_b200.utils import NLLSurvLoss
+    NS = 131072
+    g = torch.Generator(device=dev).manual_seed(99)    # the same bag on every rank
+    bag = (0.5 * torch.randn(NS, 1024, device=dev, generator=g).abs()).to(torch.bfloat16)
+    Y, c = torch.tensor([2], device=dev), torch.tensor([0.0], device=dev)
+    loss_fn = NLLSurvLoss(alpha=0.0)
+    was_training = model.training
+    model.eval()     # deterministic (no dropout): the sharded and the whole-bag runs must agree
+    for p in model.parameters():
+        p.grad = None
+    if hasattr(model, "_fused"):
+        del model._fused
+
+    def run(x, group):
+        model.bag_group = group
+        model.zero_grad(set_to_none=True)
+        hazards, S, Y_hat, A_raw = model(path_features=x)
+        loss = loss_fn(hazards=hazards, S=S, Y=Y, c=c)
+        loss.backward()
+        if group is not None:
+            parallel.sync_sharded_bag_grads(model, group)
+        return hazards.detach().clone(), loss.detach().clone()
+
+    lo, hi = parallel.shard_rows(NS, rank, world)
+    shard = bag[lo:hi].contiguous()
+    hz_s, loss_s = run(shard, dist.group.WORLD)
+    gW1_s = model.attention_net_WSI[0].weight.grad.detach().clone()
+    hz_w, loss_w = run(bag, None)                      # whole bag on this rank alone
+    gW1_w = model.attention_net_WSI[0].weight.grad.detach().clone()
+    err_h = (hz_s - hz_w).abs().max().item() / hz_w.abs().max().item()
+    err_g = (gW1_s - gW1_w).abs().max().item() / gW1_w.abs().max().item()
+    assert err_h < 1e-4 and err_g < 2e-3, f"sharded bag != whole bag (hazards {err_h:.2e}, dW1 {err_g:.2e})"
+
+    def timed(x, group, n=6):
+        for _ in range(2):
+            run(x, group)
+        torch.cuda.synchronize()
+        if group is not None:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            run(x, group)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / n], device=dev)
+        if group is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    ms_sharded = timed(shard, dist.group.WORLD)
+    ms_whole = timed(bag, None)
+    model.bag_group = None
+    model.train(was_training)
+    return {"bag": [NS, 1024], "ranks": world, "ms_per_bag_sharded": ms_sharded, "patches_per_s_sharded": NS / (ms_sharded * 1e-3),
+            "ms_per_bag_one_rank": ms_whole, "speedup_vs_one_rank": ms_whole / ms_sharded,
+            "parity_vs_one_rank": {"hazards_rel": err_h, "dW1_rel": err_g},
+            "how": "drop-in module + autograd (eager launches), eval mode, CUDA events, max over ranks; per step: NCCL "
+                   "all-gather of the (L+2)-float partial, NCCL SUM all-reduce of the fc / attention gradients"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=48)
+    ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
     if args.impl == "reference":
-        if args.steps > 20:
-            args.steps = 20   # bounded sample: ~1 s of CPU work per step
+        if args.steps > 50:
+            args.steps = 50   # bounded sample: ~0.1-1 s of CPU work per step
         run_reference(args)
     else:
         run_ours(args)

@@ -59,6 +59,9 @@ void mmf_debug_set_timing_buffer(void* device_u64_buffer);
  * [16 + 8192 ...] (count in [1]). ids: 0 fused forward, 1 head step, 2 fused gate+hidden backward, 3 wgrad GEMM,
  * 4 recompute gate, 5 other pair GEMMs. NULL disables. */
 void mmf_debug_set_timeline_buffer(void* device_u64_buffer);
+/* DEBUG ONLY (process-global): device buffer of 8 + 4 * 4000 uint64, zero-filled; CTA 0 of every peer all-reduce appends
+ * 4 %globaltimer stamps (kernel start, ready handshake done, data phase done, done handshake done); count in [0]. */
+void mmf_debug_set_p2p_stamp_buffer(void* device_u64_buffer);
 const char* mmf_error_string(int rc);
 
 /* Weights of fc(1024->L) + attention net, prepared once per optimizer step by the caller.

@@ -101,6 +101,7 @@ SIGNATURES = {
     "mmf_version": (_i, []),
     "mmf_debug_set_timing_buffer": (None, [_vp]),
     "mmf_debug_set_timeline_buffer": (None, [_vp]),
+    "mmf_debug_set_p2p_stamp_buffer": (None, [_vp]),
     "mmf_error_string": (C.c_char_p, [_i]),
     "mmf_cast_f32_to_bf16": (_i, [_vp, _vp, _i64, _vp]),
     "mmf_pack_wab": (_i, [_vp, _vp, _i, _i, _i, _vp]),

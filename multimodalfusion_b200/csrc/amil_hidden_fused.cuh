@@ -640,6 +640,14 @@ amil_hidden_fused_kernel(const __grid_constant__ CUtensorMap tmAG,   // stash fp
     for (int j = 1; j <= C::NSA; ++j)
       if (C::NKP >= j) mbar_wait(smem_u32(&bar_aempty[(C::NKP - j) % C::NSA]), ((C::NKP - j) / C::NSA) & 1);
     named_bar_sync(1, HIDDEN_ET);
+    // Each thread owns one row x PIECES 32-column pieces. The four quadrant warps of a column part complete one
+    // 64-column block of the staged tile every two pieces: they meet on their own named barrier and one of them
+    // TMA-stores the block while the others go on (the first version staged the whole 128 KB tile, then issued all
+    // stores, then walked the staged tile again for db1: 9.3k cycles, gpurun_out/r2_phase9.log). db1 comes from the
+    // registers: 31-shuffle transpose-reduce per piece, the four quadrants meet in shared memory.
+    float* s_db1 = reinterpret_cast<float*>(pool_ptr + C::STAGING);   // [4 quadrants][L], behind the staged tile
+    static_assert(C::POOL >= C::STAGING + 4u * L * 4u, "db1 scratch must fit behind the staged tile");
+    static_assert(PIECES == 2 || PIECES == 4, "a column part is one or two 64-column blocks");
     float v[2][32];
     tmem_ld32(tmem + ((q * 32u) << 16) + part * PIECES * 32, v[0]);
 #pragma unroll
@@ -650,43 +658,38 @@ amil_hidden_fused_kernel(const __grid_constant__ CUtensorMap tmAG,   // stash fp
       float (&u)[32] = v[ii & 1];
       const uint32_t bits = mw[ii];
       const float4* dm4 = reinterpret_cast<const float4*>(vec + C::V_DM + cb * 32);
-      uint32_t packed[16];
+      // dU = s (acc + p_i dM) = fma(acc, s, (s p_i) dM): two packed f32x2 operations per element PAIR (FMUL2 + FFMA2)
+      const float2 s2 = make_float2(a.du_scale, a.du_scale), sp2 = make_float2(a.du_scale * p_row, a.du_scale * p_row);
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
         const float4 d = dm4[i >> 2];
-        const float o0 = (bits >> i) & 1u ? a.du_scale * fmaf(p_row, d.x, u[i]) : 0.f;
-        const float o1 = (bits >> (i + 1)) & 1u ? a.du_scale * fmaf(p_row, d.y, u[i + 1]) : 0.f;
-        const float o2 = (bits >> (i + 2)) & 1u ? a.du_scale * fmaf(p_row, d.z, u[i + 2]) : 0.f;
-        const float o3 = (bits >> (i + 3)) & 1u ? a.du_scale * fmaf(p_row, d.w, u[i + 3]) : 0.f;
-        packed[i >> 1] = pack_bf16x2(o0, o1);
-        packed[(i >> 1) + 1] = pack_bf16x2(o2, o3);
+        const float2 o01 = __ffma2_rn(make_float2(u[i], u[i + 1]), s2, __fmul2_rn(sp2, make_float2(d.x, d.y)));
+        const float2 o23 = __ffma2_rn(make_float2(u[i + 2], u[i + 3]), s2, __fmul2_rn(sp2, make_float2(d.z, d.w)));
+        u[i] = (bits >> i) & 1u ? o01.x : 0.f;
+        u[i + 1] = (bits >> (i + 1)) & 1u ? o01.y : 0.f;
+        u[i + 2] = (bits >> (i + 2)) & 1u ? o23.x : 0.f;
+        u[i + 3] = (bits >> (i + 3)) & 1u ? o23.y : 0.f;
       }
       const uint32_t blk = pool + (cb >> 1) * 16384;
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        st_shared_v4(blk + sw128_offset(r, (cb & 1) * 4 + j), packed[4 * j], packed[4 * j + 1], packed[4 * j + 2],
-                     packed[4 * j + 3]);
-    }
-    fence_proxy_async_smem();
-    tc_fence_before();
-    named_bar_sync(1, HIDDEN_ET);     // the staged tile is complete
-    if (e == 0) {
-      for (int kb = 0; kb < L / 64; ++kb) tma_store_2d(&tmDU, pool + kb * 16384, kb * 64, (int)row0);
-      tma_store_commit();
-    }
-    // db1: column sums of the staged bf16 tile (rows past N were staged as zeros: their mask words are 0)
-    for (uint32_t cp = e; cp < (uint32_t)L / 2; cp += HIDDEN_ET) {
-      const uint32_t col = 2u * cp;
-      const uint32_t blk = pool + (col >> 6) * 16384u, chunk = (col & 63u) >> 3, inb = (col & 7u) * 2u;
-      float a0 = 0.f, a1 = 0.f;
-#pragma unroll 8
-      for (uint32_t rr = 0; rr < 128; ++rr) {
-        const float2 f = unpack_bf16x2(ld_shared_b32(blk + sw128_offset(rr, chunk) + inb));
-        a0 += f.x; a1 += f.y;
+        st_shared_v4(blk + sw128_offset(r, (cb & 1) * 4 + j), pack_bf16x2(u[8 * j], u[8 * j + 1]),
+                     pack_bf16x2(u[8 * j + 2], u[8 * j + 3]), pack_bf16x2(u[8 * j + 4], u[8 * j + 5]),
+                     pack_bf16x2(u[8 * j + 6], u[8 * j + 7]));
+      if (ii & 1) {   // this warp's half of block cb >> 1 is staged
+        fence_proxy_async_smem();
+        named_bar_sync(2 + part, 128);
+        if (q == 0 && lane == 0) {
+          tma_store_2d(&tmDU, blk, (cb >> 1) * 64, (int)row0);
+          tma_store_commit();
+        }
       }
-      atomicAdd(a.db1 + col, a0);
-      atomicAdd(a.db1 + col + 1, a1);
+      s_db1[q * L + cb * 32 + lane] = warp_colsum32(u);   // (rows past N are zeros: their mask words are 0)
     }
+    tc_fence_before();
+    named_bar_sync(1, HIDDEN_ET);     // every quadrant's column sums are in shared memory
+    for (uint32_t c0 = e; c0 < (uint32_t)L; c0 += HIDDEN_ET)
+      atomicAdd(a.db1 + c0, s_db1[c0] + s_db1[L + c0] + s_db1[2 * L + c0] + s_db1[3 * L + c0]);
     // dwc / dbab / dbc of this CTA's rows
     // column d of branch `which` lives in slice d / 64, column group (d % 64) / 16, slot which * 16 + d % 16 of the
     // four row-quarter warps of that column group
@@ -696,11 +699,9 @@ amil_hidden_fused_kernel(const __grid_constant__ CUtensorMap tmAG,   // stash fp
       const float v = s_part[ctg][off] + s_part[ctg + 4][off] + s_part[ctg + 8][off] + s_part[ctg + 12][off];
       atomicAdd(which == 0 ? a.dwc + d : a.dbab + (which - 1) * D + d, v);
     }
-    if (e == 0) {
-      atomicAdd(a.dbc, s_dbc);
-      tma_store_wait_all();
-      MMF_STAMP(a, 7);
-    }
+    if (e == 0) atomicAdd(a.dbc, s_dbc);
+    if (q == 0 && lane == 0) tma_store_wait_all();   // the threads that committed the dU block stores
+    if (e == 0) MMF_STAMP(a, 7);
   }
   tc_fence_before();
   __syncthreads();

@@ -40,6 +40,7 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // debug-only global (the one exception to "no global state"): when set, the tensor-core kernels write
 // clock64 phase stamps [gridDim.x][16]; see tools/phase_timing.py
 unsigned long long* g_timing_buffer = nullptr;
+unsigned long long* g_p2p_stamps = nullptr;
 
 struct BwdWs {
   size_t off_H, off_dG, off_dU, off_cs, off_dbc, off_db1, off_mask, off_z, off_gparts, off_gflags, total;
@@ -264,6 +265,10 @@ int mmf_version(void) { return MMF_ABI_VERSION; }
 
 void mmf_debug_set_timing_buffer(void* device_u64_buffer) {
   g_timing_buffer = reinterpret_cast<unsigned long long*>(device_u64_buffer);
+}
+
+void mmf_debug_set_p2p_stamp_buffer(void* device_u64_buffer) {
+  g_p2p_stamps = reinterpret_cast<unsigned long long*>(device_u64_buffer);
 }
 
 void mmf_debug_set_timeline_buffer(void* device_u64_buffer) {
@@ -1039,6 +1044,7 @@ int mmf_p2p_allreduce_sum_f32(void* const* bufs_host, void* const* flags_host, v
     a.flags[p] = reinterpret_cast<uint32_t*>(flags_host[p]);
   }
   a.n = n; a.world = world; a.rank = rank;
+  a.stamps = g_p2p_stamps;
   a.mc = reinterpret_cast<float*>(multicast_ptr);
   if (multicast_ptr && (reinterpret_cast<uintptr_t>(multicast_ptr) & 15u)) return MMF_E_ALIGN;
   // Plain stream-ordered launch (as a programmatic dependent of the wgrad kernel the exchange took 100 us instead of

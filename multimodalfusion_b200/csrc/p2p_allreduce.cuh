@@ -35,6 +35,8 @@ struct P2pArgs {
   uint32_t* flags[P2P_MAX_WORLD];  // flags[p] = rank p's flag block as mapped in this process
   long long n;                     // elements (multiple of 4)
   int world, rank;
+  unsigned long long* stamps;      // debug (optional): [0] = record count, records of 4 x %globaltimer ns from [8]:
+                                   // kernel start, ready handshake done, data phase done, done handshake done (CTA 0)
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
@@ -50,6 +52,11 @@ __global__ void __launch_bounds__(P2P_THREADS) p2p_allreduce_sum_kernel(const P2
   griddep_launch_dependents();
   griddep_wait();   // the local gradients come from the kernel launched just before
   const int b = blockIdx.x, tid = threadIdx.x;
+  unsigned long long* rec = nullptr;
+  if (a.stamps && b == 0 && tid == 0) {
+    const unsigned long long k = atomicAdd(a.stamps, 1ull);
+    if (k < 4000) { rec = a.stamps + 8 + 4 * k; rec[0] = globaltimer_ns(); }
+  }
   uint32_t* my = a.flags[a.rank];
   __shared__ uint32_t s_epoch;
   if (tid == 0) s_epoch = my[2 * P2P_MAX_WORLD * P2P_MAX_CTAS + b] + 1u;
@@ -65,6 +72,7 @@ __global__ void __launch_bounds__(P2P_THREADS) p2p_allreduce_sum_kernel(const P2
     }
   }
   __syncthreads();
+  if (rec) rec[1] = globaltimer_ns();
   // 2. reduce my slice from every rank, push the sum to every rank
   const long long n4 = a.n >> 2;
   const long long per_rank = (n4 + a.world - 1) / a.world;
@@ -141,6 +149,7 @@ __global__ void __launch_bounds__(P2P_THREADS) p2p_allreduce_sum_kernel(const P2
   // 3. done handshake: my pushes are visible system-wide before any peer sees the flag
   __threadfence_system();
   __syncthreads();
+  if (rec) rec[2] = globaltimer_ns();
   if (tid < a.world) {
     st_release_sys(a.flags[tid] + (P2P_MAX_WORLD + a.rank) * P2P_MAX_CTAS + b, epoch);
     const uint32_t* w = my + (P2P_MAX_WORLD + tid) * P2P_MAX_CTAS + b;
@@ -150,6 +159,7 @@ __global__ void __launch_bounds__(P2P_THREADS) p2p_allreduce_sum_kernel(const P2
     }
   }
   __syncthreads();
+  if (rec) rec[3] = globaltimer_ns();
   if (tid == 0) my[2 * P2P_MAX_WORLD * P2P_MAX_CTAS + b] = epoch;
 }
 

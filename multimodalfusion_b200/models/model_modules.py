@@ -181,19 +181,30 @@ class AmilBranch:
     fused kernel and caches the bf16 / packed weight copies until a parameter changes."""
 
     @staticmethod
-    def pooled(seq: nn.Sequential, x: torch.Tensor, training: bool, group=None):
-        from ..autograd import AmilPool
+    def _params(seq: nn.Sequential):
         fc, attn = seq[0], seq[3]
         Wa, ba, Wb, bb, wc, bc = attn.amil_weights()
         if wc.shape[0] != 1:
             raise NotImplementedError("fused attention-MIL pooling supports n_classes=1 attention heads")
-        params = (fc.weight, fc.bias, Wa, ba, Wb, bb, wc, bc)
+        return (fc.weight, fc.bias, Wa, ba, Wb, bb, wc, bc)
+
+    @staticmethod
+    def prepared(seq: nn.Sequential):
+        """bf16 / packed copies of the fc + attention weights, rebuilt when a parameter changed (version counters)."""
+        params = AmilBranch._params(seq)
         key = tuple((p.data_ptr(), p._version) for p in params if p is not None)
         cache = getattr(seq, "_mmf_prep", None)
         if cache is None or cache[0] != key:
             cache = (key, ops.prepare_amil_weights(*params))
             seq._mmf_prep = cache
-        prep = cache[1]
+        return cache[1]
+
+    @staticmethod
+    def pooled(seq: nn.Sequential, x: torch.Tensor, training: bool, group=None):
+        from ..autograd import AmilPool
+        attn = seq[3]
+        params = AmilBranch._params(seq)
+        prep = AmilBranch.prepared(seq)
         flags = ops.amil_flags(prep.gated, dropout_h=training, dropout_attn=training and attn.use_dropout)
         seed = _seed_from_torch() if training else 0
         return AmilPool.apply(x, *params, prep, flags, seed, group)
