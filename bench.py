@@ -372,8 +372,33 @@ def run_ours(args):
         with torch.cuda.graph(gr):
             losses.append(step(bags[i], i % 2, 0))
         step_graphs.append(gr)
-    loop_graph = capture_loop(1) if world == 1 else None
     comm_stream = torch.cuda.Stream() if world > 1 else None
+
+    def capture_dp_loop():
+        """N > 1: N_BAGS steps AND their gradient exchanges as ONE graph — the exchange of step i forks onto the
+        communication stream and is joined before step i + 2 clears the same gradient buffer (no host work per step;
+        tools/dp_diag.py: 107.9 vs 110.2 us/step at 2 GPUs against per-step graph launches)."""
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            cap = torch.cuda.current_stream()
+            done = [None, None]
+            for i in range(N_BAGS):
+                b = i % 2
+                if done[b] is not None:
+                    cap.wait_event(done[b])
+                losses.append(step(bags[i], b, 0))
+                ev = torch.cuda.Event()
+                ev.record(cap)
+                with torch.cuda.stream(comm_stream):
+                    comm_stream.wait_event(ev)
+                    peer_ar.all_reduce(b)
+                    done[b] = torch.cuda.Event()
+                    done[b].record(comm_stream)
+            for ev in done:
+                cap.wait_event(ev)
+        return gr
+
+    loop_graph = capture_loop(1) if world == 1 else (capture_dp_loop() if peer_ar is not None else None)
     reduced = [None, None]   # per gradient buffer: event of its last all-reduce
 
     def run_steps(n, first=0):
@@ -381,7 +406,11 @@ def run_ours(args):
         cur = torch.cuda.current_stream()
         while i < n:
             if loop_graph is not None and n - i >= N_BAGS and (first + i) % N_BAGS == 0:
-                loop_graph.replay()
+                for ev in reduced:                  # (exchanges of single-step launches before this graph)
+                    if ev is not None:
+                        cur.wait_event(ev)
+                reduced[0] = reduced[1] = None
+                loop_graph.replay()                 # (N > 1: its exchanges are joined inside the graph)
                 i += N_BAGS
                 continue
             bag = (first + i) % N_BAGS
@@ -628,14 +657,15 @@ def run_ours(args):
             "parallelism": (f"dp{world} (cohort data-parallel, one bag per rank per step, one bag in flight per rank; "
                             f"all-reduce of {n_flat * 4} B of fp32 grads EVERY step: "
                             + ("own NVLink/NVLS peer-memory kernel (p2p_allreduce_sum_kernel)" if peer_ar is not None else "NCCL")
-                            + " on a communication stream, overlapping the next bag's step (double-buffered gradient "
-                              "buffers); every exchange completes inside the timed region)")
+                            + " forked onto a communication stream inside the step graph, overlapping the next bag's "
+                              "step (double-buffered gradient buffers); every exchange completes inside the timed region)")
             if world > 1 else "single GPU, one bag in flight (batch size 1, --gc 1 as the reference's default loop)",
             "collective": ("own kernel: multimem.ld_reduce / multimem.st over NVLS (NCCL only sets up symmetric memory)"
                            if peer_ar is not None and peer_ar.multicast else
                            "own kernel: peer loads / stores over NVLink" if peer_ar is not None else
                            "NCCL all-reduce" if world > 1 else "none"),
-            "timed_with": ("CUDA graphs (8 consecutive steps per graph launch, remainder as single-step graphs)"
+            "timed_with": ("CUDA graphs (8 consecutive steps" + (" and their exchanges" if world > 1 else "")
+                           + " per graph launch, remainder as single-step graphs)"
                            if loop_graph is not None else "CUDA graph replay per step + exchange launch")
                           + ", CUDA events, max over ranks"})
         line = {
@@ -703,31 +733,53 @@ def sharded_bag_block(model, dev, rank, world):
     assert err_h < 1e-4 and err_g < 2e-3, f"sharded bag != whole bag (hazards {err_h:.2e}, dW1 {err_g:.2e})"
 
     def timed(x, group, n=6):
-        for _ in range(2):
+        """The whole step (module forward, loss, autograd backward, collectives) captured in ONE CUDA graph — the
+        eager step is ~1 ms of Python launch work per bag whatever the shard size; falls back to eager timing when
+        the capture of the NCCL collectives fails."""
+        for _ in range(3):
             run(x, group)
+        torch.cuda.synchronize()
+        if group is not None:
+            dist.barrier()
+        how = "CUDA graph of the whole step"
+        try:
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                run(x, group)
+            call = gr.replay
+        except Exception as e:     # capture unsupported for some op: time the eager loop
+            torch.cuda.synchronize()
+            how = f"eager launches (graph capture failed: {type(e).__name__})"
+            call = lambda: run(x, group)
+        for _ in range(2):
+            call()
         torch.cuda.synchronize()
         if group is not None:
             dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(n):
-            run(x, group)
+            call()
         e1.record()
         torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1) / n], device=dev)
         if group is not None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return t.item()
+        return t.item(), how
 
-    ms_sharded = timed(shard, dist.group.WORLD)
-    ms_whole = timed(bag, None)
+    ms_sharded, how_s = timed(shard, dist.group.WORLD)
+    ms_whole, how_w = timed(bag, None)
     model.bag_group = None
     model.train(was_training)
+    for p in model.parameters():
+        p.grad = None
     return {"bag": [NS, 1024], "ranks": world, "ms_per_bag_sharded": ms_sharded, "patches_per_s_sharded": NS / (ms_sharded * 1e-3),
-            "ms_per_bag_one_rank": ms_whole, "speedup_vs_one_rank": ms_whole / ms_sharded,
+            "ms_per_bag_one_rank": ms_whole, "patches_per_s_one_rank": NS / (ms_whole * 1e-3),
+            "speedup_vs_one_rank": ms_whole / ms_sharded,
             "parity_vs_one_rank": {"hazards_rel": err_h, "dW1_rel": err_g},
-            "how": "drop-in module + autograd (eager launches), eval mode, CUDA events, max over ranks; per step: NCCL "
-                   "all-gather of the (L+2)-float partial, NCCL SUM all-reduce of the fc / attention gradients"}
+            "how": f"drop-in module + autograd, eval mode, sharded: {how_s}; one rank: {how_w}; CUDA events, max over ranks; "
+                   "per step: NCCL all-gather of the (L+2)-float partial, combine + head + loss on every rank, local "
+                   "backward, NCCL SUM all-reduce of the fc / attention gradients"}
 
 
 def main():

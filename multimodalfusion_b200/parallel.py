@@ -72,10 +72,19 @@ def allreduce_sum_(tensors: Sequence[torch.Tensor], group=None) -> None:
 
 def sync_sharded_bag_grads(model: torch.nn.Module, group=None) -> None:
     """After backward of an instance-sharded bag: fc / attention-net gradients are per-shard
-    contributions (SUM over ranks); everything downstream of the replicated M is already identical."""
-    amil = [p.grad for n, p in model.named_parameters()
-            if p.grad is not None and (n.startswith("attention_net_") or n.startswith("reduce_dim"))]
-    allreduce_sum_(amil, group)
+    contributions (SUM over ranks); everything downstream of the replicated M is already identical.
+    The collective is unconditional and has the same size on every rank: a rank whose shard is empty (fewer
+    256-row units than ranks) has no gradient for these parameters and contributes zeros — selecting on
+    ``p.grad is not None`` would leave it out of the all-reduce and hang the others."""
+    params = [p for n, p in model.named_parameters()
+              if p.requires_grad and (n.startswith("attention_net_") or n.startswith("reduce_dim"))]
+    if not params:
+        return
+    grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in params]
+    allreduce_sum_(grads, group)
+    for p, g in zip(params, grads):
+        if p.grad is None:
+            p.grad = g
 
 
 def sync_cohort_grads(model: torch.nn.Module, group=None, average: bool = True) -> None:

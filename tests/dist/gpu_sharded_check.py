@@ -28,7 +28,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
-    for size, N in (("small", 5000), ("big", 16384 + 77)):
+    # (N = 200: one 256-row unit for `world` ranks — every rank but 0 owns an EMPTY shard: neutral partial in the
+    #  all-gather, zeros in the gradient all-reduce; hung before round 2's sync_sharded_bag_grads fix)
+    for size, N in (("small", 5000), ("big", 16384 + 77), ("small", 200)):
         torch.manual_seed(0)
         model = MIL_Attention_fc_surv_path(gate_path=True, model_size_wsi=size, n_classes=4).to(dev).eval()
         g = torch.Generator().manual_seed(3)

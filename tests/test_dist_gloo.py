@@ -84,6 +84,24 @@ def _worker(rank, world, port, tmp):
         lin.bias.grad = torch.full_like(lin.bias, float(rank + 1))
         P.sync_cohort_grads(lin)
         assert torch.allclose(lin.weight.grad, torch.full_like(lin.weight, (1 + world) / 2))
+        # an instance-sharded bag with an EMPTY shard (fewer 256-row units than ranks): the rank without rows has no
+        # gradient for the fc / attention parameters and must still take part in the SUM all-reduce, with zeros
+        class Tiny(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.attention_net_WSI = torch.nn.Linear(3, 2)
+                self.classifier = torch.nn.Linear(2, 1)
+        tiny = Tiny()
+        lo2, hi2 = P.shard_rows(200, rank, world)
+        assert (hi2 > lo2) == (rank == 0)
+        if hi2 > lo2:
+            for p_ in tiny.attention_net_WSI.parameters():
+                p_.grad = torch.full_like(p_, 3.0)
+        tiny.classifier.weight.grad = torch.ones_like(tiny.classifier.weight)   # replicated: not part of the exchange
+        P.sync_sharded_bag_grads(tiny)      # would hang (rank 1 skipping the collective) before the fix
+        for p_ in tiny.attention_net_WSI.parameters():
+            assert p_.grad is not None and torch.allclose(p_.grad, torch.full_like(p_, 3.0))
+        assert torch.allclose(tiny.classifier.weight.grad, torch.ones_like(tiny.classifier.weight))
         open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()

@@ -99,7 +99,39 @@ def run(mode, n):
             cur.wait_event(ev)
 
 
+# mode "graph": 8 steps AND their exchanges in ONE graph — the exchange of step i forks onto a second stream and is
+# joined before step i + 2 clears the same gradient buffer (no host work per step)
+def capture_graph_mode():
+    gr = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    with torch.cuda.graph(gr):
+        cap = torch.cuda.current_stream()
+        done = [None, None]
+        for i in range(NB):
+            b = i % 2
+            if done[b] is not None:
+                cap.wait_event(done[b])
+            step(bags[i], b)
+            ev = torch.cuda.Event(); ev.record(cap)
+            with torch.cuda.stream(side):
+                side.wait_event(ev)
+                ar.all_reduce(b)
+                done[b] = torch.cuda.Event(); done[b].record(side)
+        for ev in done:
+            cap.wait_event(ev)
+    return gr
+
+
 modes = os.environ.get("MODES", "none,overlap,inline,nccl").split(",")
+loop_graph = capture_graph_mode() if "graph" in modes else None
+_run = run
+
+
+def run(mode, n):
+    if mode != "graph":
+        return _run(mode, n)
+    for _ in range(n // NB):
+        loop_graph.replay()
 for mode in modes:
     run(mode, 16)
     torch.cuda.synchronize(); dist.barrier()
