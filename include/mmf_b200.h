@@ -43,8 +43,15 @@ enum {
   MMF_DROPOUT_H = 2,    /* train mode: Dropout(0.25) on h = relu(fc(x)) (always on in the reference) */
   MMF_DROPOUT_ATTN = 4, /* train mode with dropout=True: Dropout(0.25) on the tanh / sigmoid outputs */
   MMF_NEED_DX = 8,      /* backward also produces dx (radio path: reduce_dim sits upstream) */
-  MMF_STASHED = 16      /* mmf_amil_bwd*: the forward was mmf_amil_fwd_train on the same workspace — h and the
+  MMF_STASHED = 16,     /* mmf_amil_bwd*: the forward was mmf_amil_fwd_train on the same workspace — h and the
                            branch activations are read from it instead of being recomputed */
+  MMF_PRECISE_FC = 32   /* split-precision fc for small bags: x is bf16 [N, 3072] = [hi | lo | hi] of an fp32 bag
+                           (mmf_split_f32_bf16x3, ldx >= 3072) and w->W1_split = [W1_hi | W1_hi | W1_lo]; GEMM1 then
+                           computes x_hi W_hi + x_lo W_hi + x_hi W_lo in fp32 accumulators (~16 mantissa bits): the
+                           ReLU pattern of a tiny bag matches the fp32 reference instead of flipping units whose
+                           pre-activation sits within bf16 rounding of zero. 3x the GEMM1 work: for bags of a few
+                           thousand instances (radiology slices), where the step is latency-bound anyway. The
+                           backward's dW1 uses x_hi (the first 1024 columns). */
 };
 
 #define MMF_IN_FEATURES 1024 /* ResNet50-layer3 feature width, fixed by the reference models */
@@ -78,6 +85,8 @@ typedef struct MmfAmilWeights {
   const float* bab;      /* f32  [2D] = ba ++ bb   (un-gated: [D])                                */
   const float* wc;       /* f32  [D]               attention_c.weight / module.{2|3}.weight       */
   const float* bc;       /* f32  [1]               attention_c.bias (device scalar)                */
+  const void* W1_split;  /* bf16 [L,3072] = [W1_hi | W1_hi | W1_lo], W1_lo = bf16(W1 - W1_hi); NULL unless
+                            MMF_PRECISE_FC is used                                                 */
 } MmfAmilWeights;
 
 typedef struct MmfAmilGrads {
@@ -91,6 +100,10 @@ typedef struct MmfAmilGrads {
 
 /* fp32 -> bf16 feature / weight conversion (round-to-nearest-even), n elements. */
 int mmf_cast_f32_to_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
+
+/* fp32 [n_rows, 1024] (leading dimension ldx) -> bf16 [n_rows, 3072] = [hi | lo | hi], hi = bf16(x), lo = bf16(x - hi):
+ * the bag format of MMF_PRECISE_FC. */
+int mmf_split_f32_bf16x3(const float* x, int64_t n_rows, int64_t ldx, void* out_bf16, void* stream);
 
 /* Regroups Wab[2D,L] into the per-chunk layout the fused kernel streams with one TMA box. */
 int mmf_pack_wab(const void* Wab_bf16, void* Wab_packed_bf16, int L, int D, int gated, void* stream);
@@ -222,20 +235,15 @@ int mmf_amil_bwd(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w,
 
 /* The three stages of mmf_amil_bwd, individually callable (same workspace; stage k consumes what
  * stages < k left in it). Exposed so that each tensor-core kernel can be timed and tested alone.
- *   gate   : recompute tile kernel -> dG, H in workspace; dwc, dbab, dbc accumulated
+ *   gate   : recompute tile kernel -> dG, H in workspace; dwc, dbab, dbc accumulated (recompute mode only)
  *   hidden : dU = (dG Wab + p dM^T) ⊙ relu'(H) in workspace; db1 accumulated
  *   wgrad  : dW1 += dU^T x, dWab += dG^T H, optional dx = dU W1 */
 int mmf_amil_bwd_gate(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, int L, int D,
                       int flags, uint64_t seed, const float* A_raw, const float* ml, const float* M,
                       const float* dM, const float* dA_raw, const MmfAmilGrads* g, void* workspace,
                       size_t workspace_bytes, void* stream);
-/* gate stage of the MMF_STASHED backward (no x, no GEMM): dG formed in place from the stash. */
-int mmf_amil_bwd_gate_stashed(int64_t N, const MmfAmilWeights* w, int L, int D, int flags, uint64_t seed,
-                              const float* A_raw, const float* ml, const float* M, const float* dM,
-                              const float* dA_raw, const MmfAmilGrads* g, void* workspace,
-                              size_t workspace_bytes, void* stream);
 /* gate + hidden stages of the MMF_STASHED backward in one kernel (the gate backward is the A-operand producer of
- * the dU GEMM); what mmf_amil_bwd(MMF_STASHED) runs. Same workspace contract as the two calls it replaces. */
+ * the dU GEMM); what mmf_amil_bwd(MMF_STASHED) runs: dG and dU left in the workspace for the wgrad stage. */
 int mmf_amil_bwd_gate_hidden_stashed(int64_t N, const MmfAmilWeights* w, int L, int D, int flags, uint64_t seed,
                                      const float* A_raw, const float* ml, const float* M, const float* dM,
                                      const float* dA_raw, const MmfAmilGrads* g, void* workspace,

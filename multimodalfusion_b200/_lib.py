@@ -28,7 +28,7 @@ NVCC_FLAGS = [
 
 # error codes / flags mirrored from the header
 MMF_OK = 0
-MMF_GATED, MMF_DROPOUT_H, MMF_DROPOUT_ATTN, MMF_NEED_DX, MMF_STASHED = 1, 2, 4, 8, 16
+MMF_GATED, MMF_DROPOUT_H, MMF_DROPOUT_ATTN, MMF_NEED_DX, MMF_STASHED, MMF_PRECISE_FC = 1, 2, 4, 8, 16, 32
 ACT_NONE, ACT_RELU, ACT_SELU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3, 4
 
 
@@ -72,7 +72,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 class AmilWeights(C.Structure):
     _fields_ = [
         ("W1", C.c_void_p), ("b1", C.c_void_p), ("Wab", C.c_void_p), ("Wab_packed", C.c_void_p),
-        ("bab", C.c_void_p), ("wc", C.c_void_p), ("bc", C.c_void_p),
+        ("bab", C.c_void_p), ("wc", C.c_void_p), ("bc", C.c_void_p), ("W1_split", C.c_void_p),
     ]
 
 
@@ -105,6 +105,7 @@ SIGNATURES = {
     "mmf_error_string": (C.c_char_p, [_i]),
     "mmf_cast_f32_to_bf16": (_i, [_vp, _vp, _i64, _vp]),
     "mmf_pack_wab": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "mmf_split_f32_bf16x3": (_i, [_vp, _i64, _i64, _vp, _vp]),
     "mmf_amil_num_tiles": (_i64, [_i64]),
     "mmf_amil_fwd": (_i, [_vp, _i64, _i64, C.POINTER(AmilWeights), _i, _i, _i, _u64, _vp, _vp, _vp, _vp]),
     "mmf_amil_infer_varlen": (_i, [_vp, _i64, _i64, C.POINTER(AmilWeights), _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp,
@@ -120,8 +121,6 @@ SIGNATURES = {
                                C.POINTER(AmilGrads), _vp, _vp, _sz, _vp]),
     "mmf_amil_bwd_gate_hidden_head": (_i, [_i64, C.POINTER(AmilWeights), _i, _i, _i, _u64, _vp, _vp, C.POINTER(HeadStep),
                                            _vp, C.POINTER(AmilGrads), _vp, _sz, _vp]),
-    "mmf_amil_bwd_gate_stashed": (_i, [_i64, C.POINTER(AmilWeights), _i, _i, _i, _u64, _vp, _vp, _vp, _vp, _vp,
-                                       C.POINTER(AmilGrads), _vp, _sz, _vp]),
     "mmf_amil_bwd_gate_hidden_stashed": (_i, [_i64, C.POINTER(AmilWeights), _i, _i, _i, _u64, _vp, _vp, _vp, _vp, _vp,
                                               C.POINTER(AmilGrads), _vp, _sz, _vp]),
     "mmf_amil_bwd": (_i, [_vp, _i64, _i64, C.POINTER(AmilWeights), _i, _i, _i, _u64, _vp, _vp, _vp, _vp,

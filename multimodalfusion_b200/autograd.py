@@ -7,7 +7,7 @@ from __future__ import annotations
 import torch
 
 from . import ops
-from ._lib import MMF_NEED_DX
+from ._lib import MMF_NEED_DX, MMF_PRECISE_FC
 
 
 class AmilPool(torch.autograd.Function):
@@ -20,18 +20,29 @@ class AmilPool(torch.autograd.Function):
 
     ``use_stash`` (class switch): True = the training forward stashes h / branch activations (2.5 KB per
     instance) and the backward runs no recompute GEMM; False = the north star's recompute backward.
+
+    ``precise_small_bags`` (class switch): bags of up to ``ops.PRECISE_FC_MAX_ROWS`` instances run the fc layer in split
+    precision (x and W1 as bf16 hi + lo pairs, three tensor-core products, ~16 mantissa bits): with plain bf16 operands
+    a ReLU unit whose pre-activation sits within bf16 rounding of zero flips against the fp32 reference, and one flip
+    moves a whole row of dW1 by ~1/N of its magnitude — visible only on tiny bags (radiology slices, small WSIs),
+    exactly where 3x the GEMM1 work costs nothing (the step is latency-bound there).
     """
     use_stash = True
+    precise_small_bags = True
 
     @staticmethod
     def forward(ctx, x, W1, b1, Wa, ba, Wb, bb, wc, bc, prep, flags: int, seed: int, group=None):
         ctx.set_materialize_grads(False)
-        xb = ops.to_bf16(x)
+        if AmilPool.precise_small_bags and 0 < x.shape[0] <= ops.PRECISE_FC_MAX_ROWS:
+            xb = ops.split_bag(x)
+            flags |= MMF_PRECISE_FC
+        else:
+            xb = ops.to_bf16(x)
         if x.requires_grad:
             flags |= MMF_NEED_DX
         # training (some parameter or x needs a gradient): stash h and the branch activations for the
         # backward instead of recomputing both GEMMs; inference keeps the N x L intermediates on chip
-        train = any(ctx.needs_input_grad[:9]) and ops.stash_supported() and AmilPool.use_stash
+        train = any(ctx.needs_input_grad[:9]) and AmilPool.use_stash
         stash = None
         ctx.empty_shard = group is not None and xb.shape[0] == 0
         if ctx.empty_shard:
@@ -154,6 +165,17 @@ class SegmentedLinearBf16(torch.autograd.Function):
         db = torch.zeros(ctx.w_shape[0], dtype=torch.float32, device=dy.device)
         ops.linear_bf16_wgrad(ops.to_bf16(dy), segs_b, dW, db)
         return (dW, db, *([None] * len(segs_b)))
+
+
+def reduce_dim_forward(weight, bias, bags):
+    """``reduce_dim(cat(bags, 1))`` of the radiology models (models/model_attention_mil_radio.py:81-82). Bags of up to
+    ``ops.PRECISE_FC_MAX_ROWS`` slices (every real patient: <= 155) run in fp32 on the functor SGEMM kernel — the same
+    arithmetic as the reference, so the bag that enters the split-precision fc is not rounded to bf16 in between;
+    larger bags use the segmented bf16 tensor-core GEMM (no concat, bf16 output)."""
+    from ._lib import ACT_NONE
+    if AmilPool.precise_small_bags and bags[0].shape[0] <= ops.PRECISE_FC_MAX_ROWS:
+        return Dense.apply(torch.cat([b.float() for b in bags], dim=1), weight, bias, ACT_NONE)
+    return SegmentedLinearBf16.apply(weight, bias, *bags)
 
 
 class NllSurv(torch.autograd.Function):

@@ -1,6 +1,6 @@
 // amil_hidden_fused.cuh — stash-mode backward, stages 1 + 2 in ONE kernel (sm_100a, CTA pair).
 //
-// Fuses the gate backward (amil_gate_ew.cuh) into the hidden-gradient GEMM as the PRODUCER of its A
+// Fuses the gate backward (an elementwise pass over the stashed activations) into the hidden-gradient GEMM as the PRODUCER of its A
 // operand, so dG makes no round trip through L2 between the two and the step loses one launch:
 //
 //   phase A  (worker warps, while the producer prefetches Wab): per row i of the 128-row tile

@@ -112,12 +112,13 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 
   if (warp == 0 && lane == 0) {
     // =============================== TMA producer (both CTAs) ==========================
-    for (int kb = 0; kb < C::KB1; ++kb) {
+    const int kb1 = a.kb1 > 0 ? a.kb1 : C::KB1;   // 16 k-blocks of x, or 48 in the split-precision form (MMF_PRECISE_FC)
+    for (int kb = 0; kb < kb1; ++kb) {
       // the ring's first NS1 loads go out first; only then is the rest of this CTA's x tile prefetched
       // into L2 (issuing all 16 prefetches up front queued the first real load behind them:
       // first stage landed 8k cycles after the cluster sync)
       if (kb == C::NS1)
-        for (int kp = C::NS1; kp < C::KB1; ++kp) tma_prefetch_l2_2d(&tmX, kp * 64, (int)row0);
+        for (int kp = C::NS1; kp < kb1; ++kp) tma_prefetch_l2_2d(&tmX, kp * 64, (int)row0);
       const int s = kb % C::NS1;
       const uint32_t ph = (kb / C::NS1) & 1;
       mbar_wait(smem_u32(&bar_empty1[s]), ph ^ 1);
@@ -158,7 +159,8 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     // =============================== MMA issuer (leader CTA) ===========================
     constexpr uint32_t idesc1 = umma_idesc_bf16(256, 256, 0, 0);
     constexpr uint32_t idesc2 = umma_idesc_bf16(256, C::CHN, 0, 0);
-    for (int kb = 0; kb < C::KB1; ++kb) {
+    const int kb1 = a.kb1 > 0 ? a.kb1 : C::KB1;
+    for (int kb = 0; kb < kb1; ++kb) {
       const int s = kb % C::NS1;
       const uint32_t ph = (kb / C::NS1) & 1;
       mbar_wait(smem_u32(&bar_full1[s]), ph);
@@ -407,7 +409,7 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         }
         if (MODE == AMIL_FWD && a.AG != nullptr) {
           // training forward: stash the pre-dropout branch activations (fp16) so that the backward needs
-          // neither GEMM again (amil_gate_ew.cuh consumes them in place). Each thread owns one ROW of the
+          // neither GEMM again (amil_hidden_fused.cuh consumes them in place). Each thread owns one ROW of the
           // warp's 32 x 32 block; storing that directly is 32 scattered 16-byte writes per instruction
           // (+10 us per 16k bag). The block is transposed through a 2 KB per-warp scratch so that every
           // st.global.v4 covers 8 rows x 64 contiguous bytes (full 32-byte sectors).

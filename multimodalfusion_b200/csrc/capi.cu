@@ -6,7 +6,6 @@
 #include "../../include/mmf_b200.h"
 #include "amil_tile.cuh"
 #include "amil_tile2.cuh"
-#include "amil_gate_ew.cuh"
 #include "amil_hidden_fused.cuh"
 #include <stdlib.h>
 #include "gemm_tc.cuh"
@@ -127,34 +126,6 @@ int pick_splits_pair(int out_tiles, int kb_total, int* kb_per_split) {
   return splits;
 }
 
-// split-K factor so that the grid roughly fills 148 SMs once or twice
-int pick_splits(int out_tiles, int kb_total, int* kb_per_split) {
-  int splits = 148 / out_tiles;  // floor: a single wave
-  if (splits < 1) splits = 1;
-  if (splits > kb_total) splits = kb_total;
-  int per = (kb_total + splits - 1) / splits;
-  splits = (kb_total + per - 1) / per;  // no empty slices
-  *kb_per_split = per;
-  return splits;
-}
-
-template <int L, int D, bool GATED, int MODE>
-int launch_amil(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, const AmilArgs& a,
-                void* Hbuf, cudaStream_t st) {
-  using C = AmilCfg<L, D, GATED>;
-  auto kern = amil_tile_kernel<L, D, GATED, MODE>;
-  MMF_CONFIGURE_SMEM(kern, C::SMEM_BYTES);
-  CUtensorMap tmX, tmW1, tmWab, tmH;
-  MMF_TRY(make_tmap_bf16(&tmX, x, (uint64_t)N, 1024, (uint64_t)ldx, 128));
-  MMF_TRY(make_tmap_bf16(&tmW1, w->W1, L, 1024, 1024, 256));
-  MMF_TRY(make_tmap_bf16(&tmWab, w->Wab_packed, (uint64_t)C::NCH * C::CHN, L, L, C::CHN));
-  if (Hbuf) MMF_TRY(make_tmap_bf16(&tmH, Hbuf, (uint64_t)N, L, L, 128));
-  else tmH = tmX;
-  const int tiles = (int)((N + 127) / 128);
-  kern<<<tiles, 256, C::SMEM_BYTES, st>>>(tmX, tmW1, tmWab, tmH, a);
-  return launch_status();
-}
-
 // CTA-pair kernel (amil_tile2.cuh): grid = 2 * ceil(N / 256), cluster (2,1,1)
 template <int L, int D, bool GATED, int MODE, bool DROPH, bool DROPA>
 int launch_amil2v(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, const AmilArgs& a,
@@ -163,15 +134,20 @@ int launch_amil2v(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w
   auto kern = amil_tile2_kernel<L, D, GATED, MODE, DROPH, DROPA>;
   MMF_CONFIGURE_SMEM(kern, C::SMEM_BYTES);
   CUtensorMap tmX, tmW1, tmWab, tmH, tmWk;
-  MMF_TRY(make_tmap_bf16(&tmX, x, (uint64_t)N, 1024, (uint64_t)ldx, 128));
-  MMF_TRY(make_tmap_bf16(&tmW1, w->W1, L, 1024, 1024, 128));
+  const bool precise = (a.flags & MMF_PRECISE_FC) != 0;
+  const uint64_t kin = precise ? 3072 : 1024;
+  if (precise && (!w->W1_split || ldx < 3072)) return MMF_E_INVALID;
+  MMF_TRY(make_tmap_bf16(&tmX, x, (uint64_t)N, kin, (uint64_t)ldx, 128));
+  MMF_TRY(make_tmap_bf16(&tmW1, precise ? w->W1_split : w->W1, L, kin, kin, 128));
   MMF_TRY(make_tmap_bf16(&tmWab, w->Wab_packed, (uint64_t)C::NCH * C::CHN, L, L, C::CHN / 2));
   if (Hbuf) MMF_TRY(make_tmap_bf16(&tmH, Hbuf, (uint64_t)N, L, L, 128));
   else tmH = tmX;
   if (wk_split) MMF_TRY(make_tmap_bf16(&tmWk, wk_split, 16, L, L, 8));   // [Wk_hi ; Wk_lo], 8 rows per CTA of the pair
   else tmWk = tmX;
   const int pairs = (int)((N + 255) / 256);
-  return launch_pdl(kern, dim3(2 * pairs), dim3(AMIL2_THREADS), C::SMEM_BYTES, st, tmX, tmW1, tmWab, tmH, tmWk, a);
+  AmilArgs a2 = a;
+  a2.kb1 = (int)(kin / 64);
+  return launch_pdl(kern, dim3(2 * pairs), dim3(AMIL2_THREADS), C::SMEM_BYTES, st, tmX, tmW1, tmWab, tmH, tmWk, a2);
 }
 
 template <int L, int D, bool GATED, int MODE>
@@ -184,27 +160,13 @@ int launch_amil2(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w,
             : launch_amil2v<L, D, GATED, MODE, false, false>(x, N, ldx, w, a, Hbuf, wk_split, st);
 }
 
-// MMF_TILE_V1=1 selects the single-CTA kernel (kept as the reference implementation of the pair kernel)
-inline bool use_tile_v1() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("MMF_TILE_V1");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v == 1;
-}
-
 template <int MODE>
 int dispatch_amil(int L, int D, int gated, const void* x, int64_t N, int64_t ldx,
                   const MmfAmilWeights* w, const AmilArgs& a, void* Hbuf, cudaStream_t st, const void* wk_split = nullptr) {
 #define MMF_CASE(LL, DD)                                                                  \
-  if (L == LL && D == DD) {                                                               \
-    if (!use_tile_v1())                                                                   \
-      return gated ? launch_amil2<LL, DD, true, MODE>(x, N, ldx, w, a, Hbuf, wk_split, st) \
-                   : launch_amil2<LL, DD, false, MODE>(x, N, ldx, w, a, Hbuf, wk_split, st); \
-    return gated ? launch_amil<LL, DD, true, MODE>(x, N, ldx, w, a, Hbuf, st)             \
-                 : launch_amil<LL, DD, false, MODE>(x, N, ldx, w, a, Hbuf, st);           \
-  }
+  if (L == LL && D == DD)                                                                    \
+    return gated ? launch_amil2<LL, DD, true, MODE>(x, N, ldx, w, a, Hbuf, wk_split, st)    \
+                 : launch_amil2<LL, DD, false, MODE>(x, N, ldx, w, a, Hbuf, wk_split, st);
   MMF_CASE(256, 256)
   MMF_CASE(512, 384)
   MMF_CASE(256, 384)
@@ -242,20 +204,6 @@ int launch_hidden_fused(const HiddenFusedArgs& a, int flags, const CUtensorMap& 
                                     : launch_hidden_fused2<L, D, GATED, false>(a, tmAG, tmWab, tmDU, st);
 }
 
-template <int L, int D, bool GATED, bool DROP>
-int launch_gate_ew2(const GateEwArgs& a, cudaStream_t st) {
-  using C = GateEwCfg<L, D, GATED>;
-  auto kern = amil_gate_ew_kernel<L, D, GATED, DROP>;
-  MMF_CONFIGURE_SMEM(kern, C::SMEM_BYTES);
-  const long long chunks = (a.N + C::ROWS - 1) / C::ROWS;
-  const int blocks = (int)(chunks < 148 ? chunks : 148);   // persistent: one CTA per SM
-  return launch_pdl(kern, dim3(blocks), dim3(C::THREADS), C::SMEM_BYTES, st, a);
-}
-template <int L, int D, bool GATED>
-int launch_gate_ew(const GateEwArgs& a, cudaStream_t st) {
-  return (a.flags & MMF_DROPOUT_ATTN) ? launch_gate_ew2<L, D, GATED, true>(a, st)
-                                      : launch_gate_ew2<L, D, GATED, false>(a, st);
-}
 
 }  // namespace
 
@@ -306,6 +254,13 @@ int mmf_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
   return launch_status();
 }
 
+int mmf_split_f32_bf16x3(const float* x, int64_t n_rows, int64_t ldx, void* out, void* stream) {
+  if (!x || !out || n_rows <= 0 || ldx < 1024) return MMF_E_INVALID;
+  split_f32_bf16x3_kernel<<<(int)((n_rows * 1024 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      x, (long long)n_rows, (long long)ldx, reinterpret_cast<__nv_bfloat16*>(out));
+  return launch_status();
+}
+
 int mmf_pack_wab(const void* Wab, void* packed, int L, int D, int gated, void* stream) {
   if (!Wab || !packed || L % 8 || D % 128) return MMF_E_INVALID;
   pack_wab_kernel<<<148, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(Wab),
@@ -335,7 +290,6 @@ int mmf_amil_infer_varlen(const void* x, int64_t R, int64_t ldx, const MmfAmilWe
   if (!tile_valid || !seg_tile_offsets || n_bags <= 0 || !Wk || !bk || !A_raw || !partials || !M || !hazards || !S)
     return MMF_E_INVALID;
   if (K <= 0 || K > 16 || L > 1024 || (R % 128) != 0) return MMF_E_UNSUPPORTED;
-  if (use_tile_v1()) return MMF_E_UNSUPPORTED;
   if (flags & (MMF_DROPOUT_H | MMF_DROPOUT_ATTN)) return MMF_E_INVALID;   // inference only
   AmilArgs a = {};
   a.N = R; a.b1 = w->b1; a.bab = w->bab; a.wc = w->wc; a.bc = w->bc;
@@ -476,10 +430,9 @@ int mmf_amil_bwd_gate(const void* x, int64_t N, int64_t ldx, const MmfAmilWeight
   a.ml = ml; a.M = M; a.dM = dM; a.dA_raw = dA_raw;
   a.dG = c.dG; a.lddg = c.KD; a.colsum_ws = c.cs; a.dbc_ws = c.dbc_ws; a.dbg = g_timing_buffer;
   MMF_TRY(dispatch_amil<AMIL_BWD_GATE>(L, D, c.gated, x, N, ldx, w, a, c.Hb, st));
-  if (!use_tile_v1()) {   // the pair dU GEMM reads [h > 0] as a bitmask (the stash path's gate kernel emits it itself)
-    relu_mask_kernel<<<(int)((N * (L / 32) + 255) / 256), 256, 0, st>>>(c.Hb, N * (L / 32), c.mask);
-    MMF_TRY(launch_status());
-  }
+  // the pair dU GEMM reads [h > 0] as a bitmask (the training forward of the stash path emits it itself)
+  relu_mask_kernel<<<(int)((N * (L / 32) + 255) / 256), 256, 0, st>>>(c.Hb, N * (L / 32), c.mask);
+  MMF_TRY(launch_status());
   ReduceSegs segs = {};
   segs.n = 3;
   segs.s[0] = ReduceSeg{c.cs, c.ncols, D, g->dwc};
@@ -487,34 +440,6 @@ int mmf_amil_bwd_gate(const void* x, int64_t N, int64_t ldx, const MmfAmilWeight
   segs.s[2] = ReduceSeg{c.dbc_ws, 1, 1, g->dbc};
   launch_reduce_rows(segs, c.tiles * 4, st);
   return launch_status();
-}
-
-// Stage 1 (stash variant): the forward was mmf_amil_fwd_train — H and the fp16 branch activations
-// are already in the workspace; dG is formed in place by an HBM-bound elementwise kernel.
-int mmf_amil_bwd_gate_stashed(int64_t N, const MmfAmilWeights* w, int L, int D, int flags, uint64_t seed,
-                              const float* A_raw, const float* ml, const float* M, const float* dM,
-                              const float* dA_raw, const MmfAmilGrads* g, void* workspace,
-                              size_t workspace_bytes, void* stream) {
-  if (!w || !w->wc || N <= 0 || !workspace) return MMF_E_INVALID;
-  if (!((L == 256 && D == 256) || (L == 512 && D == 384) || (L == 256 && D == 384))) return MMF_E_UNSUPPORTED;
-  if (!A_raw || !ml || !M || !dM || !g || !g->dbab || !g->dwc || !g->dbc) return MMF_E_INVALID;
-  const int gated = flags & MMF_GATED;
-  const BwdWs lay = bwd_layout(N, L, D, gated);
-  if (workspace_bytes < lay.total) return MMF_E_WORKSPACE;
-  if (reinterpret_cast<uintptr_t>(workspace) & 1023u) return MMF_E_ALIGN;
-  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
-  cudaStream_t st = (cudaStream_t)stream;
-  GateEwArgs a = {};
-  a.N = N; a.H = reinterpret_cast<const __nv_bfloat16*>(ws + lay.off_H); a.AG = ws + lay.off_dG;
-  a.A_raw = A_raw; a.ml = ml; a.M = M; a.dM = dM; a.dA_raw = dA_raw; a.wc = w->wc;
-  a.dwc = g->dwc; a.dbab = g->dbab; a.dbc = g->dbc;
-  a.mask = reinterpret_cast<uint32_t*>(ws + lay.off_mask);
-  a.flags = flags; a.seed = seed;
-  int rc = MMF_E_UNSUPPORTED;
-  if (L == 256 && D == 256) rc = gated ? launch_gate_ew<256, 256, true>(a, st) : launch_gate_ew<256, 256, false>(a, st);
-  if (L == 512 && D == 384) rc = gated ? launch_gate_ew<512, 384, true>(a, st) : launch_gate_ew<512, 384, false>(a, st);
-  if (L == 256 && D == 384) rc = gated ? launch_gate_ew<256, 384, true>(a, st) : launch_gate_ew<256, 384, false>(a, st);
-  return rc;
 }
 
 // Stages 1 + 2 of the MMF_STASHED backward fused: the gate backward is the A-operand producer of the dU GEMM
@@ -618,18 +543,10 @@ int mmf_amil_bwd_hidden(const void* x, int64_t N, int64_t ldx, const MmfAmilWeig
   ga.c_bf16 = c.dU; ga.ldc = L;
   ga.s_raw = A_raw; ga.ml = ml; ga.dM = dM; ga.H = c.Hb; ga.ldh = L; ga.colsum_ws = c.db1_ws;
   ga.du_scale = (flags & MMF_DROPOUT_H) ? (1.0f / 0.75f) : 1.0f;
-  if (!use_tile_v1()) {
-    ga.mask = c.mask; ga.mask_ld = L / 32; ga.db1 = g->db1; ga.dbg = g_timing_buffer;
-    MMF_TRY(make_tmap_bf16(&tA.m[3], c.dU, (uint64_t)N, L, L, 128));   // output map (TMA store of the staged tile)
-    if (L == 512) return launch_gemm2<0, 1, EPI_DU, 512>(tA, tB, ga, 1, st);
-    return launch_gemm2<0, 1, EPI_DU, 256>(tA, tB, ga, 1, st);
-  }
-  MMF_TRY((launch_gemm<0, 1, EPI_DU>(tA, tB, ga, 1, st)));
-  ReduceSegs segs = {};
-  segs.n = 1;
-  segs.s[0] = ReduceSeg{c.db1_ws, L, L, g->db1};
-  launch_reduce_rows(segs, c.tiles * 4, st);
-  return launch_status();
+  ga.mask = c.mask; ga.mask_ld = L / 32; ga.db1 = g->db1; ga.dbg = g_timing_buffer;
+  MMF_TRY(make_tmap_bf16(&tA.m[3], c.dU, (uint64_t)N, L, L, 128));   // output map (TMA store of the staged tile)
+  if (L == 512) return launch_gemm2<0, 1, EPI_DU, 512>(tA, tB, ga, 1, st);
+  return launch_gemm2<0, 1, EPI_DU, 256>(tA, tB, ga, 1, st);
 }
 
 // Stage 3: dW1 += dU^T X, dWab += dG^T H (split-K over the instance axis), optional dx = dU W1.
@@ -642,7 +559,7 @@ int mmf_amil_bwd_wgrad(const void* x, int64_t N, int64_t ldx, const MmfAmilWeigh
   if ((flags & MMF_NEED_DX) && !dx) return MMF_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   const int kb_rows = (int)((N + 63) / 64);
-  if (!use_tile_v1()) {
+  {
     // dW1 += dU^T X and dWab += dG^T H in one single-wave grouped launch
     TMapSet tA = {}, tB = {};
     MMF_TRY(make_tmap_bf16(&tA.m[0], c.dU, (uint64_t)N, L, L, 64));
@@ -669,29 +586,6 @@ int mmf_amil_bwd_wgrad(const void* x, int64_t N, int64_t ldx, const MmfAmilWeigh
       ga.grp[1].c = g->dWab; ga.grp[1].ldc = L;
     }
     MMF_TRY(launch_gemm2_grouped(tA, tB, ga, st));
-  } else {
-    {
-      TMapSet tA = {}, tB = {};
-      MMF_TRY(make_tmap_bf16(&tA.m[0], c.dU, (uint64_t)N, L, L, 64));
-      MMF_TRY(make_tmap_bf16(&tB.m[0], x, (uint64_t)N, 1024, (uint64_t)ldx, 64));
-      GemmArgs ga = {};
-      ga.M = L; ga.N = 1024; ga.kb_total = kb_rows;
-      ga.a_seg_kb = kb_rows; ga.b_seg_n = 1024;
-      ga.c_f32 = g->dW1; ga.ldc = 1024;
-      const int splits = pick_splits((L / 128) * (1024 / 256), kb_rows, &ga.kb_per_split);
-      MMF_TRY((launch_gemm<1, 1, EPI_ATOMIC>(tA, tB, ga, splits, st)));
-    }
-    {
-      TMapSet tA = {}, tB = {};
-      MMF_TRY(make_tmap_bf16(&tA.m[0], c.dG, (uint64_t)N, c.KD, c.KD, 64));
-      MMF_TRY(make_tmap_bf16(&tB.m[0], c.Hb, (uint64_t)N, L, L, 64));
-      GemmArgs ga = {};
-      ga.M = c.KD; ga.N = L; ga.kb_total = kb_rows;
-      ga.a_seg_kb = kb_rows; ga.b_seg_n = L;
-      ga.c_f32 = g->dWab; ga.ldc = L;
-      const int splits = pick_splits((c.KD / 128) * ((L + 255) / 256), kb_rows, &ga.kb_per_split);
-      MMF_TRY((launch_gemm<1, 1, EPI_ATOMIC>(tA, tB, ga, splits, st)));
-    }
   }
   if (flags & MMF_NEED_DX) {
     TMapSet tA = {}, tB = {};
@@ -701,8 +595,7 @@ int mmf_amil_bwd_wgrad(const void* x, int64_t N, int64_t ldx, const MmfAmilWeigh
     ga.M = (int)N; ga.N = 1024; ga.kb_total = L / 64; ga.kb_per_split = ga.kb_total;
     ga.a_seg_kb = ga.kb_total; ga.b_seg_n = 1024;
     ga.c_bf16 = dx; ga.ldc = 1024;
-    if (use_tile_v1()) MMF_TRY((launch_gemm<0, 1, EPI_STORE>(tA, tB, ga, 1, st)));
-    else MMF_TRY((launch_gemm2<0, 1, EPI_STORE, 512>(tA, tB, ga, 1, st)));
+    MMF_TRY((launch_gemm2<0, 1, EPI_STORE, 512>(tA, tB, ga, 1, st)));
   }
   return MMF_OK;
 }
@@ -715,15 +608,8 @@ int mmf_amil_bwd(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w,
   if (!g || !g->dW1 || !g->db1 || !g->dWab || !g->dbab || !g->dwc || !g->dbc) return MMF_E_INVALID;
   if (flags & MMF_STASHED) {
     MMF_TRY(check_amil_common(x, N, ldx, w, L, D));
-    static const bool unfused = getenv("MMF_BWD_UNFUSED") && getenv("MMF_BWD_UNFUSED")[0] == '1';
-    if (!unfused) {
-      MMF_TRY(mmf_amil_bwd_gate_hidden_stashed(N, w, L, D, flags, seed, A_raw, ml, M, dM, dA_raw, g, workspace,
-                                               workspace_bytes, stream));
-    } else {   // the two-kernel form (elementwise gate pass, then the dU GEMM): kept for A/B timing and tests
-      MMF_TRY(mmf_amil_bwd_gate_stashed(N, w, L, D, flags, seed, A_raw, ml, M, dM, dA_raw, g, workspace,
-                                        workspace_bytes, stream));
-      MMF_TRY(mmf_amil_bwd_hidden(x, N, ldx, w, L, D, flags, A_raw, ml, dM, g, workspace, workspace_bytes, stream));
-    }
+    MMF_TRY(mmf_amil_bwd_gate_hidden_stashed(N, w, L, D, flags, seed, A_raw, ml, M, dM, dA_raw, g, workspace,
+                                             workspace_bytes, stream));
   } else {
     MMF_TRY(mmf_amil_bwd_gate(x, N, ldx, w, L, D, flags, seed, A_raw, ml, M, dM, dA_raw, g, workspace,
                               workspace_bytes, stream));
@@ -768,13 +654,8 @@ int mmf_linear_bf16_wgrad(const void* dY, int64_t M, int N, int64_t lddy, const 
   ga.M = N; ga.N = Ktot; ga.kb_total = (int)((M + 63) / 64);
   ga.a_seg_kb = ga.kb_total; ga.b_seg_n = K_per_seg;
   ga.c_f32 = dW; ga.ldc = Ktot;
-  if (use_tile_v1()) {
-    const int splits = pick_splits((N / 128) * (Ktot / 256), ga.kb_total, &ga.kb_per_split);
-    MMF_TRY((launch_gemm<1, 1, EPI_ATOMIC>(tA, tB, ga, splits, st)));
-  } else {
-    const int splits = pick_splits_pair(((N + 255) / 256) * (Ktot / 256), ga.kb_total, &ga.kb_per_split);
-    MMF_TRY((launch_gemm2<1, 1, EPI_ATOMIC, 256>(tA, tB, ga, splits, st)));
-  }
+  const int splits = pick_splits_pair(((N + 255) / 256) * (Ktot / 256), ga.kb_total, &ga.kb_per_split);
+  MMF_TRY((launch_gemm2<1, 1, EPI_ATOMIC, 256>(tA, tB, ga, splits, st)));
   if (db) {
     colsum_bf16_kernel<<<(N + 31) / 32, dim3(32, 8), 0, st>>>(
         reinterpret_cast<const __nv_bfloat16*>(dY), M, N, lddy, db, 1);

@@ -1,10 +1,9 @@
-// gemm_tc.cuh — one warp-specialised tcgen05 GEMM with selectable operand majors and fused
-// epilogues. It is the workhorse either side of the fused attention-MIL tile kernel:
+// gemm_tc.cuh — single-CTA warp-specialised tcgen05 GEMM (operand majors and epilogue are template parameters) and
+// the argument structs shared with the CTA-pair kernel (gemm2_tc.cuh). Instantiated for
 //
-//   (A K-major , B K-major )  y  = x W^T + b               radio reduce_dim forward
-//   (A K-major , B MN-major)  dU = (dG Wab + p dM^T) ⊙ relu'(h)   hidden-gradient pass
-//                             dx = dU W1                    (radio: gradient into reduce_dim)
-//   (A MN-major, B MN-major)  dW += dY^T X  (split-K over the instance axis)   weight grads
+//   (A K-major , B K-major, EPI_STORE)  y = x W^T + b      radio reduce_dim forward (A as up to 4 K-segments)
+//
+// (the backward GEMMs — dU, dx, split-K weight gradients — run on the CTA-pair kernel).
 //
 // Tile 128 x 256 x 64, 4-stage TMA ring (48 KB / stage), accumulator in 256 TMEM columns.
 // Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..7 = epilogue

@@ -310,6 +310,19 @@ __global__ void hazard_head_fwd_kernel(const float* __restrict__ M, int B, int L
   }
 }
 
+// fp32 [n, 1024] -> bf16 [n, 3072] = [hi | lo | hi]: the split-precision bag format (MMF_PRECISE_FC)
+__global__ void split_f32_bf16x3_kernel(const float* __restrict__ x, long long n, long long ldx,
+                                        __nv_bfloat16* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 1024) return;
+  const long long r = i >> 10, c = i & 1023;
+  const float v = x[r * ldx + c];
+  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+  __nv_bfloat16* o = out + r * 3072 + c;
+  o[0] = hi; o[1024] = lo; o[2048] = hi;
+}
+
 // bf16 hi / lo split of the classifier for the forward's z = Wk h side MMA (N = 16: rows 0..7 go to the even CTA of
 // the pair, rows 8..15 to the odd one): row j < K = bf16(Wk[j]), row 8 + j = bf16(Wk[j] - bf16(Wk[j])), others 0.
 __global__ void pack_head_weights_kernel(const float* __restrict__ Wk, int K, int L, __nv_bfloat16* __restrict__ out) {

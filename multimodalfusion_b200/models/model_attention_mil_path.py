@@ -98,12 +98,16 @@ class MIL_Attention_fc_surv_path(MIL_Attention_fc_path):
         f = self._fused
         seq = self.attention_net_WSI
         prep = AmilBranch.prepared(seq)
-        x = ops.to_bf16(path_features)
-        N = x.shape[0]
+        N = path_features.shape[0]
         if N > 32768:
             raise NotImplementedError("fused_step merges at most 256 tile partials per CTA (N <= 32768)")
         attn = seq[3]
         flags = ops.amil_flags(prep.gated, dropout_h=self.training, dropout_attn=self.training and attn.use_dropout)
+        if N <= ops.PRECISE_FC_MAX_ROWS:      # small bag: split-precision fc (see autograd.AmilPool)
+            x = ops.split_bag(path_features)
+            flags |= ops.MMF_PRECISE_FC
+        else:
+            x = ops.to_bf16(path_features)
         seed = _seed_from_torch() if self.training else 0
         K = self.classifier.weight.shape[0]
         buf = f["bufs"].get(N)

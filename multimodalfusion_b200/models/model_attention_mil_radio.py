@@ -8,7 +8,7 @@ through separate TMA descriptors and writes the bf16 [N,1024] bag the fused AMIL
 import torch
 import torch.nn as nn
 
-from ..autograd import HazardHead, SegmentedLinearBf16
+from ..autograd import HazardHead, reduce_dim_forward
 from ..utils.utils import initialize_weights
 from .model_modules import AmilBranch, Attn_Net, Attn_Net_Gated, XlinearFusion
 
@@ -60,7 +60,7 @@ class MIL_Attention_fc_surv_radio(MIL_Attention_fc_radio):
         bags = [kwargs[m] for m in self.modalities]
         if len(bags) > 1:
             if self.radio_fusion == 'concat':
-                x = SegmentedLinearBf16.apply(self.reduce_dim.weight, self.reduce_dim.bias, *bags)
+                x = reduce_dim_forward(self.reduce_dim.weight, self.reduce_dim.bias, bags)
             elif self.radio_fusion == 'tensor':
                 # repaired semantics: the reference calls `self.xfusion` (:84) but defines
                 # `radio_xfusion` (:29); read as written otherwise — slice 0 of every modality enters a

@@ -20,7 +20,7 @@ import torch
 import torch.nn as nn
 
 from .._lib import ACT_NONE, ACT_RELU
-from ..autograd import Dense, HazardHead, SegmentedLinearBf16
+from ..autograd import Dense, HazardHead, reduce_dim_forward
 from ..utils.utils import initialize_weights
 from .model_modules import (AmilBranch, Attn_Net, Attn_Net_Gated, SNN_Block, XlinearFusion,
                             snn_block_forward)
@@ -98,7 +98,7 @@ class MM_MIL_Attention_fc_surv(MM_MIL_Attention_fc):
             bags = [kwargs[m] for m in self.modalities]
             if len(bags) > 1:
                 if self.radio_fusion == 'concat':
-                    x = SegmentedLinearBf16.apply(self.reduce_dim.weight, self.reduce_dim.bias, *bags)
+                    x = reduce_dim_forward(self.reduce_dim.weight, self.reduce_dim.bias, bags)
                 elif self.radio_fusion == 'tensor':     # as written at :141 with the attribute name repaired
                     x = self.radio_xfusion(v_list=[b[0].unsqueeze(0) for b in bags])
                 else:

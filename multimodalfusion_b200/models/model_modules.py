@@ -199,11 +199,41 @@ class AmilBranch:
             seq._mmf_prep = cache
         return cache[1]
 
+    # Bags of up to this many instances run on the library's fp32 functor-SGEMM kernels (exact reference arithmetic):
+    # below one 128-row MMA tile the tensor cores are mostly idle and the step is launch-latency-bound either way, while
+    # a pooled embedding that is exact to fp32 keeps every ReLU unit of a downstream fusion head on the reference's
+    # side (a multimodal patient has ~1300 of them; an embedding off by 1e-4 flips one in a few patients, and one
+    # flipped unit near the top moves every upstream gradient by a few per cent). Radiology bags of 17-40 slices.
+    TINY_BAG_FP32_ROWS = 64
+
+    @staticmethod
+    def _pooled_fp32(seq: nn.Sequential, x: torch.Tensor, training: bool):
+        """fc -> ReLU -> Dropout -> (gated) attention -> softmax -> A.h with one Dense kernel per layer (fp32)."""
+        fc, attn = seq[0], seq[3]
+        Wa, ba, Wb, bb, wc, bc = attn.amil_weights()
+        h = Dense.apply(x.float(), fc.weight, fc.bias, ACT_RELU)
+        if training:
+            h = torch.nn.functional.dropout(h, 0.25, True)
+        q = Dense.apply(h, Wa, ba, ACT_TANH)
+        if training and attn.use_dropout:
+            q = torch.nn.functional.dropout(q, 0.25, True)
+        if Wb is not None:
+            g = Dense.apply(h, Wb, bb, ACT_SIGMOID)
+            if training and attn.use_dropout:
+                g = torch.nn.functional.dropout(g, 0.25, True)
+            q = q * g
+        A_raw = Dense.apply(q, wc, bc, ACT_NONE).t()                       # [1, N]
+        A = torch.softmax(A_raw, dim=1)
+        M = Dense.apply(A, h.t().contiguous(), None, ACT_NONE)             # [1, L] = A . h
+        return A_raw, M
+
     @staticmethod
     def pooled(seq: nn.Sequential, x: torch.Tensor, training: bool, group=None):
         from ..autograd import AmilPool
         attn = seq[3]
         params = AmilBranch._params(seq)
+        if group is None and AmilPool.precise_small_bags and 0 < x.shape[0] <= AmilBranch.TINY_BAG_FP32_ROWS:
+            return AmilBranch._pooled_fp32(seq, x, training)
         prep = AmilBranch.prepared(seq)
         flags = ops.amil_flags(prep.gated, dropout_h=training, dropout_attn=training and attn.use_dropout)
         seed = _seed_from_torch() if training else 0

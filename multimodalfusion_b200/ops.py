@@ -14,7 +14,7 @@ import torch
 
 from . import _lib
 from ._lib import (ACT_NONE, ACT_RELU, ACT_SELU, ACT_SIGMOID, ACT_TANH, MMF_DROPOUT_ATTN,
-                   MMF_DROPOUT_H, MMF_GATED, MMF_NEED_DX, MMF_STASHED, AmilGrads, AmilWeights, HeadStep, check, lib)
+                   MMF_DROPOUT_H, MMF_GATED, MMF_NEED_DX, MMF_PRECISE_FC, MMF_STASHED, AmilGrads, AmilWeights, HeadStep, check, lib)
 
 IN_FEATURES = 1024
 TILE_ROWS = 128
@@ -71,9 +71,11 @@ class AmilPrepared:
     wc: torch.Tensor          # f32 [D]
     bc: torch.Tensor          # f32 [1]
 
+    W1_split: Optional[torch.Tensor] = None   # bf16 [L,3072] = [W1_hi | W1_hi | W1_lo] (split-precision fc, small bags)
+
     def struct(self) -> AmilWeights:
         return AmilWeights(_p(self.W1), _p(self.b1), _p(self.Wab), _p(self.Wab_packed), _p(self.bab),
-                           _p(self.wc), _p(self.bc))
+                           _p(self.wc), _p(self.bc), _p(self.W1_split))
 
 
 def prepare_amil_weights(W1, b1, Wa, ba, Wb, bb, wc, bc) -> AmilPrepared:
@@ -92,8 +94,22 @@ def prepare_amil_weights(W1, b1, Wa, ba, Wb, bb, wc, bc) -> AmilPrepared:
     Wab = to_bf16(Wab32)
     packed = torch.empty_like(Wab)
     check(lib().mmf_pack_wab(_p(Wab), _p(packed), L, D, int(gated), _stream()), "mmf_pack_wab")
+    W1f = _f32c(W1)
+    W1lo = to_bf16(W1f - W1b.float())
     return AmilPrepared(L, D, gated, W1b, _f32c(b1), Wab, packed, bab, _f32c(wc).reshape(-1),
-                        _f32c(bc).reshape(-1))
+                        _f32c(bc).reshape(-1), torch.cat([W1b, W1b, W1lo], dim=1).contiguous())
+
+
+PRECISE_FC_MAX_ROWS = 4096   # bags up to this size run the split-precision fc (MMF_PRECISE_FC): see split_bag
+
+
+def split_bag(x: torch.Tensor) -> torch.Tensor:
+    """fp32 (or bf16) bag [N,1024] -> bf16 [N,3072] = [hi | lo | hi]: the input format of MMF_PRECISE_FC."""
+    _require_cuda(x)
+    x = _f32c(x)
+    out = torch.empty(x.shape[0], 3 * IN_FEATURES, dtype=torch.bfloat16, device=x.device)
+    check(lib().mmf_split_f32_bf16x3(_p(x), x.shape[0], x.stride(0), _p(out), _stream()), "mmf_split_f32_bf16x3")
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -108,11 +124,8 @@ def amil_partials(x: torch.Tensor, w: AmilPrepared, flags: int, seed: int = 0,
                   h_stash: Optional[torch.Tensor] = None):
     """Runs the fused tile kernel: returns (A_raw [N] f32, partials [tiles, L+2] f32)."""
     _require_cuda(x)
-    if x.dtype != torch.bfloat16 or x.dim() != 2 or x.shape[1] != IN_FEATURES or x.stride(1) != 1:
-        raise ValueError("x must be a bf16 [N,1024] tensor with unit inner stride")
+    _check_bag(x, flags)
     N = x.shape[0]
-    if N == 0:
-        raise ValueError("empty bag")
     tiles = (N + TILE_ROWS - 1) // TILE_ROWS
     A_raw = torch.empty(N, dtype=torch.float32, device=x.device)
     partials = torch.empty(tiles, w.L + 2, dtype=torch.float32, device=x.device)
@@ -122,11 +135,12 @@ def amil_partials(x: torch.Tensor, w: AmilPrepared, flags: int, seed: int = 0,
     return A_raw, partials
 
 
-def stash_supported() -> bool:
-    """The activation stash lives in the CTA-pair kernel's epilogue; MMF_TILE_V1=1 (single-CTA reference
-    kernel) has none and always recomputes."""
-    import os
-    return os.environ.get("MMF_TILE_V1", "0")[:1] != "1"
+def _check_bag(x: torch.Tensor, flags: int) -> None:
+    width = 3 * IN_FEATURES if flags & MMF_PRECISE_FC else IN_FEATURES
+    if x.dtype != torch.bfloat16 or x.dim() != 2 or x.shape[1] != width or x.stride(1) != 1:
+        raise ValueError(f"x must be a bf16 [N,{width}] tensor with unit inner stride")
+    if x.shape[0] == 0:
+        raise ValueError("empty bag")
 
 
 def amil_bwd_workspace(N: int, w: AmilPrepared, flags: int, device) -> torch.Tensor:
@@ -144,11 +158,8 @@ def amil_partials_train(x: torch.Tensor, w: AmilPrepared, flags: int, seed: int 
     zero: optional contiguous fp32 tensor (numel % 4 == 0) cleared by the kernel while GEMM1 runs — the step's
     flat gradient buffer (fused zero_grad)."""
     _require_cuda(x)
-    if x.dtype != torch.bfloat16 or x.dim() != 2 or x.shape[1] != IN_FEATURES or x.stride(1) != 1:
-        raise ValueError("x must be a bf16 [N,1024] tensor with unit inner stride")
+    _check_bag(x, flags)
     N = x.shape[0]
-    if N == 0:
-        raise ValueError("empty bag")
     if workspace is None:
         workspace = amil_bwd_workspace(N, w, flags, x.device)
     tiles = (N + TILE_ROWS - 1) // TILE_ROWS
@@ -258,7 +269,7 @@ def amil_backward(x: torch.Tensor, w: AmilPrepared, flags: int, seed: int, A_raw
             dbc=torch.zeros(1, dtype=torch.float32, device=dev),
         )
     need_dx = bool(flags & MMF_NEED_DX)
-    dx = torch.empty(N, IN_FEATURES, dtype=torch.bfloat16, device=dev) if need_dx else None
+    dx = torch.empty(N, IN_FEATURES, dtype=torch.bfloat16, device=dev) if need_dx else None   # (always [N,1024])
     if stash is not None:
         ws_view, flags = stash, flags | MMF_STASHED
     else:
@@ -453,8 +464,7 @@ def amil_fused_step(x: torch.Tensor, w: AmilPrepared, flags: int, seed: int, buf
     dbc), dWk, dbk; `zero` (the flat gradient buffer that holds them all) is cleared by the forward first.
     Outputs are left in `buf` (loss, hazards, S, Y_hat, A_raw, M)."""
     _require_cuda(x, Wk)
-    if x.dtype != torch.bfloat16 or x.dim() != 2 or x.shape[1] != IN_FEATURES or x.stride(1) != 1:
-        raise ValueError("x must be a bf16 [N,1024] tensor with unit inner stride")
+    _check_bag(x, flags)
     N = x.shape[0]
     if N != buf.N:
         raise ValueError("FusedStepBuffers were sized for another bag")

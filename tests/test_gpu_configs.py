@@ -140,7 +140,13 @@ def test_config5_cohort_inference_ragged_bags(dev):
         x = cases.features(n, 900 + i)
         with torch.no_grad():
             hz, S, Y_hat, A = model(path_features=x.to(dev))
-        s, h, _, _ = O.fc_attention(x, bfr(W[0]), W[1], bfr(W[2]), W[3], bfr(W[4]), W[5], W[6], W[7], round_h=True)
+        # the oracle sees the operands the kernels see: up to 64 instances the fp32 kernels (exact), up to 4096 the
+        # split-precision fc (W1 effectively fp32, bf16 h / attention weights), beyond that plain bf16 operands
+        if n <= 64:
+            s, h, _, _ = O.fc_attention(x, *W)
+        else:
+            W1o = W[0] if n <= 4096 else bfr(W[0])
+            s, h, _, _ = O.fc_attention(x, W1o, W[1], bfr(W[2]), W[3], bfr(W[4]), W[5], W[6], W[7], round_h=True)
         Mo, _, _ = O.softmax_pool(s, h)
         hz_r, S_r, Y_r = O.hazard_head(Mo.reshape(1, -1), Wk, bk)
         assert A.shape == (1, n) and rel_err(A, s) < 4e-3
@@ -166,10 +172,21 @@ def test_config5_varlen_cohort_launch_equals_per_slide_forward(dev):
         model = MIL_Attention_fc_surv_path(gate_path=True, model_size_wsi=size, n_classes=4).eval().to(dev)
         sizes = [1, 127, 128, 129, 500, 3000, 256, 7777, 64, 20000]
         bags = [cases.features(n, 40 + i).to(dev) for i, n in enumerate(sizes)]
+        from multimodalfusion_b200.autograd import AmilPool
         hz, S, Y_hat, A = model.infer_cohort(bags)
         assert hz.shape == (len(sizes), 4) and Y_hat.shape == (len(sizes), 1)
         for i, b in enumerate(bags):
-            with torch.no_grad():
-                h1, S1, Y1, A1 = model(path_features=b)
+            # the packed launch runs every slide with plain bf16 operands: bit-equal to the batch-1 forward in that mode
+            AmilPool.precise_small_bags = False
+            try:
+                with torch.no_grad():
+                    h1, S1, Y1, A1 = model(path_features=b)
+            finally:
+                AmilPool.precise_small_bags = True
             assert torch.equal(A[i], A1), (size, i)
             assert rel_err(hz[i], h1) < 1e-5 and rel_err(S[i], S1) < 1e-5 and Y_hat[i].item() == Y1.item()
+            # and close to the default batch-1 forward (small slides: split-precision / fp32 fc). Scores of a bag of
+            # one to a few instances have no large element to normalise by: 2e-2 on the scores, 1e-2 on the hazards
+            with torch.no_grad():
+                h2, S2, Y2, A2 = model(path_features=b)
+            assert rel_err(A[i], A2) < 2e-2 and rel_err(hz[i], h2) < 1e-2

@@ -61,6 +61,25 @@ def _check_param_grads(model, gold_grads, tol, relu_gated=()):
     assert not bad, f"gradients beyond {tol}: {bad}"
 
 
+def _check_param_grads_strict(model, gold_grads, tol):
+    """North-star bar: every parameter gradient within tol (max |err| / max |ref| over the sampled entries)."""
+    worst = {}
+    for k, p in model.named_parameters():
+        fp = gold_grads[k]
+        if fp is None or fp["norm"] == 0.0:
+            assert p.grad is None or p.grad.abs().max().item() <= 1e-4, k
+            continue
+        assert p.grad is not None, k
+        ref = fp["vals"]
+        if ref.abs().max().item() <= 1e-6:
+            assert p.grad.abs().max().item() <= 1e-4, k
+            continue
+        got = p.grad.detach().reshape(-1).float().cpu()[cases._sample_idx(p.numel())]
+        worst[k] = (got - ref).abs().max().item() / ref.abs().max().item()
+    bad = {k: f"{v:.3e}" for k, v in worst.items() if v >= tol}
+    assert not bad, f"gradients beyond {tol}: {bad} (worst of the rest: {max(worst.values()):.3e})"
+
+
 @pytest.mark.parametrize("name", list(cases.MM_CASES))
 def test_mm_model_vs_reference_goldens(dev, goldens_mm, name):
     from multimodalfusion_b200.utils import NLLSurvLoss
@@ -74,7 +93,7 @@ def test_mm_model_vs_reference_goldens(dev, goldens_mm, name):
         # radiology scores pass through TWO bf16 stages (reduce_dim writes a bf16 bag, then the fused AMIL kernel): the
         # bf16-operand restatement itself reaches 0.9e-2 on these 17-40-slice bags (tests/test_mm_glue_cpu.py), so they
         # get 2e-2; pathology scores and the hazards keep the north star's 1e-2
-        tol = 2 * TOL_FWD_REF if k == "radiology" else TOL_FWD_REF
+        tol = TOL_FWD_REF
         assert A_raw[k].shape == gold["A_raw"][k].shape and rel_err(A_raw[k], gold["A_raw"][k]) < tol, k
     assert rel_err(hazards, gold["hazards"]) < TOL_FWD_REF and rel_err(S, gold["S"]) < TOL_FWD_REF
     assert Y_hat.shape == (1, 1) and Y_hat.dtype == torch.int64
@@ -83,7 +102,7 @@ def test_mm_model_vs_reference_goldens(dev, goldens_mm, name):
     model.zero_grad()
     loss.backward()
     n_min = min(n for n in (cfg["Nr"], cfg["Np"]) if n)
-    _check_param_grads(model, gold["grads"], 3e-2 + 3.0 / n_min, relu_gated=("mm.", "classifier"))
+    _check_param_grads_strict(model, gold["grads"], 2e-2)
     feats = model(**kw, return_features=True)
     assert feats.shape == (1, 512 if cfg["fusion"] == "tensor" else 256 * len(cfg["mode"].split("_")))
 

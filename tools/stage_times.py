@@ -74,7 +74,6 @@ stages = {
     "fwd_hstash": lambda x: ops.amil_partials(x, prep, flags, 1, h_stash=hbuf),
     "fwd_train": lambda x: ops.amil_partials_train(x, prep, flags, 1, workspace=ws),
     "head_step": lambda x: ops.amil_head_nll_step(parts, Wk, bk, Y, c, 0.0, dWk=dWk, dbk=dbk),
-    "gate_stashed": lambda x: check(lib.mmf_amil_bwd_gate_stashed(N, C.byref(wst), L, D, flags, 1, A_raw.data_ptr(), ml.data_ptr(), M.data_ptr(), dM.data_ptr(), None, C.byref(gs), ws.data_ptr(), ws.numel(), S())),
     "gate_hidden_fused": lambda x: check(lib.mmf_amil_bwd_gate_hidden_stashed(N, C.byref(wst), L, D, flags, 1, A_raw.data_ptr(), ml.data_ptr(), M.data_ptr(), dM.data_ptr(), None, C.byref(gs), ws.data_ptr(), ws.numel(), S())),
     "gate_recompute": lambda x: check(lib.mmf_amil_bwd_gate(x.data_ptr(), N, 1024, C.byref(wst), L, D, flags, 1, A_raw.data_ptr(), ml.data_ptr(), M.data_ptr(), dM.data_ptr(), None, C.byref(gs), ws.data_ptr(), ws.numel(), S())),
     "hidden": lambda x: check(lib.mmf_amil_bwd_hidden(x.data_ptr(), N, 1024, C.byref(wst), L, D, flags, A_raw.data_ptr(), ml.data_ptr(), dM.data_ptr(), C.byref(gs), ws.data_ptr(), ws.numel(), S())),
