@@ -63,7 +63,10 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const AdamTensors T, co
   }
 }
 
-// counts[0] concordant, [1] discordant, [2] tied in risk, over comparable pairs (event_i and t_i < t_j)
+// counts[0] concordant, [1] discordant, [2] tied in risk, over the comparable pairs of
+// sksurv.metrics.concordance_index_censored (scikit-survival 0.2x, metrics.py:_get_comparable): sample i with an event
+// is comparable to every j with t_j > t_i AND to every j censored at the SAME time t_j == t_i (an event at t counts
+// as earlier than a censoring at t). Discretised survival times (months, days) make such ties common.
 __global__ void __launch_bounds__(256) cindex_pairs_kernel(const float* __restrict__ risk, const float* __restrict__ times,
                                                            const float* __restrict__ event, int B, float tied_tol,
                                                            unsigned long long* __restrict__ counts) {
@@ -75,7 +78,8 @@ __global__ void __launch_bounds__(256) cindex_pairs_kernel(const float* __restri
   if (event[i] != 0.f) {
     const float ti = times[i], ri = risk[i];
     for (int j = threadIdx.x; j < B; j += 256) {
-      if (times[j] > ti) {
+      const float tj = times[j];
+      if (tj > ti || (tj == ti && event[j] == 0.f)) {
         const float d = ri - risk[j];
         if (fabsf(d) <= tied_tol) ++tied;
         else if (d > 0.f) ++conc;

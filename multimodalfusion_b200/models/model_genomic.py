@@ -40,9 +40,13 @@ class MaxNet_base(nn.Module):
 
 class MaxNet(MaxNet_base):
     def forward(self, **kwargs):
-        feats = self.features(kwargs['genomic_features'])
+        x = kwargs['genomic_features']
+        # the reference's loaders hand over ONE patient's omics as a 1-D [d] tensor (the collate concatenates 1-D rows,
+        # datasets/dataset_survival.py); nn.Linear takes it as is and `logits.unsqueeze(0)` makes the [1,K] batch
+        one_d = x.dim() == 1
+        feats = self.features(x.unsqueeze(0) if one_d else x)
         if kwargs.get('return_features'):
-            return feats
+            return feats.squeeze(0) if one_d else feats
         if 'nll' in self.bag_loss:
             hazards, S, Y_hat = HazardHead.apply(feats, self.classifier.weight, self.classifier.bias)
             # reference: logits.unsqueeze(0) -> [1,B,K]; cumprod/topk along dim=1 (the batch axis
@@ -54,7 +58,7 @@ class MaxNet(MaxNet_base):
 
 class MaxNet_captum(MaxNet_base):
     def forward(self, x):
-        feats = self.features(x)
+        feats = self.features(x.unsqueeze(0) if x.dim() == 1 else x)
         if 'nll' in self.bag_loss:
             _, S, _ = HazardHead.apply(feats, self.classifier.weight, self.classifier.bias)
             return -torch.sum(S, dim=1)

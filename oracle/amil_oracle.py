@@ -356,17 +356,46 @@ def ce_surv_loss(hazards, S, Y, c, alpha=0.4, eps=1e-7):
 
 
 def concordance_index(risk, times, event, tied_tol=1e-8):
-    """Harrell's C as sksurv.concordance_index_censored computes it (utils/core_utils.py:258):
-    comparable pairs = (i event, t_i < t_j); ties in risk within tied_tol count 1/2."""
+    """Harrell's C as sksurv.metrics.concordance_index_censored computes it (utils/core_utils.py:258; scikit-survival
+    is not vendored in the reference tree nor installed here — pinned dependency of its env.yml — so this restates its
+    published algorithm, metrics.py:_get_comparable / _estimate_concordance_index): comparable pairs = (i has an event,
+    t_i < t_j) plus (i has an event, t_j == t_i, j censored); ties in risk within tied_tol count 1/2.
+    `sksurv_comparable_pairs` below is a second, literal restatement of _get_comparable (sort + tie groups) used to
+    cross-check this one on tied-time data."""
     risk, times, event = map(lambda a: np.asarray(a, dtype=np.float64), (risk, times, event))
     conc = disc = tied = 0
     for i in range(len(times)):
         if not event[i]:
             continue
-        mask = times > times[i]
+        mask = (times > times[i]) | ((times == times[i]) & (event == 0))
         d = risk[i] - risk[mask]
         conc += int((d > tied_tol).sum())
         tied += int((np.abs(d) <= tied_tol).sum())
         disc += int((d < -tied_tol).sum())
     tot = conc + disc + tied
     return (conc + 0.5 * tied) / tot if tot else float("nan")
+
+
+def sksurv_comparable_pairs(times, event):
+    """Literal restatement of sksurv.metrics._get_comparable: walk the samples in time order, group equal times;
+    an event j of a group is comparable to every later sample and to the censored samples of its own group.
+    Returns the set of ordered pairs (j, k)."""
+    times = np.asarray(times, dtype=np.float64)
+    event = np.asarray(event).astype(bool)
+    order = np.argsort(times, kind="stable")
+    n = len(times)
+    pairs = set()
+    i = 0
+    while i < n:
+        end = i + 1
+        while end < n and times[order[end]] == times[order[i]]:
+            end += 1
+        for j in range(i, end):
+            if event[order[j]]:
+                for k in range(end, n):
+                    pairs.add((int(order[j]), int(order[k])))
+                for k in range(i, end):
+                    if not event[order[k]]:
+                        pairs.add((int(order[j]), int(order[k])))
+        i = end
+    return pairs

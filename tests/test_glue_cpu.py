@@ -97,6 +97,51 @@ def test_snn_model_glue(goldens, name):
     _check_grads(model, gold["grads"])
 
 
+@pytest.mark.parametrize("bag_loss", ["cox_surv", "nll_surv"])
+def test_snn_model_takes_one_patient_as_a_1d_row(bag_loss):
+    """The reference's loaders hand MaxNet ONE patient's omics as a 1-D [d] tensor (the collate concatenates 1-D rows):
+    nn.Linear accepts it, `logits.unsqueeze(0)` makes the [1,K] batch, the Cox risk is squeezed to a scalar
+    (models/model_genomic.py:53-72). The mirror must return the same shapes and the values of the [1,d] batch; checked
+    against the live reference class when its tree is mounted."""
+    import os
+    import sys
+    from multimodalfusion_b200.models import MaxNet
+    torch.manual_seed(3)
+    model = MaxNet(36, bag_loss=bag_loss, n_classes=4).eval()
+    x = torch.randn(36)
+    with oracle_kernels():
+        out1 = model(genomic_features=x)
+        out2 = model(genomic_features=x.unsqueeze(0))
+        f1 = model(genomic_features=x, return_features=True)
+    assert f1.shape == (256,)
+    if bag_loss == "nll_surv":
+        assert out1[0].shape == (1, 4) and out1[1].shape == (1, 4) and out1[2].shape == (1, 1)
+        assert torch.equal(out1[0], out2[0]) and torch.equal(out1[1], out2[1])
+    else:
+        assert out1[0].dim() == 0 and torch.equal(out1[0], out2[0])
+    ref_root = os.environ.get("MMF_REFERENCE", "/root/reference")
+    if os.path.isdir(os.path.join(ref_root, "models")):
+        import importlib
+        sys.path.insert(0, ref_root)
+        try:
+            torch.cuda.FloatTensor = torch.FloatTensor
+            saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "models" or k.startswith("models.")}
+            ref_cls = importlib.import_module("models.model_genomic").MaxNet
+            torch.manual_seed(3)
+            ref = ref_cls(36, bag_loss=bag_loss, n_classes=4).eval()
+            ref.load_state_dict(model.state_dict())
+            r = ref(genomic_features=x)
+            for a, b in zip(out1[:3], r[:3]):
+                if b is not None:
+                    assert a.shape == b.shape and rel_err(a.float(), b.float()) < TOL
+            assert rel_err(f1, ref(genomic_features=x, return_features=True)) < TOL
+        finally:
+            sys.path.remove(ref_root)
+            for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
+                sys.modules.pop(k)
+            sys.modules.update(saved)
+
+
 def _head_case(model, cfg, gold):
     hr, hp, ho = [t.requires_grad_(True) for t in cases.embeddings(cfg)]
     times, c = cases.cohort_labels(cfg["B"], cfg["seed"])

@@ -331,6 +331,22 @@ def test_snn_model_vs_reference_goldens(dev, goldens, name):
     _grad_check(model, gold["grads"], 1e-4)
 
 
+@pytest.mark.parametrize("bag_loss", ["cox_surv", "nll_surv"])
+def test_snn_model_one_patient_1d_row(dev, bag_loss):
+    """One patient's omics as the 1-D [d] row the reference's loaders produce == row 0 of the [1,d] batch, with the
+    reference's output shapes (models/model_genomic.py:53-72; values pinned on the CPU in tests/test_glue_cpu.py)."""
+    from multimodalfusion_b200.models import MaxNet
+    torch.manual_seed(3)
+    model = MaxNet(36, bag_loss=bag_loss, n_classes=4).eval().to(dev)
+    x = torch.randn(36, device=dev)
+    out1, out2 = model(genomic_features=x), model(genomic_features=x.unsqueeze(0))
+    assert model(genomic_features=x, return_features=True).shape == (256,)
+    if bag_loss == "nll_surv":
+        assert out1[0].shape == (1, 4) and out1[2].shape == (1, 1) and torch.equal(out1[0], out2[0])
+    else:
+        assert out1[0].dim() == 0 and torch.equal(out1[0], out2[0])
+
+
 @pytest.mark.parametrize("name", list(cases.HEAD_CASES))
 def test_kronecker_heads_vs_reference_goldens(dev, goldens, name):
     from multimodalfusion_b200.utils import CoxSurvLoss, NLLSurvLoss, RankingSurvLoss

@@ -56,6 +56,11 @@ def test_cindex_matches_oracle(dev, B):
     got = concordance_index(risk.to(dev), times.to(dev), event.to(dev))
     want = O.concordance_index(risk, times, event)
     assert (got != got and want != want) or abs(got - want) < 1e-12
+    # discretised times (months): events tied in time with censored samples are comparable pairs (sksurv semantics)
+    times_m = torch.floor(times / times.max() * 12)
+    got = concordance_index(risk.to(dev), times_m.to(dev), event.to(dev))
+    want = O.concordance_index(risk, times_m, event)
+    assert (got != got and want != want) or abs(got - want) < 1e-12
 
 
 def test_short_training_loop_with_fused_optimizer(dev):

@@ -173,6 +173,30 @@ def test_concordance_index_simple():
     assert O.concordance_index(risk[::-1], t, e) == 0.0
 
 
+def test_concordance_index_tied_times_follow_sksurv():
+    """sksurv.concordance_index_censored: an event at time t is comparable to a sample CENSORED at the same t (and to
+    nothing else at t). Hand-checked vector + the literal restatement of sksurv's _get_comparable on random tied data."""
+    import numpy as np
+    # times: two samples at t = 2 (one event, one censored), one later event, one earlier censored
+    t = [2.0, 2.0, 3.0, 1.0]
+    e = [1, 0, 1, 0]
+    risk = [0.9, 0.1, 0.5, 0.7]
+    # comparable: (0,1) tie-in-time event vs censored, (0,2) t0 < t2. Sample 3 is censored: starts no pair. Sample 2: nobody later.
+    assert O.sksurv_comparable_pairs(t, e) == {(0, 1), (0, 2)}
+    assert O.concordance_index(risk, t, e) == 1.0                 # 0.9 > 0.1 and 0.9 > 0.5
+    assert O.concordance_index([0.1, 0.9, 0.5, 0.7], t, e) == 0.0
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        n = 60
+        times = rng.integers(1, 12, n).astype(float)              # discretised months: many ties
+        event = rng.integers(0, 2, n)
+        r = rng.standard_normal(n)
+        pairs = O.sksurv_comparable_pairs(times, event)
+        conc = sum(r[i] > r[j] for i, j in pairs)
+        want = conc / len(pairs)
+        assert abs(O.concordance_index(r, times, event) - want) < 1e-12
+
+
 @pytest.mark.parametrize("name", list(cases.HEAD2_CASES))
 def test_fcnn_highway_heads_match_reference(goldens_heads2, name):
     """Oracle restatement of the fcnn / Highway fusion heads + ce_loss against the reference's own outputs
