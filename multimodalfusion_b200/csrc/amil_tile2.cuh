@@ -286,18 +286,19 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         if (ii + 1 < PIECES1) tmem_ld32(tq + (cb + 1) * 32, v[par ^ 1]);
         float (&u)[32] = v[par];
         const float4* b4p = reinterpret_cast<const float4*>(vec + C::V_B1 + cb * 32);
-        uint32_t hb0 = 0xFFFFFFFFu, hb1 = 0xFFFFFFFFu;   // all kept when dropout is off
-        if (drop_h) { hb0 = drop_bits16(rs_h, (uint32_t)(cb * 2)); hb1 = drop_bits16(rs_h, (uint32_t)(cb * 2 + 1)); }
+        uint32_t keep = 0xFFFFFFFFu;   // bit i = column cb * 32 + i kept (all kept when dropout is off)
+        if (drop_h)
+          keep = drop_keep_mask16(drop_bits16(rs_h, (uint32_t)(cb * 2))) |
+                 (drop_keep_mask16(drop_bits16(rs_h, (uint32_t)(cb * 2 + 1))) << 16);
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
           const float4 b4 = b4p[i >> 2];
-          const uint32_t hb = (i < 16) ? hb0 : hb1;
           const float r0 = fmaxf(fmaf(u[i], h_scale, b4.x), 0.f), r1 = fmaxf(fmaf(u[i + 1], h_scale, b4.y), 0.f);
           const float r2 = fmaxf(fmaf(u[i + 2], h_scale, b4.z), 0.f), r3 = fmaxf(fmaf(u[i + 3], h_scale, b4.w), 0.f);
-          u[i] = (!DROPH || drop_keep(hb, (i & 15))) ? r0 : 0.f;
-          u[i + 1] = (!DROPH || drop_keep(hb, (i & 15) + 1)) ? r1 : 0.f;
-          u[i + 2] = (!DROPH || drop_keep(hb, (i & 15) + 2)) ? r2 : 0.f;
-          u[i + 3] = (!DROPH || drop_keep(hb, (i & 15) + 3)) ? r3 : 0.f;
+          u[i] = (!DROPH || ((keep >> i) & 1u)) ? r0 : 0.f;
+          u[i + 1] = (!DROPH || ((keep >> (i + 1)) & 1u)) ? r1 : 0.f;
+          u[i + 2] = (!DROPH || ((keep >> (i + 2)) & 1u)) ? r2 : 0.f;
+          u[i + 3] = (!DROPH || ((keep >> (i + 3)) & 1u)) ? r3 : 0.f;
         }
         const uint32_t kb_base = h_base + (cb >> 1) * 16384;
         uint32_t mword = 0u;
