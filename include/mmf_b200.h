@@ -61,10 +61,11 @@ int mmf_version(void);
 /* DEBUG ONLY (process-global): device buffer of gridDim.x*16 uint64 that the fused tile kernels fill
  * with clock64() phase stamps; NULL (default) disables it. Not for production use. */
 void mmf_debug_set_timing_buffer(void* device_u64_buffer);
-/* DEBUG ONLY (process-global): device buffer of 16 + 2 * 8192 uint64, zero-filled; CTA 0 of every hot-path kernel
- * appends (kernel id, %globaltimer ns) at its start to the log at [16 ...] (count in [0]) and at its end to the log at
- * [16 + 8192 ...] (count in [1]). ids: 0 fused forward, 1 head step, 2 fused gate+hidden backward, 3 wgrad GEMM,
- * 4 recompute gate, 5 other pair GEMMs. NULL disables. */
+/* DEBUG BUILDS ONLY: a no-op in the release library (no device-global state). In a library compiled with
+ * -DMMF_DEBUG_TIMELINE=1 (tools/step_timeline.py): device buffer of 16 + 5 * 32768 uint64, zero-filled; every CTA of every
+ * hot-path kernel appends one record (kernel id, blockIdx.x, %globaltimer ns at CTA start, after griddepcontrol.wait, at
+ * CTA end) at [16 + 5 i ...], record count in [0]. ids: 0 fused forward, 1 head step, 2 fused head + gate + hidden
+ * backward, 3 wgrad GEMM, 4 recompute gate, 5 other pair GEMMs. NULL disables. */
 void mmf_debug_set_timeline_buffer(void* device_u64_buffer);
 /* DEBUG ONLY (process-global): device buffer of 8 + 4 * 4000 uint64, zero-filled; CTA 0 of every peer all-reduce appends
  * 4 %globaltimer stamps (kernel start, ready handshake done, data phase done, done handshake done); count in [0]. */
@@ -175,7 +176,7 @@ int mmf_amil_fwd_train(const void* x, int64_t N, int64_t ldx, const MmfAmilWeigh
  * gradient accumulation: every gradient of the step is scaled by it).
  * Outputs (valid after mmf_amil_bwd_head): M [L], ml [2], hazards / S [K], Y_hat (or NULL), loss [1] (unscaled),
  * dM [L], hs [16] (dlogits, dM.M), dWk [K,L] / dbk [K] ACCUMULATED (or NULL).
- * Limits: N <= 32768 (256 tile partials merged per CTA); larger bags: mmf_amil_fwd_train + mmf_amil_head_nll_step +
+ * Limits: N <= 65536 (512 per-tile head rows merged per CTA); larger bags: mmf_amil_fwd_train + mmf_amil_head_nll_step +
  * mmf_amil_bwd. */
 typedef struct MmfHeadStep {
   const float* Wk;

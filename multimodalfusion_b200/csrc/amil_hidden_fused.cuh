@@ -47,10 +47,9 @@ struct HiddenFusedArgs {
   const uint32_t* mask;     // [N, L/32] ReLU mask words written by the training forward
   const float* z;           // HEADPROJ: [N, zld] = Wk h_i
   int zld;                  // 4 or 8
-  const float* partials;    // HEADPROJ: the forward's tile partials [n_tiles, L + 2]
+  const float* partials;    // HEADPROJ: the forward's tile partials [n_tiles, L + 2] (pooled embedding M, off the critical path)
   int n_tiles;              //           (<= HEAD_MAX_TILES)
-  float* gparts;            // HEADPROJ: group partials [HEAD_MAX_GROUPS, L + 2] (first-level merge, written here)
-  unsigned int* gflags;     // HEADPROJ: [HEAD_MAX_GROUPS] "group row written" flags, zeroed by the training forward
+  const float* tile_head;   // HEADPROJ: the forward's head rows [n_tiles, 12] = (m_t, l_t, -, -, Wk·acc_t [8])
   HeadTail head;            // HEADPROJ: the step's head, run in this kernel's prologue (amil_head_tail.cuh)
   const float* dA_raw;      // [N] or null
   const float* wc;          // [D]
@@ -101,6 +100,9 @@ struct HiddenFusedCfg {
 #ifndef MMF_HIDDEN_RELAY
 #define MMF_HIDDEN_RELAY 1
 #endif
+#ifndef MMF_HIDDEN_PACKED
+#define MMF_HIDDEN_PACKED 1   // transform in packed f32x2 arithmetic + halving-butterfly column sums (0: the scalar round-1 form)
+#endif
 #ifndef MMF_HEAD_STAMPS
 #define MMF_HEAD_STAMPS 0    // 1: stamps 8-13 time the head prologue instead of the first three slices
 #endif
@@ -116,8 +118,9 @@ amil_hidden_fused_kernel(const __grid_constant__ CUtensorMap tmAG,   // stash fp
                          const __grid_constant__ CUtensorMap tmDG,   // same memory viewed as bf16 dG (store)
                          const __grid_constant__ CUtensorMap tmWab,  // bf16 [KD, L], box [64][64]
                          const __grid_constant__ CUtensorMap tmDU,   // bf16 [N, L], box [128][64] (store)
-                         const HiddenFusedArgs a) {
+                         const HiddenFusedArgs a_in) {
   using C = HiddenFusedCfg<L, D, GATED>;
+  HiddenFusedArgs a = a_in;   // (the pointers to the previous kernel's outputs are re-derived after griddepcontrol.wait)
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_bfull[C::NSB], bar_bempty[C::NSB];
   __shared__ __align__(8) uint64_t bar_afull[C::NSA], bar_aready[C::NSA], bar_aempty[C::NSA];
@@ -125,6 +128,8 @@ amil_hidden_fused_kernel(const __grid_constant__ CUtensorMap tmAG,   // stash fp
   __shared__ __align__(8) uint64_t bar_astore[C::NSA];   // local: one arrive per epilogue warp once a stage holds dG
   __shared__ uint32_t tmem_base_slot;
   __shared__ float s_dbc;
+  __shared__ float s_dl_pub[HEAD_MAX_K];          // HEADPROJ: dlogits for the warp that forms M / dWk (valid once s_dl_flag != 0)
+  __shared__ volatile uint32_t s_dl_flag;
   // per-warp private column-sum slots (no atomics: shared-memory fp32 atomicAdd is a CAS loop): warp (column group
   // ctg = w & 3, row quarter rq = w >> 2) owns, per slice, 3 sums (dwc | dba | dbb) x 16 columns
   __shared__ float s_part[HIDDEN_EW][C::NKP * 48];
@@ -139,7 +144,7 @@ amil_hidden_fused_kernel(const __grid_constant__ CUtensorMap tmAG,   // stash fp
   const int pair_m = blockIdx.x >> 1;
   const long long row0 = (long long)pair_m * 256 + 128 * (int)rank;   // first row of this CTA
 
-  timeline_start(2);
+  Timeline tl = timeline_start(2);
   griddep_launch_dependents();
   if (threadIdx.x == 0) {
     MMF_STAMP(a, 0);
@@ -154,6 +159,7 @@ amil_hidden_fused_kernel(const __grid_constant__ CUtensorMap tmAG,   // stash fp
     fence_barrier_init();
     tma_prefetch_desc(&tmAG); tma_prefetch_desc(&tmWab); tma_prefetch_desc(&tmDG); tma_prefetch_desc(&tmDU);
     s_dbc = 0.f;
+    s_dl_flag = 0u;
   }
   if (warp == 2) {
     tmem_alloc_pair(smem_u32(&tmem_base_slot), L);
@@ -165,6 +171,10 @@ amil_hidden_fused_kernel(const __grid_constant__ CUtensorMap tmAG,   // stash fp
   tc_fence_after();
   const uint32_t tmem = tmem_base_slot;
   griddep_wait();
+  a.H = pdl_fresh(a.H); a.A_raw = pdl_fresh(a.A_raw); a.ml = pdl_fresh(a.ml); a.M = pdl_fresh(a.M); a.dM = pdl_fresh(a.dM);
+  a.mask = pdl_fresh(a.mask); a.z = pdl_fresh(a.z); a.partials = pdl_fresh(a.partials); a.tile_head = pdl_fresh(a.tile_head);
+  a.dA_raw = pdl_fresh(a.dA_raw);
+  timeline_wait_done(tl);
   if (threadIdx.x == 0) MMF_STAMP(a, 1);
 
   if (warp == 0 && lane == 0) {
@@ -241,6 +251,63 @@ amil_hidden_fused_kernel(const __grid_constant__ CUtensorMap tmAG,   // stash fp
     }
     umma_commit_pair_mc(smem_u32(&bar_acc), 3);
     MMF_STAMP(a, 3);
+  } else if (HEADPROJ && warp == 1 && !leader) {
+    // =============================== pooled embedding M and dWk (idle warp of the non-leader CTAs) =====
+    // The step's head no longer needs M (it merges Wk·acc_t per tile); M itself is an output and feeds dWk += dlogits (x) M.
+    // Pair p forms the 8-column groups p, p + pairs, ...: lane = (row group lane >> 3, column lane & 7), tiles strided by 4.
+    const HeadTail& h = a.head;
+    const int pairs = (int)(gridDim.x >> 1);
+    float m = -CUDART_INF_F;
+    for (int t = (int)lane; t < a.n_tiles; t += 32) m = fmaxf(m, __ldg(a.tile_head + (long long)t * 12));
+    m = warp_max(m);
+    float l = 0.f;
+    for (int t = (int)lane; t < a.n_tiles; t += 32) {
+      const float2 mlv = __ldg(reinterpret_cast<const float2*>(a.tile_head + (long long)t * 12));
+      l = fmaf(mlv.y, (mlv.x > -CUDART_INF_F) ? __expf(mlv.x - m) : 0.f, l);
+    }
+    l = warp_sum(l);
+    const float inv_l = 1.f / l;
+    const int c8 = (int)(lane & 7u), rgp = (int)(lane >> 3);
+    bool have_dl = false;
+    float dlv[HEAD_MAX_K];
+    for (int cg = pair_m; cg < L / 8; cg += pairs) {
+      const int col = cg * 8 + c8;
+      float acc = 0.f;
+#pragma unroll 1
+      for (int t0 = rgp; t0 < a.n_tiles; t0 += 32) {
+        float mt[8], v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int t = t0 + 4 * u;
+          const bool ok = t < a.n_tiles;
+          mt[u] = ok ? __ldg(a.partials + (long long)t * (L + 2)) : -CUDART_INF_F;
+          v[u] = ok ? __ldg(a.partials + (long long)t * (L + 2) + 2 + col) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc = fmaf(v[u], (mt[u] > -CUDART_INF_F) ? __expf(mt[u] - m) : 0.f, acc);
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+      const float Mc = acc * inv_l;
+      if (!have_dl) {   // the workers of this CTA publish dlogits after their head; long done by now
+        uint32_t spins = 0;
+        while (s_dl_flag == 0u) {
+          if (++spins > (1u << 26)) { printf("mmf: dlogits never published (block %d)\n", (int)blockIdx.x); __trap(); }
+        }
+        __threadfence_block();
+#pragma unroll
+        for (int j = 0; j < HEAD_MAX_K; ++j) dlv[j] = s_dl_pub[j];
+        have_dl = true;
+      }
+      if (rgp == 0) {
+        h.M[col] = Mc;
+        if (h.dWk) {
+#pragma unroll
+          for (int j = 0; j < HEAD_MAX_K; ++j)
+            if (j < h.K) { float* dw = h.dWk + (long long)j * L + col; *dw = fmaf(dlv[j], Mc, *dw); }
+        }
+      }
+    }
   } else if (warp >= 4) {
     // =============================== epilogue / transform warps ========================
     const uint32_t q = warp & 3;
@@ -286,89 +353,51 @@ amil_hidden_fused_kernel(const __grid_constant__ CUtensorMap tmAG,   // stash fp
       if ((int)e < D) wc_stage = __ldg(a.wc + e);
       static_assert(D <= HIDDEN_ET, "wc staged one element per thread");
       float* s_hacc = vec + C::V_HACC;
-      float* s_hml = vec + C::V_HML;
       float* s_hred = vec + C::V_HRED;
-      MMF_HS(8);
-      // Two-level merge of the tile partials (ONE copy of the code, run once or twice). Every CTA needs the pooled
-      // embedding, but 128 CTAs each reading all 128 partial rows is 34 MB of L2 reads of the same 263 KB (measured:
-      // 21k cycles, r2_phase5.log). So CTA g < n_groups first merges rows [16 g, 16 g + 16) into gparts[g] and raises
-      // gflags[g]; then every CTA merges the <= 16 group rows. CTAs 0..15 are scheduled first and wait for nobody
-      // before raising their flag: no deadlock at any grid size.
-      const int n_groups = (a.n_tiles + HEAD_GROUP - 1) / HEAD_GROUP;
-      const bool two_level = n_groups > 1;
-      PoolAcc pm = {-CUDART_INF_F, 0.f, 0.f, 0.f};
-#pragma unroll 1
-      for (int pass = (two_level && (int)blockIdx.x < n_groups) ? 0 : 1; pass < 2; ++pass) {
-        const float* rows = a.partials;
-        int count = a.n_tiles;
-        if (two_level) {
-          if (pass == 0) {
-            rows += (long long)blockIdx.x * HEAD_GROUP * (L + 2);
-            count = min(HEAD_GROUP, a.n_tiles - (int)blockIdx.x * HEAD_GROUP);
-          } else {
-            if ((int)e < n_groups) {
-              uint32_t v = 0, spins = 0;
-              do {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.gflags + e) : "memory");
-                if (++spins > (1u << 26)) { printf("mmf: head group flag %d never raised (block %d)\n", (int)e, (int)blockIdx.x); __trap(); }
-              } while (v == 0u);
-            }
-            named_bar_sync(1, HIDDEN_ET);
-            MMF_HS(10);
-            rows = a.gparts; count = n_groups;
-          }
-        }
-        // per-thread online merge of the thread's rows, then the row groups meet in shared memory
-        const PoolAcc r = combine_rows_online<L>(rows, count, cp, rg, RG);
-        named_bar_sync(1, HIDDEN_ET);    // (the previous pass's readers are done with the scratch)
-        *reinterpret_cast<float2*>(s_hacc + rg * L + 2 * cp) = make_float2(r.ax, r.ay);
-        if (cp == 0) { s_hml[2 * rg] = r.m; s_hml[2 * rg + 1] = r.l; }
-        named_bar_sync(1, HIDDEN_ET);
-        pm = PoolAcc{-CUDART_INF_F, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int g2 = 0; g2 < RG; ++g2) pm.m = fmaxf(pm.m, s_hml[2 * g2]);
-#pragma unroll
-        for (int g2 = 0; g2 < RG; ++g2) {
-          const float sc = (s_hml[2 * g2] > -CUDART_INF_F) ? __expf(s_hml[2 * g2] - pm.m) : 0.f;
-          const float2 ac = *reinterpret_cast<const float2*>(s_hacc + g2 * L + 2 * cp);
-          pm.l = fmaf(s_hml[2 * g2 + 1], sc, pm.l);
-          pm.ax = fmaf(ac.x, sc, pm.ax);
-          pm.ay = fmaf(ac.y, sc, pm.ay);
-        }
-        if (two_level && pass == 0) {
-          float* grow = a.gparts + (long long)blockIdx.x * (L + 2);
-          if (rg == 0) *reinterpret_cast<float2*>(grow + 2 + 2 * cp) = make_float2(pm.ax, pm.ay);
-          if (e == 0) *reinterpret_cast<float2*>(grow) = make_float2(pm.m, pm.l);
-          named_bar_sync(1, HIDDEN_ET);   // the row's stores are ordered before the release below
-          if (e == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.gflags + blockIdx.x), "r"(1u) : "memory");
-          MMF_HS(9);
-        }
+      // Merge of the forward's per-tile head rows (m_t, l_t, Wk·acc_t): ONE 48-byte row per thread, one L2 round trip,
+      // three CTA barriers. (Round 2a merged the (L + 2)-float partials in two levels with group flags: 14.5k cycles of
+      // the kernel's 45k sat in front of the first MMA, gpurun_out/r2_phase9.log; the pooled embedding itself is only
+      // an output and an operand of dWk: the idle warp of the non-leader CTAs forms it off the critical path.)
+      float4 th0 = make_float4(-CUDART_INF_F, 0.f, 0.f, 0.f), th1 = make_float4(0.f, 0.f, 0.f, 0.f), th2 = th1;
+      if ((int)e < a.n_tiles) {
+        const float4* th = reinterpret_cast<const float4*>(a.tile_head + (long long)e * 12);
+        th0 = __ldg(th); th1 = __ldg(th + 1); th2 = __ldg(th + 2);
       }
-      MMF_HS(11);
-      const float m = pm.m, l = pm.l;
-      const float inv_l = 1.f / l;
-      const float M0 = pm.ax * inv_l, M1 = pm.ay * inv_l;
-      // logits - bk: the threads of row group 0 hold every column pair once
+      static_assert(HEAD_MAX_TILES <= HIDDEN_ET, "one head row per worker thread");
+      MMF_HS(8);
+      {
+        const float wm = warp_max(th0.x);
+        if (lane == 0) s_hred[ew] = wm;
+      }
+      named_bar_sync(1, HIDDEN_ET);
+      float m = s_hred[0];
 #pragma unroll
-      for (int j = 0; j < HEAD_MAX_K; ++j) {
-        if (j < K && rg == 0) {   // (warp-uniform: a warp lies inside one row group)
-          const float d = warp_sum(fmaf(M0, wk[j].x, M1 * wk[j].y));
-          if (lane == 0) s_hred[ew * HEAD_MAX_K + j] = d;
+      for (int w = 1; w < HIDDEN_EW; ++w) m = fmaxf(m, s_hred[w]);
+      MMF_HS(9);
+      {
+        const float wt = (th0.x > -CUDART_INF_F) ? __expf(th0.x - m) : 0.f;
+        float vals[9] = {th0.y * wt, th1.x * wt, th1.y * wt, th1.z * wt, th1.w * wt, th2.x * wt, th2.y * wt, th2.z * wt, th2.w * wt};
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+          const float v = warp_sum(vals[j]);
+          if (lane == 0) s_hacc[ew * 16 + j] = v;
         }
       }
       named_bar_sync(1, HIDDEN_ET);
-      MMF_HS(12);
+      MMF_HS(10);
       if ((int)e < D) vec[C::V_WC + e] = wc_stage;
       // hazards, survival function, nll_surv and its gradient (closed form, amil_head_tail.cuh) by ONE warp, lane j =
-      // class j; the K dlogits and dM·M go to the other warps through shared memory
-      float* s_dl = s_hacc;   // [HEAD_MAX_K] dlogits | [8] dM·M  (the merge scratch is dead: every thread read it before the barrier above)
+      // class j; the K dlogits, dM·M and l go to the other warps through shared memory
+      float* s_dl = s_hacc + 512;   // [HEAD_MAX_K] dlogits | dM·M | l
       if (ew == 0) {
-        constexpr int NW0 = CP / 32;   // the warps of row group 0 are the only ones with partial logits
         const int j = (int)lane;
-        float lgm = 0.f;
-        if (j < K)
+        float tot = 0.f;           // lane 0: l, lane 1 + k: sum_t w_t (Wk·acc_t)_k
+        if (j < 9)
 #pragma unroll
-          for (int w = 0; w < NW0; ++w) lgm += s_hred[w * HEAD_MAX_K + j];
+          for (int w = 0; w < HIDDEN_EW; ++w) tot += s_hacc[w * 16 + j];
+        const float l = __shfl_sync(0xffffffffu, tot, 0);
+        const float zsum = __shfl_sync(0xffffffffu, tot, (j + 1) & 31);
+        const float lgm = (j < K) ? zsum / l : 0.f;     // logit_j - bk_j
         const float lg = lgm + bk_l;
         const float hz = (j < K) ? 1.f / (1.f + expf(-lg)) : 0.f;
         float sv = 1.f - hz;             // inclusive product scan over the classes: S(j)
@@ -394,8 +423,11 @@ amil_hidden_fused_kernel(const __grid_constant__ CUtensorMap tmAG,   // stash fp
           const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
           if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
         }
-        if (j < HEAD_MAX_K) s_dl[j] = dl;
-        if (j == 0) s_dl[HEAD_MAX_K] = dot;
+        if (j < HEAD_MAX_K) { s_dl[j] = dl; s_dl_pub[j] = dl; }
+        if (j == 0) { s_dl[HEAD_MAX_K] = dot; s_dl[HEAD_MAX_K + 1] = l; }
+        __threadfence_block();
+        __syncwarp();
+        if (j == 0) s_dl_flag = 1u;      // the M / dWk warp (warp 1 of the non-leader CTAs) may read s_dl_pub
         if (blockIdx.x == 0) {
           if (j < K) {
             h.hazards[j] = hz; h.S[j] = sv;
@@ -417,6 +449,7 @@ amil_hidden_fused_kernel(const __grid_constant__ CUtensorMap tmAG,   // stash fp
 #pragma unroll
       for (int j = 0; j < HEAD_MAX_K; ++j) dlv[j] = s_dl[j];
       const float dot = s_dl[HEAD_MAX_K];
+      const float inv_l = 1.f / s_dl[HEAD_MAX_K + 1];
       float d0 = 0.f, d1 = 0.f;      // dM = Wk^T dlogits, this thread's two columns
 #pragma unroll
       for (int j = 0; j < HEAD_MAX_K; ++j) {
@@ -424,19 +457,7 @@ amil_hidden_fused_kernel(const __grid_constant__ CUtensorMap tmAG,   // stash fp
         d1 = fmaf(dlv[j], wk[j].y, d1);
       }
       if (rg == 0) *reinterpret_cast<float2*>(vec + C::V_DM + 2 * cp) = make_float2(d0, d1);
-      if (blockIdx.x == 0 && rg == 0) {
-        *reinterpret_cast<float2*>(h.M + 2 * cp) = make_float2(M0, M1);
-        *reinterpret_cast<float2*>(h.dM + 2 * cp) = make_float2(d0, d1);
-        if (h.dWk) {
-#pragma unroll
-          for (int j = 0; j < HEAD_MAX_K; ++j)
-            if (j < K) {   // (scalar accesses: dWk may sit at any 4-byte offset of a flat gradient buffer)
-              float* dw = h.dWk + (long long)j * L + 2 * cp;
-              dw[0] = fmaf(dlv[j], M0, dw[0]);
-              dw[1] = fmaf(dlv[j], M1, dw[1]);
-            }
-        }
-      }
+      if (blockIdx.x == 0 && rg == 0) *reinterpret_cast<float2*>(h.dM + 2 * cp) = make_float2(d0, d1);
       MMF_HS(13);
       // ---- phase A: t_i = dlogits · z_i, p_i from the global (m, l) just formed -----------------------------
       if (e < 128) {
@@ -547,11 +568,76 @@ amil_hidden_fused_kernel(const __grid_constant__ CUtensorMap tmAG,   // stash fp
       const int s = kp % C::NSA;
       const int d0 = kp * 64 + 4 * (int)ct;
       const float4 wc4 = *reinterpret_cast<const float4*>(vec + C::V_WC + d0);
-      const float wcv[4] = {wc4.x, wc4.y, wc4.z, wc4.w};
-      float acc_wc[4] = {}, acc_a[4] = {}, acc_g[4] = {};
       mbar_wait(smem_u32(&bar_afull[s]), (kp / C::NSA) & 1);
       if (!MMF_HEAD_STAMPS && e == 0 && kp < 3) MMF_STAMP(a, 8 + 2 * kp);
       uint8_t* ta = pool_ptr + (a_ring - pool) + s * C::A_STAGE;
+#if MMF_HIDDEN_PACKED
+      // packed f32x2 arithmetic (FMUL2 / FFMA2 / FADD2 process a column pair per instruction): the transform is bound by
+      // the worker warps' instruction issue (~60 scalar instructions per row-step of 4 columns x 2 branches)
+      const float2 wc01 = make_float2(wc4.x, wc4.y), wc23 = make_float2(wc4.z, wc4.w);
+      float2 s_wc[2] = {}, s_a[2] = {}, s_g[2] = {};     // column sums: [pair 0 | pair 1] of dwc, dba, dbb
+#pragma unroll
+      for (int u = 0; u < RPT; ++u) {
+        const uint32_t r = rbase + 8u * u;
+        const uint32_t off = sw128_offset(r, ct >> 1) + (ct & 1u) * 8u;
+        uint2* pa = reinterpret_cast<uint2*>(ta + off);
+        uint2* pg = reinterpret_cast<uint2*>(ta + 16384 + off);
+        const uint2 av = *pa;
+        uint2 gv = make_uint2(0u, 0u);
+        if (GATED) gv = *pg;
+        const float ds = vec[C::V_DS + r];
+        const float2 ds2 = make_float2(ds, ds);
+        float2 ka[2] = {make_float2(attn_scale, attn_scale), make_float2(attn_scale, attn_scale)};
+        float2 kg[2] = {make_float2(GATED && DROP ? attn_scale : 1.f, GATED && DROP ? attn_scale : 1.f),
+                        make_float2(GATED && DROP ? attn_scale : 1.f, GATED && DROP ? attn_scale : 1.f)};
+        if (DROP) {
+          const uint32_t ab = drop_bits16(drop_row_state(a.seed, 1, (uint32_t)(row0 + r)), (uint32_t)(d0 >> 4));
+          const uint32_t gb = drop_bits16(drop_row_state(a.seed, 2, (uint32_t)(row0 + r)), (uint32_t)(d0 >> 4));
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            ka[k].x = drop_keep(ab, (d0 & 15) + 2 * k) ? attn_scale : 0.f;
+            ka[k].y = drop_keep(ab, (d0 & 15) + 2 * k + 1) ? attn_scale : 0.f;
+            if (GATED) {
+              kg[k].x = drop_keep(gb, (d0 & 15) + 2 * k) ? attn_scale : 0.f;
+              kg[k].y = drop_keep(gb, (d0 & 15) + 2 * k + 1) ? attn_scale : 0.f;
+            }
+          }
+        }
+        const float2 aa[2] = {__half22float2(*reinterpret_cast<const __half2*>(&av.x)),
+                              __half22float2(*reinterpret_cast<const __half2*>(&av.y))};
+        float2 gg[2] = {make_float2(1.f, 1.f), make_float2(1.f, 1.f)};
+        if (GATED) {
+          gg[0] = __half22float2(*reinterpret_cast<const __half2*>(&gv.x));
+          gg[1] = __half22float2(*reinterpret_cast<const __half2*>(&gv.y));
+        }
+        const float2 dsw[2] = {__fmul2_rn(ds2, wc01), __fmul2_rn(ds2, wc23)};
+        uint32_t oa[2], og[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          // same factoring as the scalar form: q = ds wc gd, dG_a = ka (q - (q a) a), dG_g = (q ad) - (q ad) g
+          const float2 gd = (GATED && DROP) ? __fmul2_rn(gg[k], kg[k]) : gg[k];
+          const float2 ad = DROP ? __fmul2_rn(aa[k], ka[k]) : aa[k];
+          s_wc[k] = __ffma2_rn(ds2, __fmul2_rn(ad, gd), s_wc[k]);
+          const float2 q = __fmul2_rn(dsw[k], gd);
+          const float2 qa = __fmul2_rn(q, aa[k]);
+          const float2 qad = DROP ? __fmul2_rn(q, ad) : qa;
+          float2 da = __ffma2_rn(make_float2(-qa.x, -qa.y), aa[k], q);
+          if (DROP) da = __fmul2_rn(da, ka[k]);
+          const float2 dg = GATED ? __ffma2_rn(make_float2(-qad.x, -qad.y), gg[k], qad) : make_float2(0.f, 0.f);
+          s_a[k] = __fadd2_rn(s_a[k], da);
+          s_g[k] = __fadd2_rn(s_g[k], dg);
+          oa[k] = pack_bf16x2(da.x, da.y);
+          og[k] = pack_bf16x2(dg.x, dg.y);
+        }
+        *pa = make_uint2(oa[0], oa[1]);
+        if (GATED) *pg = make_uint2(og[0], og[1]);
+      }
+      float acc_wc[4] = {s_wc[0].x, s_wc[0].y, s_wc[1].x, s_wc[1].y};
+      float acc_a[4] = {s_a[0].x, s_a[0].y, s_a[1].x, s_a[1].y};
+      float acc_g[4] = {s_g[0].x, s_g[0].y, s_g[1].x, s_g[1].y};
+#else
+      const float wcv[4] = {wc4.x, wc4.y, wc4.z, wc4.w};
+      float acc_wc[4] = {}, acc_a[4] = {}, acc_g[4] = {};
 #pragma unroll
       for (int u = 0; u < RPT; ++u) {
         const uint32_t r = rbase + 8u * u;
@@ -596,6 +682,7 @@ amil_hidden_fused_kernel(const __grid_constant__ CUtensorMap tmAG,   // stash fp
         *pa = make_uint2(pack_bf16x2(da[0], da[1]), pack_bf16x2(da[2], da[3]));
         if (GATED) *pg = make_uint2(pack_bf16x2(dg[0], dg[1]), pack_bf16x2(dg[2], dg[3]));
       }
+#endif
       fence_proxy_async_smem();
       __syncwarp();
       if (!MMF_HEAD_STAMPS && e == 0 && kp < 3) MMF_STAMP(a, 9 + 2 * kp);
@@ -603,7 +690,44 @@ amil_hidden_fused_kernel(const __grid_constant__ CUtensorMap tmAG,   // stash fp
         if (!MMF_HIDDEN_RELAY) mbar_arrive_cluster(a_ready_leader + s * 8u);   // bar_aready[s] of the leader
         mbar_arrive(smem_u32(&bar_astore[s]));   // the store thread (warp 2) relays to the MMA and writes the stage out as dG
       }
-      // column sums of this slice: reduce over the warp's 8 row lanes, then 4 row quarters meet in shared memory
+      // column sums of this slice over the warp's 8 row lanes (lane bits 2-4), then the 4 row quarters meet in shared memory
+#if MMF_HIDDEN_PACKED
+      // halving butterfly: 12 sums per thread (dwc | dba | dbb x 4 columns). At each of the 3 levels a lane keeps half of
+      // its values and hands the other half to its partner: 6 + 3 + 2 shuffles instead of 3 x 12. Afterwards the row
+      // lane rl = lane >> 2 holds: level 1 (bit 4) split wc/a/g halves ... the owner lane of sum j is given by owner_of().
+      {
+        float v12[12] = {acc_wc[0], acc_wc[1], acc_wc[2], acc_wc[3], acc_a[0], acc_a[1], acc_a[2], acc_a[3],
+                         acc_g[0], acc_g[1], acc_g[2], acc_g[3]};
+        const bool up4 = (lane & 16u) != 0u, up3 = (lane & 8u) != 0u, up2 = (lane & 4u) != 0u;
+        float v6[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {          // level 1 (xor 16): lower half keeps 0..5, upper half keeps 6..11
+          const float send = up4 ? v12[j] : v12[j + 6];
+          const float got = __shfl_xor_sync(0xffffffffu, send, 16);
+          v6[j] = (up4 ? v12[j + 6] : v12[j]) + got;
+        }
+        float v3[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {          // level 2 (xor 8): keeps 0..2 / 3..5 of its six
+          const float send = up3 ? v6[j] : v6[j + 3];
+          const float got = __shfl_xor_sync(0xffffffffu, send, 8);
+          v3[j] = (up3 ? v6[j + 3] : v6[j]) + got;
+        }
+        // level 3 (xor 4): three values, both lanes end with all three sums
+#pragma unroll
+        for (int j = 0; j < 3; ++j) v3[j] += __shfl_xor_sync(0xffffffffu, v3[j], 4);
+        // lane (up4, up3, *) holds sums 6 up4 + 3 up3 + {0,1,2}; one writer per (up4, up3): the lanes with bit 2 clear
+        if (!up2) {
+          const int base = 6 * (int)up4 + 3 * (int)up3;
+          const uint32_t cq = lane & 3u;       // column quad within the warp's 16 columns
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const int idx = base + j;          // 0..11 = which * 4 + k
+            s_part[ew][kp * 48 + (idx >> 2) * 16 + cq * 4 + (idx & 3)] = v3[j];
+          }
+        }
+      }
+#else
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
 #pragma unroll
@@ -619,6 +743,7 @@ amil_hidden_fused_kernel(const __grid_constant__ CUtensorMap tmAG,   // stash fp
         *reinterpret_cast<float4*>(slot + 16) = make_float4(acc_a[0], acc_a[1], acc_a[2], acc_a[3]);
         if (GATED) *reinterpret_cast<float4*>(slot + 32) = make_float4(acc_g[0], acc_g[1], acc_g[2], acc_g[3]);
       }
+#endif
     }
     if (e == 0) MMF_STAMP(a, 5);
 
@@ -706,7 +831,7 @@ amil_hidden_fused_kernel(const __grid_constant__ CUtensorMap tmAG,   // stash fp
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
-  timeline_end(2);
+  timeline_end(2, tl);
   if (warp == 2) tmem_dealloc_pair(tmem, L);
 }
 

@@ -52,7 +52,10 @@ struct AmilArgs {
   uint32_t* mask_out; // fwd train (optional): ReLU mask words [N, L/32], bit j of word w = (h[row][32 w + j] > 0)
   float* z_out;       // fwd train (optional): z_i = Wk h_i as fp32 [N, zld] from the N = 16 side MMA (needs tmWk)
   int zld;            // 4 or 8
-  unsigned int* gflags; // fwd train (optional): [HEAD_MAX_GROUPS] flags of the backward's two-level head merge, cleared here
+  float* tile_head;   // fwd train (optional): [tiles, 12] per-tile head rows (m_t, l_t, -, -, Wk·acc_t [8]): the backward's head
+                      // merges these 48-byte rows instead of the (L + 2)-float partials (needs head_wk / head_k)
+  const float* head_wk;  // classifier.weight fp32 [head_k, L]
+  int head_k;
   int flags;
   int kb1;            // 64-wide k-blocks of GEMM1 (0 = 16: x is [N,1024]; 48: [N,3072] = [x_hi | x_lo | x_hi], MMF_PRECISE_FC)
   unsigned long long seed;

@@ -23,6 +23,7 @@
 //                 remote arrives go through mapa + mbarrier.arrive.release.cluster
 #pragma once
 #include "amil_tile.cuh"
+#include "amil_head_tail.cuh"
 
 namespace mmf {
 
@@ -39,18 +40,33 @@ struct Amil2Cfg {
   static constexpr uint32_t STAGE2 = (CHN / 2) * 128u;       // this CTA's half of the Wab chunk
   static constexpr uint32_t POOL = 208u * 1024u;
   static constexpr uint32_t VEC_BYTES = 16u * 1024u;
-  static constexpr uint32_t XPOSE_BYTES = 8u * 2048u;   // per-epilogue-warp 32 x 32 fp16 transpose scratch (stash stores)
+#ifndef MMF_STASH_TMA
+#define MMF_STASH_TMA 1
+#endif
+  // per-epilogue-warp staging of the activation stash: MMF_STASH_TMA = 1: one 32 x 32 fp16 block per branch (2 x 2 KB),
+  // written out by TMA stores (64-byte swizzle); = 0: one 2 KB transpose scratch read back for st.global.v4
+  static constexpr uint32_t XPOSE_WARP = MMF_STASH_TMA ? 4096u : 2048u;
+  static constexpr uint32_t XPOSE_BYTES = 8u * XPOSE_WARP;
   static constexpr int NS1 = (POOL / STAGE1) < 6 ? (POOL / STAGE1) : 6;
-  static constexpr int NS2 = ((POOL - H_BYTES - XPOSE_BYTES) / STAGE2) < 8 ? ((POOL - H_BYTES - XPOSE_BYTES) / STAGE2) : 8;
+  // GEMM2 ring: NS2 stages exist (barriers, addresses); the training forward uses only the first NS2_STASH of them — its
+  // stash staging overlays the tail of the ring (run-time depth: one kernel instantiation serves both forms)
+  static constexpr int NS2 = ((POOL - H_BYTES) / STAGE2) < 8 ? ((POOL - H_BYTES) / STAGE2) : 8;
+  static constexpr int NS2_STASH = ((POOL - H_BYTES - XPOSE_BYTES) / STAGE2) < 8 ? ((POOL - H_BYTES - XPOSE_BYTES) / STAGE2) : 8;
   static constexpr uint32_t SMEM_BYTES = POOL + VEC_BYTES + 1024u;
   static constexpr int NCOLS = GATED ? 3 * D : 2 * D;
   // float offsets inside the vector region
   static constexpr int V_B1 = 0, V_BAB = L, V_WC = L + KD, V_DM = L + KD + D, V_S = V_DM + L,
                        V_P = V_S + 256, V_RED = V_P + 128, V_END = V_RED + 16;
   static_assert(V_END * 4 <= (int)VEC_BYTES, "vector region overflow");
-  static_assert(NS1 >= 2 && NS2 >= 2, "ring too shallow");
+  static_assert(NS1 >= 2 && NS2_STASH >= 2, "ring too shallow");
 };
 
+// MMF_TILE2_CHUNK_STAMPS = 1 (debug build, tools/phase_chunks.py): stamps 2 / 3 / 4 = "GEMM2 chunk c accumulators seen" and
+// 5 / 9 / 15 = "chunk c gate epilogue done" (epilogue thread 0) replace the producer / first-stage / vectors-staged stamps
+#ifndef MMF_TILE2_CHUNK_STAMPS
+#define MMF_TILE2_CHUNK_STAMPS 0
+#endif
+#define MMF_STAMP_N(a, i) do { if (!MMF_TILE2_CHUNK_STAMPS) MMF_STAMP(a, i); } while (0)
 constexpr int AMIL2_THREADS = 384;
 constexpr uint32_t AMIL2_EPI_THREADS = 256;
 
@@ -65,8 +81,10 @@ template <int L, int D, bool GATED, int MODE, bool DROPH, bool DROPA>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AMIL2_THREADS, 1)
 amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                   const __grid_constant__ CUtensorMap tmWab, const __grid_constant__ CUtensorMap tmH,
-                  const __grid_constant__ CUtensorMap tmWk, const AmilArgs a) {
+                  const __grid_constant__ CUtensorMap tmWk, const __grid_constant__ CUtensorMap tmAGs,
+                  const AmilArgs a_in) {
   using C = Amil2Cfg<L, D, GATED>;
+  AmilArgs a = a_in;   // (pointers to data the previous kernels wrote are re-derived after griddepcontrol.wait)
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full1[C::NS1], bar_empty1[C::NS1];
   __shared__ __align__(8) uint64_t bar_full2[C::NS2], bar_empty2[C::NS2];
@@ -82,8 +100,9 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   float* vec = reinterpret_cast<float*>(smem_raw + (pool - smem_u32(smem_raw)) + C::POOL);
   const int tile = blockIdx.x;
   const long long row0 = (long long)tile * 128;
+  const int ns2 = (MODE == AMIL_FWD && a.AG != nullptr) ? C::NS2_STASH : C::NS2;   // GEMM2 ring depth of this launch
 
-  timeline_start(MODE == AMIL_FWD ? 0 : 4);
+  Timeline tl = timeline_start(MODE == AMIL_FWD ? 0 : 4);
   griddep_launch_dependents();   // PDL: the next kernel's prologue may overlap this kernel's tail
   if (threadIdx.x == 0) {
     MMF_STAMP(a, 0);
@@ -108,6 +127,12 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   tc_fence_after();
   const uint32_t tmem = tmem_base_slot;
   griddep_wait();                // PDL: everything above overlapped the previous kernel; its outputs are visible now
+  a.b1 = pdl_fresh(a.b1); a.bab = pdl_fresh(a.bab); a.wc = pdl_fresh(a.wc); a.bc = pdl_fresh(a.bc);   // (optimizer step)
+  a.head_wk = pdl_fresh(a.head_wk); a.tile_valid = pdl_fresh(a.tile_valid);
+  if (MODE == AMIL_BWD_GATE) {
+    a.A_raw = pdl_fresh(a.A_raw); a.ml = pdl_fresh(a.ml); a.M = pdl_fresh(a.M); a.dM = pdl_fresh(a.dM); a.dA_raw = pdl_fresh(a.dA_raw);
+  }
+  timeline_wait_done(tl);
   if (threadIdx.x == 0) MMF_STAMP(a, 1);
 
   if (warp == 0 && lane == 0) {
@@ -130,26 +155,24 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       for (int j = 0; j < C::NH1; ++j)
         tma_load_2d_pair(dst + 16384 + j * 16384, &tmW1, full, kb * 64, j * 256 + 128 * (int)rank);
     }
-    MMF_STAMP(a, 2);
+    MMF_STAMP_N(a, 2);
     mbar_wait(smem_u32(&bar_acc1), 0);   // GEMM1 retired: its ring (overlaying H / ring2) is free
-    MMF_STAMP(a, 3);
+    MMF_STAMP_N(a, 3);
+    int s = 0;
+    uint32_t ph = 0;
     for (int c = 0; c < C::NCH; ++c) {
       for (int kb = 0; kb < C::KB2; ++kb) {
-        const int it = c * C::KB2 + kb;
-        const int s = it % C::NS2;
-        const uint32_t ph = (it / C::NS2) & 1;
         mbar_wait(smem_u32(&bar_empty2[s]), ph ^ 1);
         const uint32_t full = smem_u32(&bar_full2[s]);
         if (leader) mbar_arrive_expect_tx(full, 2 * C::STAGE2);
         tma_load_2d_pair(ring2 + s * C::STAGE2, &tmWab, full, kb * 64, c * C::CHN + (C::CHN / 2) * (int)rank);
+        if (++s == ns2) { s = 0; ph ^= 1u; }
       }
     }
     if (MODE == AMIL_FWD && a.z_out != nullptr) {
       // side product z = Wk h (head-projected backward): this CTA's 8 rows of the bf16 hi / lo split of the
       // classifier, all KB2 k-blocks in ONE ring stage (8 rows x 128 B = one swizzle atom per k-block)
-      constexpr int it = C::NCH * C::KB2;
-      constexpr int s = it % C::NS2;
-      mbar_wait(smem_u32(&bar_empty2[s]), ((it / C::NS2) & 1) ^ 1);
+      mbar_wait(smem_u32(&bar_empty2[s]), ph ^ 1);
       const uint32_t full = smem_u32(&bar_full2[s]);
       if (leader) mbar_arrive_expect_tx(full, 2 * C::KB2 * 1024);
       for (int kb = 0; kb < C::KB2; ++kb)
@@ -165,7 +188,7 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const uint32_t ph = (kb / C::NS1) & 1;
       mbar_wait(smem_u32(&bar_full1[s]), ph);
       tc_fence_after();
-      if (kb == 0) MMF_STAMP(a, 5);
+      if (kb == 0) MMF_STAMP_N(a, 5);
       const uint32_t xs = pool + s * C::STAGE1;
       const uint32_t ws = xs + 16384;
 #pragma unroll
@@ -184,14 +207,13 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     mbar_wait_cluster(smem_u32(&bar_h), 0);   // both CTAs' H tiles written, GEMM1 TMEM columns drained
     tc_fence_after();
     MMF_STAMP(a, 7);
+    int s = 0;
+    uint32_t ph = 0;
     for (int c = 0; c < C::NCH; ++c) {
       const int buf = c & 1;
       mbar_wait_cluster(smem_u32(&bar_acc2_empty[buf]), ((c >> 1) & 1) ^ 1);
       tc_fence_after();
       for (int kb = 0; kb < C::KB2; ++kb) {
-        const int it = c * C::KB2 + kb;
-        const int s = it % C::NS2;
-        const uint32_t ph = (it / C::NS2) & 1;
         mbar_wait(smem_u32(&bar_full2[s]), ph);
         tc_fence_after();
         const uint32_t hs = h_base + kb * 16384;
@@ -201,15 +223,16 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           umma_bf16_ss_pair(tmem + buf * C::CHN, umma_desc_sw128(hs + k * 32, 16, 1024),
                             umma_desc_sw128(bs + k * 32, 16, 1024), idesc2, (kb | k) != 0);
         umma_commit_pair_mc(smem_u32(&bar_empty2[s]), 3);
+        if (++s == ns2) { s = 0; ph ^= 1u; }
       }
       umma_commit_pair_mc(smem_u32(&bar_acc2_full[buf]), 3);
     }
     if (MODE == AMIL_FWD && a.z_out != nullptr) {
       // z[256, 16] = H_pair · [Wk_hi | Wk_lo]^T into the chunk buffer the last GEMM2 chunk does not use
       constexpr uint32_t idescz = umma_idesc_bf16(256, 16, 0, 0);
-      constexpr int c = C::NCH, buf = c & 1, it = C::NCH * C::KB2, s = it % C::NS2;
+      constexpr int c = C::NCH, buf = c & 1;
       mbar_wait_cluster(smem_u32(&bar_acc2_empty[buf]), ((c >> 1) & 1) ^ 1);
-      mbar_wait(smem_u32(&bar_full2[s]), (it / C::NS2) & 1);
+      mbar_wait(smem_u32(&bar_full2[s]), ph);
       tc_fence_after();
       for (int kb = 0; kb < C::KB2; ++kb) {
 #pragma unroll
@@ -221,6 +244,21 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       umma_commit_pair_mc(smem_u32(&bar_acc2_full[buf]), 3);
     }
     MMF_STAMP(a, 8);
+  } else if (MODE == AMIL_FWD && warp == 3 && lane == 0) {
+    // =============================== H stash store (training forward, each CTA) =========
+    // Issued in NCH batches, batch c once GEMM2 chunk c has retired: the 128 KB read of the H tile then shares the
+    // shared-memory / TMA pipes with chunks 1.. (hidden behind the gate epilogue) and the pooling tail. Issued right after
+    // EPI1 (round 1) it slowed the EXPOSED first chunk from 4.9k to 8.0k cycles; issued in one piece after the last chunk it
+    // held up that chunk's stash stores instead (gate epilogue 5.3k -> 7.7k cycles, gpurun_out/r2c / r2d_chunks.log).
+    if (a.store_h) {
+      for (int c = 0; c < C::NCH; ++c) {
+        mbar_wait(smem_u32(&bar_acc2_full[c & 1]), (c >> 1) & 1);   // (=> bar_h completed: both CTAs' H tiles are written and fenced)
+        for (int kb = c * C::KB2 / C::NCH; kb < (c + 1) * C::KB2 / C::NCH; ++kb)
+          tma_store_2d(&tmH, h_base + kb * 16384, kb * 64, (int)row0);
+        tma_store_commit();
+      }
+      tma_store_wait_all();
+    }
   } else if (warp >= 4) {
     // =============================== epilogue warps (both CTAs) ========================
     const uint32_t q = warp & 3;
@@ -253,8 +291,7 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     for (int i = e; i < C::KD; i += AMIL2_EPI_THREADS) vec[C::V_BAB + i] = __ldg(a.bab + i) * ((GATED && i >= D) ? 0.5f : 1.0f);
     for (int i = e; i < D; i += AMIL2_EPI_THREADS) vec[C::V_WC + i] = __ldg(a.wc + i);
     named_bar_sync(4, AMIL2_EPI_THREADS);
-    if (e == 0) MMF_STAMP(a, 9);
-    if (MODE == AMIL_FWD && a.gflags != nullptr && blockIdx.x == 0 && e < (uint32_t)HEAD_MAX_GROUPS) a.gflags[e] = 0u;
+    if (e == 0) MMF_STAMP_N(a, 9);
     if (MODE == AMIL_FWD && a.zero_ptr != nullptr) {
       // fused zero_grad: the epilogue warps have nothing to do until GEMM1 retires (~16k cycles); they clear the
       // step's gradient accumulators (a separate fill kernel costs ~8 us per step with its two kernel boundaries)
@@ -265,12 +302,22 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     }
 
     // ---------------- EPI1: H = dropout(relu(U + b1)) -> swizzled smem -----------------
+    constexpr int PIECES1 = L / 64;  // 32-column pieces per half
+    const int cb0 = half * PIECES1;
+    // Dropout(0.25) on h: the keep bits of this thread's row and column half (one 32-bit word per piece) are hashed
+    // NOW, while GEMM1 runs and the epilogue warps are idle — inside EPI1 the two hashes per piece were a third of its
+    // instructions (EPI1: 5.6k cycles without dropout, 8.6k with, gpurun_out/r2c_chunks.log). The words are consumed
+    // in order through a register shift (the piece loop is not unrolled).
+    uint32_t keepw[PIECES1];
+#pragma unroll
+    for (int ii = 0; ii < PIECES1; ++ii)
+      keepw[ii] = DROPH ? (drop_keep_mask16(drop_bits16(rs_h, (uint32_t)((cb0 + ii) * 2))) |
+                           (drop_keep_mask16(drop_bits16(rs_h, (uint32_t)((cb0 + ii) * 2 + 1))) << 16))
+                        : 0xFFFFFFFFu;
     mbar_wait(smem_u32(&bar_acc1), 0);
     tc_fence_after();
     if (e == 0) MMF_STAMP(a, 10);
     float t_i = 0.f;
-    constexpr int PIECES1 = L / 64;  // 32-column pieces per half
-    const int cb0 = half * PIECES1;
     float v[2][32];
     tmem_ld32(tq + cb0 * 32, v[0]);
     // two pieces per iteration so the TMEM double-buffer indices stay static; NOT fully unrolled: the
@@ -286,10 +333,7 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         if (ii + 1 < PIECES1) tmem_ld32(tq + (cb + 1) * 32, v[par ^ 1]);
         float (&u)[32] = v[par];
         const float4* b4p = reinterpret_cast<const float4*>(vec + C::V_B1 + cb * 32);
-        uint32_t keep = 0xFFFFFFFFu;   // bit i = column cb * 32 + i kept (all kept when dropout is off)
-        if (drop_h)
-          keep = drop_keep_mask16(drop_bits16(rs_h, (uint32_t)(cb * 2))) |
-                 (drop_keep_mask16(drop_bits16(rs_h, (uint32_t)(cb * 2 + 1))) << 16);
+        const uint32_t keep = keepw[par];   // bit i = column cb * 32 + i kept (all ones when dropout is off)
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
           const float4 b4 = b4p[i >> 2];
@@ -325,6 +369,8 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         // of the hidden-gradient kernel reads 64 B per row instead of re-deriving the bits from a re-read of H)
         if (MODE == AMIL_FWD && a.mask_out != nullptr && row_ok) a.mask_out[row * (L / 32) + cb] = mword;
       }
+#pragma unroll
+      for (int j = 0; j + 2 < PIECES1; ++j) keepw[j] = keepw[j + 2];
     }
     fence_proxy_async_smem();
     tc_fence_before();
@@ -333,7 +379,7 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     if (e == 0) MMF_STAMP(a, 11);
 
     if (MODE == AMIL_BWD_GATE) sS[half * 128 + r] = t_i;
-    if (MODE == AMIL_BWD_GATE || a.store_h) {
+    if (MODE == AMIL_BWD_GATE) {
       named_bar_sync(1, AMIL2_EPI_THREADS);   // all H writes of this CTA fenced (+ t_i halves visible)
       if (e == 0) {
         for (int kb = 0; kb < C::KB2; ++kb) tma_store_2d(&tmH, h_base + kb * 16384, kb * 64, (int)row0);
@@ -363,6 +409,7 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const int buf = c & 1;
       mbar_wait(smem_u32(&bar_acc2_full[buf]), (c >> 1) & 1);
       tc_fence_after();
+      if (MMF_TILE2_CHUNK_STAMPS && e == 0 && c < 3) MMF_STAMP(a, 2 + c);
 #pragma unroll 1
       for (int pp = 0; pp < 2; ++pp) {
         const int pc = half * 2 + pp;
@@ -412,7 +459,33 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           // training forward: stash the pre-dropout branch activations (fp16) so that the backward needs
           // neither GEMM again (amil_hidden_fused.cuh consumes them in place). Each thread owns one ROW of the
           // warp's 32 x 32 block; storing that directly is 32 scattered 16-byte writes per instruction
-          // (+10 us per 16k bag). The block is transposed through a 2 KB per-warp scratch so that every
+          // (+10 us per 16k bag).
+#if MMF_STASH_TMA
+          // The block of each branch is staged in shared memory (row = 64 bytes, 16-byte chunk index XOR (row >> 1) & 3
+          // = the TMA's 64-byte swizzle: conflict-free v4 writes) and leaves through ONE TMA store per branch: no read-back,
+          // no st.global in the epilogue warps, and the cluster-scope release arrive that ends the chunk has no generic-proxy
+          // global stores to drain. The staging is reused one piece (~500 instructions) later: the read-completion wait is free.
+          const uint32_t scratch = pool + C::POOL - C::XPOSE_BYTES + (warp - 4) * C::XPOSE_WARP;
+          if (lane == 0) tma_store_wait_read();
+          __syncwarp();
+#pragma unroll
+          for (int br = 0; br < (GATED ? 2 : 1); ++br) {
+            const float (&src)[32] = br == 0 ? va : vg;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              st_shared_v4(scratch + br * 2048u + lane * 64u + ((j ^ ((lane >> 1) & 3u)) << 4),
+                           pack_f16x2(src[8 * j], src[8 * j + 1]), pack_f16x2(src[8 * j + 2], src[8 * j + 3]),
+                           pack_f16x2(src[8 * j + 4], src[8 * j + 5]), pack_f16x2(src[8 * j + 6], src[8 * j + 7]));
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmAGs, scratch, d0, (int)(row0 + q * 32));
+            if (GATED) tma_store_2d(&tmAGs, scratch + 2048u, D + d0, (int)(row0 + q * 32));
+            tma_store_commit();
+          }
+#else
+          // The block is transposed through a 2 KB per-warp scratch so that every
           // st.global.v4 covers 8 rows x 64 contiguous bytes (full 32-byte sectors).
           const uint32_t scratch = pool + C::POOL - C::XPOSE_BYTES + (warp - 4) * 2048u;
           const uint32_t orow = lane >> 2, ochunk = lane & 3u;
@@ -435,6 +508,7 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 *reinterpret_cast<uint4*>(a.AG + grow * a.ldag + br * D + d0 + ochunk * 8) = v4;
             }
           }
+#endif
         }
         if (MODE == AMIL_BWD_GATE) {
           if (row_ok) {
@@ -465,6 +539,7 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&bar_acc2_empty[buf]), 0));
+      if (MMF_TILE2_CHUNK_STAMPS && e == 0 && c < 3) MMF_STAMP(a, c == 0 ? 5 : c == 1 ? 9 : 15);
     }
 
     if (MODE == AMIL_FWD && a.z_out != nullptr) {
@@ -492,6 +567,14 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       if (e == 0) tma_store_wait_all();
     } else {
       // ---------------- FWD: scores out + tile softmax partial ------------------------
+      // head row of the tile (training step): this thread's two classifier columns, requested before the softmax barriers
+      float2 hwk[HEAD_MAX_K];
+      const bool head_row = a.tile_head != nullptr;
+#pragma unroll
+      for (int k = 0; k < HEAD_MAX_K; ++k)
+        hwk[k] = (head_row && k < a.head_k && e < (uint32_t)L / 2)
+                     ? __ldg(reinterpret_cast<const float2*>(a.head_wk + (long long)k * L + 2 * e)) : make_float2(0.f, 0.f);
+      float m_keep = 0.f, l_keep = 0.f;
       sS[half * 128 + r] = s_acc;
       named_bar_sync(2, AMIL2_EPI_THREADS);
       const bool tile_ok = valid > 0 || (a.tile_valid != nullptr && row0 < a.N);   // (empty varlen tiles still write m = -inf)
@@ -507,10 +590,11 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const float wsum = warp_sum(p);
         if (lane == 0) sRed[4 + q] = wsum;
         named_bar_sync(3, 128);
+        m_keep = m_t; l_keep = sRed[4] + sRed[5] + sRed[6] + sRed[7];
         if (r == 0 && tile_ok) {
           float* prow = a.partials + (long long)tile * (L + 2);
           prow[0] = m_t;
-          prow[1] = sRed[4] + sRed[5] + sRed[6] + sRed[7];
+          prow[1] = l_keep;
         }
       }
       named_bar_sync(2, AMIL2_EPI_THREADS);   // sP complete
@@ -520,19 +604,52 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           const uint32_t col = 2u * cp;
           const uint32_t kb = col >> 6, chunk = (col & 63u) >> 3, inb = (col & 7u) * 2u;
           const uint32_t blk = h_base + kb * 16384u;
-          float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll 8
-          for (uint32_t rr = 0; rr < 128; ++rr) {
-            const float2 hf = unpack_bf16x2(ld_shared_b32(blk + sw128_offset(rr, chunk) + inb));
-            const float pr = sP[rr];
-            acc0 = fmaf(pr, hf.x, acc0);
-            acc1 = fmaf(pr, hf.y, acc1);
+          // 8 rows per step: two 16-byte loads of p (broadcast), eight 4-byte loads of the bf16 pairs (row r of the
+          // 128B-swizzled block: r * 128 + ((chunk ^ (r & 7)) << 4)), two independent accumulator pairs
+          float2 acc_e = make_float2(0.f, 0.f), acc_o = make_float2(0.f, 0.f);
+#pragma unroll 2
+          for (uint32_t r8 = 0; r8 < 128; r8 += 8) {
+            const float4 pa = *reinterpret_cast<const float4*>(sP + r8), pb = *reinterpret_cast<const float4*>(sP + r8 + 4);
+            const float pv[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+            uint32_t hw[8];
+#pragma unroll
+            for (uint32_t j = 0; j < 8; ++j) hw[j] = ld_shared_b32(blk + (r8 + j) * 128u + ((chunk ^ j) << 4) + inb);
+#pragma unroll
+            for (uint32_t j = 0; j < 8; j += 2) {
+              const float2 he = unpack_bf16x2(hw[j]), ho = unpack_bf16x2(hw[j + 1]);
+              acc_e.x = fmaf(pv[j], he.x, acc_e.x); acc_e.y = fmaf(pv[j], he.y, acc_e.y);
+              acc_o.x = fmaf(pv[j + 1], ho.x, acc_o.x); acc_o.y = fmaf(pv[j + 1], ho.y, acc_o.y);
+            }
           }
-          prow[2 + col] = acc0;
-          prow[2 + col + 1] = acc1;
+          const float c0 = acc_e.x + acc_o.x, c1 = acc_e.y + acc_o.y;
+          prow[2 + col] = c0;
+          prow[2 + col + 1] = c1;
+#pragma unroll
+          for (int k = 0; k < HEAD_MAX_K; ++k) hwk[k].x = fmaf(hwk[k].x, c0, hwk[k].y * c1);   // (L / 2 <= 256: one pass)
         }
       }
-      if (a.store_h && e == 0) tma_store_wait_all();
+      static_assert(L / 2 <= (int)AMIL2_EPI_THREADS, "one column pair per epilogue thread");
+      if (head_row) {
+        // Wk · acc_t: the head of the backward then merges 12 floats per tile instead of L + 2
+        // (logits - bk = sum_t e^{m_t - m} (Wk·acc_t) / l, exact fp32 classifier weights)
+        float* sZ = sS;   // (the score halves are dead)
+#pragma unroll
+        for (int k = 0; k < HEAD_MAX_K; ++k) {
+          const float v = warp_sum((tile_ok && e < (uint32_t)L / 2) ? hwk[k].x : 0.f);
+          if (lane == 0) sZ[(warp - 4) * HEAD_MAX_K + k] = v;
+        }
+        named_bar_sync(2, AMIL2_EPI_THREADS);
+        if (tile_ok && e < 12u) {
+          float v = 0.f;
+          if (e >= 4u) {
+#pragma unroll
+            for (int w = 0; w < 8; ++w) v += sZ[w * HEAD_MAX_K + (e - 4u)];
+          } else if (e == 0u) v = m_keep;
+          else if (e == 1u) v = l_keep;
+          a.tile_head[(long long)tile * 12 + e] = v;
+        }
+      }
+      if (MMF_STASH_TMA && a.AG != nullptr && lane == 0) tma_store_wait_all();   // this warp's stash stores
     }
     if (e == 0) MMF_STAMP(a, 13);
     tc_fence_before();
@@ -540,7 +657,7 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   __syncthreads();
   cluster_sync_all();   // the peer may still be reading this CTA's smem / TMEM through the pair MMA
   if (threadIdx.x == 0) MMF_STAMP(a, 14);
-  timeline_end(MODE == AMIL_FWD ? 0 : 4);
+  timeline_end(MODE == AMIL_FWD ? 0 : 4, tl);
   if (warp == 2) tmem_dealloc_pair(tmem, 512);
 }
 

@@ -39,10 +39,17 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // debug-only global (the one exception to "no global state"): when set, the tensor-core kernels write
 // clock64 phase stamps [gridDim.x][16]; see tools/phase_timing.py
 unsigned long long* g_timing_buffer = nullptr;
+// MMF_STAMP_KERNEL=<id> (debug, tools/phase_instep.py): only the kernel with this timeline id (0 forward tile, 2 gate + hidden,
+// 3 grouped wgrad, 4 recompute gate, 5 other pair GEMMs) receives the phase-stamp buffer — the kernels of a whole step can
+// then run back to back (CUDA graph) while one of them is stamped.
+unsigned long long* stamp_buf(int id) {
+  static const int only = [] { const char* e = getenv("MMF_STAMP_KERNEL"); return e ? atoi(e) : -1; }();
+  return (only < 0 || only == id) ? g_timing_buffer : nullptr;
+}
 unsigned long long* g_p2p_stamps = nullptr;
 
 struct BwdWs {
-  size_t off_H, off_dG, off_dU, off_cs, off_dbc, off_db1, off_mask, off_z, off_gparts, off_gflags, total;
+  size_t off_H, off_dG, off_dU, off_cs, off_dbc, off_db1, off_mask, off_z, off_thead, total;
 };
 BwdWs bwd_layout(int64_t N, int L, int D, int gated) {
   const int64_t tiles = ((N + 255) / 256) * 2;  // padded to whole CTA pairs
@@ -58,8 +65,7 @@ BwdWs bwd_layout(int64_t N, int L, int D, int gated) {
   w.off_db1 = o; o = align_up(o + (size_t)tiles * 4 * L * 4, 1024);
   w.off_mask = o; o = align_up(o + (size_t)N * (L / 32) * 4, 1024);   // 1 bit per element of H: [h > 0]
   w.off_z = o;    o = align_up(o + (size_t)N * 8 * 4, 1024);          // z_i = Wk h_i (head-projected backward), fp32 [N, 4 | 8]
-  w.off_gparts = o; o = align_up(o + (size_t)HEAD_MAX_GROUPS * (L + 2) * 4, 1024);   // head: first-level group partials
-  w.off_gflags = o; o = align_up(o + (size_t)HEAD_MAX_GROUPS * 4, 1024);             //       and their "written" flags
+  w.off_thead = o; o = align_up(o + (size_t)HEAD_MAX_TILES * HEAD_ROW * 4, 1024);    // head rows (m_t, l_t, Wk·acc_t) per tile
   w.total = o;
   return w;
 }
@@ -111,7 +117,7 @@ int launch_gemm2_grouped(const TMapSet& tmA, const TMapSet& tmB, GemmArgs ga, cu
     P.splits = splits; P.kb_per_split = per; P.first_pair = pairs;
     pairs += ((P.M + 255) / 256) * P.tiles_n * splits;
   }
-  ga.dbg = g_timing_buffer;
+  ga.dbg = stamp_buf(3);
   return launch_pdl(kern, dim3(2 * pairs), dim3(GEMM2_THREADS), C::SMEM_BYTES, st, tmA, tmB, ga);
 }
 
@@ -133,7 +139,7 @@ int launch_amil2v(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w
   using C = Amil2Cfg<L, D, GATED>;
   auto kern = amil_tile2_kernel<L, D, GATED, MODE, DROPH, DROPA>;
   MMF_CONFIGURE_SMEM(kern, C::SMEM_BYTES);
-  CUtensorMap tmX, tmW1, tmWab, tmH, tmWk;
+  CUtensorMap tmX, tmW1, tmWab, tmH, tmWk, tmAGs;
   const bool precise = (a.flags & MMF_PRECISE_FC) != 0;
   const uint64_t kin = precise ? 3072 : 1024;
   if (precise && (!w->W1_split || ldx < 3072)) return MMF_E_INVALID;
@@ -144,10 +150,12 @@ int launch_amil2v(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w
   else tmH = tmX;
   if (wk_split) MMF_TRY(make_tmap_bf16(&tmWk, wk_split, 16, L, L, 8));   // [Wk_hi ; Wk_lo], 8 rows per CTA of the pair
   else tmWk = tmX;
+  if (MODE == AMIL_FWD && a.AG) MMF_TRY(make_tmap_2b_sw64(&tmAGs, a.AG, (uint64_t)N, (uint64_t)a.ldag, (uint64_t)a.ldag, 32));
+  else tmAGs = tmX;
   const int pairs = (int)((N + 255) / 256);
   AmilArgs a2 = a;
   a2.kb1 = (int)(kin / 64);
-  return launch_pdl(kern, dim3(2 * pairs), dim3(AMIL2_THREADS), C::SMEM_BYTES, st, tmX, tmW1, tmWab, tmH, tmWk, a2);
+  return launch_pdl(kern, dim3(2 * pairs), dim3(AMIL2_THREADS), C::SMEM_BYTES, st, tmX, tmW1, tmWab, tmH, tmWk, tmAGs, a2);
 }
 
 template <int L, int D, bool GATED, int MODE>
@@ -220,8 +228,12 @@ void mmf_debug_set_p2p_stamp_buffer(void* device_u64_buffer) {
 }
 
 void mmf_debug_set_timeline_buffer(void* device_u64_buffer) {
+#if MMF_DEBUG_TIMELINE
   unsigned long long* p = reinterpret_cast<unsigned long long*>(device_u64_buffer);
   cudaMemcpyToSymbol(d_timeline, &p, sizeof(p));
+#else
+  (void)device_u64_buffer;   // release build: no device-global debug state (rebuild with -DMMF_DEBUG_TIMELINE=1)
+#endif
 }
 
 const char* mmf_error_string(int rc) {
@@ -277,7 +289,7 @@ int mmf_amil_fwd(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w,
   AmilArgs a = {};
   a.N = N; a.b1 = w->b1; a.bab = w->bab; a.wc = w->wc; a.bc = w->bc;
   a.A_raw = A_raw; a.partials = partials; a.store_h = H_stash != nullptr;
-  a.flags = flags; a.seed = seed; a.dbg = g_timing_buffer;
+  a.flags = flags; a.seed = seed; a.dbg = stamp_buf(0);
   return dispatch_amil<AMIL_FWD>(L, D, flags & MMF_GATED, x, N, ldx, w, a, H_stash, (cudaStream_t)stream);
 }
 
@@ -294,7 +306,7 @@ int mmf_amil_infer_varlen(const void* x, int64_t R, int64_t ldx, const MmfAmilWe
   AmilArgs a = {};
   a.N = R; a.b1 = w->b1; a.bab = w->bab; a.wc = w->wc; a.bc = w->bc;
   a.A_raw = A_raw; a.partials = partials; a.tile_valid = tile_valid;
-  a.flags = flags; a.dbg = g_timing_buffer;
+  a.flags = flags; a.dbg = stamp_buf(0);
   MMF_TRY(dispatch_amil<AMIL_FWD>(L, D, flags & MMF_GATED, x, R, ldx, w, a, nullptr, (cudaStream_t)stream));
   amil_seg_head_kernel<<<n_bags, 256, 0, (cudaStream_t)stream>>>(partials, seg_tile_offsets, L, Wk, bk, K, M, ml, hazards,
                                                                  S, risk, reinterpret_cast<long long*>(Y_hat));
@@ -348,14 +360,15 @@ int fwd_train_impl(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* 
     if ((reinterpret_cast<uintptr_t>(zero_buf) & 15u) || zero_count < 0 || (zero_count & 3)) return MMF_E_ALIGN;
     a.zero_ptr = reinterpret_cast<float4*>(zero_buf); a.zero_n4 = zero_count >> 2;
   }
-  a.flags = flags; a.seed = seed; a.dbg = g_timing_buffer;
+  a.flags = flags; a.seed = seed; a.dbg = stamp_buf(0);
   const void* wk_split = nullptr;
   if (head) {
     MMF_TRY(check_head(head, N));
     wk_split = head->Wk_split;
     a.z_out = reinterpret_cast<float*>(ws + lay.off_z);
     a.zld = head->K <= 4 ? 4 : 8;
-    a.gflags = reinterpret_cast<unsigned int*>(ws + lay.off_gflags);
+    a.tile_head = reinterpret_cast<float*>(ws + lay.off_thead);
+    a.head_wk = head->Wk; a.head_k = head->K;
   }
   return dispatch_amil<AMIL_FWD>(L, D, gated, x, N, ldx, w, a, ws + lay.off_H, (cudaStream_t)stream, wk_split);
 }
@@ -428,7 +441,7 @@ int mmf_amil_bwd_gate(const void* x, int64_t N, int64_t ldx, const MmfAmilWeight
   a.N = N; a.b1 = w->b1; a.bab = w->bab; a.wc = w->wc; a.bc = w->bc;
   a.A_raw = const_cast<float*>(A_raw); a.flags = flags; a.seed = seed;
   a.ml = ml; a.M = M; a.dM = dM; a.dA_raw = dA_raw;
-  a.dG = c.dG; a.lddg = c.KD; a.colsum_ws = c.cs; a.dbc_ws = c.dbc_ws; a.dbg = g_timing_buffer;
+  a.dG = c.dG; a.lddg = c.KD; a.colsum_ws = c.cs; a.dbc_ws = c.dbc_ws; a.dbg = stamp_buf(4);
   MMF_TRY(dispatch_amil<AMIL_BWD_GATE>(L, D, c.gated, x, N, ldx, w, a, c.Hb, st));
   // the pair dU GEMM reads [h > 0] as a bitmask (the training forward of the stash path emits it itself)
   relu_mask_kernel<<<(int)((N * (L / 32) + 255) / 256), 256, 0, st>>>(c.Hb, N * (L / 32), c.mask);
@@ -475,8 +488,7 @@ int bwd_gate_hidden_stashed_impl(int64_t N, const MmfAmilWeights* w, int L, int 
     if (!partials) return MMF_E_INVALID;
     a.z = reinterpret_cast<const float*>(ws + lay.off_z); a.zld = head->K <= 4 ? 4 : 8;
     a.partials = partials; a.n_tiles = (int)((N + 127) / 128);
-    a.gparts = reinterpret_cast<float*>(ws + lay.off_gparts);
-    a.gflags = reinterpret_cast<unsigned int*>(ws + lay.off_gflags);
+    a.tile_head = reinterpret_cast<const float*>(ws + lay.off_thead);
     HeadTail& t = a.head;
     t.Wk = head->Wk; t.bk = head->bk; t.Y = reinterpret_cast<const long long*>(head->Y); t.c = head->c;
     t.alpha = head->alpha; t.eps = head->eps; t.loss_scale = head->loss_scale; t.K = head->K;
@@ -485,7 +497,7 @@ int bwd_gate_hidden_stashed_impl(int64_t N, const MmfAmilWeights* w, int L, int 
     t.dWk = head->dWk; t.dbk = head->dbk;
   }
   a.du_scale = (flags & MMF_DROPOUT_H) ? (1.0f / 0.75f) : 1.0f;
-  a.seed = seed; a.dbg = g_timing_buffer;
+  a.seed = seed; a.dbg = stamp_buf(2);
   cudaStream_t st = (cudaStream_t)stream;
   if (L == 256 && D == 256) return gated ? launch_hidden_fused<256, 256, true>(a, flags, tmAG, tmWab, tmDU, st) : launch_hidden_fused<256, 256, false>(a, flags, tmAG, tmWab, tmDU, st);
   if (L == 512 && D == 384) return gated ? launch_hidden_fused<512, 384, true>(a, flags, tmAG, tmWab, tmDU, st) : launch_hidden_fused<512, 384, false>(a, flags, tmAG, tmWab, tmDU, st);
@@ -543,7 +555,7 @@ int mmf_amil_bwd_hidden(const void* x, int64_t N, int64_t ldx, const MmfAmilWeig
   ga.c_bf16 = c.dU; ga.ldc = L;
   ga.s_raw = A_raw; ga.ml = ml; ga.dM = dM; ga.H = c.Hb; ga.ldh = L; ga.colsum_ws = c.db1_ws;
   ga.du_scale = (flags & MMF_DROPOUT_H) ? (1.0f / 0.75f) : 1.0f;
-  ga.mask = c.mask; ga.mask_ld = L / 32; ga.db1 = g->db1; ga.dbg = g_timing_buffer;
+  ga.mask = c.mask; ga.mask_ld = L / 32; ga.db1 = g->db1; ga.dbg = stamp_buf(5);
   MMF_TRY(make_tmap_bf16(&tA.m[3], c.dU, (uint64_t)N, L, L, 128));   // output map (TMA store of the staged tile)
   if (L == 512) return launch_gemm2<0, 1, EPI_DU, 512>(tA, tB, ga, 1, st);
   return launch_gemm2<0, 1, EPI_DU, 256>(tA, tB, ga, 1, st);

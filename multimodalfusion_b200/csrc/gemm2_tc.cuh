@@ -72,7 +72,7 @@ gemm2_tc_kernel(const __grid_constant__ TMapSet tmA, const __grid_constant__ TMa
   const int kb1 = min(g.kb_total, kb0 + kb_per_split);
   const int nkb = kb1 - kb0;
 
-  timeline_start(EPI == EPI_ATOMIC ? 3 : 5);
+  Timeline tl = timeline_start(EPI == EPI_ATOMIC ? 3 : 5);
   griddep_launch_dependents();
   if (threadIdx.x == 0) {
     MMF_GSTAMP(g, 0);
@@ -93,6 +93,10 @@ gemm2_tc_kernel(const __grid_constant__ TMapSet tmA, const __grid_constant__ TMa
   tc_fence_after();
   const uint32_t tmem = tmem_base_slot;
   griddep_wait();
+  // (pointers to the previous kernel's outputs are re-derived after the wait, see pdl_fresh)
+  const float* const g_dM = pdl_fresh(g.dM); const float* const g_sraw = pdl_fresh(g.s_raw); const float* const g_ml = pdl_fresh(g.ml);
+  const uint32_t* const g_mask = pdl_fresh(g.mask); const float* const g_bias = pdl_fresh(g.bias);
+  timeline_wait_done(tl);
   if (threadIdx.x == 0) MMF_GSTAMP(g, 1);
 
   if (warp == 0 && lane == 0) {
@@ -168,14 +172,14 @@ gemm2_tc_kernel(const __grid_constant__ TMapSet tmA, const __grid_constant__ TMa
     const bool row_ok = row < g.M;
     constexpr int PIECES = BN / 64;   // 32-column pieces per half
     float* s_dm = reinterpret_cast<float*>(smem_raw + (pool - smem_u32(smem_raw)) + C::STAGES * C::STAGE);
-    for (int i = e; i < BN; i += 256) s_dm[i] = (n0 + i < g.N) ? __ldg(g.dM + n0 + i) : 0.f;
+    for (int i = e; i < BN; i += 256) s_dm[i] = (n0 + i < g.N) ? __ldg(g_dM + n0 + i) : 0.f;
     float p_row = 0.f;
     uint32_t mw[PIECES];
 #pragma unroll
     for (int i = 0; i < PIECES; ++i) mw[i] = 0u;
     if (row_ok) {
-      p_row = __expf(g.s_raw[row] - g.ml[0]) / g.ml[1];
-      const uint32_t* mp = g.mask + (long long)row * g.mask_ld + (n0 >> 5) + half * PIECES;
+      p_row = __expf(g_sraw[row] - g_ml[0]) / g_ml[1];
+      const uint32_t* mp = g_mask + (long long)row * g.mask_ld + (n0 >> 5) + half * PIECES;
 #pragma unroll
       for (int i = 0; i < PIECES; ++i) mw[i] = __ldg(mp + i);
     }
@@ -283,10 +287,10 @@ gemm2_tc_kernel(const __grid_constant__ TMapSet tmA, const __grid_constant__ TMa
       tmem_ld32(tmem + ((q * 32u) << 16) + cb * 32, v);
       tmem_ld_wait();
       if (EPI == EPI_STORE) {
-        if (g.bias) {
+        if (g_bias) {
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + col0 + i));
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(g_bias + col0 + i));
             v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
           }
         }
@@ -327,7 +331,7 @@ gemm2_tc_kernel(const __grid_constant__ TMapSet tmA, const __grid_constant__ TMa
   __syncthreads();
   cluster_sync_all();
   if (threadIdx.x == 0) MMF_GSTAMP(g, 6);
-  timeline_end(EPI == EPI_ATOMIC ? 3 : 5);
+  timeline_end(EPI == EPI_ATOMIC ? 3 : 5, tl);
   if (warp == 2) tmem_dealloc_pair(tmem, BN);
 }
 

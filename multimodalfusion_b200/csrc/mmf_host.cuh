@@ -48,6 +48,25 @@ inline int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uin
   return r == CUDA_SUCCESS ? MMF_OK : MMF_E_TMAP;
 }
 
+// 2-D row-major array of 2-byte elements, box [box_rows][32 cols] (64-byte rows, 64-byte swizzle): the target of the
+// training forward's activation-stash stores (each epilogue warp stages a 32 x 32 fp16 block whose 16-byte chunk index is
+// XORed with (row >> 1) & 3 — exactly CU_TENSOR_MAP_SWIZZLE_64B); rows past `rows` are dropped by the TMA.
+inline int make_tmap_2b_sw64(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                             uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return MMF_E_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0 || (ld * 2) % 16 != 0) return MMF_E_ALIGN;
+  if (rows == 0 || cols == 0) return MMF_E_INVALID;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {ld * 2};
+  cuuint32_t box[2] = {32, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MMF_OK : MMF_E_TMAP;
+}
+
 // 2-D row-major fp32 array, box [box_rows][32 cols] (128-byte rows, 128-byte swizzle): the target of the
 // split-K epilogue's TMA reduce-add (cp.reduce.async.bulk.tensor ... .add); out-of-bounds elements are dropped.
 inline int make_tmap_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,

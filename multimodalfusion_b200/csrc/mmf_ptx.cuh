@@ -92,29 +92,49 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
 }
 
 // ----------------------------------------------------------------------------------------
-// Debug timeline: when d_timeline is set (mmf_debug_set_timeline_buffer) CTA 0 of every hot-path kernel appends
-// its %globaltimer at kernel start and at kernel end to two logs.
+// Debug timeline (only in builds with -DMMF_DEBUG_TIMELINE=1, tools/step_timeline.py; the release library carries no
+// device-global state and mmf_debug_set_timeline_buffer is a no-op there): every CTA of every hot-path kernel appends one
+// record (kernel id, blockIdx.x | cycles << 32, %globaltimer at CTA start, after griddepcontrol.wait, at CTA end) to a log.
+// Buffer layout (uint64): [0] record count, [16 + 5 i ...] = the i-th record.
 // ----------------------------------------------------------------------------------------
-__device__ unsigned long long* d_timeline = nullptr;
+#ifndef MMF_DEBUG_TIMELINE
+#define MMF_DEBUG_TIMELINE 0
+#endif
+struct Timeline { unsigned long long t0, t1; long long c1; };
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-// Buffer layout (uint64): [0] start-log count, [1] end-log count, [16 + 2 i] = (kernel id, ns) of the i-th kernel
-// start seen by CTA 0, [16 + 8192 + 2 j] = (id, ns) of the j-th kernel end seen by CTA 0.
-__device__ __forceinline__ void timeline_start(int id) {
-  if (d_timeline && threadIdx.x == 0 && blockIdx.x == 0) {
+#if MMF_DEBUG_TIMELINE
+__device__ unsigned long long* d_timeline = nullptr;
+constexpr unsigned long long TIMELINE_MAX_RECORDS = 32768;
+__device__ __forceinline__ Timeline timeline_start(int) {
+  Timeline tl = {0ull, 0ull, 0ll};
+  if (d_timeline && threadIdx.x == 0) tl.t0 = globaltimer_ns();
+  return tl;
+}
+__device__ __forceinline__ void timeline_wait_done(Timeline& tl) {
+  if (d_timeline && threadIdx.x == 0) { tl.t1 = globaltimer_ns(); tl.c1 = clock64(); }
+}
+__device__ __forceinline__ void timeline_end(int id, const Timeline& tl) {
+  if (d_timeline && threadIdx.x == 0) {
+    const unsigned long long t2 = globaltimer_ns();
+    const long long c2 = clock64();
     const unsigned long long i = atomicAdd(d_timeline, 1ull);
-    if (i < 4096) { d_timeline[16 + 2 * i] = (unsigned long long)id; d_timeline[17 + 2 * i] = globaltimer_ns(); }
+    if (i < TIMELINE_MAX_RECORDS) {
+      unsigned long long* r = d_timeline + 16 + 5 * i;
+      // [1]: blockIdx.x in the low 32 bits, SM cycles between the wait-return and the end in the high 32 bits
+      r[0] = (unsigned long long)id; r[1] = (unsigned long long)blockIdx.x | ((unsigned long long)(c2 - tl.c1) << 32);
+      r[2] = tl.t0; r[3] = tl.t1; r[4] = t2;
+    }
   }
 }
-__device__ __forceinline__ void timeline_end(int id) {
-  if (d_timeline && threadIdx.x == 0 && blockIdx.x == 0) {
-    const unsigned long long j = atomicAdd(d_timeline + 1, 1ull);
-    if (j < 4096) { d_timeline[16 + 8192 + 2 * j] = (unsigned long long)id; d_timeline[17 + 8192 + 2 * j] = globaltimer_ns(); }
-  }
-}
+#else
+__device__ __forceinline__ Timeline timeline_start(int) { return Timeline{0ull, 0ull, 0ll}; }
+__device__ __forceinline__ void timeline_wait_done(Timeline&) {}
+__device__ __forceinline__ void timeline_end(int, const Timeline&) {}
+#endif
 
 // ----------------------------------------------------------------------------------------
 // Programmatic dependent launch (PDL). A kernel launched with
@@ -125,6 +145,16 @@ __device__ __forceinline__ void timeline_end(int id) {
 // ----------------------------------------------------------------------------------------
 __device__ __forceinline__ void griddep_launch_dependents() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+// IMPORTANT: nvcc treats ld.global.nc (__ldg, loads through const __restrict__ pointers) as loads of immutable memory and
+// schedules them freely — also ABOVE the volatile, memory-clobbering griddepcontrol.wait (seen in the SASS of the head
+// kernel: the (m_t, l_t) loads of the forward's partials sat before the wait and intermittently returned the previous
+// contents of a recycled buffer). Every pointer to data written by the preceding kernel goes through pdl_fresh() after
+// the wait: the address then depends on a volatile asm that cannot move above it.
+template <class T>
+__device__ __forceinline__ T* pdl_fresh(T* p) {
+  asm volatile("" : "+l"(p) : : "memory");
+  return p;
 }
 __device__ __forceinline__ void griddep_wait() {
   asm volatile("griddepcontrol.wait;" ::: "memory");

@@ -367,6 +367,7 @@ amil_head_step_kernel(const float* __restrict__ parts, int n, int L, const float
   const bool wk_smem = K * L <= 4096;
   griddep_launch_dependents();
   griddep_wait();
+  parts = pdl_fresh(parts);
   // (m_t, l_t) of up to 8 partials per thread, kept in registers for both reductions
   float2 mlv[8];
   float m = -CUDART_INF_F;
@@ -641,9 +642,11 @@ amil_head_step_cluster_kernel(const float* __restrict__ parts, int n, int L, con
   const int c_lo = rank * LC;
   const int CP = LC >> 1;                  // column pairs per CTA
   const int RG = 512 / CP;                 // row groups
-  timeline_start(1);
+  Timeline tl = timeline_start(1);
   griddep_launch_dependents();
-  griddep_wait();   // PDL: the partials come from the tile kernel launched just before
+  griddep_wait();
+  parts = pdl_fresh(parts);
+  timeline_wait_done(tl);   // PDL: the partials come from the tile kernel launched just before
   // early scalar loads (independent of everything else)
   long long y = 0; float cb = 0.f;
   if (tid == 0) { y = Yp[0]; cb = cp[0]; }
@@ -781,7 +784,7 @@ amil_head_step_cluster_kernel(const float* __restrict__ parts, int n, int L, con
     dM[c_lo + tid] = acc;
   }
   if (rank == 0 && dbk && tid < K) dbk[tid] += s_dlogit[tid];
-  timeline_end(1);
+  timeline_end(1, tl);
 }
 
 // -------------------------------------------------------------------------------------------

@@ -87,7 +87,7 @@ class MIL_Attention_fc_surv_path(MIL_Attention_fc_path):
         (combine, classifier, hazards, loss, their gradients) in its prologue, grouped wgrad. Gradients land in the
         parameters' ``.grad`` (views of the flat buffer of ``enable_fused_step``); ``accumulate=False`` clears them
         first inside the forward kernel (``optimizer.zero_grad()``), ``True`` adds (gradient accumulation over ``gc``
-        bags, ``loss_scale = 1 / gc``). Train mode only; bags of up to 32768 instances; returns
+        bags, ``loss_scale = 1 / gc``). Train mode only; bags of up to 65536 instances; returns
         (hazards [1,K], S [1,K], Y_hat [1,1], A_raw [1,N], loss) — views of buffers reused by the next call."""
         from .. import ops
         from .model_modules import AmilBranch, _seed_from_torch
@@ -99,8 +99,8 @@ class MIL_Attention_fc_surv_path(MIL_Attention_fc_path):
         seq = self.attention_net_WSI
         prep = AmilBranch.prepared(seq)
         N = path_features.shape[0]
-        if N > 32768:
-            raise NotImplementedError("fused_step merges at most 256 tile partials per CTA (N <= 32768)")
+        if N > 65536:
+            raise NotImplementedError("fused_step merges at most 512 per-tile head rows per CTA (N <= 65536)")
         attn = seq[3]
         flags = ops.amil_flags(prep.gated, dropout_h=self.training, dropout_attn=self.training and attn.use_dropout)
         if N <= ops.PRECISE_FC_MAX_ROWS:      # small bag: split-precision fc (see autograd.AmilPool)

@@ -460,7 +460,7 @@ def amil_fused_step(x: torch.Tensor, w: AmilPrepared, flags: int, seed: int, buf
                     zero: Optional[torch.Tensor] = None, repack_head: bool = True):
     """One batch-1 training step of the path / radio AMIL model in THREE launches: fused forward (+ z = Wk h and the
     ReLU mask words), fused gate + hidden backward whose prologue runs the head (combine, classifier, hazards,
-    nll_surv, dlogits, dM, dWk, dbk) and whose phase A is head-projected, grouped wgrad GEMM. N <= 32768. Gradients accumulate into `grads` (dW1, db1, dWab, dbab, dwc,
+    nll_surv, dlogits, dM, dWk, dbk) and whose phase A is head-projected, grouped wgrad GEMM. N <= 65536. Gradients accumulate into `grads` (dW1, db1, dWab, dbab, dwc,
     dbc), dWk, dbk; `zero` (the flat gradient buffer that holds them all) is cleared by the forward first.
     Outputs are left in `buf` (loss, hazards, S, Y_hat, A_raw, M)."""
     _require_cuda(x, Wk)

@@ -7,6 +7,8 @@ gradients within 2e-2 relative (relative = max|err| / max|ref| per tensor).
 import math
 
 import pytest
+import os
+
 import torch
 
 from helpers import (amil_weights, build_head_model, build_omic_model, build_path_model, build_radio_model, rel_err)
@@ -31,8 +33,8 @@ def bfr(t):
 def test_library_is_native_and_loaded():
     from multimodalfusion_b200 import _lib
     assert _lib.lib().mmf_version() == 1
-    with open("/proc/self/maps") as f:
-        assert "libmmf_b200.so" in f.read()
+    with open("/proc/self/maps") as f:   # (MMF_LIB_PATH: an A/B build of the same library, tools/ab_variant.py)
+        assert os.path.basename(_lib.LIB_PATH) in f.read() and os.path.basename(_lib.LIB_PATH).startswith("libmmf_b200")
     assert torch.cuda.get_device_capability(0)[0] == 10, "sm_100a kernels need a Blackwell device"
 
 

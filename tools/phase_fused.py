@@ -67,8 +67,8 @@ if os.environ.get("HEAD_STAMPS") == "1":
     hid_names = None
 hid_names_head = {0: "start", 1: "after cluster sync + griddep wait", 2: "mma: first A stage ready", 3: "mma: all issued",
                   4: "workers: phase A done", 5: "workers: mainloop done", 6: "workers: acc seen", 7: "workers: epilogue done",
-                  8: "head: inputs requested", 9: "head: group row released (CTAs < n_groups)", 10: "head: all flags seen",
-                  11: "head: group rows merged", 12: "head: logits reduced", 13: "head: dlogits / outputs done"}
+                  8: "head: inputs requested", 9: "head: global max known", 10: "head: sums reduced",
+                  13: "head: dlogits / dM done"}
 hid_names = {0: "start", 1: "after cluster sync + griddep wait", 2: "mma: first A stage ready", 3: "mma: all issued",
              4: "workers: phase A done", 5: "workers: mainloop done", 6: "workers: acc seen", 7: "workers: epilogue done",
              8: "slice 0 landed", 9: "slice 0 transformed", 10: "slice 1 landed", 11: "slice 1 transformed",
