@@ -214,13 +214,13 @@ amil_hidden_fused_kernel(const __grid_constant__ CUtensorMap tmAG,   // stash fp
       const int s = kp % C::NSA;
       mbar_wait(smem_u32(&bar_astore[s]), (kp / C::NSA) & 1);
       if (MMF_HIDDEN_RELAY) mbar_arrive_cluster(a_ready_leader + s * 8u);   // this CTA's half of the stage is ready
-      tma_store_2d(&tmDG, a_ring + s * C::A_STAGE, kp * 64, (int)row0);
-      if (GATED) tma_store_2d(&tmDG, a_ring + s * C::A_STAGE + 16384, D + kp * 64, (int)row0);
+      tma_store_2d_keep(&tmDG, a_ring + s * C::A_STAGE, kp * 64, (int)row0);
+      if (GATED) tma_store_2d_keep(&tmDG, a_ring + s * C::A_STAGE + 16384, D + kp * 64, (int)row0);
       tma_store_commit();
       tma_store_wait_read();                       // the stage may be overwritten once the store has read it
       mbar_arrive(smem_u32(&bar_aempty[s]));
     }
-    tma_store_wait_all();
+    tma_store_wait_exit();
   } else if (warp == 1 && lane == 0 && leader) {
     // =============================== MMA issuer (leader CTA) ===========================
     constexpr uint32_t idesc = umma_idesc_bf16(256, 256, 0, 1);
@@ -805,7 +805,7 @@ amil_hidden_fused_kernel(const __grid_constant__ CUtensorMap tmAG,   // stash fp
         fence_proxy_async_smem();
         named_bar_sync(2 + part, 128);
         if (q == 0 && lane == 0) {
-          tma_store_2d(&tmDU, blk, (cb >> 1) * 64, (int)row0);
+          tma_store_2d_keep(&tmDU, blk, (cb >> 1) * 64, (int)row0);
           tma_store_commit();
         }
       }
@@ -825,7 +825,7 @@ amil_hidden_fused_kernel(const __grid_constant__ CUtensorMap tmAG,   // stash fp
       atomicAdd(which == 0 ? a.dwc + d : a.dbab + (which - 1) * D + d, v);
     }
     if (e == 0) atomicAdd(a.dbc, s_dbc);
-    if (q == 0 && lane == 0) tma_store_wait_all();   // the threads that committed the dU block stores
+    if (q == 0 && lane == 0) tma_store_wait_exit();   // the threads that committed the dU block stores
     if (e == 0) MMF_STAMP(a, 7);
   }
   tc_fence_before();

@@ -63,6 +63,7 @@ struct Amil2Cfg {
 
 // MMF_TILE2_CHUNK_STAMPS = 1 (debug build, tools/phase_chunks.py): stamps 2 / 3 / 4 = "GEMM2 chunk c accumulators seen" and
 // 5 / 9 / 15 = "chunk c gate epilogue done" (epilogue thread 0) replace the producer / first-stage / vectors-staged stamps
+// MMF_L2_HINTS (mmf_ptx.cuh): >= 1 evict_first on the x stream (forward and wgrad)
 #ifndef MMF_TILE2_CHUNK_STAMPS
 #define MMF_TILE2_CHUNK_STAMPS 0
 #endif
@@ -138,19 +139,28 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   if (warp == 0 && lane == 0) {
     // =============================== TMA producer (both CTAs) ==========================
     const int kb1 = a.kb1 > 0 ? a.kb1 : C::KB1;   // 16 k-blocks of x, or 48 in the split-precision form (MMF_PRECISE_FC)
+    // x streams through L2 once per kernel (32 MB per 16k bag): evict_first keeps it from displacing the step's stash
+    // (H, [a|g] -> dG, dU: 56 MB that the backward re-reads and the next step overwrites IN PLACE — as long as those lines
+    // stay in L2 they are never written back; with default priority the x stream evicted them dirty: 63 MB of DRAM
+    // writes per step in bursts on the kernels' critical paths, profiles/r02a_ncu_step_summary.md)
+    const uint64_t pol_x = l2_policy_evict_first();
     for (int kb = 0; kb < kb1; ++kb) {
       // the ring's first NS1 loads go out first; only then is the rest of this CTA's x tile prefetched
       // into L2 (issuing all 16 prefetches up front queued the first real load behind them:
       // first stage landed 8k cycles after the cluster sync)
       if (kb == C::NS1)
-        for (int kp = C::NS1; kp < kb1; ++kp) tma_prefetch_l2_2d(&tmX, kp * 64, (int)row0);
+        for (int kp = C::NS1; kp < kb1; ++kp) {
+          if (MMF_L2_HINTS) tma_prefetch_l2_2d_hint(&tmX, kp * 64, (int)row0, pol_x);
+          else tma_prefetch_l2_2d(&tmX, kp * 64, (int)row0);
+        }
       const int s = kb % C::NS1;
       const uint32_t ph = (kb / C::NS1) & 1;
       mbar_wait(smem_u32(&bar_empty1[s]), ph ^ 1);
       const uint32_t full = smem_u32(&bar_full1[s]);
       const uint32_t dst = pool + s * C::STAGE1;
       if (leader) mbar_arrive_expect_tx(full, 2 * C::STAGE1);
-      tma_load_2d_pair(dst, &tmX, full, kb * 64, (int)row0);
+      if (MMF_L2_HINTS) tma_load_2d_pair_hint(dst, &tmX, full, kb * 64, (int)row0, pol_x);
+      else tma_load_2d_pair(dst, &tmX, full, kb * 64, (int)row0);
 #pragma unroll
       for (int j = 0; j < C::NH1; ++j)
         tma_load_2d_pair(dst + 16384 + j * 16384, &tmW1, full, kb * 64, j * 256 + 128 * (int)rank);
@@ -254,10 +264,10 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       for (int c = 0; c < C::NCH; ++c) {
         mbar_wait(smem_u32(&bar_acc2_full[c & 1]), (c >> 1) & 1);   // (=> bar_h completed: both CTAs' H tiles are written and fenced)
         for (int kb = c * C::KB2 / C::NCH; kb < (c + 1) * C::KB2 / C::NCH; ++kb)
-          tma_store_2d(&tmH, h_base + kb * 16384, kb * 64, (int)row0);
+          tma_store_2d_keep(&tmH, h_base + kb * 16384, kb * 64, (int)row0);
         tma_store_commit();
       }
-      tma_store_wait_all();
+      tma_store_wait_exit();
     }
   } else if (warp >= 4) {
     // =============================== epilogue warps (both CTAs) ========================
@@ -308,6 +318,8 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     // NOW, while GEMM1 runs and the epilogue warps are idle — inside EPI1 the two hashes per piece were a third of its
     // instructions (EPI1: 5.6k cycles without dropout, 8.6k with, gpurun_out/r2c_chunks.log). The words are consumed
     // in order through a register shift (the piece loop is not unrolled).
+    uint32_t mw_acc[PIECES1] = {};   // ReLU mask words of this thread's row and column half (training forward)
+    static_assert(PIECES1 % 4 == 0, "mask words are stored as 16-byte vectors");
     uint32_t keepw[PIECES1];
 #pragma unroll
     for (int ii = 0; ii < PIECES1; ++ii)
@@ -367,10 +379,21 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         }
         // training forward: [h > 0] of the bf16 activations the backward will see, 1 bit per element (the dU epilogue
         // of the hidden-gradient kernel reads 64 B per row instead of re-deriving the bits from a re-read of H)
-        if (MODE == AMIL_FWD && a.mask_out != nullptr && row_ok) a.mask_out[row * (L / 32) + cb] = mword;
+        if (MODE == AMIL_FWD) mw_acc[PIECES1 - 2 + par] = mword;
       }
 #pragma unroll
       for (int j = 0; j + 2 < PIECES1; ++j) keepw[j] = keepw[j + 2];
+      if (MODE == AMIL_FWD && i2 + 2 < PIECES1) {
+#pragma unroll
+        for (int j = 0; j + 2 < PIECES1; ++j) mw_acc[j] = mw_acc[j + 2];   // (register shift: the piece loop is not unrolled)
+      }
+    }
+    if (MODE == AMIL_FWD && a.mask_out != nullptr && row_ok) {
+      // this thread's PIECES1 consecutive words of the row: 16-byte stores (one word per piece and store instruction was
+      // 32 scattered 4-byte writes per warp)
+      uint4* mp = reinterpret_cast<uint4*>(a.mask_out + row * (L / 32) + cb0);
+#pragma unroll
+      for (int j = 0; j < PIECES1 / 4; ++j) mp[j] = make_uint4(mw_acc[4 * j], mw_acc[4 * j + 1], mw_acc[4 * j + 2], mw_acc[4 * j + 3]);
     }
     fence_proxy_async_smem();
     tc_fence_before();
@@ -480,8 +503,8 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&tmAGs, scratch, d0, (int)(row0 + q * 32));
-            if (GATED) tma_store_2d(&tmAGs, scratch + 2048u, D + d0, (int)(row0 + q * 32));
+            tma_store_2d_keep(&tmAGs, scratch, d0, (int)(row0 + q * 32));
+            if (GATED) tma_store_2d_keep(&tmAGs, scratch + 2048u, D + d0, (int)(row0 + q * 32));
             tma_store_commit();
           }
 #else
@@ -564,7 +587,7 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const float dsum = warp_sum(ds);
         if (lane == 0) a.dbc_ws[(long long)tile * 4 + q] = dsum;
       }
-      if (e == 0) tma_store_wait_all();
+      if (e == 0) tma_store_wait_exit();
     } else {
       // ---------------- FWD: scores out + tile softmax partial ------------------------
       // head row of the tile (training step): this thread's two classifier columns, requested before the softmax barriers
@@ -649,7 +672,7 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           a.tile_head[(long long)tile * 12 + e] = v;
         }
       }
-      if (MMF_STASH_TMA && a.AG != nullptr && lane == 0) tma_store_wait_all();   // this warp's stash stores
+      if (MMF_STASH_TMA && a.AG != nullptr && lane == 0) tma_store_wait_exit();   // this warp's stash stores
     }
     if (e == 0) MMF_STAMP(a, 13);
     tc_fence_before();

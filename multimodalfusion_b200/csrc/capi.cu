@@ -584,6 +584,8 @@ int mmf_amil_bwd_wgrad(const void* x, int64_t N, int64_t ldx, const MmfAmilWeigh
     ga.grp[0].M = L; ga.grp[0].N = 1024; ga.grp[0].a_map = 0; ga.grp[0].b_map = 0;
     ga.grp[0].c = g->dW1; ga.grp[0].ldc = 1024;
     ga.grp[0].tma_reduce = 1;
+    static const bool l2_hints = [] { const char* e = getenv("MMF_NO_L2_HINTS"); return !(e && e[0] == '1'); }();
+    ga.grp[0].b_stream = l2_hints ? 1 : 0;   // x: read once here, evict_first
     MMF_TRY(make_tmap_f32(&tA.m[3], g->dW1, (uint64_t)L, 1024, 1024, 32));
     if (L >= 512) {
       ga.grp[1].M = c.KD; ga.grp[1].N = L; ga.grp[1].a_map = 1; ga.grp[1].b_map = 1;

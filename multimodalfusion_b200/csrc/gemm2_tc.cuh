@@ -49,7 +49,7 @@ gemm2_tc_kernel(const __grid_constant__ TMapSet tmA, const __grid_constant__ TMa
 
   // problem decode: plain grid (pair_m, n_tile, split) or the grouped single-wave list
   int pair_m = blockIdx.x >> 1, n_tile = blockIdx.y, split = blockIdx.z;
-  int gM = g.M, gN = g.N, kb_per_split = g.kb_per_split, a_map = 0, b_map = -1, trans = 0, tma_red = 0;
+  int gM = g.M, gN = g.N, kb_per_split = g.kb_per_split, a_map = 0, b_map = -1, trans = 0, tma_red = 0, b_stream = 0;
   const CUtensorMap* cmap = &tmA.m[3];
   float* c_f32 = g.c_f32;
   long long ldc = g.ldc;
@@ -62,7 +62,7 @@ gemm2_tc_kernel(const __grid_constant__ TMapSet tmA, const __grid_constant__ TMa
     n_tile = t % P.tiles_n;
     pair_m = t / P.tiles_n;
     gM = P.M; gN = P.N; kb_per_split = P.kb_per_split; a_map = P.a_map; b_map = P.b_map; trans = P.trans;
-    tma_red = P.tma_reduce;
+    tma_red = P.tma_reduce; b_stream = P.b_stream;
     if (&P != &g.grp[0]) cmap = &tmB.m[3];
     c_f32 = P.c; ldc = P.ldc;
   }
@@ -101,6 +101,7 @@ gemm2_tc_kernel(const __grid_constant__ TMapSet tmA, const __grid_constant__ TMa
 
   if (warp == 0 && lane == 0) {
     // ------------------------------- TMA producer (both CTAs) -------------------------
+    const uint64_t pol_stream = l2_policy_evict_first();   // (see amil_tile2.cuh: the bag must not displace the stash in L2)
     for (int i = 0; i < nkb; ++i) {
       const int kb = kb0 + i;
       const int s = i % C::STAGES;
@@ -126,8 +127,10 @@ gemm2_tc_kernel(const __grid_constant__ TMapSet tmA, const __grid_constant__ TMa
           const int seg = b_map >= 0 ? b_map : nb / g.b_seg_n;
           const int c0 = b_map >= 0 ? nb : nb - seg * g.b_seg_n;
 #pragma unroll
-          for (int j = 0; j < 2; ++j)
-            tma_load_2d_pair(b_dst + h * 16384 + j * 8192, &tmB.m[seg], full, c0 + j * 64, kb * 64);
+          for (int j = 0; j < 2; ++j) {
+            if (b_stream) tma_load_2d_pair_hint(b_dst + h * 16384 + j * 8192, &tmB.m[seg], full, c0 + j * 64, kb * 64, pol_stream);
+            else tma_load_2d_pair(b_dst + h * 16384 + j * 8192, &tmB.m[seg], full, c0 + j * 64, kb * 64);
+          }
         }
       }
     }
@@ -234,7 +237,7 @@ gemm2_tc_kernel(const __grid_constant__ TMapSet tmA, const __grid_constant__ TMa
       }
       if (n0 + (int)col < g.N) { atomicAdd(g.db1 + n0 + col, a0); atomicAdd(g.db1 + n0 + col + 1, a1); }
     }
-    if (e == 0) { tma_store_wait_all(); MMF_GSTAMP(g, 5); }
+    if (e == 0) { tma_store_wait_exit(); MMF_GSTAMP(g, 5); }
   } else if (warp >= 4) {
     // ------------------------------- epilogue (both CTAs, 8 warps) --------------------
     const uint32_t q = warp & 3;
@@ -276,7 +279,7 @@ gemm2_tc_kernel(const __grid_constant__ TMapSet tmA, const __grid_constant__ TMa
           tma_store_commit();
         }
       }
-      if (lane == 0) tma_store_wait_all();
+      if (lane == 0) tma_store_wait_exit();
     } else
 #pragma unroll 1
     for (int ii = 0; ii < PIECES; ++ii) {

@@ -53,6 +53,7 @@ struct GemmArgs {
     int kb_per_split;
     int a_map, b_map;        // indices into tmA.m[] / tmB.m[]
     int first_pair;          // first CTA-pair index of this group
+    int b_stream;            // the B operand streams through L2 once (the bag x): TMA loads carry evict_first
     int trans;               // store C^T: element (row, col) goes to c[col * ldc + row]
     int tma_reduce;          // reduce through the TMA (cp.reduce.async.bulk.tensor .add) — output map in
                              // tmA.m[3] (group 0) / tmB.m[3] (group 1), fp32 box [32 rows][32 cols]

@@ -203,6 +203,20 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src_
                : "memory");
 }
 // shared -> global with element-wise ADD at the destination (split-K reduction done by the TMA / L2)
+// MMF_L2_HINTS >= 2 (A/B candidate): the step's stash / dG / dU stores carry evict_last
+#ifndef MMF_L2_HINTS
+#define MMF_L2_HINTS 1
+#endif
+__device__ __forceinline__ void tma_store_2d_keep(const CUtensorMap* m, uint32_t src_smem, int32_t c0, int32_t c1) {
+#if MMF_L2_HINTS >= 2
+  const uint64_t policy = l2_policy_evict_last();
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src_smem), "r"(c0), "r"(c1), "l"(policy)
+               : "memory");
+#else
+  tma_store_2d(m, src_smem, c0, c1);
+#endif
+}
 __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, uint32_t src_smem, int32_t c0,
                                                   int32_t c1) {
   asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
@@ -217,6 +231,10 @@ __device__ __forceinline__ void tma_store_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 // wait until all committed stores are complete (global writes performed)
+// Before a CTA exits (or reuses the staging memory) its bulk stores only have to have READ shared memory: the writes of
+// a grid's bulk-async stores are performed before the grid completes (and before a dependent grid's griddepcontrol.wait
+// returns). Waiting for full completion instead kept every CTA alive for an extra L2 write round trip at each kernel's tail.
+__device__ __forceinline__ void tma_store_wait_exit() { tma_store_wait_read(); }
 __device__ __forceinline__ void tma_store_wait_all() {
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
@@ -404,6 +422,20 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst_smem, const CUtens
       " [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
       : "memory");
+}
+// same with an L2 eviction-priority hint (createpolicy value): evict_first for operands that stream through once
+__device__ __forceinline__ void tma_load_2d_pair_hint(uint32_t dst_smem, const CUtensorMap* m, uint32_t bar,
+                                                      int32_t c0, int32_t c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_l2_2d_hint(const CUtensorMap* m, int32_t c0, int32_t c1, uint64_t policy) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.L2::cache_hint [%0, {%1, %2}], %3;"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "l"(policy)
+               : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int32_t c0, int32_t c1) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
