@@ -51,3 +51,9 @@ def goldens_mm():
 def goldens_unimodal():
     path = os.path.join(ROOT, "tests", "golden", "reference_goldens_unimodal.pt")
     return torch.load(path, map_location="cpu", weights_only=False)
+
+
+@pytest.fixture(scope="session")
+def goldens_losses():
+    path = os.path.join(ROOT, "tests", "golden", "reference_goldens_losses.pt")
+    return torch.load(path, map_location="cpu", weights_only=False)
