@@ -294,6 +294,14 @@ int mmf_dense_bwd(const float* x, int64_t ldx, const float* W, int B, int in_dim
 int mmf_kron_enc_fwd(const float* const* o /*HOST array of m device ptrs [B,E]*/, int m, int E, int B,
                      const float* W /*[H,E^m]*/, const float* b, int H, float* out /*[B,H]*/,
                      void* stream);
+/* Train-mode form: Dropout(0.25) on the (never materialised) product — element (b, kk) kept iff the counter hash of
+ * (seed, stream 3, b, kk) says so, scaled by 1/0.75 (XlinearFusion.post_fusion_dropout, models/model_modules.py:170);
+ * the backward regenerates the mask from the same seed. dropout = 0: identical to mmf_kron_enc_fwd / _bwd. */
+int mmf_kron_enc_train_fwd(const float* const* o, int m, int E, int B, const float* W, const float* b, int H,
+                           int dropout, uint64_t seed, float* out, void* stream);
+int mmf_kron_enc_train_bwd(const float* const* o, int m, int E, int B, const float* W, int H, int dropout,
+                           uint64_t seed, const float* out, const float* dout, float* const* d_o, float* dW,
+                           float* db, void* workspace, size_t workspace_bytes, void* stream);
 /* workspace: B * E^m floats (the gradient w.r.t. the outer product, contracted immediately). */
 size_t mmf_kron_enc_workspace_bytes(int m, int E, int B);
 int mmf_kron_enc_bwd(const float* const* o, int m, int E, int B, const float* W, int H,

@@ -139,6 +139,8 @@ SIGNATURES = {
     "mmf_kron_enc_fwd": (_i, [_PP, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "mmf_kron_enc_workspace_bytes": (_sz, [_i, _i, _i]),
     "mmf_kron_enc_bwd": (_i, [_PP, _i, _i, _i, _vp, _i, _vp, _vp, _PP, _vp, _vp, _vp, _sz, _vp]),
+    "mmf_kron_enc_train_fwd": (_i, [_PP, _i, _i, _i, _vp, _vp, _i, _i, _u64, _vp, _vp]),
+    "mmf_kron_enc_train_bwd": (_i, [_PP, _i, _i, _i, _vp, _i, _i, _u64, _vp, _vp, _PP, _vp, _vp, _vp, _sz, _vp]),
     "mmf_hazard_head_fwd": (_i, [_vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "mmf_hazard_head_bwd": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mmf_amil_head_nll_step": (_i, [_vp, _i64, _i, _vp, _vp, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp,

@@ -145,6 +145,25 @@ class KronEncoder(torch.autograd.Function):
         return (dW, db, *d_o)
 
 
+class KronEncoderTrain(torch.autograd.Function):
+    """KronEncoder with train-mode Dropout(0.25) on the outer product (XlinearFusion.post_fusion_dropout,
+    models/model_modules.py:170): the mask comes from the counter hash of (seed, stream 3, row, column) inside the
+    kernels — forward and backward — so the [B, 17^m] product is not materialised in training either."""
+
+    @staticmethod
+    def forward(ctx, W, b, seed: int, *o_list):
+        out = ops.kron_enc_fwd(o_list, W, b, dropout=True, seed=seed)
+        ctx.save_for_backward(W, out, *o_list)
+        ctx.seed = seed
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        W, out, *o_list = ctx.saved_tensors
+        d_o, dW, db = ops.kron_enc_bwd(o_list, W, out, dout, dropout=True, seed=ctx.seed)
+        return (dW, db, None, *d_o)
+
+
 class SegmentedLinearBf16(torch.autograd.Function):
     """y = cat(segs, 1) @ W^T + b on the bf16 tensor-core GEMM, the modality bags are read in place
     (radio reduce_dim: models/model_attention_mil_radio.py:81-82). Output bf16 feeds AmilPool."""

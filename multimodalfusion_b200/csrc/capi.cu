@@ -706,8 +706,13 @@ int mmf_dense_bwd(const float* x, int64_t ldx, const float* W, int B, int in_dim
 
 int mmf_kron_enc_fwd(const float* const* o, int m, int E, int B, const float* W, const float* b,
                      int H, float* out, void* stream) {
+  return mmf_kron_enc_train_fwd(o, m, E, B, W, b, H, 0, 0, out, stream);
+}
+
+int mmf_kron_enc_train_fwd(const float* const* o, int m, int E, int B, const float* W, const float* b,
+                           int H, int dropout, uint64_t seed, float* out, void* stream) {
   if (!o || m < 2 || m > 4 || E <= 0 || B <= 0 || !W || !out) return MMF_E_INVALID;
-  KronElem e{o[0], o[1], m >= 3 ? o[2] : nullptr, m >= 4 ? o[3] : nullptr, m, E};
+  KronElem e{o[0], o[1], m >= 3 ? o[2] : nullptr, m >= 4 ? o[3] : nullptr, m, E, seed, dropout ? 1 : 0};
   if (e.width() > (1ll << 30)) return MMF_E_INVALID;
   const int KK = (int)e.width();
   launch_sgemm(B, H, KK, LoadKronA{e}, LoadRowMajor{W, KK}, EpiBiasAct{out, H, b, MMF_ACT_RELU},
@@ -724,10 +729,16 @@ size_t mmf_kron_enc_workspace_bytes(int m, int E, int B) {
 int mmf_kron_enc_bwd(const float* const* o, int m, int E, int B, const float* W, int H,
                      const float* out, const float* dout, float* const* d_o, float* dW, float* db,
                      void* workspace, size_t workspace_bytes, void* stream) {
+  return mmf_kron_enc_train_bwd(o, m, E, B, W, H, 0, 0, out, dout, d_o, dW, db, workspace, workspace_bytes, stream);
+}
+
+int mmf_kron_enc_train_bwd(const float* const* o, int m, int E, int B, const float* W, int H, int dropout,
+                           uint64_t seed, const float* out, const float* dout, float* const* d_o, float* dW,
+                           float* db, void* workspace, size_t workspace_bytes, void* stream) {
   if (!o || m < 2 || m > 4 || !W || !out || !dout || !workspace) return MMF_E_INVALID;
   if (workspace_bytes < mmf_kron_enc_workspace_bytes(m, E, B)) return MMF_E_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
-  KronElem e{o[0], o[1], m >= 3 ? o[2] : nullptr, m >= 4 ? o[3] : nullptr, m, E};
+  KronElem e{o[0], o[1], m >= 3 ? o[2] : nullptr, m >= 4 ? o[3] : nullptr, m, E, seed, dropout ? 1 : 0};
   if (e.width() > (1ll << 30)) return MMF_E_INVALID;
   const int KK = (int)e.width();
   float* dkron = reinterpret_cast<float*>(workspace);

@@ -6,6 +6,7 @@
 // produced by loader functors, so activation derivatives, the hazard/cumprod chain rule and the
 // Kronecker outer product are formed on the fly instead of being materialised.
 #pragma once
+#include "amil_tile.cuh"   // counter-hash dropout bits (KronElem)
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
@@ -89,9 +90,21 @@ struct LoadDpreT {               // element (o, b): A(m=o, k=b): m contiguous
   }
 };
 // Kronecker product element kk of o_1 ⊗ o_2 (⊗ o_3 (⊗ o_4)) for sample b (first factor slowest).
+// drop != 0: train-mode Dropout(0.25) on the product (XlinearFusion.post_fusion_dropout, models/model_modules.py:170):
+// element (b, kk) is kept iff the counter hash of (seed, stream 3, row b, column kk) says so and scaled by 1 / 0.75 —
+// the same hash as the attention-MIL dropout (amil_tile.cuh), regenerated in the backward and by
+// oracle.dropout_scale_mask(seed, 3, B, E^m); the product is never materialised.
+constexpr uint32_t KRON_DROP_STREAM = 3;
 struct KronElem {
   const float* o0; const float* o1; const float* o2; const float* o3; int m; int E;
-  __device__ __forceinline__ float at(int b, int kk) const {
+  unsigned long long seed; int drop;
+  __device__ __forceinline__ float keep_scale(int b, int kk) const {
+    if (!drop) return 1.f;
+    return drop_keep(drop_bits16(drop_row_state(seed, KRON_DROP_STREAM, (uint32_t)b), (uint32_t)kk >> 4), (uint32_t)kk & 15u)
+               ? (1.0f / 0.75f) : 0.f;
+  }
+  __device__ __forceinline__ float at(int b, int kk) const { return raw(b, kk) * keep_scale(b, kk); }
+  __device__ __forceinline__ float raw(int b, int kk) const {
     if (m == 2) { const int i = kk / E, j = kk - i * E; return o0[b * E + i] * o1[b * E + j]; }
     if (m == 3) {
       const int i = kk / (E * E); const int r = kk - i * E * E; const int j = r / E, k = r - j * E;
@@ -247,7 +260,7 @@ __global__ void kron_contract_kernel(const float* __restrict__ dkron, KronElem e
   const int KK = (int)e.width();
   const float* row = dkron + (long long)b * KK;
   for (int kk = threadIdx.x; kk < KK; kk += blockDim.x) {
-    const float g = row[kk];
+    const float g = row[kk] * e.keep_scale(b, kk);   // d(product) = d(dropped product) x mask
     int i, j, k = 0, l = 0;
     if (m == 4) {
       const int E2 = E * E, ij = kk / E2, kl = kk - ij * E2;

@@ -13,7 +13,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import ops
-from ..autograd import BatchNorm1dFn, Dense, HighwayMix, KronEncoder
+from ..autograd import BatchNorm1dFn, Dense, HighwayMix, KronEncoder, KronEncoderTrain
 from .._lib import ACT_NONE, ACT_RELU, ACT_SELU, ACT_SIGMOID, ACT_TANH
 
 
@@ -284,8 +284,12 @@ class XlinearFusion(nn.Module):
             o = Dense.apply(z * h, blk[2][0].weight, blk[2][0].bias, ACT_RELU)
             o = blk[2][2](o)
             o_list.append(torch.cat([o, torch.ones(o.shape[0], 1, dtype=o.dtype, device=o.device)], dim=1))
-        if self.training and self.post_fusion_dropout.p > 0:
-            # dropout on the fused tensor needs it materialised: train-mode only (eval never does)
+        if self.training and self.post_fusion_dropout.p == 0.25:
+            # the reference's default rate: the mask is generated inside the encoder kernels (counter hash), the
+            # [B, 17^m] product is not materialised
+            out = KronEncoderTrain.apply(self.encoder1[0].weight, self.encoder1[0].bias, _seed_from_torch(), *o_list)
+        elif self.training and self.post_fusion_dropout.p > 0:
+            # any other rate: ATen dropout on the materialised product
             fused = o_list[0]
             for o in o_list[1:]:
                 fused = (fused.unsqueeze(2) * o.unsqueeze(1)).flatten(1)

@@ -343,19 +343,21 @@ def dense_bwd(x, W, act: int, y, dy, need_dx=True, need_dw=True, need_db=True):
     return dx, dW, db
 
 
-def kron_enc_fwd(o_list, W, b) -> torch.Tensor:
+def kron_enc_fwd(o_list, W, b, dropout: bool = False, seed: int = 0) -> torch.Tensor:
+    """relu(W (o_1 x o_2 [x o_3 [x o_4]]) + b); dropout: train-mode Dropout(0.25) on the (never materialised) product,
+    mask from the counter hash of (seed, stream 3, row, column)."""
     o_list = [_f32c(o) for o in o_list]
     _require_cuda(*o_list)
     B, E = o_list[0].shape
     H = W.shape[0]
     out = torch.empty(B, H, dtype=torch.float32, device=W.device)
     arr = _lib.ptr_array([o.data_ptr() for o in o_list])
-    check(lib().mmf_kron_enc_fwd(arr, len(o_list), E, B, _p(_f32c(W)), _p(_f32c(b)), H, _p(out), _stream()),
-          "mmf_kron_enc_fwd")
+    check(lib().mmf_kron_enc_train_fwd(arr, len(o_list), E, B, _p(_f32c(W)), _p(_f32c(b)), H, int(bool(dropout)), int(seed),
+                                       _p(out), _stream()), "mmf_kron_enc_train_fwd")
     return out
 
 
-def kron_enc_bwd(o_list, W, out, dout):
+def kron_enc_bwd(o_list, W, out, dout, dropout: bool = False, seed: int = 0):
     o_list = [_f32c(o) for o in o_list]
     W, out, dout = _f32c(W), _f32c(out), _f32c(dout)
     B, E = o_list[0].shape
@@ -368,8 +370,8 @@ def kron_enc_bwd(o_list, W, out, dout):
     ws = torch.empty(nbytes, dtype=torch.uint8, device=W.device)
     arr = _lib.ptr_array([o.data_ptr() for o in o_list])
     darr = _lib.ptr_array([o.data_ptr() for o in d_o])
-    check(lib().mmf_kron_enc_bwd(arr, m, E, B, _p(W), H, _p(out), _p(dout), darr, _p(dW), _p(db), _p(ws),
-                                 nbytes, _stream()), "mmf_kron_enc_bwd")
+    check(lib().mmf_kron_enc_train_bwd(arr, m, E, B, _p(W), H, int(bool(dropout)), int(seed), _p(out), _p(dout), darr,
+                                       _p(dW), _p(db), _p(ws), nbytes, _stream()), "mmf_kron_enc_train_bwd")
     return d_o, dW, db
 
 

@@ -256,9 +256,10 @@ def snn_forward(x, layers: List[Tuple[torch.Tensor, torch.Tensor]]):
     return x
 
 
-def xfusion_forward(v_list, reduce_params, enc1, enc2, skip=True):
+def xfusion_forward(v_list, reduce_params, enc1, enc2, skip=True, fused_scale=None):
     """XlinearFusion.forward in eval mode, gate=1, use_bilinear=0 (models/model_modules.py:156-178).
-    reduce_params[i] = ((Wh,bh),(Wz,bz),(Wo,bo)); enc1/enc2 = (W,b)."""
+    reduce_params[i] = ((Wh,bh),(Wz,bz),(Wo,bo)); enc1/enc2 = (W,b). fused_scale: optional [B, E^m] inverted-dropout
+    scale mask of post_fusion_dropout (models/model_modules.py:170; dropout_scale_mask(seed, 3, B, E^m))."""
     v_cat = torch.cat(v_list, dim=1)
     o_list = []
     for v, ((Wh, bh), (Wz, bz), (Wo, bo)) in zip(v_list, reduce_params):
@@ -269,6 +270,8 @@ def xfusion_forward(v_list, reduce_params, enc1, enc2, skip=True):
     fused = o_list[0]
     for o in o_list[1:]:
         fused = (fused[:, :, None] * o[:, None, :]).flatten(1)
+    if fused_scale is not None:
+        fused = fused * fused_scale
     out = torch.relu(fused @ enc1[0].t() + enc1[1])
     if skip:
         out = torch.cat([out] + list(v_list), dim=1)

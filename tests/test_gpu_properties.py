@@ -139,3 +139,52 @@ def test_config3_kronecker_head_cohort_512_exact_risk_ordering(dev):
         assert torch.equal(torch.argsort(r), order)
     assert abs(O.concordance_index(r, times, 1 - c) - O.concordance_index(risk_ref, times, 1 - c)) < 1e-6
     assert torch.isfinite(hp_d.grad).all() and torch.isfinite(ho_d.grad).all()
+
+
+@pytest.mark.parametrize("m,B", [(2, 33), (3, 64), (4, 5)])
+def test_kron_encoder_train_mode_dropout_in_kernel_vs_oracle(dev, m, B):
+    """Train-mode post_fusion_dropout without materialising the product: forward and all gradients against the oracle
+    with the regenerated mask (oracle.dropout_scale_mask(seed, 3, B, 17^m)); eval form unchanged (dropout = 0)."""
+    from multimodalfusion_b200 import ops
+    E, H, seed = 17, 96, 0xABCDE + m
+    g = torch.Generator().manual_seed(m * 100 + B)
+    o_list = [torch.rand(B, E, generator=g) for _ in range(m)]
+    W = torch.randn(H, E ** m, generator=g) * (2.0 / E ** m) ** 0.5
+    b = torch.randn(H, generator=g) * 0.1
+    dout = torch.randn(B, H, generator=g)
+    mask = O.dropout_scale_mask(seed, 3, B, E ** m)
+    leaves = [o.clone().requires_grad_(True) for o in o_list]
+    Wl, bl = W.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    fused = leaves[0]
+    for o in leaves[1:]:
+        fused = (fused[:, :, None] * o[:, None, :]).flatten(1)
+    out_ref = torch.relu((fused * mask) @ Wl.t() + bl)
+    out_ref.backward(dout)
+    od = [o.to(dev) for o in o_list]
+    out = ops.kron_enc_fwd(od, W.to(dev), b.to(dev), dropout=True, seed=seed)
+    assert rel_err(out, out_ref) < 1e-5
+    d_o, dW, db = ops.kron_enc_bwd(od, W.to(dev), out, dout.to(dev), dropout=True, seed=seed)
+    assert rel_err(dW, Wl.grad) < 1e-5 and rel_err(db, bl.grad) < 1e-5
+    for got, leaf in zip(d_o, leaves):
+        assert rel_err(got, leaf.grad) < 1e-5
+    keep = (mask > 0).float().mean().item()
+    assert 0.70 < keep < 0.80
+    out0 = ops.kron_enc_fwd(od, W.to(dev), b.to(dev))
+    fused0 = o_list[0]
+    for o in o_list[1:]:
+        fused0 = (fused0[:, :, None] * o[:, None, :]).flatten(1)
+    assert rel_err(out0, torch.relu(fused0 @ W.t() + b)) < 1e-5
+
+
+def test_xlinear_fusion_train_mode_runs_without_materialising(dev):
+    """XlinearFusion in train mode (default dropout 0.25): forward + backward finite, deterministic under manual_seed, and
+    different from eval mode."""
+    from multimodalfusion_b200.models.model_modules import XlinearFusion
+    torch.manual_seed(4)
+    xf = XlinearFusion(num_modalities=3).to(dev).train()
+    v = [torch.randn(16, 256, device=dev, requires_grad=True) for _ in range(3)]
+    torch.manual_seed(9); out1 = xf([t for t in v]); out1.sum().backward()
+    g1 = v[0].grad.clone()
+    torch.manual_seed(9); out2 = xf([t for t in v])
+    assert torch.isfinite(out1).all() and torch.isfinite(g1).all() and torch.equal(out1, out2)
+    assert not torch.equal(xf.eval()([t for t in v]), out1)
