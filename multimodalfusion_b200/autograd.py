@@ -33,7 +33,9 @@ class AmilPool(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, W1, b1, Wa, ba, Wb, bb, wc, bc, prep, flags: int, seed: int, group=None):
         ctx.set_materialize_grads(False)
-        if AmilPool.precise_small_bags and 0 < x.shape[0] <= ops.PRECISE_FC_MAX_ROWS:
+        # (an instance-sharded bag runs the plain bf16 path on every rank: the choice must not depend on the size of the
+        #  local shard, or the ranks of one bag — and the whole-bag run it is compared with — would mix two arithmetics)
+        if group is None and AmilPool.precise_small_bags and 0 < x.shape[0] <= ops.PRECISE_FC_MAX_ROWS:
             xb = ops.split_bag(x)
             flags |= MMF_PRECISE_FC
         else:

@@ -37,9 +37,13 @@ def main():
         x = (0.5 * torch.randn(N, 1024, generator=g).abs()).to(torch.bfloat16).to(dev)
         Y, c = torch.tensor([1], device=dev), torch.tensor([0.0], device=dev)
         loss_fn = NLLSurvLoss(alpha=0.0)
-        # whole bag on every rank (reference for the sharded run)
+        # whole bag on every rank (reference for the sharded run), in the arithmetic the sharded path uses: plain bf16
+        # operands at every size (a whole bag of <= 4096 instances would otherwise take the split-precision fc)
+        from multimodalfusion_b200.autograd import AmilPool
+        AmilPool.precise_small_bags = False
         hz, S, _, A = model(path_features=x)
         loss_fn(hazards=hz, S=S, Y=Y, c=c).backward()
+        AmilPool.precise_small_bags = True
         ref = {n: p.grad.clone() for n, p in model.named_parameters()}
         model.zero_grad(set_to_none=True)
         # sharded
