@@ -1,0 +1,67 @@
+"""Shared implementation of ``fused_step`` for the models whose pooled embedding feeds a linear classifier directly
+(path and radiology attention-MIL survival models): model -> nll_surv -> backward of utils/core_utils.py:200-247 as the
+library's three-launch step (mmf_amil_fwd_train_head + mmf_amil_bwd_head), gradients written into the parameters' ``.grad``."""
+import torch
+
+from .. import ops
+from .model_modules import AmilBranch, _seed_from_torch
+
+
+def enable(model, seq, classifier):
+    """ONE flat fp32 gradient buffer for the fc / attention / classifier parameters; every ``.grad`` becomes a view of it
+    (the layout the step's kernels accumulate into). Returns the flat buffer."""
+    fc, attn = seq[0], seq[3]
+    Wa, ba, Wb, bb, wc, bc = attn.amil_weights()
+    order = [fc.weight, fc.bias, Wa] + ([Wb] if Wb is not None else []) + [ba] + ([bb] if bb is not None else []) \
+        + [wc, bc, classifier.weight, classifier.bias]
+    dev = fc.weight.device
+    if dev.type != "cuda":
+        raise RuntimeError("enable_fused_step needs the model on a CUDA device (no CPU fallback)")
+    n = sum(p.numel() for p in order)
+    flat = torch.zeros((n + 3) // 4 * 4, dtype=torch.float32, device=dev)
+    o = 0
+    for p_ in order:
+        p_.grad = flat[o:o + p_.numel()].view_as(p_)
+        o += p_.numel()
+    L, D = fc.weight.shape[0], Wa.shape[0]
+    KD = D * (2 if Wb is not None else 1)
+    state = dict(flat=flat, L=L, D=D, KD=KD, gated=Wb is not None, bufs={})
+    g, o = {}, 0
+    for name, cnt, shape in (("dW1", L * 1024, (L, 1024)), ("db1", L, (L,)), ("dWab", KD * L, (KD, L)),
+                             ("dbab", KD, (KD,)), ("dwc", D, (D,)), ("dbc", 1, (1,))):
+        g[name] = flat[o:o + cnt].view(shape)
+        o += cnt
+    K = classifier.weight.shape[0]
+    state.update(grads=g, dWk=flat[o:o + K * L].view(K, L), dbk=flat[o + K * L:o + K * L + K])
+    model._fused = state
+    return flat
+
+
+def run(model, seq, classifier, bag, Y, c, alpha, loss_scale, accumulate, eps, need_dx=False):
+    """One step on `bag` ([N,1024], fp32 or bf16). Returns (hazards, S, Y_hat, A_raw [1,N], loss, dx or None)."""
+    f = model._fused
+    prep = AmilBranch.prepared(seq)
+    N = bag.shape[0]
+    if N > 65536:
+        raise NotImplementedError("fused_step merges at most 512 per-tile head rows per CTA (N <= 65536)")
+    attn = seq[3]
+    flags = ops.amil_flags(prep.gated, dropout_h=model.training, dropout_attn=model.training and attn.use_dropout)
+    if N <= ops.PRECISE_FC_MAX_ROWS:      # small bag: split-precision fc (see autograd.AmilPool)
+        x = ops.split_bag(bag)
+        flags |= ops.MMF_PRECISE_FC
+    else:
+        x = ops.to_bf16(bag)
+    seed = _seed_from_torch() if model.training else 0
+    K = classifier.weight.shape[0]
+    buf = f["bufs"].get(N)
+    if buf is None:
+        if len(f["bufs"]) >= 4:     # bags come in many sizes: keep a few workspaces, not one per size
+            f["bufs"].pop(next(iter(f["bufs"])))
+        buf = f["bufs"][N] = ops.FusedStepBuffers(N, prep, flags, K, x.device)
+    Yd = Y.detach().reshape(-1).to(device=x.device, dtype=torch.int64)
+    cd = c.detach().reshape(-1).to(device=x.device, dtype=torch.float32)
+    dx = torch.empty(N, 1024, dtype=torch.bfloat16, device=x.device) if need_dx else None
+    ops.amil_fused_step(x, prep, flags, seed, buf, classifier.weight.detach(), classifier.bias.detach(),
+                        Yd, cd, alpha, f["grads"], dWk=f["dWk"], dbk=f["dbk"], eps=eps, loss_scale=loss_scale,
+                        zero=None if accumulate else f["flat"], dx=dx)
+    return buf.hazards, buf.S, buf.Y_hat, buf.A_raw.view(1, -1), buf.loss, dx

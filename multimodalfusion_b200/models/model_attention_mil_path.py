@@ -54,32 +54,8 @@ class MIL_Attention_fc_surv_path(MIL_Attention_fc_path):
         """Allocates ONE flat fp32 gradient buffer and makes every parameter's ``.grad`` a view of it (the layout the
         fused step's kernels accumulate into; ``optimizer.zero_grad(set_to_none=False)`` / ``FusedAdam`` keep the
         views). Call after ``.cuda()`` / ``relocate()``."""
-        from .. import ops
-        fc, attn = self.attention_net_WSI[0], self.attention_net_WSI[3]
-        Wa, ba, Wb, bb, wc, bc = attn.amil_weights()
-        order = [fc.weight, fc.bias, Wa] + ([Wb] if Wb is not None else []) + [ba] + ([bb] if bb is not None else []) \
-            + [wc, bc, self.classifier.weight, self.classifier.bias]
-        dev = fc.weight.device
-        if dev.type != "cuda":
-            raise RuntimeError("enable_fused_step needs the model on a CUDA device (no CPU fallback)")
-        n = sum(p.numel() for p in order)
-        flat = torch.zeros((n + 3) // 4 * 4, dtype=torch.float32, device=dev)
-        o = 0
-        for p_ in order:
-            p_.grad = flat[o:o + p_.numel()].view_as(p_)
-            o += p_.numel()
-        L, D = fc.weight.shape[0], Wa.shape[0]
-        KD = D * (2 if Wb is not None else 1)
-        self._fused = dict(flat=flat, L=L, D=D, KD=KD, gated=Wb is not None, bufs={})
-        g = {}
-        o = 0
-        for name, cnt, shape in (("dW1", L * 1024, (L, 1024)), ("db1", L, (L,)), ("dWab", KD * L, (KD, L)),
-                                 ("dbab", KD, (KD,)), ("dwc", D, (D,)), ("dbc", 1, (1,))):
-            g[name] = flat[o:o + cnt].view(shape)
-            o += cnt
-        K = self.classifier.weight.shape[0]
-        self._fused.update(grads=g, dWk=flat[o:o + K * L].view(K, L), dbk=flat[o + K * L:o + K * L + K])
-        return flat
+        from . import _fused_step
+        return _fused_step.enable(self, self.attention_net_WSI, self.classifier)
 
     def fused_step(self, path_features, Y, c, alpha=0.0, loss_scale=1.0, accumulate=False, eps=1e-7):
         """``hazards, S, Y_hat, A_raw = model(path_features=x); loss = nll_surv(...); (loss * loss_scale).backward()``
@@ -89,38 +65,13 @@ class MIL_Attention_fc_surv_path(MIL_Attention_fc_path):
         first inside the forward kernel (``optimizer.zero_grad()``), ``True`` adds (gradient accumulation over ``gc``
         bags, ``loss_scale = 1 / gc``). Train mode only; bags of up to 65536 instances; returns
         (hazards [1,K], S [1,K], Y_hat [1,1], A_raw [1,N], loss) — views of buffers reused by the next call."""
-        from .. import ops
-        from .model_modules import AmilBranch, _seed_from_torch
+        from . import _fused_step
         if not hasattr(self, "_fused"):
             self.enable_fused_step()
         if self.bag_group is not None:
             raise NotImplementedError("fused_step runs whole bags; instance-sharded bags go through forward()")
-        f = self._fused
-        seq = self.attention_net_WSI
-        prep = AmilBranch.prepared(seq)
-        N = path_features.shape[0]
-        if N > 65536:
-            raise NotImplementedError("fused_step merges at most 512 per-tile head rows per CTA (N <= 65536)")
-        attn = seq[3]
-        flags = ops.amil_flags(prep.gated, dropout_h=self.training, dropout_attn=self.training and attn.use_dropout)
-        if N <= ops.PRECISE_FC_MAX_ROWS:      # small bag: split-precision fc (see autograd.AmilPool)
-            x = ops.split_bag(path_features)
-            flags |= ops.MMF_PRECISE_FC
-        else:
-            x = ops.to_bf16(path_features)
-        seed = _seed_from_torch() if self.training else 0
-        K = self.classifier.weight.shape[0]
-        buf = f["bufs"].get(N)
-        if buf is None:
-            if len(f["bufs"]) >= 4:     # bags come in many sizes: keep a few workspaces, not one per size
-                f["bufs"].pop(next(iter(f["bufs"])))
-            buf = f["bufs"][N] = ops.FusedStepBuffers(N, prep, flags, K, x.device)
-        Yd = Y.detach().reshape(-1).to(device=x.device, dtype=torch.int64)
-        cd = c.detach().reshape(-1).to(device=x.device, dtype=torch.float32)
-        ops.amil_fused_step(x, prep, flags, seed, buf, self.classifier.weight.detach(), self.classifier.bias.detach(),
-                            Yd, cd, alpha, f["grads"], dWk=f["dWk"], dbk=f["dbk"], eps=eps, loss_scale=loss_scale,
-                            zero=None if accumulate else f["flat"])
-        return buf.hazards, buf.S, buf.Y_hat, buf.A_raw.view(1, -1), buf.loss
+        return _fused_step.run(self, self.attention_net_WSI, self.classifier, path_features, Y, c, alpha, loss_scale,
+                               accumulate, eps)[:5]
 
     @torch.no_grad()
     def infer_cohort(self, bags):

@@ -79,3 +79,57 @@ class MIL_Attention_fc_surv_radio(MIL_Attention_fc_radio):
             return A_raw
         hazards, S, Y_hat = HazardHead.apply(M, self.classifier.weight, self.classifier.bias)
         return hazards, S, Y_hat, A_raw
+
+    # ---- fused batch-1 training step (utils/core_utils.py:200-247; radio loop :184-247) ------------------------------
+    def enable_fused_step(self):
+        """As MIL_Attention_fc_surv_path.enable_fused_step; reduce_dim keeps ordinary ``.grad`` tensors (16.8 MB: too large
+        to be cleared by the two tile CTAs of a 155-slice bag)."""
+        from . import _fused_step
+        flat = _fused_step.enable(self, self.attention_net_radio, self.classifier)
+        if hasattr(self, "reduce_dim"):
+            for p_ in self.reduce_dim.parameters():
+                p_.grad = torch.zeros_like(p_)
+        return flat
+
+    def fused_step(self, Y, c, alpha=0.0, loss_scale=1.0, accumulate=False, eps=1e-7, **bags):
+        """One patient of the reference's batch-1 radiology loop without an autograd graph: ``model(T1=.., T2=.., ...)`` ->
+        nll_surv -> ``(loss * loss_scale).backward()`` as reduce_dim (one fp32 functor-SGEMM launch on the concatenated
+        slices) + the library's fused step on the reduced bag (3 launches + the dx GEMM) + reduce_dim's weight gradient
+        (one launch, accumulated in place): ~9 launches per patient instead of ~40 through autograd. ``radio_fusion=
+        'concat'`` (or a single modality) and bags of up to 4096 slices; returns (hazards, S, Y_hat, A_raw, loss)."""
+        from .. import ops
+        from .._lib import ACT_NONE
+        from . import _fused_step
+        if not hasattr(self, "_fused"):
+            self.enable_fused_step()
+        if self.bag_group is not None:
+            raise NotImplementedError("fused_step runs whole bags; instance-sharded bags go through forward()")
+        xs = [bags[m] for m in self.modalities]
+        from ..autograd import AmilPool
+        if AmilPool.precise_small_bags and xs[0].shape[0] <= AmilBranch.TINY_BAG_FP32_ROWS:
+            # tiny bags (real radiology patients: 17-40 slices) keep the exact-fp32 kernels of forward() — a pooled
+            # embedding exact to fp32 keeps every ReLU unit on the reference's side (model_modules.AmilBranch) — through
+            # the autograd.Functions; same gradient buffers, same return values
+            from ..utils.loss_utils import nll_loss
+            if not accumulate:
+                self.zero_grad(set_to_none=False)
+            hz, S, Y_hat, A_raw = self(**bags)
+            loss = nll_loss(hz, S, Y, c, alpha=alpha, eps=eps)
+            (loss * loss_scale).backward()
+            return hz.detach(), S.detach(), Y_hat, A_raw.detach(), loss.detach()
+        if len(xs) == 1:
+            return _fused_step.run(self, self.attention_net_radio, self.classifier, xs[0], Y, c, alpha, loss_scale,
+                                   accumulate, eps)[:5]
+        if self.radio_fusion != 'concat' or xs[0].shape[0] > ops.PRECISE_FC_MAX_ROWS:
+            raise NotImplementedError("fused_step: radio_fusion='concat' with at most 4096 slices; use forward() + autograd")
+        Wr, br = self.reduce_dim.weight, self.reduce_dim.bias
+        xc = torch.cat([b.float() for b in xs], dim=1)                         # [N, 1024 m]
+        h0 = ops.dense_fwd(xc, Wr.detach(), br.detach(), ACT_NONE)             # reduce_dim, fp32 (models/...radio.py:81-82)
+        out = _fused_step.run(self, self.attention_net_radio, self.classifier, h0, Y, c, alpha, loss_scale, accumulate,
+                              eps, need_dx=True)
+        if not accumulate:
+            Wr.grad.zero_(); br.grad.zero_()
+        # dWr += dh0^T xc, dbr += colsum(dh0): accumulated in place by the functor SGEMM
+        ops.dense_bwd_into(xc, Wr.detach(), h0, out[5].float(), Wr.grad, br.grad)
+        return out[:5]
+

@@ -343,6 +343,17 @@ def dense_bwd(x, W, act: int, y, dy, need_dx=True, need_dw=True, need_db=True):
     return dx, dW, db
 
 
+def dense_bwd_into(x, W, y, dy, dW: torch.Tensor, db: torch.Tensor) -> None:
+    """Weight / bias gradient of y = x W^T + b ACCUMULATED into the caller's dW [out,in] and db [out] (no dx)."""
+    x, W, y, dy = _f32c(x), _f32c(W), _f32c(y), _f32c(dy)
+    B, in_dim = x.shape
+    out_dim = W.shape[0]
+    if not (dW.is_contiguous() and db.is_contiguous() and dW.dtype == torch.float32):
+        raise ValueError("dense_bwd_into needs contiguous fp32 gradient tensors")
+    check(lib().mmf_dense_bwd(_p(x), in_dim, _p(W), B, in_dim, out_dim, ACT_NONE, _p(y), out_dim, _p(dy), out_dim,
+                              None, in_dim, 0, _p(dW), _p(db), _stream()), "mmf_dense_bwd")
+
+
 def kron_enc_fwd(o_list, W, b, dropout: bool = False, seed: int = 0) -> torch.Tensor:
     """relu(W (o_1 x o_2 [x o_3 [x o_4]]) + b); dropout: train-mode Dropout(0.25) on the (never materialised) product,
     mask from the counter hash of (seed, stream 3, row, column)."""
@@ -459,12 +470,13 @@ class FusedStepBuffers:
 
 def amil_fused_step(x: torch.Tensor, w: AmilPrepared, flags: int, seed: int, buf: FusedStepBuffers, Wk, bk, Y, c,
                     alpha: float, grads: dict, dWk=None, dbk=None, eps: float = 1e-7, loss_scale: float = 1.0,
-                    zero: Optional[torch.Tensor] = None, repack_head: bool = True):
+                    zero: Optional[torch.Tensor] = None, repack_head: bool = True, dx: Optional[torch.Tensor] = None):
     """One batch-1 training step of the path / radio AMIL model in THREE launches: fused forward (+ z = Wk h and the
     ReLU mask words), fused gate + hidden backward whose prologue runs the head (combine, classifier, hazards,
     nll_surv, dlogits, dM, dWk, dbk) and whose phase A is head-projected, grouped wgrad GEMM. N <= 65536. Gradients accumulate into `grads` (dW1, db1, dWab, dbab, dwc,
     dbc), dWk, dbk; `zero` (the flat gradient buffer that holds them all) is cleared by the forward first.
-    Outputs are left in `buf` (loss, hazards, S, Y_hat, A_raw, M)."""
+    Outputs are left in `buf` (loss, hazards, S, Y_hat, A_raw, M). dx: optional bf16 [N,1024] output, the gradient w.r.t.
+    the bag (a layer sits upstream: the radiology models' reduce_dim) — one more pair-GEMM launch."""
     _require_cuda(x, Wk)
     _check_bag(x, flags)
     N = x.shape[0]
@@ -480,8 +492,9 @@ def amil_fused_step(x: torch.Tensor, w: AmilPrepared, flags: int, seed: int, buf
           "mmf_amil_fwd_train_head")
     g = AmilGrads(_p(grads["dW1"]), _p(grads["db1"]), _p(grads["dWab"]), _p(grads["dbab"]),
                   _p(grads["dwc"]), _p(grads["dbc"]))
-    check(lib().mmf_amil_bwd_head(_p(x), N, x.stride(0), C.byref(wst), w.L, w.D, flags | MMF_STASHED, seed, _p(buf.A_raw),
-                                  _p(buf.partials), C.byref(head), None, C.byref(g), None, buf.workspace.data_ptr(),
+    bflags = flags | MMF_STASHED | (MMF_NEED_DX if dx is not None else 0)
+    check(lib().mmf_amil_bwd_head(_p(x), N, x.stride(0), C.byref(wst), w.L, w.D, bflags, seed, _p(buf.A_raw),
+                                  _p(buf.partials), C.byref(head), None, C.byref(g), _p(dx), buf.workspace.data_ptr(),
                                   buf.workspace.numel(), _stream()), "mmf_amil_bwd_head")
     return buf.loss
 

@@ -207,3 +207,34 @@ def test_fused_step_full_size_with_dropout_vs_fp32_oracle(dev, N, L, D):
     for k in ("dW1", "db1", "dWab", "dbab", "dwc"):
         assert rel_err(grads[k], go[k]) < TOL_GRAD_REF, k
     assert rel_err(dWk, Wr.grad) < TOL_GRAD_REF and rel_err(dbk, br.grad) < TOL_GRAD_REF
+
+
+@pytest.mark.parametrize("N,gate", [(17, True), (80, True), (155, True), (131, False)])
+def test_radio_fused_step_matches_autograd_path(dev, N, gate):
+    """MIL_Attention_fc_surv_radio.fused_step (reduce_dim + the fused 3-launch step with dx + reduce_dim wgrad, no
+    autograd graph) == model(**bags) -> NLLSurvLoss -> backward through the autograd.Functions (eval mode: no dropout)."""
+    from multimodalfusion_b200.models import MIL_Attention_fc_surv_radio
+    from multimodalfusion_b200.utils import NLLSurvLoss
+    torch.manual_seed(21)
+    model = MIL_Attention_fc_surv_radio(gate_radio=gate, dropout=True, n_classes=4).to(dev).eval()
+    bags = {m: cases.features(N, 300 + i).to(dev) for i, m in enumerate(model.modalities)}
+    Y, c = torch.tensor([2], device=dev), torch.tensor([0.0], device=dev)
+    hz, S, Y_hat, A = model(**bags)
+    loss = NLLSurvLoss(alpha=0.15)(hazards=hz, S=S, Y=Y, c=c)
+    (loss * 0.5).backward()
+    ref = {n: p.grad.clone() for n, p in model.named_parameters()}
+    model.zero_grad(set_to_none=True)
+    model.enable_fused_step()
+    for rep in range(2):     # the second call must not accumulate
+        hz2, S2, Y2, A2, loss2 = model.fused_step(Y=Y, c=c, alpha=0.15, loss_scale=0.5, **bags)
+    assert rel_err(hz2, hz) < 2e-3 and rel_err(A2, A) < 2e-3 and abs(loss2.item() - loss.item()) < 2e-3 * max(1, abs(loss.item()))
+    assert torch.equal(Y2.cpu(), Y_hat.cpu())
+    for n, p in model.named_parameters():
+        if n.endswith("attention_c.bias"):
+            continue   # sum_i ds_i: exactly 0 in exact arithmetic, rounding residue on both sides
+        assert close(p.grad, ref[n], 2e-2), n
+    # accumulation over a gc window of two patients
+    model.fused_step(Y=Y, c=c, alpha=0.15, loss_scale=0.5, accumulate=True, **bags)
+    for n, p in model.named_parameters():
+        if not n.endswith("attention_c.bias"):
+            assert close(p.grad, 2 * ref[n], 2e-2), n

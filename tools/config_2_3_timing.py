@@ -36,6 +36,28 @@ t0 = time.perf_counter(); radio_epoch(256); torch.cuda.synchronize(); dt = time.
 print(json.dumps({"config": "2 radio_attention_mil batch-1 training loop", "patients": 256, "ms_per_patient": dt / 256 * 1e3,
                   "patients_per_s": 256 / dt, "slices_per_s": sum(ns) / dt,
                   "note": "eager launches from Python (fwd + loss + bwd + fused Adam per patient), wall clock incl. host"}))
+# ---- config 2 through the fused step (no autograd graph): reduce_dim + 3-launch step + dx GEMM + reduce_dim wgrad + Adam
+model.enable_fused_step()
+opt = get_optim(model, args)
+
+
+def radio_epoch_fused(count):
+    for i in range(count):
+        model.fused_step(Y=Y, c=c, alpha=0.0, **bags[i % len(bags)])
+        opt.step(zero_grad=False)     # (the next fused step clears the gradients inside its forward kernel)
+
+
+radio_epoch_fused(8)
+torch.cuda.synchronize()
+t0 = time.perf_counter(); radio_epoch_fused(256); torch.cuda.synchronize(); dt = time.perf_counter() - t0
+# launches per patient, counted with the profiler's kernel events of 4 patients
+from torch.profiler import profile, ProfilerActivity
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    radio_epoch_fused(4); torch.cuda.synchronize()
+launches = sum(e.count for e in prof.key_averages() if e.device_type.name == "CUDA") / 4
+print(json.dumps({"config": "2 radio_attention_mil batch-1 training loop, fused_step", "patients": 256, "ms_per_patient": dt / 256 * 1e3,
+                  "patients_per_s": 256 / dt, "kernel_launches_per_patient": launches,
+                  "note": "MIL_Attention_fc_surv_radio.fused_step + fused Adam per patient, eager launches from Python, wall clock incl. host"}))
 # ---- config 3
 B = 512
 head = cox_heads.multimodal_pretrained(mode="radio_path_omic", train_type="kronecker", n_classes=4).to(dev).train()
