@@ -57,6 +57,8 @@ struct AmilArgs {
   const float* head_wk;  // classifier.weight fp32 [head_k, L]
   int head_k;
   int flags;
+  const void* x_bulk;  // fwd (optional): the bag itself when its rows are contiguous (ldx == row width): this CTA's tile is then
+                      // one contiguous block that a single cp.async.bulk.prefetch.L2 requests before griddepcontrol.wait
   int kb1;            // 64-wide k-blocks of GEMM1 (0 = 16: x is [N,1024]; 48: [N,3072] = [x_hi | x_lo | x_hi], MMF_PRECISE_FC)
   unsigned long long seed;
   // backward only

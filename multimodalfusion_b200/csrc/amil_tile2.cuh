@@ -64,6 +64,10 @@ struct Amil2Cfg {
 // MMF_TILE2_CHUNK_STAMPS = 1 (debug build, tools/phase_chunks.py): stamps 2 / 3 / 4 = "GEMM2 chunk c accumulators seen" and
 // 5 / 9 / 15 = "chunk c gate epilogue done" (epilogue thread 0) replace the producer / first-stage / vectors-staged stamps
 // MMF_L2_HINTS (mmf_ptx.cuh): >= 1 evict_first on the x stream (forward and wgrad)
+// MMF_X_BULK_PREFETCH = 1 (A/B candidate): this CTA's x tile requested with one bulk L2 prefetch BEFORE griddepcontrol.wait
+#ifndef MMF_X_BULK_PREFETCH
+#define MMF_X_BULK_PREFETCH 0
+#endif
 #ifndef MMF_TILE2_CHUNK_STAMPS
 #define MMF_TILE2_CHUNK_STAMPS 0
 #endif
@@ -107,6 +111,16 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   griddep_launch_dependents();   // PDL: the next kernel's prologue may overlap this kernel's tail
   if (threadIdx.x == 0) {
     MMF_STAMP(a, 0);
+    if (MMF_X_BULK_PREFETCH && a.x_bulk != nullptr && row0 < a.N) {
+      // This CTA's x tile is requested from HBM NOW, before griddepcontrol.wait, with ONE bulk prefetch: the bag is an
+      // input of the step, not an output of the preceding kernel (and an L2 prefetch of a line somebody is still writing is
+      // harmless — L2 is the point of coherence), so its HBM latency overlaps the predecessor's tail, the launch gap and this
+      // prologue (GEMM1 took 21.6k cycles inside the step against 16.4k at the tensor peak, gpurun_out/r2i_instep_fwd.log)
+      const long long rows = min((long long)128, a.N - row0);
+      const uint32_t row_bytes = (uint32_t)(a.kb1 > 0 ? a.kb1 : C::KB1) * 128u;
+      bulk_prefetch_l2_hint(reinterpret_cast<const uint8_t*>(a.x_bulk) + row0 * row_bytes, (uint32_t)rows * row_bytes,
+                            l2_policy_evict_first());
+    }
     for (int s = 0; s < C::NS1; ++s) { mbar_init(smem_u32(&bar_full1[s]), 1); mbar_init(smem_u32(&bar_empty1[s]), 1); }
     for (int s = 0; s < C::NS2; ++s) { mbar_init(smem_u32(&bar_full2[s]), 1); mbar_init(smem_u32(&bar_empty2[s]), 1); }
     mbar_init(smem_u32(&bar_acc1), 1);
@@ -148,7 +162,7 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       // the ring's first NS1 loads go out first; only then is the rest of this CTA's x tile prefetched
       // into L2 (issuing all 16 prefetches up front queued the first real load behind them:
       // first stage landed 8k cycles after the cluster sync)
-      if (kb == C::NS1)
+      if (kb == C::NS1 && !(MMF_X_BULK_PREFETCH && a.x_bulk != nullptr))
         for (int kp = C::NS1; kp < kb1; ++kp) {
           if (MMF_L2_HINTS) tma_prefetch_l2_2d_hint(&tmX, kp * 64, (int)row0, pol_x);
           else tma_prefetch_l2_2d(&tmX, kp * 64, (int)row0);

@@ -155,6 +155,7 @@ int launch_amil2v(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w
   const int pairs = (int)((N + 255) / 256);
   AmilArgs a2 = a;
   a2.kb1 = (int)(kin / 64);
+  a2.x_bulk = ((uint64_t)ldx == kin) ? x : nullptr;
   return launch_pdl(kern, dim3(2 * pairs), dim3(AMIL2_THREADS), C::SMEM_BYTES, st, tmX, tmW1, tmWab, tmH, tmWk, tmAGs, a2);
 }
 
