@@ -436,13 +436,17 @@ def run_ours(args):
 
     warmup = max(args.warmup, 3)
     run_steps(warmup)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     clk = ClockSampler(local_rank)   # samples through the device-resident AND the e2e timed regions
     clk.__enter__()
     time.sleep(0.05)
+    # The barrier is the LAST thing before the timed region: the sampler start-up and the sleep used to sit between the
+    # barrier and ev0, so the ranks entered the region milliseconds apart and the first exchange of the early ranks
+    # waited for the late ones inside their timed region (48 steps = 4.5 ms: 2.7 ms of entry skew read as 150 us/step at
+    # 8 GPUs where tools/dp_diag.py measures 98 us/step for the same graph, gpurun_out/r2o_bench_n8.log / r2p_dpdiag_n8.log)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     torch.cuda.synchronize()
     ev0.record()
     run_steps(args.steps, first=0)
