@@ -169,9 +169,10 @@ int mmf_amil_fwd_train(const void* x, int64_t N, int64_t ldx, const MmfAmilWeigh
 /* ---- fused batch-1 training step (utils/core_utils.py:200-247 for the path / radio AMIL models) ------------------
  * THREE launches: mmf_amil_fwd_train_head (fused forward; also leaves z_i = Wk h_i and the ReLU mask words for the
  * backward), then mmf_amil_bwd_head = [gate + hidden backward whose prologue runs the head] + [grouped wgrad GEMM].
- * Head block: softmax combine of the tile partials, classifier -> sigmoid -> cumprod
- * (models/model_attention_mil_path.py:55-61), nll_surv (utils/loss_utils.py:22-39) and their backward — computed
- * redundantly by every CTA of the gate + hidden kernel while its first tiles are in flight (no head launch).
+ * Head block: softmax combine, classifier -> sigmoid -> cumprod (models/model_attention_mil_path.py:55-61), nll_surv
+ * (utils/loss_utils.py:22-39) and their backward — computed redundantly by every CTA of the gate + hidden kernel from the
+ * forward's 12-float head rows (m_t, l_t, Wk.acc_t) while its first tiles are in flight (no head launch); the pooled
+ * embedding M and dWk are formed off the critical path inside the same kernel.
  * Inputs: Wk, bk, Wk_split (mmf_pack_head_weights), K <= 8, Y, c, alpha, eps, loss_scale (1/gc of the reference's
  * gradient accumulation: every gradient of the step is scaled by it).
  * Outputs (valid after mmf_amil_bwd_head): M [L], ml [2], hazards / S [K], Y_hat (or NULL), loss [1] (unscaled),
@@ -202,7 +203,8 @@ typedef struct MmfHeadStep {
  * operand of the N = 16 tensor-core side product z_i = Wk h_i of the training forward (hi + lo: fp32-grade z). */
 int mmf_pack_head_weights(const float* Wk, int K, int L, void* Wk_split_bf16, void* stream);
 
-/* mmf_amil_fwd_train that additionally leaves z_i = Wk h_i (fp32 [N, 4|8]) in the workspace (uses head->Wk_split, K). */
+/* mmf_amil_fwd_train that additionally leaves z_i = Wk h_i (fp32 [N, 4|8]) and one head row per tile (m_t, l_t, Wk.acc_t)
+ * in the workspace (uses head->Wk, head->Wk_split, head->K). */
 int mmf_amil_fwd_train_head(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, int L, int D,
                             int flags, uint64_t seed, float* A_raw, float* partials, void* workspace,
                             size_t workspace_bytes, float* zero_buf, int64_t zero_count, const MmfHeadStep* head,

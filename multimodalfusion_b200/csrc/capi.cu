@@ -701,7 +701,7 @@ int mmf_dense_bwd(const float* x, int64_t ldx, const float* W, int B, int in_dim
     launch_sgemm(out_dim, in_dim, B, LoadDpreT{dy, lddy, y, ldy, act}, LoadColMajor{x, ldx},
                  EpiStoreAcc{dW, in_dim, 1}, st);
   if (db)
-    colsum_functor_kernel<<<(out_dim + 127) / 128, 128, 0, st>>>(B, out_dim, LoadDpre{dy, lddy, y, ldy, act}, db, 1);
+    colsum_functor_kernel<<<(out_dim + 31) / 32, 256, 0, st>>>(B, out_dim, LoadDpre{dy, lddy, y, ldy, act}, db, 1);
   return launch_status();
 }
 
@@ -754,7 +754,7 @@ int mmf_kron_enc_train_bwd(const float* const* o, int m, int E, int B, const flo
   }
   if (dW)  // dW[h,kk] += sum_b dpre[b,h] kron[b,kk]
     launch_sgemm(H, KK, B, dpreT, LoadKronB{e}, EpiStoreAcc{dW, KK, 1}, st);
-  if (db) colsum_functor_kernel<<<(H + 127) / 128, 128, 0, st>>>(B, H, dpre, db, 1);
+  if (db) colsum_functor_kernel<<<(H + 31) / 32, 256, 0, st>>>(B, H, dpre, db, 1);
   return launch_status();
 }
 
@@ -779,7 +779,7 @@ int mmf_hazard_head_bwd(const float* M, int B, int Lin, const float* Wk, int K, 
     launch_sgemm(B, Lin, K, LoadHazA{d}, LoadColMajor{Wk, Lin}, EpiStoreAcc{dM, Lin, 0}, st);
   if (dWk)  // dWk[j,l] += sum_b dlogit[b,j] M[b,l]
     launch_sgemm(K, Lin, B, LoadHazAT{d}, LoadColMajor{M, Lin}, EpiStoreAcc{dWk, Lin, 1}, st);
-  if (dbk) colsum_functor_kernel<<<1, 32, 0, st>>>(B, K, LoadHazA{d}, dbk, 1);
+  if (dbk) colsum_functor_kernel<<<(K + 31) / 32, 256, 0, st>>>(B, K, LoadHazA{d}, dbk, 1);
   return launch_status();
 }
 

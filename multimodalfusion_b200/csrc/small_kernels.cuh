@@ -155,19 +155,26 @@ struct LoadHazAT { HazardDlogit d; static constexpr bool kContig = false;
 
 struct EpiBiasAct {              // y[m*ld+n] = act(acc + bias[n])
   float* y; long long ld; const float* bias; int act;
+  static constexpr bool kLinear = false;       // (non-linear epilogue: no split-K)
   __device__ __forceinline__ void operator()(int m, int n, float acc) const {
     y[m * ld + n] = act_fwd(act, acc + (bias ? bias[n] : 0.f));
   }
+  __device__ __forceinline__ void add(int, int, float) const {}
 };
 struct EpiStoreAcc {             // c[m*ld+n] = (accumulate ? c : 0) + acc
   float* c; long long ld; int accumulate;
+  static constexpr bool kLinear = true;        // split-K slices add their partial sums atomically (c zeroed first if !accumulate)
   __device__ __forceinline__ void operator()(int m, int n, float acc) const {
     float* p = c + m * ld + n;
     *p = accumulate ? *p + acc : acc;
   }
+  __device__ __forceinline__ void add(int m, int n, float acc) const { atomicAdd(c + m * ld + n, acc); }
 };
 
-// C(m,n) = sum_k A(m,k) * B(n,k).  64x64 tile, 256 threads, 4x4 micro-tile, BK = 16.
+// C(m,n) = sum_k A(m,k) * B(n,k).  64x64 tile, 256 threads, 4x4 micro-tile, BK = 16. The operand elements of the NEXT
+// k-step are fetched into registers while the current one is multiplied (the functor loads are scalar global loads: with
+// the fetch inside the step a skinny GEMM of 48 k-steps took ~1 us per step — latency, not work). gridDim.z > 1: split-K,
+// slice z takes k-steps z, z + gridDim.z, ... and adds its partial tile atomically (linear epilogues only).
 template <class ALoad, class BLoad, class Epi>
 __global__ void __launch_bounds__(256)
 sgemm_functor_kernel(int M, int N, int K, ALoad la, BLoad lb, Epi epi) {
@@ -181,8 +188,8 @@ sgemm_functor_kernel(int M, int N, int K, ALoad la, BLoad lb, Epi epi) {
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-
-  for (int k0 = 0; k0 < K; k0 += 16) {
+  float ra[4], rb[4];
+  auto fetch = [&](int k0) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int idx = tid + e * 256;
@@ -190,16 +197,28 @@ sgemm_functor_kernel(int M, int N, int K, ALoad la, BLoad lb, Epi epi) {
         const int mm = ALoad::kContig ? idx / 16 : idx % 64;
         const int kk = ALoad::kContig ? idx % 16 : idx / 64;
         const int gm = m0 + mm, gk = k0 + kk;
-        As[kk][mm] = (gm < M && gk < K) ? la(gm, gk) : 0.f;
+        ra[e] = (gm < M && gk < K) ? la(gm, gk) : 0.f;
       }
       {
         const int nn = BLoad::kContig ? idx / 16 : idx % 64;
         const int kk = BLoad::kContig ? idx % 16 : idx / 64;
         const int gn = n0 + nn, gk = k0 + kk;
-        Bs[kk][nn] = (gn < N && gk < K) ? lb(gn, gk) : 0.f;
+        rb[e] = (gn < N && gk < K) ? lb(gn, gk) : 0.f;
       }
     }
+  };
+  const int kstep = 16 * (int)gridDim.z;
+  int k0 = 16 * (int)blockIdx.z;
+  if (k0 < K) fetch(k0);
+  for (; k0 < K; k0 += kstep) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = tid + e * 256;
+      As[ALoad::kContig ? idx % 16 : idx / 64][ALoad::kContig ? idx / 16 : idx % 64] = ra[e];
+      Bs[BLoad::kContig ? idx % 16 : idx / 64][BLoad::kContig ? idx / 16 : idx % 64] = rb[e];
+    }
     __syncthreads();
+    if (k0 + kstep < K) fetch(k0 + kstep);
 #pragma unroll
     for (int kk = 0; kk < 16; ++kk) {
       float av[4], bv[4];
@@ -214,29 +233,61 @@ sgemm_functor_kernel(int M, int N, int K, ALoad la, BLoad lb, Epi epi) {
     }
     __syncthreads();
   }
+  const bool split = gridDim.z > 1;
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int gm = m0 + tm * 4 + i, gn = n0 + tn * 4 + j;
-      if (gm < M && gn < N) epi(gm, gn, acc[i][j]);
+      if (gm < M && gn < N) {
+        if (Epi::kLinear && split) epi.add(gm, gn, acc[i][j]);
+        else epi(gm, gn, acc[i][j]);
+      }
     }
 }
 
+// Split-K for grids that would leave most of the 148 SMs idle (the fusion heads' weight gradients: 16 x 768 outputs
+// over a 512-sample cohort = 12 tiles of 32 k-steps): only for linear epilogues; an output that is not accumulated
+// into is cleared first.
 template <class ALoad, class BLoad, class Epi>
 inline void launch_sgemm(int M, int N, int K, ALoad la, BLoad lb, Epi epi, cudaStream_t st) {
   dim3 grid((N + 63) / 64, (M + 63) / 64);
+  int splits = 1;
+  if constexpr (Epi::kLinear) {
+    const int tiles = (int)(grid.x * grid.y), ksteps = (K + 15) / 16;
+    if (tiles <= 74 && ksteps >= 8) {
+      splits = (148 + tiles - 1) / tiles;
+      if (splits > ksteps / 4) splits = ksteps / 4;      // at least 4 k-steps per slice
+      if (splits > 32) splits = 32;
+      if (splits < 1) splits = 1;
+    }
+    if (splits > 1 && !epi.accumulate) {
+      if (epi.ld == N) cudaMemsetAsync(epi.c, 0, sizeof(float) * (size_t)M * (size_t)N, st);
+      else cudaMemset2DAsync(epi.c, sizeof(float) * (size_t)epi.ld, 0, sizeof(float) * (size_t)N, (size_t)M, st);
+    }
+  }
+  grid.z = splits;
   sgemm_functor_kernel<ALoad, BLoad, Epi><<<grid, 256, 0, st>>>(M, N, K, la, lb, epi);
 }
 
-// out[o] (+)= sum_b elem(b, o)   — one thread per column
+// out[o] (+)= sum_b elem(b, o): one warp per 32 columns x a slice of the rows, 8 warps per block meet in shared memory
+// (one thread per column walking all B rows took 32 us per call at B = 512)
 template <class Elem>
-__global__ void colsum_functor_kernel(int B, int O, Elem e, float* out, int accumulate) {
-  const int o = blockIdx.x * blockDim.x + threadIdx.x;
-  if (o >= O) return;
+__global__ void __launch_bounds__(256) colsum_functor_kernel(int B, int O, Elem e, float* out, int accumulate) {
+  __shared__ float part[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int o = blockIdx.x * 32 + lane;
   float s = 0.f;
-  for (int b = 0; b < B; ++b) s += e(b, o);
-  out[o] = accumulate ? out[o] + s : s;
+  if (o < O)
+    for (int b = w; b < B; b += 8) s += e(b, o);
+  part[w][lane] = s;
+  __syncthreads();
+  if (w == 0 && o < O) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += part[i][lane];
+    out[o] = accumulate ? out[o] + t : t;
+  }
 }
 
 // -------------------------------------------------------------------------------------------
