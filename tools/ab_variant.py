@@ -48,7 +48,7 @@ def run(names, tests, lanes):
             print(t.stdout[-3000:], t.stderr[-2000:], sep="\n")
         for n in lanes:
             b = subprocess.run([sys.executable, "bench.py", "--steps", "64", "--warmup", "8"], cwd=ROOT,
-                               env=dict(env, MMF_BENCH_QUICK="1", MMF_BENCH_INFLIGHT=str(n)), capture_output=True, text=True)
+                               env=dict(env, MMF_BENCH_QUICK="1"), capture_output=True, text=True)
             try:
                 line = json.loads([l for l in b.stdout.splitlines() if l.startswith("{")][-1])
                 row[f"us/step @{n} lane(s)"] = round(line["ms_per_step"] * 1e3, 2)
