@@ -54,6 +54,12 @@ enum {
                            backward's dW1 uses x_hi (the first 1024 columns). */
 };
 
+/* Dropout seeds: every `uint64_t seed` argument of this header is either a host value below 2^63 or
+ * MMF_SEED_DEVICE(ptr): the device address of a uint64 that holds the seed. The kernels then read the seed when they RUN,
+ * not when they are launched — a launch captured in a CUDA graph draws a new mask on every replay once the word is moved
+ * on by mmf_step_state_advance() at the head of the graph. (The reference draws its masks from torch's generator per call,
+ * models/model_attention_mil_path.py:22-26; per-step seeds are the equivalent here.) */
+#define MMF_SEED_DEVICE(ptr) ((uint64_t)(uintptr_t)(ptr) | 0x8000000000000000ull)
 #define MMF_IN_FEATURES 1024 /* ResNet50-layer3 feature width, fixed by the reference models */
 #define MMF_TILE_ROWS 128    /* instances per CTA tile; one (m, l, acc[L]) partial per tile */
 
@@ -284,6 +290,14 @@ enum { MMF_ACT_NONE = 0, MMF_ACT_RELU = 1, MMF_ACT_SELU = 2, MMF_ACT_SIGMOID = 3
  * (models/model_modules.py:64-68), classifier heads, XlinearFusion.reduce/encoder layers. */
 int mmf_dense_fwd(const float* x, int64_t ldx, const float* W, const float* b, int B, int in_dim,
                   int out_dim, int act, float* y, int64_t ldy, void* stream);
+/* The same layer with a caller-owned workspace: when the output has few 64 x 64 tiles and the k loop is long (the radiology
+ * reduce_dim Linear(4096, 1024) on a ~100-slice patient, models/model_attention_mil_radio.py:31,81-82; the fc of a tiny bag)
+ * the k loop is split over the whole machine — every slice stores its partial tile to the workspace and a fix-up kernel
+ * adds the slices in a FIXED order (deterministic, no atomics) before bias + activation. mmf_dense_fwd_workspace_bytes()
+ * returns 0 when the shape is not split (the call is then mmf_dense_fwd). */
+size_t mmf_dense_fwd_workspace_bytes(int B, int in_dim, int out_dim);
+int mmf_dense_fwd_ws(const float* x, int64_t ldx, const float* W, const float* b, int B, int in_dim, int out_dim,
+                     int act, float* y, int64_t ldy, void* workspace, size_t workspace_bytes, void* stream);
 /* Given y (post-activation) and dy: dpre = dy * act'(y); dx[B,in] (=|+=) dpre W; dW += dpre^T x;
  * db += colsum(dpre).  dx may be NULL. accumulate_dx != 0 adds into dx. */
 int mmf_dense_bwd(const float* x, int64_t ldx, const float* W, int B, int in_dim, int out_dim,
@@ -382,6 +396,18 @@ int mmf_adam_step_multi(float* const* params_host, const float* const* grads_hos
                         float* const* exp_avg_sq_host, const int64_t* numel_host, int n_tensors, int step, float lr,
                         float beta1, float beta2, float eps, float weight_decay, float grad_scale, float l1_lambda,
                         int zero_grad, float* l1_out, void* stream);
+
+/* The same update with the step count read from the device (graph-captured training steps): *step_dev >= 1 when the kernel
+ * runs; the bias corrections are formed in the kernel. */
+int mmf_adam_step_multi_dev(float* const* params_host, const float* const* grads_host, float* const* exp_avg_host,
+                            float* const* exp_avg_sq_host, const int64_t* numel_host, int n_tensors,
+                            const uint64_t* step_dev, float lr, float beta1, float beta2, float eps, float weight_decay,
+                            float grad_scale, float l1_lambda, int zero_grad, float* l1_out, void* stream);
+/* Device-resident state of a graph-captured training step (the batch-1 loop of utils/core_utils.py:184-247 replayed as ONE
+ * graph launch per patient / cohort step): state[0] = optimizer step count, state[1 .. n_seeds] = dropout seeds. One launch
+ * at the head of each replay: state[0] += 1 and every seed moves to the next value of its splitmix64 sequence (< 2^62).
+ * Consumers: mmf_adam_step_multi_dev(step_dev = state) and any seed passed as MMF_SEED_DEVICE(state + i). */
+int mmf_step_state_advance(uint64_t* state, int n_seeds, void* stream);
 
 /* Concordance index counts as sksurv.concordance_index_censored(event, time, risk, tied_tol) computes them
  * (utils/core_utils.py:258): over comparable pairs (event_i != 0 and t_i < t_j): counts[0] concordant

@@ -29,6 +29,7 @@ NVCC_FLAGS = [
 # error codes / flags mirrored from the header
 MMF_OK = 0
 MMF_GATED, MMF_DROPOUT_H, MMF_DROPOUT_ATTN, MMF_NEED_DX, MMF_STASHED, MMF_PRECISE_FC = 1, 2, 4, 8, 16, 32
+SEED_DEVICE_BIT = 1 << 63     # MMF_SEED_DEVICE(ptr): the seed argument is the device address of the seed word
 ACT_NONE, ACT_RELU, ACT_SELU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3, 4
 
 
@@ -135,6 +136,8 @@ SIGNATURES = {
     "mmf_linear_bf16_wgrad_workspace_bytes": (_sz, [_i64, _i]),
     "mmf_linear_bf16_wgrad": (_i, [_vp, _i64, _i, _i64, _PP, _i, _i, _i64, _vp, _vp, _vp, _sz, _vp]),
     "mmf_dense_fwd": (_i, [_vp, _i64, _vp, _vp, _i, _i, _i, _i, _vp, _i64, _vp]),
+    "mmf_dense_fwd_workspace_bytes": (_sz, [_i, _i, _i]),
+    "mmf_dense_fwd_ws": (_i, [_vp, _i64, _vp, _vp, _i, _i, _i, _i, _vp, _i64, _vp, _sz, _vp]),
     "mmf_dense_bwd": (_i, [_vp, _i64, _vp, _i, _i, _i, _i, _vp, _i64, _vp, _i64, _vp, _i64, _i, _vp, _vp, _vp]),
     "mmf_kron_enc_fwd": (_i, [_PP, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "mmf_kron_enc_workspace_bytes": (_sz, [_i, _i, _i]),
@@ -154,6 +157,8 @@ SIGNATURES = {
     "mmf_cox_workspace_bytes": (_sz, [_i]),
     "mmf_cox_fwd_bwd": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "mmf_adam_step_multi": (_i, [_PP, _PP, _PP, _PP, C.POINTER(C.c_int64), _i, _i, _f, _f, _f, _f, _f, _f, _f, _i, _vp, _vp]),
+    "mmf_adam_step_multi_dev": (_i, [_PP, _PP, _PP, _PP, C.POINTER(C.c_int64), _i, _vp, _f, _f, _f, _f, _f, _f, _f, _i, _vp, _vp]),
+    "mmf_step_state_advance": (_i, [_vp, _i, _vp]),
     "mmf_percentile_of_score": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
     "mmf_cindex_counts": (_i, [_vp, _vp, _vp, _i, _f, _vp, _vp]),
     "mmf_p2p_flag_bytes": (_sz, []),

@@ -174,6 +174,7 @@ amil_hidden_fused_kernel(const __grid_constant__ CUtensorMap tmAG,   // stash fp
   a.H = pdl_fresh(a.H); a.A_raw = pdl_fresh(a.A_raw); a.ml = pdl_fresh(a.ml); a.M = pdl_fresh(a.M); a.dM = pdl_fresh(a.dM);
   a.mask = pdl_fresh(a.mask); a.z = pdl_fresh(a.z); a.partials = pdl_fresh(a.partials); a.tile_head = pdl_fresh(a.tile_head);
   a.dA_raw = pdl_fresh(a.dA_raw);
+  if (DROP) a.seed = seed_resolve(a.seed);   // (device-resident seed of a graph-captured step)
   timeline_wait_done(tl);
   if (threadIdx.x == 0) MMF_STAMP(a, 1);
 

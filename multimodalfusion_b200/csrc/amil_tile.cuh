@@ -80,6 +80,20 @@ __host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
   x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
   return x;
 }
+// A seed argument with bit 63 set (MMF_SEED_DEVICE(ptr), include/mmf_b200.h) is the device address of the 64-bit seed:
+// the kernels read it at run time (after griddepcontrol.wait), so that the replays of a CUDA graph that contains the
+// launch see a fresh seed each — mmf_step_state_advance re-hashes the word at the start of every replay. A plain
+// (non-nc, volatile, memory-clobbering) load: the word is written by a kernel earlier in the same stream.
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long seed_resolve(unsigned long long s) {
+  if (s >> 63) {
+    unsigned long long v;
+    asm volatile("ld.global.u64 %0, [%1];" : "=l"(v) : "l"(s & 0x7FFFFFFFFFFFFFFFull) : "memory");
+    return v;
+  }
+  return s;
+}
+#endif
 // per-row state; stream: 0 = h, 1 = tanh branch, 2 = sigmoid branch
 __host__ __device__ __forceinline__ uint32_t drop_row_state(unsigned long long seed, uint32_t stream,
                                                             uint32_t row) {

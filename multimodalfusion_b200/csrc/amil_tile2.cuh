@@ -144,6 +144,7 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   griddep_wait();                // PDL: everything above overlapped the previous kernel; its outputs are visible now
   a.b1 = pdl_fresh(a.b1); a.bab = pdl_fresh(a.bab); a.wc = pdl_fresh(a.wc); a.bc = pdl_fresh(a.bc);   // (optimizer step)
   a.head_wk = pdl_fresh(a.head_wk); a.tile_valid = pdl_fresh(a.tile_valid);
+  if (DROPH || DROPA) a.seed = seed_resolve(a.seed);   // (device-resident seed of a graph-captured step)
   if (MODE == AMIL_BWD_GATE) {
     a.A_raw = pdl_fresh(a.A_raw); a.ml = pdl_fresh(a.ml); a.M = pdl_fresh(a.M); a.dM = pdl_fresh(a.dM); a.dA_raw = pdl_fresh(a.dA_raw);
   }

@@ -684,8 +684,31 @@ int mmf_linear_bf16_wgrad(const void* dY, int64_t M, int N, int64_t lddy, const 
 int mmf_dense_fwd(const float* x, int64_t ldx, const float* W, const float* b, int B, int in_dim,
                   int out_dim, int act, float* y, int64_t ldy, void* stream) {
   if (!x || !W || !y || B <= 0 || in_dim <= 0 || out_dim <= 0) return MMF_E_INVALID;
-  launch_sgemm(B, out_dim, in_dim, LoadRowMajor{x, ldx}, LoadRowMajor{W, in_dim},
-               EpiBiasAct{y, ldy, b, act}, (cudaStream_t)stream);
+  launch_sgemm(B, out_dim, in_dim, LoadRowMajor{x, ldx}, LoadRowMajor{W, in_dim}, EpiBiasAct{y, ldy, b, act},
+               (cudaStream_t)stream);
+  return launch_status();
+}
+
+size_t mmf_dense_fwd_workspace_bytes(int B, int in_dim, int out_dim) {
+  if (B <= 0 || in_dim <= 0 || out_dim <= 0) return 0;
+  const int splits = dense_fwd_splits(B, in_dim, out_dim);
+  return splits > 1 ? sizeof(float) * (size_t)splits * (size_t)B * (size_t)out_dim : 0;
+}
+
+int mmf_dense_fwd_ws(const float* x, int64_t ldx, const float* W, const float* b, int B, int in_dim, int out_dim,
+                     int act, float* y, int64_t ldy, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!x || !W || !y || B <= 0 || in_dim <= 0 || out_dim <= 0) return MMF_E_INVALID;
+  const int splits = dense_fwd_splits(B, in_dim, out_dim);
+  if (splits <= 1) return mmf_dense_fwd(x, ldx, W, b, B, in_dim, out_dim, act, y, ldy, stream);
+  if (!workspace || workspace_bytes < mmf_dense_fwd_workspace_bytes(B, in_dim, out_dim)) return MMF_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* ws = static_cast<float*>(workspace);
+  dim3 grid((out_dim + 63) / 64, (B + 63) / 64, splits);
+  sgemm_functor_kernel<LoadRowMajor, LoadRowMajor, EpiSlice><<<grid, 256, 0, st>>>(
+      B, out_dim, in_dim, LoadRowMajor{x, ldx}, LoadRowMajor{W, in_dim}, EpiSlice{ws, (long long)B * out_dim, out_dim});
+  long long blocks = ((long long)B * out_dim + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  splitk_fixup_kernel<<<(int)blocks, 256, 0, st>>>(ws, splits, B, out_dim, b, act, y, ldy);
   return launch_status();
 }
 
@@ -886,17 +909,22 @@ int mmf_ranking_fwd_bwd(const float* risks, const float* times, const float* c, 
   return launch_status();
 }
 
-int mmf_adam_step_multi(float* const* params_host, const float* const* grads_host, float* const* exp_avg_host,
-                        float* const* exp_avg_sq_host, const int64_t* numel_host, int n_tensors, int step, float lr,
-                        float beta1, float beta2, float eps, float weight_decay, float grad_scale, float l1_lambda,
-                        int zero_grad, float* l1_out, void* stream) {
-  if (!params_host || !grads_host || !exp_avg_host || !exp_avg_sq_host || !numel_host || n_tensors <= 0 || step < 1)
+namespace {
+int adam_step_multi_impl(float* const* params_host, const float* const* grads_host, float* const* exp_avg_host,
+                         float* const* exp_avg_sq_host, const int64_t* numel_host, int n_tensors, int step,
+                         const uint64_t* step_dev, float lr, float beta1, float beta2, float eps, float weight_decay,
+                         float grad_scale, float l1_lambda, int zero_grad, float* l1_out, void* stream) {
+  if (!params_host || !grads_host || !exp_avg_host || !exp_avg_sq_host || !numel_host || n_tensors <= 0 ||
+      (step_dev == nullptr && step < 1))
     return MMF_E_INVALID;
   AdamHyper h = {};
   h.lr = lr; h.beta1 = beta1; h.beta2 = beta2; h.eps = eps; h.weight_decay = weight_decay; h.grad_scale = grad_scale;
   h.l1_lambda = l1_lambda; h.zero_grad = zero_grad;
-  h.bias1 = (float)(1.0 - pow((double)beta1, (double)step));
-  h.bias2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+  h.step_dev = reinterpret_cast<const unsigned long long*>(step_dev);
+  if (step_dev == nullptr) {
+    h.bias1 = (float)(1.0 - pow((double)beta1, (double)step));
+    h.bias2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+  }
   for (int t0 = 0; t0 < n_tensors; t0 += ADAM_MAX_TENSORS) {
     AdamTensors T = {};
     T.n = n_tensors - t0 < ADAM_MAX_TENSORS ? n_tensors - t0 : ADAM_MAX_TENSORS;
@@ -917,6 +945,31 @@ int mmf_adam_step_multi(float* const* params_host, const float* const* grads_hos
     MMF_TRY(launch_status());
   }
   return MMF_OK;
+}
+}  // namespace
+
+int mmf_adam_step_multi(float* const* params_host, const float* const* grads_host, float* const* exp_avg_host,
+                        float* const* exp_avg_sq_host, const int64_t* numel_host, int n_tensors, int step, float lr,
+                        float beta1, float beta2, float eps, float weight_decay, float grad_scale, float l1_lambda,
+                        int zero_grad, float* l1_out, void* stream) {
+  return adam_step_multi_impl(params_host, grads_host, exp_avg_host, exp_avg_sq_host, numel_host, n_tensors, step, nullptr,
+                              lr, beta1, beta2, eps, weight_decay, grad_scale, l1_lambda, zero_grad, l1_out, stream);
+}
+
+int mmf_adam_step_multi_dev(float* const* params_host, const float* const* grads_host, float* const* exp_avg_host,
+                            float* const* exp_avg_sq_host, const int64_t* numel_host, int n_tensors,
+                            const uint64_t* step_dev, float lr, float beta1, float beta2, float eps, float weight_decay,
+                            float grad_scale, float l1_lambda, int zero_grad, float* l1_out, void* stream) {
+  if (!step_dev) return MMF_E_INVALID;
+  return adam_step_multi_impl(params_host, grads_host, exp_avg_host, exp_avg_sq_host, numel_host, n_tensors, 0, step_dev,
+                              lr, beta1, beta2, eps, weight_decay, grad_scale, l1_lambda, zero_grad, l1_out, stream);
+}
+
+int mmf_step_state_advance(uint64_t* state, int n_seeds, void* stream) {
+  if (!state || n_seeds < 0 || n_seeds > 1023) return MMF_E_INVALID;
+  step_state_advance_kernel<<<(n_seeds + 1 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<unsigned long long*>(state), n_seeds);
+  return launch_status();
 }
 
 int mmf_cindex_counts(const float* risk, const float* times, const float* event, int B, float tied_tol,

@@ -97,10 +97,13 @@ struct LoadDpreT {               // element (o, b): A(m=o, k=b): m contiguous
 constexpr uint32_t KRON_DROP_STREAM = 3;
 struct KronElem {
   const float* o0; const float* o1; const float* o2; const float* o3; int m; int E;
-  unsigned long long seed; int drop;
+  unsigned long long seed; int drop;   // seed with bit 63 set = device address of the seed word (MMF_SEED_DEVICE, amil_tile.cuh)
   __device__ __forceinline__ float keep_scale(int b, int kk) const {
     if (!drop) return 1.f;
-    return drop_keep(drop_bits16(drop_row_state(seed, KRON_DROP_STREAM, (uint32_t)b), (uint32_t)kk >> 4), (uint32_t)kk & 15u)
+    // (these kernels are launched without the PDL attribute: a read-only load of the word an EARLIER kernel wrote is safe,
+    // and the compiler may hoist it out of the k loop)
+    const unsigned long long sd = (seed >> 63) ? __ldg(reinterpret_cast<const unsigned long long*>(seed & 0x7FFFFFFFFFFFFFFFull)) : seed;
+    return drop_keep(drop_bits16(drop_row_state(sd, KRON_DROP_STREAM, (uint32_t)b), (uint32_t)kk >> 4), (uint32_t)kk & 15u)
                ? (1.0f / 0.75f) : 0.f;
   }
   __device__ __forceinline__ float at(int b, int kk) const { return raw(b, kk) * keep_scale(b, kk); }
@@ -244,6 +247,38 @@ sgemm_functor_kernel(int M, int N, int K, ALoad la, BLoad lb, Epi epi) {
         else epi(gm, gn, acc[i][j]);
       }
     }
+}
+
+// Deterministic split-K forward (mmf_dense_fwd_ws): slice z stores its partial tile to ws[z][m][n] (plain stores, no
+// atomics), the fix-up kernel adds the slices in a fixed order, then bias + activation.
+struct EpiSlice {
+  float* ws; long long MN; int N;
+  static constexpr bool kLinear = false;
+  __device__ __forceinline__ void operator()(int m, int n, float acc) const { ws[blockIdx.z * MN + (long long)m * N + n] = acc; }
+  __device__ __forceinline__ void add(int, int, float) const {}
+};
+__global__ void __launch_bounds__(256) splitk_fixup_kernel(const float* __restrict__ ws, int splits, int M, int N,
+                                                           const float* __restrict__ bias, int act, float* __restrict__ y,
+                                                           long long ld) {
+  const long long total = (long long)M * N;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int m = (int)(i / N), n = (int)(i - (long long)m * N);
+    float acc = 0.f;
+    for (int z = 0; z < splits; ++z) acc += ws[z * total + i];
+    y[m * ld + n] = act_fwd(act, acc + (bias ? bias[n] : 0.f));
+  }
+}
+// split count of the deterministic split-K forward: few output tiles and a long k loop (the radiology reduce_dim,
+// [155, 4096] -> 1024: 48 CTAs of 256 serial k-steps took 205 us); 8 warps per CTA cannot fill an SM's FMA pipes
+// (the k loop is latency-bound), so the slices aim at ~4 CTAs per SM. 1 = no split.
+inline int dense_fwd_splits(int B, int in_dim, int out_dim) {
+  const long long tiles = (long long)((B + 63) / 64) * ((out_dim + 63) / 64);
+  const int ksteps = (in_dim + 15) / 16;
+  if (tiles > 74 || in_dim < 512) return 1;
+  int splits = (int)((4 * 148 + tiles - 1) / tiles);
+  if (splits > ksteps / 4) splits = ksteps / 4;
+  if (splits > 32) splits = 32;
+  return splits < 1 ? 1 : splits;
 }
 
 // Split-K for grids that would leave most of the 148 SMs idle (the fusion heads' weight gradients: 16 x 768 outputs

@@ -27,10 +27,40 @@ struct AdamHyper {
   float lr, beta1, beta2, eps, weight_decay, grad_scale, l1_lambda;
   float bias1, bias2_sqrt;   // 1 - beta1^t, sqrt(1 - beta2^t)
   int zero_grad;             // also clear g (optimizer.zero_grad() fused)
+  const unsigned long long* step_dev;   // non-null: the 1-based step count lives on the device (graph-captured training
+                                        // step, mmf_step_state_advance); the bias corrections are then formed in the kernel
 };
+
+// Device-resident state of a graph-captured training step: word 0 = optimizer step count, words 1.. = dropout seeds.
+// One launch at the head of every replay: the count goes up by one and every seed moves to the next value of its own
+// splitmix64 sequence, so that each replay of the SAME graph runs with the bias corrections and dropout masks an eager
+// loop would have drawn host-side.
+__device__ __forceinline__ unsigned long long splitmix64_next(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ull;
+  unsigned long long z = x;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return (z ^ (z >> 31)) & 0x3FFFFFFFFFFFFFFFull;   // seeds stay below 2^62 like the host-drawn ones
+}
+__global__ void step_state_advance_kernel(unsigned long long* __restrict__ state, int n_seeds) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) state[0] += 1ull;
+  else if (i <= n_seeds) state[i] = splitmix64_next(state[i]);
+}
 
 __global__ void __launch_bounds__(256) adam_multi_kernel(const AdamTensors T, const AdamHyper h, float* __restrict__ l1_out) {
   __shared__ float s_red[8];
+  __shared__ float s_bias[2];
+  float bias1 = h.bias1, bias2_sqrt = h.bias2_sqrt;
+  if (h.step_dev != nullptr) {
+    if (threadIdx.x == 0) {
+      const double t = (double)*h.step_dev;
+      s_bias[0] = (float)(1.0 - pow((double)h.beta1, t));
+      s_bias[1] = (float)sqrt(1.0 - pow((double)h.beta2, t));
+    }
+    __syncthreads();
+    bias1 = s_bias[0]; bias2_sqrt = s_bias[1];
+  }
   const long long total = T.start[T.n];
   float l1 = 0.f;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
@@ -46,8 +76,8 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const AdamTensors T, co
     const float v = fmaf(h.beta2, T.v[k][j], (1.f - h.beta2) * g * g);
     T.m[k][j] = m;
     T.v[k][j] = v;
-    const float denom = sqrtf(v) / h.bias2_sqrt + h.eps;
-    T.p[k][j] = p - (h.lr / h.bias1) * (m / denom);
+    const float denom = sqrtf(v) / bias2_sqrt + h.eps;
+    T.p[k][j] = p - (h.lr / bias1) * (m / denom);
     if (h.zero_grad) const_cast<float*>(T.g[k])[j] = 0.f;
   }
   if (l1_out) {

@@ -65,3 +65,40 @@ def run(model, seq, classifier, bag, Y, c, alpha, loss_scale, accumulate, eps, n
                         Yd, cd, alpha, f["grads"], dWk=f["dWk"], dbk=f["dbk"], eps=eps, loss_scale=loss_scale,
                         zero=None if accumulate else f["flat"], dx=dx)
     return buf.hazards, buf.S, buf.Y_hat, buf.A_raw.view(1, -1), buf.loss, dx
+
+
+def graphed(model, optimizer, bags: dict, Y, c, alpha=0.0, loss_scale=1.0, eps=1e-7):
+    """``model.fused_step(...)`` + ``optimizer.step()`` of one patient as ONE CUDA-graph launch (multimodalfusion_b200.graphs):
+    the batch-1 loop of utils/core_utils.py:184-247 with `--gc 1`. One graph per (bag size, dtype, hyper-parameters), captured
+    the first time the size is seen (that patient's step runs eagerly) and replayed afterwards; the bags, Y and c are copied
+    into the graph's static inputs (one stack kernel + two small copies). The dropout seeds and Adam's step count live on the
+    device and move on with every replay. Returns fused_step's tuple — static buffers, overwritten by the next call."""
+    from ..graphs import GraphedStep, GraphedStepFamily
+    names = list(bags)
+    x0 = bags[names[0]]
+    key = (tuple(names), x0.shape[0], x0.dtype, bool(model.training), float(alpha), float(loss_scale), float(eps), id(optimizer))
+    fam = getattr(model, "_graph_family", None)
+    if fam is None:
+        fam = model._graph_family = GraphedStepFamily()
+    entry = fam.graphs.get(key)
+    if entry is None:
+        sx = torch.empty((len(names),) + tuple(x0.shape), dtype=x0.dtype, device=x0.device)
+        sY = torch.zeros(1, dtype=torch.int64, device=x0.device)
+        sc = torch.zeros(1, dtype=torch.float32, device=x0.device)
+
+        def fn():
+            out = model.fused_step(Y=sY, c=sc, alpha=alpha, loss_scale=loss_scale, accumulate=False, eps=eps,
+                                   **{n: sx[i] for i, n in enumerate(names)})
+            optimizer.step(zero_grad=False)     # (the next step clears the gradients inside its forward kernel)
+            return out
+
+        entry = fam.get(key, lambda: GraphedStep(fn, optimizers=(optimizer,), modules=(model,)))
+        entry.static = (sx, sY, sc)
+    sx, sY, sc = entry.static
+    if len(names) == 1:
+        sx[0].copy_(x0)
+    else:
+        torch.stack([bags[n] for n in names], out=sx)
+    sY.copy_(Y.reshape(-1), non_blocking=True)
+    sc.copy_(c.reshape(-1), non_blocking=True)
+    return entry()

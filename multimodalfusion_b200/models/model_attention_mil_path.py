@@ -73,6 +73,11 @@ class MIL_Attention_fc_surv_path(MIL_Attention_fc_path):
         return _fused_step.run(self, self.attention_net_WSI, self.classifier, path_features, Y, c, alpha, loss_scale,
                                accumulate, eps)[:5]
 
+    def graphed_fused_step(self, optimizer, path_features, Y, c, alpha=0.0, loss_scale=1.0, eps=1e-7):
+        """fused_step + ``optimizer.step()`` (FusedAdam) as one CUDA-graph launch per bag size; see _fused_step.graphed."""
+        from . import _fused_step
+        return _fused_step.graphed(self, optimizer, {"path_features": path_features}, Y, c, alpha, loss_scale, eps)
+
     @torch.no_grad()
     def infer_cohort(self, bags):
         """Eval-mode forward of MANY slides at once (new capability; the reference loops batch-1, e.g.

@@ -91,6 +91,13 @@ class MIL_Attention_fc_surv_radio(MIL_Attention_fc_radio):
                 p_.grad = torch.zeros_like(p_)
         return flat
 
+    def graphed_fused_step(self, optimizer, Y, c, alpha=0.0, loss_scale=1.0, eps=1e-7, **bags):
+        """One patient of the batch-1 radiology loop — fused_step + ``optimizer.step()`` (FusedAdam) — as ONE CUDA-graph
+        launch per slice count (the ~29 kernels of the patient step cost ~16 us of host time each when launched from
+        Python); see _fused_step.graphed."""
+        from . import _fused_step
+        return _fused_step.graphed(self, optimizer, {m: bags[m] for m in self.modalities}, Y, c, alpha, loss_scale, eps)
+
     def fused_step(self, Y, c, alpha=0.0, loss_scale=1.0, accumulate=False, eps=1e-7, **bags):
         """One patient of the reference's batch-1 radiology loop without an autograd graph: ``model(T1=.., T2=.., ...)`` ->
         nll_surv -> ``(loss * loss_scale).backward()`` as reduce_dim (one fp32 functor-SGEMM launch on the concatenated
@@ -123,7 +130,9 @@ class MIL_Attention_fc_surv_radio(MIL_Attention_fc_radio):
         if self.radio_fusion != 'concat' or xs[0].shape[0] > ops.PRECISE_FC_MAX_ROWS:
             raise NotImplementedError("fused_step: radio_fusion='concat' with at most 4096 slices; use forward() + autograd")
         Wr, br = self.reduce_dim.weight, self.reduce_dim.bias
-        xc = torch.cat([b.float() for b in xs], dim=1)                         # [N, 1024 m]
+        # [N, 1024 m] fp32: one concat in the bags' dtype + one conversion (a conversion per modality + the concat were five
+        # launches of ~4 us each)
+        xc = (torch.cat(xs, dim=1) if len({b.dtype for b in xs}) == 1 else torch.cat([b.float() for b in xs], dim=1)).float()
         h0 = ops.dense_fwd(xc, Wr.detach(), br.detach(), ACT_NONE)             # reduce_dim, fp32 (models/...radio.py:81-82)
         out = _fused_step.run(self, self.attention_net_radio, self.classifier, h0, Y, c, alpha, loss_scale, accumulate,
                               eps, need_dx=True)

@@ -18,7 +18,12 @@ from .._lib import ACT_NONE, ACT_RELU, ACT_SELU, ACT_SIGMOID, ACT_TANH
 
 
 def _seed_from_torch() -> int:
-    """Per-call dropout seed drawn from torch's CPU generator (reproducible under manual_seed)."""
+    """Per-call dropout seed drawn from torch's CPU generator (reproducible under manual_seed). While a step is being
+    captured into a CUDA graph (multimodalfusion_b200.graphs) the seed is a device word instead, advanced per replay."""
+    from ..graphs import current_state
+    st = current_state()
+    if st is not None:
+        return st.new_seed()
     return int(torch.randint(0, 2 ** 62, (1,)).item())
 
 

@@ -326,8 +326,10 @@ def dense_fwd(x, W, b, act: int) -> torch.Tensor:
     x, W = _f32c(x), _f32c(W)
     B, in_dim = x.shape
     out = torch.empty(B, W.shape[0], dtype=torch.float32, device=x.device)
-    check(lib().mmf_dense_fwd(_p(x), in_dim, _p(W), _p(None if b is None else _f32c(b)), B, in_dim, W.shape[0],
-                              act, _p(out), W.shape[0], _stream()), "mmf_dense_fwd")
+    nbytes = lib().mmf_dense_fwd_workspace_bytes(B, in_dim, W.shape[0])   # > 0: deterministic split-K (few tiles, long k loop)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device) if nbytes else None
+    check(lib().mmf_dense_fwd_ws(_p(x), in_dim, _p(W), _p(None if b is None else _f32c(b)), B, in_dim, W.shape[0],
+                                 act, _p(out), W.shape[0], _p(ws), nbytes, _stream()), "mmf_dense_fwd_ws")
     return out
 
 

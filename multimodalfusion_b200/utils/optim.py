@@ -23,13 +23,37 @@ class FusedAdam(torch.optim.Optimizer):
                  weight_decay: float = 0.0, l1_lambda: float = 0.0):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, l1_lambda=l1_lambda))
         self.l1_value: Optional[torch.Tensor] = None
+        self._graph_steps = 0    # steps taken by CUDA-graph replays, not yet folded into the per-parameter "step" entries
+
+    # ---- graph-captured steps (multimodalfusion_b200.graphs): the step count lives on the device -------------------
+    def note_graph_step(self):
+        self._graph_steps += 1
+
+    def flush_graph_steps(self):
+        if self._graph_steps:
+            for st in self.state.values():
+                if "step" in st:
+                    st["step"] += self._graph_steps
+            self._graph_steps = 0
+
+    def host_step(self) -> int:
+        self.flush_graph_steps()
+        return max((st.get("step", 0) for st in self.state.values()), default=0)
+
+    def state_dict(self):
+        self.flush_graph_steps()
+        return super().state_dict()
 
     @torch.no_grad()
     def step(self, closure=None, zero_grad: bool = False, grad_scale: float = 1.0):
+        from ..graphs import current_state
+        dev_state = current_state()      # not None: this call is being captured into a CUDA graph
         loss = None
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        if dev_state is None:
+            self.flush_graph_steps()
         for group in self.param_groups:
             ps = [p for p in group["params"] if p.grad is not None]
             if not ps:
@@ -42,18 +66,20 @@ class FusedAdam(torch.optim.Optimizer):
                     st["step"] = 0
                     st["exp_avg"] = torch.zeros_like(p)
                     st["exp_avg_sq"] = torch.zeros_like(p)
-                st["step"] += 1
+                if dev_state is None:
+                    st["step"] += 1
             step = self.state[ps[0]]["step"]
             dev = ps[0].device
             if self.l1_value is None or self.l1_value.device != dev:
                 self.l1_value = torch.zeros((), dtype=torch.float32, device=dev)
             self.l1_value.zero_()
             numel = (C.c_int64 * len(ps))(*[p.numel() for p in ps])
-            check(lib().mmf_adam_step_multi(
+            fn = lib().mmf_adam_step_multi if dev_state is None else lib().mmf_adam_step_multi_dev
+            check(fn(
                 ptr_array([p.data_ptr() for p in ps]), ptr_array([p.grad.data_ptr() for p in ps]),
                 ptr_array([self.state[p]["exp_avg"].data_ptr() for p in ps]),
-                ptr_array([self.state[p]["exp_avg_sq"].data_ptr() for p in ps]), numel, len(ps), step,
-                float(group["lr"]), float(group["betas"][0]), float(group["betas"][1]), float(group["eps"]),
+                ptr_array([self.state[p]["exp_avg_sq"].data_ptr() for p in ps]), numel, len(ps),
+                step if dev_state is None else dev_state.step_ptr, float(group["lr"]), float(group["betas"][0]), float(group["betas"][1]), float(group["eps"]),
                 float(group["weight_decay"]), float(grad_scale), float(group["l1_lambda"]), int(zero_grad),
                 self.l1_value.data_ptr(), torch.cuda.current_stream().cuda_stream), "mmf_adam_step_multi")
             # parameters changed in place behind autograd's back: bump the version counters (no kernel) so that the

@@ -55,9 +55,37 @@ from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     radio_epoch_fused(4); torch.cuda.synchronize()
 launches = sum(e.count for e in prof.key_averages() if e.device_type.name == "CUDA") / 4
+if os.environ.get("MMF_CFG2_KERNELS"):
+    for e_ in sorted((e for e in prof.key_averages() if e.device_type.name == "CUDA"), key=lambda e: -e.device_time_total)[:30]:
+        print(f"  {e_.device_time_total / 4:8.1f} us  x{e_.count / 4:4.1f}  {e_.key[:150]}")
 print(json.dumps({"config": "2 radio_attention_mil batch-1 training loop, fused_step", "patients": 256, "ms_per_patient": dt / 256 * 1e3,
                   "patients_per_s": 256 / dt, "kernel_launches_per_patient": launches,
                   "note": "MIL_Attention_fc_surv_radio.fused_step + fused Adam per patient, eager launches from Python, wall clock incl. host"}))
+# ---- config 2, the same patient step (fused_step + fused Adam) replayed as ONE CUDA graph per slice count
+model.train()
+opt = get_optim(model, args)
+
+
+def radio_epoch_graphed(count):
+    for i in range(count):
+        model.graphed_fused_step(opt, Y=Y, c=c, alpha=0.0, **bags[i % len(bags)])
+
+
+radio_epoch_graphed(2 * len(bags))      # every slice count of the 32 patients is captured here (first visit: eager step + capture)
+torch.cuda.synchronize()
+t0 = time.perf_counter(); radio_epoch_graphed(256); torch.cuda.synchronize(); dt = time.perf_counter() - t0
+ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+entry = next(iter(model._graph_family.graphs.values()))
+ev0.record()
+for _ in range(50):
+    entry.graph.replay()
+ev1.record(); torch.cuda.synchronize()
+print(json.dumps({"config": "2 radio_attention_mil batch-1 training loop, graphed_fused_step", "patients": 256,
+                  "ms_per_patient": dt / 256 * 1e3, "patients_per_s": 256 / dt, "graphs": len(model._graph_family.graphs),
+                  "graph_replay_gpu_ms": ev0.elapsed_time(ev1) / 50,
+                  "launches_per_patient_from_python": 4,
+                  "note": "fused_step + fused Adam per patient as one CUDA-graph launch per slice count (device-resident Adam step "
+                          "count and dropout seeds), + 1 stack and 2 small copies into the static inputs; wall clock incl. host"}))
 # ---- config 3
 B = 512
 head = cox_heads.multimodal_pretrained(mode="radio_path_omic", train_type="kronecker", n_classes=4).to(dev).train()
@@ -71,7 +99,7 @@ for name, lf in (("cox", CoxSurvLoss()), ("ranking", RankingSurvLoss())):
         loss = lf(risks=risk.reshape(-1), times=times, c=cens) if name == "ranking" else lf(risks=risk, times=times, c=cens)
         loss.backward()
         opt3.step(zero_grad=True)
-        return loss
+        return loss.detach()
     for _ in range(3):
         it()
     torch.cuda.synchronize()
@@ -82,3 +110,17 @@ for name, lf in (("cox", CoxSurvLoss()), ("ranking", RankingSurvLoss())):
     print(json.dumps({"config": f"3 multimodal kronecker head + {name} loss, B=512 cohort", "ms_per_step": dt * 1e3,
                       "patients_per_s": B / dt, "loss": l.item(),
                       "note": "fwd + loss + bwd + fused Adam, eager, wall clock; the reference's Cox / ranking host loops alone take 2.5 s / 7.2 s at B=512 (SURVEY.md)"}))
+
+    # the same cohort step replayed as one CUDA graph (static embeddings; device-resident Adam step count / dropout seeds)
+    from multimodalfusion_b200.graphs import GraphedStep
+    graphed = GraphedStep(it, optimizers=(opt3,), modules=(head,))
+    for _ in range(3):
+        graphed()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(50):
+        l = graphed()
+    torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 50
+    print(json.dumps({"config": f"3 multimodal kronecker head + {name} loss, B=512 cohort, CUDA-graph replay", "ms_per_step": dt * 1e3,
+                      "patients_per_s": B / dt, "loss": l.item(),
+                      "note": "GraphedStep(fwd + loss + bwd + fused Adam): one graph launch per cohort step, wall clock"}))
