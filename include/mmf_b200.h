@@ -384,6 +384,29 @@ int mmf_ranking_fwd_bwd(const float* risks, const float* times, const float* c, 
                         int reduction, float* loss, float* drisks, int64_t* n_pairs, void* workspace,
                         size_t workspace_bytes, void* stream);
 
+/* ---- XlinearFusion gated reduction, all modalities in one launch ---------------
+ * models/model_modules.py:156-166: per modality i  h_i = relu(Wh_i v_i + bh_i), z_i = sigmoid(Wz_i cat(v_1..v_m) + bz_i),
+ * o_i = dropout(relu(Wo_i (z_i * h_i) + bo_i)), then a constant 1 is appended (the Kronecker factor [B, S + 1]).
+ * S = dim / scale_dim must be 16 (every configuration of the reference), dim a multiple of 256, m = 2..4.
+ * The concatenation is never formed. mask (nullable): [m, B, 16] dropout scale mask (0 or 1 / (1 - p)), made by the caller.
+ * Forward outputs: h, z [m, B, 16] (kept for the backward), o [m, B, 17]. */
+typedef struct MmfXfusionMod {
+  const float* v;                    /* [B, dim] embedding of this modality                          */
+  const float* Wh; const float* bh;  /* reduce[i][0][0]: Linear(dim, 16)                              */
+  const float* Wz; const float* bz;  /* reduce[i][1][0]: Linear(dim * m, 16)                          */
+  const float* Wo; const float* bo;  /* reduce[i][2][0]: Linear(16, 16)                               */
+} MmfXfusionMod;
+typedef struct MmfXfusionGrads {     /* per modality; all written (accumulate = 0) or added to (accumulate = 1)        */
+  float* dWh; float* dbh; float* dWz; float* dbz; float* dWo; float* dbo;
+  float* dv;                         /* [B, dim] gradient of the embedding (always overwritten), or NULL if not needed */
+} MmfXfusionGrads;
+int mmf_xfusion_gate_fwd(const MmfXfusionMod* mods_host, int m, int B, int dim, const float* mask, float* h, float* z,
+                         float* o, void* stream);
+/* d_o: [m, B, 17] (the constant column's gradient is ignored); workspace: m * B * 32 floats ([dz | dh] per sample). */
+int mmf_xfusion_gate_bwd(const MmfXfusionMod* mods_host, int m, int B, int dim, const float* mask, const float* h,
+                         const float* z, const float* o, const float* d_o, const MmfXfusionGrads* grads_host,
+                         int accumulate, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- training-step glue -------------------------------------------------
  * Fused multi-tensor Adam: torch.optim.Adam(lr, weight_decay) as the reference builds it (utils/utils.py:144-151), one
  * launch for all parameter tensors; step >= 1 is the 1-based step count (bias corrections). Per element:

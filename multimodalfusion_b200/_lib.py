@@ -94,6 +94,17 @@ class HeadStep(C.Structure):
     ]
 
 
+class XfusionMod(C.Structure):
+    """MmfXfusionMod (include/mmf_b200.h): one modality of the fused XlinearFusion gate."""
+    _fields_ = [("v", C.c_void_p), ("Wh", C.c_void_p), ("bh", C.c_void_p), ("Wz", C.c_void_p), ("bz", C.c_void_p),
+                ("Wo", C.c_void_p), ("bo", C.c_void_p)]
+
+
+class XfusionGrads(C.Structure):
+    _fields_ = [("dWh", C.c_void_p), ("dbh", C.c_void_p), ("dWz", C.c_void_p), ("dbz", C.c_void_p), ("dWo", C.c_void_p),
+                ("dbo", C.c_void_p), ("dv", C.c_void_p)]
+
+
 _vp, _i, _i64, _sz, _f, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_float, C.c_uint64
 _PP = C.POINTER(C.c_void_p)
 
@@ -157,6 +168,9 @@ SIGNATURES = {
     "mmf_cox_workspace_bytes": (_sz, [_i]),
     "mmf_cox_fwd_bwd": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "mmf_adam_step_multi": (_i, [_PP, _PP, _PP, _PP, C.POINTER(C.c_int64), _i, _i, _f, _f, _f, _f, _f, _f, _f, _i, _vp, _vp]),
+    "mmf_xfusion_gate_fwd": (_i, [C.POINTER(XfusionMod), _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "mmf_xfusion_gate_bwd": (_i, [C.POINTER(XfusionMod), _i, _i, _i, _vp, _vp, _vp, _vp, _vp, C.POINTER(XfusionGrads), _i,
+                                  _vp, _sz, _vp]),
     "mmf_adam_step_multi_dev": (_i, [_PP, _PP, _PP, _PP, C.POINTER(C.c_int64), _i, _vp, _f, _f, _f, _f, _f, _f, _f, _i, _vp, _vp]),
     "mmf_step_state_advance": (_i, [_vp, _i, _vp]),
     "mmf_percentile_of_score": (_i, [_vp, _i, _vp, _i, _vp, _vp]),

@@ -166,6 +166,30 @@ class KronEncoderTrain(torch.autograd.Function):
         return (dW, db, None, *d_o)
 
 
+class XfusionGate(torch.autograd.Function):
+    """Per-modality gated reduction of XlinearFusion for ALL modalities in one forward launch and two or three backward
+    launches (models/model_modules.py:156-166; csrc/xfusion_gate.cuh). apply(m, mask, v_1..v_m, then (Wh, bh, Wz, bz, Wo, bo)
+    per modality) -> o [m, B, 17] (o[i] = cat(dropout(relu(Wo (z * h) + bo)), 1))."""
+
+    @staticmethod
+    def forward(ctx, m: int, mask, *tensors):
+        v_list = tensors[:m]
+        params = [tensors[m + 6 * i: m + 6 * i + 6] for i in range(m)]
+        h, z, o = ops.xfusion_gate_fwd(v_list, params, mask)
+        ctx.m, ctx.mask = m, mask
+        ctx.save_for_backward(h, z, o, *tensors)
+        return o
+
+    @staticmethod
+    def backward(ctx, d_o):
+        m = ctx.m
+        h, z, o, *tensors = ctx.saved_tensors
+        v_list = tensors[:m]
+        params = [tensors[m + 6 * i: m + 6 * i + 6] for i in range(m)]
+        dv, grads = ops.xfusion_gate_bwd(v_list, params, ctx.mask, h, z, o, d_o, ctx.needs_input_grad[2:2 + m])
+        return (None, None, *dv, *[g for gs in grads for g in gs])
+
+
 class SegmentedLinearBf16(torch.autograd.Function):
     """y = cat(segs, 1) @ W^T + b on the bf16 tensor-core GEMM, the modality bags are read in place
     (radio reduce_dim: models/model_attention_mil_radio.py:81-82). Output bf16 feeds AmilPool."""

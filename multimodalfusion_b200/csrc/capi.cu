@@ -15,6 +15,7 @@
 #include "p2p_allreduce.cuh"
 #include "train_glue.cuh"
 #include "head_kernels.cuh"
+#include "xfusion_gate.cuh"
 #include <math.h>
 
 using namespace mmf;
@@ -969,6 +970,54 @@ int mmf_step_state_advance(uint64_t* state, int n_seeds, void* stream) {
   if (!state || n_seeds < 0 || n_seeds > 1023) return MMF_E_INVALID;
   step_state_advance_kernel<<<(n_seeds + 1 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<unsigned long long*>(state), n_seeds);
+  return launch_status();
+}
+
+namespace {
+int xf_pack(const MmfXfusionMod* mods, int m, int B, int dim, XfMods* P) {
+  if (!mods || m < 2 || m > XF_MAX_MOD || B <= 0 || dim <= 0 || dim % XF_KC != 0) return MMF_E_INVALID;
+  *P = XfMods{};
+  P->m = m; P->B = B; P->dim = dim;
+  for (int i = 0; i < m; ++i) {
+    const MmfXfusionMod& q = mods[i];
+    if (!q.v || !q.Wh || !q.bh || !q.Wz || !q.bz || !q.Wo || !q.bo) return MMF_E_INVALID;
+    if ((reinterpret_cast<uintptr_t>(q.v) & 15u) != 0) return MMF_E_ALIGN;
+    P->mod[i] = XfMod{q.v, q.Wh, q.bh, q.Wz, q.bz, q.Wo, q.bo};
+  }
+  return MMF_OK;
+}
+}  // namespace
+
+int mmf_xfusion_gate_fwd(const MmfXfusionMod* mods_host, int m, int B, int dim, const float* mask, float* h, float* z,
+                         float* o, void* stream) {
+  XfMods P;
+  MMF_TRY(xf_pack(mods_host, m, B, dim, &P));
+  if (!h || !z || !o) return MMF_E_INVALID;
+  xfusion_gate_fwd_kernel<<<dim3((B + XF_RB - 1) / XF_RB, m), 256, 0, (cudaStream_t)stream>>>(P, mask, h, z, o);
+  return launch_status();
+}
+
+int mmf_xfusion_gate_bwd(const MmfXfusionMod* mods_host, int m, int B, int dim, const float* mask, const float* h,
+                         const float* z, const float* o, const float* d_o, const MmfXfusionGrads* grads_host,
+                         int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
+  XfMods P;
+  MMF_TRY(xf_pack(mods_host, m, B, dim, &P));
+  if (!h || !z || !o || !d_o || !grads_host) return MMF_E_INVALID;
+  if (!workspace || workspace_bytes < sizeof(float) * (size_t)m * (size_t)B * 2 * XF_S) return MMF_E_WORKSPACE;
+  XfGrads G = {};
+  bool any_dv = false;
+  for (int i = 0; i < m; ++i) {
+    const MmfXfusionGrads& g = grads_host[i];
+    if (!g.dWh || !g.dbh || !g.dWz || !g.dbz || !g.dWo || !g.dbo) return MMF_E_INVALID;
+    G.dWh[i] = g.dWh; G.dbh[i] = g.dbh; G.dWz[i] = g.dWz; G.dbz[i] = g.dbz; G.dWo[i] = g.dWo; G.dbo[i] = g.dbo;
+    G.dv[i] = g.dv;
+    any_dv = any_dv || g.dv != nullptr;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  float* dhz = static_cast<float*>(workspace);
+  xfusion_gate_bwd_small_kernel<<<m, 1024, 0, st>>>(P, mask, h, z, o, d_o, dhz, G, accumulate);
+  xfusion_gate_bwd_wgrad_kernel<<<dim3(dim * m / 64, m), 256, 0, st>>>(P, dhz, G, accumulate);
+  if (any_dv) xfusion_gate_bwd_dv_kernel<<<dim3((B + XF_RB - 1) / XF_RB, m), 256, 0, st>>>(P, dhz, G);
   return launch_status();
 }
 

@@ -356,6 +356,56 @@ def dense_bwd_into(x, W, y, dy, dW: torch.Tensor, db: torch.Tensor) -> None:
                               None, in_dim, 0, _p(dW), _p(db), _stream()), "mmf_dense_bwd")
 
 
+def _xf_mods(v_list, params):
+    arr = (_lib.XfusionMod * len(v_list))()
+    for i, (v, (Wh, bh, Wz, bz, Wo, bo)) in enumerate(zip(v_list, params)):
+        arr[i] = _lib.XfusionMod(_p(v), _p(Wh), _p(bh), _p(Wz), _p(bz), _p(Wo), _p(bo))
+    return arr
+
+
+def xfusion_gate_supported(v_list, params) -> bool:
+    """Shapes the fused gate kernels cover: 2-4 modalities of equal width, dim % 256 == 0, gate width 16."""
+    if not 2 <= len(v_list) <= 4:
+        return False
+    dim = v_list[0].shape[1]
+    return (dim % 256 == 0 and all(v.dim() == 2 and v.shape == v_list[0].shape for v in v_list)
+            and all(p_[0].shape == (16, dim) and p_[2].shape == (16, dim * len(v_list)) and p_[4].shape == (16, 16) for p_ in params))
+
+
+def xfusion_gate_fwd(v_list, params, mask: Optional[torch.Tensor]):
+    """The gated reduction of every modality of XlinearFusion in ONE launch (models/model_modules.py:156-166).
+    v_list: m x [B, dim]; params: m x (Wh, bh, Wz, bz, Wo, bo); mask: [m, B, 16] dropout scale mask or None.
+    Returns (h, z [m, B, 16], o [m, B, 17] with the constant column)."""
+    v_list = [_f32c(v) for v in v_list]
+    params = [tuple(_f32c(t) for t in p_) for p_ in params]
+    _require_cuda(*v_list)
+    m, (B, dim) = len(v_list), v_list[0].shape
+    h = torch.empty(m, B, 16, dtype=torch.float32, device=v_list[0].device)
+    z, o = torch.empty_like(h), torch.empty(m, B, 17, dtype=torch.float32, device=h.device)
+    mask = None if mask is None else _f32c(mask)
+    check(lib().mmf_xfusion_gate_fwd(_xf_mods(v_list, params), m, B, dim, _p(mask), _p(h), _p(z), _p(o), _stream()),
+          "mmf_xfusion_gate_fwd")
+    return h, z, o
+
+
+def xfusion_gate_bwd(v_list, params, mask, h, z, o, d_o, need_dv):
+    """Gradients of xfusion_gate_fwd: returns (dv list (None where not needed), m x (dWh, dbh, dWz, dbz, dWo, dbo))."""
+    v_list = [_f32c(v) for v in v_list]
+    params = [tuple(_f32c(t) for t in p_) for p_ in params]
+    m, (B, dim) = len(v_list), v_list[0].shape
+    d_o = _f32c(d_o)
+    grads = [tuple(torch.empty_like(t) for t in p_) for p_ in params]
+    dv = [torch.empty_like(v) if nd else None for v, nd in zip(v_list, need_dv)]
+    garr = (_lib.XfusionGrads * m)()
+    for i in range(m):
+        garr[i] = _lib.XfusionGrads(*[_p(t) for t in grads[i]], _p(dv[i]))
+    ws = torch.empty(m * B * 32, dtype=torch.float32, device=d_o.device)
+    check(lib().mmf_xfusion_gate_bwd(_xf_mods(v_list, params), m, B, dim, _p(None if mask is None else _f32c(mask)), _p(h),
+                                     _p(z), _p(o), _p(d_o), garr, 0, _p(ws), ws.numel() * 4, _stream()),
+          "mmf_xfusion_gate_bwd")
+    return dv, grads
+
+
 def kron_enc_fwd(o_list, W, b, dropout: bool = False, seed: int = 0) -> torch.Tensor:
     """relu(W (o_1 x o_2 [x o_3 [x o_4]]) + b); dropout: train-mode Dropout(0.25) on the (never materialised) product,
     mask from the counter hash of (seed, stream 3, row, column)."""

@@ -256,6 +256,22 @@ def snn_forward(x, layers: List[Tuple[torch.Tensor, torch.Tensor]]):
     return x
 
 
+def xfusion_gate(v_list, reduce_params, o_scale=None):
+    """The per-modality gated reduction of XlinearFusion (models/model_modules.py:156-166), restated for the fused gate
+    kernels (csrc/xfusion_gate.cuh): returns o [m, B, S + 1]. reduce_params[i] = ((Wh,bh),(Wz,bz),(Wo,bo));
+    o_scale: optional [m, B, S] inverted-dropout scale mask of reduce[i][2][2] (nn.Dropout on o)."""
+    v_cat = torch.cat(v_list, dim=1)
+    outs = []
+    for i, (v, ((Wh, bh), (Wz, bz), (Wo, bo))) in enumerate(zip(v_list, reduce_params)):
+        h = torch.relu(v @ Wh.t() + bh)
+        z = torch.sigmoid(v_cat @ Wz.t() + bz)
+        o = torch.relu((z * h) @ Wo.t() + bo)
+        if o_scale is not None:
+            o = o * o_scale[i]
+        outs.append(torch.cat([o, torch.ones(o.shape[0], 1, dtype=o.dtype, device=o.device)], dim=1))
+    return torch.stack(outs)
+
+
 def xfusion_forward(v_list, reduce_params, enc1, enc2, skip=True, fused_scale=None):
     """XlinearFusion.forward in eval mode, gate=1, use_bilinear=0 (models/model_modules.py:156-178).
     reduce_params[i] = ((Wh,bh),(Wz,bz),(Wo,bo)); enc1/enc2 = (W,b). fused_scale: optional [B, E^m] inverted-dropout
