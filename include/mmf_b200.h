@@ -310,11 +310,20 @@ int mmf_dense_bwd(const float* x, int64_t ldx, const float* W, int B, int in_dim
 int mmf_kron_enc_fwd(const float* const* o /*HOST array of m device ptrs [B,E]*/, int m, int E, int B,
                      const float* W /*[H,E^m]*/, const float* b, int H, float* out /*[B,H]*/,
                      void* stream);
-/* Train-mode form: Dropout(0.25) on the (never materialised) product — element (b, kk) kept iff the counter hash of
- * (seed, stream 3, b, kk) says so, scaled by 1/0.75 (XlinearFusion.post_fusion_dropout, models/model_modules.py:170);
- * the backward regenerates the mask from the same seed. dropout = 0: identical to mmf_kron_enc_fwd / _bwd. */
+/* Train-mode form: dropout on the (never materialised) product — element (b, kk) kept iff the counter hash of
+ * (seed, stream 3, b, kk) says so (XlinearFusion.post_fusion_dropout, models/model_modules.py:170); the backward
+ * regenerates the mask from the same seed. dropout = 0: identical to mmf_kron_enc_fwd / _bwd; dropout = 1: p = 0.25
+ * (2-bit fields, scale 1/0.75: the reference's default rate); dropout = 2..65535: p = dropout / 65536 with one 16-bit
+ * field per element and scale 65536 / (65536 - dropout) — any rate (the cohort heads build XlinearFusion with 0.7,
+ * models/coxranking_models_pretrained.py:107). */
 int mmf_kron_enc_train_fwd(const float* const* o, int m, int E, int B, const float* W, const float* b, int H,
                            int dropout, uint64_t seed, float* out, void* stream);
+/* The same with a caller-owned workspace for the deterministic split-K form (few output tiles, K = E^m long: see
+ * mmf_dense_fwd_ws); mmf_kron_enc_fwd_workspace_bytes() returns 0 when the shape is not split. */
+size_t mmf_kron_enc_fwd_workspace_bytes(int m, int E, int B, int H);
+int mmf_kron_enc_train_fwd_ws(const float* const* o, int m, int E, int B, const float* W, const float* b, int H,
+                              int dropout, uint64_t seed, float* out, void* workspace, size_t workspace_bytes,
+                              void* stream);
 int mmf_kron_enc_train_bwd(const float* const* o, int m, int E, int B, const float* W, int H, int dropout,
                            uint64_t seed, const float* out, const float* dout, float* const* d_o, float* dW,
                            float* db, void* workspace, size_t workspace_bytes, void* stream);
@@ -402,7 +411,9 @@ typedef struct MmfXfusionGrads {     /* per modality; all written (accumulate = 
 } MmfXfusionGrads;
 int mmf_xfusion_gate_fwd(const MmfXfusionMod* mods_host, int m, int B, int dim, const float* mask, float* h, float* z,
                          float* o, void* stream);
-/* d_o: [m, B, 17] (the constant column's gradient is ignored); workspace: m * B * 32 floats ([dz | dh] per sample). */
+/* d_o: [m, B, 17] (the constant column's gradient is ignored); workspace: mmf_xfusion_gate_bwd_workspace_bytes(m, B, dim)
+ * ([dz | dh] per sample + the partial sums of up to 16 batch slices, added in a fixed order: deterministic). */
+size_t mmf_xfusion_gate_bwd_workspace_bytes(int m, int B, int dim);
 int mmf_xfusion_gate_bwd(const MmfXfusionMod* mods_host, int m, int B, int dim, const float* mask, const float* h,
                          const float* z, const float* o, const float* d_o, const MmfXfusionGrads* grads_host,
                          int accumulate, void* workspace, size_t workspace_bytes, void* stream);

@@ -154,6 +154,8 @@ SIGNATURES = {
     "mmf_kron_enc_workspace_bytes": (_sz, [_i, _i, _i]),
     "mmf_kron_enc_bwd": (_i, [_PP, _i, _i, _i, _vp, _i, _vp, _vp, _PP, _vp, _vp, _vp, _sz, _vp]),
     "mmf_kron_enc_train_fwd": (_i, [_PP, _i, _i, _i, _vp, _vp, _i, _i, _u64, _vp, _vp]),
+    "mmf_kron_enc_fwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "mmf_kron_enc_train_fwd_ws": (_i, [_PP, _i, _i, _i, _vp, _vp, _i, _i, _u64, _vp, _vp, _sz, _vp]),
     "mmf_kron_enc_train_bwd": (_i, [_PP, _i, _i, _i, _vp, _i, _i, _u64, _vp, _vp, _PP, _vp, _vp, _vp, _sz, _vp]),
     "mmf_hazard_head_fwd": (_i, [_vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "mmf_hazard_head_bwd": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -169,6 +171,7 @@ SIGNATURES = {
     "mmf_cox_fwd_bwd": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "mmf_adam_step_multi": (_i, [_PP, _PP, _PP, _PP, C.POINTER(C.c_int64), _i, _i, _f, _f, _f, _f, _f, _f, _f, _i, _vp, _vp]),
     "mmf_xfusion_gate_fwd": (_i, [C.POINTER(XfusionMod), _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "mmf_xfusion_gate_bwd_workspace_bytes": (_sz, [_i, _i, _i]),
     "mmf_xfusion_gate_bwd": (_i, [C.POINTER(XfusionMod), _i, _i, _i, _vp, _vp, _vp, _vp, _vp, C.POINTER(XfusionGrads), _i,
                                   _vp, _sz, _vp]),
     "mmf_adam_step_multi_dev": (_i, [_PP, _PP, _PP, _PP, C.POINTER(C.c_int64), _i, _vp, _f, _f, _f, _f, _f, _f, _f, _i, _vp, _vp]),

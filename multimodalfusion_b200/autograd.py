@@ -148,22 +148,22 @@ class KronEncoder(torch.autograd.Function):
 
 
 class KronEncoderTrain(torch.autograd.Function):
-    """KronEncoder with train-mode Dropout(0.25) on the outer product (XlinearFusion.post_fusion_dropout,
+    """KronEncoder with train-mode Dropout(p) on the outer product (XlinearFusion.post_fusion_dropout,
     models/model_modules.py:170): the mask comes from the counter hash of (seed, stream 3, row, column) inside the
     kernels — forward and backward — so the [B, 17^m] product is not materialised in training either."""
 
     @staticmethod
-    def forward(ctx, W, b, seed: int, *o_list):
-        out = ops.kron_enc_fwd(o_list, W, b, dropout=True, seed=seed)
+    def forward(ctx, W, b, seed: int, p: float, *o_list):
+        out = ops.kron_enc_fwd(o_list, W, b, dropout=p, seed=seed)
         ctx.save_for_backward(W, out, *o_list)
-        ctx.seed = seed
+        ctx.seed, ctx.p = seed, p
         return out
 
     @staticmethod
     def backward(ctx, dout):
         W, out, *o_list = ctx.saved_tensors
-        d_o, dW, db = ops.kron_enc_bwd(o_list, W, out, dout, dropout=True, seed=ctx.seed)
-        return (dW, db, None, *d_o)
+        d_o, dW, db = ops.kron_enc_bwd(o_list, W, out, dout, dropout=ctx.p, seed=ctx.seed)
+        return (dW, db, None, None, *d_o)
 
 
 class XfusionGate(torch.autograd.Function):

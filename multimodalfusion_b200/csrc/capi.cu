@@ -734,14 +734,47 @@ int mmf_kron_enc_fwd(const float* const* o, int m, int E, int B, const float* W,
   return mmf_kron_enc_train_fwd(o, m, E, B, W, b, H, 0, 0, out, stream);
 }
 
+namespace {
+inline KronElem kron_elem(const float* const* o, int m, int E, uint64_t seed, int dropout) {
+  return KronElem{o[0], o[1], m >= 3 ? o[2] : nullptr, m >= 4 ? o[3] : nullptr, m, E, seed, dropout,
+                  dropout > 1 ? 65536.0f / (65536.0f - (float)dropout) : 1.0f};
+}
+}  // namespace
+
 int mmf_kron_enc_train_fwd(const float* const* o, int m, int E, int B, const float* W, const float* b,
                            int H, int dropout, uint64_t seed, float* out, void* stream) {
-  if (!o || m < 2 || m > 4 || E <= 0 || B <= 0 || !W || !out) return MMF_E_INVALID;
-  KronElem e{o[0], o[1], m >= 3 ? o[2] : nullptr, m >= 4 ? o[3] : nullptr, m, E, seed, dropout ? 1 : 0};
+  return mmf_kron_enc_train_fwd_ws(o, m, E, B, W, b, H, dropout, seed, out, nullptr, 0, stream);
+}
+
+size_t mmf_kron_enc_fwd_workspace_bytes(int m, int E, int B, int H) {
+  long long kk = 1;
+  for (int t = 0; t < m; ++t) kk *= E;
+  if (B <= 0 || H <= 0 || kk <= 0 || kk > (1ll << 30)) return 0;
+  const int splits = dense_fwd_splits(B, (int)kk, H);
+  return splits > 1 ? sizeof(float) * (size_t)splits * (size_t)B * (size_t)H : 0;
+}
+
+int mmf_kron_enc_train_fwd_ws(const float* const* o, int m, int E, int B, const float* W, const float* b, int H,
+                              int dropout, uint64_t seed, float* out, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+  if (!o || m < 2 || m > 4 || E <= 0 || B <= 0 || !W || !out || dropout < 0 || dropout > 65535) return MMF_E_INVALID;
+  KronElem e = kron_elem(o, m, E, seed, dropout);
   if (e.width() > (1ll << 30)) return MMF_E_INVALID;
   const int KK = (int)e.width();
-  launch_sgemm(B, H, KK, LoadKronA{e}, LoadRowMajor{W, KK}, EpiBiasAct{out, H, b, MMF_ACT_RELU},
-               (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int splits = dense_fwd_splits(B, KK, H);
+  if (splits > 1 && workspace && workspace_bytes >= mmf_kron_enc_fwd_workspace_bytes(m, E, B, H)) {
+    // few output tiles, K = E^m (4913 for three modalities): deterministic split-K as mmf_dense_fwd_ws
+    float* ws = static_cast<float*>(workspace);
+    dim3 grid((H + 63) / 64, (B + 63) / 64, splits);
+    sgemm_functor_kernel<LoadKronA, LoadRowMajor, EpiSlice><<<grid, 256, 0, st>>>(
+        B, H, KK, LoadKronA{e}, LoadRowMajor{W, KK}, EpiSlice{ws, (long long)B * H, H});
+    long long blocks = ((long long)B * H + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    splitk_fixup_kernel<<<(int)blocks, 256, 0, st>>>(ws, splits, B, H, b, MMF_ACT_RELU, out, H);
+    return launch_status();
+  }
+  launch_sgemm(B, H, KK, LoadKronA{e}, LoadRowMajor{W, KK}, EpiBiasAct{out, H, b, MMF_ACT_RELU}, st);
   return launch_status();
 }
 
@@ -760,10 +793,10 @@ int mmf_kron_enc_bwd(const float* const* o, int m, int E, int B, const float* W,
 int mmf_kron_enc_train_bwd(const float* const* o, int m, int E, int B, const float* W, int H, int dropout,
                            uint64_t seed, const float* out, const float* dout, float* const* d_o, float* dW,
                            float* db, void* workspace, size_t workspace_bytes, void* stream) {
-  if (!o || m < 2 || m > 4 || !W || !out || !dout || !workspace) return MMF_E_INVALID;
+  if (!o || m < 2 || m > 4 || !W || !out || !dout || !workspace || dropout < 0 || dropout > 65535) return MMF_E_INVALID;
   if (workspace_bytes < mmf_kron_enc_workspace_bytes(m, E, B)) return MMF_E_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
-  KronElem e{o[0], o[1], m >= 3 ? o[2] : nullptr, m >= 4 ? o[3] : nullptr, m, E, seed, dropout ? 1 : 0};
+  KronElem e = kron_elem(o, m, E, seed, dropout);
   if (e.width() > (1ll << 30)) return MMF_E_INVALID;
   const int KK = (int)e.width();
   float* dkron = reinterpret_cast<float*>(workspace);
@@ -997,13 +1030,19 @@ int mmf_xfusion_gate_fwd(const MmfXfusionMod* mods_host, int m, int B, int dim, 
   return launch_status();
 }
 
+size_t mmf_xfusion_gate_bwd_workspace_bytes(int m, int B, int dim) {
+  if (m < 2 || m > XF_MAX_MOD || B <= 0 || dim <= 0) return 0;
+  const size_t Z = (size_t)xf_slices(B);
+  return sizeof(float) * ((size_t)m * B * 2 * XF_S + Z * m * XF_SMALL_OUT + Z * m * XF_S * ((size_t)dim * m + dim));
+}
+
 int mmf_xfusion_gate_bwd(const MmfXfusionMod* mods_host, int m, int B, int dim, const float* mask, const float* h,
                          const float* z, const float* o, const float* d_o, const MmfXfusionGrads* grads_host,
                          int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
   XfMods P;
   MMF_TRY(xf_pack(mods_host, m, B, dim, &P));
   if (!h || !z || !o || !d_o || !grads_host) return MMF_E_INVALID;
-  if (!workspace || workspace_bytes < sizeof(float) * (size_t)m * (size_t)B * 2 * XF_S) return MMF_E_WORKSPACE;
+  if (!workspace || workspace_bytes < mmf_xfusion_gate_bwd_workspace_bytes(m, B, dim)) return MMF_E_WORKSPACE;
   XfGrads G = {};
   bool any_dv = false;
   for (int i = 0; i < m; ++i) {
@@ -1014,9 +1053,14 @@ int mmf_xfusion_gate_bwd(const MmfXfusionMod* mods_host, int m, int B, int dim, 
     any_dv = any_dv || g.dv != nullptr;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  const int Z = xf_slices(B);
   float* dhz = static_cast<float*>(workspace);
-  xfusion_gate_bwd_small_kernel<<<m, 1024, 0, st>>>(P, mask, h, z, o, d_o, dhz, G, accumulate);
-  xfusion_gate_bwd_wgrad_kernel<<<dim3(dim * m / 64, m), 256, 0, st>>>(P, dhz, G, accumulate);
+  float* part_small = dhz + (size_t)m * B * 2 * XF_S;
+  float* part_w = part_small + (size_t)Z * m * XF_SMALL_OUT;
+  xfusion_gate_bwd_small_kernel<<<dim3(Z, m), 1024, 0, st>>>(P, mask, h, z, o, d_o, dhz, part_small);
+  xfusion_gate_bwd_wgrad_kernel<<<dim3(dim * m / 64, m, Z), 256, 0, st>>>(P, dhz, part_w);
+  const long long total = (long long)m * (XF_S * ((long long)dim * m + dim) + XF_SMALL_OUT);
+  xfusion_gate_bwd_finalize_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(P, part_small, part_w, G, accumulate);
   if (any_dv) xfusion_gate_bwd_dv_kernel<<<dim3((B + XF_RB - 1) / XF_RB, m), 256, 0, st>>>(P, dhz, G);
   return launch_status();
 }

@@ -98,13 +98,21 @@ constexpr uint32_t KRON_DROP_STREAM = 3;
 struct KronElem {
   const float* o0; const float* o1; const float* o2; const float* o3; int m; int E;
   unsigned long long seed; int drop;   // seed with bit 63 set = device address of the seed word (MMF_SEED_DEVICE, amil_tile.cuh)
+  float inv_keep;                      // 1 / (1 - p) of the 16-bit scheme
+  // drop: 0 = no dropout; 1 = p = 0.25 with the 2-bit fields shared with the attention-MIL kernels; 2..65535 = drop
+  // probability drop / 65536 (any rate, e.g. the cohort heads' 0.7): one 32-bit hash per column PAIR, 16 bits per element,
+  // dropped iff the field is below `drop` (oracle.dropout_scale_mask_p)
   __device__ __forceinline__ float keep_scale(int b, int kk) const {
     if (!drop) return 1.f;
     // (these kernels are launched without the PDL attribute: a read-only load of the word an EARLIER kernel wrote is safe,
     // and the compiler may hoist it out of the k loop)
     const unsigned long long sd = (seed >> 63) ? __ldg(reinterpret_cast<const unsigned long long*>(seed & 0x7FFFFFFFFFFFFFFFull)) : seed;
-    return drop_keep(drop_bits16(drop_row_state(sd, KRON_DROP_STREAM, (uint32_t)b), (uint32_t)kk >> 4), (uint32_t)kk & 15u)
-               ? (1.0f / 0.75f) : 0.f;
+    const uint32_t rs = drop_row_state(sd, KRON_DROP_STREAM, (uint32_t)b);
+    if (drop > 1) {
+      const uint32_t w = mix32(rs ^ (((uint32_t)kk >> 1) * 0xC2B2AE35U));
+      return ((w >> (16u * ((uint32_t)kk & 1u))) & 0xFFFFu) >= (uint32_t)drop ? inv_keep : 0.f;
+    }
+    return drop_keep(drop_bits16(rs, (uint32_t)kk >> 4), (uint32_t)kk & 15u) ? (1.0f / 0.75f) : 0.f;
   }
   __device__ __forceinline__ float at(int b, int kk) const { return raw(b, kk) * keep_scale(b, kk); }
   __device__ __forceinline__ float raw(int b, int kk) const {

@@ -11,8 +11,8 @@
 // and the h GEMM of modality i rides on segment i of the same pass (same x values, second weight row).
 //
 // Everything is fp32 on the CUDA cores (16 output units per layer: no tensor-core shape), deterministic (no atomics):
-// the forward is one CTA per (8 samples, modality); the weight gradients loop over the whole batch inside one CTA per
-// (64 input columns, modality).
+// the forward is one CTA per (8 samples, modality); the backward reduces the batch in up to 16 row slices whose partial
+// sums a finalize kernel adds in a fixed order.
 #pragma once
 #include <stdint.h>
 
@@ -112,22 +112,30 @@ __global__ void __launch_bounds__(256) xfusion_gate_fwd_kernel(const XfMods P, c
   }
 }
 
-// backward A: one CTA per modality walks the batch 64 samples at a time (deterministic sums):
+// The backward splits the batch into Z row slices (xf_slices): every CTA reduces its slice and stores PARTIAL sums (plain
+// stores), a finalize kernel adds the Z partials in a fixed order — deterministic, no atomics, and the two batch loops
+// (latency-bound: one global-load round trip per 32 / 64 rows) run Z-wide instead of serially.
+constexpr int XF_SMALL_OUT = XF_S * XF_S + 3 * XF_S;     // per (slice, modality): dWo [16 x 16] | dbo | dbh | dbz
+__host__ __device__ inline int xf_slices(int B) { const int z = (B + 63) / 64; return z < 1 ? 1 : (z > 16 ? 16 : z); }
+__host__ __device__ inline int xf_rows_per_slice(int B) { const int z = xf_slices(B); return ((B + z - 1) / z + 63) / 64 * 64; }
+
+// backward A: grid (Z, m), one CTA per (row slice, modality), 64 samples per iteration:
 //   dpre_o = d_o * mask * [o > 0];  dWo = dpre_o^T (z * h), dbo;  dg = dpre_o Wo;  dh = dg z [h > 0];  dz = dg h z (1 - z)
 //   dhz[m, B, 2 S] = [dz | dh] for the weight / input gradient kernels;  dbh = sum dh, dbz = sum dz
 __global__ void __launch_bounds__(1024) xfusion_gate_bwd_small_kernel(const XfMods P, const float* __restrict__ mask,
                                                                       const float* __restrict__ h, const float* __restrict__ z,
                                                                       const float* __restrict__ o, const float* __restrict__ d_o,
-                                                                      float* __restrict__ dhz, const XfGrads G, int accumulate) {
+                                                                      float* __restrict__ dhz, float* __restrict__ part_small) {
   __shared__ float dps[64][XF_S + 1], gsm[64][XF_S + 1], dhs[64][XF_S + 1], dzs[64][XF_S + 1], wo[XF_S][XF_S];
-  const int i = blockIdx.x, B = P.B;
+  const int i = blockIdx.y, B = P.B;
+  const int rows = xf_rows_per_slice(B), b_begin = blockIdx.x * rows, b_end = min(B, b_begin + rows);
   const int r = threadIdx.x >> 4, s = threadIdx.x & 15;
   if (threadIdx.x < XF_S * XF_S) wo[threadIdx.x >> 4][threadIdx.x & 15] = __ldg(P.mod[i].Wo + threadIdx.x);
   // threads 0..255 own dWo[s2][t2]; 256..271 dbo; 272..287 dbh; 288..303 dbz
   float red = 0.f;
-  for (int b0 = 0; b0 < B; b0 += 64) {
+  for (int b0 = b_begin; b0 < b_end; b0 += 64) {
     const int b = b0 + r;
-    const bool ok = b < B;
+    const bool ok = b < b_end;
     const long long idx = ((long long)i * B + b) * XF_S + s;
     float hv = 0.f, zv = 0.f, dp = 0.f;
     if (ok) {
@@ -153,45 +161,40 @@ __global__ void __launch_bounds__(1024) xfusion_gate_bwd_small_kernel(const XfMo
       const int s2 = threadIdx.x >> 4, t2 = threadIdx.x & 15;
 #pragma unroll 8
       for (int rr = 0; rr < 64; ++rr) red = fmaf(dps[rr][s2], gsm[rr][t2], red);
-    } else if (threadIdx.x < 256 + 3 * XF_S) {
+    } else if (threadIdx.x < XF_SMALL_OUT) {
       const int which = (threadIdx.x - 256) >> 4, s2 = threadIdx.x & 15;
       const float (*src)[XF_S + 1] = which == 0 ? dps : which == 1 ? dhs : dzs;
 #pragma unroll 8
       for (int rr = 0; rr < 64; ++rr) red += src[rr][s2];
     }
   }
-  if (threadIdx.x < 256) {
-    float* p = G.dWo[i] + threadIdx.x;
-    *p = accumulate ? *p + red : red;
-  } else if (threadIdx.x < 256 + 3 * XF_S) {
-    const int which = (threadIdx.x - 256) >> 4, s2 = threadIdx.x & 15;
-    float* p = (which == 0 ? G.dbo[i] : which == 1 ? G.dbh[i] : G.dbz[i]) + s2;
-    *p = accumulate ? *p + red : red;
-  }
+  if (threadIdx.x < XF_SMALL_OUT)
+    part_small[((long long)blockIdx.x * P.m + i) * XF_SMALL_OUT + threadIdx.x] = red;
 }
 
-// backward B: weight gradients. One CTA per (64 columns of the concatenated input, modality i) walks the whole batch:
-//   dWz_i[s][k] = sum_b dz_i[b][s] x[b][k];   on segment i also dWh_i[s][k - i dim] = sum_b dh_i[b][s] v_i[b][k - i dim]
+// backward B: weight gradients. One CTA per (64 columns of the concatenated input, modality i, row slice) -> partials
+//   part_w[z][i][s][0 .. KZ) : sum_b dz_i[b][s] x[b][k];   on segment i also [KZ + (k - i dim)] : sum_b dh_i[b][s] v_i[b][k - i dim]
 __global__ void __launch_bounds__(256) xfusion_gate_bwd_wgrad_kernel(const XfMods P, const float* __restrict__ dhz,
-                                                                     const XfGrads G, int accumulate) {
+                                                                     float* __restrict__ part_w) {
   __shared__ float xs[32][64];
   __shared__ float ds[32][2 * XF_S];
   const int i = blockIdx.y, k0 = blockIdx.x * 64;
   const int dim = P.dim, KZ = P.dim * P.m, B = P.B;
+  const int rows = xf_rows_per_slice(B), b_begin = blockIdx.z * rows, b_end = min(B, b_begin + rows);
   const int j = k0 / dim, kj = k0 - j * dim;
   const bool own = j == i;
   const float* vj = P.mod[j].v;
   const int kcol = threadIdx.x & 63, sg = threadIdx.x >> 6;     // units 4 sg .. 4 sg + 3
   float az[4] = {0.f, 0.f, 0.f, 0.f}, ah[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int b0 = 0; b0 < B; b0 += 32) {
+  for (int b0 = b_begin; b0 < b_end; b0 += 32) {
     __syncthreads();
     for (int e = threadIdx.x; e < 32 * 64; e += 256) {
       const int rr = e >> 6, cc = e & 63;
-      xs[rr][cc] = (b0 + rr < B) ? vj[(long long)(b0 + rr) * dim + kj + cc] : 0.f;
+      xs[rr][cc] = (b0 + rr < b_end) ? vj[(long long)(b0 + rr) * dim + kj + cc] : 0.f;
     }
     for (int e = threadIdx.x; e < 32 * 2 * XF_S; e += 256) {
       const int rr = e >> 5, cc = e & 31;
-      ds[rr][cc] = (b0 + rr < B) ? dhz[((long long)i * B + b0 + rr) * (2 * XF_S) + cc] : 0.f;
+      ds[rr][cc] = (b0 + rr < b_end) ? dhz[((long long)i * B + b0 + rr) * (2 * XF_S) + cc] : 0.f;
     }
     __syncthreads();
 #pragma unroll 8
@@ -204,14 +207,36 @@ __global__ void __launch_bounds__(256) xfusion_gate_bwd_wgrad_kernel(const XfMod
       }
     }
   }
+  float* base = part_w + ((long long)blockIdx.z * P.m + i) * XF_S * (KZ + dim);
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    float* pz = G.dWz[i] + (long long)(4 * sg + q) * KZ + k0 + kcol;
-    *pz = accumulate ? *pz + az[q] : az[q];
-    if (own) {
-      float* ph = G.dWh[i] + (long long)(4 * sg + q) * dim + kj + kcol;
-      *ph = accumulate ? *ph + ah[q] : ah[q];
+    float* row = base + (long long)(4 * sg + q) * (KZ + dim);
+    row[k0 + kcol] = az[q];
+    if (own) row[KZ + kj + kcol] = ah[q];
+  }
+}
+
+// backward finalize: the Z partials added in slice order -> dWz, dWh, dWo, dbo, dbh, dbz (written or accumulated)
+__global__ void __launch_bounds__(256) xfusion_gate_bwd_finalize_kernel(const XfMods P, const float* __restrict__ part_small,
+                                                                        const float* __restrict__ part_w, const XfGrads G,
+                                                                        int accumulate) {
+  const int dim = P.dim, KZ = P.dim * P.m, m = P.m, Z = xf_slices(P.B);
+  const long long per_w = (long long)XF_S * (KZ + dim), per_mod = per_w + XF_SMALL_OUT;
+  for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < per_mod * m; e += (long long)gridDim.x * 256) {
+    const int i = (int)(e / per_mod);
+    const long long q = e - (long long)i * per_mod;
+    float acc = 0.f;
+    float* dst;
+    if (q < per_w) {
+      for (int zz = 0; zz < Z; ++zz) acc += part_w[((long long)zz * m + i) * per_w + q];
+      const int s = (int)(q / (KZ + dim)), c = (int)(q - (long long)s * (KZ + dim));
+      dst = c < KZ ? G.dWz[i] + (long long)s * KZ + c : G.dWh[i] + (long long)s * dim + (c - KZ);
+    } else {
+      const int t = (int)(q - per_w);
+      for (int zz = 0; zz < Z; ++zz) acc += part_small[((long long)zz * m + i) * XF_SMALL_OUT + t];
+      dst = t < 256 ? G.dWo[i] + t : t < 272 ? G.dbo[i] + (t - 256) : t < 288 ? G.dbh[i] + (t - 272) : G.dbz[i] + (t - 288);
     }
+    *dst = accumulate ? *dst + acc : acc;
   }
 }
 

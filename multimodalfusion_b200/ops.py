@@ -399,28 +399,46 @@ def xfusion_gate_bwd(v_list, params, mask, h, z, o, d_o, need_dv):
     garr = (_lib.XfusionGrads * m)()
     for i in range(m):
         garr[i] = _lib.XfusionGrads(*[_p(t) for t in grads[i]], _p(dv[i]))
-    ws = torch.empty(m * B * 32, dtype=torch.float32, device=d_o.device)
+    nbytes = lib().mmf_xfusion_gate_bwd_workspace_bytes(m, B, dim)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=d_o.device)
     check(lib().mmf_xfusion_gate_bwd(_xf_mods(v_list, params), m, B, dim, _p(None if mask is None else _f32c(mask)), _p(h),
-                                     _p(z), _p(o), _p(d_o), garr, 0, _p(ws), ws.numel() * 4, _stream()),
+                                     _p(z), _p(o), _p(d_o), garr, 0, _p(ws), nbytes, _stream()),
           "mmf_xfusion_gate_bwd")
     return dv, grads
 
 
-def kron_enc_fwd(o_list, W, b, dropout: bool = False, seed: int = 0) -> torch.Tensor:
-    """relu(W (o_1 x o_2 [x o_3 [x o_4]]) + b); dropout: train-mode Dropout(0.25) on the (never materialised) product,
-    mask from the counter hash of (seed, stream 3, row, column)."""
+def kron_dropout_code(dropout) -> int:
+    """The `dropout` argument of mmf_kron_enc_train_*: False / 0 -> 0; True or p == 0.25 -> 1 (2-bit scheme, the reference's
+    default rate); any other rate p -> round(p * 65536) in 2..65535 (16-bit scheme)."""
+    if dropout is True:
+        return 1
+    p_ = float(dropout)
+    if p_ <= 0.0:
+        return 0
+    if p_ == 0.25:
+        return 1
+    if not p_ < 1.0:
+        raise ValueError("dropout rate must be below 1")
+    return min(max(int(round(p_ * 65536)), 2), 65535)
+
+
+def kron_enc_fwd(o_list, W, b, dropout=False, seed: int = 0) -> torch.Tensor:
+    """relu(W (o_1 x o_2 [x o_3 [x o_4]]) + b); dropout (True = 0.25, or a rate): train-mode Dropout on the (never
+    materialised) product, mask from the counter hash of (seed, stream 3, row, column)."""
     o_list = [_f32c(o) for o in o_list]
     _require_cuda(*o_list)
     B, E = o_list[0].shape
     H = W.shape[0]
     out = torch.empty(B, H, dtype=torch.float32, device=W.device)
     arr = _lib.ptr_array([o.data_ptr() for o in o_list])
-    check(lib().mmf_kron_enc_train_fwd(arr, len(o_list), E, B, _p(_f32c(W)), _p(_f32c(b)), H, int(bool(dropout)), int(seed),
-                                       _p(out), _stream()), "mmf_kron_enc_train_fwd")
+    nbytes = lib().mmf_kron_enc_fwd_workspace_bytes(len(o_list), E, B, H)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=W.device) if nbytes else None
+    check(lib().mmf_kron_enc_train_fwd_ws(arr, len(o_list), E, B, _p(_f32c(W)), _p(_f32c(b)), H, kron_dropout_code(dropout),
+                                          int(seed), _p(out), _p(ws), nbytes, _stream()), "mmf_kron_enc_train_fwd_ws")
     return out
 
 
-def kron_enc_bwd(o_list, W, out, dout, dropout: bool = False, seed: int = 0):
+def kron_enc_bwd(o_list, W, out, dout, dropout=False, seed: int = 0):
     o_list = [_f32c(o) for o in o_list]
     W, out, dout = _f32c(W), _f32c(out), _f32c(dout)
     B, E = o_list[0].shape
@@ -433,7 +451,7 @@ def kron_enc_bwd(o_list, W, out, dout, dropout: bool = False, seed: int = 0):
     ws = torch.empty(nbytes, dtype=torch.uint8, device=W.device)
     arr = _lib.ptr_array([o.data_ptr() for o in o_list])
     darr = _lib.ptr_array([o.data_ptr() for o in d_o])
-    check(lib().mmf_kron_enc_train_bwd(arr, m, E, B, _p(W), H, int(bool(dropout)), int(seed), _p(out), _p(dout), darr,
+    check(lib().mmf_kron_enc_train_bwd(arr, m, E, B, _p(W), H, kron_dropout_code(dropout), int(seed), _p(out), _p(dout), darr,
                                        _p(dW), _p(db), _p(ws), nbytes, _stream()), "mmf_kron_enc_train_bwd")
     return d_o, dW, db
 

@@ -58,6 +58,23 @@ def dropout_scale_mask(seed: int, stream: int, rows: int, cols: int) -> torch.Te
     return torch.from_numpy(keep.astype(np.float32) / 0.75)
 
 
+def dropout_scale_mask_p(seed: int, stream: int, rows: int, cols: int, p: float) -> torch.Tensor:
+    """[rows, cols] inverted-dropout factor at ANY rate p (csrc/small_kernels.cuh KronElem::keep_scale, drop > 1): one
+    32-bit hash per (row, column pair), 16 bits per column, dropped iff the field is below t = round(p * 65536); the
+    kept elements are scaled by 65536 / (65536 - t)."""
+    t = min(max(int(round(p * 65536)), 2), 65535)
+    m32 = np.uint64(0xFFFFFFFF)
+    s0 = _mix32(np.array([(seed & 0xFFFFFFFF) ^ ((stream * 0x9E3779B9) & 0xFFFFFFFF)], dtype=np.uint64))
+    r = np.arange(rows, dtype=np.uint64)
+    row_state = _mix32((s0 + r * np.uint64(0x85EBCA6B) + np.uint64((seed >> 32) & 0xFFFFFFFF)) & m32)
+    cp = np.arange((cols + 1) // 2, dtype=np.uint64)
+    w = _mix32(row_state[:, None] ^ ((cp[None, :] * np.uint64(0xC2B2AE35)) & m32))
+    j = np.arange(2, dtype=np.uint64)
+    fields = (w[:, :, None] >> (np.uint64(16) * j[None, None, :])) & np.uint64(0xFFFF)
+    keep = (fields >= np.uint64(t)).reshape(rows, -1)[:, :cols]
+    return torch.from_numpy(keep.astype(np.float32) * np.float32(65536.0 / (65536.0 - t)))
+
+
 # ------------------------------------------------------------------------------------------------
 # attention-MIL forward   (models/model_attention_mil_path.py:20-21,29,50-61;
 #                          models/model_modules.py:84-85 un-gated, :105-110 gated)

@@ -141,8 +141,8 @@ def test_config3_kronecker_head_cohort_512_exact_risk_ordering(dev):
     assert torch.isfinite(hp_d.grad).all() and torch.isfinite(ho_d.grad).all()
 
 
-@pytest.mark.parametrize("m,B", [(2, 33), (3, 64), (4, 5)])
-def test_kron_encoder_train_mode_dropout_in_kernel_vs_oracle(dev, m, B):
+@pytest.mark.parametrize("m,B,p", [(2, 33, 0.25), (3, 64, 0.25), (4, 5, 0.25), (3, 70, 0.7), (2, 9, 0.1), (3, 512, 0.7)])
+def test_kron_encoder_train_mode_dropout_in_kernel_vs_oracle(dev, m, B, p):
     """Train-mode post_fusion_dropout without materialising the product: forward and all gradients against the oracle
     with the regenerated mask (oracle.dropout_scale_mask(seed, 3, B, 17^m)); eval form unchanged (dropout = 0)."""
     from multimodalfusion_b200 import ops
@@ -152,7 +152,7 @@ def test_kron_encoder_train_mode_dropout_in_kernel_vs_oracle(dev, m, B):
     W = torch.randn(H, E ** m, generator=g) * (2.0 / E ** m) ** 0.5
     b = torch.randn(H, generator=g) * 0.1
     dout = torch.randn(B, H, generator=g)
-    mask = O.dropout_scale_mask(seed, 3, B, E ** m)
+    mask = O.dropout_scale_mask(seed, 3, B, E ** m) if p == 0.25 else O.dropout_scale_mask_p(seed, 3, B, E ** m, p)
     leaves = [o.clone().requires_grad_(True) for o in o_list]
     Wl, bl = W.clone().requires_grad_(True), b.clone().requires_grad_(True)
     fused = leaves[0]
@@ -161,14 +161,14 @@ def test_kron_encoder_train_mode_dropout_in_kernel_vs_oracle(dev, m, B):
     out_ref = torch.relu((fused * mask) @ Wl.t() + bl)
     out_ref.backward(dout)
     od = [o.to(dev) for o in o_list]
-    out = ops.kron_enc_fwd(od, W.to(dev), b.to(dev), dropout=True, seed=seed)
+    out = ops.kron_enc_fwd(od, W.to(dev), b.to(dev), dropout=p, seed=seed)
     assert rel_err(out, out_ref) < 1e-5
-    d_o, dW, db = ops.kron_enc_bwd(od, W.to(dev), out, dout.to(dev), dropout=True, seed=seed)
+    d_o, dW, db = ops.kron_enc_bwd(od, W.to(dev), out, dout.to(dev), dropout=p, seed=seed)
     assert rel_err(dW, Wl.grad) < 1e-5 and rel_err(db, bl.grad) < 1e-5
     for got, leaf in zip(d_o, leaves):
         assert rel_err(got, leaf.grad) < 1e-5
     keep = (mask > 0).float().mean().item()
-    assert 0.70 < keep < 0.80
+    assert abs(keep - (1 - p)) < 0.05
     out0 = ops.kron_enc_fwd(od, W.to(dev), b.to(dev))
     fused0 = o_list[0]
     for o in o_list[1:]:

@@ -23,7 +23,8 @@ def it():
     risk, _, _ = head(*emb)
     loss = lf(risks=risk, times=times, c=cens)
     loss.backward()
-    opt3.step(zero_grad=True)
+    opt3.step()
+    opt3.zero_grad(set_to_none=True)
 
 
 for _ in range(3):

@@ -98,8 +98,9 @@ for name, lf in (("cox", CoxSurvLoss()), ("ranking", RankingSurvLoss())):
         risk, _, _ = head(*emb)
         loss = lf(risks=risk.reshape(-1), times=times, c=cens) if name == "ranking" else lf(risks=risk, times=times, c=cens)
         loss.backward()
-        opt3.step(zero_grad=True)
-        return loss.detach()
+        opt3.step()
+        opt3.zero_grad(set_to_none=True)    # (torch's default, as the reference's optimizer.zero_grad(): the next backward's
+        return loss.detach()                # gradients are adopted, not added — no accumulate kernels)
     for _ in range(3):
         it()
     torch.cuda.synchronize()
