@@ -293,13 +293,7 @@ def xfusion_forward(v_list, reduce_params, enc1, enc2, skip=True, fused_scale=No
     """XlinearFusion.forward in eval mode, gate=1, use_bilinear=0 (models/model_modules.py:156-178).
     reduce_params[i] = ((Wh,bh),(Wz,bz),(Wo,bo)); enc1/enc2 = (W,b). fused_scale: optional [B, E^m] inverted-dropout
     scale mask of post_fusion_dropout (models/model_modules.py:170; dropout_scale_mask(seed, 3, B, E^m))."""
-    v_cat = torch.cat(v_list, dim=1)
-    o_list = []
-    for v, ((Wh, bh), (Wz, bz), (Wo, bo)) in zip(v_list, reduce_params):
-        h = torch.relu(v @ Wh.t() + bh)
-        z = v_cat @ Wz.t() + bz
-        o = torch.relu((torch.sigmoid(z) * h) @ Wo.t() + bo)
-        o_list.append(torch.cat([o, torch.ones(o.shape[0], 1, dtype=o.dtype)], dim=1))
+    o_list = list(xfusion_gate(v_list, reduce_params).unbind(0))     # (the gate restatement is pinned by the same goldens)
     fused = o_list[0]
     for o in o_list[1:]:
         fused = (fused[:, :, None] * o[:, None, :]).flatten(1)

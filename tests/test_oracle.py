@@ -143,6 +143,28 @@ def test_dropout_mask_statistics_and_determinism():
     assert len(u) == 2 and u[0] == 0.0 and abs(u[1] - 1 / 0.75) < 1e-6
 
 
+def test_dropout_mask_any_rate_statistics_and_determinism():
+    """The 16-bit-field mask of the Kronecker encoder (csrc/small_kernels.cuh KronElem::keep_scale, drop > 1)."""
+    for p in (0.7, 0.1, 0.5):
+        m1 = O.dropout_scale_mask_p(0xABCDEF0123, 3, 129, 4913, p)
+        assert torch.equal(m1, O.dropout_scale_mask_p(0xABCDEF0123, 3, 129, 4913, p))
+        assert not torch.equal(m1, O.dropout_scale_mask_p(0xABCDEF0124, 3, 129, 4913, p))
+        keep = (m1 > 0).float().mean().item()
+        assert abs(keep - (1 - p)) < 0.01
+        t = round(p * 65536)
+        u = m1.unique().tolist()
+        assert len(u) == 2 and u[0] == 0.0 and abs(u[1] - 65536 / (65536 - t)) < 1e-5
+        assert abs(m1.mean().item() - 1.0) < 0.02          # inverted dropout keeps the expectation
+
+
+def test_kron_dropout_code():
+    from multimodalfusion_b200.ops import kron_dropout_code
+    assert kron_dropout_code(False) == 0 and kron_dropout_code(0.0) == 0 and kron_dropout_code(True) == 1
+    assert kron_dropout_code(0.25) == 1 and kron_dropout_code(0.7) == 45875 and kron_dropout_code(1e-9) == 2
+    with pytest.raises(ValueError):
+        kron_dropout_code(1.0)
+
+
 def test_train_mode_backward_restatement_matches_autograd():
     """Analytic backward with dropout masks == autograd through the masked forward."""
     torch.manual_seed(3)
