@@ -704,9 +704,7 @@ int mmf_dense_fwd_ws(const float* x, int64_t ldx, const float* W, const float* b
   if (!workspace || workspace_bytes < mmf_dense_fwd_workspace_bytes(B, in_dim, out_dim)) return MMF_E_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   float* ws = static_cast<float*>(workspace);
-  dim3 grid((out_dim + 63) / 64, (B + 63) / 64, splits);
-  sgemm_functor_kernel<LoadRowMajor, LoadRowMajor, EpiSlice><<<grid, 256, 0, st>>>(
-      B, out_dim, in_dim, LoadRowMajor{x, ldx}, LoadRowMajor{W, in_dim}, EpiSlice{ws, (long long)B * out_dim, out_dim});
+  launch_sgemm_slices(B, out_dim, in_dim, LoadRowMajor{x, ldx}, LoadRowMajor{W, in_dim}, ws, splits, st);
   long long blocks = ((long long)B * out_dim + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   splitk_fixup_kernel<<<(int)blocks, 256, 0, st>>>(ws, splits, B, out_dim, b, act, y, ldy);
@@ -766,9 +764,7 @@ int mmf_kron_enc_train_fwd_ws(const float* const* o, int m, int E, int B, const 
   if (splits > 1 && workspace && workspace_bytes >= mmf_kron_enc_fwd_workspace_bytes(m, E, B, H)) {
     // few output tiles, K = E^m (4913 for three modalities): deterministic split-K as mmf_dense_fwd_ws
     float* ws = static_cast<float*>(workspace);
-    dim3 grid((H + 63) / 64, (B + 63) / 64, splits);
-    sgemm_functor_kernel<LoadKronA, LoadRowMajor, EpiSlice><<<grid, 256, 0, st>>>(
-        B, H, KK, LoadKronA{e}, LoadRowMajor{W, KK}, EpiSlice{ws, (long long)B * H, H});
+    launch_sgemm_slices(B, H, KK, LoadKronA{e}, LoadRowMajor{W, KK}, ws, splits, st);
     long long blocks = ((long long)B * H + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     splitk_fixup_kernel<<<(int)blocks, 256, 0, st>>>(ws, splits, B, H, b, MMF_ACT_RELU, out, H);

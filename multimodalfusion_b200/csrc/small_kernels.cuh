@@ -182,37 +182,43 @@ struct EpiStoreAcc {             // c[m*ld+n] = (accumulate ? c : 0) + acc
   __device__ __forceinline__ void add(int m, int n, float acc) const { atomicAdd(c + m * ld + n, acc); }
 };
 
-// C(m,n) = sum_k A(m,k) * B(n,k).  64x64 tile, 256 threads, 4x4 micro-tile, BK = 16. The operand elements of the NEXT
-// k-step are fetched into registers while the current one is multiplied (the functor loads are scalar global loads: with
-// the fetch inside the step a skinny GEMM of 48 k-steps took ~1 us per step — latency, not work). gridDim.z > 1: split-K,
-// slice z takes k-steps z, z + gridDim.z, ... and adds its partial tile atomically (linear epilogues only).
-template <class ALoad, class BLoad, class Epi>
-__global__ void __launch_bounds__(256)
+// C(m,n) = sum_k A(m,k) * B(n,k).  256 threads, BK = 16, MT x MT micro-tile per thread: MT = 4 -> 64 x 64 tile (skinny /
+// small outputs), MT = 8 -> 128 x 128 tile (ncu, gpurun_out/r2y_sgemm.ncu-rep: the 4 x 4 form issues one LDS.128 per 8 FFMA
+// and, with ~9 resident warps per scheduler-quarter at best, stalls on the shared-memory latency — issue slots 63 % active,
+// FMA pipe 42 % on the 4913-wide encoder GEMMs; 8 x 8 halves the LDS : FFMA ratio and gives every warp 64 independent
+// FFMA per k). The 8 rows / columns of a thread are two groups of 4, 64 apart: the operand reads stay conflict-free
+// LDS.128. The operand elements of the NEXT k-step are fetched into registers while the current one is multiplied (the
+// functor loads are scalar global loads: with the fetch inside the step a skinny GEMM of 48 k-steps took ~1 us per step —
+// latency, not work). gridDim.z > 1: split-K, slice z takes k-steps z, z + gridDim.z, ... and adds its partial tile
+// atomically (linear epilogues only; EpiSlice stores per-slice partials instead).
+template <class ALoad, class BLoad, class Epi, int MT = 4>
+__global__ void __launch_bounds__(256, MT == 8 ? 2 : 3)
 sgemm_functor_kernel(int M, int N, int K, ALoad la, BLoad lb, Epi epi) {
-  __shared__ float As[16][68];
-  __shared__ float Bs[16][68];
+  constexpr int TS = 16 * MT;                      // tile side
+  __shared__ __align__(16) float As[16][TS + 4];
+  __shared__ __align__(16) float Bs[16][TS + 4];
   const int tid = threadIdx.x;
   const int tm = tid / 16, tn = tid % 16;
-  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
-  float acc[4][4];
+  const int m0 = blockIdx.y * TS, n0 = blockIdx.x * TS;
+  float acc[MT][MT];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < MT; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  float ra[4], rb[4];
+    for (int j = 0; j < MT; ++j) acc[i][j] = 0.f;
+  float ra[MT], rb[MT];
   auto fetch = [&](int k0) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
+    for (int e = 0; e < MT; ++e) {
       const int idx = tid + e * 256;
       {
-        const int mm = ALoad::kContig ? idx / 16 : idx % 64;
-        const int kk = ALoad::kContig ? idx % 16 : idx / 64;
+        const int mm = ALoad::kContig ? idx / 16 : idx % TS;
+        const int kk = ALoad::kContig ? idx % 16 : idx / TS;
         const int gm = m0 + mm, gk = k0 + kk;
         ra[e] = (gm < M && gk < K) ? la(gm, gk) : 0.f;
       }
       {
-        const int nn = BLoad::kContig ? idx / 16 : idx % 64;
-        const int kk = BLoad::kContig ? idx % 16 : idx / 64;
+        const int nn = BLoad::kContig ? idx / 16 : idx % TS;
+        const int kk = BLoad::kContig ? idx % 16 : idx / TS;
         const int gn = n0 + nn, gk = k0 + kk;
         rb[e] = (gn < N && gk < K) ? lb(gn, gk) : 0.f;
       }
@@ -223,33 +229,36 @@ sgemm_functor_kernel(int M, int N, int K, ALoad la, BLoad lb, Epi epi) {
   if (k0 < K) fetch(k0);
   for (; k0 < K; k0 += kstep) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
+    for (int e = 0; e < MT; ++e) {
       const int idx = tid + e * 256;
-      As[ALoad::kContig ? idx % 16 : idx / 64][ALoad::kContig ? idx / 16 : idx % 64] = ra[e];
-      Bs[BLoad::kContig ? idx % 16 : idx / 64][BLoad::kContig ? idx / 16 : idx % 64] = rb[e];
+      As[ALoad::kContig ? idx % 16 : idx / TS][ALoad::kContig ? idx / 16 : idx % TS] = ra[e];
+      Bs[BLoad::kContig ? idx % 16 : idx / TS][BLoad::kContig ? idx / 16 : idx % TS] = rb[e];
     }
     __syncthreads();
     if (k0 + kstep < K) fetch(k0 + kstep);
 #pragma unroll
     for (int kk = 0; kk < 16; ++kk) {
-      float av[4], bv[4];
+      float av[MT], bv[MT];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) av[i] = As[kk][tm * 4 + i];
+      for (int g = 0; g < MT / 4; ++g) {
+        const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][g * 64 + tm * 4]);
+        const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][g * 64 + tn * 4]);
+        av[4 * g] = a4.x; av[4 * g + 1] = a4.y; av[4 * g + 2] = a4.z; av[4 * g + 3] = a4.w;
+        bv[4 * g] = b4.x; bv[4 * g + 1] = b4.y; bv[4 * g + 2] = b4.z; bv[4 * g + 3] = b4.w;
+      }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) bv[j] = Bs[kk][tn * 4 + j];
+      for (int i = 0; i < MT; ++i)
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        for (int j = 0; j < MT; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
     __syncthreads();
   }
   const bool split = gridDim.z > 1;
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < MT; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int gm = m0 + tm * 4 + i, gn = n0 + tn * 4 + j;
+    for (int j = 0; j < MT; ++j) {
+      const int gm = m0 + (i / 4) * 64 + tm * 4 + (i % 4), gn = n0 + (j / 4) * 64 + tn * 4 + (j % 4);
       if (gm < M && gn < N) {
         if (Epi::kLinear && split) epi.add(gm, gn, acc[i][j]);
         else epi(gm, gn, acc[i][j]);
@@ -279,11 +288,19 @@ __global__ void __launch_bounds__(256) splitk_fixup_kernel(const float* __restri
 // split count of the deterministic split-K forward: few output tiles and a long k loop (the radiology reduce_dim,
 // [155, 4096] -> 1024: 48 CTAs of 256 serial k-steps took 205 us); 8 warps per CTA cannot fill an SM's FMA pipes
 // (the k loop is latency-bound), so the slices aim at ~4 CTAs per SM. 1 = no split.
+// 128 x 128 tiles (MT = 8) when both output dimensions fill them (at most a quarter of the padded tile rows / columns idle);
+// 64 x 64 otherwise
+inline bool sgemm_big_tiles(int M, int N) {
+  auto fits = [](int d) { return d >= 128 && (long long)((d + 127) / 128) * 128 * 4 <= 5ll * d; };
+  return fits(M) && fits(N) && (long long)M * N >= 128 * 128 * 8;
+}
 inline int dense_fwd_splits(int B, int in_dim, int out_dim) {
-  const long long tiles = (long long)((B + 63) / 64) * ((out_dim + 63) / 64);
+  const bool big = sgemm_big_tiles(B, out_dim);
+  const int ts = big ? 128 : 64, want = (big ? 2 : 4) * 148;
+  const long long tiles = (long long)((B + ts - 1) / ts) * ((out_dim + ts - 1) / ts);
   const int ksteps = (in_dim + 15) / 16;
-  if (tiles > 74 || in_dim < 512) return 1;
-  int splits = (int)((4 * 148 + tiles - 1) / tiles);
+  if (tiles >= want / 2 || in_dim < 512) return 1;
+  int splits = (int)((want + tiles - 1) / tiles);
   if (splits > ksteps / 4) splits = ksteps / 4;
   if (splits > 32) splits = 32;
   return splits < 1 ? 1 : splits;
@@ -294,12 +311,20 @@ inline int dense_fwd_splits(int B, int in_dim, int out_dim) {
 // into is cleared first.
 template <class ALoad, class BLoad, class Epi>
 inline void launch_sgemm(int M, int N, int K, ALoad la, BLoad lb, Epi epi, cudaStream_t st) {
-  dim3 grid((N + 63) / 64, (M + 63) / 64);
+  // 128 x 128 tiles only pay in the plain-operand forward (launch_sgemm_slices: 75 -> 64 us on the two encoder layers of
+  // config 3); with the derivative-forming operand functors of the backward GEMMs they measured SLOWER (LoadDpre 100 -> 125 us,
+  // LoadDpreT 95 -> 111 us, gpurun_out/r2z / r3a_cfg3_profile.log): those loops are bound by the functor loads, not by LDS / FFMA
+  const bool big = false && sgemm_big_tiles(M, N);
+  const int ts = big ? 128 : 64;
+  dim3 grid((N + ts - 1) / ts, (M + ts - 1) / ts);
   int splits = 1;
   if constexpr (Epi::kLinear) {
     const int tiles = (int)(grid.x * grid.y), ksteps = (K + 15) / 16;
-    if (tiles <= 74 && ksteps >= 8) {
-      splits = (148 + tiles - 1) / tiles;
+    // (ncu, gpurun_out/r2y_sgemm.ncu-rep: with one 8-warp CTA per SM the k loop is latency-bound — issue slots 19 % active,
+    // FMA pipe 11 %: grids under two waves of single CTAs are split towards 4 (64 x 64) / 2 (128 x 128) CTAs per SM)
+    const int want = (big ? 2 : 4) * 148;
+    if (tiles < want / 2 && ksteps >= 8) {
+      splits = (want + tiles - 1) / tiles;
       if (splits > ksteps / 4) splits = ksteps / 4;      // at least 4 k-steps per slice
       if (splits > 32) splits = 32;
       if (splits < 1) splits = 1;
@@ -310,7 +335,19 @@ inline void launch_sgemm(int M, int N, int K, ALoad la, BLoad lb, Epi epi, cudaS
     }
   }
   grid.z = splits;
-  sgemm_functor_kernel<ALoad, BLoad, Epi><<<grid, 256, 0, st>>>(M, N, K, la, lb, epi);
+  if (big) sgemm_functor_kernel<ALoad, BLoad, Epi, 8><<<grid, 256, 0, st>>>(M, N, K, la, lb, epi);
+  else sgemm_functor_kernel<ALoad, BLoad, Epi, 4><<<grid, 256, 0, st>>>(M, N, K, la, lb, epi);
+}
+
+// deterministic split-K forward (EpiSlice partials + fix-up): launches the slices, returns the split count used
+template <class ALoad, class BLoad>
+inline void launch_sgemm_slices(int M, int N, int K, ALoad la, BLoad lb, float* ws, int splits, cudaStream_t st) {
+  const bool big = sgemm_big_tiles(M, N);
+  const int ts = big ? 128 : 64;
+  dim3 grid((N + ts - 1) / ts, (M + ts - 1) / ts, splits);
+  EpiSlice epi{ws, (long long)M * N, N};
+  if (big) sgemm_functor_kernel<ALoad, BLoad, EpiSlice, 8><<<grid, 256, 0, st>>>(M, N, K, la, lb, epi);
+  else sgemm_functor_kernel<ALoad, BLoad, EpiSlice, 4><<<grid, 256, 0, st>>>(M, N, K, la, lb, epi);
 }
 
 // out[o] (+)= sum_b elem(b, o): one warp per 32 columns x a slice of the rows, 8 warps per block meet in shared memory
