@@ -138,7 +138,14 @@ class MIL_Attention_fc_surv_radio(MIL_Attention_fc_radio):
                               eps, need_dx=True)
         if not accumulate:
             Wr.grad.zero_(); br.grad.zero_()
-        # dWr += dh0^T xc, dbr += colsum(dh0): accumulated in place by the functor SGEMM
-        ops.dense_bwd_into(xc, Wr.detach(), h0, out[5].float(), Wr.grad, br.grad)
+        dh0 = out[5]                                                            # bf16 [N, 1024] (the AMIL dx GEMM's output)
+        if all(b.dtype == torch.bfloat16 and b.is_contiguous() for b in xs):
+            # dWr += dh0^T cat(bags), dbr += colsum(dh0) on the tensor cores: BOTH operands are bf16 values already (the
+            # stored bags and the dx GEMM's output), so their products are exact in the fp32 accumulator — the same
+            # gradient as the fp32 SGEMM up to summation order, read straight from the four modality bags (47 -> ~10 us)
+            ops.linear_bf16_wgrad(dh0, xs, Wr.grad, br.grad)
+        else:
+            # fp32 bags: accumulated in place by the functor SGEMM
+            ops.dense_bwd_into(xc, Wr.detach(), h0, dh0.float(), Wr.grad, br.grad)
         return out[:5]
 

@@ -209,8 +209,9 @@ def test_fused_step_full_size_with_dropout_vs_fp32_oracle(dev, N, L, D):
     assert rel_err(dWk, Wr.grad) < TOL_GRAD_REF and rel_err(dbk, br.grad) < TOL_GRAD_REF
 
 
-@pytest.mark.parametrize("N,gate", [(17, True), (80, True), (155, True), (131, False)])
-def test_radio_fused_step_matches_autograd_path(dev, N, gate):
+@pytest.mark.parametrize("N,gate,bf16_bags", [(17, True, False), (80, True, False), (155, True, False), (131, False, False),
+                                              (155, True, True), (96, False, True)])
+def test_radio_fused_step_matches_autograd_path(dev, N, gate, bf16_bags):
     """MIL_Attention_fc_surv_radio.fused_step (reduce_dim + the fused 3-launch step with dx + reduce_dim wgrad, no
     autograd graph) == model(**bags) -> NLLSurvLoss -> backward through the autograd.Functions (eval mode: no dropout)."""
     from multimodalfusion_b200.models import MIL_Attention_fc_surv_radio
@@ -218,6 +219,8 @@ def test_radio_fused_step_matches_autograd_path(dev, N, gate):
     torch.manual_seed(21)
     model = MIL_Attention_fc_surv_radio(gate_radio=gate, dropout=True, n_classes=4).to(dev).eval()
     bags = {m: cases.features(N, 300 + i).to(dev) for i, m in enumerate(model.modalities)}
+    if bf16_bags:      # stored bf16 features: reduce_dim's weight gradient runs on the tensor cores (exact products)
+        bags = {m: b.to(torch.bfloat16) for m, b in bags.items()}
     Y, c = torch.tensor([2], device=dev), torch.tensor([0.0], device=dev)
     hz, S, Y_hat, A = model(**bags)
     loss = NLLSurvLoss(alpha=0.15)(hazards=hz, S=S, Y=Y, c=c)
