@@ -136,3 +136,37 @@ class multimodal_pretrained(nn.Module):
             return fcnn_forward(self.classifier, MM), None, None
         MM = self.highway(MM)
         return Dense.apply(MM, self.classifier.weight, self.classifier.bias, ACT_NONE), None, None
+
+    # ---- captum entry points (models/coxranking_models_pretrained.py:202-305; called by create_attributions.py on
+    # initiate_pretrained_model(...)): the risk as a function of the embeddings only, fixed modality orders -------------
+    def _captum_risk(self, pairs):
+        """pairs: [(modality key, embedding)] in the reference method's concatenation order."""
+        tt = self.train_type
+        hs = [h for _, h in pairs]
+        if tt == 'kronecker':
+            MM = self.xfusion(v_list=hs)
+            return Dense.apply(MM, self.classifier.weight, self.classifier.bias, ACT_NONE)
+        if tt.startswith('late'):
+            mods = {'radio': self.layer_MRI, 'path': self.layer_WSI, 'omic': self.layer_omic} if tt == 'late-fcnn' else \
+                {'radio': self.highway_radio, 'path': self.highway_path, 'omic': self.highway_omic}
+            outs = [fcnn_forward(mods[k], h.float()) if tt == 'late-fcnn' else mods[k](h) for k, h in pairs]
+            MM = torch.cat(outs, dim=1)                     # == cat(axis=2) of the unsqueeze(0)-ed layers
+            lin = self.classifier[0] if tt == 'late-fcnn' else self.classifier
+            return Dense.apply(MM, lin.weight, lin.bias, ACT_NONE).unsqueeze(0).squeeze()
+        MM = torch.cat([h.float() for h in hs], dim=1)
+        if tt == 'early-fcnn':
+            return fcnn_forward(self.classifier, MM)
+        MM = self.highway(MM)
+        return Dense.apply(MM, self.classifier.weight, self.classifier.bias, ACT_NONE)
+
+    def captum_radio_path(self, h_radio, h_path):
+        return self._captum_risk([('radio', h_radio), ('path', h_path)])
+
+    def captum_path_omic(self, h_omic, h_path):
+        return self._captum_risk([('omic', h_omic), ('path', h_path)])
+
+    def captum_radio_omic(self, h_radio, h_omic):
+        return self._captum_risk([('radio', h_radio), ('omic', h_omic)])
+
+    def captum(self, h_radio, h_path, h_omic):
+        return self._captum_risk([('radio', h_radio), ('path', h_path), ('omic', h_omic)])

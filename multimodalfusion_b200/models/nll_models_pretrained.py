@@ -102,3 +102,39 @@ class multimodal_pretrained(nn.Module):
         hazards, S, _ = HazardHead.apply(MM, lin.weight, lin.bias)
         risk = -torch.sum(S, dim=1)
         return risk, hazards, S
+
+    # ---- captum entry points (models/nll_models_pretrained.py:200-318; called by create_attributions.py on
+    # initiate_pretrained_model(...)): risk = -sum_k S_k as a function of the embeddings only, fixed modality orders ----
+    def _captum_risk(self, pairs):
+        """pairs: [(modality key, embedding)] in the reference method's concatenation order."""
+        tt = self.train_type
+        hs = [h for _, h in pairs]
+        if tt == 'kronecker':
+            MM, lin = self.xfusion(v_list=hs), self.classifier
+        elif tt.startswith('late'):
+            mods = {'radio': self.layer_MRI, 'path': self.layer_WSI, 'omic': self.layer_omic} if tt == 'late-fcnn' else \
+                {'radio': self.highway_radio, 'path': self.highway_path, 'omic': self.highway_omic}
+            outs = [fcnn_forward(mods[k], h.float()) if tt == 'late-fcnn' else mods[k](h) for k, h in pairs]
+            MM = torch.cat(outs, dim=1)
+            lin = self.classifier[0] if tt == 'late-fcnn' else self.classifier
+        else:
+            MM = torch.cat([h.float() for h in hs], dim=1)
+            if tt == 'early-fcnn':
+                MM = fcnn_forward(nn.Sequential(*list(self.classifier)[:4]), MM)
+                lin = self.classifier[4]
+            else:
+                MM, lin = self.highway(MM), self.classifier
+        _, S, _ = HazardHead.apply(MM, lin.weight, lin.bias)
+        return -torch.sum(S, dim=1)
+
+    def captum_radio_path(self, h_radio, h_path):
+        return self._captum_risk([('radio', h_radio), ('path', h_path)])
+
+    def captum_path_omic(self, h_omic, h_path):
+        return self._captum_risk([('omic', h_omic), ('path', h_path)])
+
+    def captum_radio_omic(self, h_radio, h_omic):
+        return self._captum_risk([('radio', h_radio), ('omic', h_omic)])
+
+    def captum(self, h_radio, h_path, h_omic):
+        return self._captum_risk([('radio', h_radio), ('path', h_path), ('omic', h_omic)])

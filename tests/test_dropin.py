@@ -182,3 +182,33 @@ def test_l1_penalty_and_freeze_helpers_match_the_reference_definitions():
     assert not any(p.requires_grad for p in m.parameters())
     dfs_unfreeze(m)
     assert all(p.requires_grad for p in m.parameters())
+
+
+CAPTUM_MATRIX = [(f, tt, mode, meth) for f in ("coxranking_models_pretrained", "nll_models_pretrained")
+                 for tt in ("kronecker", "early-fcnn", "late-fcnn", "early-highway", "late-highway")
+                 for mode, meth in (("radio_path_omic", "captum"), ("radio_path", "captum_radio_path"),
+                                    ("path_omic", "captum_path_omic"), ("radio_omic", "captum_radio_omic"))]
+
+
+@pytest.mark.parametrize("modname,train_type,mode,method", CAPTUM_MATRIX)
+def test_pretrained_head_captum_entry_points_match_live_reference(ref, modname, train_type, mode, method):
+    """multimodal_pretrained.captum / captum_radio_path / captum_path_omic / captum_radio_omic (the entry points
+    create_attributions.py calls, models/*_models_pretrained.py:200-318) against the live reference in eval mode: the same
+    seeded construction, the oracle's fp32 restatements standing in for the kernels (host glue: orders, reshapes)."""
+    from cpu_standins import oracle_kernels
+    kw = dict(mode=mode, train_type=train_type, n_classes=4, bag_loss="nll_surv" if modname.startswith("nll") else "cox_surv")
+    torch.manual_seed(5)
+    theirs = getattr(ref[modname], "multimodal_pretrained")(**kw).eval()
+    torch.manual_seed(5)
+    ours = getattr(getattr(M, modname), "multimodal_pretrained")(**kw).eval()
+    ours.load_state_dict(theirs.state_dict(), strict=True)
+    g = torch.Generator().manual_seed(9)
+    emb = {k: torch.randn(6, 256, generator=g) for k in ("h_radio", "h_path", "h_omic")}
+    names = list(inspect.signature(getattr(theirs, method)).parameters)
+    assert list(inspect.signature(getattr(ours, method)).parameters) == names
+    args = [emb[n] for n in names]
+    want = getattr(theirs, method)(*args)
+    with oracle_kernels():
+        got = getattr(ours, method)(*args)
+    assert got.shape == want.shape
+    torch.testing.assert_close(got, want, rtol=2e-5, atol=2e-6)

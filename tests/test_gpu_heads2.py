@@ -161,3 +161,36 @@ def test_radio_tensor_fusion_vs_repaired_reference(dev, goldens_xfusion4, name):
         if err >= 3e-2:
             bad[k] = err
     assert not bad, f"gradients beyond 3e-2: {bad}"
+
+
+@pytest.mark.parametrize("modname", ["coxranking_models_pretrained", "nll_models_pretrained"])
+@pytest.mark.parametrize("train_type,mode,method", [
+    ("kronecker", "radio_path_omic", "captum"), ("kronecker", "path_omic", "captum_path_omic"),
+    ("late-fcnn", "radio_path", "captum_radio_path"), ("early-highway", "radio_omic", "captum_radio_omic"),
+    ("late-highway", "radio_path_omic", "captum"), ("early-fcnn", "radio_path_omic", "captum")])
+def test_pretrained_head_captum_on_gpu_equals_cpu_restatement(dev, modname, train_type, mode, method):
+    """The captum* entry points of the pretrained heads on the kernels (risk and its gradient w.r.t. the embeddings, what
+    IntegratedGradients consumes) == the same module run through the oracle's fp32 restatements on the CPU (which
+    tests/test_dropin.py pins to the live reference)."""
+    import copy
+    import inspect
+    from cpu_standins import oracle_kernels
+    from multimodalfusion_b200 import models as M
+    kw = dict(mode=mode, train_type=train_type, n_classes=4, bag_loss="nll_surv" if modname.startswith("nll") else "cox_surv")
+    torch.manual_seed(3)
+    cpu_model = getattr(getattr(M, modname), "multimodal_pretrained")(**kw).eval()
+    gpu_model = copy.deepcopy(cpu_model).to(dev)
+    g = torch.Generator().manual_seed(4)
+    emb = {k: torch.randn(5, 256, generator=g) for k in ("h_radio", "h_path", "h_omic")}
+    names = list(inspect.signature(getattr(cpu_model, method)).parameters)
+    a_cpu = [emb[n].clone().requires_grad_() for n in names]
+    a_gpu = [emb[n].to(dev).requires_grad_() for n in names]
+    with oracle_kernels():
+        want = getattr(cpu_model, method)(*a_cpu)
+        want.sum().backward()
+    got = getattr(gpu_model, method)(*a_gpu)
+    got.sum().backward()
+    torch.testing.assert_close(got.detach().cpu(), want.detach(), rtol=1e-4, atol=1e-5)
+    for x, y in zip(a_gpu, a_cpu):
+        scale = y.grad.abs().max().item() + 1e-8
+        assert (x.grad.cpu() - y.grad).abs().max().item() <= 2e-4 * scale + 1e-7
