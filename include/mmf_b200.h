@@ -64,16 +64,18 @@ enum {
 #define MMF_TILE_ROWS 128    /* instances per CTA tile; one (m, l, acc[L]) partial per tile */
 
 int mmf_version(void);
-/* DEBUG ONLY (process-global): device buffer of gridDim.x*16 uint64 that the fused tile kernels fill
- * with clock64() phase stamps; NULL (default) disables it. Not for production use. */
+/* DEBUG BUILDS ONLY: a no-op in the release library (no global state). In a library compiled with -DMMF_DEBUG_STAMPS=1
+ * (tools/phase_*.py, tools/dp_diag.py): device buffer of gridDim.x*16 uint64 that the tensor-core kernels fill with clock64()
+ * phase stamps; NULL disables it. mmf_debug_stamps_enabled() tells which build is loaded. */
 void mmf_debug_set_timing_buffer(void* device_u64_buffer);
+int mmf_debug_stamps_enabled(void);
 /* DEBUG BUILDS ONLY: a no-op in the release library (no device-global state). In a library compiled with
  * -DMMF_DEBUG_TIMELINE=1 (tools/step_timeline.py): device buffer of 16 + 5 * 32768 uint64, zero-filled; every CTA of every
  * hot-path kernel appends one record (kernel id, blockIdx.x, %globaltimer ns at CTA start, after griddepcontrol.wait, at
  * CTA end) at [16 + 5 i ...], record count in [0]. ids: 0 fused forward, 1 head step, 2 fused head + gate + hidden
  * backward, 3 wgrad GEMM, 4 recompute gate, 5 other pair GEMMs. NULL disables. */
 void mmf_debug_set_timeline_buffer(void* device_u64_buffer);
-/* DEBUG ONLY (process-global): device buffer of 8 + 4 * 4000 uint64, zero-filled; CTA 0 of every peer all-reduce appends
+/* DEBUG BUILDS ONLY (-DMMF_DEBUG_STAMPS=1; no-op in the release library): device buffer of 8 + 4 * 4000 uint64, zero-filled; CTA 0 of every peer all-reduce appends
  * 4 %globaltimer stamps (kernel start, ready handshake done, data phase done, done handshake done); count in [0]. */
 void mmf_debug_set_p2p_stamp_buffer(void* device_u64_buffer);
 const char* mmf_error_string(int rc);

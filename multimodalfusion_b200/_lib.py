@@ -112,6 +112,7 @@ _PP = C.POINTER(C.c_void_p)
 SIGNATURES = {
     "mmf_version": (_i, []),
     "mmf_debug_set_timing_buffer": (None, [_vp]),
+    "mmf_debug_stamps_enabled": (_i, []),
     "mmf_debug_set_timeline_buffer": (None, [_vp]),
     "mmf_debug_set_p2p_stamp_buffer": (None, [_vp]),
     "mmf_error_string": (C.c_char_p, [_i]),
@@ -206,6 +207,13 @@ def lib() -> C.CDLL:
                 fn.argtypes = args
             _lib = handle
     return _lib
+
+
+def require_debug_stamps() -> None:
+    """The phase-stamp tools need a library compiled with -DMMF_DEBUG_STAMPS=1 (the release build keeps no global state)."""
+    if not lib().mmf_debug_stamps_enabled():
+        raise MmfError("this libmmf_b200.so is a release build: `python tools/ab_variant.py build stamps -DMMF_DEBUG_STAMPS=1` "
+                       "and run the tool with MMF_LIB_PATH pointing at the variant")
 
 
 def check(rc: int, what: str = "") -> None:

@@ -37,8 +37,14 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
     }                                                                                                          \
   } while (0)
 
-// debug-only global (the one exception to "no global state"): when set, the tensor-core kernels write
-// clock64 phase stamps [gridDim.x][16]; see tools/phase_timing.py
+// MMF_DEBUG_STAMPS = 1 (debug builds only: tools/ab_variant.py build stamps -DMMF_DEBUG_STAMPS=1): process-global pointers
+// to the clock64 phase-stamp buffer [gridDim.x][16] of the tensor-core kernels (tools/phase_*.py) and to the %globaltimer
+// stamps of the peer all-reduce (tools/dp_diag.py). The RELEASE library holds no global state: the setters are no-ops and
+// every kernel receives a null stamp pointer.
+#ifndef MMF_DEBUG_STAMPS
+#define MMF_DEBUG_STAMPS 0
+#endif
+#if MMF_DEBUG_STAMPS
 unsigned long long* g_timing_buffer = nullptr;
 // MMF_STAMP_KERNEL=<id> (debug, tools/phase_instep.py): only the kernel with this timeline id (0 forward tile, 2 gate + hidden,
 // 3 grouped wgrad, 4 recompute gate, 5 other pair GEMMs) receives the phase-stamp buffer — the kernels of a whole step can
@@ -48,6 +54,10 @@ unsigned long long* stamp_buf(int id) {
   return (only < 0 || only == id) ? g_timing_buffer : nullptr;
 }
 unsigned long long* g_p2p_stamps = nullptr;
+#else
+inline unsigned long long* stamp_buf(int) { return nullptr; }
+constexpr unsigned long long* g_p2p_stamps = nullptr;
+#endif
 
 struct BwdWs {
   size_t off_H, off_dG, off_dU, off_cs, off_dbc, off_db1, off_mask, off_z, off_thead, total;
@@ -222,12 +232,23 @@ extern "C" {
 int mmf_version(void) { return MMF_ABI_VERSION; }
 
 void mmf_debug_set_timing_buffer(void* device_u64_buffer) {
+#if MMF_DEBUG_STAMPS
   g_timing_buffer = reinterpret_cast<unsigned long long*>(device_u64_buffer);
+#else
+  (void)device_u64_buffer;   // release build: no global state (rebuild with -DMMF_DEBUG_STAMPS=1)
+#endif
 }
 
 void mmf_debug_set_p2p_stamp_buffer(void* device_u64_buffer) {
+#if MMF_DEBUG_STAMPS
   g_p2p_stamps = reinterpret_cast<unsigned long long*>(device_u64_buffer);
+#else
+  (void)device_u64_buffer;
+#endif
 }
+
+/* 1 when this library was compiled with -DMMF_DEBUG_STAMPS=1 (the phase-stamp tools refuse to run otherwise). */
+int mmf_debug_stamps_enabled(void) { return MMF_DEBUG_STAMPS; }
 
 void mmf_debug_set_timeline_buffer(void* device_u64_buffer) {
 #if MMF_DEBUG_TIMELINE

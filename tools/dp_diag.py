@@ -16,6 +16,7 @@ sys.path.insert(0, ROOT)
 import torch
 import torch.distributed as dist
 import multimodalfusion_b200 as mmf
+from multimodalfusion_b200._lib import require_debug_stamps; require_debug_stamps()   # needs a -DMMF_DEBUG_STAMPS=1 build (MMF_LIB_PATH)
 from multimodalfusion_b200 import ops
 from multimodalfusion_b200.models import MIL_Attention_fc_surv_path
 from multimodalfusion_b200.parallel import PeerAllReduce

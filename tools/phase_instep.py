@@ -7,6 +7,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 import multimodalfusion_b200 as mmf
+from multimodalfusion_b200._lib import require_debug_stamps; require_debug_stamps()   # needs a -DMMF_DEBUG_STAMPS=1 build (MMF_LIB_PATH)
 from multimodalfusion_b200 import ops
 kid = int(os.environ.get("MMF_STAMP_KERNEL", "0"))
 L, D, N, K = 512, 384, int(os.environ.get("N", 16384)), 4
