@@ -420,6 +420,28 @@ int mmf_xfusion_gate_bwd(const MmfXfusionMod* mods_host, int m, int B, int dim, 
                          const float* z, const float* o, const float* d_o, const MmfXfusionGrads* grads_host,
                          int accumulate, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- self-normalising MLP (SNN_Block x n) in one launch ---------------------------
+ * models/model_modules.py:64-68 (Linear -> SELU -> AlphaDropout), models/model_genomic.py:17-25,53-57 (fc_omic), the omics
+ * branch of models/model_mm_attention_mil.py. n = 1..4 layers, hidden widths <= 1024, any input width.
+ * keep (nullable, per layer): [B, width] keep mask (0 / 1) of that layer's AlphaDropout(p), drawn by the caller; the kernel
+ * applies torch's affine a (y m + alpha' (1 - m)) + b. y: [B, width] pre-dropout SELU outputs, kept for the backward.
+ * out: [B, width of the last layer] = the network output (after the last layer's dropout). */
+typedef struct MmfSnnLayer {
+  const float* W;     /* [width, width of the previous layer (input width for layer 0)] */
+  const float* b;     /* [width] */
+  const float* keep;  /* [B, width] or NULL (eval mode / p = 0) */
+  float p;            /* AlphaDropout rate (used when keep != NULL) */
+  float* y;           /* [B, width] saved activations (forward: out, backward: in) */
+  int width;
+} MmfSnnLayer;
+int mmf_snn_mlp_fwd(const float* x, int B, int in_dim, const MmfSnnLayer* layers_host, int n_layers, float* out,
+                    void* stream);
+/* dout: [B, last width]. dW_host / db_host: HOST arrays of n_layers device pointers ([width, in] / [width]), written
+ * (accumulate = 0) or added to. dx: [B, in_dim] or NULL. workspace: B * sum(widths) floats (the pre-activation gradients). */
+int mmf_snn_mlp_bwd(const float* x, int B, int in_dim, const MmfSnnLayer* layers_host, int n_layers, const float* dout,
+                    float* const* dW_host, float* const* db_host, int accumulate, float* dx, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
 /* ---- training-step glue -------------------------------------------------
  * Fused multi-tensor Adam: torch.optim.Adam(lr, weight_decay) as the reference builds it (utils/utils.py:144-151), one
  * launch for all parameter tensors; step >= 1 is the 1-based step count (bias corrections). Per element:

@@ -105,6 +105,12 @@ class XfusionGrads(C.Structure):
                 ("dbo", C.c_void_p), ("dv", C.c_void_p)]
 
 
+class SnnLayer(C.Structure):
+    """MmfSnnLayer (include/mmf_b200.h): one Linear -> SELU -> AlphaDropout block of the fused SNN MLP."""
+    _fields_ = [("W", C.c_void_p), ("b", C.c_void_p), ("keep", C.c_void_p), ("p", C.c_float), ("y", C.c_void_p),
+                ("width", C.c_int)]
+
+
 _vp, _i, _i64, _sz, _f, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_float, C.c_uint64
 _PP = C.POINTER(C.c_void_p)
 
@@ -171,6 +177,8 @@ SIGNATURES = {
     "mmf_cox_workspace_bytes": (_sz, [_i]),
     "mmf_cox_fwd_bwd": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "mmf_adam_step_multi": (_i, [_PP, _PP, _PP, _PP, C.POINTER(C.c_int64), _i, _i, _f, _f, _f, _f, _f, _f, _f, _i, _vp, _vp]),
+    "mmf_snn_mlp_fwd": (_i, [_vp, _i, _i, C.POINTER(SnnLayer), _i, _vp, _vp]),
+    "mmf_snn_mlp_bwd": (_i, [_vp, _i, _i, C.POINTER(SnnLayer), _i, _vp, _PP, _PP, _i, _vp, _vp, _sz, _vp]),
     "mmf_xfusion_gate_fwd": (_i, [C.POINTER(XfusionMod), _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "mmf_xfusion_gate_bwd_workspace_bytes": (_sz, [_i, _i, _i]),
     "mmf_xfusion_gate_bwd": (_i, [C.POINTER(XfusionMod), _i, _i, _i, _vp, _vp, _vp, _vp, _vp, C.POINTER(XfusionGrads), _i,

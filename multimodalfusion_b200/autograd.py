@@ -166,6 +166,29 @@ class KronEncoderTrain(torch.autograd.Function):
         return (dW, db, None, None, *d_o)
 
 
+class SnnMlp(torch.autograd.Function):
+    """SNN_Block x n (Linear -> SELU -> AlphaDropout, models/model_modules.py:64-68) as one forward launch and one backward
+    chain launch + the weight-gradient GEMMs (csrc/snn_mlp.cuh). apply(x, ps, keeps, W_0, b_0, W_1, b_1, ...): ps = tuple of
+    the blocks' dropout rates, keeps = tuple of keep masks [B, width] (or None: eval mode)."""
+
+    @staticmethod
+    def forward(ctx, x, ps, keeps, *wb):
+        layers = [(wb[2 * i], wb[2 * i + 1], keeps[i], ps[i]) for i in range(len(ps))]
+        out, ys = ops.snn_mlp_fwd(x, layers)
+        ctx.ps, ctx.keeps = ps, keeps
+        ctx.save_for_backward(x, *ys, *wb)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        n = len(ctx.ps)
+        x, *rest = ctx.saved_tensors
+        ys, wb = rest[:n], rest[n:]
+        layers = [(wb[2 * i], wb[2 * i + 1], ctx.keeps[i], ctx.ps[i]) for i in range(n)]
+        dx, grads = ops.snn_mlp_bwd(x, layers, ys, dout, ctx.needs_input_grad[0])
+        return (dx, None, None, *[g for pair in grads for g in pair])
+
+
 class XfusionGate(torch.autograd.Function):
     """Per-modality gated reduction of XlinearFusion for ALL modalities in one forward launch and two or three backward
     launches (models/model_modules.py:156-166; csrc/xfusion_gate.cuh). apply(m, mask, v_1..v_m, then (Wh, bh, Wz, bz, Wo, bo)

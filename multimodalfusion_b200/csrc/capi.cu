@@ -16,6 +16,7 @@
 #include "train_glue.cuh"
 #include "head_kernels.cuh"
 #include "xfusion_gate.cuh"
+#include "snn_mlp.cuh"
 #include <math.h>
 
 using namespace mmf;
@@ -1079,6 +1080,62 @@ int mmf_xfusion_gate_bwd(const MmfXfusionMod* mods_host, int m, int B, int dim, 
   const long long total = (long long)m * (XF_S * ((long long)dim * m + dim) + XF_SMALL_OUT);
   xfusion_gate_bwd_finalize_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(P, part_small, part_w, G, accumulate);
   if (any_dv) xfusion_gate_bwd_dv_kernel<<<dim3((B + XF_RB - 1) / XF_RB, m), 256, 0, st>>>(P, dhz, G);
+  return launch_status();
+}
+
+namespace {
+int snn_pack(const float* x, int B, int in_dim, const MmfSnnLayer* layers, int n, SnnLayers* P) {
+  if (!x || !layers || B <= 0 || in_dim <= 0 || n < 1 || n > SNN_MAX_LAYERS) return MMF_E_INVALID;
+  *P = SnnLayers{};
+  P->n = n; P->B = B; P->d[0] = in_dim;
+  for (int l = 0; l < n; ++l) {
+    const MmfSnnLayer& q = layers[l];
+    if (!q.W || !q.b || !q.y || q.width <= 0 || q.width > SNN_MAX_WIDTH) return MMF_E_INVALID;
+    if (q.keep && !(q.p > 0.f && q.p < 1.f)) return MMF_E_INVALID;
+    P->d[l + 1] = q.width; P->W[l] = q.W; P->b[l] = q.b; P->keep[l] = q.keep; P->y[l] = q.y;
+    const double al = (double)MMF_ALPHA_PRIME, pp = q.keep ? (double)q.p : 0.0;
+    const double a = 1.0 / sqrt((1.0 - pp) * (1.0 + pp * al * al));
+    P->da[l] = (float)a; P->db[l] = (float)(-a * al * pp);
+  }
+  return MMF_OK;
+}
+}  // namespace
+
+int mmf_snn_mlp_fwd(const float* x, int B, int in_dim, const MmfSnnLayer* layers_host, int n_layers, float* out,
+                    void* stream) {
+  SnnLayers P;
+  MMF_TRY(snn_pack(x, B, in_dim, layers_host, n_layers, &P));
+  if (!out) return MMF_E_INVALID;
+  snn_mlp_fwd_kernel<<<(B + SNN_RB - 1) / SNN_RB, 256, 0, (cudaStream_t)stream>>>(P, x, out);
+  return launch_status();
+}
+
+int mmf_snn_mlp_bwd(const float* x, int B, int in_dim, const MmfSnnLayer* layers_host, int n_layers, const float* dout,
+                    float* const* dW_host, float* const* db_host, int accumulate, float* dx, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  SnnLayers P;
+  MMF_TRY(snn_pack(x, B, in_dim, layers_host, n_layers, &P));
+  if (!dout || !dW_host || !db_host) return MMF_E_INVALID;
+  size_t need = 0;
+  for (int l = 0; l < n_layers; ++l) need += (size_t)B * (size_t)P.d[l + 1] * sizeof(float);
+  if (!workspace || workspace_bytes < need) return MMF_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  SnnBwd G = {};
+  float* w = static_cast<float*>(workspace);
+  for (int l = 0; l < n_layers; ++l) { G.dpre[l] = w; w += (size_t)B * P.d[l + 1]; }
+  G.dx = dx;
+  snn_mlp_bwd_chain_kernel<<<(B + SNN_RB - 1) / SNN_RB, 256, 0, st>>>(P, dout, G);
+  for (int l = 0; l < n_layers; ++l) {
+    const int d_in = P.d[l], d_out = P.d[l + 1];
+    if (dW_host[l]) {
+      LoadPlainT A{G.dpre[l], d_out};
+      EpiStoreAcc E{dW_host[l], d_in, accumulate};
+      if (l == 0) launch_sgemm(d_out, d_in, B, A, LoadColMajor{x, d_in}, E, st);
+      else launch_sgemm(d_out, d_in, B, A, LoadAlphaDropCol{P.y[l - 1], P.keep[l - 1], d_in, P.da[l - 1], P.db[l - 1]}, E, st);
+    }
+    if (db_host[l])
+      colsum_functor_kernel<<<(d_out + 31) / 32, 256, 0, st>>>(B, d_out, ElemPlain{G.dpre[l], d_out}, db_host[l], accumulate);
+  }
   return launch_status();
 }
 

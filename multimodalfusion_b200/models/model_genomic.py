@@ -6,7 +6,7 @@ import torch.nn as nn
 from .._lib import ACT_NONE
 from ..autograd import Dense, HazardHead
 from ..utils.utils import init_max_weights
-from .model_modules import SNN_Block, snn_block_forward
+from .model_modules import SNN_Block, snn_forward
 
 
 class MaxNet_base(nn.Module):
@@ -30,9 +30,7 @@ class MaxNet_base(nn.Module):
         self.classifier = self.classifier.to(device)
 
     def features(self, x):
-        for block in self.fc_omic:
-            x = snn_block_forward(block, x)
-        return x
+        return snn_forward(self.fc_omic, x)
 
     def forward(self, **kwargs):
         pass

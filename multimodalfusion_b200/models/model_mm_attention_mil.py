@@ -22,8 +22,7 @@ import torch.nn as nn
 from .._lib import ACT_NONE, ACT_RELU
 from ..autograd import Dense, HazardHead, reduce_dim_forward
 from ..utils.utils import initialize_weights
-from .model_modules import (AmilBranch, Attn_Net, Attn_Net_Gated, SNN_Block, XlinearFusion,
-                            snn_block_forward)
+from .model_modules import AmilBranch, Attn_Net, Attn_Net_Gated, SNN_Block, XlinearFusion, snn_forward
 
 
 class MM_MIL_Attention_fc(nn.Module):
@@ -112,9 +111,7 @@ class MM_MIL_Attention_fc_surv(MM_MIL_Attention_fc):
         if 'omic' in self.mode:
             o = kwargs['genomic_features']
             o = o.unsqueeze(0) if o.dim() == 1 else o
-            for block in self.fc_omic:
-                o = snn_block_forward(block, o)
-            emb['omic'] = o
+            emb['omic'] = snn_forward(self.fc_omic, o)
         # fusion order of the reference (:167-186): (radio, path), (radio, omic), (omic, path),
         # (radio, path, omic)
         has = lambda k: k in emb
@@ -179,10 +176,7 @@ class MM_MIL_Attention_fc_surv(MM_MIL_Attention_fc):
     def _captum_omic(self, h_omic):
         if 'omic' not in self.mode:
             raise NotImplementedError('use another captum function')
-        o = h_omic.float()
-        for block in self.fc_omic:
-            o = snn_block_forward(block, o)
-        return o
+        return snn_forward(self.fc_omic, h_omic.float())
 
     def _captum_risk(self, vs):
         _, hid, Wk, bk = self._fuse(vs)

@@ -13,7 +13,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import ops
-from ..autograd import BatchNorm1dFn, Dense, HighwayMix, KronEncoder, KronEncoderTrain, XfusionGate
+from ..autograd import BatchNorm1dFn, Dense, HighwayMix, KronEncoder, KronEncoderTrain, SnnMlp, XfusionGate
 from .._lib import ACT_NONE, ACT_RELU, ACT_SELU, ACT_SIGMOID, ACT_TANH
 
 
@@ -121,6 +121,25 @@ def snn_block_forward(block: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
     if block.training and block[2].p > 0:
         y = F.alpha_dropout(y, block[2].p, True)  # elementwise mask only; the GEMM+SELU is ours
     return y
+
+
+def snn_forward(blocks, x: torch.Tensor) -> torch.Tensor:
+    """A chain of SNN_Blocks (``fc_omic`` of models/model_genomic.py:22-25 and of the multimodal model) on a [B, d] input:
+    one fused launch on the GPU (csrc/snn_mlp.cuh; the AlphaDropout keep masks are drawn here, one Bernoulli draw per block),
+    block by block otherwise (CPU glue tests, shapes the fused kernel does not cover)."""
+    blocks = list(blocks)
+    layers = [(b_[0].weight, b_[0].bias) for b_ in blocks]
+    if x.is_cuda and x.dim() == 2 and ops.snn_mlp_supported(x, layers):
+        ps, keeps = [], []
+        for b_ in blocks:
+            p_ = float(b_[2].p) if (b_.training and b_[2].p > 0) else 0.0
+            ps.append(p_)
+            keeps.append(torch.empty(x.shape[0], b_[0].weight.shape[0], dtype=torch.float32, device=x.device).bernoulli_(1 - p_)
+                         if p_ > 0 else None)
+        return SnnMlp.apply(x.float(), tuple(ps), tuple(keeps), *[t for wb in layers for t in wb])
+    for b_ in blocks:
+        x = snn_block_forward(b_, x)
+    return x
 
 
 class _AttnBase(nn.Module):

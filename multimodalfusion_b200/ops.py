@@ -356,6 +356,46 @@ def dense_bwd_into(x, W, y, dy, dW: torch.Tensor, db: torch.Tensor) -> None:
                               None, in_dim, 0, _p(dW), _p(db), _stream()), "mmf_dense_bwd")
 
 
+def snn_mlp_supported(x, layers) -> bool:
+    """Shapes the fused SNN MLP covers: 1-4 blocks, hidden widths <= 1024, a 2-D input."""
+    return x.dim() == 2 and 1 <= len(layers) <= 4 and all(W.shape[0] <= 1024 for W, *_ in layers)
+
+
+def _snn_layers(layers, ys):
+    arr = (_lib.SnnLayer * len(layers))()
+    for i, ((W, b, keep, p_), y) in enumerate(zip(layers, ys)):
+        arr[i] = _lib.SnnLayer(_p(W), _p(b), _p(keep), float(p_), _p(y), W.shape[0])
+    return arr
+
+
+def snn_mlp_fwd(x, layers):
+    """SNN_Block x n in ONE launch (models/model_modules.py:64-68). layers: [(W, b, keep mask [B, width] or None, p)].
+    Returns (out [B, last width], [y_l]: the pre-dropout SELU outputs the backward needs)."""
+    _require_cuda(x)
+    x = _f32c(x)
+    layers = [(_f32c(W), _f32c(b), None if k is None else _f32c(k), p_) for W, b, k, p_ in layers]
+    B = x.shape[0]
+    ys = [torch.empty(B, W.shape[0], dtype=torch.float32, device=x.device) for W, *_ in layers]
+    out = torch.empty_like(ys[-1])
+    check(lib().mmf_snn_mlp_fwd(_p(x), B, x.shape[1], _snn_layers(layers, ys), len(layers), _p(out), _stream()),
+          "mmf_snn_mlp_fwd")
+    return out, ys
+
+
+def snn_mlp_bwd(x, layers, ys, dout, need_dx: bool):
+    """Returns (dx or None, [(dW, db)])."""
+    x, dout = _f32c(x), _f32c(dout)
+    layers = [(_f32c(W), _f32c(b), None if k is None else _f32c(k), p_) for W, b, k, p_ in layers]
+    B = x.shape[0]
+    grads = [(torch.empty_like(W), torch.empty_like(b)) for W, b, *_ in layers]
+    dx = torch.empty_like(x) if need_dx else None
+    ws = torch.empty(B * sum(W.shape[0] for W, *_ in layers), dtype=torch.float32, device=x.device)
+    check(lib().mmf_snn_mlp_bwd(_p(x), B, x.shape[1], _snn_layers(layers, ys), len(layers), _p(dout),
+                                _lib.ptr_array([g[0].data_ptr() for g in grads]), _lib.ptr_array([g[1].data_ptr() for g in grads]),
+                                0, _p(dx), _p(ws), ws.numel() * 4, _stream()), "mmf_snn_mlp_bwd")
+    return dx, grads
+
+
 def _xf_mods(v_list, params):
     arr = (_lib.XfusionMod * len(v_list))()
     for i, (v, (Wh, bh, Wz, bz, Wo, bo)) in enumerate(zip(v_list, params)):
