@@ -266,6 +266,30 @@ int mmf_amil_bwd_wgrad(const void* x, int64_t N, int64_t ldx, const MmfAmilWeigh
                        int flags, const MmfAmilGrads* g, void* dx, void* workspace,
                        size_t workspace_bytes, void* stream);
 
+/* ---- varlen-packed TRAINING of a window of bags ------------------------------------------------------------------
+ * The bags of a gradient-accumulation window (`--gc` bags between optimizer steps, utils/core_utils.py:242-247: loss / gc,
+ * backward, step every gc bags) as ONE launch set: the bags are packed into one [R, 1024] buffer, each starting on a
+ * 128-row boundary (zero padding; the format of mmf_amil_infer_varlen); tile_valid[t] = rows of tile t that belong to its
+ * bag, tile_bag[t] = its bag, seg_tile_offsets[b .. b + 1] = the bag's tile range (device int32 arrays; tile_valid /
+ * tile_bag padded to an EVEN number of tiles with valid = 0). Call order on one stream:
+ *   mmf_amil_window_fwd_train      fused forward + activation stash of every tile, per-tile softmax partials
+ *   mmf_amil_window_head_nll_step  per bag (grid.y): combine, classifier, hazards, nll_surv, loss_scale * its gradient ->
+ *                                  M / dM [bags, L], ml [bags, 2], hazards / S [bags, K], loss [bags]; dWk / dbk += (atomic)
+ *   mmf_amil_window_bwd            gate + hidden backward with per-tile bag statistics, then the grouped weight gradients:
+ *                                  the window's summed gradients accumulate into g (MMF_STASHED required; no dx)
+ * R is a multiple of 128; workspace as mmf_amil_bwd_workspace_bytes(R, ...). */
+int mmf_amil_window_fwd_train(const void* x, int64_t R, int64_t ldx, const MmfAmilWeights* w, int L, int D, int flags,
+                              uint64_t seed, const int32_t* tile_valid, float* A_raw, float* partials, void* workspace,
+                              size_t workspace_bytes, float* zero_buf, int64_t zero_count, void* stream);
+int mmf_amil_window_head_nll_step(const float* partials, const int32_t* seg_tile_offsets, int n_bags, int max_tiles,
+                                  int L, const float* Wk, const float* bk, int K, const int64_t* Y, const float* c,
+                                  float alpha, float eps, float loss_scale, float* M, float* ml, float* hazards, float* S,
+                                  int64_t* Y_hat, float* loss, float* dM, float* dWk, float* dbk, void* stream);
+int mmf_amil_window_bwd(const void* x, int64_t R, int64_t ldx, const MmfAmilWeights* w, int L, int D, int flags,
+                        uint64_t seed, const float* A_raw, const float* ml, const float* M, const float* dM,
+                        const int32_t* tile_bag, const int32_t* tile_valid, const MmfAmilGrads* g, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
 /* Dense bf16 tensor-core GEMM used either side of the AMIL core (radio reduce_dim and its
  * gradients): C[M,N] = A[M,K] B[N,K]^T + bias (A given as up to 4 K-segments = the modality
  * bags that the reference concatenates, models/model_attention_mil_radio.py:81-82).

@@ -58,6 +58,9 @@ struct HiddenFusedArgs {
   float* dbc;               // [1]  accumulated
   float* db1;               // [L]  accumulated
   float du_scale;           // 1 or 1/(1-p)
+  // varlen window (general phase A only): the rows are a packed buffer of several bags that start on 128-row boundaries
+  const int* tile_bag;      // [tiles] bag of every 128-row tile: M / dM are [bags, L], ml is [bags, 2]
+  const int* tile_valid;    // [tiles] rows of the tile that belong to its bag (the rest is zero padding)
   unsigned long long seed;
   unsigned long long* dbg;
 };
@@ -175,6 +178,15 @@ amil_hidden_fused_kernel(const __grid_constant__ CUtensorMap tmAG,   // stash fp
   a.mask = pdl_fresh(a.mask); a.z = pdl_fresh(a.z); a.partials = pdl_fresh(a.partials); a.tile_head = pdl_fresh(a.tile_head);
   a.dA_raw = pdl_fresh(a.dA_raw);
   if (DROP) a.seed = seed_resolve(a.seed);   // (device-resident seed of a graph-captured step)
+  if (!HEADPROJ && a.tile_bag != nullptr && row0 < a.N) {
+    // packed window of bags: this CTA's tile belongs to ONE bag — its softmax statistics, pooled embedding and dM — and
+    // only its first tile_valid rows exist (padding rows get p = ds = 0 and a zero mask: dG = dU = 0, nothing reaches
+    // the weight gradients)
+    const long long tile = row0 >> 7;
+    const long long bag = pdl_fresh(a.tile_bag)[tile];
+    a.M += bag * L; a.dM += bag * L; a.ml += 2 * bag;
+    a.N = row0 + pdl_fresh(a.tile_valid)[tile];
+  }
   timeline_wait_done(tl);
   if (threadIdx.x == 0) MMF_STAMP(a, 1);
 

@@ -367,9 +367,11 @@ int check_head(const MmfHeadStep* h, int64_t N) {
 // additionally z = Wk h (fp32 [N, 4|8]) and the folded head step run by the last tile CTA.
 int fwd_train_impl(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, int L, int D, int flags,
                    uint64_t seed, float* A_raw, float* partials, void* workspace, size_t workspace_bytes,
-                   float* zero_buf, int64_t zero_count, const MmfHeadStep* head, void* stream) {
+                   float* zero_buf, int64_t zero_count, const MmfHeadStep* head, void* stream,
+                   const int32_t* tile_valid = nullptr) {
   MMF_TRY(check_amil_common(x, N, ldx, w, L, D));
   if (!A_raw || !partials || !workspace) return MMF_E_INVALID;
+  if (tile_valid && (head || (N & 127))) return MMF_E_INVALID;   // packed windows: whole 128-row tiles, general head
   const int gated = flags & MMF_GATED;
   const BwdWs lay = bwd_layout(N, L, D, gated);
   if (workspace_bytes < lay.total) return MMF_E_WORKSPACE;
@@ -377,7 +379,7 @@ int fwd_train_impl(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* 
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   AmilArgs a = {};
   a.N = N; a.b1 = w->b1; a.bab = w->bab; a.wc = w->wc; a.bc = w->bc;
-  a.A_raw = A_raw; a.partials = partials; a.store_h = 1;
+  a.A_raw = A_raw; a.partials = partials; a.store_h = 1; a.tile_valid = tile_valid;
   a.AG = reinterpret_cast<uint16_t*>(ws + lay.off_dG); a.ldag = gated ? 2 * D : D;
   a.mask_out = reinterpret_cast<uint32_t*>(ws + lay.off_mask);
   if (zero_buf) {
@@ -486,8 +488,10 @@ namespace {
 int bwd_gate_hidden_stashed_impl(int64_t N, const MmfAmilWeights* w, int L, int D, int flags, uint64_t seed,
                                  const float* A_raw, const float* ml, const float* M, const float* dM,
                                  const float* dA_raw, const MmfAmilGrads* g, void* workspace,
-                                 size_t workspace_bytes, const MmfHeadStep* head, const float* partials, void* stream) {
+                                 size_t workspace_bytes, const MmfHeadStep* head, const float* partials, void* stream,
+                                 const int32_t* tile_bag = nullptr, const int32_t* tile_valid = nullptr) {
   if (!w || !w->wc || !w->Wab || N <= 0 || !workspace) return MMF_E_INVALID;
+  if ((tile_bag != nullptr) != (tile_valid != nullptr) || (tile_bag && (head || (N & 127)))) return MMF_E_INVALID;
   if (!((L == 256 && D == 256) || (L == 512 && D == 384) || (L == 256 && D == 384))) return MMF_E_UNSUPPORTED;
   if (!A_raw || !g || !g->dbab || !g->dwc || !g->dbc || !g->db1) return MMF_E_INVALID;
   if (!head && (!ml || !M || !dM)) return MMF_E_INVALID;
@@ -521,6 +525,7 @@ int bwd_gate_hidden_stashed_impl(int64_t N, const MmfAmilWeights* w, int L, int 
     t.dWk = head->dWk; t.dbk = head->dbk;
   }
   a.du_scale = (flags & MMF_DROPOUT_H) ? (1.0f / 0.75f) : 1.0f;
+  a.tile_bag = tile_bag; a.tile_valid = tile_valid;
   a.seed = seed; a.dbg = stamp_buf(2);
   cudaStream_t st = (cudaStream_t)stream;
   if (L == 256 && D == 256) return gated ? launch_hidden_fused<256, 256, true>(a, flags, tmAG, tmWab, tmDU, st) : launch_hidden_fused<256, 256, false>(a, flags, tmAG, tmWab, tmDU, st);
@@ -654,6 +659,42 @@ int mmf_amil_bwd(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w,
     MMF_TRY(mmf_amil_bwd_hidden(x, N, ldx, w, L, D, flags, A_raw, ml, dM, g, workspace, workspace_bytes, stream));
   }
   return mmf_amil_bwd_wgrad(x, N, ldx, w, L, D, flags, g, dx, workspace, workspace_bytes, stream);
+}
+
+// ---- varlen-packed TRAINING of a window of bags (gradient accumulation over `gc` small bags in one launch set) ----
+int mmf_amil_window_fwd_train(const void* x, int64_t R, int64_t ldx, const MmfAmilWeights* w, int L, int D, int flags,
+                              uint64_t seed, const int32_t* tile_valid, float* A_raw, float* partials, void* workspace,
+                              size_t workspace_bytes, float* zero_buf, int64_t zero_count, void* stream) {
+  if (!tile_valid) return MMF_E_INVALID;
+  return fwd_train_impl(x, R, ldx, w, L, D, flags, seed, A_raw, partials, workspace, workspace_bytes, zero_buf, zero_count,
+                        nullptr, stream, tile_valid);
+}
+
+int mmf_amil_window_head_nll_step(const float* partials, const int32_t* seg_tile_offsets, int n_bags, int max_tiles,
+                                  int L, const float* Wk, const float* bk, int K, const int64_t* Y, const float* c,
+                                  float alpha, float eps, float loss_scale, float* M, float* ml, float* hazards, float* S,
+                                  int64_t* Y_hat, float* loss, float* dM, float* dWk, float* dbk, void* stream) {
+  if (!partials || !seg_tile_offsets || !Wk || !bk || !Y || !c || !M || !ml || !hazards || !S || !loss || !dM)
+    return MMF_E_INVALID;
+  if (n_bags <= 0 || n_bags > 65535 || max_tiles <= 0 || max_tiles > 4096 || K <= 0 || K > 16) return MMF_E_UNSUPPORTED;
+  const int cp = L / (2 * HEAD_CLUSTER);
+  if (!(L % (2 * HEAD_CLUSTER) == 0 && cp >= 16 && cp <= 64 && 512 % cp == 0)) return MMF_E_UNSUPPORTED;   // L in {256, 512, 1024}
+  return launch_pdl(amil_head_step_cluster_kernel, dim3(HEAD_CLUSTER, n_bags), dim3(512), 0, (cudaStream_t)stream,
+                    partials, 0, L, Wk, bk, K, reinterpret_cast<const long long*>(Y), c, alpha, eps, M, ml, hazards, S,
+                    reinterpret_cast<long long*>(Y_hat), loss, dM, dWk, dbk, reinterpret_cast<const int*>(seg_tile_offsets),
+                    loss_scale);
+}
+
+int mmf_amil_window_bwd(const void* x, int64_t R, int64_t ldx, const MmfAmilWeights* w, int L, int D, int flags,
+                        uint64_t seed, const float* A_raw, const float* ml, const float* M, const float* dM,
+                        const int32_t* tile_bag, const int32_t* tile_valid, const MmfAmilGrads* g, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  if (!g || !g->dW1 || !g->db1 || !g->dWab || !g->dbab || !g->dwc || !g->dbc || !tile_bag || !tile_valid) return MMF_E_INVALID;
+  if (!(flags & MMF_STASHED) || (flags & MMF_NEED_DX)) return MMF_E_UNSUPPORTED;
+  MMF_TRY(check_amil_common(x, R, ldx, w, L, D));
+  MMF_TRY(bwd_gate_hidden_stashed_impl(R, w, L, D, flags, seed, A_raw, ml, M, dM, nullptr, g, workspace, workspace_bytes,
+                                       nullptr, nullptr, stream, tile_bag, tile_valid));
+  return mmf_amil_bwd_wgrad(x, R, ldx, w, L, D, flags, g, nullptr, workspace, workspace_bytes, stream);
 }
 
 int mmf_linear_bf16(const void* const* A_segs, int n_segs, int64_t M, int K_per_seg, int64_t lda,
@@ -869,7 +910,7 @@ int mmf_amil_head_nll_step(const float* partials, int64_t n, int L, const float*
   if (L % (2 * HEAD_CLUSTER) == 0 && cp >= 16 && cp <= 64 && 512 % cp == 0)
     return launch_pdl(amil_head_step_cluster_kernel, dim3(HEAD_CLUSTER), dim3(512), 0, (cudaStream_t)stream,
                       partials, (int)n, L, Wk, bk, K, reinterpret_cast<const long long*>(Y), c, alpha, eps, M, ml,
-                      hazards, S, reinterpret_cast<long long*>(Y_hat), loss, dM, dWk, dbk);
+                      hazards, S, reinterpret_cast<long long*>(Y_hat), loss, dM, dWk, dbk, (const int*)nullptr, 1.0f);
   return launch_pdl(amil_head_step_kernel, dim3(1), dim3(512), 0, (cudaStream_t)stream, partials, (int)n, L, Wk, bk, K,
                     reinterpret_cast<const long long*>(Y), c, alpha, eps, M, ml, hazards, S,
                     reinterpret_cast<long long*>(Y_hat), loss, dM, dWk, dbk);

@@ -771,7 +771,8 @@ amil_head_step_cluster_kernel(const float* __restrict__ parts, int n, int L, con
                               const float* __restrict__ cp, float alpha, float eps, float* __restrict__ M,
                               float* __restrict__ ml, float* __restrict__ hazards, float* __restrict__ S,
                               long long* __restrict__ Y_hat, float* __restrict__ loss, float* __restrict__ dM,
-                              float* __restrict__ dWk, float* __restrict__ dbk) {
+                              float* __restrict__ dWk, float* __restrict__ dbk, const int* __restrict__ seg,
+                              float loss_scale) {
   __shared__ float s_w[4096];
   __shared__ float s_acc[1024];            // [RG][LC] partial column sums of this CTA's slice
   __shared__ float s_M[128];               // this CTA's slice of M
@@ -791,6 +792,19 @@ amil_head_step_cluster_kernel(const float* __restrict__ parts, int n, int L, con
   griddep_wait();
   parts = pdl_fresh(parts);
   timeline_wait_done(tl);   // PDL: the partials come from the tile kernel launched just before
+  // seg != null: a WINDOW of bags (varlen-packed training, blockIdx.y = bag): the bag's tiles are partial rows
+  // seg[bag] .. seg[bag + 1], every per-bag input / output is indexed by the bag, the classifier gradients of the bags are
+  // added atomically and the loss gradient carries loss_scale (1 / gc of the accumulation window)
+  const bool window = seg != nullptr;
+  if (window) {
+    const int bag = blockIdx.y;
+    const int t0 = seg[bag];
+    n = seg[bag + 1] - t0;
+    parts += (long long)t0 * (L + 2);
+    Yp += bag; cp += bag; M += (long long)bag * L; ml += 2 * bag; hazards += (long long)bag * K; S += (long long)bag * K;
+    if (Y_hat) Y_hat += bag;
+    loss += bag; dM += (long long)bag * L;
+  }
   // early scalar loads (independent of everything else)
   long long y = 0; float cb = 0.f;
   if (tid == 0) { y = Yp[0]; cb = cp[0]; }
@@ -913,7 +927,7 @@ amil_head_step_cluster_kernel(const float* __restrict__ parts, int n, int L, con
         if (k > j) run *= (1.f - h[k]);
         g -= dS[k] * run;
       }
-      s_dlogit[j] = g * h[j] * (1.f - h[j]);
+      s_dlogit[j] = g * h[j] * (1.f - h[j]) * loss_scale;
     }
   }
   __syncthreads();
@@ -923,11 +937,16 @@ amil_head_step_cluster_kernel(const float* __restrict__ parts, int n, int L, con
     for (int j = 0; j < K; ++j) {
       const float dl = s_dlogit[j];
       acc = fmaf(dl, s_Wk[j * LC + tid], acc);
-      if (dWk) dWk[(long long)j * L + c_lo + tid] += dl * mv;
+      if (dWk) {
+        float* pw = dWk + (long long)j * L + c_lo + tid;
+        if (window) atomicAdd(pw, dl * mv); else *pw += dl * mv;
+      }
     }
     dM[c_lo + tid] = acc;
   }
-  if (rank == 0 && dbk && tid < K) dbk[tid] += s_dlogit[tid];
+  if (rank == 0 && dbk && tid < K) {
+    if (window) atomicAdd(dbk + tid, s_dlogit[tid]); else dbk[tid] += s_dlogit[tid];
+  }
   timeline_end(1, tl);
 }
 

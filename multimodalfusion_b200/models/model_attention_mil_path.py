@@ -73,6 +73,32 @@ class MIL_Attention_fc_surv_path(MIL_Attention_fc_path):
         return _fused_step.run(self, self.attention_net_WSI, self.classifier, path_features, Y, c, alpha, loss_scale,
                                accumulate, eps)[:5]
 
+    def fused_window_step(self, bags, Y, c, alpha=0.0, accumulate=False, eps=1e-7):
+        """The `gc` bags of one gradient-accumulation window (utils/core_utils.py:242-247: ``loss / gc`` -> backward per bag,
+        optimizer step every gc bags) as ONE launch set instead of gc steps: the bags are packed varlen (each on a 128-row
+        boundary), the fused forward runs every tile of the window, one head launch evaluates every bag's classifier /
+        hazards / nll_surv (scaled by 1 / gc), the backward accumulates the window's summed gradients into the parameters'
+        ``.grad``. bags: list of [N_i, 1024] CUDA tensors; Y, c: one entry per bag. Train-mode dropout draws one mask per
+        packed row. Returns (hazards [gc,K], S [gc,K], Y_hat [gc,1], [A_raw_i [1,N_i]], loss [gc] (unscaled))."""
+        from .. import ops
+        from . import _fused_step
+        from .model_modules import _seed_from_torch
+        if not hasattr(self, "_fused"):
+            self.enable_fused_step()
+        if self.bag_group is not None:
+            raise NotImplementedError("fused_window_step runs whole bags")
+        f = self._fused
+        seq, attn = self.attention_net_WSI, self.attention_net_WSI[3]
+        prep = AmilBranch.prepared(seq)
+        flags = ops.amil_flags(prep.gated, dropout_h=self.training, dropout_attn=self.training and attn.use_dropout)
+        packed = ops.pack_bags(bags)
+        out = ops.amil_window_step(packed, prep, flags, _seed_from_torch() if self.training else 0,
+                                   self.classifier.weight.detach(), self.classifier.bias.detach(), Y, c, alpha, f["grads"],
+                                   dWk=f["dWk"], dbk=f["dbk"], eps=eps, loss_scale=1.0 / len(bags),
+                                   zero=None if accumulate else f["flat"])
+        A = [out["A_raw"][o:o + n].view(1, n) for o, n in zip(packed.row_offsets, packed.sizes)]
+        return out["hazards"], out["S"], out["Y_hat"], A, out["loss"]
+
     def graphed_fused_step(self, optimizer, path_features, Y, c, alpha=0.0, loss_scale=1.0, eps=1e-7):
         """fused_step + ``optimizer.step()`` (FusedAdam) as one CUDA-graph launch per bag size; see _fused_step.graphed."""
         from . import _fused_step

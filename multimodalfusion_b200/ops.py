@@ -182,6 +182,8 @@ class PackedBags:
     seg_tile_offsets: torch.Tensor
     row_offsets: list
     sizes: list
+    tile_bag: Optional[torch.Tensor] = None      # int32 [tiles padded to an even count]: bag of every tile (training windows)
+    tile_valid_even: Optional[torch.Tensor] = None   # tile_valid padded likewise (pad tile: 0 rows)
 
 
 def pack_bags(bags: Sequence[torch.Tensor]) -> PackedBags:
@@ -204,7 +206,13 @@ def pack_bags(bags: Sequence[torch.Tensor]) -> PackedBags:
     tv = torch.full((seg[-1],), TILE_ROWS, dtype=torch.int32)
     for t0, t, n in zip(seg, tiles, sizes):
         tv[t0 + t - 1] = n - (t - 1) * TILE_ROWS
-    return PackedBags(x, tv.to(dev), torch.tensor(seg, dtype=torch.int32, device=dev), row_off, sizes)
+    n_even = seg[-1] + (seg[-1] & 1)
+    tb = torch.zeros(n_even, dtype=torch.int32)
+    tve = torch.zeros(n_even, dtype=torch.int32)
+    tve[:seg[-1]] = tv
+    for i, (t0, t) in enumerate(zip(seg, tiles)):
+        tb[t0:t0 + t] = i
+    return PackedBags(x, tv.to(dev), torch.tensor(seg, dtype=torch.int32, device=dev), row_off, sizes, tb.to(dev), tve.to(dev))
 
 
 def amil_infer_varlen(packed: PackedBags, w: AmilPrepared, Wk: torch.Tensor, bk: torch.Tensor):
@@ -607,6 +615,51 @@ def amil_fused_step(x: torch.Tensor, w: AmilPrepared, flags: int, seed: int, buf
                                   _p(buf.partials), C.byref(head), None, C.byref(g), _p(dx), buf.workspace.data_ptr(),
                                   buf.workspace.numel(), _stream()), "mmf_amil_bwd_head")
     return buf.loss
+
+
+def amil_window_step(packed: PackedBags, w: AmilPrepared, flags: int, seed: int, Wk, bk, Y, c, alpha: float, grads: dict,
+                     dWk=None, dbk=None, eps: float = 1e-7, loss_scale: float = 1.0, zero: Optional[torch.Tensor] = None):
+    """fwd + nll_surv + bwd of a WINDOW of bags (the `gc` bags between two optimizer steps, utils/core_utils.py:242-247) in
+    one launch set: fused forward of every tile of the packed buffer, one head launch (a cluster per bag), gate + hidden
+    backward with per-tile bag statistics, grouped weight gradients. The window's summed gradients (each bag's loss scaled
+    by `loss_scale` = 1 / gc) accumulate into `grads` / dWk / dbk; `zero` (the flat gradient buffer) is cleared by the
+    forward first. Bags of up to 4096 rows run the split-precision fc like the batch-1 step. Returns dict(loss [n],
+    hazards, S [n,K], Y_hat [n,1], M [n,L], A_raw [R] (index with packed.row_offsets / sizes))."""
+    _require_cuda(packed.x, Wk)
+    n, R, dev = len(packed.sizes), packed.x.shape[0], packed.x.device
+    x = packed.x
+    if max(packed.sizes) <= PRECISE_FC_MAX_ROWS:
+        x = split_bag(packed.x)
+        flags |= MMF_PRECISE_FC
+    _check_bag(x, flags)
+    K, L = Wk.shape[0], w.L
+    Wk, bk = _f32c(Wk), _f32c(bk)
+    Y = Y.detach().reshape(-1).to(device=dev, dtype=torch.int64).contiguous()
+    c = c.detach().reshape(-1).to(device=dev, dtype=torch.float32).contiguous()
+    if Y.numel() != n or c.numel() != n:
+        raise ValueError("one label / censorship flag per bag")
+    f32 = dict(dtype=torch.float32, device=dev)
+    ws = amil_bwd_workspace(R, w, flags, dev)
+    A_raw = torch.empty(R, **f32)
+    partials = torch.empty(R // TILE_ROWS, L + 2, **f32)
+    out = dict(M=torch.empty(n, L, **f32), ml=torch.empty(n, 2, **f32), hazards=torch.empty(n, K, **f32),
+               S=torch.empty(n, K, **f32), Y_hat=torch.empty(n, 1, dtype=torch.int64, device=dev),
+               loss=torch.empty(n, **f32), dM=torch.empty(n, L, **f32), A_raw=A_raw)
+    wst = w.struct()
+    check(lib().mmf_amil_window_fwd_train(_p(x), R, x.stride(0), C.byref(wst), w.L, w.D, flags, seed, _p(packed.tile_valid_even),
+                                          _p(A_raw), _p(partials), ws.data_ptr(), ws.numel(), _p(zero),
+                                          0 if zero is None else zero.numel(), _stream()), "mmf_amil_window_fwd_train")
+    max_tiles = max((s_ + TILE_ROWS - 1) // TILE_ROWS for s_ in packed.sizes)
+    check(lib().mmf_amil_window_head_nll_step(_p(partials), _p(packed.seg_tile_offsets), n, max_tiles, L, _p(Wk), _p(bk), K,
+                                              _p(Y), _p(c), float(alpha), float(eps), float(loss_scale), _p(out["M"]),
+                                              _p(out["ml"]), _p(out["hazards"]), _p(out["S"]), _p(out["Y_hat"]),
+                                              _p(out["loss"]), _p(out["dM"]), _p(dWk), _p(dbk), _stream()),
+          "mmf_amil_window_head_nll_step")
+    g = AmilGrads(_p(grads["dW1"]), _p(grads["db1"]), _p(grads["dWab"]), _p(grads["dbab"]), _p(grads["dwc"]), _p(grads["dbc"]))
+    check(lib().mmf_amil_window_bwd(_p(x), R, x.stride(0), C.byref(wst), w.L, w.D, flags | MMF_STASHED, seed, _p(A_raw),
+                                    _p(out["ml"]), _p(out["M"]), _p(out["dM"]), _p(packed.tile_bag), _p(packed.tile_valid_even),
+                                    C.byref(g), ws.data_ptr(), ws.numel(), _stream()), "mmf_amil_window_bwd")
+    return out
 
 
 def nll_surv(hazards, S, Y, c, alpha: float, eps: float = 1e-7):

@@ -1,0 +1,83 @@
+"""GPU parity of the varlen-packed TRAINING window (mmf_amil_window_fwd_train / _head_nll_step / _bwd;
+MIL_Attention_fc_surv_path.fused_window_step): the `gc` bags of a gradient-accumulation window in one launch set == the
+reference's loop over the bags (utils/core_utils.py:242-247: loss / gc, backward per bag), here the batch-1 fused_step
+accumulating over the same bags — per-bag hazards / loss / attention scores and the window's summed gradients."""
+import pytest
+import torch
+
+from helpers import rel_err
+from oracle import cases
+
+pytestmark = pytest.mark.gpu
+
+
+def _score_bias(name, model):
+    """The bias of the attention score layer (attention_c.bias / the last Linear of the un-gated Attn_Net)."""
+    bc = model.attention_net_WSI[3].amil_weights()[5]
+    return dict(model.named_parameters())[name] is bc
+
+
+def _model(size, gate, dev, train):
+    from multimodalfusion_b200.models import MIL_Attention_fc_surv_path
+    torch.manual_seed(17)
+    m = MIL_Attention_fc_surv_path(gate_path=gate, model_size_wsi=size, dropout=True, n_classes=4).to(dev)
+    cases.perturb_biases(m, 3)
+    m.train(train)
+    m.enable_fused_step()
+    return m
+
+
+@pytest.mark.parametrize("size,gate,sizes", [
+    ("small", True, [1, 127, 300, 129, 700, 128]), ("big", True, [155, 80, 96]), ("small", False, [64, 2000]),
+    ("big", True, [4200, 5000, 4100])])      # (all above 4096 rows: plain bf16 fc in the window AND in the batch-1 steps)
+def test_window_step_equals_loop_over_bags(size, gate, sizes):
+    dev = torch.device("cuda")
+    model = _model(size, gate, dev, train=False)
+    bags = [cases.features(n, 700 + i).to(dev).to(torch.bfloat16) for i, n in enumerate(sizes)]
+    gc = len(bags)
+    Y = torch.tensor([i % 4 for i in range(gc)], device=dev)
+    c = torch.tensor([float(i % 2) for i in range(gc)], device=dev)
+    per = []
+    for i, b in enumerate(bags):
+        hz, S, Yh, A, loss = model.fused_step(path_features=b, Y=Y[i:i + 1], c=c[i:i + 1], alpha=0.15, loss_scale=1.0 / gc,
+                                              accumulate=i > 0)
+        per.append((hz.clone(), S.clone(), Yh.clone(), A.clone(), loss.clone()))
+    ref = {n: p.grad.clone() for n, p in model.named_parameters()}
+    hz, S, Yh, A, loss = model.fused_window_step(bags, Y, c, alpha=0.15)
+    assert hz.shape == (gc, 4) and loss.shape == (gc,)
+    for i in range(gc):
+        assert rel_err(hz[i], per[i][0]) < 2e-4 and rel_err(S[i], per[i][1]) < 2e-4, i
+        assert Yh[i].item() == per[i][2].item()
+        assert A[i].shape == (1, sizes[i]) and rel_err(A[i], per[i][3]) < 2e-4, i
+        assert abs(loss[i].item() - per[i][4].item()) < 2e-4 * max(1.0, abs(per[i][4].item())), i
+    for n, p in model.named_parameters():
+        if _score_bias(n, model):
+            continue      # sum_i ds_i: exactly 0 in exact arithmetic, rounding residue on both sides
+        assert rel_err(p.grad, ref[n]) < 8e-3, n
+    # the window call without accumulate replaces, with accumulate adds
+    model.fused_window_step(bags, Y, c, alpha=0.15, accumulate=True)
+    for n, p in model.named_parameters():
+        if not _score_bias(n, model):
+            assert rel_err(p.grad, 2 * ref[n]) < 8e-3, n
+
+
+def test_window_of_one_bag_in_train_mode_equals_fused_step(monkeypatch):
+    """Train-mode dropout: a window of ONE bag draws the masks of the batch-1 step under the same seed (rows coincide)."""
+    from multimodalfusion_b200.models import _fused_step, model_modules
+    dev = torch.device("cuda")
+    model = _model("small", True, dev, train=True)
+    monkeypatch.setattr(_fused_step, "_seed_from_torch", lambda: 987654321)
+    monkeypatch.setattr(model_modules, "_seed_from_torch", lambda: 987654321)
+    bag = cases.features(333, 5).to(dev).to(torch.bfloat16)
+    Y, c = torch.tensor([2], device=dev), torch.tensor([0.0], device=dev)
+    hz, S, Yh, A, loss = [t.clone() for t in model.fused_step(path_features=bag, Y=Y, c=c, alpha=0.0)]
+    ref = {n: p.grad.clone() for n, p in model.named_parameters()}
+    hz2, S2, Yh2, A2, loss2 = model.fused_window_step([bag], Y, c, alpha=0.0)
+    assert rel_err(hz2[0], hz) < 2e-4 and rel_err(A2[0], A) < 2e-4 and abs(loss2[0].item() - loss.item()) < 2e-4 * max(1, abs(loss.item()))
+    for n, p in model.named_parameters():
+        if not _score_bias(n, model):
+            assert rel_err(p.grad, ref[n]) < 8e-3, n
+    # and the masks matter: another seed gives other hazards
+    monkeypatch.setattr(model_modules, "_seed_from_torch", lambda: 123)
+    hz3 = model.fused_window_step([bag], Y, c, alpha=0.0)[0]
+    assert rel_err(hz3[0], hz) > 1e-4
