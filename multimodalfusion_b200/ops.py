@@ -186,8 +186,13 @@ class PackedBags:
     tile_valid_even: Optional[torch.Tensor] = None   # tile_valid padded likewise (pad tile: 0 rows)
 
 
+_PAD_ROWS = {}     # (device, dtype) -> [127, 1024] zeros: the padding rows of pack_bags are views of it
+
+
 def pack_bags(bags: Sequence[torch.Tensor]) -> PackedBags:
-    """Packs CUDA feature bags ([N_i,1024], fp32 or bf16) into the varlen layout of mmf_amil_infer_varlen."""
+    """Packs CUDA feature bags ([N_i,1024], fp32 or bf16) into the varlen layout of mmf_amil_infer_varlen / the training
+    window: ONE concatenation launch (bags interleaved with views of a zero block; + one cast for fp32 bags) and ONE
+    host-to-device copy of the four index arrays."""
     _require_cuda(*bags)
     sizes = [int(b.shape[0]) for b in bags]
     if min(sizes) < 1:
@@ -198,21 +203,39 @@ def pack_bags(bags: Sequence[torch.Tensor]) -> PackedBags:
         seg.append(seg[-1] + t)
     R = seg[-1] * TILE_ROWS
     dev = bags[0].device
-    x = torch.zeros(R, IN_FEATURES, dtype=torch.bfloat16, device=dev)
-    row_off = []
-    for b, t0, n in zip(bags, seg, sizes):
-        row_off.append(t0 * TILE_ROWS)
-        x[t0 * TILE_ROWS:t0 * TILE_ROWS + n].copy_(b)       # casts fp32 -> bf16 (RNE) on the fly
-    tv = torch.full((seg[-1],), TILE_ROWS, dtype=torch.int32)
-    for t0, t, n in zip(seg, tiles, sizes):
+    row_off = [t0 * TILE_ROWS for t0 in seg[:-1]]
+    if len({b.dtype for b in bags}) == 1 and all(b.dim() == 2 and b.shape[1] == IN_FEATURES for b in bags):
+        key = (dev, bags[0].dtype)
+        pad = _PAD_ROWS.get(key)
+        if pad is None:
+            pad = _PAD_ROWS[key] = torch.zeros(TILE_ROWS - 1, IN_FEATURES, dtype=bags[0].dtype, device=dev)
+        pieces = []
+        for b, t, n in zip(bags, tiles, sizes):
+            pieces.append(b)
+            if t * TILE_ROWS > n:
+                pieces.append(pad[:t * TILE_ROWS - n])
+        x = torch.cat(pieces, dim=0)
+        if x.dtype != torch.bfloat16:
+            x = to_bf16(x)                                   # fp32 -> bf16 (RNE), the library's cast kernel
+    else:
+        x = torch.zeros(R, IN_FEATURES, dtype=torch.bfloat16, device=dev)
+        for b, r0, n in zip(bags, row_off, sizes):
+            x[r0:r0 + n].copy_(b)       # casts fp32 -> bf16 (RNE) on the fly
+    n_tiles = seg[-1]
+    n_even = n_tiles + (n_tiles & 1)
+    nb = len(sizes)
+    host = torch.zeros(n_tiles + (nb + 1) + 2 * n_even, dtype=torch.int32)
+    tv, sg = host[:n_tiles], host[n_tiles:n_tiles + nb + 1]
+    tb, tve = host[n_tiles + nb + 1:n_tiles + nb + 1 + n_even], host[n_tiles + nb + 1 + n_even:]
+    tv.fill_(TILE_ROWS)
+    sg.copy_(torch.tensor(seg, dtype=torch.int32))
+    for i, (t0, t, n) in enumerate(zip(seg, tiles, sizes)):
         tv[t0 + t - 1] = n - (t - 1) * TILE_ROWS
-    n_even = seg[-1] + (seg[-1] & 1)
-    tb = torch.zeros(n_even, dtype=torch.int32)
-    tve = torch.zeros(n_even, dtype=torch.int32)
-    tve[:seg[-1]] = tv
-    for i, (t0, t) in enumerate(zip(seg, tiles)):
         tb[t0:t0 + t] = i
-    return PackedBags(x, tv.to(dev), torch.tensor(seg, dtype=torch.int32, device=dev), row_off, sizes, tb.to(dev), tve.to(dev))
+    tve[:n_tiles] = tv
+    d = host.to(dev)
+    o1, o2, o3 = n_tiles, n_tiles + nb + 1, n_tiles + nb + 1 + n_even
+    return PackedBags(x, d[:o1], d[o1:o2], row_off, sizes, d[o2:o3], d[o3:])
 
 
 def amil_infer_varlen(packed: PackedBags, w: AmilPrepared, Wk: torch.Tensor, bk: torch.Tensor):
