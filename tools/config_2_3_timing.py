@@ -86,8 +86,8 @@ print(json.dumps({"config": "2 radio_attention_mil batch-1 training loop, graphe
                   "launches_per_patient_from_python": 4,
                   "note": "fused_step + fused Adam per patient as one CUDA-graph launch per slice count (device-resident Adam step "
                           "count and dropout seeds), + 1 stack and 2 small copies into the static inputs; wall clock incl. host"}))
-# ---- config 3
-B = 512
+# ---- config 3 (COHORT=32: the batch size of the reference's own command, commands/commands.sh:69-72 `--batch_size 32`)
+B = int(os.environ.get("COHORT", 512))
 head = cox_heads.multimodal_pretrained(mode="radio_path_omic", train_type="kronecker", n_classes=4).to(dev).train()
 opt3 = get_optim(head, args)
 emb = [torch.randn(B, 256, device=dev) for _ in range(3)]
@@ -108,7 +108,7 @@ for name, lf in (("cox", CoxSurvLoss()), ("ranking", RankingSurvLoss())):
     for _ in range(20):
         l = it()
     torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 20
-    print(json.dumps({"config": f"3 multimodal kronecker head + {name} loss, B=512 cohort", "ms_per_step": dt * 1e3,
+    print(json.dumps({"config": f"3 multimodal kronecker head + {name} loss, B={B} cohort", "ms_per_step": dt * 1e3,
                       "patients_per_s": B / dt, "loss": l.item(),
                       "note": "fwd + loss + bwd + fused Adam, eager, wall clock; the reference's Cox / ranking host loops alone take 2.5 s / 7.2 s at B=512 (SURVEY.md)"}))
 
@@ -122,6 +122,6 @@ for name, lf in (("cox", CoxSurvLoss()), ("ranking", RankingSurvLoss())):
     for _ in range(50):
         l = graphed()
     torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 50
-    print(json.dumps({"config": f"3 multimodal kronecker head + {name} loss, B=512 cohort, CUDA-graph replay", "ms_per_step": dt * 1e3,
+    print(json.dumps({"config": f"3 multimodal kronecker head + {name} loss, B={B} cohort, CUDA-graph replay", "ms_per_step": dt * 1e3,
                       "patients_per_s": B / dt, "loss": l.item(),
                       "note": "GraphedStep(fwd + loss + bwd + fused Adam): one graph launch per cohort step, wall clock"}))
