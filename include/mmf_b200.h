@@ -276,7 +276,8 @@ int mmf_amil_bwd_wgrad(const void* x, int64_t N, int64_t ldx, const MmfAmilWeigh
  *   mmf_amil_window_head_nll_step  per bag (grid.y): combine, classifier, hazards, nll_surv, loss_scale * its gradient ->
  *                                  M / dM [bags, L], ml [bags, 2], hazards / S [bags, K], loss [bags]; dWk / dbk += (atomic)
  *   mmf_amil_window_bwd            gate + hidden backward with per-tile bag statistics, then the grouped weight gradients:
- *                                  the window's summed gradients accumulate into g (MMF_STASHED required; no dx)
+ *                                  the window's summed gradients accumulate into g (MMF_STASHED required); with
+ *                                  MMF_NEED_DX also dx = dU W1 (bf16 [R, 1024]; zero on padding rows) for an upstream layer
  * R is a multiple of 128; workspace as mmf_amil_bwd_workspace_bytes(R, ...). */
 int mmf_amil_window_fwd_train(const void* x, int64_t R, int64_t ldx, const MmfAmilWeights* w, int L, int D, int flags,
                               uint64_t seed, const int32_t* tile_valid, float* A_raw, float* partials, void* workspace,
@@ -287,8 +288,8 @@ int mmf_amil_window_head_nll_step(const float* partials, const int32_t* seg_tile
                                   int64_t* Y_hat, float* loss, float* dM, float* dWk, float* dbk, void* stream);
 int mmf_amil_window_bwd(const void* x, int64_t R, int64_t ldx, const MmfAmilWeights* w, int L, int D, int flags,
                         uint64_t seed, const float* A_raw, const float* ml, const float* M, const float* dM,
-                        const int32_t* tile_bag, const int32_t* tile_valid, const MmfAmilGrads* g, void* workspace,
-                        size_t workspace_bytes, void* stream);
+                        const int32_t* tile_bag, const int32_t* tile_valid, const MmfAmilGrads* g, void* dx,
+                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* Dense bf16 tensor-core GEMM used either side of the AMIL core (radio reduce_dim and its
  * gradients): C[M,N] = A[M,K] B[N,K]^T + bias (A given as up to 4 K-segments = the modality

@@ -155,7 +155,7 @@ SIGNATURES = {
     "mmf_amil_window_head_nll_step": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _f, _f, _f, _vp, _vp, _vp, _vp, _vp,
                                            _vp, _vp, _vp, _vp, _vp]),
     "mmf_amil_window_bwd": (_i, [_vp, _i64, _i64, C.POINTER(AmilWeights), _i, _i, _i, _u64, _vp, _vp, _vp, _vp, _vp, _vp,
-                                 C.POINTER(AmilGrads), _vp, _sz, _vp]),
+                                 C.POINTER(AmilGrads), _vp, _vp, _sz, _vp]),
     "mmf_linear_bf16": (_i, [_PP, _i, _i64, _i, _i64, _vp, _vp, _i, _vp, _vp, _i64, _vp]),
     "mmf_linear_bf16_wgrad_workspace_bytes": (_sz, [_i64, _i]),
     "mmf_linear_bf16_wgrad": (_i, [_vp, _i64, _i, _i64, _PP, _i, _i, _i64, _vp, _vp, _vp, _sz, _vp]),

@@ -687,14 +687,14 @@ int mmf_amil_window_head_nll_step(const float* partials, const int32_t* seg_tile
 
 int mmf_amil_window_bwd(const void* x, int64_t R, int64_t ldx, const MmfAmilWeights* w, int L, int D, int flags,
                         uint64_t seed, const float* A_raw, const float* ml, const float* M, const float* dM,
-                        const int32_t* tile_bag, const int32_t* tile_valid, const MmfAmilGrads* g, void* workspace,
-                        size_t workspace_bytes, void* stream) {
+                        const int32_t* tile_bag, const int32_t* tile_valid, const MmfAmilGrads* g, void* dx,
+                        void* workspace, size_t workspace_bytes, void* stream) {
   if (!g || !g->dW1 || !g->db1 || !g->dWab || !g->dbab || !g->dwc || !g->dbc || !tile_bag || !tile_valid) return MMF_E_INVALID;
-  if (!(flags & MMF_STASHED) || (flags & MMF_NEED_DX)) return MMF_E_UNSUPPORTED;
+  if (!(flags & MMF_STASHED)) return MMF_E_UNSUPPORTED;
   MMF_TRY(check_amil_common(x, R, ldx, w, L, D));
   MMF_TRY(bwd_gate_hidden_stashed_impl(R, w, L, D, flags, seed, A_raw, ml, M, dM, nullptr, g, workspace, workspace_bytes,
                                        nullptr, nullptr, stream, tile_bag, tile_valid));
-  return mmf_amil_bwd_wgrad(x, R, ldx, w, L, D, flags, g, nullptr, workspace, workspace_bytes, stream);
+  return mmf_amil_bwd_wgrad(x, R, ldx, w, L, D, flags, g, dx, workspace, workspace_bytes, stream);
 }
 
 int mmf_linear_bf16(const void* const* A_segs, int n_segs, int64_t M, int K_per_seg, int64_t lda,

@@ -189,8 +189,9 @@ class PackedBags:
 _PAD_ROWS = {}     # (device, dtype) -> [127, 1024] zeros: the padding rows of pack_bags are views of it
 
 
-def pack_bags(bags: Sequence[torch.Tensor]) -> PackedBags:
-    """Packs CUDA feature bags ([N_i,1024], fp32 or bf16) into the varlen layout of mmf_amil_infer_varlen / the training
+def pack_bags(bags: Sequence[torch.Tensor], index_from: Optional[PackedBags] = None) -> PackedBags:
+    """(index_from: reuse the index arrays of a PackedBags of the same bag sizes — another modality of the same patients.)
+    Packs CUDA feature bags ([N_i,1024], fp32 or bf16) into the varlen layout of mmf_amil_infer_varlen / the training
     window: ONE concatenation launch (bags interleaved with views of a zero block; + one cast for fp32 bags) and ONE
     host-to-device copy of the four index arrays."""
     _require_cuda(*bags)
@@ -221,6 +222,11 @@ def pack_bags(bags: Sequence[torch.Tensor]) -> PackedBags:
         x = torch.zeros(R, IN_FEATURES, dtype=torch.bfloat16, device=dev)
         for b, r0, n in zip(bags, row_off, sizes):
             x[r0:r0 + n].copy_(b)       # casts fp32 -> bf16 (RNE) on the fly
+    if index_from is not None:
+        if index_from.sizes != sizes:
+            raise ValueError("index_from was packed from bags of other sizes")
+        return PackedBags(x, index_from.tile_valid, index_from.seg_tile_offsets, row_off, sizes, index_from.tile_bag,
+                          index_from.tile_valid_even)
     n_tiles = seg[-1]
     n_even = n_tiles + (n_tiles & 1)
     nb = len(sizes)
@@ -641,7 +647,8 @@ def amil_fused_step(x: torch.Tensor, w: AmilPrepared, flags: int, seed: int, buf
 
 
 def amil_window_step(packed: PackedBags, w: AmilPrepared, flags: int, seed: int, Wk, bk, Y, c, alpha: float, grads: dict,
-                     dWk=None, dbk=None, eps: float = 1e-7, loss_scale: float = 1.0, zero: Optional[torch.Tensor] = None):
+                     dWk=None, dbk=None, eps: float = 1e-7, loss_scale: float = 1.0, zero: Optional[torch.Tensor] = None,
+                     need_dx: bool = False):
     """fwd + nll_surv + bwd of a WINDOW of bags (the `gc` bags between two optimizer steps, utils/core_utils.py:242-247) in
     one launch set: fused forward of every tile of the packed buffer, one head launch (a cluster per bag), gate + hidden
     backward with per-tile bag statistics, grouped weight gradients. The window's summed gradients (each bag's loss scaled
@@ -650,10 +657,11 @@ def amil_window_step(packed: PackedBags, w: AmilPrepared, flags: int, seed: int,
     hazards, S [n,K], Y_hat [n,1], M [n,L], A_raw [R] (index with packed.row_offsets / sizes))."""
     _require_cuda(packed.x, Wk)
     n, R, dev = len(packed.sizes), packed.x.shape[0], packed.x.device
-    x = packed.x
     if max(packed.sizes) <= PRECISE_FC_MAX_ROWS:
-        x = split_bag(packed.x)
+        x = split_bag(packed.x)                 # (packed.x may be an fp32 bag: the output of an upstream layer)
         flags |= MMF_PRECISE_FC
+    else:
+        x = to_bf16(packed.x)
     _check_bag(x, flags)
     K, L = Wk.shape[0], w.L
     Wk, bk = _f32c(Wk), _f32c(bk)
@@ -679,9 +687,11 @@ def amil_window_step(packed: PackedBags, w: AmilPrepared, flags: int, seed: int,
                                               _p(out["loss"]), _p(out["dM"]), _p(dWk), _p(dbk), _stream()),
           "mmf_amil_window_head_nll_step")
     g = AmilGrads(_p(grads["dW1"]), _p(grads["db1"]), _p(grads["dWab"]), _p(grads["dbab"]), _p(grads["dwc"]), _p(grads["dbc"]))
-    check(lib().mmf_amil_window_bwd(_p(x), R, x.stride(0), C.byref(wst), w.L, w.D, flags | MMF_STASHED, seed, _p(A_raw),
+    out["dx"] = torch.empty(R, IN_FEATURES, dtype=torch.bfloat16, device=dev) if need_dx else None   # gradient w.r.t. the bag rows
+    check(lib().mmf_amil_window_bwd(_p(x), R, x.stride(0), C.byref(wst), w.L, w.D,
+                                    flags | MMF_STASHED | (MMF_NEED_DX if need_dx else 0), seed, _p(A_raw),
                                     _p(out["ml"]), _p(out["M"]), _p(out["dM"]), _p(packed.tile_bag), _p(packed.tile_valid_even),
-                                    C.byref(g), ws.data_ptr(), ws.numel(), _stream()), "mmf_amil_window_bwd")
+                                    C.byref(g), _p(out["dx"]), ws.data_ptr(), ws.numel(), _stream()), "mmf_amil_window_bwd")
     return out
 
 
