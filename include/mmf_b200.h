@@ -169,7 +169,11 @@ size_t mmf_amil_bwd_workspace_bytes(int64_t N, int L, int D, int flags);
  * zero_buf / zero_count (optional, NULL / 0): an fp32 buffer (16-byte aligned, count a multiple of 4) that the
  * kernel clears while its first GEMM runs — the step's gradient accumulators, i.e. optimizer.zero_grad() fused
  * into the forward (a separate fill costs two kernel boundaries per step). It must not alias anything the
- * forward reads. */
+ * forward reads.
+ * The workspace belongs to ONE step at a time: the training forward treats what the previous step left in it as dead — it
+ * overwrites the stash in place and DISCARDS the L2 lines of the dU slot (discard.global.L2: no write-back of data that the
+ * previous wgrad has consumed and this step's backward rewrites). Do not start a step's forward on a workspace whose
+ * backward is still pending. */
 int mmf_amil_fwd_train(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* w, int L, int D,
                        int flags, uint64_t seed, float* A_raw, float* partials, void* workspace,
                        size_t workspace_bytes, float* zero_buf, int64_t zero_count, void* stream);

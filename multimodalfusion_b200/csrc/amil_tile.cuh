@@ -49,6 +49,10 @@ struct AmilArgs {
                           // multi-bag buffer; null = one bag of N rows
   float4* zero_ptr;   // fwd (optional): buffer the epilogue warps clear while GEMM1 runs ("zero_grad" of the step)
   long long zero_n4;  // its length in float4
+  uint8_t* discard_ptr;    // fwd train (optional): a DEAD region of the workspace (the previous step's dU: read by its wgrad,
+  long long discard_n128;  // rewritten by this step's hidden-gradient kernel) whose dirty L2 lines are dropped, in 128-byte lines
+  uint8_t* h_stash;        // fwd train (optional, MMF_DISCARD_DEAD_STASH): base of the H stash [N, L] bf16 — every CTA drops the
+                           // dead lines of ITS OWN tile's rows of H and [a|g] (it rewrites exactly those rows later)
   uint32_t* mask_out; // fwd train (optional): ReLU mask words [N, L/32], bit j of word w = (h[row][32 w + j] > 0)
   float* z_out;       // fwd train (optional): z_i = Wk h_i as fp32 [N, zld] from the N = 16 side MMA (needs tmWk)
   int zld;            // 4 or 8

@@ -65,6 +65,14 @@ struct Amil2Cfg {
 // 5 / 9 / 15 = "chunk c gate epilogue done" (epilogue thread 0) replace the producer / first-stage / vectors-staged stamps
 // MMF_L2_HINTS (mmf_ptx.cuh): >= 1 evict_first on the x stream (forward and wgrad)
 // MMF_X_BULK_PREFETCH = 1 (A/B candidate): this CTA's x tile requested with one bulk L2 prefetch BEFORE griddepcontrol.wait
+// MMF_DISCARD_DEAD_DU = 1: the training forward drops the dirty L2 lines of the previous step's dU (see EPI1's prologue)
+#ifndef MMF_DISCARD_DEAD_DU
+#define MMF_DISCARD_DEAD_DU 1
+#endif
+// MMF_DISCARD_DEAD_STASH = 1 (A/B candidate): every CTA also drops its own tile's dead H / dG lines before rewriting them
+#ifndef MMF_DISCARD_DEAD_STASH
+#define MMF_DISCARD_DEAD_STASH 0
+#endif
 #ifndef MMF_X_BULK_PREFETCH
 #define MMF_X_BULK_PREFETCH 0
 #endif
@@ -325,6 +333,33 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
            i += (long long)gridDim.x * AMIL2_EPI_THREADS)
         a.zero_ptr[i] = z;
     }
+
+#if MMF_DISCARD_DEAD_DU
+    if (MODE == AMIL_FWD && a.discard_ptr != nullptr) {
+      // The previous step's dU (16 MB at the metric shape) is dead — its wgrad has read it, this step's hidden-gradient
+      // kernel rewrites every line — but its lines sit DIRTY in L2, and while this kernel streams the bag and allocates the
+      // stash they are evicted: 17.5 MB of DRAM write-backs of data nobody will read, inside the forward
+      // (profiles/r02d_ncu_step_summary.md §2). discard.global.L2 drops the lines without a write-back.
+      for (long long i = (long long)blockIdx.x * AMIL2_EPI_THREADS + e; i < a.discard_n128;
+           i += (long long)gridDim.x * AMIL2_EPI_THREADS)
+        asm volatile("discard.global.L2 [%0], 128;" ::"l"(a.discard_ptr + i * 128) : "memory");
+    }
+#endif
+#if MMF_DISCARD_DEAD_STASH
+    if (MODE == AMIL_FWD && a.h_stash != nullptr && a.AG != nullptr && valid > 0) {
+      // the previous step's H and dG rows of THIS tile (dead; this CTA rewrites exactly these rows at its end)
+      const long long rows = min((long long)128, a.N - row0);
+      uint8_t* hb = a.h_stash + row0 * (L * 2);
+      for (long long i = e; i < rows * (L * 2 / 128); i += AMIL2_EPI_THREADS)
+        asm volatile("discard.global.L2 [%0], 128;" ::"l"(hb + i * 128) : "memory");
+      uint8_t* gb = reinterpret_cast<uint8_t*>(a.AG) + row0 * (a.ldag * 2);
+      for (long long i = e; i < rows * (a.ldag * 2 / 128); i += AMIL2_EPI_THREADS)
+        asm volatile("discard.global.L2 [%0], 128;" ::"l"(gb + i * 128) : "memory");
+      // (these lines are rewritten later in this kernel by TMA stores = the async proxy: order the generic-proxy discards
+      //  before them; the stores are issued behind several CTA barriers by other warps)
+      asm volatile("fence.proxy.async;" ::: "memory");
+    }
+#endif
 
     // ---------------- EPI1: H = dropout(relu(U + b1)) -> swizzled smem -----------------
     constexpr int PIECES1 = L / 64;  // 32-column pieces per half

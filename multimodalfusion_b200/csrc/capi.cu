@@ -382,6 +382,9 @@ int fwd_train_impl(const void* x, int64_t N, int64_t ldx, const MmfAmilWeights* 
   a.A_raw = A_raw; a.partials = partials; a.store_h = 1; a.tile_valid = tile_valid;
   a.AG = reinterpret_cast<uint16_t*>(ws + lay.off_dG); a.ldag = gated ? 2 * D : D;
   a.mask_out = reinterpret_cast<uint32_t*>(ws + lay.off_mask);
+  // (the dU slot of the workspace: dead between the previous step's wgrad and this step's hidden-gradient kernel)
+  a.discard_ptr = ws + lay.off_dU; a.discard_n128 = (long long)N * L * 2 / 128;
+  a.h_stash = ws + lay.off_H;
   if (zero_buf) {
     if ((reinterpret_cast<uintptr_t>(zero_buf) & 15u) || zero_count < 0 || (zero_count & 3)) return MMF_E_ALIGN;
     a.zero_ptr = reinterpret_cast<float4*>(zero_buf); a.zero_n4 = zero_count >> 2;
