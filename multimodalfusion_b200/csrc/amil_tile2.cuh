@@ -69,7 +69,14 @@ struct Amil2Cfg {
 #ifndef MMF_DISCARD_DEAD_DU
 #define MMF_DISCARD_DEAD_DU 1
 #endif
-// MMF_DISCARD_DEAD_STASH = 1 (A/B candidate): every CTA also drops its own tile's dead H / dG lines before rewriting them
+// MMF_DISCARD_DEAD_STASH: every CTA also drops its own tile's dead H / dG lines (the previous step's) before rewriting them.
+//   1: from the epilogue warps' idle window next to the dU discard — 2560 more CCTL per CTA overflow the window into EPI1:
+//      SLOWER (91.5 -> 93.2 us per step, profiles/r02_ab_discard_stash.txt);
+//   2: from the 32 otherwise idle lanes of warp 3 through the whole GEMM1 + EPI1 phase: 90.85 -> 90.4 us per step in three
+//      interleaved A/B pairs on one box (profiles/r02_ab_discard_stash2.txt) — but the forward timed ALONE (bench.py's
+//      roofline stage: the same workspace re-written launch after launch) slows from 35.2 to 36.6 us, the discarded lines
+//      being re-allocated by the stash stores; 0 (default): off. A 0.5 % step gain is not worth a forward kernel that is
+//      slower in isolation.
 #ifndef MMF_DISCARD_DEAD_STASH
 #define MMF_DISCARD_DEAD_STASH 0
 #endif
@@ -277,7 +284,28 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       umma_commit_pair_mc(smem_u32(&bar_acc2_full[buf]), 3);
     }
     MMF_STAMP(a, 8);
-  } else if (MODE == AMIL_FWD && warp == 3 && lane == 0) {
+  } else if (MODE == AMIL_FWD && warp == 3 && (lane == 0 || (MMF_DISCARD_DEAD_STASH == 2 && a.AG != nullptr))) {
+#if MMF_DISCARD_DEAD_STASH == 2
+    if (a.h_stash != nullptr && a.AG != nullptr) {
+      // the otherwise idle lanes of this warp drop the dead lines of THIS tile's H / dG rows (the previous
+      // step's; this CTA rewrites exactly these rows) while GEMM1 and EPI1 run. Order: generic-proxy discards, proxy
+      // fence, then (a) this warp's own H stores in program order and (b) the epilogue warps' [a|g] stores behind named
+      // barrier 5 (they wait on it once, before their first stash store).
+      if (row0 < a.N) {
+        const long long rows = min((long long)128, a.N - row0);
+        uint8_t* hb = a.h_stash + row0 * (L * 2);
+        for (long long i = lane; i < rows * (L * 2 / 128); i += 32)
+          asm volatile("discard.global.L2 [%0], 128;" ::"l"(hb + i * 128) : "memory");
+        uint8_t* gb = reinterpret_cast<uint8_t*>(a.AG) + row0 * (a.ldag * 2);
+        for (long long i = lane; i < rows * (a.ldag * 2 / 128); i += 32)
+          asm volatile("discard.global.L2 [%0], 128;" ::"l"(gb + i * 128) : "memory");
+      }
+      asm volatile("fence.proxy.async;" ::: "memory");
+      __syncwarp();
+      named_bar_arrive(5, AMIL2_EPI_THREADS + 32);
+    }
+    if (lane == 0)
+#endif
     // =============================== H stash store (training forward, each CTA) =========
     // Issued in NCH batches, batch c once GEMM2 chunk c has retired: the 128 KB read of the H tile then shares the
     // shared-memory / TMA pipes with chunks 1.. (hidden behind the gate epilogue) and the pooling tail. Issued right after
@@ -345,7 +373,7 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         asm volatile("discard.global.L2 [%0], 128;" ::"l"(a.discard_ptr + i * 128) : "memory");
     }
 #endif
-#if MMF_DISCARD_DEAD_STASH
+#if MMF_DISCARD_DEAD_STASH == 1
     if (MODE == AMIL_FWD && a.h_stash != nullptr && a.AG != nullptr && valid > 0) {
       // the previous step's H and dG rows of THIS tile (dead; this CTA rewrites exactly these rows at its end)
       const long long rows = min((long long)128, a.N - row0);
@@ -539,6 +567,9 @@ amil_tile2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           // no st.global in the epilogue warps, and the cluster-scope release arrive that ends the chunk has no generic-proxy
           // global stores to drain. The staging is reused one piece (~500 instructions) later: the read-completion wait is free.
           const uint32_t scratch = pool + C::POOL - C::XPOSE_BYTES + (warp - 4) * C::XPOSE_WARP;
+#if MMF_DISCARD_DEAD_STASH == 2
+          if (c == 0 && pp == 0 && a.h_stash != nullptr) named_bar_sync(5, AMIL2_EPI_THREADS + 32);   // warp 3's discards are fenced
+#endif
           if (lane == 0) tma_store_wait_read();
           __syncwarp();
 #pragma unroll
